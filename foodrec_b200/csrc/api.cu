@@ -1,0 +1,457 @@
+// C ABI of libfoodrec_b200.so (see include/foodrec_b200.h): context, workspace and the
+// orchestration of one training step.  No compute happens on the host; there is no CPU
+// fallback -- every entry point fails with FR_ERR_CUDA if the device is unusable.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "train.cuh"
+
+using namespace fr;
+
+struct fr_ctx {
+  fr_config cfg{};
+  fr_tables tab{};
+  bool has_tables = false;
+  ModelConsts mc{};
+  int NV = 1, sm_count = 148, device = 0;
+  int64_t step = 0;
+  float b1p = 0.f, b2p = 0.f;
+  char err[512] = {0};
+  std::vector<void*> allocs;
+
+  // workspace (device)
+  uint32_t* ukeys = nullptr; float* ws_row = nullptr; float* g = nullptr; float* scores = nullptr;
+  float4* z = nullptr;
+  SortBufs sortU, sortI, sortL;
+  float *part_loss = nullptr, *part_nrm = nullptr; float4* part_gcat = nullptr; int fwd_grid_cap = 0;
+  float* packed = nullptr;
+  float4 *pieces_u = nullptr, *pieces_i = nullptr, *pieces_g = nullptr, *pieces_personal = nullptr;
+  size_t pieces_personal_chunks = 0;
+  uint32_t *counts = nullptr, *offs = nullptr, *ent_key = nullptr, *ent_row = nullptr, *n_entries = nullptr;
+  float* ent_coef = nullptr;
+  uint32_t* counters = nullptr;
+  float4* cat_pre = nullptr;
+  float* lr_hist = nullptr; int64_t lr_hist_cap = 0;
+  double* mean_partials = nullptr;
+  float* out_internal = nullptr;
+  uint32_t* scan_tmp = nullptr;
+  // staging for fr_train_step_host
+  void* stage = nullptr; size_t stage_bytes = 0;
+};
+
+static int fail(fr_ctx* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+#define FR_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail(h, FR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define FR_CHECK_LAUNCH(h) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+  return fail(h, FR_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+template <class T>
+static int dalloc(fr_ctx* h, T** p, size_t count) {
+  void* q = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) return fail(h, FR_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return FR_OK;
+}
+
+static int bits_for(int64_t n) {  // bits needed to represent ids in [0, n)
+  int b = 0;
+  while (b < 32 && ((int64_t)1 << b) < n) ++b;
+  return b < 1 ? 1 : b;
+}
+
+static int alloc_sort(fr_ctx* h, SortBufs& s, size_t cap) {
+  s.cap = (int)cap;
+  for (int i = 0; i < 2; ++i) {
+    int rc = dalloc(h, &s.k[i], cap); if (rc) return rc;
+    rc = dalloc(h, &s.v[i], cap); if (rc) return rc;
+  }
+  const size_t ntiles = (cap + SORT_TILE - 1) / SORT_TILE;
+  int rc = dalloc(h, &s.tile_hist, RADIX_BINS * ntiles + 1); if (rc) return rc;
+  return dalloc(h, &s.scan_tmp, (RADIX_BINS * ntiles) / 4096 + 2);
+}
+
+extern "C" int fr_abi_version(void) { return FR_ABI_VERSION; }
+
+extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
+  if (!cfg || !out) return FR_ERR_ARG;
+  *out = nullptr;
+  fr_ctx* h = new fr_ctx();
+  *out = h;   // returned even on failure so fr_last_error works; caller must fr_destroy
+  h->cfg = *cfg;
+  const int D = cfg->embed_size;
+  if (D <= 0 || D % 4 != 0 || D > 256) return fail(h, FR_ERR_ARG, "embed_size must be a multiple of 4 in (0,256], got %d", D);
+  if (cfg->num_users <= 0 || cfg->num_items <= 0 || cfg->num_labels <= 0 || cfg->max_rows <= 0)
+    return fail(h, FR_ERR_ARG, "num_users/num_items/num_labels/max_rows must be positive");
+  if (cfg->learner < FR_SGD || cfg->learner > FR_ADAM) return fail(h, FR_ERR_ARG, "bad learner %d", cfg->learner);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, FR_ERR_CUDA, "no CUDA device (%s); foodrec_b200 has no CPU fallback", cudaGetErrorString(e));
+  FR_CUDA(h, cudaGetDevice(&h->device));
+  cudaDeviceProp prop;
+  FR_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  h->mc.D = D; h->mc.DV = D / 4; h->mc.L = cfg->num_labels;
+  h->mc.a = cfg->high_level_score_coefficient;
+  h->mc.oma = 1.0f - cfg->high_level_score_coefficient;     // fp32 (1 - a), Model_Recommender.py:96
+  h->mc.beta_1 = cfg->beta_1; h->mc.beta_2 = cfg->beta_2; h->mc.alpha = cfg->alpha;
+  h->NV = h->mc.DV <= 32 ? 1 : 2;
+  h->b1p = cfg->adam_beta1; h->b2p = cfg->adam_beta2;
+
+  const size_t S = (size_t)cfg->max_rows, E = (size_t)(cfg->max_label_entries > 0 ? cfg->max_label_entries : 1);
+  const size_t DV = h->mc.DV;
+  int rc;
+#define A(p, n) if ((rc = dalloc(h, &(p), (n)))) return rc
+  A(h->ukeys, S); A(h->ws_row, S); A(h->g, S); A(h->scores, S); A(h->z, S * DV);
+  if ((rc = alloc_sort(h, h->sortU, S))) return rc;
+  if ((rc = alloc_sort(h, h->sortI, S))) return rc;
+  if ((rc = alloc_sort(h, h->sortL, E))) return rc;
+  h->fwd_grid_cap = h->sm_count * 4;
+  A(h->part_loss, h->fwd_grid_cap); A(h->part_nrm, h->fwd_grid_cap); A(h->part_gcat, (size_t)h->fwd_grid_cap * 4 * DV);
+  A(h->packed, 4 + 4 * (size_t)D);
+  const size_t chS = S / 32 + 2, chE = E / 32 + 2;
+  A(h->pieces_u, chS * 2 * 5 * DV); A(h->pieces_i, chS * 2 * DV); A(h->pieces_g, chE * 2 * 5 * DV);
+  A(h->counts, S + 1); A(h->offs, S + 1); A(h->ent_key, E); A(h->ent_row, E); A(h->ent_coef, E); A(h->n_entries, 1);
+  A(h->counters, 4); A(h->cat_pre, 4 * DV); A(h->mean_partials, 1024); A(h->out_internal, FR_OUT_COUNT);
+  A(h->scan_tmp, S / 4096 + 2);
+  h->lr_hist_cap = 1 << 16;
+  A(h->lr_hist, (size_t)h->lr_hist_cap);
+#undef A
+  FR_CUDA(h, cudaMemset(h->lr_hist, 0, (size_t)h->lr_hist_cap * sizeof(float)));
+  FR_CUDA(h, cudaMemset(h->out_internal, 0, FR_OUT_COUNT * sizeof(float)));
+  return FR_OK;
+}
+
+extern "C" int fr_destroy(fr_handle h) {
+  if (!h) return FR_OK;
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->stage) cudaFree(h->stage);
+  if (h->pieces_personal) cudaFree(h->pieces_personal);
+  delete h;
+  return FR_OK;
+}
+
+extern "C" const char* fr_last_error(fr_handle h) { return h ? h->err : "null handle"; }
+
+extern "C" int fr_set_tables(fr_handle h, const fr_tables* t) {
+  if (!h || !t) return FR_ERR_ARG;
+  if (!t->P || !t->R || !t->Cat || !t->G) return fail(h, FR_ERR_ARG, "P/R/Cat/G must be non-null");
+  const int L = h->cfg.learner;
+  if (L != FR_SGD && (!t->s1_P || !t->s1_R || !t->s1_Cat)) return fail(h, FR_ERR_ARG, "optimizer slot s1 missing");
+  if ((L == FR_ADAM || L == FR_RMSPROP) && (!t->s2_P || !t->s2_R || !t->s2_Cat)) return fail(h, FR_ERR_ARG, "optimizer slot s2 missing");
+  if (L == FR_ADAM && (!t->last_P || !t->last_R)) return fail(h, FR_ERR_ARG, "Adam needs last_P/last_R stamps");
+  const uintptr_t al = (uintptr_t)t->P | (uintptr_t)t->R | (uintptr_t)t->Cat | (uintptr_t)t->G |
+                       (uintptr_t)t->s1_P | (uintptr_t)t->s2_P | (uintptr_t)t->s1_R | (uintptr_t)t->s2_R |
+                       (uintptr_t)t->s1_Cat | (uintptr_t)t->s2_Cat | (uintptr_t)t->item_cats;
+  if (al & 15) return fail(h, FR_ERR_ARG, "table pointers must be 16-byte aligned");
+  h->tab = *t;
+  h->has_tables = true;
+  return FR_OK;
+}
+
+extern "C" int fr_get_step(fr_handle h, int64_t* step) {
+  if (!h || !step) return FR_ERR_ARG;
+  *step = h->step;
+  return FR_OK;
+}
+
+static int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st) {
+  if (need < h->lr_hist_cap) return FR_OK;
+  int64_t cap = h->lr_hist_cap;
+  while (cap <= need) cap *= 2;
+  float* nb = nullptr;
+  FR_CUDA(h, cudaMalloc(&nb, (size_t)cap * sizeof(float)));
+  FR_CUDA(h, cudaMemsetAsync(nb, 0, (size_t)cap * sizeof(float), st));
+  FR_CUDA(h, cudaMemcpyAsync(nb, h->lr_hist, (size_t)h->lr_hist_cap * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  FR_CUDA(h, cudaStreamSynchronize(st));
+  for (auto& p : h->allocs) if (p == h->lr_hist) p = nb;
+  cudaFree(h->lr_hist);
+  h->lr_hist = nb; h->lr_hist_cap = cap;
+  return FR_OK;
+}
+
+static float adam_lr_t(const fr_ctx* h) {   // adam.py: lr * sqrt(1 - beta2_power) / (1 - beta1_power), fp32
+  const float num = h->cfg.lr * sqrtf(1.0f - h->b2p);
+  return num / (1.0f - h->b1p);
+}
+
+extern "C" int fr_set_step(fr_handle h, int64_t step) {
+  if (!h || step < 0) return FR_ERR_ARG;
+  int rc = ensure_lr_hist(h, step + 1, 0); if (rc) return rc;
+  std::vector<float> hist((size_t)step + 1, 0.f);
+  h->b1p = h->cfg.adam_beta1; h->b2p = h->cfg.adam_beta2;
+  for (int64_t t = 1; t <= step; ++t) {
+    hist[(size_t)t] = adam_lr_t(h);
+    h->b1p *= h->cfg.adam_beta1; h->b2p *= h->cfg.adam_beta2;
+  }
+  FR_CUDA(h, cudaMemcpy(h->lr_hist, hist.data(), hist.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->step = step;
+  return FR_OK;
+}
+
+static OptConsts make_oc(const fr_ctx* h, int64_t step) {
+  OptConsts oc{};
+  oc.learner = h->cfg.learner; oc.adam_mode = h->cfg.adam_mode;
+  oc.lr = h->cfg.lr; oc.lr_t = adam_lr_t(h);
+  oc.b1 = h->cfg.adam_beta1; oc.b2 = h->cfg.adam_beta2; oc.eps = h->cfg.adam_eps;
+  oc.omb1 = 1.0f - oc.b1; oc.omb2 = 1.0f - oc.b2;
+  oc.rho = h->cfg.rms_decay; oc.omrho = 1.0f - oc.rho; oc.rms_eps = h->cfg.rms_eps;
+  oc.step = (int)step; oc.lr_hist = h->lr_hist;
+  return oc;
+}
+
+extern "C" int fr_fwd_score(fr_handle h, const int32_t* users, const int32_t* items, const float* cats,
+                            int32_t n, float* scores, fr_stream s) {
+  if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (n < 0 || (n > 0 && (!users || !items || !scores))) return fail(h, FR_ERR_ARG, "null batch pointer");
+  if (!cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cats is NULL and no item_cats table");
+  Launch l{h->sm_count, (cudaStream_t)s};
+  launch_fwd_score(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, items,
+                   (const float4*)(cats ? cats : h->tab.item_cats), cats ? 0 : 1, n, scores, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+extern "C" int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int32_t* cand, const int32_t* n_cand,
+                                    int32_t n_users, int32_t cand_stride, const float* cand_cats, int32_t K,
+                                    int32_t* topk_ids, int32_t* gt_rank, float* scores, fr_stream s) {
+  if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (n_users < 0 || cand_stride <= 0 || cand_stride > 128 || K <= 0) return fail(h, FR_ERR_ARG, "need 0<cand_stride<=128, K>0");
+  if (n_users > 0 && (!users || !cand || !n_cand || !topk_ids || !gt_rank)) return fail(h, FR_ERR_ARG, "null pointer");
+  if (!cand_cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cand_cats is NULL and no item_cats table");
+  Launch l{h->sm_count, (cudaStream_t)s};
+  launch_eval_sampled(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, cand,
+                      n_cand, n_users, cand_stride, (const float4*)cand_cats, (const float4*)h->tab.item_cats, K,
+                      topk_ids, gt_rank, scores, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+extern "C" int fr_sort_pairs(fr_handle h, const uint32_t* keys, int32_t n, int32_t nbits, uint32_t* out_keys,
+                             uint32_t* out_idx, fr_stream s) {
+  if (!h) return FR_ERR_ARG;
+  if (n < 0 || n > h->sortU.cap) return fail(h, FR_ERR_ARG, "n=%d exceeds max_rows=%d", n, h->sortU.cap);
+  if (n == 0) return FR_OK;
+  cudaStream_t st = (cudaStream_t)s;
+  const int r = radix_sort_pairs(h->sortU, keys, (uint32_t)n, nullptr, nbits, st, h->sm_count);
+  FR_CHECK_LAUNCH(h);
+  FR_CUDA(h, cudaMemcpyAsync(out_keys, h->sortU.k[r], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  FR_CUDA(h, cudaMemcpyAsync(out_idx, h->sortU.v[r], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  return FR_OK;
+}
+
+extern "C" int fr_adam_flush(fr_handle h, fr_stream s) {
+  if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (h->cfg.learner != FR_ADAM || h->step == 0) return FR_OK;
+  Launch l{h->sm_count, (cudaStream_t)s};
+  const OptConsts oc = make_oc(h, h->step);
+  launch_adam_sweep((float4*)h->tab.P, (float4*)h->tab.s1_P, (float4*)h->tab.s2_P, h->tab.last_P, h->cfg.num_users,
+                    5 * h->mc.DV, oc, (int)h->step, l);
+  launch_adam_sweep((float4*)h->tab.R, (float4*)h->tab.s1_R, (float4*)h->tab.s2_R, h->tab.last_R, h->cfg.num_items,
+                    h->mc.DV, oc, (int)h->step, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_personal, float* out_scalars,
+                             float* out_scores, fr_stream s) {
+  if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (!b) return fail(h, FR_ERR_ARG, "null batch");
+  if (b->mode != FR_POINTWISE && b->mode != FR_BPR) return fail(h, FR_ERR_ARG, "bad mode %d", b->mode);
+  const int group = b->mode == FR_BPR ? 2 : 1;
+  const int B = b->n_groups;
+  const int64_t S64 = (int64_t)B * group;
+  if (B <= 0) return fail(h, FR_ERR_ARG, "empty batch (n_groups=%d): the reference never runs one "
+                                         "(Train_recommender.py:163-166 drops the tail)", B);
+  if (S64 > h->cfg.max_rows) return fail(h, FR_ERR_ARG, "batch has %lld item rows > max_rows=%d", (long long)S64, h->cfg.max_rows);
+  const int S = (int)S64;
+  if (!b->users || !b->items) return fail(h, FR_ERR_ARG, "users/items are required");
+  if (b->mode == FR_POINTWISE && !b->labels) return fail(h, FR_ERR_ARG, "labels are required in pointwise mode");
+  if (!b->cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cats is NULL and no item_cats table");
+  if (!b->user_labels && !(h->tab.user_label_off && h->tab.user_label_idx))
+    return fail(h, FR_ERR_ARG, "user_labels is NULL and no user-label CSR table");
+  cudaStream_t st = (cudaStream_t)s;
+  Launch l{h->sm_count, st};
+  const fr_tables& T = h->tab;
+  const int DV = h->mc.DV, NV = h->NV;
+  const int64_t step = h->step + 1;
+  int rc = ensure_lr_hist(h, step + 1, st); if (rc) return rc;
+  const OptConsts oc = make_oc(h, step);
+  float* out = out_scalars ? out_scalars : h->out_internal;
+  const float4* cats = (const float4*)(b->cats ? b->cats : T.item_cats);
+  const int cats_by_item = b->cats ? 0 : 1;
+
+  // 0. pre-step snapshot of Category_Embedding (every read of Cat in this step sees it)
+  FR_CUDA(h, cudaMemcpyAsync(h->cat_pre, T.Cat, (size_t)4 * h->mc.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  FR_CUDA(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(uint32_t), st));
+
+  // 1. row keys, write sign; sort item rows by user and by recipe
+  launch_prep_rows(b->mode, B, b->users, b->labels, b->write_sign, h->ukeys, h->ws_row, l);
+  const int ru = radix_sort_pairs(h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), st, h->sm_count);
+  const int ri = radix_sort_pairs(h->sortI, (const uint32_t*)b->items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), st, h->sm_count);
+  FR_CHECK_LAUNCH(h);
+
+  // 2. forward, loss, per-slice norms, dCat partials, z stash
+  FwdParams fp{};
+  fp.P = (const float4*)T.P; fp.R = (const float4*)T.R; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B;
+  fp.users = b->users; fp.items = b->items; fp.cats = cats; fp.cats_by_item = cats_by_item;
+  fp.labels = b->labels; fp.a = h->mc.a; fp.oma = h->mc.oma;
+  fp.g = h->g; fp.z = h->z; fp.scores = out_scores ? out_scores : h->scores;
+  fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
+  const int fgrid = fwd_train_grid(B, h->sm_count);
+  launch_fwd_train(NV, group, fp, fgrid, l);
+  FR_CHECK_LAUNCH(h);
+
+  // 3. global norm -> clip scale; dense optimizer on Cat
+  FinalizeParams fin{};
+  fin.part_loss = h->part_loss; fin.part_nrm = h->part_nrm; fin.part_gcat = h->part_gcat; fin.nblk = fgrid;
+  fin.DV = DV; fin.B = (float)B; fin.packed = h->packed; fin.do_reduce = 1; fin.do_apply = 1;
+  fin.Cat = (float4*)T.Cat; fin.s1Cat = (float4*)T.s1_Cat; fin.s2Cat = (float4*)T.s2_Cat;
+  fin.oc = oc; fin.clip = h->cfg.clip_norm; fin.out = out; fin.lr_hist = h->lr_hist;
+  launch_finalize(fin, l);
+  FR_CHECK_LAUNCH(h);
+
+  // 4. Personal_Memory: segment-reduce by user + optimizer (+ personal write)
+  {
+    SegCommon c{};
+    c.keys = h->sortU.k[ru]; c.perm = h->sortU.v[ru]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
+    c.uniq_counter = h->counters + 0;
+    if (write_personal) {
+      const size_t need = (size_t)S / 32 + 2;
+      if (need > h->pieces_personal_chunks) {
+        if (h->pieces_personal) { FR_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->pieces_personal); h->pieces_personal = nullptr; }
+        FR_CUDA(h, cudaMalloc(&h->pieces_personal, need * 2 * 15 * DV * sizeof(float4)));
+        h->pieces_personal_chunks = need;
+      }
+      c.pieces = h->pieces_personal;
+    } else {
+      c.pieces = h->pieces_u;
+    }
+    UserPolParams up{};
+    up.P = (float4*)T.P; up.s1 = (float4*)T.s1_P; up.s2 = (float4*)T.s2_P; up.last = T.last_P;
+    up.R = (const float4*)T.R; up.G = (const float4*)T.G; up.cat = h->cat_pre;
+    up.items = b->items; up.g = h->g; up.cats = cats; up.cats_by_item = cats_by_item;
+    up.ws_row = h->ws_row; up.out = out; up.group = group; up.mc = h->mc; up.oc = oc;
+    up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = b->users;
+    launch_user_pass(NV, write_personal ? 1 : 0, c, up, l);
+    FR_CHECK_LAUNCH(h);
+  }
+
+  // 5. General_Memory: label feed -> entries -> sort by label -> segment-reduce (reads pre-step R)
+  {
+    LabelEmitParams ep{};
+    ep.S = S; ep.group = group; ep.L = h->mc.L; ep.users = b->users;
+    ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
+    ep.ws_row = h->ws_row; ep.counts = h->counts; ep.offs = h->offs;
+    ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
+    ep.cap = (uint32_t)h->sortL.cap; ep.n_entries = h->n_entries; ep.out = out;
+    launch_label_count(ep, l);
+    exclusive_scan_u32(h->counts, h->offs, (uint32_t)S, h->scan_tmp, h->n_entries, st);
+    launch_label_emit(ep, l);
+    const uint32_t ecap = (uint32_t)h->sortL.cap;
+    const int rl = radix_sort_pairs(h->sortL, h->ent_key, ecap, h->n_entries, bits_for(h->mc.L), st, h->sm_count);
+    FR_CHECK_LAUNCH(h);
+    SegCommon c{};
+    c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
+    c.pieces = h->pieces_g; c.uniq_counter = nullptr;
+    LabelPolParams lp{};
+    lp.G = (float4*)T.G; lp.R = (const float4*)T.R; lp.cat = h->cat_pre;
+    lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = b->items; lp.cats = cats;
+    lp.cats_by_item = cats_by_item; lp.mc = h->mc;
+    launch_label_pass(NV, c, lp, l);
+    FR_CHECK_LAUNCH(h);
+  }
+
+  // 6. Recipe_Embedding: segment-reduce by recipe + optimizer
+  {
+    SegCommon c{};
+    c.keys = h->sortI.k[ri]; c.perm = h->sortI.v[ri]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
+    c.pieces = h->pieces_i; c.uniq_counter = h->counters + 1;
+    ItemPolParams ip{};
+    ip.R = (float4*)T.R; ip.s1 = (float4*)T.s1_R; ip.s2 = (float4*)T.s2_R; ip.last = T.last_R;
+    ip.z = h->z; ip.g = h->g; ip.out = out; ip.mc = h->mc; ip.oc = oc;
+    launch_item_pass(NV, c, ip, l);
+    FR_CHECK_LAUNCH(h);
+  }
+
+  // 7. TF-1.x dense Adam: every untouched row decays this step too
+  if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_DENSE) {
+    launch_adam_sweep((float4*)T.P, (float4*)T.s1_P, (float4*)T.s2_P, T.last_P, h->cfg.num_users, 5 * DV, oc, (int)step, l);
+    launch_adam_sweep((float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R, T.last_R, h->cfg.num_items, DV, oc, (int)step, l);
+    FR_CHECK_LAUNCH(h);
+  }
+
+  // 8. fetches: general = mean(G) (:219), personal = mean(P) (:218, personal steps only)
+  launch_mean((const float4*)T.G, (int64_t)h->mc.L * 5 * DV, h->mean_partials, out + FR_OUT_GENERAL,
+              (double)h->mc.L * 5.0 * h->mc.D, l);
+  if (write_personal) {
+    if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_EXACT) {
+      // mean(P) must see every row at step t
+      launch_adam_sweep((float4*)T.P, (float4*)T.s1_P, (float4*)T.s2_P, T.last_P, h->cfg.num_users, 5 * DV, oc, (int)step, l);
+    }
+    launch_mean((const float4*)T.P, (int64_t)h->cfg.num_users * 5 * DV, h->mean_partials, out + FR_OUT_PERSONAL,
+                (double)h->cfg.num_users * 5.0 * h->mc.D, l);
+  }
+  launch_write_counters(h->counters, out, l);
+  FR_CHECK_LAUNCH(h);
+
+  h->step = step;
+  h->b1p *= h->cfg.adam_beta1;     // adam.py _finish
+  h->b2p *= h->cfg.adam_beta2;
+  return FR_OK;
+}
+
+extern "C" int fr_train_step_host(fr_handle h, const fr_batch* hb, int32_t write_personal,
+                                  float* host_out_scalars, fr_stream s) {
+  if (!h || !hb) return FR_ERR_ARG;
+  const int group = hb->mode == FR_BPR ? 2 : 1;
+  const int B = hb->n_groups;
+  if (B <= 0) return fail(h, FR_ERR_ARG, "empty batch");
+  const size_t S = (size_t)B * group, L = (size_t)h->mc.L;
+  cudaStream_t st = (cudaStream_t)s;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_users = 0;
+  const size_t o_items = o_users + al(B * 4);
+  const size_t o_cats = o_items + al(S * 4);
+  const size_t o_labels = o_cats + al(hb->cats ? S * 16 : 0);
+  const size_t o_ws = o_labels + al(hb->labels ? (size_t)B * 4 : 0);
+  const size_t o_ul = o_ws + al(hb->write_sign ? S * 4 : 0);
+  const size_t o_out = o_ul + al(hb->user_labels ? (size_t)B * L * 4 : 0);
+  const size_t total = o_out + al(FR_OUT_COUNT * 4);
+  if (total > h->stage_bytes) {
+    if (h->stage) { FR_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->stage); h->stage = nullptr; }
+    FR_CUDA(h, cudaMalloc(&h->stage, total));
+    h->stage_bytes = total;
+  }
+  char* base = (char*)h->stage;
+  fr_batch db = *hb;
+#define H2D(field, off, bytes) if (hb->field) { \
+    FR_CUDA(h, cudaMemcpyAsync(base + (off), hb->field, (bytes), cudaMemcpyHostToDevice, st)); \
+    db.field = reinterpret_cast<decltype(db.field)>(base + (off)); }
+  H2D(users, o_users, (size_t)B * 4)
+  H2D(items, o_items, S * 4)
+  H2D(cats, o_cats, S * 16)
+  H2D(labels, o_labels, (size_t)B * 4)
+  H2D(write_sign, o_ws, S * 4)
+  H2D(user_labels, o_ul, (size_t)B * L * 4)
+#undef H2D
+  float* dout = reinterpret_cast<float*>(base + o_out);
+  int rc = fr_train_step(h, &db, write_personal, dout, nullptr, s);
+  if (rc) return rc;
+  if (host_out_scalars)
+    FR_CUDA(h, cudaMemcpyAsync(host_out_scalars, dout, FR_OUT_COUNT * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return FR_OK;
+}

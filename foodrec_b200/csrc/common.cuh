@@ -1,0 +1,105 @@
+// Shared device helpers for the foodrec_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FR_FULL 0xffffffffu
+#define FR_WARPS_PER_BLOCK 8
+#define FR_THREADS (FR_WARPS_PER_BLOCK * 32)
+
+namespace fr {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FR_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FR_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+__device__ __forceinline__ void fma4(float4& acc, const float s, const float4 v) {
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y);
+  acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 scale4(const float s, const float4 v) {
+  return make_float4(s * v.x, s * v.y, s * v.z, s * v.w);
+}
+__device__ __forceinline__ float4 shfl4(const float4 v, const int src) {
+  return make_float4(__shfl_sync(FR_FULL, v.x, src), __shfl_sync(FR_FULL, v.y, src),
+                     __shfl_sync(FR_FULL, v.z, src), __shfl_sync(FR_FULL, v.w, src));
+}
+
+// 16-byte row access.  A row of D floats is DV = D/4 float4; lane l owns float4
+// l, l+32, ... (NV of them).  Lanes past DV carry zeros.
+__device__ __forceinline__ float4 ld_stream(const float4* p) {   // read-once data: keep out of L1
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int NV>
+__device__ __forceinline__ void load_row(float4 (&dst)[NV], const float4* row, int DV, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    dst[k] = (i < DV) ? ld_stream(row + i) : f4zero();
+  }
+}
+template <int NV>
+__device__ __forceinline__ void load_row_ro(float4 (&dst)[NV], const float4* __restrict__ row, int DV, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    dst[k] = (i < DV) ? __ldg(row + i) : f4zero();
+  }
+}
+template <int NV>
+__device__ __forceinline__ void store_row(float4* row, const float4 (&src)[NV], int DV, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < DV) st_stream(row + i, src[k]);
+  }
+}
+
+// sum_c m_c * Cat[c]  (un-normalised pooled category row; Model_Recommender.py:67,124-128)
+template <int NV>
+__device__ __forceinline__ void pooled_cat(float4 (&pc)[NV], const float4* sCat, const float4 m, int DV, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < DV) {
+      const float4 c0 = sCat[i], c1 = sCat[DV + i], c2 = sCat[2 * DV + i], c3 = sCat[3 * DV + i];
+      float4 r;
+      r.x = m.x * c0.x + m.y * c1.x + m.z * c2.x + m.w * c3.x;
+      r.y = m.x * c0.y + m.y * c1.y + m.z * c2.y + m.w * c3.y;
+      r.z = m.x * c0.z + m.y * c1.z + m.z * c2.z + m.w * c3.z;
+      r.w = m.x * c0.w + m.y * c1.w + m.z * c2.w + m.w * c3.w;
+      pc[k] = r;
+    } else {
+      pc[k] = f4zero();
+    }
+  }
+}
+__device__ __forceinline__ float4 div4(const float4 v, const float n) {
+  return make_float4(v.x / n, v.y / n, v.z / n, v.w / n);
+}
+__device__ __forceinline__ float comp(const float4 v, const int c) {
+  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
+}  // namespace fr

@@ -1,0 +1,83 @@
+// Parameter blocks for the train-step kernels (train.cu) and their launchers.
+#pragma once
+#include "internal.h"
+
+namespace fr {
+
+struct FwdParams {
+  const float4 *P, *R, *cat;        // cat = step-start snapshot of Category_Embedding
+  int DV, B;
+  const int32_t *users, *items;
+  const float4* cats; int cats_by_item;
+  const float* labels;
+  float a, oma;
+  float* g; float4* z; float* scores;
+  float *part_loss, *part_nrm; float4* part_gcat;   // one slot per block
+};
+
+struct FinalizeParams {
+  const float *part_loss, *part_nrm; const float4* part_gcat; int nblk;
+  int DV; float inv_count_B;  // loss mean divisor (global batch)
+  float B;
+  float* packed;          // [2 + 4*D]: loss_sum, nrm_sum, gCat  (all-reduced across ranks in multi-GPU)
+  int do_reduce, do_apply;
+  float4 *Cat, *s1Cat, *s2Cat;
+  OptConsts oc; float clip;
+  float* out; float* lr_hist;
+};
+
+struct SegCommon {
+  const uint32_t* keys; const uint32_t* perm;
+  const uint32_t* n_dev; uint32_t n_host;
+  float4* pieces;              // [(chunk*2+slot) * NR*DV]
+  uint32_t* uniq_counter;      // nullable
+  uint32_t* head_chunk_flags;  // unused
+};
+
+struct UserPolParams {
+  float4 *P, *s1, *s2; int32_t* last;
+  const float4 *R, *G; const float4* cat;   // pre-step values
+  const int32_t* items; const float* g; const float4* cats; int cats_by_item;
+  const float* ws_row; const float* out;    // out[FR_OUT_SCALE]
+  int group; ModelConsts mc; OptConsts oc;
+  const float* user_labels; const int32_t *lab_off, *lab_idx; const int32_t* users;
+};
+struct ItemPolParams {
+  float4 *R, *s1, *s2; int32_t* last;
+  const float4* z; const float* g; const float* out;
+  ModelConsts mc; OptConsts oc;
+};
+struct LabelPolParams {
+  float4* G; const float4 *R, *cat;
+  const uint32_t* ent_row; const float* ent_coef;
+  const int32_t* items; const float4* cats; int cats_by_item;
+  ModelConsts mc;
+};
+
+struct LabelEmitParams {
+  int S, group, L; const int32_t* users;
+  const float* user_labels; const int32_t *lab_off, *lab_idx;
+  const float* ws_row;
+  uint32_t* counts;     // [S]
+  const uint32_t* offs; // [S]
+  uint32_t *ent_key, *ent_row; float* ent_coef; uint32_t cap;
+  uint32_t* n_entries; float* out;
+};
+
+void launch_prep_rows(int mode, int B, const int32_t* users, const float* labels, const float* ws_in,
+                      uint32_t* ukeys, float* ws_row, const Launch& l);
+void launch_fwd_train(int NV, int group, const FwdParams& p, int grid, const Launch& l);
+int fwd_train_grid(int B, int sm_count);
+void launch_finalize(const FinalizeParams& p, const Launch& l);
+void launch_user_pass(int NV, int personal, const SegCommon& c, const UserPolParams& p, const Launch& l);
+void launch_item_pass(int NV, const SegCommon& c, const ItemPolParams& p, const Launch& l);
+void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, const Launch& l);
+void launch_label_count(const LabelEmitParams& p, const Launch& l);
+void launch_label_emit(const LabelEmitParams& p, const Launch& l);
+void launch_adam_sweep(float4* var, float4* m, float4* v, int32_t* last, int64_t nrows, int rowDV,
+                       const OptConsts& oc, int target_step, const Launch& l);
+void launch_fill_i32(int32_t* p, int64_t n, int32_t v, const Launch& l);
+void launch_mean(const float4* x, int64_t n4, double* partials, float* out_slot, double count, const Launch& l);
+void launch_write_counters(const uint32_t* counters, float* out, const Launch& l);
+
+}  // namespace fr

@@ -1,0 +1,269 @@
+"""Device engine: owns the tables (torch CUDA tensors = device memory + streams only)
+and drives libfoodrec_b200.so through the C ABI.  No compute happens in Python or
+torch; without the CUDA library every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+@dataclass
+class Hyper:
+    """The ``args`` fields ``Model.__init__`` reads (Model_Recommender.py:6-24) plus the
+    TF-1.x optimizer defaults the reference inherits."""
+    learner: str = "adam"
+    lr: float = 0.001
+    high_level_score_coefficient: float = 0.99
+    beta_1: float = 0.01
+    beta_2: float = 0.01
+    alpha: float = 0.01
+    clip_norm: float = 5.0
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_eps: float = 1e-8
+    adagrad_init: float = 0.1
+    rms_decay: float = 0.9
+    rms_eps: float = 1e-10
+
+    @classmethod
+    def from_args(cls, args):
+        return cls(learner=args.learner, lr=float(args.lr),
+                   high_level_score_coefficient=float(args.high_level_score_coefficient),
+                   beta_1=float(args.beta_1), beta_2=float(args.beta_2), alpha=float(args.alpha))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, hyper: Hyper, P, R, Cat, G, device="cuda:0", max_rows=1 << 16,
+                 max_label_entries=None, adam_mode="lazy_exact", item_cats=None, user_labels=None):
+        self.lib = L.lib()                       # raises if the .so is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("foodrec_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.h = hyper
+        dev = lambda x: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x,
+                                        dtype=torch.float32).to(self.device).contiguous().clone()
+        self.P, self.R, self.Cat, self.G = dev(P), dev(R), dev(Cat), dev(G)
+        self.U, five, self.D = self.P.shape
+        assert five == 5 and self.Cat.shape == (4, self.D) and self.R.shape[1] == self.D
+        self.I, self.Lb = self.R.shape[0], self.G.shape[0]
+        self.learner = L.learner_code(hyper.learner)
+        self.adam_mode = L.FR_ADAM_LAZY_EXACT if adam_mode == "lazy_exact" else L.FR_ADAM_DENSE
+        z = torch.zeros_like
+        self.s1 = {}; self.s2 = {}
+        tabs = {"P": self.P, "R": self.R, "Cat": self.Cat}
+        if self.learner == L.FR_ADAM:
+            self.s1 = {k: z(v) for k, v in tabs.items()}; self.s2 = {k: z(v) for k, v in tabs.items()}
+        elif self.learner == L.FR_ADAGRAD:
+            self.s1 = {k: torch.full_like(v, hyper.adagrad_init) for k, v in tabs.items()}
+        elif self.learner == L.FR_RMSPROP:
+            self.s1 = {k: torch.ones_like(v) for k, v in tabs.items()}; self.s2 = {k: z(v) for k, v in tabs.items()}
+        self.last_P = torch.zeros(self.U, dtype=torch.int32, device=self.device)
+        self.last_R = torch.zeros(self.I, dtype=torch.int32, device=self.device)
+        self.item_cats = None
+        self.lab_off = self.lab_idx = None
+        self.max_labels_per_user = self.Lb
+        if item_cats is not None:
+            self.item_cats = torch.as_tensor(np.asarray(item_cats, np.float32).reshape(self.I, 4)).to(self.device).contiguous()
+        if user_labels is not None:     # dense [U, L] multi-hot -> CSR (weights must be 0/1)
+            ul = np.asarray(user_labels)
+            assert ul.shape == (self.U, self.Lb)
+            if not np.isin(ul, (0, 1)).all():
+                raise ValueError("resident user-label table must be 0/1 (use the dense feed for weights)")
+            rows, cols = np.nonzero(ul)
+            cnt = np.bincount(rows, minlength=self.U)
+            off = np.zeros(self.U + 1, np.int32); off[1:] = np.cumsum(cnt)
+            self.lab_off = torch.as_tensor(off).to(self.device)
+            self.lab_idx = torch.as_tensor(cols.astype(np.int32)).to(self.device)
+            self.max_labels_per_user = int(cnt.max()) if cnt.size else 1
+        self.max_rows = int(max_rows)
+        if max_label_entries is None:
+            max_label_entries = self.max_rows * (self.max_labels_per_user if user_labels is not None else min(self.Lb, 16))
+        self.max_label_entries = int(min(max_label_entries, 2**31 - 1))
+        cfg = L.fr_config(self.D, self.U, self.I, self.Lb, self.learner, self.adam_mode, self.max_rows,
+                          self.max_label_entries, hyper.lr, hyper.high_level_score_coefficient,
+                          hyper.beta_1, hyper.beta_2, hyper.alpha, hyper.clip_norm,
+                          hyper.adam_beta1, hyper.adam_beta2, hyper.adam_eps, hyper.rms_decay, hyper.rms_eps)
+        self.handle = C.c_void_p()
+        rc = self.lib.fr_create(C.byref(cfg), C.byref(self.handle))
+        if rc != L.FR_OK:
+            msg = self.lib.fr_last_error(self.handle).decode() if self.handle else "fr_create failed"
+            self.lib.fr_destroy(self.handle); self.handle = None
+            raise L.FoodRecError(msg)
+        self._set_tables()
+        self.out = torch.zeros(L.FR_OUT_COUNT, dtype=torch.float32, device=self.device)
+        self.out_host = torch.zeros(L.FR_OUT_COUNT, dtype=torch.float32).pin_memory()
+        self._dirty = False          # lazy Adam rows pending a flush
+        self._keep = []
+
+    # ------------------------------------------------------------------ plumbing
+    def _set_tables(self):
+        t = L.fr_tables()
+        t.P, t.R, t.Cat, t.G = _ptr(self.P), _ptr(self.R), _ptr(self.Cat), _ptr(self.G)
+        g = lambda d, k: _ptr(d.get(k))
+        t.s1_P, t.s2_P = g(self.s1, "P"), g(self.s2, "P")
+        t.s1_R, t.s2_R = g(self.s1, "R"), g(self.s2, "R")
+        t.s1_Cat, t.s2_Cat = g(self.s1, "Cat"), g(self.s2, "Cat")
+        t.last_P, t.last_R = _ptr(self.last_P), _ptr(self.last_R)
+        t.item_cats, t.user_label_off, t.user_label_idx = _ptr(self.item_cats), _ptr(self.lab_off), _ptr(self.lab_idx)
+        L.check(self.handle, self.lib.fr_set_tables(self.handle, C.byref(t)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.fr_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def step(self) -> int:
+        s = C.c_int64()
+        L.check(self.handle, self.lib.fr_get_step(self.handle, C.byref(s)))
+        return s.value
+
+    def _i32(self, x):
+        if torch.is_tensor(x):
+            return x.to(self.device, torch.int32).contiguous().reshape(-1)
+        return torch.as_tensor(np.ascontiguousarray(np.asarray(x).astype(np.int32)).reshape(-1)).to(self.device)
+
+    def _f32(self, x, shape=None):
+        if x is None:
+            return None
+        if torch.is_tensor(x):
+            t = x.to(self.device, torch.float32).contiguous()
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float32))).to(self.device)
+        return t.reshape(shape) if shape is not None else t
+
+    # ------------------------------------------------------------------ hot path
+    def train_step(self, users, items, labels=None, categories=None, write_sign=None,
+                   user_one_hot_label=None, neg_items=None, neg_categories=None,
+                   write_personal=False, return_scores=False):
+        """One optimizer step on device-resident (or host, copied here) feed tensors.
+        Pointwise when ``neg_items`` is None, else BPR.  Returns the device scalar
+        vector (FR_OUT_*); nothing is synchronised."""
+        u = self._i32(users)
+        B = u.numel()
+        bpr = neg_items is not None
+        if bpr:
+            it = torch.stack([self._i32(items), self._i32(neg_items)], 1).reshape(-1).contiguous()
+            cats = None
+            if categories is not None:
+                cats = torch.stack([self._f32(categories, (B, 4)), self._f32(neg_categories, (B, 4))], 1).reshape(-1, 4).contiguous()
+        else:
+            it = self._i32(items)
+            cats = self._f32(categories, (B, 4))
+        return self._step_dev(L.FR_BPR if bpr else L.FR_POINTWISE, B, u, it, cats, self._f32(labels, (-1,)),
+                              self._f32(write_sign, (-1,)), self._f32(user_one_hot_label, (B, self.Lb)),
+                              write_personal, return_scores)
+
+    def _step_dev(self, mode, B, users, items, cats, labels, ws, ulab, write_personal=False, return_scores=False):
+        b = L.fr_batch(mode, B, _ptr(users), _ptr(items), _ptr(cats), _ptr(labels), _ptr(ws), _ptr(ulab))
+        scores = torch.empty(items.numel(), dtype=torch.float32, device=self.device) if return_scores else None
+        L.check(self.handle, self.lib.fr_train_step(self.handle, C.byref(b), int(bool(write_personal)),
+                                                    _ptr(self.out), _ptr(scores), self._stream()))
+        self._dirty = True
+        self._keep = [users, items, cats, labels, ws, ulab]    # alive until the next step is queued
+        return (self.out, scores) if return_scores else self.out
+
+    def train_step_host(self, mode, B, users, items, cats=None, labels=None, ws=None, ulab=None,
+                        write_personal=False):
+        """fr_train_step_host: host (ideally pinned) torch/numpy buffers; H2D + step +
+        D2H of the scalars are queued on the current stream.  Returns the pinned
+        host scalar tensor (valid after a stream sync)."""
+        hp = lambda x: C.c_void_p(0) if x is None else C.c_void_p(x.data_ptr() if torch.is_tensor(x) else x.ctypes.data)
+        b = L.fr_batch(mode, B, hp(users), hp(items), hp(cats), hp(labels), hp(ws), hp(ulab))
+        L.check(self.handle, self.lib.fr_train_step_host(self.handle, C.byref(b), int(bool(write_personal)),
+                                                         C.c_void_p(self.out_host.data_ptr()), self._stream()))
+        self._dirty = True
+        self._keep = [users, items, cats, labels, ws, ulab]
+        return self.out_host
+
+    def read_scalars(self):
+        v = self.out.cpu().numpy()       # synchronises
+        if v[L.FR_OUT_OVERFLOW] != 0:
+            raise L.FoodRecError(f"label feed has {int(v[L.FR_OUT_LABEL_ENTRIES])} non-zeros > "
+                                 f"max_label_entries={self.max_label_entries}; General_Memory write truncated")
+        return v
+
+    def flush(self):
+        """Lazy-exact Adam: bring every row to the current step before the tables are read."""
+        if self._dirty and self.learner == L.FR_ADAM and self.adam_mode == L.FR_ADAM_LAZY_EXACT:
+            L.check(self.handle, self.lib.fr_adam_flush(self.handle, self._stream()))
+        self._dirty = False
+
+    def score(self, users, items, categories=None):
+        self.flush()
+        u, it = self._i32(users), self._i32(items)
+        cats = self._f32(categories, (u.numel(), 4))
+        out = torch.empty(u.numel(), dtype=torch.float32, device=self.device)
+        L.check(self.handle, self.lib.fr_fwd_score(self.handle, _ptr(u), _ptr(it), _ptr(cats), u.numel(), _ptr(out), self._stream()))
+        self._keep = [u, it, cats]
+        return out
+
+    def eval_sampled_topk(self, users, cand, n_cand, K, cand_cats=None, return_scores=False):
+        self.flush()
+        u = self._i32(users)
+        n = u.numel()
+        cand = torch.as_tensor(np.asarray(cand, np.int32)) if not torch.is_tensor(cand) else cand
+        stride = cand.shape[1]
+        cand_d = cand.to(self.device, torch.int32).contiguous()
+        nc = self._i32(n_cand)
+        cc = self._f32(cand_cats, (n, stride, 4))
+        ids = torch.empty((n, K), dtype=torch.int32, device=self.device)
+        rank = torch.empty(n, dtype=torch.int32, device=self.device)
+        sc = torch.zeros((n, stride), dtype=torch.float32, device=self.device) if return_scores else None
+        L.check(self.handle, self.lib.fr_eval_sampled_topk(self.handle, _ptr(u), _ptr(cand_d), _ptr(nc), n, stride,
+                                                           _ptr(cc), K, _ptr(ids), _ptr(rank), _ptr(sc), self._stream()))
+        self._keep = [u, cand_d, nc, cc]
+        return (ids, rank, sc) if return_scores else (ids, rank)
+
+    def sort_pairs(self, keys, nbits):
+        k = torch.as_tensor(np.asarray(keys, np.int64).astype(np.uint32).view(np.int32)).to(self.device)
+        ok = torch.empty_like(k); oi = torch.empty_like(k)
+        L.check(self.handle, self.lib.fr_sort_pairs(self.handle, _ptr(k), k.numel(), nbits, _ptr(ok), _ptr(oi), self._stream()))
+        return ok.cpu().numpy().view(np.uint32), oi.cpu().numpy().view(np.uint32)
+
+    # ------------------------------------------------------------------ state
+    def tables(self):
+        """Host copies of the four tables at the current step (flushes lazy Adam)."""
+        self.flush()
+        return {k: getattr(self, k).detach().cpu().numpy() for k in ("P", "R", "Cat", "G")}
+
+    def state_dict(self):
+        self.flush()
+        sd = {k: getattr(self, k).detach().cpu().numpy() for k in ("P", "R", "Cat", "G")}
+        for name, d in (("s1", self.s1), ("s2", self.s2)):
+            for k, v in d.items():
+                sd[f"{name}_{k}"] = v.detach().cpu().numpy()
+        sd["step"] = np.int64(self.step)
+        return sd
+
+    def load_state_dict(self, sd):
+        for k in ("P", "R", "Cat", "G"):
+            getattr(self, k).copy_(torch.as_tensor(sd[k]))
+        for name, d in (("s1", self.s1), ("s2", self.s2)):
+            for k, v in d.items():
+                v.copy_(torch.as_tensor(sd[f"{name}_{k}"]))
+        step = int(sd["step"])
+        self.last_P.fill_(step); self.last_R.fill_(step)
+        L.check(self.handle, self.lib.fr_set_step(self.handle, step))
+        self._dirty = False

@@ -1,0 +1,152 @@
+/* foodrec_b200.h -- C ABI of the B200-native Market2Dish Recommender hot path.
+ *
+ * The reference (WenjieWWJ/FoodRec, Code/Recommender) has no FFI/plugin layer:
+ * its hot path is the TF-1.x graph built by Model_Recommender.py and driven by
+ * sess.run() from Train_recommender.py / evaluate.py.  This header is the
+ * boundary the Python `foodrec_b200.Model` / `Session` shim binds (ctypes); each
+ * entry point cites the reference graph section it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch/CUDA types (fr_stream == cudaStream_t
+ *    passed as void*).
+ *  - the caller owns every table and batch buffer (device memory unless the
+ *    entry point says "host"); the library owns only its workspace.
+ *  - every call is asynchronous and ordered on the given stream; returns FR_OK
+ *    or a negative code and never throws; fr_last_error() gives the message.
+ *  - one handle per device, not thread-safe; multi-GPU = one process per GPU.
+ *  - no CPU fallback: a missing/failed CUDA device is an error.
+ *
+ * Layouts (all row-major, fp32 tables, int32 ids -- as in the reference):
+ *   P   Personal_Memory   [U,5,D]  slot 0 = category memory, 1..4 = dish memories
+ *   R   Recipe_Embedding  [I,D]
+ *   Cat Category_Embedding[4,D]
+ *   G   General_Memory    [L,5,D]
+ * D must be a multiple of 4 and <= 256; all table pointers 16-byte aligned.
+ */
+#ifndef FOODREC_B200_H
+#define FOODREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR_ABI_VERSION 1
+
+typedef struct fr_ctx* fr_handle;
+typedef void* fr_stream; /* cudaStream_t */
+
+enum { FR_OK = 0, FR_ERR_ARG = -1, FR_ERR_CUDA = -2, FR_ERR_STATE = -3, FR_ERR_UNSUPPORTED = -4 };
+
+/* Model_Recommender.py:228-235 -- learner is matched case-insensitively, anything else = SGD */
+enum { FR_SGD = 0, FR_ADAGRAD = 1, FR_RMSPROP = 2, FR_ADAM = 3 };
+/* TF-1.x sparse Adam decays m,v and moves var for EVERY row each step (adam.py
+ * _apply_sparse_shared).  DENSE does that sweep literally; LAZY_EXACT defers it per
+ * row (last-step stamp) and replays the skipped steps with identical arithmetic
+ * when the row is next touched or on fr_adam_flush -- same results, O(touched) traffic. */
+enum { FR_ADAM_DENSE = 0, FR_ADAM_LAZY_EXACT = 1 };
+enum { FR_POINTWISE = 0, FR_BPR = 1 };
+
+/* Mirrors the args fields Model.__init__ reads (Model_Recommender.py:6-24). */
+typedef struct {
+  int32_t embed_size;   /* D */
+  int32_t num_users;    /* U (rows of P held by this process) */
+  int32_t num_items;    /* I (rows of R held by this process) */
+  int32_t num_labels;   /* L */
+  int32_t learner;      /* FR_SGD.. */
+  int32_t adam_mode;    /* FR_ADAM_* */
+  int32_t max_rows;     /* capacity: item rows per step (B pointwise, 2B BPR) */
+  int32_t max_label_entries; /* capacity: non-zeros of the label feed per step */
+  float lr;                             /* args.lr (global_step never advances: lr is constant, :224-226) */
+  float high_level_score_coefficient;   /* a, :17 ; low coefficient = 1-a, :96 */
+  float beta_1, beta_2, alpha;          /* write coefficients :115,:140,:196 */
+  float clip_norm;                      /* 5.0, :237 */
+  float adam_beta1, adam_beta2, adam_eps;
+  float rms_decay, rms_eps;
+} fr_config;
+
+/* Device tables + optimizer slots (caller-owned).  Slot meaning by learner:
+ *   ADAM: s1=m (0), s2=v (0);  ADAGRAD: s1=accumulator (0.1);  RMSPROP: s1=ms (1), s2=mom (0)
+ * last_* (int32 per row, 0-initialised) are required for FR_ADAM only. */
+typedef struct {
+  float *P, *R, *Cat, *G;
+  float *s1_P, *s2_P, *s1_R, *s2_R, *s1_Cat, *s2_Cat;
+  int32_t *last_P, *last_R;
+  /* optional device-resident side tables for the compact (ids-only) feed:
+   * item_cats [I,4] = dish_to_category; label CSR over users = user_to_one_hot_label */
+  const float* item_cats;
+  const int32_t* user_label_off; /* [U+1] */
+  const int32_t* user_label_idx; /* [nnz], values in [0,L) , weight 1 */
+} fr_tables;
+
+/* One batch = the placeholders of Model_Recommender.py:26-33.
+ * n_groups = B.  Item rows: pointwise S=B (row b); BPR S=2B (row 2t = positive,
+ * 2t+1 = negative of triple t).  NULL selects the compact alternative. */
+typedef struct {
+  int32_t mode;            /* FR_POINTWISE | FR_BPR */
+  int32_t n_groups;        /* B */
+  const int32_t* users;    /* [B]    user_input */
+  const int32_t* items;    /* [S]    item_input (BPR: interleaved pos/neg) */
+  const float* cats;       /* [S,4]  categories ([.,4,1] flattened); NULL -> tables.item_cats[item] */
+  const float* labels;     /* [B]    labels (pointwise only) */
+  const float* write_sign; /* [S]    write_sign; NULL -> +1 if label>0.5 else -1 (BPR: +1 pos, -1 neg) */
+  const float* user_labels;/* [B,L]  user_one_hot_label; NULL -> tables.user_label_* CSR by user */
+} fr_batch;
+
+/* Device scalars written by fr_train_step (index into float out[FR_OUT_COUNT]). */
+enum { FR_OUT_LOSS = 0, FR_OUT_NORM = 1, FR_OUT_SCALE = 2, FR_OUT_GENERAL = 3,
+       FR_OUT_PERSONAL = 4, FR_OUT_LR = 5, FR_OUT_UNIQ_USERS = 6, FR_OUT_UNIQ_ITEMS = 7,
+       FR_OUT_LABEL_ENTRIES = 8, FR_OUT_OVERFLOW = 9 /* !=0: label feed exceeded max_label_entries */,
+       FR_OUT_COUNT = 12 };
+
+int fr_abi_version(void);
+int fr_create(const fr_config* cfg, fr_handle* out);
+int fr_destroy(fr_handle h);
+const char* fr_last_error(fr_handle h);
+int fr_set_tables(fr_handle h, const fr_tables* t);
+
+/* Optimizer step counter (TF: the beta-power accumulators of adam.py); set on restore. */
+int fr_get_step(fr_handle h, int64_t* step);
+int fr_set_step(fr_handle h, int64_t step);
+
+/* inference, Model_Recommender.py:56-97 -> scores[n].  cats NULL -> item_cats table. */
+int fr_fwd_score(fr_handle h, const int32_t* users, const int32_t* items, const float* cats,
+                 int32_t n, float* scores, fr_stream s);
+
+/* One sess.run([loss_value, learning_rate, (personal,) general, train_op]) --
+ * Train_recommender.py:182-199: inference :56-97, loss :99-104, compute_gradients +
+ * clip_by_global_norm + apply_gradients :223-241, Write_Memory :106-220
+ * (write_personal != 0 <=> the run fetches model.personal).
+ * out_scalars: device float[FR_OUT_COUNT]; out_scores: device float[S] or NULL. */
+int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_personal,
+                  float* out_scalars, float* out_scores, fr_stream s);
+
+/* Same step with HOST batch buffers and a HOST out_scalars[FR_OUT_COUNT] (pinned for
+ * true async): H2D of the feed and D2H of the scalars are issued on the stream. */
+int fr_train_step_host(fr_handle h, const fr_batch* host_batch, int32_t write_personal,
+                       float* host_out_scalars, fr_stream s);
+
+/* Bring every row of P and R to the current step (LAZY_EXACT); no-op otherwise.
+ * Must precede any read of the tables by the caller (eval, checkpoint). */
+int fr_adam_flush(fr_handle h, fr_stream s);
+
+/* evaluate.py:35-66 batched: per test user, candidates cand[u, 0..n_cand[u]) (first =
+ * held-out positive), dict-dedup + heapq.nlargest(K) semantics (ties keep insertion
+ * order).  Outputs: topk_ids [n_users,K] (-1 padded), gt_rank [n_users] (position of the
+ * positive in the ranklist or -1), scores [n_users,cand_stride] or NULL. */
+int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int32_t* cand,
+                         const int32_t* n_cand, int32_t n_users, int32_t cand_stride,
+                         const float* cand_cats /* [n_users,cand_stride,4] or NULL */,
+                         int32_t K, int32_t* topk_ids, int32_t* gt_rank, float* scores,
+                         fr_stream s);
+
+/* stable LSD radix sort of (key, index) pairs -- exported for tests of the
+ * sort-and-segment machinery.  keys [n] (values < 2^nbits), out_keys/out_idx [n]. */
+int fr_sort_pairs(fr_handle h, const uint32_t* keys, int32_t n, int32_t nbits,
+                  uint32_t* out_keys, uint32_t* out_idx, fr_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOODREC_B200_H */

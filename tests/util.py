@@ -1,0 +1,71 @@
+"""Shared helpers for the parity tests (problem builders, tolerances)."""
+from __future__ import annotations
+
+import types
+
+import numpy as np
+
+from oracle import synth
+from oracle.recommender_oracle import Hyper as OHyper, OracleModel
+
+# north_star tolerance: 1e-5 relative for fp32 scores, losses and updated embeddings.
+# "Relative" is taken against max(|ref|, rms(ref)) so that entries that cancel to ~0 are
+# judged against the scale of the tensor (hard part 4).
+RTOL = 1e-5
+
+
+def assert_close(x, ref, rtol=RTOL, what=""):
+    x = np.asarray(x, np.float64); ref = np.asarray(ref, np.float64)
+    assert x.shape == ref.shape, (what, x.shape, ref.shape)
+    assert np.isfinite(x).all(), f"{what}: non-finite values"
+    rms = float(np.sqrt(np.mean(ref ** 2))) if ref.size else 0.0
+    tol = rtol * np.maximum(np.abs(ref), rms)
+    err = np.abs(x - ref)
+    bad = err > tol
+    if bad.any():
+        i = np.unravel_index(np.argmax(err / np.maximum(tol, 1e-300)), err.shape)
+        raise AssertionError(f"{what}: {bad.sum()} / {bad.size} entries off; worst at {i}: "
+                             f"got {x[i]!r} want {ref[i]!r} err {err[i]:.3e} tol {tol[i]:.3e}")
+
+
+class Problem:
+    def __init__(self, U, I, L, D, seed=0, scale=0.1):
+        self.U, self.I, self.L, self.D = U, I, L, D
+        self.tb = synth.make_tables(U, I, L, D, seed=seed, scale=scale)
+        self.item_cats = synth.make_item_categories(I, seed=seed + 1)
+        self.user_labels = synth.make_user_labels(U, L, seed=seed + 2)
+
+    def oracle(self, hyper: OHyper, dtype=np.float64):
+        return OracleModel(self.tb.P, self.tb.R, self.tb.Cat, self.tb.G, hyper, dtype=dtype)
+
+    def pointwise(self, B, seed, users=None):
+        f = synth.shuffled_pointwise_batch(self.U, self.I, B, self.item_cats, self.user_labels, seed)
+        if users is not None:
+            f["user_input"] = np.asarray(users, np.int32)
+            f["user_one_hot_label"] = self.user_labels[f["user_input"]].copy()
+        return f
+
+    def contiguous(self, B, seed, run=50):
+        """reference-stream shape: user-contiguous runs (Train_recommender.py:76-94)."""
+        rng = np.random.default_rng(seed)
+        users = np.repeat(rng.integers(0, self.U, (B + run - 1) // run), run)[:B]
+        return self.pointwise(B, seed, users=users)
+
+    def bpr(self, B, seed, users=None):
+        f = synth.shuffled_bpr_batch(self.U, self.I, B, self.item_cats, self.user_labels, seed)
+        if users is not None:
+            f["user_input"] = np.asarray(users, np.int32)
+            f["user_one_hot_label"] = self.user_labels[f["user_input"]].copy()
+        return f
+
+
+def args_ns(p: Problem, learner="adam", lr=0.001, a=0.99, beta_1=0.01, beta_2=0.01, alpha=0.01, batch_size=128):
+    """argparse-like namespace with the fields Model.__init__ reads."""
+    return types.SimpleNamespace(learner=learner, num_categories=4, num_users=p.U, num_labels=p.L,
+                                 embed_size=p.D, lr=lr, decay_steps=1000, decay_rate=1.0,
+                                 high_level_score_coefficient=a, beta_1=beta_1, beta_2=beta_2, alpha=alpha,
+                                 batch_size=batch_size)
+
+
+def ohyper(learner="adam", lr=0.001, **kw):
+    return OHyper(learner=learner, lr=lr, **kw)
