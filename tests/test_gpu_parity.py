@@ -1,0 +1,389 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the
+CPU oracle on the same seeded inputs and against the committed golden vectors.
+
+Tolerance (north_star): bit-exact for indices / top-K ids; 1e-5 relative for fp32
+scores, losses and updated embeddings (tests/util.py:assert_close), judged against the
+float64 oracle."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import evaluate_oracle, synth
+from oracle.recommender_oracle import Hyper as OHyper, OracleModel
+from tests.util import Problem, args_ns, assert_close
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_engine(p, learner="adam", lr=0.01, adam_mode="lazy_exact", max_rows=4096, resident=False, **hk):
+    from foodrec_b200 import Engine, Hyper
+    h = Hyper(learner=learner, lr=lr, **hk)
+    return Engine(h, p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=max_rows, adam_mode=adam_mode,
+                  max_label_entries=max_rows * p.L,
+                  item_cats=p.item_cats if resident else None,
+                  user_labels=p.user_labels if resident else None)
+
+
+def step_gpu(e, f, personal=False, bpr=False, compact=False):
+    kw = {}
+    if bpr:
+        kw = dict(neg_items=f["neg_item_input"], neg_categories=None if compact else f["neg_categories"])
+    e.train_step(f["user_input"], f["item_input"], labels=None if bpr else f["labels"],
+                 categories=None if compact else f["categories"],
+                 write_sign=None if (bpr or compact) else f["write_sign"],
+                 user_one_hot_label=None if compact else f["user_one_hot_label"],
+                 write_personal=personal, **kw)
+    return e.read_scalars()
+
+
+def compare_tables(e, om, what=""):
+    t = e.tables()
+    for k in ("P", "R", "Cat", "G"):
+        assert_close(t[k], getattr(om, k), what=f"{what}{k}")
+
+
+# ---------------------------------------------------------------- sort
+@pytest.mark.parametrize("n,nbits", [(1, 3), (31, 5), (2048, 8), (2049, 9), (5000, 20), (70000, 17), (100000, 1)])
+def test_radix_sort_is_stable_and_exact(n, nbits):
+    p = Problem(8, 8, 3, 8)
+    e = make_engine(p, max_rows=max(n, 128))
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << nbits, n).astype(np.uint32)
+    ok, oi = e.sort_pairs(keys, nbits)
+    ref = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(oi, ref.astype(np.uint32))
+    np.testing.assert_array_equal(ok, keys[ref])
+
+
+# ---------------------------------------------------------------- forward
+@pytest.mark.parametrize("D", [16, 64, 128, 200])
+def test_fwd_score_matches_oracle(D):
+    p = Problem(300, 200, 7, D, seed=D)
+    e = make_engine(p)
+    f = p.pointwise(777, seed=1)
+    got = e.score(f["user_input"], f["item_input"], f["categories"]).cpu().numpy()
+    ref = p.oracle(OHyper()).scores(f["user_input"], f["item_input"], f["categories"])
+    assert_close(got, ref, what="scores")
+
+
+def test_fwd_score_general_float_category_weights():
+    p = Problem(50, 40, 5, 32, seed=3)
+    e = make_engine(p)
+    f = p.pointwise(200, seed=2)
+    cats = np.random.default_rng(0).random((200, 4, 1)).astype(np.float32) + 0.1
+    got = e.score(f["user_input"], f["item_input"], cats).cpu().numpy()
+    ref = p.oracle(OHyper()).scores(f["user_input"], f["item_input"], cats)
+    assert_close(got, ref, what="scores")
+
+
+# ---------------------------------------------------------------- train step
+@pytest.mark.parametrize("learner,adam_mode", [("sgd", "dense"), ("adagrad", "dense"), ("rmsprop", "dense"),
+                                               ("adam", "dense"), ("adam", "lazy_exact")])
+@pytest.mark.parametrize("D", [64, 200])
+def test_pointwise_steps_match_oracle(learner, adam_mode, D):
+    p = Problem(500, 300, 9, D, seed=17)
+    e = make_engine(p, learner=learner, adam_mode=adam_mode)
+    om = p.oracle(OHyper(learner=learner, lr=0.01))
+    for s in range(5):
+        if s == 1:
+            f = p.contiguous(256, seed=40 + s, run=100)       # runs that cross 32-entry chunks
+        elif s == 3:
+            f = p.pointwise(200, seed=40 + s, users=np.full(200, 7))   # one user, one long run
+        else:
+            f = p.pointwise(300, seed=40 + s)
+        o = om.train_step(f)
+        v = step_gpu(e, f)
+        assert v[0] == pytest.approx(o["loss"], rel=1e-5), f"loss step {s}"
+        assert v[1] == pytest.approx(o["norm"], rel=1e-5), f"norm step {s}"
+        assert v[3] == pytest.approx(o["general"], rel=1e-5, abs=1e-9), f"general step {s}"
+        assert int(v[6]) == len(np.unique(f["user_input"])) and int(v[7]) == len(np.unique(f["item_input"]))
+    compare_tables(e, om, what=f"{learner}/{adam_mode}/D{D} ")
+
+
+@pytest.mark.parametrize("learner", ["sgd", "adam"])
+def test_bpr_steps_match_oracle(learner):
+    p = Problem(400, 250, 9, 128, seed=23)
+    e = make_engine(p, learner=learner)
+    om = p.oracle(OHyper(learner=learner, lr=0.01))
+    for s in range(4):
+        f = p.bpr(333, seed=70 + s, users=None if s != 2 else np.repeat(np.arange(9), 37))
+        o = om.train_step_bpr(f, write_personal=(s == 0))
+        v = step_gpu(e, f, personal=(s == 0), bpr=True)
+        assert v[0] == pytest.approx(o["loss"], rel=1e-5)
+        assert v[1] == pytest.approx(o["norm"], rel=1e-5)
+        if s == 0:
+            assert v[4] == pytest.approx(o["personal"], rel=1e-5, abs=1e-9)
+    compare_tables(e, om, what=f"bpr/{learner} ")
+
+
+@pytest.mark.parametrize("learner", ["sgd", "adagrad", "rmsprop", "adam"])
+def test_personal_write_step_matches_oracle(learner):
+    """Train_recommender.py:170-187: 16 mini-steps of 8 rows, each fetching model.personal."""
+    p = Problem(60, 80, 9, 64, seed=29)
+    e = make_engine(p, learner=learner)
+    om = p.oracle(OHyper(learner=learner, lr=0.01))
+    f = p.contiguous(128, seed=5, run=40)
+    for mini in range(16):
+        sl = slice(mini * 8, mini * 8 + 8)
+        fm = {k: v[sl] for k, v in f.items()}
+        o = om.train_step(fm, write_personal=True)
+        v = step_gpu(e, fm, personal=True)
+        assert v[0] == pytest.approx(o["loss"], rel=1e-5)
+        assert v[4] == pytest.approx(o["personal"], rel=1e-5, abs=1e-9)
+        assert v[3] == pytest.approx(o["general"], rel=1e-5, abs=1e-9)
+    compare_tables(e, om, what=f"personal/{learner} ")
+
+
+def test_clip_active_matches_oracle():
+    p = Problem(50, 40, 5, 64, seed=31, scale=20.0)        # large tables -> global norm > 5
+    e = make_engine(p, learner="sgd", lr=0.01)
+    om = p.oracle(OHyper(learner="sgd", lr=0.01))
+    f = p.pointwise(64, seed=3, users=np.zeros(64, np.int32))
+    o = om.train_step(f)
+    v = step_gpu(e, f)
+    assert o["scale"] < 1.0
+    assert v[2] == pytest.approx(o["scale"], rel=1e-5) and v[1] == pytest.approx(o["norm"], rel=1e-5)
+    compare_tables(e, om, what="clip ")
+
+
+def test_lazy_exact_adam_is_bit_identical_to_dense_sweep():
+    """SURVEY hard part 1: lazy catch-up replays the skipped steps with identical
+    arithmetic, so after a flush the tables equal the TF-1.x dense sweep bit for bit."""
+    p = Problem(2000, 500, 9, 64, seed=37)
+    ed = make_engine(p, adam_mode="dense")
+    el = make_engine(p, adam_mode="lazy_exact")
+    for s in range(12):
+        f = p.pointwise(256, seed=100 + s) if s % 3 else p.contiguous(256, seed=100 + s, run=64)
+        step_gpu(ed, f); step_gpu(el, f)
+    td, tl = ed.tables(), el.tables()
+    for k in ("P", "R", "Cat", "G"):
+        np.testing.assert_array_equal(td[k], tl[k], err_msg=k)
+    for k in ("P", "R"):
+        np.testing.assert_array_equal(ed.s1[k].cpu().numpy(), el.s1[k].cpu().numpy())
+        np.testing.assert_array_equal(ed.s2[k].cpu().numpy(), el.s2[k].cpu().numpy())
+
+
+def test_compact_feed_equals_dense_feed():
+    """ids-only feed (resident dish_to_category / user-label tables) == reference dense feed."""
+    p = Problem(300, 200, 9, 128, seed=41)
+    ed, ec = make_engine(p), make_engine(p, resident=True)
+    for s in range(3):
+        f = p.pointwise(500, seed=7 + s)
+        f["write_sign"] = np.where(f["labels"] > 0, 1.0, -1.0).astype(np.float32).reshape(-1, 1)
+        a = step_gpu(ed, f).copy(); b = step_gpu(ec, f, compact=True).copy()
+        np.testing.assert_array_equal(a[:6], b[:6])
+    fb = p.bpr(400, seed=11)
+    step_gpu(ed, fb, bpr=True); step_gpu(ec, fb, bpr=True, compact=True)
+    td, tc = ed.tables(), ec.tables()
+    for k in ("P", "R", "Cat", "G"):
+        np.testing.assert_array_equal(td[k], tc[k], err_msg=k)
+
+
+def test_host_buffer_entry_point_equals_device_entry_point():
+    from foodrec_b200 import _lib as L
+    p = Problem(300, 200, 9, 64, seed=43)
+    e1, e2 = make_engine(p), make_engine(p)
+    f = p.pointwise(256, seed=3)
+    v1 = step_gpu(e1, f).copy()
+    pin = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x.astype(dt))).pin_memory()
+    out = e2.train_step_host(L.FR_POINTWISE, 256, pin(f["user_input"], np.int32), pin(f["item_input"], np.int32),
+                             pin(f["categories"].reshape(-1, 4), np.float32), pin(f["labels"], np.float32),
+                             pin(f["write_sign"].reshape(-1), np.float32), pin(f["user_one_hot_label"], np.float32))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.numpy()[:6], v1[:6])
+    t1, t2 = e1.tables(), e2.tables()
+    for k in ("P", "R", "Cat", "G"):
+        np.testing.assert_array_equal(t1[k], t2[k], err_msg=k)
+
+
+def test_label_overflow_is_reported():
+    from foodrec_b200 import Engine, Hyper, _lib as L
+    p = Problem(50, 40, 9, 16, seed=2)
+    e = Engine(Hyper(), p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=256, max_label_entries=8)
+    f = p.pointwise(64, seed=1)
+    e.train_step(f["user_input"], f["item_input"], labels=f["labels"], categories=f["categories"],
+                 write_sign=f["write_sign"], user_one_hot_label=f["user_one_hot_label"])
+    with pytest.raises(L.FoodRecError, match="max_label_entries"):
+        e.read_scalars()
+
+
+def test_bad_batches_raise():
+    from foodrec_b200 import _lib as L
+    p = Problem(50, 40, 9, 16, seed=2)
+    e = make_engine(p, max_rows=64)
+    f = p.pointwise(100, seed=1)
+    with pytest.raises(L.FoodRecError, match="max_rows"):
+        step_gpu(e, f)
+    f0 = {k: v[:0] for k, v in f.items()}
+    with pytest.raises(L.FoodRecError, match="empty batch"):
+        step_gpu(e, f0)
+
+
+# ---------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("learner", ["sgd", "adagrad", "rmsprop", "adam"])
+@pytest.mark.parametrize("mode", ["pointwise", "bpr"])
+def test_cuda_path_matches_golden(learner, mode):
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    g = np.load(os.path.join(GOLD, f"train_{learner}_{mode}.npz"))
+    seed = int(g["seed"])
+    tb, ic, ul = mg.problem(seed)
+    from foodrec_b200 import Engine, Hyper
+    e = Engine(Hyper(learner=learner, lr=0.01), tb.P, tb.R, tb.Cat, tb.G, max_rows=512, max_label_entries=512 * mg.L)
+    for s, f in enumerate(mg.feeds(ic, ul, seed, bpr=(mode == "bpr"))):
+        v = step_gpu(e, f, personal=(s == 0), bpr=(mode == "bpr"))
+        assert v[0] == pytest.approx(float(g[f"loss{s}"]), rel=1e-5)
+        assert v[1] == pytest.approx(float(g[f"norm{s}"]), rel=1e-5)
+        assert v[3] == pytest.approx(float(g[f"general{s}"]), rel=1e-5, abs=1e-9)
+        if s == 0:
+            assert v[4] == pytest.approx(float(g["personal0"]), rel=1e-5, abs=1e-9)
+    t = e.tables()
+    for k in ("P", "R", "Cat", "G"):
+        assert_close(t[k], g[k], what=f"golden {learner}/{mode} {k}")
+
+
+# ---------------------------------------------------------------- evaluation
+def test_sampled_eval_matches_evaluate_py_semantics():
+    p = Problem(120, 400, 7, 64, seed=47)
+    e = make_engine(p)
+    train, tr, tn = synth.make_reference_dataset(120, 400, seed=5)
+    tn["3"][60] = tr["3"][0]                # duplicate of the positive among the negatives
+    tn["4"][70] = tn["4"][55]               # duplicate negative
+    tn["5"] = tn["5"][:80]                  # ragged: only 30 eval negatives
+    d2c, _ = synth.reference_side_maps(p.item_cats, p.user_labels)
+    from foodrec_b200.evaluate import build_candidates
+    users, cand, ncand, ccats = build_candidates(tr, tn, d2c)
+    ids, rank, sc = e.eval_sampled_topk(users, cand, ncand, 10, cand_cats=ccats, return_scores=True)
+    ids, rank, sc = ids.cpu().numpy(), rank.cpu().numpy(), sc.cpu().numpy()
+    om = p.oracle(OHyper(), dtype=np.float64)
+    hits, ndcgs, ranks = evaluate_oracle.evaluate_model(om, tr, tn, 10, p.item_cats)
+    n_checked = 0
+    for r, u in enumerate(tr):
+        c = cand[r, :ncand[r]]
+        ref = om.scores(np.full(len(c), int(u)), c, p.item_cats[c])
+        assert_close(sc[r, :ncand[r]], ref, what=f"eval scores user {u}")
+        # ids are bit-exact whenever the oracle's ranking is not decided by a sub-tolerance gap
+        top = sorted(set(ref), reverse=True)[:11]
+        if len(top) > 1 and np.min(-np.diff(top)) < 1e-6 * np.abs(ref).max():
+            continue
+        assert list(ids[r][ids[r] >= 0]) == ranks[r], f"user {u}"
+        assert (rank[r] >= 0) == bool(hits[r])
+        n_checked += 1
+    assert n_checked > 100
+    # dict semantics on exact ties / duplicates, independent of rounding:
+    assert len(set(ids[3][ids[3] >= 0])) == len(ids[3][ids[3] >= 0])
+
+
+def test_sampled_eval_tie_break_is_insertion_order():
+    """All-equal scores (zero tables): nlargest keeps insertion order (evaluate.py:63)."""
+    p = Problem(4, 100, 3, 16, seed=1)
+    p.tb.P[:] = 0
+    e = make_engine(p)
+    cand = np.array([[9, 3, 7, 3, 1, 9, 2, 8, 6, 5, 4, 0]], np.int32)
+    ids, rank = e.eval_sampled_topk(np.array([2]), cand, np.array([12]), 5, cand_cats=p.item_cats[cand])
+    assert list(ids.cpu().numpy()[0]) == [9, 3, 7, 1, 2] and int(rank.cpu()[0]) == 0
+
+
+# ---------------------------------------------------------------- reference driver protocol
+def test_session_protocol_runs_the_reference_loop():
+    """Train_recommender.py:156-205 + evaluate.py through the shim, with the reference's own
+    feed types (python lists, str user ids, [4][1] category nesting)."""
+    import foodrec_b200.tf_shim as tf
+    from foodrec_b200 import Model, evaluate_model
+    p = Problem(40, 300, 7, 32, seed=53)
+    train, tr, tn = synth.make_reference_dataset(40, 300, seed=6, pos_range=(3, 12))
+    d2c, u2l = synth.reference_side_maps(p.item_cats, p.user_labels)
+    ui, ii, y, c, ws, ul = synth.get_train_instances(train, tn, d2c, u2l, seed=1)
+    args = args_ns(p, learner="adam", lr=0.001, batch_size=128)
+    om = p.oracle(OHyper(learner="adam", lr=0.001))
+    with tf.Session(config=tf.ConfigProto()) as sess:
+        model = Model(args, p.tb.P, p.tb.R, p.tb.Cat, p.tb.G)
+        sess.run(tf.global_variables_initializer())
+        assert sess.run(model.epoch_step) == 0
+        nb = len(ui) // 128
+        for b in range(min(nb, 4)):
+            start, end = b * 128, (b + 1) * 128
+            if b == 0:                                    # :170-187
+                for mini in range(16):
+                    s0, s1 = start + mini * 8, start + (mini + 1) * 8
+                    feed = {model.user_input: ui[s0:s1], model.item_input: ii[s0:s1], model.labels: y[s0:s1],
+                            model.categories: c[s0:s1], model.user_one_hot_label: ul[s0:s1],
+                            model.write_sign: ws[s0:s1], model.dropout_keep_prob: 0.8, model.is_training_flag: True}
+                    loss, lr, personal, general, _ = sess.run(
+                        [model.loss_value, model.learning_rate, model.personal, model.general, model.train_op], feed)
+                    o = om.train_step(dict(user_input=np.asarray(ui[s0:s1]).astype(np.int32), item_input=ii[s0:s1],
+                                           labels=y[s0:s1], categories=c[s0:s1], write_sign=ws[s0:s1],
+                                           user_one_hot_label=ul[s0:s1]), write_personal=True)
+                    assert loss == pytest.approx(o["loss"], rel=1e-5) and personal == pytest.approx(o["personal"], rel=1e-5, abs=1e-9)
+            else:                                         # :189-199
+                feed = {model.user_input: ui[start:end], model.item_input: ii[start:end], model.labels: y[start:end],
+                        model.categories: c[start:end], model.user_one_hot_label: ul[start:end],
+                        model.write_sign: ws[start:end], model.dropout_keep_prob: 0.8, model.is_training_flag: True}
+                loss, lr, general, _ = sess.run([model.loss_value, model.learning_rate, model.general, model.train_op], feed)
+                o = om.train_step(dict(user_input=np.asarray(ui[start:end]).astype(np.int32), item_input=ii[start:end],
+                                       labels=y[start:end], categories=c[start:end], write_sign=ws[start:end],
+                                       user_one_hot_label=ul[start:end]))
+                assert loss == pytest.approx(o["loss"], rel=1e-5) and general == pytest.approx(o["general"], rel=1e-5, abs=1e-9)
+                assert lr == np.float32(0.001)
+        sess.run(model.epoch_increment)
+        assert sess.run(model.epoch_step) == 1
+        hits, ndcgs = evaluate_model(sess, model, tr, tn, 10, d2c)
+        oh, on, _ = evaluate_oracle.evaluate_model(om, tr, tn, 10, p.item_cats)
+        assert len(hits) == len(tr) and abs(np.mean(hits) - np.mean(oh)) <= 2 / len(tr)
+        assert abs(np.mean(ndcgs) - np.mean(on)) <= 2 / len(tr)
+        compare_tables(model.engine, om, what="session ")
+        # checkpoint round trip (Train_recommender.py:145-151,216-223)
+        import tempfile
+        d = tempfile.mkdtemp() + "/"
+        saver = tf.train.Saver()
+        saver.save(sess, d + "model.ckpt", global_step=0)
+        assert os.path.exists(d + "checkpoint")
+        before = model.engine.tables()
+        model.engine.P.zero_()
+        saver.restore(sess, tf.train.latest_checkpoint(d))
+        np.testing.assert_array_equal(model.engine.tables()["P"], before["P"])
+        assert sess.run(model.epoch_step) == 1 and model.engine.step == om.t
+
+
+# ---------------------------------------------------------------- full-size properties (cfg2)
+def test_cfg2_full_size_properties():
+    """BASELINE cfg2 (1M users / 200k recipes / D=128) is too big for the numpy oracle;
+    check size-independent properties instead: (1) lr=0 leaves P/R/Cat untouched while G
+    moves by exactly the write; (2) a step followed by the same step with flipped labels and
+    write signs restores G (linearity of Write_Memory); (3) only touched rows change;
+    (4) the loss of an all-zero model is ln 2."""
+    from foodrec_b200 import Engine, Hyper
+    U, I, L, D, B = 1_000_000, 200_000, 95, 128, 65536
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    P = torch.randn((U, 5, D), device="cuda", generator=g) * 0.1
+    R = torch.randn((I, D), device="cuda", generator=g) * 0.1
+    Cat = torch.randn((4, D), device="cuda", generator=g) * 0.1
+    G = torch.randn((L, 5, D), device="cuda", generator=g) * 0.1
+    ic = synth.make_item_categories(I); ul = synth.make_user_labels(U, L)
+    e = Engine(Hyper(learner="sgd", lr=0.0), P, R, Cat, G, max_rows=2 * B, item_cats=ic, user_labels=ul)
+    rng = np.random.default_rng(0)
+    users = rng.integers(0, U, B).astype(np.int32); items = synth.zipf_items(rng, I, B)
+    y = (rng.random(B) < 0.5).astype(np.float32)
+    G0 = e.G.clone(); P0 = e.P.clone()
+    e.train_step(users, items, labels=y); v = e.read_scalars()
+    assert torch.equal(e.P, P0) and not torch.equal(e.G, G0)
+    assert int(v[6]) == len(np.unique(users)) and int(v[7]) == len(np.unique(items))
+    e.train_step(users, items, labels=1 - y); e.read_scalars()
+    assert_close(e.G.cpu().numpy(), G0.cpu().numpy(), what="G after +/- write")
+    del e, P0
+    e = Engine(Hyper(learner="adam", lr=0.01), P, R, Cat, G, max_rows=2 * B, item_cats=ic, user_labels=ul)
+    P0 = e.P.clone()
+    e.train_step(users, items, labels=y); e.read_scalars(); e.flush()
+    changed = (e.P != P0).reshape(U, -1).any(1).cpu().numpy()
+    touched = np.zeros(U, bool); touched[users] = True
+    assert (changed <= touched).all() and changed.sum() > 0.99 * touched.sum()
+    del e, P0
+    z = lambda t: torch.zeros_like(t)
+    e = Engine(Hyper(learner="sgd", lr=0.1), z(P), z(R), z(Cat), z(G), max_rows=2 * B, item_cats=ic, user_labels=ul)
+    e.train_step(users, items, labels=y)
+    assert e.read_scalars()[0] == pytest.approx(np.log(2.0), rel=1e-6)
