@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- BPR train triples/s (+ top-K users/s) of the Recommender hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host cores)
+
+Workload (BASELINE.json configs[1]): 1M users / 200k recipes / 95 labels, D=128, BPR
+triples (uniform users, Zipf(1.05) positives, uniform negatives), Adam with TF-1.x
+semantics (lazy-exact), global-norm clip 5.0, General_Memory write every step.
+One step = one fr_train_step over B triples.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = dict(U=1_000_000, I=200_000, L=95, D=128)
+SMALL = dict(U=20_000, I=5_000, L=95, D=128)       # --small: functional check of the harness only
+METRIC, UNIT = "bpr_train_triples_per_sec", "triples/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def make_batches(cfg, B, nb, seed, item_cats, lab_csr, dense):
+    """nb BPR batches: ids only, plus (dense) the reference-format feed tensors."""
+    import synth_data as synth
+    out = []
+    for k in range(nb):
+        rng = np.random.default_rng(seed + k)
+        users = rng.integers(0, cfg["U"], B).astype(np.int32)
+        pos = synth.zipf_items(rng, cfg["I"], B)
+        neg = rng.integers(0, cfg["I"], B).astype(np.int32)
+        neg[neg == pos] = (neg[neg == pos] + 1) % cfg["I"]
+        items = np.stack([pos, neg], 1).reshape(-1).copy()
+        b = dict(users=users, items=items)
+        if dense:
+            b["cats"] = item_cats[items].copy()                                   # [2B,4]  categories
+            b["ulab"] = synth.csr_rows_dense(lab_csr[0], lab_csr[1], users, cfg["L"])   # [B,L] user_one_hot_label
+        out.append(b)
+    return out
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def run_reference(args, cfg, B):
+    """The reference's CPU implementation of the path = the oracle's torch-CPU port
+    (TensorFlow 1.x cannot be installed here: oracle/cpu_port.py header), on all host
+    cores, on a bounded sample: `steps` BPR steps of B triples at the same table sizes."""
+    import torch
+    import synth_data as synth
+    from oracle.cpu_port import CpuPort
+    from oracle.recommender_oracle import Hyper
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1)
+    U, I, L, D = cfg["U"], cfg["I"], cfg["L"], cfg["D"]
+    P = torch.randn((U, 5, D), generator=g) * 0.1; R = torch.randn((I, D), generator=g) * 0.1
+    Cat = torch.randn((4, D), generator=g) * 0.1; G = torch.randn((L, 5, D), generator=g) * 0.1
+    item_cats = synth.make_item_categories(I)
+    lab = synth.make_user_label_csr(U, L)
+    port = CpuPort(P, R, Cat, G, Hyper(learner="adam", lr=0.001), threads=cores)
+    del P
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    bs = make_batches(cfg, B, steps + warm, 777, item_cats, lab, dense=True)
+    T = lambda x, dt=None: torch.as_tensor(x if dt is None else x.astype(dt))
+    t0 = None
+    for k, b in enumerate(bs):
+        if k == warm:
+            t0 = time.perf_counter()
+        it = T(b["items"], np.int64)
+        port.train_step_bpr(T(b["users"], np.int64), it[0::2], it[1::2], T(b["cats"][0::2]), T(b["cats"][1::2]), T(b["ulab"]))
+    dt = time.perf_counter() - t0
+    val = B * steps / dt
+    sample = f"{steps} steps of {B} BPR triples at full table size after {warm} warm-up (dense TF-1.x Adam sweep)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, B), "batch_triples": B, "optimizer": "adam (TF-1.x dense sweep)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle restatement on torch-CPU, not TensorFlow (TF 1.x is not installable in this image)"}))
+
+
+def workload_name(cfg, B):
+    return (f"cfg2: {cfg['U']} users x {cfg['I']} recipes x {cfg['L']} labels, D={cfg['D']}, "
+            f"BPR B={B} triples/step, shuffled users, Zipf(1.05) positives")
+
+
+def cpu_baseline_leg(cfg, B, budget_steps=3):
+    """cpu_baseline of the default run: the same port, bounded to a few steps."""
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(budget_steps),
+                          "--warmup", "1", "--batch", str(B)] + (["--small"] if cfg is SMALL else []),
+                         capture_output=True, text=True, timeout=900,
+                         env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    for line in out.stdout.splitlines()[::-1]:
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    return {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
+            "sample": "failed: " + out.stderr[-300:]}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, cfg, B):
+    import torch
+    import torch.distributed as dist
+    from foodrec_b200 import Engine, Hyper, _lib as L
+    import synth_data as synth      # input generator only; nothing under oracle/ runs in this arm
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    U, I, Lb, D = cfg["U"], cfg["I"], cfg["L"], cfg["D"]
+    g = torch.Generator(device=dev); g.manual_seed(1 + rank)
+    P = torch.randn((U, 5, D), device=dev, generator=g) * 0.1; R = torch.randn((I, D), device=dev, generator=g) * 0.1
+    Cat = torch.randn((4, D), device=dev, generator=g) * 0.1; G = torch.randn((Lb, 5, D), device=dev, generator=g) * 0.1
+    item_cats = synth.make_item_categories(I)
+    lab = synth.make_user_label_csr(U, Lb)
+    eng = Engine(Hyper(learner="adam", lr=0.001), P, R, Cat, G, device=dev, max_rows=2 * B,
+                 adam_mode="lazy_exact", item_cats=item_cats, user_label_csr=lab,
+                 max_label_entries=2 * B * Lb if B * Lb < (1 << 26) else 2 * B * 8)
+    del P
+    NB = 8
+    host = make_batches(cfg, B, NB, 1000 + 100 * rank, item_cats, lab, dense=True)
+    dev_b = [(torch.as_tensor(b["users"]).to(dev), torch.as_tensor(b["items"]).to(dev)) for b in host]
+
+    def step(k):
+        u, it = dev_b[k % NB]
+        eng._step_dev(L.FR_BPR, B, u, it, None, None, None, None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # steady state for lazy Adam: most rows have live moments before anything is timed
+    preroll = args.preroll
+    for k in range(preroll):
+        step(k)
+    for k in range(args.warmup):
+        step(preroll + k)
+    v = eng.read_scalars()
+    uniq_users, uniq_items = float(v[L.FR_OUT_UNIQ_USERS]), float(v[L.FR_OUT_UNIQ_ITEMS])
+    # ---- timed region: device timing, inputs resident in HBM
+    clocks = ClockSampler(local); clocks.start()
+    launches0 = eng.lib.fr_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        step(k)
+    ev1.record()
+    barrier()
+    launches = eng.lib.fr_launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    clk = clocks.stop()
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- per-kernel timing (CUDA events inside fr_train_step, on its stream), same steps again
+    eng.timing_enable(True)
+    for k in range(args.steps):
+        step(k)
+    torch.cuda.synchronize()
+    phases, nst = eng.timing_read()
+    eng.timing_enable(False)
+    peak, peak_src = peaks()
+    adam_k = 6
+    alg = {   # algorithmic bytes per launch, SURVEY 8(d) (fp32)
+        "fwd": B * (28 * D + 16),
+        "user_chunk": uniq_users * adam_k * 20 * D,
+        "item_chunk": uniq_items * adam_k * 4 * D,
+    }
+    kern = {k: {"ms": phases[k], "alg_bytes": alg[k], "gbs": alg[k] / (phases[k] * 1e-3) / 1e9 if phases[k] > 0 else None}
+            for k in alg}
+    dom = max(alg, key=lambda k: phases[k])
+    roofline = {"bound": "hbm", "kernel": {"fwd": "fwd_train_kernel", "user_chunk": "seg_chunk_kernel<UserPol>",
+                                           "item_chunk": "seg_chunk_kernel<ItemPol>"}[dom],
+                "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
+                "peak_source": peak_src, "traffic": None,
+                "alg_bytes_per_launch": alg[dom], "ms_per_launch": phases[dom]}
+
+    # ---- e2e: reference-format dense feed from pinned host memory through the C ABI host entry point
+    pin = lambda x: torch.as_tensor(np.ascontiguousarray(x)).pin_memory()
+    hb = [dict(users=pin(b["users"]), items=pin(b["items"]), cats=pin(b["cats"]), ulab=pin(b["ulab"])) for b in host]
+    h2d = sum(int(t.numel() * t.element_size()) for t in hb[0].values())
+
+    def estep(k, dense=True):
+        b = hb[k % NB]
+        return eng.train_step_host(L.FR_BPR, B, b["users"], b["items"], b["cats"] if dense else None, None, None,
+                                   b["ulab"] if dense else None)
+
+    def e2e_run(dense):
+        for k in range(3):
+            estep(k, dense)
+        barrier()
+        t0 = time.perf_counter()
+        loss_sum = 0.0
+        for k in range(args.steps):
+            out = estep(k, dense)
+            torch.cuda.current_stream().synchronize()      # the step's loss is read on the host every step
+            loss_sum += float(out[L.FR_OUT_LOSS])
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        return world * B * args.steps / dt, loss_sum / args.steps
+    e2e_val, e2e_loss = e2e_run(True)
+    e2e_cval, _ = e2e_run(False)
+
+    # ---- top-K users/s: sampled evaluation (51 candidates, K=10: evaluate.py) over NU users
+    NU = min(U, 1 << 20)
+    rng = np.random.default_rng(5)
+    eu = torch.as_tensor(rng.permutation(U)[:NU].astype(np.int32)).to(dev)
+    cand = torch.as_tensor(rng.integers(0, I, (NU, 51)).astype(np.int32)).to(dev)
+    nc = torch.full((NU,), 51, dtype=torch.int32, device=dev)
+    eng.eval_sampled_topk(eu, cand, nc, 10)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eng.eval_sampled_topk(eu, cand, nc, 10); e1.record(); torch.cuda.synchronize()
+    eval_ms = e0.elapsed_time(e1)
+    eval_alg = NU * (20 * D + 51 * 4 * D + 51 * 12)
+
+    if rank == 0:
+        cpu = cpu_baseline_leg(cfg, B) if (world == 1 and not args.no_cpu) else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, B), "batch_triples": B, "optimizer": "adam (TF-1.x semantics, lazy-exact)",
+                       "l2": "per-step working set (~%.1f GB of table rows) >> 126 MB L2; %d distinct batches cycled" % (
+                           (alg["fwd"] + alg["user_chunk"] + alg["item_chunk"]) / 1e9, NB),
+                       "preroll_steps": preroll,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (sharded path: see DESIGN.md)"},
+            "clocks": clk, "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": kern, "phases_ms": phases,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
+                    "feed": "reference dense feed (user_input,item_input,categories,user_one_hot_label), pinned, "
+                            "host read of the loss every step", "mean_loss": e2e_loss},
+            "e2e_compact": {"value": e2e_cval, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
+                            "feed": "ids only; dish_to_category / user labels resident on device"},
+            "topk": {"metric": "sampled_topk_users_per_sec", "value": NU / (eval_ms * 1e-3), "unit": "users/s",
+                     "candidates": 51, "K": 10, "users": NU, "ms": eval_ms,
+                     "roofline": {"bound": "hbm", "achieved": eval_alg / (eval_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": eval_alg / (eval_ms * 1e-3) / 1e9 / peak}},
+            "uniq_users_per_step": uniq_users, "uniq_items_per_step": uniq_items,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--preroll", type=int, default=40)
+    ap.add_argument("--small", action="store_true", help="tiny tables: harness check only, not a bench number")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = SMALL if args.small else CFG2
+    if args.impl == "reference":
+        run_reference(args, cfg, args.batch)
+    else:
+        run_ours(args, cfg, args.batch)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,9 @@ FR_POINTWISE, FR_BPR = 0, 1
 (FR_OUT_LOSS, FR_OUT_NORM, FR_OUT_SCALE, FR_OUT_GENERAL, FR_OUT_PERSONAL, FR_OUT_LR,
  FR_OUT_UNIQ_USERS, FR_OUT_UNIQ_ITEMS, FR_OUT_LABEL_ENTRIES, FR_OUT_OVERFLOW) = range(10)
 FR_OUT_COUNT = 12
+FR_T_NAMES = ("sort", "fwd", "finalize", "user_chunk", "user_combine", "label", "item_chunk",
+              "item_combine", "sweep", "misc")
+FR_T_COUNT = len(FR_T_NAMES)
 
 LEARNERS = {"sgd": FR_SGD, "adagrad": FR_ADAGRAD, "rmsprop": FR_RMSPROP, "adam": FR_ADAM}
 
@@ -58,6 +61,9 @@ _PROTOS = {
     "fr_train_step": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_train_step_host": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.c_int32, C.c_void_p, C.c_void_p]),
     "fr_adam_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fr_launch_count": (C.c_int64, []),
+    "fr_timing_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "fr_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "fr_eval_sampled_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

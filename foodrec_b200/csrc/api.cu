@@ -40,7 +40,25 @@ struct fr_ctx {
   uint32_t* scan_tmp = nullptr;
   // staging for fr_train_step_host
   void* stage = nullptr; size_t stage_bytes = 0;
+  // per-phase timing (fr_timing_*)
+  bool timing = false;
+  struct TimingSet { cudaEvent_t ev[FR_T_COUNT + 1]; bool used = false; };
+  std::vector<TimingSet> tsets;
+  size_t ts_next = 0;
+  double t_sum[FR_T_COUNT] = {0};
+  int64_t t_steps = 0;
 };
+
+static void timing_collect(fr_ctx* h, fr_ctx::TimingSet& ts) {
+  if (!ts.used) return;
+  cudaEventSynchronize(ts.ev[FR_T_COUNT]);
+  for (int i = 0; i < FR_T_COUNT; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ts.ev[i], ts.ev[i + 1]) == cudaSuccess) h->t_sum[i] += ms;
+  }
+  h->t_steps += 1;
+  ts.used = false;
+}
 
 static int fail(fr_ctx* h, int code, const char* fmt, ...) {
   if (h) {
@@ -135,8 +153,31 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   return FR_OK;
 }
 
+extern "C" int64_t fr_launch_count(void) { return (int64_t)fr::g_launches; }
+
+extern "C" int fr_timing_enable(fr_handle h, int32_t enable) {
+  if (!h) return FR_ERR_ARG;
+  if (enable && h->tsets.empty()) {
+    h->tsets.resize(32);
+    for (auto& ts : h->tsets)
+      for (auto& e : ts.ev) FR_CUDA(h, cudaEventCreate(&e));
+  }
+  h->timing = enable != 0;
+  return FR_OK;
+}
+
+extern "C" int fr_timing_read(fr_handle h, double* ms_sum, int64_t* n_steps, int32_t reset) {
+  if (!h || !ms_sum || !n_steps) return FR_ERR_ARG;
+  for (auto& ts : h->tsets) timing_collect(h, ts);
+  for (int i = 0; i < FR_T_COUNT; ++i) ms_sum[i] = h->t_sum[i];
+  *n_steps = h->t_steps;
+  if (reset) { for (auto& x : h->t_sum) x = 0.0; h->t_steps = 0; }
+  return FR_OK;
+}
+
 extern "C" int fr_destroy(fr_handle h) {
   if (!h) return FR_OK;
+  for (auto& ts : h->tsets) for (auto& e : ts.ev) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->stage) cudaFree(h->stage);
   if (h->pieces_personal) cudaFree(h->pieces_personal);
@@ -284,7 +325,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   if (!b->user_labels && !(h->tab.user_label_off && h->tab.user_label_idx))
     return fail(h, FR_ERR_ARG, "user_labels is NULL and no user-label CSR table");
   cudaStream_t st = (cudaStream_t)s;
-  Launch l{h->sm_count, st};
+  Launch l{h->sm_count, st, nullptr};
   const fr_tables& T = h->tab;
   const int DV = h->mc.DV, NV = h->NV;
   const int64_t step = h->step + 1;
@@ -294,6 +335,14 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   const float4* cats = (const float4*)(b->cats ? b->cats : T.item_cats);
   const int cats_by_item = b->cats ? 0 : 1;
 
+  fr_ctx::TimingSet* ts = nullptr;
+  if (h->timing) {
+    ts = &h->tsets[h->ts_next++ % h->tsets.size()];
+    timing_collect(h, *ts);
+    ts->used = true;
+  }
+#define FR_MARK(i) do { if (ts) cudaEventRecord(ts->ev[i], st); } while (0)
+  FR_MARK(FR_T_SORT);
   // 0. pre-step snapshot of Category_Embedding (every read of Cat in this step sees it)
   FR_CUDA(h, cudaMemcpyAsync(h->cat_pre, T.Cat, (size_t)4 * h->mc.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   FR_CUDA(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(uint32_t), st));
@@ -303,7 +352,14 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   const int ru = radix_sort_pairs(h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), st, h->sm_count);
   const int ri = radix_sort_pairs(h->sortI, (const uint32_t*)b->items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), st, h->sm_count);
   FR_CHECK_LAUNCH(h);
+  const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_EXACT;
+  if (lazy) {   // recipe rows of this batch must be current before anything reads them
+    launch_item_catchup(NV, h->sortI.k[ri], (uint32_t)S, (float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R,
+                        T.last_R, DV, oc, l);
+    FR_CHECK_LAUNCH(h);
+  }
 
+  FR_MARK(FR_T_FWD);
   // 2. forward, loss, per-slice norms, dCat partials, z stash
   FwdParams fp{};
   fp.P = (const float4*)T.P; fp.R = (const float4*)T.R; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B;
@@ -311,10 +367,12 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   fp.labels = b->labels; fp.a = h->mc.a; fp.oma = h->mc.oma;
   fp.g = h->g; fp.z = h->z; fp.scores = out_scores ? out_scores : h->scores;
   fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
+  fp.lazy = lazy ? 1 : 0; fp.mP = (const float4*)T.s1_P; fp.vP = (const float4*)T.s2_P; fp.lastP = T.last_P; fp.oc = oc;
   const int fgrid = fwd_train_grid(B, h->sm_count);
   launch_fwd_train(NV, group, fp, fgrid, l);
   FR_CHECK_LAUNCH(h);
 
+  FR_MARK(FR_T_FINALIZE);
   // 3. global norm -> clip scale; dense optimizer on Cat
   FinalizeParams fin{};
   fin.part_loss = h->part_loss; fin.part_nrm = h->part_nrm; fin.part_gcat = h->part_gcat; fin.nblk = fgrid;
@@ -324,8 +382,10 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   launch_finalize(fin, l);
   FR_CHECK_LAUNCH(h);
 
+  FR_MARK(FR_T_USER_CHUNK);
   // 4. Personal_Memory: segment-reduce by user + optimizer (+ personal write)
   {
+    l.mid = ts ? ts->ev[FR_T_USER_COMBINE] : nullptr;
     SegCommon c{};
     c.keys = h->sortU.k[ru]; c.perm = h->sortU.v[ru]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
     c.uniq_counter = h->counters + 0;
@@ -350,8 +410,10 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     FR_CHECK_LAUNCH(h);
   }
 
+  FR_MARK(FR_T_LABEL);
   // 5. General_Memory: label feed -> entries -> sort by label -> segment-reduce (reads pre-step R)
   {
+    l.mid = nullptr;
     LabelEmitParams ep{};
     ep.S = S; ep.group = group; ep.L = h->mc.L; ep.users = b->users;
     ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
@@ -375,8 +437,10 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     FR_CHECK_LAUNCH(h);
   }
 
+  FR_MARK(FR_T_ITEM_CHUNK);
   // 6. Recipe_Embedding: segment-reduce by recipe + optimizer
   {
+    l.mid = ts ? ts->ev[FR_T_ITEM_COMBINE] : nullptr;
     SegCommon c{};
     c.keys = h->sortI.k[ri]; c.perm = h->sortI.v[ri]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
     c.pieces = h->pieces_i; c.uniq_counter = h->counters + 1;
@@ -387,6 +451,8 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     FR_CHECK_LAUNCH(h);
   }
 
+  l.mid = nullptr;
+  FR_MARK(FR_T_SWEEP);
   // 7. TF-1.x dense Adam: every untouched row decays this step too
   if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_DENSE) {
     launch_adam_sweep((float4*)T.P, (float4*)T.s1_P, (float4*)T.s2_P, T.last_P, h->cfg.num_users, 5 * DV, oc, (int)step, l);
@@ -394,6 +460,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     FR_CHECK_LAUNCH(h);
   }
 
+  FR_MARK(FR_T_MISC);
   // 8. fetches: general = mean(G) (:219), personal = mean(P) (:218, personal steps only)
   launch_mean((const float4*)T.G, (int64_t)h->mc.L * 5 * DV, h->mean_partials, out + FR_OUT_GENERAL,
               (double)h->mc.L * 5.0 * h->mc.D, l);
@@ -407,6 +474,8 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   }
   launch_write_counters(h->counters, out, l);
   FR_CHECK_LAUNCH(h);
+  FR_MARK(FR_T_COUNT);
+#undef FR_MARK
 
   h->step = step;
   h->b1p *= h->cfg.adam_beta1;     // adam.py _finish

@@ -71,6 +71,7 @@ void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, c
   int grid = (n + 8 * FR_WARPS_PER_BLOCK - 1) / (8 * FR_WARPS_PER_BLOCK);
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   const size_t smem = (size_t)4 * mc.DV * sizeof(float4);
+  ++g_launches;
   if (mc.DV <= 32)
     fwd_score_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores);
   else
@@ -170,6 +171,7 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   int grid = (n_users + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   const size_t smem = (size_t)4 * mc.DV * sizeof(float4);
+  ++g_launches;
   if (mc.DV <= 32)
     eval_sampled_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, mc.a, mc.oma, users, cand, n_cand, n_users,
                                                              stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores);

@@ -67,7 +67,9 @@ struct StepView {
   float* out;      // device scalars FR_OUT_*
 };
 
-struct Launch { int sm_count; cudaStream_t st; };
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
+
+struct Launch { int sm_count; cudaStream_t st; cudaEvent_t mid = nullptr; /* recorded between chunk and combine */ };
 
 void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                       const int32_t* users, const int32_t* items, const float4* cats,

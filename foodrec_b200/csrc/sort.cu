@@ -15,6 +15,8 @@
 
 namespace fr {
 
+unsigned long long g_launches = 0;
+
 __device__ __forceinline__ uint32_t resolve_n(const uint32_t* n_dev, uint32_t n_host) {
   if (n_dev) { const uint32_t v = *n_dev; return v < n_host ? v : n_host; }
   return n_host;
@@ -191,12 +193,14 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t*
   }
   if (n <= 4 * SCAN_TILE) {
     scan_single_kernel<<<1, SCAN_THREADS, 0, st>>>(in, out, n, total_out);
+    g_launches += 1;
     return;
   }
   const uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
   scan_tile_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp);
   scan_single_kernel<<<1, SCAN_THREADS, 0, st>>>(tmp, tmp, nb, total_out);
   scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, tmp);
+  g_launches += 3;
 }
 
 int radix_sort_pairs(SortBufs& bufs, const uint32_t* keys_in, uint32_t n_host,
@@ -215,6 +219,7 @@ int radix_sort_pairs(SortBufs& bufs, const uint32_t* keys_in, uint32_t n_host,
     exclusive_scan_u32(bufs.tile_hist, bufs.tile_hist, RADIX_BINS * ntiles, bufs.scan_tmp, nullptr, st);
     radix_scatter_kernel<<<grid, FR_THREADS, 0, st>>>(kin, vin, bufs.k[dst], bufs.v[dst], n_host, n_dev,
                                                       shift, ntiles, bufs.tile_hist);
+    g_launches += 2;
     kin = bufs.k[dst];
     vin = bufs.v[dst];
     dst ^= 1;

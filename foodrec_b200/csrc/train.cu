@@ -141,6 +141,7 @@ void launch_prep_rows(int mode, int B, const int32_t* users, const float* labels
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   if (grid < 1) grid = 1;
   prep_rows_kernel<<<grid, 256, 0, l.st>>>(mode, B, users, labels, ws_in, ukeys, ws_row);
+  ++g_launches;
 }
 
 // ------------------------------------------------------------------ forward + loss + norms
@@ -172,6 +173,24 @@ fwd_train_kernel(const FwdParams p) {
     float4 pr[5][NV];
 #pragma unroll
     for (int s = 0; s < 5; ++s) load_row<NV>(pr[s], p.P + ((size_t)u * 5 + s) * DV, DV, lane);
+    if (p.lazy) {
+      const int from = p.lastP[u] + 1, to = p.oc.step - 1;
+      if (from <= to) {
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+          float4 mm[NV], vv[NV];
+          load_row<NV>(mm, p.mP + ((size_t)u * 5 + s) * DV, DV, lane);
+          load_row<NV>(vv, p.vP + ((size_t)u * 5 + s) * DV, DV, lane);
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            adam_decay(pr[s][k].x, mm[k].x, vv[k].x, from, to, p.oc);
+            adam_decay(pr[s][k].y, mm[k].y, vv[k].y, from, to, p.oc);
+            adam_decay(pr[s][k].z, mm[k].z, vv[k].z, from, to, p.oc);
+            adam_decay(pr[s][k].w, mm[k].w, vv[k].w, from, to, p.oc);
+          }
+        }
+      }
+    }
     float4 rr[GROUP][NV], pcn[GROUP][NV];   // R rows, pooledCat (normalised)
     float4 mm[GROUP];
     float sc[GROUP], nn[GROUP], nzq[GROUP], nRq[GROUP], npcq[GROUP];
@@ -305,6 +324,7 @@ void launch_fwd_train(int NV, int group, const FwdParams& p, int grid, const Lau
   if (NV == 1) { if (group == 1) FR_FWD(1, 1); else FR_FWD(1, 2); }
   else         { if (group == 1) FR_FWD(2, 1); else FR_FWD(2, 2); }
 #undef FR_FWD
+  ++g_launches;
 }
 
 // ------------------------------------------------------------------ finalize
@@ -382,6 +402,7 @@ finalize_kernel(const FinalizeParams p) {
 
 void launch_finalize(const FinalizeParams& p, const Launch& l) {
   finalize_kernel<<<1, FR_THREADS, 0, l.st>>>(p);
+  ++g_launches;
 }
 
 // ------------------------------------------------------------------ segment reduce skeleton
@@ -724,7 +745,9 @@ static void launch_seg(const SegCommon& c, const Pol& pol, int DV, bool needs_ca
   if (grid > cap) grid = cap;
   const size_t smem = needs_cat ? (size_t)4 * DV * sizeof(float4) : 0;
   seg_chunk_kernel<Pol><<<grid, FR_THREADS, smem, l.st>>>(c, pol);
+  if (l.mid) cudaEventRecord(l.mid, l.st);
   seg_combine_kernel<Pol><<<grid, FR_THREADS, 0, l.st>>>(c, pol);
+  g_launches += 2;
 }
 
 void launch_user_pass(int NV, int personal, const SegCommon& c, const UserPolParams& p, const Launch& l) {
@@ -815,9 +838,11 @@ static int warp_grid(int nwarps_needed, int sm_count) {
 }
 void launch_label_count(const LabelEmitParams& p, const Launch& l) {
   label_count_kernel<<<warp_grid(p.S, l.sm_count), FR_THREADS, 0, l.st>>>(p);
+  ++g_launches;
 }
 void launch_label_emit(const LabelEmitParams& p, const Launch& l) {
   label_emit_kernel<<<warp_grid(p.S, l.sm_count), FR_THREADS, 0, l.st>>>(p);
+  ++g_launches;
 }
 
 // ------------------------------------------------------------------ Adam sweep / fill / mean
@@ -839,6 +864,61 @@ adam_sweep_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __re
     __stcs(var + i, x); __stcs(m + i, mm); __stcs(v + i, vv);
   }
 }
+// lazy-exact Adam: the batch's unique recipe rows are brought to step-1 before anything
+// reads them (forward, dP accumulation, Write_Memory all read R).  keys = recipe ids of the
+// item rows, sorted; the warp that sees a run's head owns that row.
+template <int NV>
+__global__ void __launch_bounds__(FR_THREADS)
+item_catchup_kernel(const uint32_t* __restrict__ keys, uint32_t n, float4* __restrict__ R,
+                    float4* __restrict__ m, float4* __restrict__ v, int32_t* __restrict__ last,
+                    int DV, const OptConsts oc) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const uint32_t nw = gridDim.x * FR_WARPS_PER_BLOCK;
+  const uint32_t nchunks = (n + 31) >> 5;
+  const int to = oc.step - 1;
+  for (uint32_t chunk = gw; chunk < nchunks; chunk += nw) {
+    const uint32_t base = chunk << 5;
+    const bool valid = base + lane < n;
+    const uint32_t key = valid ? keys[base + lane] : 0xffffffffu;
+    const uint32_t prevKey = base > 0 ? keys[base - 1] : 0u;
+    const uint32_t up = __shfl_up_sync(FR_FULL, key, 1);
+    const bool head = valid && (lane == 0 ? (base == 0 || prevKey != key) : (up != key));
+    uint32_t hm = __ballot_sync(FR_FULL, head);
+    while (hm) {
+      const int e = __ffs(hm) - 1;
+      hm &= hm - 1;
+      const uint32_t k = __shfl_sync(FR_FULL, key, e);
+      const int from = last[k] + 1;
+      __syncwarp();
+      if (from > to) continue;
+      float4 x[NV], mm[NV], vv[NV];
+      load_row<NV>(mm, m + (size_t)k * DV, DV, lane);
+      load_row<NV>(vv, v + (size_t)k * DV, DV, lane);
+      load_row<NV>(x, R + (size_t)k * DV, DV, lane);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        adam_decay(x[q].x, mm[q].x, vv[q].x, from, to, oc); adam_decay(x[q].y, mm[q].y, vv[q].y, from, to, oc);
+        adam_decay(x[q].z, mm[q].z, vv[q].z, from, to, oc); adam_decay(x[q].w, mm[q].w, vv[q].w, from, to, oc);
+      }
+      store_row<NV>(R + (size_t)k * DV, x, DV, lane);
+      store_row<NV>(m + (size_t)k * DV, mm, DV, lane);
+      store_row<NV>(v + (size_t)k * DV, vv, DV, lane);
+      if (lane == 0) last[k] = to;
+    }
+  }
+}
+void launch_item_catchup(int NV, const uint32_t* keys, uint32_t n, float4* R, float4* m, float4* v,
+                         int32_t* last, int DV, const OptConsts& oc, const Launch& l) {
+  const uint32_t nchunks = (n + 31) / 32;
+  if (nchunks == 0) return;
+  int grid = (int)((nchunks + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
+  if (grid > l.sm_count * 16) grid = l.sm_count * 16;
+  if (NV == 1) item_catchup_kernel<1><<<grid, FR_THREADS, 0, l.st>>>(keys, n, R, m, v, last, DV, oc);
+  else item_catchup_kernel<2><<<grid, FR_THREADS, 0, l.st>>>(keys, n, R, m, v, last, DV, oc);
+  ++g_launches;
+}
+
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t val) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = val;
 }
@@ -849,6 +929,7 @@ void launch_adam_sweep(float4* var, float4* m, float4* v, int32_t* last, int64_t
   int64_t grid = (n4 + 255) / 256;
   if (grid > (int64_t)l.sm_count * 16) grid = (int64_t)l.sm_count * 16;
   adam_sweep_kernel<<<(int)grid, 256, 0, l.st>>>(var, m, v, last, n4, rowDV, oc, target_step);
+  ++g_launches;
   launch_fill_i32(last, nrows, target_step, l);
 }
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, const Launch& l) {
@@ -856,6 +937,7 @@ void launch_fill_i32(int32_t* p, int64_t n, int32_t v, const Launch& l) {
   int64_t grid = (n + 255) / 256;
   if (grid > (int64_t)l.sm_count * 8) grid = (int64_t)l.sm_count * 8;
   fill_i32_kernel<<<(int)grid, 256, 0, l.st>>>(p, n, v);
+  ++g_launches;
 }
 
 // mean of a table (reduce_mean, :218-219): fixed grid, double partials, fixed-order final sum.
@@ -889,6 +971,7 @@ void launch_mean(const float4* x, int64_t n4, double* partials, float* out_slot,
   if (nb < 1) nb = 1;
   mean_partial_kernel<<<(int)nb, 256, 0, l.st>>>(x, n4, partials);
   mean_final_kernel<<<1, 32, 0, l.st>>>(partials, (int)nb, count, out_slot);
+  g_launches += 2;
 }
 
 __global__ void write_counters_kernel(const uint32_t* counters, float* out) {
@@ -897,6 +980,7 @@ __global__ void write_counters_kernel(const uint32_t* counters, float* out) {
 }
 void launch_write_counters(const uint32_t* counters, float* out, const Launch& l) {
   write_counters_kernel<<<1, 1, 0, l.st>>>(counters, out);
+  ++g_launches;
 }
 
 }  // namespace fr

@@ -13,6 +13,9 @@ struct FwdParams {
   float a, oma;
   float* g; float4* z; float* scores;
   float *part_loss, *part_nrm; float4* part_gcat;   // one slot per block
+  // lazy-exact Adam: P[u] in memory may be stale; the forward replays the skipped decay
+  // steps last+1..step-1 in registers from (m, v) so that it scores the row TF would see
+  int lazy; const float4 *mP, *vP; const int32_t* lastP; OptConsts oc;
 };
 
 struct FinalizeParams {
@@ -77,6 +80,8 @@ void launch_label_emit(const LabelEmitParams& p, const Launch& l);
 void launch_adam_sweep(float4* var, float4* m, float4* v, int32_t* last, int64_t nrows, int rowDV,
                        const OptConsts& oc, int target_step, const Launch& l);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, const Launch& l);
+void launch_item_catchup(int NV, const uint32_t* keys, uint32_t n, float4* R, float4* m, float4* v,
+                         int32_t* last, int DV, const OptConsts& oc, const Launch& l);
 void launch_mean(const float4* x, int64_t n4, double* partials, float* out_slot, double count, const Launch& l);
 void launch_write_counters(const uint32_t* counters, float* out, const Launch& l);
 

@@ -44,7 +44,8 @@ def _ptr(t):
 
 class Engine:
     def __init__(self, hyper: Hyper, P, R, Cat, G, device="cuda:0", max_rows=1 << 16,
-                 max_label_entries=None, adam_mode="lazy_exact", item_cats=None, user_labels=None):
+                 max_label_entries=None, adam_mode="lazy_exact", item_cats=None, user_labels=None,
+                 user_label_csr=None):
         self.lib = L.lib()                       # raises if the .so is missing
         if not torch.cuda.is_available():
             raise RuntimeError("foodrec_b200 needs a CUDA device (no CPU fallback)")
@@ -86,9 +87,15 @@ class Engine:
             self.lab_off = torch.as_tensor(off).to(self.device)
             self.lab_idx = torch.as_tensor(cols.astype(np.int32)).to(self.device)
             self.max_labels_per_user = int(cnt.max()) if cnt.size else 1
+        elif user_label_csr is not None:   # (offsets [U+1], label ids [nnz]) built by the caller
+            off, idx = (np.asarray(x, np.int32) for x in user_label_csr)
+            assert off.shape == (self.U + 1,) and off[-1] == idx.shape[0]
+            self.lab_off = torch.as_tensor(off).to(self.device)
+            self.lab_idx = torch.as_tensor(idx).to(self.device)
+            self.max_labels_per_user = int(np.diff(off).max())
         self.max_rows = int(max_rows)
         if max_label_entries is None:
-            max_label_entries = self.max_rows * (self.max_labels_per_user if user_labels is not None else min(self.Lb, 16))
+            max_label_entries = self.max_rows * (self.max_labels_per_user if self.lab_off is not None else min(self.Lb, 16))
         self.max_label_entries = int(min(max_label_entries, 2**31 - 1))
         cfg = L.fr_config(self.D, self.U, self.I, self.Lb, self.learner, self.adam_mode, self.max_rows,
                           self.max_label_entries, hyper.lr, hyper.high_level_score_coefficient,
@@ -203,6 +210,17 @@ class Engine:
             raise L.FoodRecError(f"label feed has {int(v[L.FR_OUT_LABEL_ENTRIES])} non-zeros > "
                                  f"max_label_entries={self.max_label_entries}; General_Memory write truncated")
         return v
+
+    def timing_enable(self, on=True):
+        L.check(self.handle, self.lib.fr_timing_enable(self.handle, int(bool(on))))
+
+    def timing_read(self, reset=True):
+        """{phase: mean ms per step} from CUDA events recorded on the step's stream."""
+        ms = (C.c_double * L.FR_T_COUNT)()
+        n = C.c_int64()
+        L.check(self.handle, self.lib.fr_timing_read(self.handle, ms, C.byref(n), int(bool(reset))))
+        k = max(n.value, 1)
+        return {name: ms[i] / k for i, name in enumerate(L.FR_T_NAMES)}, n.value
 
     def flush(self):
         """Lazy-exact Adam: bring every row to the current step before the tables are read."""

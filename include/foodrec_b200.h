@@ -127,6 +127,17 @@ int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_personal,
 int fr_train_step_host(fr_handle h, const fr_batch* host_batch, int32_t write_personal,
                        float* host_out_scalars, fr_stream s);
 
+/* Per-phase device time of fr_train_step, measured with CUDA events recorded on the
+ * step's stream (the measurement bench.py's roofline uses).  fr_timing_read waits for
+ * the outstanding events and returns, per phase, the summed milliseconds over n_steps. */
+enum { FR_T_SORT = 0, FR_T_FWD = 1, FR_T_FINALIZE = 2, FR_T_USER_CHUNK = 3, FR_T_USER_COMBINE = 4,
+       FR_T_LABEL = 5, FR_T_ITEM_CHUNK = 6, FR_T_ITEM_COMBINE = 7, FR_T_SWEEP = 8, FR_T_MISC = 9,
+       FR_T_COUNT = 10 };
+/* number of CUDA kernels this library has launched in this process (bench.py gpu_launches) */
+int64_t fr_launch_count(void);
+int fr_timing_enable(fr_handle h, int32_t enable);
+int fr_timing_read(fr_handle h, double* ms_sum /* [FR_T_COUNT] */, int64_t* n_steps, int32_t reset);
+
 /* Bring every row of P and R to the current step (LAZY_EXACT); no-op otherwise.
  * Must precede any read of the tables by the caller (eval, checkpoint). */
 int fr_adam_flush(fr_handle h, fr_stream s);
