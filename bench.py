@@ -45,28 +45,46 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Started before the warm-up (nvidia-smi needs ~0.5 s to produce its first line);
+        mark_begin/mark_end bracket the timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        ok = lambda r: len(r) >= 7 and r[0].replace(".", "").isdigit()
+        inside = [r for t, r in self.rows if ok(r) and self.t0 is not None and self.t0 <= t <= self.t1 + 0.02]
+        window = "timed region"
+        if len(inside) < 3:      # region shorter than the sampling period: use the whole loaded span
+            lo = (self.t0 or 0) - 1.0
+            inside = [r for t, r in self.rows if ok(r) and lo <= t <= (self.t1 or 1e18) + 0.05] or \
+                     [r for _, r in self.rows if ok(r)]
+            window = "pre-roll + warm-up + timed region (the 1 s up to the end of the timed region)"
+        sm = [float(r[0]) for r in inside]
+        mx = [float(r[1]) for r in inside]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k] == "Active" for r in inside)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "power_w_max": max((float(r[2]) for r in inside), default=None),
+                "samples": len(sm), "window": window, "reasons": reasons}
 
 
 def make_batches(cfg, B, nb, seed, item_cats, lab_csr, dense):
@@ -160,6 +178,7 @@ def run_ours(args, cfg, B):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    clocks = ClockSampler(local); clocks.start()      # early: nvidia-smi takes ~1 s to emit its first sample
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     U, I, Lb, D = cfg["U"], cfg["I"], cfg["L"], cfg["D"]
@@ -168,8 +187,8 @@ def run_ours(args, cfg, B):
     Cat = torch.randn((4, D), device=dev, generator=g) * 0.1; G = torch.randn((Lb, 5, D), device=dev, generator=g) * 0.1
     item_cats = synth.make_item_categories(I)
     lab = synth.make_user_label_csr(U, Lb)
-    eng = Engine(Hyper(learner="adam", lr=0.001), P, R, Cat, G, device=dev, max_rows=2 * B,
-                 adam_mode="lazy_exact", item_cats=item_cats, user_label_csr=lab,
+    eng = Engine(Hyper(learner=args.learner, lr=0.001), P, R, Cat, G, device=dev, max_rows=2 * B,
+                 adam_mode=args.adam_mode, item_cats=item_cats, user_label_csr=lab,
                  max_label_entries=2 * B * Lb if B * Lb < (1 << 26) else 2 * B * 8)
     del P
     NB = 8
@@ -194,15 +213,16 @@ def run_ours(args, cfg, B):
     v = eng.read_scalars()
     uniq_users, uniq_items = float(v[L.FR_OUT_UNIQ_USERS]), float(v[L.FR_OUT_UNIQ_ITEMS])
     # ---- timed region: device timing, inputs resident in HBM
-    clocks = ClockSampler(local); clocks.start()
     launches0 = eng.lib.fr_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark_begin()
     ev0.record()
     for k in range(args.steps):
         step(k)
     ev1.record()
     barrier()
+    clocks.mark_end()
     launches = eng.lib.fr_launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     if world > 1:
@@ -218,7 +238,7 @@ def run_ours(args, cfg, B):
     phases, nst = eng.timing_read()
     eng.timing_enable(False)
     peak, peak_src = peaks()
-    adam_k = 6
+    adam_k = {"adam": 6, "adagrad": 4, "rmsprop": 6, "sgd": 2}.get(args.learner.lower(), 2)   # var(+slots) read+write
     alg = {   # algorithmic bytes per launch, SURVEY 8(d) (fp32)
         "fwd": B * (28 * D + 16),
         "user_chunk": uniq_users * adam_k * 20 * D,
@@ -280,7 +300,7 @@ def run_ours(args, cfg, B):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, B), "batch_triples": B, "optimizer": "adam (TF-1.x semantics, lazy-exact)",
+            "config": {"workload": workload_name(cfg, B), "batch_triples": B, "optimizer": (f"adam (TF-1.x semantics, {args.adam_mode})" if args.learner.lower() == "adam" else args.learner),
                        "l2": "per-step working set (~%.1f GB of table rows) >> 126 MB L2; %d distinct batches cycled" % (
                            (alg["fwd"] + alg["user_chunk"] + alg["item_chunk"]) / 1e9, NB),
                        "preroll_steps": preroll,
@@ -315,6 +335,8 @@ def main():
     ap.add_argument("--preroll", type=int, default=40)
     ap.add_argument("--small", action="store_true", help="tiny tables: harness check only, not a bench number")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--learner", default="adam", help="adam (reference default) | adagrad | rmsprop | sgd")
+    ap.add_argument("--adam-mode", default="lazy_exact", choices=["lazy_exact", "dense"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = SMALL if args.small else CFG2

@@ -27,6 +27,14 @@ __device__ __forceinline__ void fma4(float4& acc, const float s, const float4 v)
   acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y);
   acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
 }
+// acc += round(s*v): the product is rounded BEFORE the add, like TF's gradient slices
+// (IndexedSlices values are materialised, then segment-summed).  With an FMA the exact
+// cancellations of the reference (e.g. a BPR pair whose two recipes share a category mask:
+// g*a*pc - g*a*pc == 0) would leave a rounding residual that Adam's 1/eps gain amplifies.
+__device__ __forceinline__ void mad4_rn(float4& acc, const float s, const float4 v) {
+  acc.x = __fadd_rn(acc.x, __fmul_rn(s, v.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(s, v.y));
+  acc.z = __fadd_rn(acc.z, __fmul_rn(s, v.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(s, v.w));
+}
 __device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
@@ -49,6 +57,14 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {   // read-once da
 __device__ __forceinline__ void st_stream(float4* p, const float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Fire-and-forget TMA bulk prefetch of a contiguous span into L2 (UBLKPF).  The row
+// movers are latency-bound (a warp's registers hold one table row at a time); prefetching
+// the rows of the NEXT work item turns their demand loads into L2 hits and gives the
+// memory system more bytes in flight without holding any registers.
+__device__ __forceinline__ void prefetch_l2_span(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
 }
 
 template <int NV>

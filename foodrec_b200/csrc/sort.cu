@@ -48,8 +48,9 @@ __global__ void __launch_bounds__(FR_THREADS)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                      uint32_t n_host, const uint32_t* n_dev, int shift, uint32_t ntiles,
-                     const uint32_t* __restrict__ tile_off) {
+                     const uint32_t* __restrict__ tile_off, int fused_scan) {
   __shared__ uint32_t wcnt[FR_WARPS_PER_BLOCK][RADIX_BINS];
+  __shared__ uint32_t wtot[FR_WARPS_PER_BLOCK];
   const uint32_t n = resolve_n(n_dev, n_host);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
@@ -74,7 +75,33 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     __syncthreads();
     {  // exclusive scan over warps per digit, seeded with the global tile offset
       const int b = threadIdx.x;
-      uint32_t run = tile_off[b * ntiles + tile];
+      uint32_t run;
+      if (fused_scan) {
+        // few tiles: tile_off holds the RAW per-tile histograms and every block derives
+        // its own offsets (saves the separate scan launches of the pass):
+        //   offset[b][tile] = sum_{b'<b} total[b'] + sum_{t<tile} hist[b][t]
+        const uint32_t* hrow = tile_off + (size_t)b * ntiles;
+        uint32_t pre = 0, tot = 0;
+        for (uint32_t t = 0; t < ntiles; ++t) {
+          const uint32_t c = hrow[t];
+          tot += c;
+          if (t < tile) pre += c;
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(FR_FULL, inc, o);
+          if (lane >= o) inc += y;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < FR_WARPS_PER_BLOCK; ++w) if (w < warp) wbase += wtot[w];
+        run = wbase + (inc - tot) + pre;
+      } else {
+        run = tile_off[b * ntiles + tile];
+      }
 #pragma unroll
       for (int w = 0; w < FR_WARPS_PER_BLOCK; ++w) {
         const uint32_t c = wcnt[w][b];
@@ -215,10 +242,11 @@ int radix_sort_pairs(SortBufs& bufs, const uint32_t* keys_in, uint32_t n_host,
   int dst = 0;
   for (int p = 0; p < passes; ++p) {
     const int shift = p * RADIX_BITS;
+    const int fused = ntiles <= 128 ? 1 : 0;
     radix_hist_kernel<<<grid, FR_THREADS, 0, st>>>(kin, n_host, n_dev, shift, ntiles, bufs.tile_hist);
-    exclusive_scan_u32(bufs.tile_hist, bufs.tile_hist, RADIX_BINS * ntiles, bufs.scan_tmp, nullptr, st);
+    if (!fused) exclusive_scan_u32(bufs.tile_hist, bufs.tile_hist, RADIX_BINS * ntiles, bufs.scan_tmp, nullptr, st);
     radix_scatter_kernel<<<grid, FR_THREADS, 0, st>>>(kin, vin, bufs.k[dst], bufs.v[dst], n_host, n_dev,
-                                                      shift, ntiles, bufs.tile_hist);
+                                                      shift, ntiles, bufs.tile_hist, fused);
     g_launches += 2;
     kin = bufs.k[dst];
     vin = bufs.v[dst];

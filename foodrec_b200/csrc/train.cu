@@ -18,15 +18,45 @@ namespace fr {
 // ------------------------------------------------------------------ optimizer math
 // Explicit _rn intrinsics: no FMA contraction, so the per-element arithmetic is the
 // IEEE sequence the TF CPU kernels (and the numpy oracle) perform.
-__device__ __forceinline__ void adam_decay(float& var, float& m, float& v, int from, int to,
-                                           const OptConsts& oc) {
+// Decay-only Adam steps (rows NOT in the batch, adam.py _apply_sparse_shared):
+//   m <- b1*m ; v <- b2*v ; var <- var - lr_s*m/(sqrt(v)+eps)      for s = from..to
+// One routine serves the dense sweep, the lazy catch-up and the lazy forward, so the
+// three produce bit-identical rows.  All N float4 of the thread advance together inside
+// one loop over steps (4N independent chains: throughput- not latency-bound); the
+// quotient uses MUFU sqrt/rcp (<= 2 ulp on a term that is itself <= lr_s: far inside the
+// 1e-5 parity bound) -- the loop is the only part of the step whose cost scales with the
+// number of skipped steps.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  // .ftz: one MUFU, no denormal fix-up code.  A denormal v flushes to sqrt = 0, and
+  // 0 + eps == sqrt(v) + eps in fp32 for any v < 2^-126 (sqrt(v) < 1e-19 << ulp(eps)).
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {    // argument >= eps: always normal
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ void adam_decay1(float& var, float& m, float& v, float lr, const OptConsts& oc) {
+  m = __fmul_rn(m, oc.b1);
+  v = __fmul_rn(v, oc.b2);
+  const float r = fast_rcp(__fadd_rn(fast_sqrt(v), oc.eps));
+  var = __fmaf_rn(-__fmul_rn(lr, m), r, var);
+}
+template <int N>
+__device__ __forceinline__ void adam_replay(float4* var, float4* m, float4* v, int from, int to,
+                                            const OptConsts& oc) {
   if (from > to) return;
-  if (m == 0.f && v == 0.f) return;      // never-touched element: every skipped step is a no-op
+  bool any = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    any |= (m[i].x != 0.f) | (m[i].y != 0.f) | (m[i].z != 0.f) | (m[i].w != 0.f) |
+           (v[i].x != 0.f) | (v[i].y != 0.f) | (v[i].z != 0.f) | (v[i].w != 0.f);
+  if (!any) return;                      // never-touched elements: every skipped step is a no-op
   for (int s = from; s <= to; ++s) {
-    m = __fmul_rn(m, oc.b1);
-    v = __fmul_rn(v, oc.b2);
-    if (m != 0.f)
-      var = __fsub_rn(var, __fdiv_rn(__fmul_rn(__ldg(oc.lr_hist + s), m), __fadd_rn(__fsqrt_rn(v), oc.eps)));
+    const float lr = __ldg(oc.lr_hist + s);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      adam_decay1(var[i].x, m[i].x, v[i].x, lr, oc); adam_decay1(var[i].y, m[i].y, v[i].y, lr, oc);
+      adam_decay1(var[i].z, m[i].z, v[i].z, lr, oc); adam_decay1(var[i].w, m[i].w, v[i].w, lr, oc);
+    }
   }
 }
 __device__ __forceinline__ void adam_touch(float& var, float& m, float& v, float g, const OptConsts& oc) {
@@ -81,6 +111,8 @@ __device__ __forceinline__ void apply_and_store(RowState<NR, NV>& st, float4* va
                                                 const OptConsts& oc, int DV, int lane,
                                                 const float4 (*w1)[NV], const float4 (*w2)[NV], float alpha) {
   const size_t base = (size_t)rowid * NR * DV;
+  if (oc.learner == FR_ADAM)      // lazy-exact: the steps this row sat out, then this step's update
+    adam_replay<NR * NV>(&st.var[0][0], &st.s1[0][0], &st.s2[0][0], st.last + 1, oc.step - 1, oc);
 #pragma unroll
   for (int s = 0; s < NR; ++s)
 #pragma unroll
@@ -90,11 +122,8 @@ __device__ __forceinline__ void apply_and_store(RowState<NR, NV>& st, float4* va
       float4 var = st.var[s][k], a = st.s1[s][k], b = st.s2[s][k];
       const float4 g = grad[s][k];
       if (oc.learner == FR_ADAM) {
-        const int from = st.last + 1, to = oc.step - 1;
-        adam_decay(var.x, a.x, b.x, from, to, oc); adam_touch(var.x, a.x, b.x, g.x, oc);
-        adam_decay(var.y, a.y, b.y, from, to, oc); adam_touch(var.y, a.y, b.y, g.y, oc);
-        adam_decay(var.z, a.z, b.z, from, to, oc); adam_touch(var.z, a.z, b.z, g.z, oc);
-        adam_decay(var.w, a.w, b.w, from, to, oc); adam_touch(var.w, a.w, b.w, g.w, oc);
+        adam_touch(var.x, a.x, b.x, g.x, oc); adam_touch(var.y, a.y, b.y, g.y, oc);
+        adam_touch(var.z, a.z, b.z, g.z, oc); adam_touch(var.w, a.w, b.w, g.w, oc);
       } else if (oc.learner == FR_ADAGRAD) {
         adagrad_touch(var.x, a.x, g.x, oc); adagrad_touch(var.y, a.y, g.y, oc);
         adagrad_touch(var.z, a.z, g.z, oc); adagrad_touch(var.w, a.w, g.w, oc);
@@ -170,25 +199,27 @@ fwd_train_kernel(const FwdParams p) {
 
   for (int grp = gw; grp < p.B; grp += nw) {
     const int u = p.users[grp];
+    if (grp + nw < p.B) {       // L2-prefetch the rows of this warp's next group
+      const int gn = grp + nw;
+      const uint32_t ub = 5u * (uint32_t)DV * 16u, rb = (uint32_t)DV * 16u;
+      if (lane == 0) prefetch_l2_span(p.P + (size_t)p.users[gn] * 5 * DV, ub);
+      else if (lane == 1 && p.lazy) prefetch_l2_span(p.mP + (size_t)p.users[gn] * 5 * DV, ub);
+      else if (lane == 2 && p.lazy) prefetch_l2_span(p.vP + (size_t)p.users[gn] * 5 * DV, ub);
+      else if (lane >= 3 && lane < 3 + GROUP) prefetch_l2_span(p.R + (size_t)p.items[gn * GROUP + lane - 3] * DV, rb);
+    }
     float4 pr[5][NV];
 #pragma unroll
     for (int s = 0; s < 5; ++s) load_row<NV>(pr[s], p.P + ((size_t)u * 5 + s) * DV, DV, lane);
     if (p.lazy) {
       const int from = p.lastP[u] + 1, to = p.oc.step - 1;
       if (from <= to) {
+        float4 mm[5][NV], vv[5][NV];
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
-          float4 mm[NV], vv[NV];
-          load_row<NV>(mm, p.mP + ((size_t)u * 5 + s) * DV, DV, lane);
-          load_row<NV>(vv, p.vP + ((size_t)u * 5 + s) * DV, DV, lane);
-#pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            adam_decay(pr[s][k].x, mm[k].x, vv[k].x, from, to, p.oc);
-            adam_decay(pr[s][k].y, mm[k].y, vv[k].y, from, to, p.oc);
-            adam_decay(pr[s][k].z, mm[k].z, vv[k].z, from, to, p.oc);
-            adam_decay(pr[s][k].w, mm[k].w, vv[k].w, from, to, p.oc);
-          }
+          load_row<NV>(mm[s], p.mP + ((size_t)u * 5 + s) * DV, DV, lane);
+          load_row<NV>(vv[s], p.vP + ((size_t)u * 5 + s) * DV, DV, lane);
         }
+        adam_replay<5 * NV>(&pr[0][0], &mm[0][0], &vv[0][0], from, to, p.oc);
       }
     }
     float4 rr[GROUP][NV], pcn[GROUP][NV];   // R rows, pooledCat (normalised)
@@ -313,7 +344,7 @@ fwd_train_kernel(const FwdParams p) {
 
 int fwd_train_grid(int B, int sm_count) {
   int grid = (B + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
-  const int cap = sm_count * 4;
+  const int cap = sm_count * 3;      // 3 CTAs of 8 warps are resident per SM (<= 85 regs/thread)
   if (grid > cap) grid = cap;
   return grid < 1 ? 1 : grid;
 }
@@ -338,12 +369,7 @@ finalize_kernel(const FinalizeParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n4 = 4 * p.DV;
   float4* pk_gcat = reinterpret_cast<float4*>(p.packed + 4);   // packed[0..3] = loss, nrm, pad, pad
-  if (p.do_reduce) {
-    for (int j = threadIdx.x; j < n4; j += blockDim.x) {
-      float4 s = f4zero();
-      for (int b = 0; b < p.nblk; ++b) s = add4(s, p.part_gcat[(size_t)b * n4 + j]);
-      pk_gcat[j] = s;
-    }
+  if (p.do_reduce) {      // (dCat partials were reduced by gcat_reduce_kernel just before)
     if (warp == 0) {
       double l = 0.0, q = 0.0;
       for (int b = lane; b < p.nblk; b += 32) { l += (double)p.part_loss[b]; q += (double)p.part_nrm[b]; }
@@ -400,7 +426,32 @@ finalize_kernel(const FinalizeParams p) {
   }
 }
 
+// dCat block partials [nblk][4*DV] -> [4*DV]: 8 float4 columns per block, 32 row groups per
+// column, fixed-order shared-memory tree (deterministic).
+__global__ void __launch_bounds__(256)
+gcat_reduce_kernel(const float4* __restrict__ part, int nblk, int n4, float4* __restrict__ out) {
+  __shared__ float4 sh[32][8];
+  const int c = threadIdx.x & 7, r = threadIdx.x >> 3;
+  const int j = blockIdx.x * 8 + c;
+  float4 s = f4zero();
+  if (j < n4)
+    for (int b = r; b < nblk; b += 32) s = add4(s, part[(size_t)b * n4 + j]);
+  sh[r][c] = s;
+  __syncthreads();
+  if (r == 0 && j < n4) {
+    float4 t = sh[0][c];
+#pragma unroll
+    for (int q = 1; q < 32; ++q) t = add4(t, sh[q][c]);
+    out[j] = t;
+  }
+}
+
 void launch_finalize(const FinalizeParams& p, const Launch& l) {
+  if (p.do_reduce) {
+    const int n4 = 4 * p.DV;
+    gcat_reduce_kernel<<<(n4 + 7) / 8, 256, 0, l.st>>>(p.part_gcat, p.nblk, n4, reinterpret_cast<float4*>(p.packed + 4));
+    ++g_launches;
+  }
   finalize_kernel<<<1, FR_THREADS, 0, l.st>>>(p);
   ++g_launches;
 }
@@ -445,9 +496,17 @@ seg_chunk_kernel(const SegCommon c, const Pol pol) {
     const bool to_next = has_next && nextKey == lastKey;
     if (c.uniq_counter && lane == 0) atomicAdd(c.uniq_counter, (uint32_t)__popc(hm));
     int e0 = 0;
+    {   // state rows of the second run of the chunk (the first is loaded right away)
+      const uint32_t r1 = hm & ~1u;
+      if (r1) pol.prefetch_state(__shfl_sync(FR_FULL, key, __ffs(r1) - 1), lane);
+    }
     while (e0 < cnt) {
       const uint32_t rest = (e0 >= 31) ? 0u : (hm & ~((2u << e0) - 1u));
       const int e1 = rest ? (__ffs(rest) - 1) : cnt;
+      {   // ... and, while this run is processed, of the run after the next one
+        const uint32_t r2 = rest & (rest - 1u);
+        if (r2) pol.prefetch_state(__shfl_sync(FR_FULL, key, __ffs(r2) - 1), lane);
+      }
       const bool starts = (e0 > 0) || !from_prev;
       const bool ends = (e1 < cnt) || !to_next;
       const uint32_t k = __shfl_sync(FR_FULL, key, e0);
@@ -511,18 +570,34 @@ seg_combine_kernel(const SegCommon c, const Pol pol) {
           acc[s][q] = i < DV ? __ldcg(src + s * DV + i) : f4zero();
         }
     }
-    uint32_t kc = chunk + 1;
-    while (true) {
-      const float4* src = c.pieces + ((size_t)kc * 2) * NR * DV;
+    // end of the run: first position > base+31 whose key differs (binary search: the
+    // keys are sorted), so the piece loads below are independent and can be pipelined
+    uint32_t lo = base + 32, hi = n;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (c.keys[mid] == lastKey) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t kend = (lo - 1) >> 5;          // last chunk holding an entry of the run
+    constexpr int PF = (NR * NV <= 2) ? 8 : (NR * NV <= 5 ? 4 : 2);
+    for (uint32_t kc = chunk + 1; kc <= kend; kc += PF) {
+      float4 buf[PF][NR][NV];
 #pragma unroll
-      for (int s = 0; s < NR; ++s)
+      for (int u = 0; u < PF; ++u) {
+        const float4* src = c.pieces + ((size_t)(kc + u) * 2) * NR * DV;
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          const int i = lane + 32 * q;
-          if (i < DV) acc[s][q] = add4(acc[s][q], __ldcg(src + s * DV + i));
-        }
-      const uint32_t nb = (kc + 1) << 5;
-      if (nb < n && c.keys[nb] == lastKey) ++kc; else break;
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const int i = lane + 32 * q;
+            buf[u][s][q] = (kc + u <= kend && i < DV) ? __ldcg(src + s * DV + i) : f4zero();
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u)      // summed in chunk order: deterministic
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) acc[s][q] = add4(acc[s][q], buf[u][s][q]);
     }
     typename Pol::State st;
     pol.load_state(st, lastKey, lane);
@@ -547,6 +622,7 @@ struct UserPol {
     Entry e; e.item = 0; e.g = 0.f; e.m = make_float4(1.f, 0.f, 0.f, 0.f); e.ws = 0.f; e.grp = 0;
     if (valid) {
       e.item = p.items[row];
+      prefetch_l2_span(p.R + (size_t)e.item * p.mc.DV, (uint32_t)p.mc.DV * 16u);
       e.g = p.g[row] * p.out[FR_OUT_SCALE];
       e.m = __ldg(p.cats + (p.cats_by_item ? e.item : (int)row));
       e.ws = p.ws_row[row];
@@ -557,27 +633,35 @@ struct UserPol {
   __device__ __forceinline__ void accumulate(float4 (&acc)[NR][NV], const Entry& e, int e0, int e1, int lane,
                                              const float4* sCat) const {
     const int DVv = p.mc.DV;
-    for (int j = e0; j < e1; ++j) {
-      const int it = __shfl_sync(FR_FULL, e.item, j);
+    // two recipe rows in flight per iteration (a BPR triple is exactly one such pair)
+    for (int j0 = e0; j0 < e1; j0 += 2) {
+     const int jn = (j0 + 1 < e1) ? j0 + 1 : j0;
+     float4 rr2[2][NV];
+     load_row_ro<NV>(rr2[0], p.R + (size_t)__shfl_sync(FR_FULL, e.item, j0) * DVv, DVv, lane);
+     load_row_ro<NV>(rr2[1], p.R + (size_t)__shfl_sync(FR_FULL, e.item, jn) * DVv, DVv, lane);
+#pragma unroll
+     for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u;
+      if (j >= e1) break;
       const float g = __shfl_sync(FR_FULL, e.g, j);
       const float4 m = shfl4(e.m, j);
-      float4 rr[NV], pcs[NV];
-      load_row_ro<NV>(rr, p.R + (size_t)it * DVv, DVv, lane);
+      float4 (&rr)[NV] = rr2[u];
+      float4 pcs[NV];
       pooled_cat<NV>(pcs, sCat, m, DVv, lane);
       const float n = ((m.x + m.y) + m.z) + m.w;
       const float ga = g * p.mc.a, go = g * p.mc.oma;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const float4 pc = div4(pcs[k], n);
-        fma4(acc[0][k], ga, pc);
-        fma4(acc[1][k], go * (m.x / n), rr[k]); fma4(acc[2][k], go * (m.y / n), rr[k]);
-        fma4(acc[3][k], go * (m.z / n), rr[k]); fma4(acc[4][k], go * (m.w / n), rr[k]);
+        mad4_rn(acc[0][k], ga, pc);
+        mad4_rn(acc[1][k], go * (m.x / n), rr[k]); mad4_rn(acc[2][k], go * (m.y / n), rr[k]);
+        mad4_rn(acc[3][k], go * (m.z / n), rr[k]); mad4_rn(acc[4][k], go * (m.w / n), rr[k]);
         if (PERSONAL) {
           const float ws = __shfl_sync(FR_FULL, e.ws, j);
           const float hc = p.mc.beta_2 * ws, lc = p.mc.beta_1 * ws;
-          fma4(acc[5][k], hc, pc);                                   // :140-144
-          fma4(acc[6][k], lc, scale4(m.x, rr[k])); fma4(acc[7][k], lc, scale4(m.y, rr[k]));   // :111-119
-          fma4(acc[8][k], lc, scale4(m.z, rr[k])); fma4(acc[9][k], lc, scale4(m.w, rr[k]));
+          mad4_rn(acc[5][k], hc, pc);                                   // :140-144
+          mad4_rn(acc[6][k], lc, scale4(m.x, rr[k])); mad4_rn(acc[7][k], lc, scale4(m.y, rr[k]));   // :111-119
+          mad4_rn(acc[8][k], lc, scale4(m.z, rr[k])); mad4_rn(acc[9][k], lc, scale4(m.w, rr[k]));
         }
       }
       if (PERSONAL) {            // (sum_l lam_l G_old[l]) / sum_l lam_l   (:170-186)
@@ -621,10 +705,19 @@ struct UserPol {
 #pragma unroll
           for (int k = 0; k < NV; ++k) acc[10 + s][k] = add4(acc[10 + s][k], div4(gs[s][k], lsum));
       }
+     }
     }
   }
   __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
     fr::load_state<5, NV>(st, p.P, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
+  }
+  __device__ __forceinline__ void prefetch_state(uint32_t key, int lane) const {
+    const uint32_t bytes = 5u * (uint32_t)p.mc.DV * 16u;      // a user's 5 slots are contiguous
+    const size_t off = (size_t)key * 5 * p.mc.DV;
+    const int L = p.oc.learner;
+    if (lane == 0) prefetch_l2_span(p.P + off, bytes);
+    else if (lane == 1 && L != FR_SGD) prefetch_l2_span(p.s1 + off, bytes);
+    else if (lane == 2 && (L == FR_ADAM || L == FR_RMSPROP)) prefetch_l2_span(p.s2 + off, bytes);
   }
   __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[NR][NV], int lane) const {
     float4 (&grad)[5][NV] = *reinterpret_cast<float4 (*)[5][NV]>(&acc[0]);
@@ -655,18 +748,37 @@ struct ItemPol {
   __device__ __forceinline__ void accumulate(float4 (&acc)[1][NV], const Entry& e, int e0, int e1, int lane,
                                              const float4*) const {
     const int DVv = p.mc.DV;
-    for (int j = e0; j < e1; ++j) {
-      const uint32_t row = __shfl_sync(FR_FULL, e.row, j);
-      const float g = __shfl_sync(FR_FULL, e.g, j);
+    constexpr int PF = 4;                       // z rows in flight
+    for (int j0 = e0; j0 < e1; j0 += PF) {
+      float4 zz[PF][NV];
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const int i = lane + 32 * k;
-        if (i < DVv) fma4(acc[0][k], g, __ldcg(p.z + (size_t)row * DVv + i));
+      for (int u = 0; u < PF; ++u) {
+        const uint32_t row = __shfl_sync(FR_FULL, e.row, min(j0 + u, e1 - 1));
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int i = lane + 32 * k;
+          zz[u][k] = i < DVv ? __ldcg(p.z + (size_t)row * DVv + i) : f4zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (j0 + u >= e1) break;
+        const float g = __shfl_sync(FR_FULL, e.g, j0 + u);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) mad4_rn(acc[0][k], g, zz[u][k]);
       }
     }
   }
   __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
     fr::load_state<1, NV>(st, p.R, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
+  }
+  __device__ __forceinline__ void prefetch_state(uint32_t key, int lane) const {
+    const uint32_t bytes = (uint32_t)p.mc.DV * 16u;
+    const size_t off = (size_t)key * p.mc.DV;
+    const int L = p.oc.learner;
+    if (lane == 0) prefetch_l2_span(p.R + off, bytes);
+    else if (lane == 1 && L != FR_SGD) prefetch_l2_span(p.s1 + off, bytes);
+    else if (lane == 2 && (L == FR_ADAM || L == FR_RMSPROP)) prefetch_l2_span(p.s2 + off, bytes);
   }
   __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[1][NV], int lane) const {
     apply_and_store<1, NV>(st, p.R, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane, nullptr, nullptr, 0.f);
@@ -689,6 +801,7 @@ struct LabelPol {
     if (valid) {
       const uint32_t row = p.ent_row[ent];
       e.item = p.items[row];
+      prefetch_l2_span(p.R + (size_t)e.item * p.mc.DV, (uint32_t)p.mc.DV * 16u);
       e.coef = p.ent_coef[ent];
       e.m = __ldg(p.cats + (p.cats_by_item ? e.item : (int)row));
     }
@@ -697,23 +810,32 @@ struct LabelPol {
   __device__ __forceinline__ void accumulate(float4 (&acc)[5][NV], const Entry& e, int e0, int e1, int lane,
                                              const float4* sCat) const {
     const int DVv = p.mc.DV;
-    for (int j = e0; j < e1; ++j) {
-      const int it = __shfl_sync(FR_FULL, e.item, j);
-      const float coef = __shfl_sync(FR_FULL, e.coef, j);
-      const float4 m = shfl4(e.m, j);
-      float4 rr[NV], pcs[NV];
-      load_row_ro<NV>(rr, p.R + (size_t)it * DVv, DVv, lane);
-      pooled_cat<NV>(pcs, sCat, m, DVv, lane);
-      const float n = ((m.x + m.y) + m.z) + m.w;
-      const float hc = p.mc.beta_2 * coef, lc = p.mc.beta_1 * coef;
+    constexpr int PF = 4;                       // recipe rows in flight
+    for (int j0 = e0; j0 < e1; j0 += PF) {
+      float4 rr4[PF][NV];
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        fma4(acc[0][k], hc, div4(pcs[k], n));
-        fma4(acc[1][k], lc, scale4(m.x, rr[k])); fma4(acc[2][k], lc, scale4(m.y, rr[k]));
-        fma4(acc[3][k], lc, scale4(m.z, rr[k])); fma4(acc[4][k], lc, scale4(m.w, rr[k]));
+      for (int u = 0; u < PF; ++u)
+        load_row_ro<NV>(rr4[u], p.R + (size_t)__shfl_sync(FR_FULL, e.item, min(j0 + u, e1 - 1)) * DVv, DVv, lane);
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int j = j0 + u;
+        if (j >= e1) break;
+        const float coef = __shfl_sync(FR_FULL, e.coef, j);
+        const float4 m = shfl4(e.m, j);
+        float4 pcs[NV];
+        pooled_cat<NV>(pcs, sCat, m, DVv, lane);
+        const float n = ((m.x + m.y) + m.z) + m.w;
+        const float hc = p.mc.beta_2 * coef, lc = p.mc.beta_1 * coef;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          mad4_rn(acc[0][k], hc, div4(pcs[k], n));
+          mad4_rn(acc[1][k], lc, scale4(m.x, rr4[u][k])); mad4_rn(acc[2][k], lc, scale4(m.y, rr4[u][k]));
+          mad4_rn(acc[3][k], lc, scale4(m.z, rr4[u][k])); mad4_rn(acc[4][k], lc, scale4(m.w, rr4[u][k]));
+        }
       }
     }
   }
+  __device__ __forceinline__ void prefetch_state(uint32_t, int) const {}   // G is tiny and hot
   __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
     const int DVv = p.mc.DV;
 #pragma unroll
@@ -741,9 +863,15 @@ static void launch_seg(const SegCommon& c, const Pol& pol, int DV, bool needs_ca
   const uint32_t nchunks = (c.n_host + 31) / 32;
   if (nchunks == 0) return;
   int grid = (int)((nchunks + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
-  const int cap = l.sm_count * 16;
-  if (grid > cap) grid = cap;
   const size_t smem = needs_cat ? (size_t)4 * DV * sizeof(float4) : 0;
+  // persistent grid = exactly the resident CTAs (SM count x occupancy): no partial wave
+  static int occ_chunk = 0;
+  if (!occ_chunk) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_chunk, seg_chunk_kernel<Pol>, FR_THREADS, smem);
+    if (occ_chunk < 1) occ_chunk = 1;
+  }
+  const int cap = l.sm_count * occ_chunk;
+  if (grid > cap) grid = cap;
   seg_chunk_kernel<Pol><<<grid, FR_THREADS, smem, l.st>>>(c, pol);
   if (l.mid) cudaEventRecord(l.mid, l.st);
   seg_combine_kernel<Pol><<<grid, FR_THREADS, 0, l.st>>>(c, pol);
@@ -859,8 +987,7 @@ adam_sweep_kernel(float4* __restrict__ var, float4* __restrict__ m, float4* __re
     if (mm.x == 0.f && mm.y == 0.f && mm.z == 0.f && mm.w == 0.f &&
         vv.x == 0.f && vv.y == 0.f && vv.z == 0.f && vv.w == 0.f) continue;
     float4 x = __ldcs(var + i);
-    adam_decay(x.x, mm.x, vv.x, from, target, oc); adam_decay(x.y, mm.y, vv.y, from, target, oc);
-    adam_decay(x.z, mm.z, vv.z, from, target, oc); adam_decay(x.w, mm.w, vv.w, from, target, oc);
+    adam_replay<1>(&x, &mm, &vv, from, target, oc);
     __stcs(var + i, x); __stcs(m + i, mm); __stcs(v + i, vv);
   }
 }
@@ -896,11 +1023,7 @@ item_catchup_kernel(const uint32_t* __restrict__ keys, uint32_t n, float4* __res
       load_row<NV>(mm, m + (size_t)k * DV, DV, lane);
       load_row<NV>(vv, v + (size_t)k * DV, DV, lane);
       load_row<NV>(x, R + (size_t)k * DV, DV, lane);
-#pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        adam_decay(x[q].x, mm[q].x, vv[q].x, from, to, oc); adam_decay(x[q].y, mm[q].y, vv[q].y, from, to, oc);
-        adam_decay(x[q].z, mm[q].z, vv[q].z, from, to, oc); adam_decay(x[q].w, mm[q].w, vv[q].w, from, to, oc);
-      }
+      adam_replay<NV>(x, mm, vv, from, to, oc);
       store_row<NV>(R + (size_t)k * DV, x, DV, lane);
       store_row<NV>(m + (size_t)k * DV, mm, DV, lane);
       store_row<NV>(v + (size_t)k * DV, vv, DV, lane);

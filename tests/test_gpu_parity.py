@@ -53,7 +53,8 @@ def compare_tables(e, om, what="", om32=None):
 
 
 # ---------------------------------------------------------------- sort
-@pytest.mark.parametrize("n,nbits", [(1, 3), (31, 5), (2048, 8), (2049, 9), (5000, 20), (70000, 17), (100000, 1)])
+@pytest.mark.parametrize("n,nbits", [(1, 3), (31, 5), (2048, 8), (2049, 9), (5000, 20), (70000, 17), (100000, 1),
+                                     (400000, 19)])     # > 128 tiles: separate scan path
 def test_radix_sort_is_stable_and_exact(n, nbits):
     p = Problem(8, 8, 3, 8)
     e = make_engine(p, max_rows=max(n, 128))

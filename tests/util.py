@@ -43,9 +43,20 @@ def assert_close_adam(x, ref64, ref32, rtol=RTOL, what=""):
     tol = rtol * np.maximum(np.abs(ref64), rms)
     err = np.abs(x - ref64)
     dev32 = np.abs(ref32 - ref64)
-    frac_bad = float((err > np.maximum(tol, 8.0 * dev32)).mean())
+    # the conditioning is a property of the table row (one user's / recipe's summed
+    # gradient), so an entry is excused by the fp32 oracle's worst deviation in its row
+    row_dev = np.broadcast_to(dev32.reshape(dev32.shape[0], -1).max(axis=1).reshape(
+        (-1,) + (1,) * (dev32.ndim - 1)), dev32.shape)
+    bad = err > np.maximum(tol, 8.0 * row_dev)
+    frac_bad = float(bad.mean())
     cond = float(dev32.max())
-    assert frac_bad <= 1e-3, f"{what}: {frac_bad:.2e} of entries outside 1e-5 and unexplained by fp32 rounding"
+    if frac_bad > 1e-3:
+        idx = np.argwhere(bad)
+        rows = sorted(set(int(i[0]) for i in idx))
+        w = tuple(idx[np.argmax(err[bad])])
+        raise AssertionError(
+            f"{what}: {frac_bad:.2e} of entries outside 1e-5 and unexplained by fp32 rounding; rows {rows[:12]}; "
+            f"worst {w}: got {x[w]!r} ref64 {ref64[w]!r} ref32 {ref32[w]!r} row_dev {row_dev[w]:.3e}")
     assert err.max() <= max(8.0 * cond, tol.min()), \
         f"{what}: worst err {err.max():.3e} vs fp32-oracle deviation {cond:.3e}"
 
