@@ -336,7 +336,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny tables: harness check only, not a bench number")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--learner", default="adam", help="adam (reference default) | adagrad | rmsprop | sgd")
-    ap.add_argument("--adam-mode", default="lazy_exact", choices=["lazy_exact", "dense"])
+    ap.add_argument("--adam-mode", default="lazy", choices=["lazy", "lazy_exact", "dense"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = SMALL if args.small else CFG2

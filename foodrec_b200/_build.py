@@ -1,10 +1,12 @@
 """In-tree build of libfoodrec_b200.so (nvcc, sm_100a only).
 
-``python -m foodrec_b200._build`` or ``foodrec_b200._build.build()``.  The .so is
-git-ignored but travels to the GPU box with the repo snapshot.
+``python -m foodrec_b200._build`` or ``foodrec_b200._build.build()``.  Each translation
+unit is compiled to an object in parallel, then linked.  The .so is git-ignored but
+travels to the GPU box with the repo snapshot.
 """
 from __future__ import annotations
 
+import concurrent.futures as cf
 import os
 import shutil
 import subprocess
@@ -13,10 +15,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libfoodrec_b200.so")
-SOURCES = ["sort.cu", "train.cu", "eval.cu", "catalog.cu", "api.cu"]
-HEADERS = ["common.cuh", "internal.h", "train.cuh", os.path.join("..", "..", "include", "foodrec_b200.h")]
+SOURCES = ["sort.cu", "train_fwd.cu", "train_seg.cu", "eval.cu", "catalog.cu", "api.cu"]
+HEADERS = ["common.cuh", "internal.h", "train.cuh", "optim.cuh", os.path.join("..", "..", "include", "foodrec_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:
@@ -30,24 +32,54 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def needs_build(lib=LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = sources() + [os.path.join(CSRC, h) for h in HEADERS]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+def _compile(out_lib, defines=(), verbose=False, tag="") -> str:
+    objdir = os.path.join(CSRC, "build" + tag)
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    extra = [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h)))
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t) and not verbose:
+            return obj, ""
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        return obj, r.stderr
+
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+        res = list(ex.map(one, sources()))
+    if verbose:
+        sys.stderr.write("".join(e for _, e in res))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_lib] + [o for o, _ in res]
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if verbose:
-        sys.stderr.write(r.stderr)
-    return LIB
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return out_lib
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not verbose and not needs_build():
+        return LIB
+    if force:
+        shutil.rmtree(os.path.join(CSRC, "build"), ignore_errors=True)
+    return _compile(LIB, verbose=verbose)
+
+
+def build_variant(name: str, defines) -> str:
+    """A/B build of the same sources with extra -D flags -> csrc/libfoodrec_b200_<name>.so
+    (selected at run time with FOODREC_B200_LIB=<path>)."""
+    return _compile(os.path.join(CSRC, f"libfoodrec_b200_{name}.so"), defines=defines, tag="_" + name)
 
 
 if __name__ == "__main__":

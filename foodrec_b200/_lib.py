@@ -9,7 +9,7 @@ from . import _build
 
 FR_OK = 0
 FR_SGD, FR_ADAGRAD, FR_RMSPROP, FR_ADAM = 0, 1, 2, 3
-FR_ADAM_DENSE, FR_ADAM_LAZY_EXACT = 0, 1
+FR_ADAM_DENSE, FR_ADAM_LAZY_EXACT, FR_ADAM_LAZY_SERIES = 0, 1, 2
 FR_POINTWISE, FR_BPR = 0, 1
 (FR_OUT_LOSS, FR_OUT_NORM, FR_OUT_SCALE, FR_OUT_GENERAL, FR_OUT_PERSONAL, FR_OUT_LR,
  FR_OUT_UNIQ_USERS, FR_OUT_UNIQ_ITEMS, FR_OUT_LABEL_ENTRIES, FR_OUT_OVERFLOW) = range(10)
@@ -86,7 +86,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("FOODREC_B200_LIB", _build.LIB)     # override: A/B builds of the same sources
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: build it with `python -m foodrec_b200._build` "

@@ -35,6 +35,7 @@ struct fr_ctx {
   uint32_t* counters = nullptr;
   float4* cat_pre = nullptr;
   float* lr_hist = nullptr; int64_t lr_hist_cap = 0;
+  double* cser = nullptr;          // LAZY_SERIES coefficient table [lr_hist_cap * SERIES_TERMS]
   double* mean_partials = nullptr;
   float* out_internal = nullptr;
   uint32_t* scan_tmp = nullptr;
@@ -147,8 +148,10 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   A(h->scan_tmp, S / 4096 + 2);
   h->lr_hist_cap = 1 << 16;
   A(h->lr_hist, (size_t)h->lr_hist_cap);
+  A(h->cser, (size_t)h->lr_hist_cap * SERIES_TERMS);
 #undef A
   FR_CUDA(h, cudaMemset(h->lr_hist, 0, (size_t)h->lr_hist_cap * sizeof(float)));
+  FR_CUDA(h, cudaMemset(h->cser, 0, (size_t)h->lr_hist_cap * SERIES_TERMS * sizeof(double)));
   FR_CUDA(h, cudaMemset(h->out_internal, 0, FR_OUT_COUNT * sizeof(float)));
   return FR_OK;
 }
@@ -214,13 +217,18 @@ static int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st) {
   int64_t cap = h->lr_hist_cap;
   while (cap <= need) cap *= 2;
   float* nb = nullptr;
+  double* nc = nullptr;
+  const size_t cb_old = (size_t)h->lr_hist_cap * SERIES_TERMS * sizeof(double), cb_new = (size_t)cap * SERIES_TERMS * sizeof(double);
   FR_CUDA(h, cudaMalloc(&nb, (size_t)cap * sizeof(float)));
+  FR_CUDA(h, cudaMalloc(&nc, cb_new));
   FR_CUDA(h, cudaMemsetAsync(nb, 0, (size_t)cap * sizeof(float), st));
+  FR_CUDA(h, cudaMemsetAsync(nc, 0, cb_new, st));
   FR_CUDA(h, cudaMemcpyAsync(nb, h->lr_hist, (size_t)h->lr_hist_cap * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  FR_CUDA(h, cudaMemcpyAsync(nc, h->cser, cb_old, cudaMemcpyDeviceToDevice, st));
   FR_CUDA(h, cudaStreamSynchronize(st));
-  for (auto& p : h->allocs) if (p == h->lr_hist) p = nb;
-  cudaFree(h->lr_hist);
-  h->lr_hist = nb; h->lr_hist_cap = cap;
+  for (auto& p : h->allocs) { if (p == h->lr_hist) p = nb; else if (p == h->cser) p = nc; }
+  cudaFree(h->lr_hist); cudaFree(h->cser);
+  h->lr_hist = nb; h->cser = nc; h->lr_hist_cap = cap;
   return FR_OK;
 }
 
@@ -239,6 +247,12 @@ extern "C" int fr_set_step(fr_handle h, int64_t step) {
     h->b1p *= h->cfg.adam_beta1; h->b2p *= h->cfg.adam_beta2;
   }
   FR_CUDA(h, cudaMemcpy(h->lr_hist, hist.data(), hist.size() * sizeof(float), cudaMemcpyHostToDevice));
+  FR_CUDA(h, cudaMemset(h->cser, 0, (size_t)h->lr_hist_cap * SERIES_TERMS * sizeof(double)));
+  if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_SERIES) {
+    Launch l{h->sm_count, 0, nullptr};
+    launch_series_rebuild(h->cser, h->lr_hist, (int)step, h->cfg.adam_beta1, h->cfg.adam_beta2, l);
+    FR_CUDA(h, cudaDeviceSynchronize());
+  }
   h->step = step;
   return FR_OK;
 }
@@ -251,6 +265,7 @@ static OptConsts make_oc(const fr_ctx* h, int64_t step) {
   oc.omb1 = 1.0f - oc.b1; oc.omb2 = 1.0f - oc.b2;
   oc.rho = h->cfg.rms_decay; oc.omrho = 1.0f - oc.rho; oc.rms_eps = h->cfg.rms_eps;
   oc.step = (int)step; oc.lr_hist = h->lr_hist;
+  oc.cser = h->cser; oc.l2b1 = log2f(oc.b1); oc.l2b2 = log2f(oc.b2);
   return oc;
 }
 
@@ -352,7 +367,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   const int ru = radix_sort_pairs(h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), st, h->sm_count);
   const int ri = radix_sort_pairs(h->sortI, (const uint32_t*)b->items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), st, h->sm_count);
   FR_CHECK_LAUNCH(h);
-  const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_EXACT;
+  const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
   if (lazy) {   // recipe rows of this batch must be current before anything reads them
     launch_item_catchup(NV, h->sortI.k[ri], (uint32_t)S, (float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R,
                         T.last_R, DV, oc, l);
@@ -389,25 +404,28 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     SegCommon c{};
     c.keys = h->sortU.k[ru]; c.perm = h->sortU.v[ru]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
     c.uniq_counter = h->counters + 0;
-    if (write_personal) {
-      const size_t need = (size_t)S / 32 + 2;
-      if (need > h->pieces_personal_chunks) {
-        if (h->pieces_personal) { FR_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->pieces_personal); h->pieces_personal = nullptr; }
-        FR_CUDA(h, cudaMalloc(&h->pieces_personal, need * 2 * 15 * DV * sizeof(float4)));
-        h->pieces_personal_chunks = need;
-      }
-      c.pieces = h->pieces_personal;
-    } else {
-      c.pieces = h->pieces_u;
-    }
+    c.pieces = h->pieces_u;
     UserPolParams up{};
     up.P = (float4*)T.P; up.s1 = (float4*)T.s1_P; up.s2 = (float4*)T.s2_P; up.last = T.last_P;
     up.R = (const float4*)T.R; up.G = (const float4*)T.G; up.cat = h->cat_pre;
     up.items = b->items; up.g = h->g; up.cats = cats; up.cats_by_item = cats_by_item;
     up.ws_row = h->ws_row; up.out = out; up.group = group; up.mc = h->mc; up.oc = oc;
     up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = b->users;
-    launch_user_pass(NV, write_personal ? 1 : 0, c, up, l);
+    launch_user_pass(NV, c, up, l);
     FR_CHECK_LAUNCH(h);
+    if (write_personal) {     // Write_Memory :149-198 on the optimizer's output; reads pre-step R, Cat, G
+      const size_t need = (size_t)S / 32 + 2;
+      if (need > h->pieces_personal_chunks) {
+        if (h->pieces_personal) { FR_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->pieces_personal); h->pieces_personal = nullptr; }
+        FR_CUDA(h, cudaMalloc(&h->pieces_personal, need * 2 * 10 * DV * sizeof(float4)));
+        h->pieces_personal_chunks = need;
+      }
+      c.pieces = h->pieces_personal;
+      c.uniq_counter = nullptr;
+      l.mid = nullptr;
+      launch_personal_pass(NV, c, up, l);
+      FR_CHECK_LAUNCH(h);
+    }
   }
 
   FR_MARK(FR_T_LABEL);
@@ -465,7 +483,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   launch_mean((const float4*)T.G, (int64_t)h->mc.L * 5 * DV, h->mean_partials, out + FR_OUT_GENERAL,
               (double)h->mc.L * 5.0 * h->mc.D, l);
   if (write_personal) {
-    if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_EXACT) {
+    if (lazy) {
       // mean(P) must see every row at step t
       launch_adam_sweep((float4*)T.P, (float4*)T.s1_P, (float4*)T.s2_P, T.last_P, h->cfg.num_users, 5 * DV, oc, (int)step, l);
     }
@@ -473,6 +491,8 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
                 (double)h->cfg.num_users * 5.0 * h->mc.D, l);
   }
   launch_write_counters(h->counters, out, l);
+  if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_SERIES)
+    launch_series_update(h->cser, h->lr_hist, (int)step, h->cfg.adam_beta1, h->cfg.adam_beta2, l);
   FR_CHECK_LAUNCH(h);
   FR_MARK(FR_T_COUNT);
 #undef FR_MARK

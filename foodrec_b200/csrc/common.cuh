@@ -63,8 +63,26 @@ __device__ __forceinline__ void st_stream(float4* p, const float4 v) {
 // movers are latency-bound (a warp's registers hold one table row at a time); prefetching
 // the rows of the NEXT work item turns their demand loads into L2 hits and gives the
 // memory system more bytes in flight without holding any registers.
-__device__ __forceinline__ void prefetch_l2_span(const void* p, uint32_t bytes) {
+// Build variants (bench A/B): -DFR_PREFETCH (TMA bulk) [-DFR_PREFETCH_LINES: per-128B prefetch.global.L2].
+__device__ __forceinline__ void prefetch_l2_span(const void* p, uint32_t bytes) {   // one lane, whole span
+#if !defined(FR_PREFETCH)   // measured on B200: no gain (kernels are not latency-bound), so off by default
+  (void)p; (void)bytes;
+#elif defined(FR_PREFETCH_LINES)
+  for (uint32_t o = 0; o < bytes; o += 128)
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(p) + o));
+#else
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void prefetch_l2_warp(const void* p, uint32_t bytes, int lane) {   // all lanes call
+#if !defined(FR_PREFETCH)   // measured on B200: no gain (kernels are not latency-bound), so off by default
+  (void)p; (void)bytes; (void)lane;
+#elif defined(FR_PREFETCH_LINES)
+  for (uint32_t o = (uint32_t)lane * 128u; o < bytes; o += 32u * 128u)
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(p) + o));
+#else
+  if (lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+#endif
 }
 
 template <int NV>

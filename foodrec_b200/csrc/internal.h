@@ -37,7 +37,13 @@ struct OptConsts {
   float rho, omrho, rms_eps;
   int step;            // t of this step (1-based)
   const float* lr_hist;  // lr_t of every past step, index = step
+  // LAZY_SERIES: cser[5*t0 + n] = C_n(t0 -> current step count), see foodrec_b200.h
+  const double* cser;
+  float l2b1, l2b2;    // log2(beta1), log2(beta2)
 };
+
+constexpr int SERIES_TERMS = 5;
+constexpr int SERIES_WINDOW = 2048;   // b1^j underflows fp32 long before j = 2048
 
 struct ModelConsts {
   int D, DV, L;

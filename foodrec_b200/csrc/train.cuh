@@ -72,7 +72,8 @@ void launch_prep_rows(int mode, int B, const int32_t* users, const float* labels
 void launch_fwd_train(int NV, int group, const FwdParams& p, int grid, const Launch& l);
 int fwd_train_grid(int B, int sm_count);
 void launch_finalize(const FinalizeParams& p, const Launch& l);
-void launch_user_pass(int NV, int personal, const SegCommon& c, const UserPolParams& p, const Launch& l);
+void launch_user_pass(int NV, const SegCommon& c, const UserPolParams& p, const Launch& l);
+void launch_personal_pass(int NV, const SegCommon& c, const UserPolParams& p, const Launch& l);
 void launch_item_pass(int NV, const SegCommon& c, const ItemPolParams& p, const Launch& l);
 void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, const Launch& l);
 void launch_label_count(const LabelEmitParams& p, const Launch& l);
@@ -80,6 +81,8 @@ void launch_label_emit(const LabelEmitParams& p, const Launch& l);
 void launch_adam_sweep(float4* var, float4* m, float4* v, int32_t* last, int64_t nrows, int rowDV,
                        const OptConsts& oc, int target_step, const Launch& l);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, const Launch& l);
+void launch_series_update(double* cser, const float* lr_hist, int t, float b1, float b2, const Launch& l);
+void launch_series_rebuild(double* cser, const float* lr_hist, int step, float b1, float b2, const Launch& l);
 void launch_item_catchup(int NV, const uint32_t* keys, uint32_t n, float4* R, float4* m, float4* v,
                          int32_t* last, int DV, const OptConsts& oc, const Launch& l);
 void launch_mean(const float4* x, int64_t n4, double* partials, float* out_slot, double count, const Launch& l);

@@ -1,0 +1,556 @@
+// Sort-and-segment reduce of the sparse gradients, fused with the optimizer
+// (Model_Recommender.py:236-240) and with Write_Memory (:106-220).
+//
+// Entries are sorted by key (stable radix sort, sort.cu).  A warp owns CHUNK = 32
+// consecutive entries and walks the runs of equal keys inside them in batch order -- the
+// order TF's unsorted_segment_sum uses.  A run fully inside the chunk is reduced and applied
+// immediately (state rows are requested before the reduction so both are in flight).  A run
+// that crosses a chunk boundary leaves a partial ("piece") in slot 0 (run contains the
+// chunk's first entry) or slot 1 (otherwise); seg_combine_kernel then sums a crossing run's
+// pieces in chunk order -- deterministic, no atomics -- and applies it once.
+//
+// Every kernel here is an HBM-bound row mover: one warp holds one table row at a time, a
+// row of D floats moves as 16-byte vectors (lane l <-> float4 l, l+32, ...), the four
+// category rows live in shared memory.
+#include "optim.cuh"
+#include "train.cuh"
+
+namespace fr {
+
+template <class Pol>
+__global__ void __launch_bounds__(FR_THREADS)
+seg_chunk_kernel(const SegCommon c, const Pol pol) {
+  extern __shared__ float4 smem[];
+  constexpr int NR = Pol::NR, NV = Pol::NV;
+  const int DV = pol.DV();
+  if (pol.cat_src()) {
+    for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) smem[i] = pol.cat_src()[i];
+    __syncthreads();
+  }
+  const uint32_t n = c.n_dev ? min(*c.n_dev, c.n_host) : c.n_host;
+  const uint32_t nchunks = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const uint32_t nw = gridDim.x * FR_WARPS_PER_BLOCK;
+  for (uint32_t chunk = gw; chunk < nchunks; chunk += nw) {
+    const uint32_t base = chunk << 5;
+    const int cnt = (int)min(32u, n - base);
+    const bool valid = lane < cnt;
+    const uint32_t key = valid ? c.keys[base + lane] : 0xffffffffu;
+    const uint32_t ent = valid ? c.perm[base + lane] : 0u;
+    const uint32_t prevKey = base > 0 ? c.keys[base - 1] : 0u;
+    const bool has_next = base + 32 < n;
+    const uint32_t nextKey = has_next ? c.keys[base + 32] : 0u;
+    const typename Pol::Entry e = pol.load_entry(ent, valid);
+    const uint32_t up = __shfl_up_sync(FR_FULL, key, 1);
+    const bool head = valid && (lane == 0 ? (base == 0 || prevKey != key) : (up != key));
+    const uint32_t hm = __ballot_sync(FR_FULL, head);
+    const uint32_t lastKey = __shfl_sync(FR_FULL, key, cnt - 1);
+    const bool from_prev = !(hm & 1u);
+    const bool to_next = has_next && nextKey == lastKey;
+    if (c.uniq_counter && lane == 0) atomicAdd(c.uniq_counter, (uint32_t)__popc(hm));
+    int e0 = 0;
+    while (e0 < cnt) {
+      const uint32_t rest = (e0 >= 31) ? 0u : (hm & ~((2u << e0) - 1u));
+      const int e1 = rest ? (__ffs(rest) - 1) : cnt;
+      const bool starts = (e0 > 0) || !from_prev;
+      const bool ends = (e1 < cnt) || !to_next;
+      const uint32_t k = __shfl_sync(FR_FULL, key, e0);
+      float4 acc[NR][NV];
+#pragma unroll
+      for (int s = 0; s < NR; ++s)
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[s][q] = f4zero();
+      const bool contained = starts && ends;
+      typename Pol::State st;
+      if (contained) pol.load_state(st, k, lane);      // requested first: in flight during the reduce
+      pol.accumulate(acc, e, e0, e1, lane, smem);      // (one instance: the kernel must fit the I-cache)
+      if (contained) {
+        pol.apply(st, k, acc, lane);
+      } else {
+        float4* dst = c.pieces + ((size_t)chunk * 2 + (e0 == 0 ? 0 : 1)) * NR * DV;
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const int i = lane + 32 * q;
+            if (i < DV) __stcg(dst + s * DV + i, acc[s][q]);
+          }
+      }
+      e0 = e1;
+    }
+  }
+}
+
+template <class Pol>
+__global__ void __launch_bounds__(FR_THREADS)
+seg_combine_kernel(const SegCommon c, const Pol pol) {
+  constexpr int NR = Pol::NR, NV = Pol::NV;
+  const int DV = pol.DV();
+  const uint32_t n = c.n_dev ? min(*c.n_dev, c.n_host) : c.n_host;
+  const uint32_t nchunks = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const uint32_t nw = gridDim.x * FR_WARPS_PER_BLOCK;
+  for (uint32_t chunk = gw; chunk < nchunks; chunk += nw) {
+    const uint32_t base = chunk << 5;
+    if (base + 32 >= n) continue;                       // last chunk: nothing continues
+    const uint32_t lastKey = c.keys[base + 31];
+    if (c.keys[base + 32] != lastKey) continue;         // its last run ends here
+    // does the run that crosses into chunk+1 START in this chunk?
+    const uint32_t key = c.keys[base + lane];
+    const uint32_t prevKey = base > 0 ? c.keys[base - 1] : 0u;
+    const uint32_t up = __shfl_up_sync(FR_FULL, key, 1);
+    const bool head = lane == 0 ? (base == 0 || prevKey != key) : (up != key);
+    const uint32_t hm = __ballot_sync(FR_FULL, head);
+    if (hm == 0) continue;                              // run started in an earlier chunk
+    const int s0 = 31 - __clz(hm);                      // start of the chunk's last run
+    float4 acc[NR][NV];
+    {
+      const float4* src = c.pieces + ((size_t)chunk * 2 + (s0 == 0 ? 0 : 1)) * NR * DV;
+#pragma unroll
+      for (int s = 0; s < NR; ++s)
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          const int i = lane + 32 * q;
+          acc[s][q] = i < DV ? __ldcg(src + s * DV + i) : f4zero();
+        }
+    }
+    // end of the run: first position > base+31 whose key differs (binary search: the keys
+    // are sorted), so the piece loads below are independent and can be pipelined
+    uint32_t lo = base + 32, hi = n;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (c.keys[mid] == lastKey) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t kend = (lo - 1) >> 5;          // last chunk holding an entry of the run
+    constexpr int PF = (NR * NV <= 2) ? 8 : (NR * NV <= 5 ? 4 : 2);
+    for (uint32_t kc = chunk + 1; kc <= kend; kc += PF) {
+      float4 buf[PF][NR][NV];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const float4* src = c.pieces + ((size_t)(kc + u) * 2) * NR * DV;
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const int i = lane + 32 * q;
+            buf[u][s][q] = (kc + u <= kend && i < DV) ? __ldcg(src + s * DV + i) : f4zero();
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u)      // summed in chunk order: deterministic
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) acc[s][q] = add4(acc[s][q], buf[u][s][q]);
+    }
+    typename Pol::State st;
+    pol.load_state(st, lastKey, lane);
+    pol.apply(st, lastKey, acc, lane);
+  }
+}
+
+// ---- per-entry contributions shared by the user / personal / label policies ------------
+// pooledCat (normalised) and the category weights of one item row.
+// One IEEE reciprocal of the category count n per entry; pooledCat and the weights w_c use
+// x * (1/n) (exact for n = 1, 2, 4; 1 ulp from x/n for n = 3) -- eight divisions less per
+// entry in the code the warp loops over.
+template <int NV>
+struct RowTerms { float4 pc[NV]; float4 w; };
+template <int NV>
+__device__ __forceinline__ RowTerms<NV> row_terms(const float4 m, const float4* sCat, int DV, int lane) {
+  RowTerms<NV> t;
+  float4 pcs[NV];
+  pooled_cat<NV>(pcs, sCat, m, DV, lane);
+  const float rn = __frcp_rn(((m.x + m.y) + m.z) + m.w);
+  t.w = make_float4(m.x * rn, m.y * rn, m.z * rn, m.w * rn);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) t.pc[k] = scale4(rn, pcs[k]);
+  return t;
+}
+
+// ---- policy: Personal_Memory rows.  grad slice of item row r (App. A.3):
+//   dP[u,0]   += g*a*pooledCat_r ;  dP[u,1+c] += g*(1-a)*w_rc*R[i_r]
+template <int NVV, int OPT>
+struct UserPol {
+  static constexpr int NV = NVV;
+  static constexpr int NR = 5;
+  UserPolParams p;
+  struct Entry { int item; float g; float4 m; };
+  using State = RowState<5, NVV>;
+  __device__ __forceinline__ int DV() const { return p.mc.DV; }
+  __device__ __forceinline__ const float4* cat_src() const { return p.cat; }
+  __device__ __forceinline__ Entry load_entry(uint32_t row, bool valid) const {
+    Entry e; e.item = 0; e.g = 0.f; e.m = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      e.item = p.items[row];
+      e.g = p.g[row] * p.out[FR_OUT_SCALE];
+      e.m = __ldg(p.cats + (p.cats_by_item ? e.item : (int)row));
+    }
+    return e;
+  }
+  __device__ __forceinline__ void accumulate(float4 (&acc)[5][NV], const Entry& e, int e0, int e1, int lane,
+                                             const float4* sCat) const {
+    const int DVv = p.mc.DV;
+    // two recipe rows in flight per iteration (a BPR triple is exactly one such pair)
+    for (int j0 = e0; j0 < e1; j0 += 2) {
+      const int jn = (j0 + 1 < e1) ? j0 + 1 : j0;
+      float4 rr2[2][NV];
+      load_row_ro<NV>(rr2[0], p.R + (size_t)__shfl_sync(FR_FULL, e.item, j0) * DVv, DVv, lane);
+      load_row_ro<NV>(rr2[1], p.R + (size_t)__shfl_sync(FR_FULL, e.item, jn) * DVv, DVv, lane);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = j0 + u;
+        if (j >= e1) break;
+        const float g = __shfl_sync(FR_FULL, e.g, j);
+        const float4 m = shfl4(e.m, j);
+        const RowTerms<NV> t = row_terms<NV>(m, sCat, DVv, lane);
+        const float ga = g * p.mc.a, go = g * p.mc.oma;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          mad4_rn(acc[0][k], ga, t.pc[k]);
+          mad4_rn(acc[1][k], go * t.w.x, rr2[u][k]); mad4_rn(acc[2][k], go * t.w.y, rr2[u][k]);
+          mad4_rn(acc[3][k], go * t.w.z, rr2[u][k]); mad4_rn(acc[4][k], go * t.w.w, rr2[u][k]);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
+    fr::load_state<OPT, 5, NV>(st, p.P, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
+  }
+  __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[5][NV], int lane) const {
+    apply_and_store<OPT, 5, NV>(st, p.P, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
+  }
+};
+
+// ---- policy: the personal-memory write of Write_Memory (:149-198), personal steps only
+// (first batch of epoch 0 and w.p. 1e-5: 16 mini-steps of 8 rows, Train_recommender.py:170-187).
+// acc rows 0..4 = bias (sum of per-sample deltas), rows 5..9 = sum of the label-mean of
+// G_old.  Runs right after the optimizer pass on P:  P = (P_opt + bias) + alpha*general_bias.
+template <int NVV>
+struct PersonalPol {
+  static constexpr int NV = NVV;
+  static constexpr int NR = 10;
+  UserPolParams p;
+  struct Entry { int item; float ws; float4 m; int grp; };
+  struct State { float4 var[5][NVV]; };
+  __device__ __forceinline__ int DV() const { return p.mc.DV; }
+  __device__ __forceinline__ const float4* cat_src() const { return p.cat; }
+  __device__ __forceinline__ Entry load_entry(uint32_t row, bool valid) const {
+    Entry e; e.item = 0; e.ws = 0.f; e.m = make_float4(1.f, 0.f, 0.f, 0.f); e.grp = 0;
+    if (valid) {
+      e.item = p.items[row];
+      e.ws = p.ws_row[row];
+      e.m = __ldg(p.cats + (p.cats_by_item ? e.item : (int)row));
+      e.grp = (int)row / p.group;
+    }
+    return e;
+  }
+  __device__ __forceinline__ void accumulate(float4 (&acc)[10][NV], const Entry& e, int e0, int e1, int lane,
+                                             const float4* sCat) const {
+    const int DVv = p.mc.DV;
+    for (int j = e0; j < e1; ++j) {
+      const int it = __shfl_sync(FR_FULL, e.item, j);
+      const float ws = __shfl_sync(FR_FULL, e.ws, j);
+      const float4 m = shfl4(e.m, j);
+      const int grp = __shfl_sync(FR_FULL, e.grp, j);
+      float4 rr[NV];
+      load_row_ro<NV>(rr, p.R + (size_t)it * DVv, DVv, lane);
+      const RowTerms<NV> t = row_terms<NV>(m, sCat, DVv, lane);
+      const float hc = p.mc.beta_2 * ws, lc = p.mc.beta_1 * ws;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        mad4_rn(acc[0][k], hc, t.pc[k]);                                                   // :140-144
+        mad4_rn(acc[1][k], lc, scale4(m.x, rr[k])); mad4_rn(acc[2][k], lc, scale4(m.y, rr[k]));   // :111-119
+        mad4_rn(acc[3][k], lc, scale4(m.z, rr[k])); mad4_rn(acc[4][k], lc, scale4(m.w, rr[k]));
+      }
+      // (sum_l lam_l G_old[l]) / sum_l lam_l   (:170-186)
+      float4 gs[5][NV];
+#pragma unroll
+      for (int s = 0; s < 5; ++s)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) gs[s][k] = f4zero();
+      float lsum = 0.f;
+      if (p.user_labels) {
+        for (int l = 0; l < p.mc.L; ++l) {
+          const float lam = p.user_labels[(size_t)grp * p.mc.L + l];
+          if (lam != 0.f) {
+            lsum += lam;
+#pragma unroll
+            for (int s = 0; s < 5; ++s)
+#pragma unroll
+              for (int k = 0; k < NV; ++k) {
+                const int i = lane + 32 * k;
+                if (i < DVv) fma4(gs[s][k], lam, p.G[((size_t)l * 5 + s) * DVv + i]);
+              }
+          }
+        }
+      } else {
+        const int u = p.users[grp];
+        for (int q = p.lab_off[u]; q < p.lab_off[u + 1]; ++q) {
+          const int l = p.lab_idx[q];
+          lsum += 1.f;
+#pragma unroll
+          for (int s = 0; s < 5; ++s)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              const int i = lane + 32 * k;
+              if (i < DVv) gs[s][k] = add4(gs[s][k], p.G[((size_t)l * 5 + s) * DVv + i]);
+            }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 5; ++s)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[5 + s][k] = add4(acc[5 + s][k], div4(gs[s][k], lsum));
+    }
+  }
+  __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
+    const int DVv = p.mc.DV;
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        st.var[s][k] = i < DVv ? p.P[((size_t)key * 5 + s) * DVv + i] : f4zero();
+      }
+  }
+  __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[10][NV], int lane) const {
+    const int DVv = p.mc.DV;
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        if (i >= DVv) continue;
+        float4 v = add4(st.var[s][k], acc[s][k]);                  // P + bias           (:167)
+        v = add4(v, scale4(p.mc.alpha, acc[5 + s][k]));            // + alpha*general_bias (:196-198)
+        p.P[((size_t)key * 5 + s) * DVv + i] = v;
+      }
+  }
+};
+
+// ---- policy: Recipe_Embedding rows.  dR[i] += g * z_r  (z stashed by the forward pass)
+template <int NVV, int OPT>
+struct ItemPol {
+  static constexpr int NV = NVV;
+  static constexpr int NR = 1;
+  ItemPolParams p;
+  struct Entry { float g; uint32_t row; };
+  using State = RowState<1, NVV>;
+  __device__ __forceinline__ int DV() const { return p.mc.DV; }
+  __device__ __forceinline__ const float4* cat_src() const { return nullptr; }
+  __device__ __forceinline__ Entry load_entry(uint32_t row, bool valid) const {
+    Entry e; e.g = 0.f; e.row = row;
+    if (valid) e.g = p.g[row] * p.out[FR_OUT_SCALE];
+    return e;
+  }
+  __device__ __forceinline__ void accumulate(float4 (&acc)[1][NV], const Entry& e, int e0, int e1, int lane,
+                                             const float4*) const {
+    const int DVv = p.mc.DV;
+    constexpr int PF = 4;                       // z rows in flight
+    for (int j0 = e0; j0 < e1; j0 += PF) {
+      float4 zz[PF][NV];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const uint32_t row = __shfl_sync(FR_FULL, e.row, min(j0 + u, e1 - 1));
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int i = lane + 32 * k;
+          zz[u][k] = i < DVv ? __ldcg(p.z + (size_t)row * DVv + i) : f4zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (j0 + u >= e1) break;
+        const float g = __shfl_sync(FR_FULL, e.g, j0 + u);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) mad4_rn(acc[0][k], g, zz[u][k]);
+      }
+    }
+  }
+  __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
+    fr::load_state<OPT, 1, NV>(st, p.R, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
+  }
+  __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[1][NV], int lane) const {
+    apply_and_store<OPT, 1, NV>(st, p.R, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
+  }
+};
+
+// ---- policy: General_Memory rows (Write_Memory :201-215), entries = non-zeros of the
+// label feed sorted by label:  G[l] += sum lam*ws*[beta_2*pooledCat ; beta_1*m_c*R[i]]
+template <int NVV>
+struct LabelPol {
+  static constexpr int NV = NVV;
+  static constexpr int NR = 5;
+  LabelPolParams p;
+  struct Entry { int item; float coef; float4 m; };
+  struct State { float4 var[5][NVV]; };
+  __device__ __forceinline__ int DV() const { return p.mc.DV; }
+  __device__ __forceinline__ const float4* cat_src() const { return p.cat; }
+  __device__ __forceinline__ Entry load_entry(uint32_t ent, bool valid) const {
+    Entry e; e.item = 0; e.coef = 0.f; e.m = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const uint32_t row = p.ent_row[ent];
+      e.item = p.items[row];
+      e.coef = p.ent_coef[ent];
+      e.m = __ldg(p.cats + (p.cats_by_item ? e.item : (int)row));
+    }
+    return e;
+  }
+  __device__ __forceinline__ void accumulate(float4 (&acc)[5][NV], const Entry& e, int e0, int e1, int lane,
+                                             const float4* sCat) const {
+    const int DVv = p.mc.DV;
+    constexpr int PF = 4;                       // recipe rows in flight
+    for (int j0 = e0; j0 < e1; j0 += PF) {
+      float4 rr4[PF][NV];
+#pragma unroll
+      for (int u = 0; u < PF; ++u)
+        load_row_ro<NV>(rr4[u], p.R + (size_t)__shfl_sync(FR_FULL, e.item, min(j0 + u, e1 - 1)) * DVv, DVv, lane);
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int j = j0 + u;
+        if (j >= e1) break;
+        const float coef = __shfl_sync(FR_FULL, e.coef, j);
+        const float4 m = shfl4(e.m, j);
+        const RowTerms<NV> t = row_terms<NV>(m, sCat, DVv, lane);
+        const float hc = p.mc.beta_2 * coef, lc = p.mc.beta_1 * coef;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          mad4_rn(acc[0][k], hc, t.pc[k]);
+          mad4_rn(acc[1][k], lc, scale4(m.x, rr4[u][k])); mad4_rn(acc[2][k], lc, scale4(m.y, rr4[u][k]));
+          mad4_rn(acc[3][k], lc, scale4(m.z, rr4[u][k])); mad4_rn(acc[4][k], lc, scale4(m.w, rr4[u][k]));
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
+    const int DVv = p.mc.DV;
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        st.var[s][k] = i < DVv ? p.G[((size_t)key * 5 + s) * DVv + i] : f4zero();
+      }
+  }
+  __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[5][NV], int lane) const {
+    const int DVv = p.mc.DV;
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < DVv) p.G[((size_t)key * 5 + s) * DVv + i] = add4(st.var[s][k], acc[s][k]);
+      }
+  }
+};
+
+template <class Pol>
+static void launch_seg(const SegCommon& c, const Pol& pol, int DV, bool needs_cat, const Launch& l) {
+  const uint32_t nchunks = (c.n_host + 31) / 32;
+  if (nchunks == 0) return;
+  int grid = (int)((nchunks + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
+  const size_t smem = needs_cat ? (size_t)4 * DV * sizeof(float4) : 0;
+  // more CTAs than are resident: the block scheduler then balances the uneven per-chunk
+  // work (measured: x16 beats a resident-sized persistent grid)
+  const int cap = l.sm_count * 16;
+  if (grid > cap) grid = cap;
+  seg_chunk_kernel<Pol><<<grid, FR_THREADS, smem, l.st>>>(c, pol);
+  if (l.mid) cudaEventRecord(l.mid, l.st);
+  seg_combine_kernel<Pol><<<grid, FR_THREADS, 0, l.st>>>(c, pol);
+  g_launches += 2;
+}
+
+#define FR_DISPATCH_NV_OPT(NVx, OPTx, ...)                                                  \
+  do {                                                                                        \
+    if ((NVx) == 1) {                                                                         \
+      switch (OPTx) {                                                                         \
+        case OPT_ADAM_DENSE:  { constexpr int NV_ = 1, OPT_ = OPT_ADAM_DENSE;  __VA_ARGS__ } break;  \
+        case OPT_ADAM_EXACT:  { constexpr int NV_ = 1, OPT_ = OPT_ADAM_EXACT;  __VA_ARGS__ } break;  \
+        case OPT_ADAM_SERIES: { constexpr int NV_ = 1, OPT_ = OPT_ADAM_SERIES; __VA_ARGS__ } break;  \
+        default:              { constexpr int NV_ = 1, OPT_ = OPT_GENERIC;     __VA_ARGS__ } break;  \
+      }                                                                                       \
+    } else {                                                                                  \
+      switch (OPTx) {                                                                         \
+        case OPT_ADAM_DENSE:  { constexpr int NV_ = 2, OPT_ = OPT_ADAM_DENSE;  __VA_ARGS__ } break;  \
+        case OPT_ADAM_EXACT:  { constexpr int NV_ = 2, OPT_ = OPT_ADAM_EXACT;  __VA_ARGS__ } break;  \
+        case OPT_ADAM_SERIES: { constexpr int NV_ = 2, OPT_ = OPT_ADAM_SERIES; __VA_ARGS__ } break;  \
+        default:              { constexpr int NV_ = 2, OPT_ = OPT_GENERIC;     __VA_ARGS__ } break;  \
+      }                                                                                       \
+    }                                                                                         \
+  } while (0)
+
+void launch_user_pass(int NV, const SegCommon& c, const UserPolParams& p, const Launch& l) {
+  const int opt = opt_of(p.oc.learner, p.oc.adam_mode);
+  FR_DISPATCH_NV_OPT(NV, opt, { UserPol<NV_, OPT_> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); });
+}
+void launch_personal_pass(int NV, const SegCommon& c, const UserPolParams& p, const Launch& l) {
+  if (NV == 1) { PersonalPol<1> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
+  else { PersonalPol<2> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
+}
+void launch_item_pass(int NV, const SegCommon& c, const ItemPolParams& p, const Launch& l) {
+  const int opt = opt_of(p.oc.learner, p.oc.adam_mode);
+  FR_DISPATCH_NV_OPT(NV, opt, { ItemPol<NV_, OPT_> pol{p}; launch_seg(c, pol, p.mc.DV, false, l); });
+}
+void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, const Launch& l) {
+  if (NV == 1) { LabelPol<1> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
+  else { LabelPol<2> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
+}
+
+// ---- lazy Adam: the batch's unique recipe rows are brought to step-1 before anything
+// reads them (forward, dP accumulation, Write_Memory all read R).  keys = recipe ids of the
+// item rows, sorted; the warp that sees a run's head owns that row.
+template <int NV, int OPT>
+__global__ void __launch_bounds__(FR_THREADS)
+item_catchup_kernel(const uint32_t* __restrict__ keys, uint32_t n, float4* __restrict__ R,
+                    float4* __restrict__ m, float4* __restrict__ v, int32_t* __restrict__ last,
+                    int DV, const OptConsts oc) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const uint32_t nw = gridDim.x * FR_WARPS_PER_BLOCK;
+  const uint32_t nchunks = (n + 31) >> 5;
+  const int to = oc.step - 1;
+  for (uint32_t chunk = gw; chunk < nchunks; chunk += nw) {
+    const uint32_t base = chunk << 5;
+    const bool valid = base + lane < n;
+    const uint32_t key = valid ? keys[base + lane] : 0xffffffffu;
+    const uint32_t prevKey = base > 0 ? keys[base - 1] : 0u;
+    const uint32_t up = __shfl_up_sync(FR_FULL, key, 1);
+    const bool head = valid && (lane == 0 ? (base == 0 || prevKey != key) : (up != key));
+    uint32_t hm = __ballot_sync(FR_FULL, head);
+    while (hm) {
+      const int e = __ffs(hm) - 1;
+      hm &= hm - 1;
+      const uint32_t k = __shfl_sync(FR_FULL, key, e);
+      const int lastk = last[k];
+      __syncwarp();
+      if (lastk >= to) continue;
+      float4 x[NV], mm[NV], vv[NV];
+      load_row<NV>(mm, m + (size_t)k * DV, DV, lane);
+      load_row<NV>(vv, v + (size_t)k * DV, DV, lane);
+      load_row<NV>(x, R + (size_t)k * DV, DV, lane);
+      adam_catchup<OPT, NV>(x, mm, vv, lastk, to, oc);
+      store_row<NV>(R + (size_t)k * DV, x, DV, lane);
+      store_row<NV>(m + (size_t)k * DV, mm, DV, lane);
+      store_row<NV>(v + (size_t)k * DV, vv, DV, lane);
+      if (lane == 0) last[k] = to;
+    }
+  }
+}
+void launch_item_catchup(int NV, const uint32_t* keys, uint32_t n, float4* R, float4* m, float4* v,
+                         int32_t* last, int DV, const OptConsts& oc, const Launch& l) {
+  const uint32_t nchunks = (n + 31) / 32;
+  if (nchunks == 0) return;
+  int grid = (int)((nchunks + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
+  if (grid > l.sm_count * 16) grid = l.sm_count * 16;
+  const bool series = oc.adam_mode == FR_ADAM_LAZY_SERIES;
+#define FR_ICU(NVV, OO) item_catchup_kernel<NVV, OO><<<grid, FR_THREADS, 0, l.st>>>(keys, n, R, m, v, last, DV, oc)
+  if (NV == 1) { if (series) FR_ICU(1, OPT_ADAM_SERIES); else FR_ICU(1, OPT_ADAM_EXACT); }
+  else         { if (series) FR_ICU(2, OPT_ADAM_SERIES); else FR_ICU(2, OPT_ADAM_EXACT); }
+#undef FR_ICU
+  ++g_launches;
+}
+
+}  // namespace fr

@@ -44,7 +44,7 @@ def _ptr(t):
 
 class Engine:
     def __init__(self, hyper: Hyper, P, R, Cat, G, device="cuda:0", max_rows=1 << 16,
-                 max_label_entries=None, adam_mode="lazy_exact", item_cats=None, user_labels=None,
+                 max_label_entries=None, adam_mode="lazy", item_cats=None, user_labels=None,
                  user_label_csr=None):
         self.lib = L.lib()                       # raises if the .so is missing
         if not torch.cuda.is_available():
@@ -59,7 +59,11 @@ class Engine:
         assert five == 5 and self.Cat.shape == (4, self.D) and self.R.shape[1] == self.D
         self.I, self.Lb = self.R.shape[0], self.G.shape[0]
         self.learner = L.learner_code(hyper.learner)
-        self.adam_mode = L.FR_ADAM_LAZY_EXACT if adam_mode == "lazy_exact" else L.FR_ADAM_DENSE
+        modes = {"dense": L.FR_ADAM_DENSE, "lazy_exact": L.FR_ADAM_LAZY_EXACT,
+                 "lazy": L.FR_ADAM_LAZY_SERIES, "lazy_series": L.FR_ADAM_LAZY_SERIES}
+        if adam_mode not in modes:
+            raise ValueError(f"adam_mode must be one of {sorted(modes)}")
+        self.adam_mode = modes[adam_mode]
         z = torch.zeros_like
         self.s1 = {}; self.s2 = {}
         tabs = {"P": self.P, "R": self.R, "Cat": self.Cat}
@@ -224,7 +228,7 @@ class Engine:
 
     def flush(self):
         """Lazy-exact Adam: bring every row to the current step before the tables are read."""
-        if self._dirty and self.learner == L.FR_ADAM and self.adam_mode == L.FR_ADAM_LAZY_EXACT:
+        if self._dirty and self.learner == L.FR_ADAM and self.adam_mode != L.FR_ADAM_DENSE:
             L.check(self.handle, self.lib.fr_adam_flush(self.handle, self._stream()))
         self._dirty = False
 

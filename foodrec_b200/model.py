@@ -40,7 +40,7 @@ class Handle:
 
 class Model:
     def __init__(self, args, Personal_Memory, Recipe_Embedding, Category_Embedding, General_Memory,
-                 device="cuda:0", max_batch=None, adam_mode="lazy_exact"):
+                 device="cuda:0", max_batch=None, adam_mode="lazy"):
         self.learner = args.learner
         self.num_categories = args.num_categories
         self.num_users = args.num_users
