@@ -471,6 +471,10 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
 
   l.mid = nullptr;
   FR_MARK(FR_T_SWEEP);
+  // LAZY_SERIES table: every catch-up of this step (target t-1) is done; add the s = t term so
+  // that the table serves target t (the personal-step sweep below, fr_adam_flush, step t+1)
+  if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_SERIES)
+    launch_series_update(h->cser, h->lr_hist, (int)step, h->cfg.adam_beta1, h->cfg.adam_beta2, l);
   // 7. TF-1.x dense Adam: every untouched row decays this step too
   if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_DENSE) {
     launch_adam_sweep((float4*)T.P, (float4*)T.s1_P, (float4*)T.s2_P, T.last_P, h->cfg.num_users, 5 * DV, oc, (int)step, l);
@@ -491,8 +495,6 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
                 (double)h->cfg.num_users * 5.0 * h->mc.D, l);
   }
   launch_write_counters(h->counters, out, l);
-  if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_SERIES)
-    launch_series_update(h->cser, h->lr_hist, (int)step, h->cfg.adam_beta1, h->cfg.adam_beta2, l);
   FR_CHECK_LAUNCH(h);
   FR_MARK(FR_T_COUNT);
 #undef FR_MARK

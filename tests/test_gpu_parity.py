@@ -109,7 +109,7 @@ def test_pointwise_steps_match_oracle(learner, adam_mode, D):
         v = step_gpu(e, f)
         assert v[0] == pytest.approx(o["loss"], rel=1e-5), f"loss step {s}"
         assert v[1] == pytest.approx(o["norm"], rel=1e-5), f"norm step {s}"
-        assert v[3] == pytest.approx(o["general"], rel=1e-5, abs=1e-9), f"general step {s}"
+        assert v[3] == pytest.approx(o["general"], rel=1e-5, abs=1e-5 * float(np.abs(om.G).mean())), f"general step {s}"
         assert int(v[6]) == len(np.unique(f["user_input"])) and int(v[7]) == len(np.unique(f["item_input"]))
     compare_tables(e, om, what=f"{learner}/{adam_mode}/D{D} ", om32=om32)
 
@@ -129,7 +129,7 @@ def test_bpr_steps_match_oracle(learner):
         assert v[0] == pytest.approx(o["loss"], rel=1e-5)
         assert v[1] == pytest.approx(o["norm"], rel=1e-5)
         if s == 0:
-            assert v[4] == pytest.approx(o["personal"], rel=1e-5, abs=1e-9)
+            assert v[4] == pytest.approx(o["personal"], rel=1e-5, abs=1e-5 * float(np.abs(om.P).mean()))
     compare_tables(e, om, what=f"bpr/{learner} ", om32=om32)
 
 
@@ -149,8 +149,8 @@ def test_personal_write_step_matches_oracle(learner):
             om32.train_step(fm, write_personal=True)
         v = step_gpu(e, fm, personal=True)
         assert v[0] == pytest.approx(o["loss"], rel=1e-5)
-        assert v[4] == pytest.approx(o["personal"], rel=1e-5, abs=1e-9)
-        assert v[3] == pytest.approx(o["general"], rel=1e-5, abs=1e-9)
+        assert v[4] == pytest.approx(o["personal"], rel=1e-5, abs=1e-5 * float(np.abs(om.P).mean()))
+        assert v[3] == pytest.approx(o["general"], rel=1e-5, abs=1e-5 * float(np.abs(om.G).mean()))
     compare_tables(e, om, what=f"personal/{learner} ", om32=om32)
 
 
@@ -278,9 +278,10 @@ def test_cuda_path_matches_golden(learner, mode):
         v = step_gpu(e, f, personal=(s == 0), bpr=(mode == "bpr"))
         assert v[0] == pytest.approx(float(g[f"loss{s}"]), rel=1e-5)
         assert v[1] == pytest.approx(float(g[f"norm{s}"]), rel=1e-5)
-        assert v[3] == pytest.approx(float(g[f"general{s}"]), rel=1e-5, abs=1e-9)
+        # means of a table are sums that cancel: judged against the scale of the averaged terms
+        assert v[3] == pytest.approx(float(g[f"general{s}"]), rel=1e-5, abs=1e-5 * float(np.abs(g["G"]).mean()))
         if s == 0:
-            assert v[4] == pytest.approx(float(g["personal0"]), rel=1e-5, abs=1e-9)
+            assert v[4] == pytest.approx(float(g["personal0"]), rel=1e-5, abs=1e-5 * float(np.abs(g["P"]).mean()))
     t = e.tables()
     for k in ("P", "R", "Cat", "G"):
         if learner == "adam" and k != "G":
@@ -362,7 +363,7 @@ def test_session_protocol_runs_the_reference_loop():
                     of = dict(user_input=np.asarray(ui[s0:s1]).astype(np.int32), item_input=ii[s0:s1],
                               labels=y[s0:s1], categories=c[s0:s1], write_sign=ws[s0:s1], user_one_hot_label=ul[s0:s1])
                     o = om.train_step(of, write_personal=True); om32.train_step(of, write_personal=True)
-                    assert loss == pytest.approx(o["loss"], rel=1e-5) and personal == pytest.approx(o["personal"], rel=1e-5, abs=1e-9)
+                    assert loss == pytest.approx(o["loss"], rel=1e-5) and personal == pytest.approx(o["personal"], rel=1e-5, abs=1e-5 * float(np.abs(om.P).mean()))
             else:                                         # :189-199
                 feed = {model.user_input: ui[start:end], model.item_input: ii[start:end], model.labels: y[start:end],
                         model.categories: c[start:end], model.user_one_hot_label: ul[start:end],
@@ -372,7 +373,7 @@ def test_session_protocol_runs_the_reference_loop():
                           labels=y[start:end], categories=c[start:end], write_sign=ws[start:end],
                           user_one_hot_label=ul[start:end])
                 o = om.train_step(of); om32.train_step(of)
-                assert loss == pytest.approx(o["loss"], rel=1e-5) and general == pytest.approx(o["general"], rel=1e-5, abs=1e-9)
+                assert loss == pytest.approx(o["loss"], rel=1e-5) and general == pytest.approx(o["general"], rel=1e-5, abs=1e-5 * float(np.abs(om.G).mean()))
                 assert lr == np.float32(0.001)
         sess.run(model.epoch_increment)
         assert sess.run(model.epoch_step) == 1
