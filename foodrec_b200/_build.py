@@ -15,8 +15,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libfoodrec_b200.so")
-SOURCES = ["sort.cu", "train_fwd.cu", "train_seg.cu", "eval.cu", "catalog.cu", "api.cu"]
-HEADERS = ["common.cuh", "internal.h", "train.cuh", "optim.cuh", os.path.join("..", "..", "include", "foodrec_b200.h")]
+SOURCES = ["sort.cu", "train_fwd.cu", "train_seg.cu", "train_shard.cu", "eval.cu", "catalog.cu", "api.cu", "api_shard.cu"]
+HEADERS = ["common.cuh", "internal.h", "train.cuh", "optim.cuh", "ctx.h",
+           os.path.join("..", "..", "include", "foodrec_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 

@@ -49,6 +49,11 @@ class fr_batch(C.Structure):
                 ("labels", C.c_void_p), ("write_sign", C.c_void_p), ("user_labels", C.c_void_p)]
 
 
+class fr_shard(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("cap", C.c_int32),
+                ("items_per_rank", C.c_int32), ("global_batch", C.c_int32)]
+
+
 _PROTOS = {
     "fr_abi_version": (C.c_int, []),
     "fr_create": (C.c_int, [C.POINTER(fr_config), C.POINTER(C.c_void_p)]),
@@ -67,6 +72,13 @@ _PROTOS = {
     "fr_eval_sampled_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fr_shard_packed_len": (C.c_int64, [C.c_void_p]),
+    "fr_shard_plan": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.POINTER(fr_shard), C.c_void_p, C.c_void_p]),
+    "fr_shard_serve": (C.c_int, [C.c_void_p, C.POINTER(fr_shard), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fr_shard_forward": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.POINTER(fr_shard), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fr_shard_update": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.POINTER(fr_shard), C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fr_shard_apply": (C.c_int, [C.c_void_p, C.POINTER(fr_shard), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -1,106 +1,7 @@
 // C ABI of libfoodrec_b200.so (see include/foodrec_b200.h): context, workspace and the
 // orchestration of one training step.  No compute happens on the host; there is no CPU
 // fallback -- every entry point fails with FR_ERR_CUDA if the device is unusable.
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <vector>
-
-#include "common.cuh"
-#include "train.cuh"
-
-using namespace fr;
-
-struct fr_ctx {
-  fr_config cfg{};
-  fr_tables tab{};
-  bool has_tables = false;
-  ModelConsts mc{};
-  int NV = 1, sm_count = 148, device = 0;
-  int64_t step = 0;
-  float b1p = 0.f, b2p = 0.f;
-  char err[512] = {0};
-  std::vector<void*> allocs;
-
-  // workspace (device)
-  uint32_t* ukeys = nullptr; float* ws_row = nullptr; float* g = nullptr; float* scores = nullptr;
-  float4* z = nullptr;
-  SortBufs sortU, sortI, sortL;
-  float *part_loss = nullptr, *part_nrm = nullptr; float4* part_gcat = nullptr; int fwd_grid_cap = 0;
-  float* packed = nullptr;
-  float4 *pieces_u = nullptr, *pieces_i = nullptr, *pieces_g = nullptr, *pieces_personal = nullptr;
-  size_t pieces_personal_chunks = 0;
-  uint32_t *counts = nullptr, *offs = nullptr, *ent_key = nullptr, *ent_row = nullptr, *n_entries = nullptr;
-  float* ent_coef = nullptr;
-  uint32_t* counters = nullptr;
-  float4* cat_pre = nullptr;
-  float* lr_hist = nullptr; int64_t lr_hist_cap = 0;
-  double* cser = nullptr;          // LAZY_SERIES coefficient table [lr_hist_cap * SERIES_TERMS]
-  double* mean_partials = nullptr;
-  float* out_internal = nullptr;
-  uint32_t* scan_tmp = nullptr;
-  // staging for fr_train_step_host
-  void* stage = nullptr; size_t stage_bytes = 0;
-  // per-phase timing (fr_timing_*)
-  bool timing = false;
-  struct TimingSet { cudaEvent_t ev[FR_T_COUNT + 1]; bool used = false; };
-  std::vector<TimingSet> tsets;
-  size_t ts_next = 0;
-  double t_sum[FR_T_COUNT] = {0};
-  int64_t t_steps = 0;
-};
-
-static void timing_collect(fr_ctx* h, fr_ctx::TimingSet& ts) {
-  if (!ts.used) return;
-  cudaEventSynchronize(ts.ev[FR_T_COUNT]);
-  for (int i = 0; i < FR_T_COUNT; ++i) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ts.ev[i], ts.ev[i + 1]) == cudaSuccess) h->t_sum[i] += ms;
-  }
-  h->t_steps += 1;
-  ts.used = false;
-}
-
-static int fail(fr_ctx* h, int code, const char* fmt, ...) {
-  if (h) {
-    va_list ap; va_start(ap, fmt);
-    vsnprintf(h->err, sizeof(h->err), fmt, ap);
-    va_end(ap);
-  }
-  return code;
-}
-#define FR_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
-  return fail(h, FR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
-#define FR_CHECK_LAUNCH(h) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
-  return fail(h, FR_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
-
-template <class T>
-static int dalloc(fr_ctx* h, T** p, size_t count) {
-  void* q = nullptr;
-  if (count == 0) count = 1;
-  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
-  if (e != cudaSuccess) return fail(h, FR_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
-  h->allocs.push_back(q);
-  *p = static_cast<T*>(q);
-  return FR_OK;
-}
-
-static int bits_for(int64_t n) {  // bits needed to represent ids in [0, n)
-  int b = 0;
-  while (b < 32 && ((int64_t)1 << b) < n) ++b;
-  return b < 1 ? 1 : b;
-}
-
-static int alloc_sort(fr_ctx* h, SortBufs& s, size_t cap) {
-  s.cap = (int)cap;
-  for (int i = 0; i < 2; ++i) {
-    int rc = dalloc(h, &s.k[i], cap); if (rc) return rc;
-    rc = dalloc(h, &s.v[i], cap); if (rc) return rc;
-  }
-  const size_t ntiles = (cap + SORT_TILE - 1) / SORT_TILE;
-  int rc = dalloc(h, &s.tile_hist, RADIX_BINS * ntiles + 1); if (rc) return rc;
-  return dalloc(h, &s.scan_tmp, (RADIX_BINS * ntiles) / 4096 + 2);
-}
+#include "ctx.h"
 
 extern "C" int fr_abi_version(void) { return FR_ABI_VERSION; }
 
@@ -140,7 +41,7 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   if ((rc = alloc_sort(h, h->sortL, E))) return rc;
   h->fwd_grid_cap = h->sm_count * 4;
   A(h->part_loss, h->fwd_grid_cap); A(h->part_nrm, h->fwd_grid_cap); A(h->part_gcat, (size_t)h->fwd_grid_cap * 4 * DV);
-  A(h->packed, 4 + 4 * (size_t)D);
+  A(h->packed, 4 + 4 * (size_t)D + 5 * (size_t)cfg->num_labels * D);   // loss, |g|^2, dCat (+ dG when sharded)
   const size_t chS = S / 32 + 2, chE = E / 32 + 2;
   A(h->pieces_u, chS * 2 * 5 * DV); A(h->pieces_i, chS * 2 * DV); A(h->pieces_g, chE * 2 * 5 * DV);
   A(h->counts, S + 1); A(h->offs, S + 1); A(h->ent_key, E); A(h->ent_row, E); A(h->ent_coef, E); A(h->n_entries, 1);
@@ -212,7 +113,7 @@ extern "C" int fr_get_step(fr_handle h, int64_t* step) {
   return FR_OK;
 }
 
-static int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st) {
+int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st) {
   if (need < h->lr_hist_cap) return FR_OK;
   int64_t cap = h->lr_hist_cap;
   while (cap <= need) cap *= 2;
@@ -232,7 +133,7 @@ static int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st) {
   return FR_OK;
 }
 
-static float adam_lr_t(const fr_ctx* h) {   // adam.py: lr * sqrt(1 - beta2_power) / (1 - beta1_power), fp32
+float adam_lr_t(const fr_ctx* h) {   // adam.py: lr * sqrt(1 - beta2_power) / (1 - beta1_power), fp32
   const float num = h->cfg.lr * sqrtf(1.0f - h->b2p);
   return num / (1.0f - h->b1p);
 }
@@ -257,7 +158,7 @@ extern "C" int fr_set_step(fr_handle h, int64_t step) {
   return FR_OK;
 }
 
-static OptConsts make_oc(const fr_ctx* h, int64_t step) {
+OptConsts make_oc(const fr_ctx* h, int64_t step) {
   OptConsts oc{};
   oc.learner = h->cfg.learner; oc.adam_mode = h->cfg.adam_mode;
   oc.lr = h->cfg.lr; oc.lr_t = adam_lr_t(h);
@@ -361,6 +262,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   // 0. pre-step snapshot of Category_Embedding (every read of Cat in this step sees it)
   FR_CUDA(h, cudaMemcpyAsync(h->cat_pre, T.Cat, (size_t)4 * h->mc.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   FR_CUDA(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(uint32_t), st));
+  FR_CUDA(h, cudaMemsetAsync(out + FR_OUT_OVERFLOW, 0, sizeof(float), st));
 
   // 1. row keys, write sign; sort item rows by user and by recipe
   launch_prep_rows(b->mode, B, b->users, b->labels, b->write_sign, h->ukeys, h->ws_row, l);
@@ -377,7 +279,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   FR_MARK(FR_T_FWD);
   // 2. forward, loss, per-slice norms, dCat partials, z stash
   FwdParams fp{};
-  fp.P = (const float4*)T.P; fp.R = (const float4*)T.R; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B;
+  fp.P = (const float4*)T.P; fp.R = (const float4*)T.R; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B; fp.Bnorm = (float)B;
   fp.users = b->users; fp.items = b->items; fp.cats = cats; fp.cats_by_item = cats_by_item;
   fp.labels = b->labels; fp.a = h->mc.a; fp.oma = h->mc.oma;
   fp.g = h->g; fp.z = h->z; fp.scores = out_scores ? out_scores : h->scores;

@@ -1,0 +1,272 @@
+// Row-sharded training step: the five phases declared in include/foodrec_b200.h.  The
+// collectives between them belong to the caller (torch.distributed over NCCL/NVLink, or the
+// in-process emulation the tests use); nothing here talks to another GPU.
+#include "ctx.h"
+
+static int shard_check(fr_ctx* h, const fr_shard* sh) {
+  if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (!sh || sh->world < 1 || sh->world > 8 || sh->rank < 0 || sh->rank >= sh->world || sh->cap < 1 ||
+      sh->items_per_rank < 1 || sh->global_batch < 1)
+    return fail(h, FR_ERR_ARG, "bad fr_shard (1 <= world <= 8, cap >= 1)");
+  if (sh->items_per_rank != h->cfg.num_items)
+    return fail(h, FR_ERR_ARG, "fr_shard.items_per_rank=%d != local Recipe_Embedding rows %d", sh->items_per_rank, h->cfg.num_items);
+  return FR_OK;
+}
+
+template <class T>
+static int ws_alloc(fr_ctx* h, T** p, size_t n) {
+  if (*p) { for (auto& q : h->allocs) if (q == *p) { cudaFree(q); q = nullptr; } *p = nullptr; }
+  return dalloc(h, p, n);
+}
+
+static int shard_ensure(fr_ctx* h, size_t S, size_t n) {
+  auto& w = h->sh;
+  int rc;
+  if (S > w.s_cap) {
+    if ((rc = ws_alloc(h, &w.okeys, S)) || (rc = ws_alloc(h, &w.flags, S)) || (rc = ws_alloc(h, &w.excl, S)) ||
+        (rc = ws_alloc(h, &w.slot_sorted, S)) || (rc = ws_alloc(h, &w.slot_of_row, S)) ||
+        (rc = ws_alloc(h, &w.cats_row, S)))
+      return rc;
+    if (!w.owner_counts && (rc = dalloc(h, &w.owner_counts, 8))) return rc;
+    if (!w.n_valid && (rc = dalloc(h, &w.n_valid, 1))) return rc;
+    w.s_cap = S;
+  }
+  if (n > w.n_cap) {
+    if ((rc = ws_alloc(h, &w.serve_keys, n))) return rc;
+    if ((rc = alloc_sort(h, w.sortS, n))) return rc;       // (old buffers stay in allocs until fr_destroy)
+    if ((rc = ws_alloc(h, &w.pieces_s, (n / 32 + 2) * 2 * (size_t)h->mc.DV))) return rc;
+    w.n_cap = n;
+  }
+  return FR_OK;
+}
+
+extern "C" int64_t fr_shard_packed_len(fr_handle h) {
+  return h ? 4 + 4 * (int64_t)h->mc.D + 5 * (int64_t)h->mc.L * h->mc.D : 0;
+}
+
+// ---------------------------------------------------------------- 1. plan
+extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh, int32_t* req, fr_stream s) {
+  int rc = shard_check(h, sh); if (rc) return rc;
+  if (!b || !req) return fail(h, FR_ERR_ARG, "null batch/req");
+  if (b->mode != FR_POINTWISE && b->mode != FR_BPR) return fail(h, FR_ERR_ARG, "bad mode %d", b->mode);
+  const int group = b->mode == FR_BPR ? 2 : 1, B = b->n_groups;
+  if (B <= 0) return fail(h, FR_ERR_ARG, "empty batch");
+  if ((int64_t)B * group > h->cfg.max_rows) return fail(h, FR_ERR_ARG, "batch exceeds max_rows=%d", h->cfg.max_rows);
+  if (!b->users || !b->items) return fail(h, FR_ERR_ARG, "users/items are required");
+  if (b->mode == FR_POINTWISE && !b->labels) return fail(h, FR_ERR_ARG, "labels are required in pointwise mode");
+  if (!b->cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cats is NULL and no (global) item_cats table");
+  if (!b->user_labels && !(h->tab.user_label_off && h->tab.user_label_idx))
+    return fail(h, FR_ERR_ARG, "user_labels is NULL and no user-label CSR table");
+  const int S = B * group, W = sh->world;
+  const size_t n = (size_t)W * sh->cap;
+  if ((rc = shard_ensure(h, (size_t)S, n))) return rc;
+  cudaStream_t st = (cudaStream_t)s;
+  Launch l{h->sm_count, st, nullptr};
+  auto& w = h->sh;
+  w.mode = b->mode; w.B = B; w.S = S; w.group = group;
+  const fr_tables& T = h->tab;
+
+  FR_CUDA(h, cudaMemcpyAsync(h->cat_pre, T.Cat, (size_t)4 * h->mc.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  FR_CUDA(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(uint32_t), st));
+  FR_CUDA(h, cudaMemsetAsync(w.owner_counts, 0, 8 * sizeof(uint32_t), st));
+  FR_CUDA(h, cudaMemsetAsync(req, 0xff, n * sizeof(int32_t), st));
+  FR_CUDA(h, cudaMemsetAsync(h->out_internal, 0, FR_OUT_COUNT * sizeof(float), st));
+  launch_prep_rows(b->mode, B, b->users, b->labels, b->write_sign, h->ukeys, h->ws_row, l);
+
+  ShardPlanParams p{};
+  p.S = S; p.W = W; p.cap = sh->cap; p.items_per_rank = (uint32_t)sh->items_per_rank;
+  p.items = b->items; p.item_cats = (const float4*)T.item_cats; p.cats_in = (const float4*)b->cats;
+  p.okeys = w.okeys; p.cats_row = w.cats_row;
+  p.flags = w.flags; p.excl = w.excl; p.owner_counts = w.owner_counts;
+  p.req = req; p.slot_of_row = w.slot_of_row; p.slot_sorted = w.slot_sorted; p.out = h->out_internal;
+  launch_shard_prep(p, l);
+  w.ru = radix_sort_pairs(h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), st, h->sm_count);
+  w.ri = radix_sort_pairs(h->sortI, w.okeys, (uint32_t)S, nullptr, bits_for((int64_t)W * sh->items_per_rank), st, h->sm_count);
+  p.okeys_sorted = h->sortI.k[w.ri]; p.perm = h->sortI.v[w.ri];
+  launch_shard_heads(p, l);
+  exclusive_scan_u32(w.flags, w.excl, (uint32_t)S, h->scan_tmp, nullptr, st);
+  launch_shard_fill(p, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+// ---------------------------------------------------------------- 2. serve
+extern "C" int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rreq, float* rows, fr_stream s) {
+  int rc = shard_check(h, sh); if (rc) return rc;
+  if (!rreq || !rows) return fail(h, FR_ERR_ARG, "null rreq/rows");
+  const size_t n = (size_t)sh->world * sh->cap;
+  if ((rc = shard_ensure(h, 0, n))) return rc;
+  cudaStream_t st = (cudaStream_t)s;
+  Launch l{h->sm_count, st, nullptr};
+  auto& w = h->sh;
+  const fr_tables& T = h->tab;
+  const int64_t step = h->step + 1;
+  if ((rc = ensure_lr_hist(h, step + 1, st))) return rc;
+  const OptConsts oc = make_oc(h, step);
+  launch_serve_keys(rreq, (uint32_t)n, (uint32_t)sh->items_per_rank, w.serve_keys, w.n_valid, l);
+  w.rs = radix_sort_pairs(w.sortS, w.serve_keys, (uint32_t)n, nullptr, bits_for((int64_t)sh->items_per_rank + 1), st, h->sm_count);
+  if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE)    // requested rows must be current
+    launch_item_catchup(h->NV, w.sortS.k[w.rs], (uint32_t)n, (float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R, T.last_R,
+                        h->mc.DV, oc, l, w.n_valid);
+  launch_gather_rows((const float4*)T.R, rreq, (uint32_t)n, h->mc.DV, (float4*)rows, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+// ---------------------------------------------------------------- 3. forward
+extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* sh, const float* rbuf, float* packed,
+                                fr_stream s) {
+  int rc = shard_check(h, sh); if (rc) return rc;
+  if (!b || !rbuf || !packed) return fail(h, FR_ERR_ARG, "null argument");
+  auto& w = h->sh;
+  if (w.S <= 0 || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_forward");
+  cudaStream_t st = (cudaStream_t)s;
+  Launch l{h->sm_count, st, nullptr};
+  const fr_tables& T = h->tab;
+  const int DV = h->mc.DV, NV = h->NV, S = w.S, B = w.B;
+  const OptConsts oc = make_oc(h, h->step + 1);
+  const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
+
+  FwdParams fp{};
+  fp.P = (const float4*)T.P; fp.R = (const float4*)rbuf; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B;
+  fp.Bnorm = (float)sh->global_batch;
+  fp.users = b->users; fp.items = w.slot_of_row; fp.cats = w.cats_row; fp.cats_by_item = 0;
+  fp.labels = b->labels; fp.a = h->mc.a; fp.oma = h->mc.oma;
+  fp.g = h->g; fp.z = h->z; fp.scores = h->scores;
+  fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
+  fp.lazy = lazy ? 1 : 0; fp.mP = (const float4*)T.s1_P; fp.vP = (const float4*)T.s2_P; fp.lastP = T.last_P; fp.oc = oc;
+  const int fgrid = fwd_train_grid(B, h->sm_count);
+  launch_fwd_train(NV, w.group, fp, fgrid, l);
+
+  FinalizeParams fin{};
+  fin.part_loss = h->part_loss; fin.part_nrm = h->part_nrm; fin.part_gcat = h->part_gcat; fin.nblk = fgrid;
+  fin.DV = DV; fin.B = (float)sh->global_batch; fin.packed = packed; fin.do_reduce = 1; fin.do_apply = 0;
+  fin.oc = oc; fin.clip = h->cfg.clip_norm; fin.out = h->out_internal; fin.lr_hist = nullptr;
+  launch_finalize(fin, l);
+
+  // General_Memory delta of this rank's rows -> packed (G itself is updated after the all-reduce)
+  float* dG = packed + 4 + 4 * (size_t)h->mc.D;
+  FR_CUDA(h, cudaMemsetAsync(dG, 0, 5 * (size_t)h->mc.L * h->mc.D * sizeof(float), st));
+  LabelEmitParams ep{};
+  ep.S = S; ep.group = w.group; ep.L = h->mc.L; ep.users = b->users;
+  ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
+  ep.ws_row = h->ws_row; ep.counts = h->counts; ep.offs = h->offs;
+  ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
+  ep.cap = (uint32_t)h->sortL.cap; ep.n_entries = h->n_entries; ep.out = h->out_internal;
+  launch_label_count(ep, l);
+  exclusive_scan_u32(h->counts, h->offs, (uint32_t)S, h->scan_tmp, h->n_entries, st);
+  launch_label_emit(ep, l);
+  const uint32_t ecap = (uint32_t)h->sortL.cap;
+  const int rl = radix_sort_pairs(h->sortL, h->ent_key, ecap, h->n_entries, bits_for(h->mc.L), st, h->sm_count);
+  SegCommon c{};
+  c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
+  c.pieces = h->pieces_g; c.uniq_counter = nullptr;
+  LabelPolParams lp{};
+  lp.G = (float4*)dG; lp.R = (const float4*)rbuf; lp.cat = h->cat_pre;
+  lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = w.slot_of_row; lp.cats = w.cats_row;
+  lp.cats_by_item = 0; lp.mc = h->mc;
+  launch_label_pass(NV, c, lp, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+// ---------------------------------------------------------------- 4. update
+extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* sh, int32_t write_personal,
+                               const float* rbuf, const float* packed_reduced, float* grows, float* out_scalars,
+                               fr_stream s) {
+  int rc = shard_check(h, sh); if (rc) return rc;
+  if (!b || !rbuf || !packed_reduced || !grows) return fail(h, FR_ERR_ARG, "null argument");
+  auto& w = h->sh;
+  if (w.S <= 0 || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_update");
+  cudaStream_t st = (cudaStream_t)s;
+  Launch l{h->sm_count, st, nullptr};
+  const fr_tables& T = h->tab;
+  const int DV = h->mc.DV, NV = h->NV, S = w.S;
+  const int64_t step = h->step + 1;
+  const OptConsts oc = make_oc(h, step);
+  float* out = out_scalars ? out_scalars : h->out_internal;
+  if (out != h->out_internal)   // flags raised by plan/forward (capacity / label overflow)
+    FR_CUDA(h, cudaMemcpyAsync(out, h->out_internal, FR_OUT_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  FinalizeParams fin{};
+  fin.DV = DV; fin.B = (float)sh->global_batch; fin.packed = const_cast<float*>(packed_reduced);
+  fin.do_reduce = 0; fin.do_apply = 1;
+  fin.Cat = (float4*)T.Cat; fin.s1Cat = (float4*)T.s1_Cat; fin.s2Cat = (float4*)T.s2_Cat;
+  fin.oc = oc; fin.clip = h->cfg.clip_norm; fin.out = out; fin.lr_hist = h->lr_hist;
+  launch_finalize(fin, l);
+
+  SegCommon c{};
+  c.keys = h->sortU.k[w.ru]; c.perm = h->sortU.v[w.ru]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
+  c.uniq_counter = h->counters + 0; c.pieces = h->pieces_u;
+  UserPolParams up{};
+  up.P = (float4*)T.P; up.s1 = (float4*)T.s1_P; up.s2 = (float4*)T.s2_P; up.last = T.last_P;
+  up.R = (const float4*)rbuf; up.G = (const float4*)T.G; up.cat = h->cat_pre;
+  up.items = w.slot_of_row; up.g = h->g; up.cats = w.cats_row; up.cats_by_item = 0;
+  up.ws_row = h->ws_row; up.out = out; up.group = w.group; up.mc = h->mc; up.oc = oc;
+  up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = b->users;
+  launch_user_pass(NV, c, up, l);
+  if (write_personal) {
+    const size_t need = (size_t)S / 32 + 2;
+    if (need > h->pieces_personal_chunks) {
+      if (h->pieces_personal) { FR_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->pieces_personal); h->pieces_personal = nullptr; }
+      FR_CUDA(h, cudaMalloc(&h->pieces_personal, need * 2 * 10 * DV * sizeof(float4)));
+      h->pieces_personal_chunks = need;
+    }
+    c.pieces = h->pieces_personal; c.uniq_counter = nullptr;
+    launch_personal_pass(NV, c, up, l);
+  }
+  // G += all-reduced delta (after the personal pass, which reads G_old)
+  launch_add_inplace((float4*)T.G, (const float4*)(packed_reduced + 4 + 4 * (size_t)h->mc.D), (int64_t)h->mc.L * 5 * DV, l);
+
+  // finished gradient rows of the recipes this rank touched, in the owners' slot order
+  SegCommon ci{};
+  ci.keys = w.slot_sorted; ci.perm = h->sortI.v[w.ri]; ci.n_dev = nullptr; ci.n_host = (uint32_t)S;
+  ci.pieces = h->pieces_i; ci.uniq_counter = h->counters + 1;
+  ItemPolParams ip{};
+  ip.z = h->z; ip.g = h->g; ip.out = out; ip.mc = h->mc; ip.oc = oc;
+  launch_item_grad_pass(NV, ci, ip, (float4*)grows, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+// ---------------------------------------------------------------- 5. apply
+extern "C" int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rreq, const float* rgrows,
+                              float* out_scalars, fr_stream s) {
+  int rc = shard_check(h, sh); if (rc) return rc;
+  if (!rreq || !rgrows) return fail(h, FR_ERR_ARG, "null argument");
+  auto& w = h->sh;
+  if (w.S <= 0) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_apply");
+  cudaStream_t st = (cudaStream_t)s;
+  Launch l{h->sm_count, st, nullptr};
+  const fr_tables& T = h->tab;
+  const int DV = h->mc.DV, NV = h->NV;
+  const int64_t step = h->step + 1;
+  const OptConsts oc = make_oc(h, step);
+  float* out = out_scalars ? out_scalars : h->out_internal;
+  const uint32_t n = (uint32_t)((size_t)sh->world * sh->cap);
+
+  // received (recipe, gradient row) pairs, sorted by recipe at serve time (stable: rank order)
+  SegCommon c{};
+  c.keys = w.sortS.k[w.rs]; c.perm = w.sortS.v[w.rs]; c.n_dev = w.n_valid; c.n_host = n;
+  c.pieces = w.pieces_s; c.uniq_counter = nullptr;
+  ItemPolParams ip{};
+  ip.R = (float4*)T.R; ip.s1 = (float4*)T.s1_R; ip.s2 = (float4*)T.s2_R; ip.last = T.last_R;
+  ip.z = (const float4*)rgrows; ip.g = nullptr; ip.out = out; ip.mc = h->mc; ip.oc = oc;
+  launch_item_pass(NV, c, ip, l);
+
+  if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_SERIES)
+    launch_series_update(h->cser, h->lr_hist, (int)step, h->cfg.adam_beta1, h->cfg.adam_beta2, l);
+  if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_DENSE) {
+    launch_adam_sweep((float4*)T.P, (float4*)T.s1_P, (float4*)T.s2_P, T.last_P, h->cfg.num_users, 5 * DV, oc, (int)step, l);
+    launch_adam_sweep((float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R, T.last_R, h->cfg.num_items, DV, oc, (int)step, l);
+  }
+  launch_mean((const float4*)T.G, (int64_t)h->mc.L * 5 * DV, h->mean_partials, out + FR_OUT_GENERAL,
+              (double)h->mc.L * 5.0 * h->mc.D, l);
+  launch_write_counters(h->counters, out, l);
+  FR_CHECK_LAUNCH(h);
+  w.S = 0;
+  h->step = step;
+  h->b1p *= h->cfg.adam_beta1;
+  h->b2p *= h->cfg.adam_beta2;
+  return FR_OK;
+}

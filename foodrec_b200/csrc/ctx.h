@@ -1,0 +1,119 @@
+// Context of one fr_handle + small host helpers shared by api.cu and api_shard.cu.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "train.cuh"
+
+using namespace fr;
+
+struct fr_ctx {
+  fr_config cfg{};
+  fr_tables tab{};
+  bool has_tables = false;
+  ModelConsts mc{};
+  int NV = 1, sm_count = 148, device = 0;
+  int64_t step = 0;
+  float b1p = 0.f, b2p = 0.f;
+  char err[512] = {0};
+  std::vector<void*> allocs;
+
+  // workspace (device)
+  uint32_t* ukeys = nullptr; float* ws_row = nullptr; float* g = nullptr; float* scores = nullptr;
+  float4* z = nullptr;
+  SortBufs sortU, sortI, sortL;
+  float *part_loss = nullptr, *part_nrm = nullptr; float4* part_gcat = nullptr; int fwd_grid_cap = 0;
+  float* packed = nullptr;
+  float4 *pieces_u = nullptr, *pieces_i = nullptr, *pieces_g = nullptr, *pieces_personal = nullptr;
+  size_t pieces_personal_chunks = 0;
+  uint32_t *counts = nullptr, *offs = nullptr, *ent_key = nullptr, *ent_row = nullptr, *n_entries = nullptr;
+  float* ent_coef = nullptr;
+  uint32_t* counters = nullptr;
+  float4* cat_pre = nullptr;
+  float* lr_hist = nullptr; int64_t lr_hist_cap = 0;
+  double* cser = nullptr;          // LAZY_SERIES coefficient table [lr_hist_cap * SERIES_TERMS]
+  double* mean_partials = nullptr;
+  float* out_internal = nullptr;
+  uint32_t* scan_tmp = nullptr;
+  // row-sharded training (api_shard.cu): allocated on first use
+  struct ShardWs {
+    size_t s_cap = 0, n_cap = 0;          // item rows / W*cap the buffers are sized for
+    uint32_t *okeys = nullptr, *flags = nullptr, *excl = nullptr, *owner_counts = nullptr, *slot_sorted = nullptr;
+    int32_t* slot_of_row = nullptr;
+    float4* cats_row = nullptr;
+    uint32_t *serve_keys = nullptr, *n_valid = nullptr;
+    SortBufs sortS;                        // owner side: received requests
+    float4* pieces_s = nullptr;
+    int ru = 0, ri = 0, rs = 0;            // which sort buffer holds each result
+    int mode = 0, B = 0, S = 0, group = 1;
+  } sh;
+  // staging for fr_train_step_host
+  void* stage = nullptr; size_t stage_bytes = 0;
+  // per-phase timing (fr_timing_*)
+  bool timing = false;
+  struct TimingSet { cudaEvent_t ev[FR_T_COUNT + 1]; bool used = false; };
+  std::vector<TimingSet> tsets;
+  size_t ts_next = 0;
+  double t_sum[FR_T_COUNT] = {0};
+  int64_t t_steps = 0;
+};
+
+static inline void timing_collect(fr_ctx* h, fr_ctx::TimingSet& ts) {
+  if (!ts.used) return;
+  cudaEventSynchronize(ts.ev[FR_T_COUNT]);
+  for (int i = 0; i < FR_T_COUNT; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ts.ev[i], ts.ev[i + 1]) == cudaSuccess) h->t_sum[i] += ms;
+  }
+  h->t_steps += 1;
+  ts.used = false;
+}
+
+static inline int fail(fr_ctx* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+#define FR_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail(h, FR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define FR_CHECK_LAUNCH(h) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+  return fail(h, FR_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+template <class T>
+static inline int dalloc(fr_ctx* h, T** p, size_t count) {
+  void* q = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) return fail(h, FR_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return FR_OK;
+}
+
+static inline int bits_for(int64_t n) {  // bits needed to represent ids in [0, n)
+  int b = 0;
+  while (b < 32 && ((int64_t)1 << b) < n) ++b;
+  return b < 1 ? 1 : b;
+}
+
+static inline int alloc_sort(fr_ctx* h, SortBufs& s, size_t cap) {
+  s.cap = (int)cap;
+  for (int i = 0; i < 2; ++i) {
+    int rc = dalloc(h, &s.k[i], cap); if (rc) return rc;
+    rc = dalloc(h, &s.v[i], cap); if (rc) return rc;
+  }
+  const size_t ntiles = (cap + SORT_TILE - 1) / SORT_TILE;
+  int rc = dalloc(h, &s.tile_hist, RADIX_BINS * ntiles + 1); if (rc) return rc;
+  return dalloc(h, &s.scan_tmp, (RADIX_BINS * ntiles) / 4096 + 2);
+}
+
+
+int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st);
+float adam_lr_t(const fr_ctx* h);
+fr::OptConsts make_oc(const fr_ctx* h, int64_t step);

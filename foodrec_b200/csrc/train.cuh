@@ -7,6 +7,7 @@ namespace fr {
 struct FwdParams {
   const float4 *P, *R, *cat;        // cat = step-start snapshot of Category_Embedding
   int DV, B;
+  float Bnorm;                      // batch size the loss mean divides by (GLOBAL batch when sharded)
   const int32_t *users, *items;
   const float4* cats; int cats_by_item;
   const float* labels;
@@ -84,7 +85,33 @@ void launch_fill_i32(int32_t* p, int64_t n, int32_t v, const Launch& l);
 void launch_series_update(double* cser, const float* lr_hist, int t, float b1, float b2, const Launch& l);
 void launch_series_rebuild(double* cser, const float* lr_hist, int step, float b1, float b2, const Launch& l);
 void launch_item_catchup(int NV, const uint32_t* keys, uint32_t n, float4* R, float4* m, float4* v,
-                         int32_t* last, int DV, const OptConsts& oc, const Launch& l);
+                         int32_t* last, int DV, const OptConsts& oc, const Launch& l,
+                         const uint32_t* n_dev = nullptr);
+void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, float4* gbuf, const Launch& l);
+
+// ---- row-sharded training helpers (train_shard.cu)
+struct ShardPlanParams {
+  int S, W, cap; uint32_t items_per_rank;
+  const int32_t* items;          // [S] GLOBAL recipe ids
+  const float4* item_cats;       // [I] replicated, or null when per-row cats are fed
+  const float4* cats_in;         // [S] per-row cats (or null)
+  uint32_t* okeys;               // [S] owner-major key  (id % W) * items_per_rank + id / W
+  float4* cats_row;              // [S] gathered per-row categories
+  // after the sort by okey:
+  const uint32_t* okeys_sorted; const uint32_t* perm;
+  uint32_t* flags; uint32_t* excl; uint32_t* owner_counts;   // [S], [S], [W]
+  int32_t* req;                  // [W*cap] local row at the owner, -1 = empty
+  int32_t* slot_of_row;          // [S]
+  uint32_t* slot_sorted;         // [S] slot of sorted position (monotone: doubles as sort key)
+  float* out;                    // FR_OUT_OVERFLOW on capacity overflow
+};
+void launch_shard_prep(const ShardPlanParams& p, const Launch& l);
+void launch_shard_heads(const ShardPlanParams& p, const Launch& l);
+void launch_shard_fill(const ShardPlanParams& p, const Launch& l);
+void launch_serve_keys(const int32_t* rreq, uint32_t n, uint32_t items_per_rank, uint32_t* keys, uint32_t* n_valid,
+                       const Launch& l);
+void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const Launch& l);
+void launch_add_inplace(float4* dst, const float4* src, int64_t n4, const Launch& l);
 void launch_mean(const float4* x, int64_t n4, double* partials, float* out_slot, double count, const Launch& l);
 void launch_write_counters(const uint32_t* counters, float* out, const Launch& l);
 

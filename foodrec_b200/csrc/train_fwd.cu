@@ -55,7 +55,7 @@ fwd_train_kernel(const FwdParams p) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * FR_WARPS_PER_BLOCK + warp, nw = gridDim.x * FR_WARPS_PER_BLOCK;
-  const float a = p.a, oma = p.oma, Bf = (float)p.B;
+  const float a = p.a, oma = p.oma, Bf = p.Bnorm;
   float4 gc[4][NV];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -355,7 +355,7 @@ label_emit_kernel(const LabelEmitParams p) {
   if (gw == 0 && lane == 0) {
     const uint32_t tot = *p.n_entries;
     p.out[FR_OUT_LABEL_ENTRIES] = (float)tot;
-    p.out[FR_OUT_OVERFLOW] = tot > p.cap ? 1.f : 0.f;
+    if (tot > p.cap) p.out[FR_OUT_OVERFLOW] = 1.f;      // (slot is zeroed at step start)
   }
   for (int r = gw; r < p.S; r += nw) {
     const int grp = r / p.group;

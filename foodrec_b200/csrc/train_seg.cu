@@ -343,7 +343,8 @@ struct ItemPol {
   __device__ __forceinline__ const float4* cat_src() const { return nullptr; }
   __device__ __forceinline__ Entry load_entry(uint32_t row, bool valid) const {
     Entry e; e.g = 0.f; e.row = row;
-    if (valid) e.g = p.g[row] * p.out[FR_OUT_SCALE];
+    // g == nullptr: the rows are finished gradient rows received from other ranks (coef 1)
+    if (valid) e.g = p.g ? p.g[row] * p.out[FR_OUT_SCALE] : 1.f;
     return e;
   }
   __device__ __forceinline__ void accumulate(float4 (&acc)[1][NV], const Entry& e, int e0, int e1, int lane,
@@ -375,6 +376,24 @@ struct ItemPol {
   }
   __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[1][NV], int lane) const {
     apply_and_store<OPT, 1, NV>(st, p.R, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
+  }
+};
+
+// ---- policy (row-sharded training): the same reduction dR[slot] = sum g*z, but the result
+// is a finished gradient row written to the send buffer of the recipe's owner instead of
+// being applied (the owner applies it after the all-to-all: ItemPol with g == nullptr).
+template <int NVV>
+struct ItemGradPol : ItemPol<NVV, OPT_GENERIC> {
+  float4* gbuf;                       // [W*cap, DV], key = slot
+  struct State {};
+  __device__ __forceinline__ void load_state(State&, uint32_t, int) const {}
+  __device__ __forceinline__ void apply(State&, uint32_t key, float4 (&acc)[1][NVV], int lane) const {
+    const int DVv = this->p.mc.DV;
+#pragma unroll
+    for (int k = 0; k < NVV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < DVv) gbuf[(size_t)key * DVv + i] = acc[0][k];
+    }
   }
 };
 
@@ -494,6 +513,10 @@ void launch_item_pass(int NV, const SegCommon& c, const ItemPolParams& p, const 
   const int opt = opt_of(p.oc.learner, p.oc.adam_mode);
   FR_DISPATCH_NV_OPT(NV, opt, { ItemPol<NV_, OPT_> pol{p}; launch_seg(c, pol, p.mc.DV, false, l); });
 }
+void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, float4* gbuf, const Launch& l) {
+  if (NV == 1) { ItemGradPol<1> pol{{p}, gbuf}; launch_seg(c, pol, p.mc.DV, false, l); }
+  else { ItemGradPol<2> pol{{p}, gbuf}; launch_seg(c, pol, p.mc.DV, false, l); }
+}
 void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, const Launch& l) {
   if (NV == 1) { LabelPol<1> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
   else { LabelPol<2> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
@@ -504,9 +527,10 @@ void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, cons
 // item rows, sorted; the warp that sees a run's head owns that row.
 template <int NV, int OPT>
 __global__ void __launch_bounds__(FR_THREADS)
-item_catchup_kernel(const uint32_t* __restrict__ keys, uint32_t n, float4* __restrict__ R,
-                    float4* __restrict__ m, float4* __restrict__ v, int32_t* __restrict__ last,
-                    int DV, const OptConsts oc) {
+item_catchup_kernel(const uint32_t* __restrict__ keys, uint32_t n_host, const uint32_t* n_dev,
+                    float4* __restrict__ R, float4* __restrict__ m, float4* __restrict__ v,
+                    int32_t* __restrict__ last, int DV, const OptConsts oc) {
+  const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
   const int lane = threadIdx.x & 31;
   const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const uint32_t nw = gridDim.x * FR_WARPS_PER_BLOCK;
@@ -540,13 +564,13 @@ item_catchup_kernel(const uint32_t* __restrict__ keys, uint32_t n, float4* __res
   }
 }
 void launch_item_catchup(int NV, const uint32_t* keys, uint32_t n, float4* R, float4* m, float4* v,
-                         int32_t* last, int DV, const OptConsts& oc, const Launch& l) {
+                         int32_t* last, int DV, const OptConsts& oc, const Launch& l, const uint32_t* n_dev) {
   const uint32_t nchunks = (n + 31) / 32;
   if (nchunks == 0) return;
   int grid = (int)((nchunks + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
   if (grid > l.sm_count * 16) grid = l.sm_count * 16;
   const bool series = oc.adam_mode == FR_ADAM_LAZY_SERIES;
-#define FR_ICU(NVV, OO) item_catchup_kernel<NVV, OO><<<grid, FR_THREADS, 0, l.st>>>(keys, n, R, m, v, last, DV, oc)
+#define FR_ICU(NVV, OO) item_catchup_kernel<NVV, OO><<<grid, FR_THREADS, 0, l.st>>>(keys, n, n_dev, R, m, v, last, DV, oc)
   if (NV == 1) { if (series) FR_ICU(1, OPT_ADAM_SERIES); else FR_ICU(1, OPT_ADAM_EXACT); }
   else         { if (series) FR_ICU(2, OPT_ADAM_SERIES); else FR_ICU(2, OPT_ADAM_EXACT); }
 #undef FR_ICU

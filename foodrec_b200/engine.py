@@ -79,7 +79,8 @@ class Engine:
         self.lab_off = self.lab_idx = None
         self.max_labels_per_user = self.Lb
         if item_cats is not None:
-            self.item_cats = torch.as_tensor(np.asarray(item_cats, np.float32).reshape(self.I, 4)).to(self.device).contiguous()
+            # [I,4] for this table's recipes -- or, for a row-sharded engine, the GLOBAL map
+            self.item_cats = torch.as_tensor(np.asarray(item_cats, np.float32).reshape(-1, 4)).to(self.device).contiguous()
         if user_labels is not None:     # dense [U, L] multi-hot -> CSR (weights must be 0/1)
             ul = np.asarray(user_labels)
             assert ul.shape == (self.U, self.Lb)

@@ -1,0 +1,197 @@
+"""Row-sharded training over W GPUs (one process per GPU, torch.distributed/NCCL for the
+plumbing).  SURVEY 8(e): Personal_Memory (+ optimizer slots) is sharded by ``user % W`` and
+every sample is routed to the GPU that owns its user when it is loaded, so the 5*D-float
+user rows and their updates never move; Recipe_Embedding is sharded by ``recipe % W`` and
+the looked-up rows / their gradient rows travel in fixed-capacity all-to-alls; loss,
+sum|g|^2, dCat and dG travel in ONE packed all-reduce.  The reference has none of this
+(single ``tf.Session``).
+
+Two runners drive the five C-ABI phases (``fr_shard_*``):
+  * :class:`DistRunner`   -- this process is one rank; collectives via torch.distributed.
+  * :class:`LocalRunner`  -- all W ranks live in THIS process on one GPU and the collectives
+    are tensor shuffles: the same kernels and protocol, used by the parity tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import Engine, Hyper, _ptr
+
+
+# ---------------------------------------------------------------------------- host-side layout
+def local_rows(n: int, world: int) -> int:
+    return (n + world - 1) // world
+
+
+def shard_rows(x: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """rows r, r+W, r+2W, ... (local row k <-> global row r + k*W), zero-padded to ceil(n/W)."""
+    part = np.ascontiguousarray(x[rank::world])
+    need = local_rows(x.shape[0], world)
+    if part.shape[0] < need:
+        part = np.concatenate([part, np.zeros((need - part.shape[0],) + x.shape[1:], x.dtype)])
+    return part
+
+
+def unshard_rows(parts, n: int) -> np.ndarray:
+    world = len(parts)
+    out = np.zeros((n,) + parts[0].shape[1:], parts[0].dtype)
+    for r, p in enumerate(parts):
+        cnt = len(range(r, n, world))
+        out[r::world] = p[:cnt]
+    return out
+
+
+def route_batch(users: np.ndarray, world: int):
+    """Index lists (stable, i.e. batch order) of the groups each rank owns: user % W."""
+    users = np.asarray(users)
+    return [np.nonzero(users % world == r)[0] for r in range(world)]
+
+
+def shard_label_csr(off: np.ndarray, idx: np.ndarray, rank: int, world: int, n_users: int):
+    """CSR over the rank's local user rows."""
+    us = np.arange(rank, n_users, world)
+    cnt = off[us + 1] - off[us]
+    need = local_rows(n_users, world)
+    loff = np.zeros(need + 1, np.int32)
+    loff[1:len(us) + 1] = np.cumsum(cnt)
+    loff[len(us) + 1:] = loff[len(us)]
+    src = np.concatenate([np.arange(off[u], off[u + 1]) for u in us]) if len(us) < 20000 else \
+        (np.repeat(off[us], cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)))
+    return loff, idx[src].astype(np.int32)
+
+
+# ---------------------------------------------------------------------------- one rank
+class ShardedEngine:
+    """The tables of one rank + the five phases of a sharded step."""
+
+    def __init__(self, hyper: Hyper, P_loc, R_loc, Cat, G, rank, world, device="cuda:0", max_rows=1 << 16,
+                 cap=None, adam_mode="lazy", item_cats_global=None, user_label_csr_local=None,
+                 max_label_entries=None):
+        if not (1 <= world <= 8):
+            raise ValueError("1 <= world <= 8")
+        self.rank, self.world = rank, world
+        self.e = Engine(hyper, P_loc, R_loc, Cat, G, device=device, max_rows=max_rows, adam_mode=adam_mode,
+                        item_cats=item_cats_global, user_label_csr=user_label_csr_local,
+                        max_label_entries=max_label_entries)
+        e = self.e
+        self.device = e.device
+        if cap is None:      # unique recipes per (source, owner): generous, checked on device
+            cap = min(max_rows, e.I) if world == 1 else min(max_rows, e.I, int(1.5 * max_rows / world) + 1024)
+        self.cap = int(cap)
+        n = world * self.cap
+        dev = self.device
+        self.req = torch.empty(n, dtype=torch.int32, device=dev)
+        self.rreq = torch.empty(n, dtype=torch.int32, device=dev)
+        self.rows = torch.empty((n, e.D), dtype=torch.float32, device=dev)
+        self.rbuf = torch.empty((n, e.D), dtype=torch.float32, device=dev)
+        self.grows = torch.empty((n, e.D), dtype=torch.float32, device=dev)
+        self.rgrows = torch.empty((n, e.D), dtype=torch.float32, device=dev)
+        self.packed = torch.zeros(int(e.lib.fr_shard_packed_len(e.handle)), dtype=torch.float32, device=dev)
+        self._sh = None
+        self._b = None
+
+    def _shard(self, global_batch):
+        return L.fr_shard(self.world, self.rank, self.cap, self.e.I, int(global_batch))
+
+    def set_batch(self, users_local, items_global, labels=None, neg_items=None, categories=None, neg_categories=None,
+                  write_sign=None, user_one_hot_label=None, global_batch=None):
+        e = self.e
+        u = e._i32(users_local)
+        B = u.numel()
+        bpr = neg_items is not None
+        if bpr:
+            it = torch.stack([e._i32(items_global), e._i32(neg_items)], 1).reshape(-1).contiguous()
+            cats = None if categories is None else torch.stack(
+                [e._f32(categories, (B, 4)), e._f32(neg_categories, (B, 4))], 1).reshape(-1, 4).contiguous()
+        else:
+            it = e._i32(items_global)
+            cats = e._f32(categories, (B, 4))
+        lab, ws = e._f32(labels, (-1,)), e._f32(write_sign, (-1,))
+        ul = e._f32(user_one_hot_label, (B, e.Lb))
+        self._keep = [u, it, cats, lab, ws, ul]
+        self._b = L.fr_batch(L.FR_BPR if bpr else L.FR_POINTWISE, B, _ptr(u), _ptr(it), _ptr(cats), _ptr(lab), _ptr(ws), _ptr(ul))
+        self._sh = self._shard(global_batch if global_batch is not None else B)
+
+    # the five phases ------------------------------------------------------------------
+    def plan(self):
+        e = self.e
+        L.check(e.handle, e.lib.fr_shard_plan(e.handle, C.byref(self._b), C.byref(self._sh), _ptr(self.req), e._stream()))
+        return self.req
+
+    def serve(self):
+        e = self.e
+        L.check(e.handle, e.lib.fr_shard_serve(e.handle, C.byref(self._sh), _ptr(self.rreq), _ptr(self.rows), e._stream()))
+        return self.rows
+
+    def forward(self):
+        e = self.e
+        L.check(e.handle, e.lib.fr_shard_forward(e.handle, C.byref(self._b), C.byref(self._sh), _ptr(self.rbuf),
+                                                 _ptr(self.packed), e._stream()))
+        return self.packed
+
+    def update(self, write_personal=False):
+        e = self.e
+        L.check(e.handle, e.lib.fr_shard_update(e.handle, C.byref(self._b), C.byref(self._sh), int(bool(write_personal)),
+                                                _ptr(self.rbuf), _ptr(self.packed), _ptr(self.grows), _ptr(e.out), e._stream()))
+        return self.grows
+
+    def apply(self):
+        e = self.e
+        L.check(e.handle, e.lib.fr_shard_apply(e.handle, C.byref(self._sh), _ptr(self.rreq), _ptr(self.rgrows), _ptr(e.out),
+                                               e._stream()))
+        e._dirty = True
+        return e.out
+
+
+# ---------------------------------------------------------------------------- runners
+class DistRunner:
+    """This process is rank `dist.get_rank()`; NCCL (or gloo on CPU tensors in tests)."""
+
+    def __init__(self, engine: ShardedEngine):
+        import torch.distributed as dist
+        self.dist, self.eng = dist, engine
+        assert dist.get_world_size() == engine.world and dist.get_rank() == engine.rank
+
+    def step(self, write_personal=False):
+        d, g = self.dist, self.eng
+        g.plan()
+        d.all_to_all_single(g.rreq, g.req)               # requests -> owners
+        g.serve()
+        d.all_to_all_single(g.rbuf, g.rows)              # recipe rows -> requesters (NVLink)
+        g.forward()
+        d.all_reduce(g.packed)                           # loss, sum|g|^2, dCat, dG
+        g.update(write_personal)
+        d.all_to_all_single(g.rgrows, g.grows)           # finished gradient rows -> owners
+        return g.apply()
+
+
+class LocalRunner:
+    """All W ranks in one process on one GPU: the collectives become tensor shuffles."""
+
+    def __init__(self, engines):
+        self.engs = list(engines)
+        self.W = len(self.engs)
+        assert all(g.world == self.W and g.rank == r for r, g in enumerate(self.engs))
+
+    def _all_to_all(self, src_attr, dst_attr):
+        W = self.W
+        for r, g in enumerate(self.engs):
+            dst = getattr(g, dst_attr).view(W, g.cap, -1)
+            for s, gs in enumerate(self.engs):
+                dst[s].copy_(getattr(gs, src_attr).view(W, gs.cap, -1)[r])
+
+    def step(self, write_personal=False):
+        for g in self.engs: g.plan()
+        self._all_to_all("req", "rreq")
+        for g in self.engs: g.serve()
+        self._all_to_all("rows", "rbuf")
+        for g in self.engs: g.forward()
+        total = torch.stack([g.packed for g in self.engs]).sum(0)       # rank order, like a ring on W=2
+        for g in self.engs: g.packed.copy_(total)
+        for g in self.engs: g.update(write_personal)
+        self._all_to_all("grows", "rgrows")
+        return [g.apply() for g in self.engs]

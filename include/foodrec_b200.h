@@ -158,6 +158,41 @@ int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int32_t* cand,
                          int32_t K, int32_t* topk_ids, int32_t* gt_rank, float* scores,
                          fr_stream s);
 
+/* ---- Row-sharded training: one process per GPU (torchrun), W <= 8 ranks.
+ * Personal_Memory (+slots) is sharded by user % W -- samples are routed to the user owner
+ * when they are loaded, so the 5D-float user rows and their updates never move;
+ * Recipe_Embedding (+slots) is sharded by recipe % W; Category_Embedding and General_Memory
+ * are replicated.  fr_config.num_users / num_items are the LOCAL row counts.
+ * batch.users are LOCAL user rows (user / W), batch.items GLOBAL recipe ids.
+ * One step = five phases separated by the caller's collectives (torch.distributed / NCCL):
+ *
+ *   fr_shard_plan     sort rows, dedup recipes per owner -> req[W*cap] (row at owner, -1 empty)
+ *     all_to_all(req)                                     -> rreq
+ *   fr_shard_serve    owner: catch up (lazy Adam) and gather the requested rows -> rows[W*cap,D]
+ *     all_to_all(rows)                                    -> rbuf
+ *   fr_shard_forward  forward/loss/norm partials + General_Memory delta -> packed[fr_shard_packed_len]
+ *     all_reduce(packed, SUM)        {loss, sum|g|^2, dCat[4,D], dG[L,5,D]}
+ *   fr_shard_update   clip scale, Cat, Personal_Memory pass, G += dG, recipe gradient rows -> grows[W*cap,D]
+ *     all_to_all(grows)                                   -> rgrows
+ *   fr_shard_apply    owner: segment-reduce the received gradient rows by recipe + optimizer
+ *
+ * cap = per-(source,owner) capacity in unique recipes; overflow sets FR_OUT_OVERFLOW = 2.
+ * All buffers are device memory owned by the caller. */
+typedef struct {
+  int32_t world, rank, cap;
+  int32_t items_per_rank;   /* ceil(I / world): local rows of Recipe_Embedding */
+  int32_t global_batch;     /* groups summed over ranks: the loss mean divides by it */
+} fr_shard;
+int64_t fr_shard_packed_len(fr_handle h);
+int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh, int32_t* req, fr_stream s);
+int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rreq, float* rows, fr_stream s);
+int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* sh, const float* rbuf, float* packed,
+                     fr_stream s);
+int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* sh, int32_t write_personal, const float* rbuf,
+                    const float* packed_reduced, float* grows, float* out_scalars, fr_stream s);
+int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rreq, const float* rgrows, float* out_scalars,
+                   fr_stream s);
+
 /* stable LSD radix sort of (key, index) pairs -- exported for tests of the
  * sort-and-segment machinery.  keys [n] (values < 2^nbits), out_keys/out_idx [n]. */
 int fr_sort_pairs(fr_handle h, const uint32_t* keys, int32_t n, int32_t nbits,

@@ -1,0 +1,96 @@
+"""GPU parity of the row-sharded step: W ranks emulated in one process on one GPU
+(LocalRunner: same kernels, same five phases, collectives as tensor shuffles) must produce
+the tables the unsharded engine produces on the same global batches (tier iv).
+Differences are summation order only: recipe gradients are pre-reduced per rank and loss /
+norm partials per rank."""
+import numpy as np
+import pytest
+import torch
+
+from foodrec_b200 import sharded
+from oracle.recommender_oracle import Hyper as OHyper
+from tests.util import Problem, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def build(p, W, learner, adam_mode, max_rows=2048, cap=None):
+    from foodrec_b200 import Engine, Hyper
+    h = Hyper(learner=learner, lr=0.01)
+    single = Engine(h, p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=max_rows, adam_mode=adam_mode,
+                    max_label_entries=max_rows * p.L)
+    rows, cols = np.nonzero(p.user_labels)
+    cnt = np.bincount(rows, minlength=p.U)
+    off = np.zeros(p.U + 1, np.int32); off[1:] = np.cumsum(cnt)
+    engs = []
+    for r in range(W):
+        engs.append(sharded.ShardedEngine(
+            h, sharded.shard_rows(p.tb.P, r, W), sharded.shard_rows(p.tb.R, r, W), p.tb.Cat, p.tb.G, r, W,
+            max_rows=max_rows, cap=cap, adam_mode=adam_mode, item_cats_global=p.item_cats,
+            user_label_csr_local=sharded.shard_label_csr(off, cols.astype(np.int32), r, W, p.U),
+            max_label_entries=max_rows * p.L))
+    return single, engs
+
+
+def gather(engs, p):
+    W = len(engs)
+    for g in engs:
+        g.e.flush()
+    t = {"P": sharded.unshard_rows([g.e.P.cpu().numpy() for g in engs], p.U),
+         "R": sharded.unshard_rows([g.e.R.cpu().numpy() for g in engs], p.I),
+         "Cat": engs[0].e.Cat.cpu().numpy(), "G": engs[0].e.G.cpu().numpy()}
+    for g in engs[1:]:        # replicated tables must be identical on every rank
+        np.testing.assert_array_equal(g.e.Cat.cpu().numpy(), t["Cat"])
+        np.testing.assert_array_equal(g.e.G.cpu().numpy(), t["G"])
+    return t
+
+
+@pytest.mark.parametrize("W", [2, 4])
+@pytest.mark.parametrize("learner,adam_mode,bpr", [("sgd", "dense", False), ("adagrad", "dense", True),
+                                                  ("adam", "dense", False), ("adam", "lazy_exact", True),
+                                                  ("adam", "lazy", True), ("adam", "lazy", False)])
+def test_sharded_equals_unsharded(W, learner, adam_mode, bpr):
+    p = Problem(403, 257, 9, 64, seed=61)            # sizes not divisible by W: padded shards
+    single, engs = build(p, W, learner, adam_mode)
+    run = sharded.LocalRunner(engs)
+    for s in range(5):
+        B = 300
+        users = None
+        if s == 2:
+            users = np.repeat(np.arange(12), 25)      # duplicate-heavy, runs cross chunks
+        f = p.bpr(B, seed=80 + s, users=users) if bpr else p.pointwise(B, seed=80 + s, users=users)
+        personal = (s == 0)
+        # unsharded reference: compact feed so both sides use the same side tables
+        kw = dict(neg_items=f["neg_item_input"], neg_categories=f["neg_categories"]) if bpr else {}
+        single.train_step(f["user_input"], f["item_input"], labels=None if bpr else f["labels"],
+                          categories=f["categories"], user_one_hot_label=f["user_one_hot_label"],
+                          write_sign=None, write_personal=personal, **kw)
+        v1 = single.read_scalars().copy()
+        idx = sharded.route_batch(f["user_input"], W)
+        for r, g in enumerate(engs):
+            ix = idx[r]
+            assert len(ix) > 0
+            g.set_batch(f["user_input"][ix] // W, f["item_input"][ix],
+                        labels=None if bpr else f["labels"][ix],
+                        neg_items=f["neg_item_input"][ix] if bpr else None, global_batch=B)
+        outs = run.step(write_personal=personal)
+        v = outs[0].cpu().numpy()
+        assert v[9] == 0, "capacity/label overflow flag"
+        assert v[0] == pytest.approx(v1[0], rel=1e-5) and v[1] == pytest.approx(v1[1], rel=1e-5)   # global loss / norm
+        assert v[2] == pytest.approx(v1[2], rel=1e-6)
+    ts, tr = gather(engs, p), single.tables()
+    rt = 1e-5 if learner != "adam" else 1e-4          # Adam: conditioning (tests/util.py), summation order differs
+    for k in ("P", "R", "Cat", "G"):
+        assert_close(ts[k], tr[k], rtol=rt, what=f"W={W} {learner}/{adam_mode} {k}")
+
+
+def test_capacity_overflow_is_reported():
+    p = Problem(64, 200, 5, 16, seed=3)
+    single, engs = build(p, 2, "sgd", "dense", max_rows=512, cap=4)     # far too small
+    run = sharded.LocalRunner(engs)
+    f = p.pointwise(200, seed=1)
+    idx = sharded.route_batch(f["user_input"], 2)
+    for r, g in enumerate(engs):
+        g.set_batch(f["user_input"][idx[r]] // 2, f["item_input"][idx[r]], labels=f["labels"][idx[r]], global_batch=200)
+    outs = run.step()
+    assert outs[0].cpu().numpy()[9] == 2.0
