@@ -116,6 +116,13 @@ class ShardedEngine:
         self._b = L.fr_batch(L.FR_BPR if bpr else L.FR_POINTWISE, B, _ptr(u), _ptr(it), _ptr(cats), _ptr(lab), _ptr(ws), _ptr(ul))
         self._sh = self._shard(global_batch if global_batch is not None else B)
 
+    def set_batch_dev(self, mode, B, users_local, items, labels=None, global_batch=None):
+        """Device tensors already in the C-ABI layout (int32 users [B]; int32 items [S],
+        BPR rows interleaved pos/neg): nothing is copied or reshaped."""
+        self._keep = [users_local, items, labels]
+        self._b = L.fr_batch(mode, B, _ptr(users_local), _ptr(items), _ptr(None), _ptr(labels), _ptr(None), _ptr(None))
+        self._sh = self._shard(global_batch if global_batch is not None else B)
+
     # the five phases ------------------------------------------------------------------
     def plan(self):
         e = self.e

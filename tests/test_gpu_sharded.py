@@ -84,6 +84,20 @@ def test_sharded_equals_unsharded(W, learner, adam_mode, bpr):
         assert_close(ts[k], tr[k], rtol=rt, what=f"W={W} {learner}/{adam_mode} {k}")
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_nccl_sharded_equals_unsharded():
+    """The same comparison across real processes: torchrun x2, NCCL all-to-all / all-reduce."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(root, "tests", "dist_check.py")],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and out.stdout.count("DIST_CHECK_OK_") == 2, out.stdout[-1500:] + out.stderr[-3000:]
+
+
 def test_capacity_overflow_is_reported():
     p = Problem(64, 200, 5, 16, seed=3)
     single, engs = build(p, 2, "sgd", "dense", max_rows=512, cap=4)     # far too small

@@ -45,7 +45,7 @@ def test_label_csr_sharding():
 
 WIRING = textwrap.dedent("""
     import os, sys, torch, torch.distributed as dist
-    sys.path.insert(0, %r)
+    sys.path.insert(0, "__ROOT__")
     from foodrec_b200.sharded import DistRunner
     dist.init_process_group("gloo")
     r, W, cap, D = dist.get_rank(), dist.get_world_size(), 3, 2
@@ -82,7 +82,7 @@ WIRING = textwrap.dedent("""
 
 def test_dist_runner_wiring_gloo_world2(tmp_path):
     script = tmp_path / "wiring.py"
-    script.write_text(WIRING % ROOT)
+    script.write_text(WIRING.replace("__ROOT__", ROOT))
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
