@@ -266,8 +266,10 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
 
   // 1. row keys, write sign; sort item rows by user and by recipe
   launch_prep_rows(b->mode, B, b->users, b->labels, b->write_sign, h->ukeys, h->ws_row, l);
-  const int ru = radix_sort_pairs(h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), st, h->sm_count);
-  const int ri = radix_sort_pairs(h->sortI, (const uint32_t*)b->items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), st, h->sm_count);
+  SortJob sj[2] = {{&h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), 0},
+                   {&h->sortI, (const uint32_t*)b->items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), 0}};
+  radix_sort_jobs(sj, 2, st, h->sm_count);      // by user and by recipe, sharing their launches
+  const int ru = sj[0].result, ri = sj[1].result;
   FR_CHECK_LAUNCH(h);
   const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
   if (lazy) {   // recipe rows of this batch must be current before anything reads them

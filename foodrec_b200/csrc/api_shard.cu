@@ -80,8 +80,10 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   p.flags = w.flags; p.excl = w.excl; p.owner_counts = w.owner_counts;
   p.req = req; p.slot_of_row = w.slot_of_row; p.slot_sorted = w.slot_sorted; p.out = h->out_internal;
   launch_shard_prep(p, l);
-  w.ru = radix_sort_pairs(h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), st, h->sm_count);
-  w.ri = radix_sort_pairs(h->sortI, w.okeys, (uint32_t)S, nullptr, bits_for((int64_t)W * sh->items_per_rank), st, h->sm_count);
+  SortJob sj[2] = {{&h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), 0},
+                   {&h->sortI, w.okeys, (uint32_t)S, nullptr, bits_for((int64_t)W * sh->items_per_rank), 0}};
+  radix_sort_jobs(sj, 2, st, h->sm_count);
+  w.ru = sj[0].result; w.ri = sj[1].result;
   p.okeys_sorted = h->sortI.k[w.ri]; p.perm = h->sortI.v[w.ri];
   launch_shard_heads(p, l);
   exclusive_scan_u32(w.flags, w.excl, (uint32_t)S, h->scan_tmp, nullptr, st);

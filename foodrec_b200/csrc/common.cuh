@@ -59,25 +59,15 @@ __device__ __forceinline__ void st_stream(float4* p, const float4 v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Fire-and-forget TMA bulk prefetch of a contiguous span into L2 (UBLKPF).  The row
-// movers are latency-bound (a warp's registers hold one table row at a time); prefetching
-// the rows of the NEXT work item turns their demand loads into L2 hits and gives the
-// memory system more bytes in flight without holding any registers.
-// Build variants (bench A/B): -DFR_PREFETCH (TMA bulk) [-DFR_PREFETCH_LINES: per-128B prefetch.global.L2].
-__device__ __forceinline__ void prefetch_l2_span(const void* p, uint32_t bytes) {   // one lane, whole span
-#if !defined(FR_PREFETCH)   // measured on B200: no gain (kernels are not latency-bound), so off by default
-  (void)p; (void)bytes;
-#elif defined(FR_PREFETCH_LINES)
-  for (uint32_t o = 0; o < bytes; o += 128)
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(p) + o));
-#else
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-#endif
-}
+// Fire-and-forget TMA bulk prefetch of a contiguous span into L2 (SASS: UBLKPF).  A row
+// mover is latency-bound per warp (its registers hold one table row at a time); prefetching
+// the rows of the warp's NEXT work item turns their demand loads into L2 hits and puts
+// more bytes in flight without holding registers.  Measured on B200 (bench A/B, B=65536):
+// forward 0.226 -> 0.186 ms with it (used there); the segment-reduce passes got 5 % slower
+// (they already run at ~80 % of the HBM peak; kept behind -DFR_PREFETCH_SEG).
+// -DFR_PREFETCH_LINES swaps the bulk op for per-128 B prefetch.global.L2 (same result).
 __device__ __forceinline__ void prefetch_l2_warp(const void* p, uint32_t bytes, int lane) {   // all lanes call
-#if !defined(FR_PREFETCH)   // measured on B200: no gain (kernels are not latency-bound), so off by default
-  (void)p; (void)bytes; (void)lane;
-#elif defined(FR_PREFETCH_LINES)
+#if defined(FR_PREFETCH_LINES)
   for (uint32_t o = (uint32_t)lane * 128u; o < bytes; o += 32u * 128u)
     asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(p) + o));
 #else

@@ -7,7 +7,7 @@
 namespace fr {
 
 constexpr int SORT_TILE = 2048;     // keys per block-iteration of the radix passes
-constexpr int RADIX_BITS = 8;
+constexpr int RADIX_BITS = 10;      // widest digit of a pass (sort.cu picks <= this per job)
 constexpr int RADIX_BINS = 1 << RADIX_BITS;
 
 struct SortBufs {
@@ -23,6 +23,13 @@ struct SortBufs {
 // n_host with a device-resident count <= n_host.
 int radix_sort_pairs(SortBufs& bufs, const uint32_t* keys_in, uint32_t n_host,
                      const uint32_t* n_dev, int nbits, cudaStream_t st, int sm_count);
+
+// Up to two independent sorts sharing their launches (blockIdx.y): job i's output lands in
+// (bufs->k[result], bufs->v[result]).
+struct SortJob {
+  SortBufs* bufs; const uint32_t* keys_in; uint32_t n_host; const uint32_t* n_dev; int nbits; int result;
+};
+void radix_sort_jobs(SortJob* jobs, int njobs, cudaStream_t st, int sm_count);
 
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp,
                         uint32_t* total_out /*nullable*/, cudaStream_t st);

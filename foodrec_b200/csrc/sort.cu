@@ -6,10 +6,13 @@
 // unsorted_segment_sum uses on CPU (optimizer.py:_deduplicate_indexed_slices).
 // Stability is what preserves batch order inside a segment.
 //
-// Per 8-bit pass: (1) per-tile digit histogram, (2) exclusive scan of the
-// bin-major [256 x ntiles] table, (3) scatter with warp-level stable ranking
-// (__match_any_sync multisplit).  All loads are coalesced; the tile is re-read by
-// the scatter pass (L2 hit: a tile is 16 KB).
+// Per pass (digit of up to 10 bits: 20-bit user ids sort in 2 passes): (1) per-tile digit
+// histogram, (2) offsets -- derived inside the scatter kernel from the raw histograms when
+// there are few tiles, else by a separate scan of the bin-major [bins x ntiles] table,
+// (3) scatter with warp-level stable ranking (__match_any_sync multisplit).  One launch
+// serves up to two independent jobs (blockIdx.y): the by-user and the by-recipe sort of a
+// step share their launches.  All loads are coalesced; the tile is re-read by the scatter
+// pass (L2 hit: a tile is 16 KB).
 #include "common.cuh"
 #include "internal.h"
 
@@ -22,22 +25,37 @@ __device__ __forceinline__ uint32_t resolve_n(const uint32_t* n_dev, uint32_t n_
   return n_host;
 }
 
+constexpr int MAX_DIGIT_BITS = 10;
+constexpr int MAX_BINS = 1 << MAX_DIGIT_BITS;
+constexpr int FUSED_SCAN_MAX_TILES = 128;
+
+struct PassJob {
+  const uint32_t* keys_in; const uint32_t* vals_in;   // vals_in == nullptr: identity
+  uint32_t* keys_out; uint32_t* vals_out;
+  uint32_t n_host; const uint32_t* n_dev;
+  int shift, bits;                                     // bits == 0: job idle in this pass
+  uint32_t ntiles; uint32_t* tile_hist; int fused;
+};
+struct PassJobs { PassJob j[2]; };
+
 __global__ void __launch_bounds__(FR_THREADS)
-radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_host, const uint32_t* n_dev,
-                  int shift, uint32_t ntiles, uint32_t* __restrict__ tile_hist) {
-  __shared__ uint32_t hist[RADIX_BINS];
-  const uint32_t n = resolve_n(n_dev, n_host);
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    hist[threadIdx.x] = 0;
+radix_hist_kernel(const PassJobs jobs) {
+  __shared__ uint32_t hist[MAX_BINS];
+  const PassJob& J = jobs.j[blockIdx.y];
+  if (J.bits == 0) return;
+  const uint32_t n = resolve_n(J.n_dev, J.n_host);
+  const uint32_t bins = 1u << J.bits, mask = bins - 1u;
+  for (uint32_t tile = blockIdx.x; tile < J.ntiles; tile += gridDim.x) {
+    for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) hist[b] = 0;
     __syncthreads();
     const uint32_t base = tile * SORT_TILE;
 #pragma unroll
     for (int r = 0; r < SORT_TILE / FR_THREADS; ++r) {
       const uint32_t idx = base + r * FR_THREADS + threadIdx.x;
-      if (idx < n) atomicAdd(&hist[(keys[idx] >> shift) & (RADIX_BINS - 1)], 1u);
+      if (idx < n) atomicAdd(&hist[(J.keys_in[idx] >> J.shift) & mask], 1u);
     }
     __syncthreads();
-    tile_hist[threadIdx.x * ntiles + tile] = hist[threadIdx.x];
+    for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) J.tile_hist[(size_t)b * J.ntiles + tile] = hist[b];
     __syncthreads();
   }
 }
@@ -45,49 +63,57 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_host, const uint
 // Each warp owns 256 consecutive keys of the tile (8 rounds of 32), so the order
 // (warp, round, lane) is the input order.
 __global__ void __launch_bounds__(FR_THREADS)
-radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                     uint32_t n_host, const uint32_t* n_dev, int shift, uint32_t ntiles,
-                     const uint32_t* __restrict__ tile_off, int fused_scan) {
-  __shared__ uint32_t wcnt[FR_WARPS_PER_BLOCK][RADIX_BINS];
+radix_scatter_kernel(const PassJobs jobs) {
+  __shared__ uint32_t wcnt[FR_WARPS_PER_BLOCK][MAX_BINS];
   __shared__ uint32_t wtot[FR_WARPS_PER_BLOCK];
-  const uint32_t n = resolve_n(n_dev, n_host);
+  const PassJob& J = jobs.j[blockIdx.y];
+  if (J.bits == 0) return;
+  const uint32_t n = resolve_n(J.n_dev, J.n_host);
+  const uint32_t bins = 1u << J.bits, mask = bins - 1u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   constexpr int ROUNDS = SORT_TILE / FR_THREADS;  // 8
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  constexpr int BPT = MAX_BINS / FR_THREADS;      // bins per thread (contiguous) in the offset scan
+  for (uint32_t tile = blockIdx.x; tile < J.ntiles; tile += gridDim.x) {
     const uint32_t base = tile * SORT_TILE + warp * (ROUNDS * 32);
     if (tile * SORT_TILE >= n) break;   // uniform: later tiles are empty too
-    for (int b = lane; b < RADIX_BINS; b += 32) wcnt[warp][b] = 0;
+    for (uint32_t b = lane; b < bins; b += 32) wcnt[warp][b] = 0;
     __syncwarp();
     uint32_t key[ROUNDS], val[ROUNDS];
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
       const uint32_t idx = base + r * 32 + lane;
       const bool valid = idx < n;
-      key[r] = valid ? keys_in[idx] : 0u;
-      val[r] = valid ? (vals_in ? vals_in[idx] : idx) : 0u;
-      const uint32_t d = valid ? ((key[r] >> shift) & (RADIX_BINS - 1)) : (RADIX_BINS + lane);
-      const uint32_t mask = __match_any_sync(FR_FULL, d);
-      if (valid && (mask & lt) == 0) wcnt[warp][d] += __popc(mask);   // group leader
+      key[r] = valid ? J.keys_in[idx] : 0u;
+      val[r] = valid ? (J.vals_in ? J.vals_in[idx] : idx) : 0u;
+      const uint32_t d = valid ? ((key[r] >> J.shift) & mask) : (MAX_BINS + lane);
+      const uint32_t m = __match_any_sync(FR_FULL, d);
+      if (valid && (m & lt) == 0) wcnt[warp][d] += __popc(m);   // group leader
       __syncwarp();
     }
     __syncthreads();
-    {  // exclusive scan over warps per digit, seeded with the global tile offset
-      const int b = threadIdx.x;
-      uint32_t run;
-      if (fused_scan) {
-        // few tiles: tile_off holds the RAW per-tile histograms and every block derives
-        // its own offsets (saves the separate scan launches of the pass):
-        //   offset[b][tile] = sum_{b'<b} total[b'] + sum_{t<tile} hist[b][t]
-        const uint32_t* hrow = tile_off + (size_t)b * ntiles;
-        uint32_t pre = 0, tot = 0;
-        for (uint32_t t = 0; t < ntiles; ++t) {
-          const uint32_t c = hrow[t];
-          tot += c;
-          if (t < tile) pre += c;
+    {  // per digit: exclusive scan over warps, seeded with the global offset of (digit, tile)
+      uint32_t run[BPT];
+      const uint32_t b0 = threadIdx.x * BPT;
+      if (J.fused) {
+        // few tiles: tile_hist holds the RAW per-tile histograms and every block derives its
+        // own offsets:  offset[b][tile] = sum_{b'<b} total[b'] + sum_{t<tile} hist[b][t]
+        uint32_t pre[BPT], tot[BPT], tsum = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+          pre[q] = 0; tot[q] = 0;
+          const uint32_t b = b0 + q;
+          if (b < bins) {
+            const uint32_t* hrow = J.tile_hist + (size_t)b * J.ntiles;
+            for (uint32_t t = 0; t < J.ntiles; ++t) {
+              const uint32_t c = hrow[t];
+              tot[q] += c;
+              if (t < tile) pre[q] += c;
+            }
+          }
+          tsum += tot[q];
         }
-        uint32_t inc = tot;
+        uint32_t inc = tsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const uint32_t y = __shfl_up_sync(FR_FULL, inc, o);
@@ -95,18 +121,27 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         }
         if (lane == 31) wtot[warp] = inc;
         __syncthreads();
-        uint32_t wbase = 0;
+        uint32_t acc = inc - tsum;
 #pragma unroll
-        for (int w = 0; w < FR_WARPS_PER_BLOCK; ++w) if (w < warp) wbase += wtot[w];
-        run = wbase + (inc - tot) + pre;
+        for (int w = 0; w < FR_WARPS_PER_BLOCK; ++w) if (w < warp) acc += wtot[w];
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) { run[q] = acc + pre[q]; acc += tot[q]; }
       } else {
-        run = tile_off[b * ntiles + tile];
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) run[q] = (b0 + q < bins) ? J.tile_hist[(size_t)(b0 + q) * J.ntiles + tile] : 0u;
       }
 #pragma unroll
-      for (int w = 0; w < FR_WARPS_PER_BLOCK; ++w) {
-        const uint32_t c = wcnt[w][b];
-        wcnt[w][b] = run;
-        run += c;
+      for (int q = 0; q < BPT; ++q) {
+        const uint32_t b = b0 + q;
+        if (b < bins) {
+          uint32_t r2 = run[q];
+#pragma unroll
+          for (int w = 0; w < FR_WARPS_PER_BLOCK; ++w) {
+            const uint32_t c = wcnt[w][b];
+            wcnt[w][b] = r2;
+            r2 += c;
+          }
+        }
       }
     }
     __syncthreads();
@@ -114,14 +149,14 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     for (int r = 0; r < ROUNDS; ++r) {
       const uint32_t idx = base + r * 32 + lane;
       const bool valid = idx < n;
-      const uint32_t d = valid ? ((key[r] >> shift) & (RADIX_BINS - 1)) : (RADIX_BINS + lane);
-      const uint32_t mask = __match_any_sync(FR_FULL, d);
+      const uint32_t d = valid ? ((key[r] >> J.shift) & mask) : (MAX_BINS + lane);
+      const uint32_t m = __match_any_sync(FR_FULL, d);
       uint32_t dst = 0;
-      if (valid) dst = wcnt[warp][d] + __popc(mask & lt);
+      if (valid) dst = wcnt[warp][d] + __popc(m & lt);
       __syncwarp();
-      if (valid && (mask & lt) == 0) wcnt[warp][d] += __popc(mask);
+      if (valid && (m & lt) == 0) wcnt[warp][d] += __popc(m);
       __syncwarp();
-      if (valid) { keys_out[dst] = key[r]; vals_out[dst] = val[r]; }
+      if (valid) { J.keys_out[dst] = key[r]; J.vals_out[dst] = val[r]; }
     }
     __syncthreads();
   }
@@ -230,29 +265,68 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t*
   g_launches += 3;
 }
 
+// ---------------------------------------------------------------- host side
+static void plan_digits(int nbits, int& passes, int& bits_per_pass) {
+  if (nbits < 1) nbits = 1;
+  passes = (nbits + MAX_DIGIT_BITS - 1) / MAX_DIGIT_BITS;
+  bits_per_pass = (nbits + passes - 1) / passes;
+}
+
+// Sort up to two independent jobs with shared launches.  result[i] = index of the buffer
+// pair (bufs.k[r], bufs.v[r]) that holds job i's sorted output.
+void radix_sort_jobs(SortJob* jobs, int njobs, cudaStream_t st, int sm_count) {
+  int passes[2] = {0, 0}, bpp[2] = {0, 0}, dst[2] = {0, 0};
+  const uint32_t* kin[2]; const uint32_t* vin[2];
+  int maxp = 0;
+  uint32_t max_tiles = 0;
+  for (int i = 0; i < njobs; ++i) {
+    plan_digits(jobs[i].nbits, passes[i], bpp[i]);
+    if (jobs[i].n_host == 0) passes[i] = 0;
+    if (passes[i] > maxp) maxp = passes[i];
+    kin[i] = jobs[i].keys_in; vin[i] = nullptr;
+    const uint32_t nt = (jobs[i].n_host + SORT_TILE - 1) / SORT_TILE;
+    if (nt > max_tiles) max_tiles = nt;
+    jobs[i].result = 0;
+  }
+  if (maxp == 0 || max_tiles == 0) return;
+  const int gx = (int)(max_tiles < (uint32_t)(sm_count * 4) ? max_tiles : (uint32_t)(sm_count * 4));
+  for (int p = 0; p < maxp; ++p) {
+    PassJobs pj{};
+    for (int i = 0; i < 2; ++i) {
+      PassJob& J = pj.j[i];
+      if (i >= njobs || p >= passes[i]) { J.bits = 0; continue; }
+      SortBufs& b = *jobs[i].bufs;
+      J.keys_in = kin[i]; J.vals_in = vin[i]; J.keys_out = b.k[dst[i]]; J.vals_out = b.v[dst[i]];
+      J.n_host = jobs[i].n_host; J.n_dev = jobs[i].n_dev;
+      J.shift = p * bpp[i];
+      const int left = jobs[i].nbits - J.shift;
+      J.bits = left < bpp[i] ? (left < 1 ? 1 : left) : bpp[i];
+      J.ntiles = (jobs[i].n_host + SORT_TILE - 1) / SORT_TILE;
+      J.tile_hist = b.tile_hist;
+      J.fused = J.ntiles <= FUSED_SCAN_MAX_TILES ? 1 : 0;
+    }
+    radix_hist_kernel<<<dim3(gx, njobs), FR_THREADS, 0, st>>>(pj);
+    ++g_launches;
+    for (int i = 0; i < njobs; ++i)
+      if (pj.j[i].bits && !pj.j[i].fused)
+        exclusive_scan_u32(pj.j[i].tile_hist, pj.j[i].tile_hist, (uint32_t)(1u << pj.j[i].bits) * pj.j[i].ntiles,
+                           jobs[i].bufs->scan_tmp, nullptr, st);
+    radix_scatter_kernel<<<dim3(gx, njobs), FR_THREADS, 0, st>>>(pj);
+    ++g_launches;
+    for (int i = 0; i < njobs; ++i) {
+      if (!pj.j[i].bits) continue;
+      kin[i] = pj.j[i].keys_out; vin[i] = pj.j[i].vals_out;
+      jobs[i].result = dst[i];
+      dst[i] ^= 1;
+    }
+  }
+}
+
 int radix_sort_pairs(SortBufs& bufs, const uint32_t* keys_in, uint32_t n_host,
                      const uint32_t* n_dev, int nbits, cudaStream_t st, int sm_count) {
-  int passes = (nbits + RADIX_BITS - 1) / RADIX_BITS;
-  if (passes < 1) passes = 1;
-  const uint32_t ntiles = (n_host + SORT_TILE - 1) / SORT_TILE;
-  if (ntiles == 0) return 0;
-  const int grid = (int)(ntiles < (uint32_t)(sm_count * 4) ? ntiles : (uint32_t)(sm_count * 4));
-  const uint32_t* kin = keys_in;
-  const uint32_t* vin = nullptr;
-  int dst = 0;
-  for (int p = 0; p < passes; ++p) {
-    const int shift = p * RADIX_BITS;
-    const int fused = ntiles <= 128 ? 1 : 0;
-    radix_hist_kernel<<<grid, FR_THREADS, 0, st>>>(kin, n_host, n_dev, shift, ntiles, bufs.tile_hist);
-    if (!fused) exclusive_scan_u32(bufs.tile_hist, bufs.tile_hist, RADIX_BINS * ntiles, bufs.scan_tmp, nullptr, st);
-    radix_scatter_kernel<<<grid, FR_THREADS, 0, st>>>(kin, vin, bufs.k[dst], bufs.v[dst], n_host, n_dev,
-                                                      shift, ntiles, bufs.tile_hist, fused);
-    g_launches += 2;
-    kin = bufs.k[dst];
-    vin = bufs.v[dst];
-    dst ^= 1;
-  }
-  return dst ^ 1;
+  SortJob j{&bufs, keys_in, n_host, n_dev, nbits, 0};
+  radix_sort_jobs(&j, 1, st, sm_count);
+  return j.result;
 }
 
 }  // namespace fr

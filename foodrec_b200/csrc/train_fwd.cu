@@ -65,6 +65,18 @@ fwd_train_kernel(const FwdParams p) {
 
   for (int grp = gw; grp < p.B; grp += nw) {
     const int u = p.users[grp];
+#ifndef FR_NO_FWD_PREFETCH
+    if (grp + nw < p.B) {       // L2-prefetch the rows of this warp's next group (no registers held)
+      const int gn = grp + nw;
+      const uint32_t ub = 5u * (uint32_t)DV * 16u, rb = (uint32_t)DV * 16u;
+      const size_t uo = (size_t)p.users[gn] * 5 * DV;
+      prefetch_l2_warp(p.P + uo, ub, lane);
+      if (LAZY != 0) { prefetch_l2_warp(p.mP + uo, ub, (lane + 31) & 31); prefetch_l2_warp(p.vP + uo, ub, (lane + 30) & 31); }
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j)
+        prefetch_l2_warp(p.R + (size_t)p.items[gn * GROUP + j] * DV, rb, (lane + 29 - j) & 31);
+    }
+#endif
     float4 pr[5][NV];
 #pragma unroll
     for (int s = 0; s < 5; ++s) load_row<NV>(pr[s], p.P + ((size_t)u * 5 + s) * DV, DV, lane);

@@ -50,9 +50,21 @@ seg_chunk_kernel(const SegCommon c, const Pol pol) {
     const bool to_next = has_next && nextKey == lastKey;
     if (c.uniq_counter && lane == 0) atomicAdd(c.uniq_counter, (uint32_t)__popc(hm));
     int e0 = 0;
+#ifdef FR_PREFETCH_SEG
+    {   // state rows of the second run of the chunk (the first is loaded right away)
+      const uint32_t r1 = hm & ~1u;
+      if (r1) pol.prefetch_state(__shfl_sync(FR_FULL, key, __ffs(r1) - 1), lane);
+    }
+#endif
     while (e0 < cnt) {
       const uint32_t rest = (e0 >= 31) ? 0u : (hm & ~((2u << e0) - 1u));
       const int e1 = rest ? (__ffs(rest) - 1) : cnt;
+#ifdef FR_PREFETCH_SEG
+      {   // ... and, while this run is processed, of the run after the next one
+        const uint32_t r2 = rest & (rest - 1u);
+        if (r2) pol.prefetch_state(__shfl_sync(FR_FULL, key, __ffs(r2) - 1), lane);
+      }
+#endif
       const bool starts = (e0 > 0) || !from_prev;
       const bool ends = (e1 < cnt) || !to_next;
       const uint32_t k = __shfl_sync(FR_FULL, key, e0);
@@ -219,6 +231,13 @@ struct UserPol {
   __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
     fr::load_state<OPT, 5, NV>(st, p.P, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
   }
+  __device__ __forceinline__ void prefetch_state(uint32_t key, int lane) const {
+    const uint32_t bytes = 5u * (uint32_t)p.mc.DV * 16u;      // a user's 5 slots are contiguous
+    const size_t off = (size_t)key * 5 * p.mc.DV;
+    prefetch_l2_warp(p.P + off, bytes, lane);
+    if (OPT != OPT_GENERIC || p.oc.learner != FR_SGD) prefetch_l2_warp(p.s1 + off, bytes, (lane + 31) & 31);
+    if (OPT != OPT_GENERIC || p.oc.learner == FR_RMSPROP) prefetch_l2_warp(p.s2 + off, bytes, (lane + 30) & 31);
+  }
   __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[5][NV], int lane) const {
     apply_and_store<OPT, 5, NV>(st, p.P, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
   }
@@ -235,6 +254,7 @@ struct PersonalPol {
   UserPolParams p;
   struct Entry { int item; float ws; float4 m; int grp; };
   struct State { float4 var[5][NVV]; };
+  __device__ __forceinline__ void prefetch_state(uint32_t, int) const {}
   __device__ __forceinline__ int DV() const { return p.mc.DV; }
   __device__ __forceinline__ const float4* cat_src() const { return p.cat; }
   __device__ __forceinline__ Entry load_entry(uint32_t row, bool valid) const {
@@ -374,6 +394,13 @@ struct ItemPol {
   __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
     fr::load_state<OPT, 1, NV>(st, p.R, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
   }
+  __device__ __forceinline__ void prefetch_state(uint32_t key, int lane) const {
+    const uint32_t bytes = (uint32_t)p.mc.DV * 16u;
+    const size_t off = (size_t)key * p.mc.DV;
+    prefetch_l2_warp(p.R + off, bytes, lane);
+    if (OPT != OPT_GENERIC || p.oc.learner != FR_SGD) prefetch_l2_warp(p.s1 + off, bytes, (lane + 31) & 31);
+    if (OPT != OPT_GENERIC || p.oc.learner == FR_RMSPROP) prefetch_l2_warp(p.s2 + off, bytes, (lane + 30) & 31);
+  }
   __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[1][NV], int lane) const {
     apply_and_store<OPT, 1, NV>(st, p.R, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
   }
@@ -386,6 +413,7 @@ template <int NVV>
 struct ItemGradPol : ItemPol<NVV, OPT_GENERIC> {
   float4* gbuf;                       // [W*cap, DV], key = slot
   struct State {};
+  __device__ __forceinline__ void prefetch_state(uint32_t, int) const {}
   __device__ __forceinline__ void load_state(State&, uint32_t, int) const {}
   __device__ __forceinline__ void apply(State&, uint32_t key, float4 (&acc)[1][NVV], int lane) const {
     const int DVv = this->p.mc.DV;
@@ -406,6 +434,7 @@ struct LabelPol {
   LabelPolParams p;
   struct Entry { int item; float coef; float4 m; };
   struct State { float4 var[5][NVV]; };
+  __device__ __forceinline__ void prefetch_state(uint32_t, int) const {}
   __device__ __forceinline__ int DV() const { return p.mc.DV; }
   __device__ __forceinline__ const float4* cat_src() const { return p.cat; }
   __device__ __forceinline__ Entry load_entry(uint32_t ent, bool valid) const {
@@ -466,6 +495,172 @@ struct LabelPol {
   }
 };
 
+// ---- tiled variant for FEW, LONG runs (the label pass: <= ~100 keys, runs of thousands).
+// A warp owns a tile of TC consecutive 32-entry chunks and carries its accumulator from
+// chunk to chunk, so a run leaves at most two partials per TILE instead of per chunk and
+// the combine chain is TC times shorter.  Same slot rule (slot 0: the run holding the
+// tile's first entry, slot 1: the run holding its last), same deterministic order.
+template <class Pol, int TC>
+__global__ void __launch_bounds__(FR_THREADS)
+seg_tile_kernel(const SegCommon c, const Pol pol) {
+  extern __shared__ float4 smem[];
+  constexpr int NR = Pol::NR, NV = Pol::NV;
+  const int DV = pol.DV();
+  if (pol.cat_src()) {
+    for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) smem[i] = pol.cat_src()[i];
+    __syncthreads();
+  }
+  const uint32_t n = c.n_dev ? min(*c.n_dev, c.n_host) : c.n_host;
+  constexpr uint32_t TL = 32u * TC;
+  const uint32_t ntiles = (n + TL - 1) / TL;
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const uint32_t nw = gridDim.x * FR_WARPS_PER_BLOCK;
+  for (uint32_t tile = gw; tile < ntiles; tile += nw) {
+    const uint32_t tbase = tile * TL;
+    float4 acc[NR][NV];
+#pragma unroll
+    for (int s = 0; s < NR; ++s)
+#pragma unroll
+      for (int q = 0; q < NV; ++q) acc[s][q] = f4zero();
+    bool started_in_tile = false;      // the open run's head lies inside this tile
+    bool has_first = true;             // the open run holds the tile's first entry
+    for (int sub = 0; sub < TC; ++sub) {
+      const uint32_t base = tbase + (uint32_t)sub * 32u;
+      if (base >= n) break;
+      const int cnt = (int)min(32u, n - base);
+      const bool valid = lane < cnt;
+      const uint32_t key = valid ? c.keys[base + lane] : 0xffffffffu;
+      const uint32_t ent = valid ? c.perm[base + lane] : 0u;
+      const uint32_t prevKey = base > 0 ? c.keys[base - 1] : 0u;
+      const bool has_next = base + 32 < n;
+      const uint32_t nextKey = has_next ? c.keys[base + 32] : 0u;
+      const typename Pol::Entry e = pol.load_entry(ent, valid);
+      const uint32_t up = __shfl_up_sync(FR_FULL, key, 1);
+      const bool head = valid && (lane == 0 ? (base == 0 || prevKey != key) : (up != key));
+      const uint32_t hm = __ballot_sync(FR_FULL, head);
+      const uint32_t lastKey = __shfl_sync(FR_FULL, key, cnt - 1);
+      const bool to_next = has_next && nextKey == lastKey;
+      const bool tile_ends = (sub == TC - 1) || (base + 32 >= n);
+      int e0 = 0;
+      while (e0 < cnt) {
+        const uint32_t rest = (e0 >= 31) ? 0u : (hm & ~((2u << e0) - 1u));
+        const int e1 = rest ? (__ffs(rest) - 1) : cnt;
+        if ((hm >> e0) & 1u) started_in_tile = true;          // a new run begins at e0
+        const uint32_t k = __shfl_sync(FR_FULL, key, e0);
+        pol.accumulate(acc, e, e0, e1, lane, smem);
+        const bool run_ends = (e1 < cnt) || !to_next;
+        if (run_ends || tile_ends) {
+          if (run_ends && started_in_tile) {                   // whole run inside the tile
+            typename Pol::State st;
+            pol.load_state(st, k, lane);
+            pol.apply(st, k, acc, lane);
+          } else {                                             // crosses a tile boundary: leave a partial
+            float4* dst = c.pieces + ((size_t)tile * 2 + (has_first ? 0 : 1)) * NR * DV;
+#pragma unroll
+            for (int s = 0; s < NR; ++s)
+#pragma unroll
+              for (int q = 0; q < NV; ++q) {
+                const int i = lane + 32 * q;
+                if (i < DV) __stcg(dst + s * DV + i, acc[s][q]);
+              }
+          }
+#pragma unroll
+          for (int s = 0; s < NR; ++s)
+#pragma unroll
+            for (int q = 0; q < NV; ++q) acc[s][q] = f4zero();
+          started_in_tile = false;
+          has_first = false;
+        }
+        e0 = e1;
+      }
+    }
+  }
+}
+
+template <class Pol, int TC>
+__global__ void __launch_bounds__(FR_THREADS)
+seg_tile_combine_kernel(const SegCommon c, const Pol pol) {
+  constexpr int NR = Pol::NR, NV = Pol::NV;
+  const int DV = pol.DV();
+  const uint32_t n = c.n_dev ? min(*c.n_dev, c.n_host) : c.n_host;
+  constexpr uint32_t TL = 32u * TC;
+  const uint32_t ntiles = (n + TL - 1) / TL;
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const uint32_t nw = gridDim.x * FR_WARPS_PER_BLOCK;
+  for (uint32_t tile = gw; tile < ntiles; tile += nw) {
+    const uint32_t tbase = tile * TL, tnext = tbase + TL;
+    if (tnext >= n) continue;                               // last tile: nothing continues
+    const uint32_t lastKey = c.keys[tnext - 1];
+    if (c.keys[tnext] != lastKey) continue;                 // its last run ends here
+    // start of that run (lower bound of lastKey): this warp combines it iff the head is in this tile
+    uint32_t lo = 0, hi = tnext - 1;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (c.keys[mid] < lastKey) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t start = lo;
+    if (start < tbase) continue;                            // the run began in an earlier tile
+    // end of the run (upper bound)
+    lo = tnext; hi = n;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (c.keys[mid] == lastKey) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t tend = (lo - 1) / TL;                    // last tile holding an entry of the run
+    float4 acc[NR][NV];
+    {
+      const float4* src = c.pieces + ((size_t)tile * 2 + (start == tbase ? 0 : 1)) * NR * DV;
+#pragma unroll
+      for (int s = 0; s < NR; ++s)
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          const int i = lane + 32 * q;
+          acc[s][q] = i < DV ? __ldcg(src + s * DV + i) : f4zero();
+        }
+    }
+    constexpr int PF = 2;
+    for (uint32_t kt = tile + 1; kt <= tend; kt += PF) {
+      float4 buf[PF][NR][NV];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const float4* src = c.pieces + ((size_t)(kt + u) * 2) * NR * DV;
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const int i = lane + 32 * q;
+            buf[u][s][q] = (kt + u <= tend && i < DV) ? __ldcg(src + s * DV + i) : f4zero();
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u)      // summed in tile order: deterministic
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) acc[s][q] = add4(acc[s][q], buf[u][s][q]);
+    }
+    typename Pol::State st;
+    pol.load_state(st, lastKey, lane);
+    pol.apply(st, lastKey, acc, lane);
+  }
+}
+
+template <class Pol, int TC>
+static void launch_seg_tiled(const SegCommon& c, const Pol& pol, int DV, bool needs_cat, const Launch& l) {
+  const uint32_t ntiles = (c.n_host + 32 * TC - 1) / (32 * TC);
+  if (ntiles == 0) return;
+  int grid = (int)((ntiles + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
+  const size_t smem = needs_cat ? (size_t)4 * DV * sizeof(float4) : 0;
+  const int cap = l.sm_count * 16;
+  if (grid > cap) grid = cap;
+  seg_tile_kernel<Pol, TC><<<grid, FR_THREADS, smem, l.st>>>(c, pol);
+  if (l.mid) cudaEventRecord(l.mid, l.st);
+  seg_tile_combine_kernel<Pol, TC><<<grid, FR_THREADS, 0, l.st>>>(c, pol);
+  g_launches += 2;
+}
+
 template <class Pol>
 static void launch_seg(const SegCommon& c, const Pol& pol, int DV, bool needs_cat, const Launch& l) {
   const uint32_t nchunks = (c.n_host + 31) / 32;
@@ -518,8 +713,9 @@ void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, f
   else { ItemGradPol<2> pol{{p}, gbuf}; launch_seg(c, pol, p.mc.DV, false, l); }
 }
 void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, const Launch& l) {
-  if (NV == 1) { LabelPol<1> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
-  else { LabelPol<2> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
+  // <= ~100 labels, runs of thousands of entries: 8 chunks per warp-tile
+  if (NV == 1) { LabelPol<1> pol{p}; launch_seg_tiled<LabelPol<1>, 8>(c, pol, p.mc.DV, true, l); }
+  else { LabelPol<2> pol{p}; launch_seg_tiled<LabelPol<2>, 8>(c, pol, p.mc.DV, true, l); }
 }
 
 // ---- lazy Adam: the batch's unique recipe rows are brought to step-1 before anything

@@ -211,6 +211,9 @@ class Engine:
 
     def read_scalars(self):
         v = self.out.cpu().numpy()       # synchronises
+        if v[L.FR_OUT_OVERFLOW] == 2:
+            raise L.FoodRecError("row-sharded step: a rank needed more distinct recipes from one owner than "
+                                 "fr_shard.cap; raise ShardedEngine(cap=...)")
         if v[L.FR_OUT_OVERFLOW] != 0:
             raise L.FoodRecError(f"label feed has {int(v[L.FR_OUT_LABEL_ENTRIES])} non-zeros > "
                                  f"max_label_entries={self.max_label_entries}; General_Memory write truncated")

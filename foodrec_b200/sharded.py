@@ -79,8 +79,12 @@ class ShardedEngine:
                         max_label_entries=max_label_entries)
         e = self.e
         self.device = e.device
-        if cap is None:      # unique recipes per (source, owner): generous, checked on device
-            cap = min(max_rows, e.I) if world == 1 else min(max_rows, e.I, int(1.5 * max_rows / world) + 1024)
+        if cap is None:
+            # unique recipes per (source, owner).  A batch has at most max_rows distinct recipes,
+            # spread over the owners by id % W: max_rows/W on average even when every row is
+            # distinct; 10 % head-room + 256 for the imbalance.  Overflow is detected on device
+            # (FR_OUT_OVERFLOW = 2) and raised by read_scalars(), never silent.
+            cap = min(max_rows, e.I) if world == 1 else min(max_rows, e.I, int(1.1 * max_rows / world) + 256)
         self.cap = int(cap)
         n = world * self.cap
         dev = self.device
