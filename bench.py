@@ -194,8 +194,7 @@ def run_sharded(args, cfg, B):
     item_cats = synth.make_item_categories(I)
     lab = synth.make_user_label_csr(Ul, Lb, seed=synth.BASE_SEED + 200 + rank)
     eng = ShardedEngine(Hyper(learner=args.learner, lr=0.001), P, R, Cat, G, rank, world, device=dev, max_rows=2 * B,
-                        adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab,
-                        max_label_entries=2 * B * 8)
+                        adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab)
     del P
     run = DistRunner(eng)
     NB = 8
@@ -283,8 +282,8 @@ def run_ours(args, cfg, B):
     item_cats = synth.make_item_categories(I)
     lab = synth.make_user_label_csr(U, Lb)
     eng = Engine(Hyper(learner=args.learner, lr=0.001), P, R, Cat, G, device=dev, max_rows=2 * B,
-                 adam_mode=args.adam_mode, item_cats=item_cats, user_label_csr=lab,
-                 max_label_entries=2 * B * Lb if B * Lb < (1 << 26) else 2 * B * 8)
+                 adam_mode=args.adam_mode, item_cats=item_cats, user_label_csr=lab)
+    # (label-entry capacity defaults to rows x max labels per user = 2B x 3: sized to the data)
     del P
     NB = 8
     host = make_batches(cfg, B, NB, 1000 + 100 * rank, item_cats, lab, dense=True)

@@ -45,7 +45,9 @@ radix_hist_kernel(const PassJobs jobs) {
   if (J.bits == 0) return;
   const uint32_t n = resolve_n(J.n_dev, J.n_host);
   const uint32_t bins = 1u << J.bits, mask = bins - 1u;
-  for (uint32_t tile = blockIdx.x; tile < J.ntiles; tile += gridDim.x) {
+  // fused offsets only ever read the tiles that hold keys; the separate scan reads them all
+  const uint32_t nt = J.fused ? min(J.ntiles, (n + SORT_TILE - 1) / SORT_TILE) : J.ntiles;
+  for (uint32_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
     for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) hist[b] = 0;
     __syncthreads();
     const uint32_t base = tile * SORT_TILE;
@@ -105,7 +107,8 @@ radix_scatter_kernel(const PassJobs jobs) {
           const uint32_t b = b0 + q;
           if (b < bins) {
             const uint32_t* hrow = J.tile_hist + (size_t)b * J.ntiles;
-            for (uint32_t t = 0; t < J.ntiles; ++t) {
+            const uint32_t nt_act = min(J.ntiles, (n + SORT_TILE - 1) / SORT_TILE);
+            for (uint32_t t = 0; t < nt_act; ++t) {
               const uint32_t c = hrow[t];
               tot[q] += c;
               if (t < tile) pre[q] += c;
