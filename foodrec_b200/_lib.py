@@ -49,6 +49,10 @@ class fr_batch(C.Structure):
                 ("labels", C.c_void_p), ("write_sign", C.c_void_p), ("user_labels", C.c_void_p)]
 
 
+class fr_catalog_opts(C.Structure):
+    _fields_ = [("cta_group", C.c_int32), ("max_pass_rows", C.c_int32), ("splits", C.c_int32)]
+
+
 class fr_shard(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("cap", C.c_int32),
                 ("items_per_rank", C.c_int32), ("global_batch", C.c_int32)]
@@ -72,6 +76,13 @@ _PROTOS = {
     "fr_eval_sampled_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fr_catalog_prepare": (C.c_int, [C.c_void_p, C.POINTER(fr_catalog_opts), C.c_void_p]),
+    "fr_catalog_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fr_catalog_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fr_catalog_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
+    "fr_catalog_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "fr_shard_packed_len": (C.c_int64, [C.c_void_p]),
     "fr_shard_plan": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.POINTER(fr_shard), C.c_void_p, C.c_void_p]),
     "fr_shard_serve": (C.c_int, [C.c_void_p, C.POINTER(fr_shard), C.c_void_p, C.c_void_p, C.c_void_p]),

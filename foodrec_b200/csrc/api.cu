@@ -82,6 +82,7 @@ extern "C" int fr_timing_read(fr_handle h, double* ms_sum, int64_t* n_steps, int
 extern "C" int fr_destroy(fr_handle h) {
   if (!h) return FR_OK;
   for (auto& ts : h->tsets) for (auto& e : ts.ev) cudaEventDestroy(e);
+  catalog_free(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->stage) cudaFree(h->stage);
   if (h->pieces_personal) cudaFree(h->pieces_personal);

@@ -1,0 +1,693 @@
+// Full-catalog top-K: index build (recipes grouped by category mask, bf16 B operand), per-pass
+// user operand, exact fp64 re-ranking of the GEMM filter's survivors, exact fallback, cross-shard
+// merge, and the fr_catalog_* C ABI.  The tcgen05 kernel itself is in catalog_gemm.cu; the maths
+// and the error bound are stated in catalog.cuh.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <array>
+#include <vector>
+
+#include "catalog.cuh"
+#include "ctx.h"
+
+namespace fr {
+
+struct CatalogWs {
+  bool prepared = false;
+  int cta_group = 1, I = 0, KP = 0, k_blocks = 0, n_tiles = 0, present = 0, n_valid_items = 0;
+  int max_pass_rows = 0, force_splits = 0;
+  // index (built by fr_catalog_prepare)
+  uint32_t* keys = nullptr; SortBufs sortM; int32_t* gs_dev = nullptr;
+  __nv_bfloat16* Bq = nullptr; int32_t *row_item = nullptr, *tile_group = nullptr, *tile_valid = nullptr, *tile_pos = nullptr;
+  float* rmax = nullptr;
+  int tiles_cap = 0;
+  CUtensorMap tmB;
+  // per-pass workspace
+  int mp_cap = 0;
+  __nv_bfloat16* A = nullptr; float *bias = nullptr, *margin2 = nullptr, *cand_sc = nullptr;
+  int32_t *cand_row = nullptr, *cand_cnt = nullptr, *ovf = nullptr, *ovf_list = nullptr, *ovf_count = nullptr;
+  double* scratch = nullptr; int exact_blocks = 0;
+  // timing
+  std::vector<std::array<cudaEvent_t, 5>> evs; size_t ev_used = 0;
+  double t_sum[4] = {0, 0, 0, 0}; int64_t t_passes = 0;
+};
+
+// ------------------------------------------------------------------ index build
+__global__ void cat_mask_kernel(const float4* __restrict__ item_cats, int I, uint32_t* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= I) return;
+  const float4 m = __ldg(item_cats + i);
+  keys[i] = (m.x != 0.f ? 1u : 0u) | (m.y != 0.f ? 2u : 0u) | (m.z != 0.f ? 4u : 0u) | (m.w != 0.f ? 8u : 0u);
+}
+
+__global__ void cat_group_bounds_kernel(const uint32_t* __restrict__ sorted_keys, int I, int32_t* __restrict__ gs) {
+  const uint32_t g = threadIdx.x;     // 0..16: first sorted position with key >= g
+  if (g > 16) return;
+  int lo = 0, hi = I;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_keys[mid] < g) lo = mid + 1; else hi = mid; }
+  gs[g] = lo;
+}
+
+// one warp per padded row: B[row] = bf16(R[item]) (zero rows pad a group's last tile)
+__global__ void __launch_bounds__(FR_THREADS)
+cat_pack_items_kernel(const float4* __restrict__ R, int DV, int KP, const uint32_t* __restrict__ sorted_idx,
+                      const int32_t* __restrict__ tile_valid, const int32_t* __restrict__ tile_pos, int n_rows,
+                      __nv_bfloat16* __restrict__ Bq, int32_t* __restrict__ row_item, float* __restrict__ rmax) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int tile = r / CAT_BN, j = r % CAT_BN;
+  const bool valid = j < __ldg(tile_valid + tile);
+  const int item = valid ? (int)__ldg(sorted_idx + __ldg(tile_pos + tile) + j) : -1;
+  if (lane == 0) row_item[r] = item;
+  float nrm = 0.f;
+  uint2* dst = reinterpret_cast<uint2*>(Bq + (size_t)r * KP);
+  for (int i = lane; i < KP / 4; i += 32) {
+    float4 v = f4zero();
+    if (valid && i < DV) v = __ldg(R + (size_t)item * DV + i);
+    nrm += dot4(v, v);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    dst[i] = o;
+  }
+  nrm = warp_sum(nrm);
+  if (lane == 0 && valid) atomicMax(reinterpret_cast<int*>(rmax), __float_as_int(sqrtf(nrm) * 1.000001f));
+}
+
+// ------------------------------------------------------------------ per-pass user operand
+struct UserSrc {
+  const float4* P;        // table or dense query rows
+  const int32_t* uidx;    // nullable: row -> user id
+  int row0;               // first query row of this pass
+};
+__device__ __forceinline__ const float4* user_row(const UserSrc& s, int j, int DV) {
+  const size_t u = s.uidx ? (size_t)__ldg(s.uidx + s.row0 + j) : (size_t)(s.row0 + j);
+  return s.P + u * 5 * DV;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(FR_THREADS)
+cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restrict__ Cat, int DV, int KP, float a,
+                      float oma, int present, const float* __restrict__ rmax_p, float cfac,
+                      __nv_bfloat16* __restrict__ A, float* __restrict__ bias, float* __restrict__ margin2) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (j >= m_pad) return;
+  const bool valid = j < n_rows;
+  float4 pr[5][NV];
+  double h[4] = {0, 0, 0, 0};
+  if (valid) {
+    const float4* prow = user_row(src, j, DV);
+#pragma unroll
+    for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], prow + (size_t)s * DV, DV, lane);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < DV) {
+          const float4 cv = __ldg(Cat + c * DV + i);
+          acc += (double)pr[0][k].x * cv.x + (double)pr[0][k].y * cv.y + (double)pr[0][k].z * cv.z + (double)pr[0][k].w * cv.w;
+        }
+      }
+      h[c] = warp_sum_d(acc);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) pr[s][k] = f4zero();
+  }
+  const float rmax = __ldg(rmax_p);
+  float emax = 0.f;
+  for (int g = 1; g < 16; ++g) {
+    if (!((present >> g) & 1)) continue;
+    const float inv_n = 1.0f / (float)__popc(g);
+    float nrm = 0.f;
+    uint2* dst = reinterpret_cast<uint2*>(A + ((size_t)g * m_pad + j) * KP);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < KP / 4) {
+        float4 z = f4zero();
+        if (i < DV) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if ((g >> c) & 1) z = add4(z, pr[1 + c][k]);
+          z = scale4(oma * inv_n, z);
+        }
+        nrm += dot4(z, z);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(z.x, z.y), hi = __floats2bfloat162_rn(z.z, z.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        dst[i] = o;
+      }
+    }
+    nrm = warp_sum(nrm);
+    double hs = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if ((g >> c) & 1) hs += h[c];
+    const float b = (float)((double)a * (hs / (double)__popc(g)));
+    const float ar = sqrtf(nrm) * rmax;
+    const float E = cfac * ar + 4.76837158e-7f * (fabsf(b) + ar);     // 2^-21: fp32 rounding of bias and of v + bias
+    emax = fmaxf(emax, E);
+    if (lane == 0) bias[(size_t)g * m_pad + j] = b;
+  }
+  if (lane == 0) margin2[j] = 2.0f * emax * 1.00001f;
+}
+
+// ------------------------------------------------------------------ exact scoring + ranking helpers
+// inference (Model_Recommender.py:56-97) for one (user, recipe) in fp64 from the fp32 tables.
+// sP = the user's [5,D] row, sH[c] = <P[u,0], Cat[c]>.  All lanes return the score.
+__device__ __forceinline__ double exact_score_warp(const float* sP, const double* sH, const float* __restrict__ Rrow,
+                                                   const float4 m, int D, int lane, double a, double oma) {
+  const bool m0 = m.x != 0.f, m1 = m.y != 0.f, m2 = m.z != 0.f, m3 = m.w != 0.f;
+  const int n = (int)m0 + (int)m1 + (int)m2 + (int)m3;
+  double acc = 0.0;
+  for (int d = lane; d < D; d += 32) {
+    double z = 0.0;
+    if (m0) z += (double)sP[D + d];
+    if (m1) z += (double)sP[2 * D + d];
+    if (m2) z += (double)sP[3 * D + d];
+    if (m3) z += (double)sP[4 * D + d];
+    acc = fma(z, (double)__ldg(Rrow + d), acc);
+  }
+  acc = warp_sum_d(acc);
+  double hs = 0.0;
+  if (m0) hs += sH[0];
+  if (m1) hs += sH[1];
+  if (m2) hs += sH[2];
+  if (m3) hs += sH[3];
+  if (n == 0) return -CUDART_INF;
+  return a * (hs / n) + oma * (acc / n);
+}
+
+__device__ __forceinline__ void load_user_exact(const float4* prow, const float* __restrict__ Cat, int D, float* sP,
+                                                double* sH, int tid, int nthreads) {
+  const float* pf = reinterpret_cast<const float*>(prow);
+  for (int i = tid; i < 5 * D; i += nthreads) sP[i] = __ldg(pf + i);
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < 4) {
+    double acc = 0.0;
+    for (int d = lane; d < D; d += 32) acc = fma((double)sP[d], (double)__ldg(Cat + warp * D + d), acc);
+    acc = warp_sum_d(acc);
+    if (lane == 0) sH[warp] = acc;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ bool ranks_before(double sa, int ia, double sb, int ib) {
+  return sa > sb || (sa == sb && ia < ib);      // score desc, id asc
+}
+__device__ void bitonic_rank_sort(double* s, int* id, int n2, int tid, int nthreads) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n2; i += nthreads) {
+        const int x = i ^ j;
+        if (x > i) {
+          const bool first = ranks_before(s[i], id[i], s[x], id[x]);
+          const bool up = (i & k) == 0;
+          if (up ? (!first && ranks_before(s[x], id[x], s[i], id[i])) : first) {
+            const double ts = s[i]; s[i] = s[x]; s[x] = ts;
+            const int ti = id[i]; id[i] = id[x]; id[x] = ti;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct FinParams {
+  UserSrc src;
+  const float* R; const float* Cat; const float4* item_cats; const int32_t* row_item;
+  int D, n_rows, m_pad, n_split, K;
+  double a, oma;
+  const float* margin2; const float* cand_sc; const int32_t* cand_row; const int32_t* cand_cnt;
+  const int32_t* ovf; int32_t* ovf_list; int32_t* ovf_count;
+  int id_mul, id_add;
+  int32_t* out_ids; double* out_scores;     // [n_users, K]
+};
+
+constexpr int FIN_THREADS = 128;
+
+__global__ void __launch_bounds__(FIN_THREADS) cat_finalize_kernel(const FinParams f) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  double* es = reinterpret_cast<double*>(fsm);                 // [FCAP]
+  double* sH = es + CAT_FCAP;                                  // [4]
+  int* eid = reinterpret_cast<int*>(sH + 4);                   // [FCAP]
+  int* frow = eid + CAT_FCAP;                                  // [FCAP]
+  float* sP = reinterpret_cast<float*>(frow + CAT_FCAP);       // [5*D]
+  float* csc = sP + 5 * f.D;                                   // [n_split*CAP]
+  int* crow = reinterpret_cast<int*>(csc + f.n_split * CAT_CAP);
+  __shared__ int s_red[FIN_THREADS / 32];
+  __shared__ int s_nF;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  bool overflow = f.ovf[row] != 0;
+  int n_tot = 0;
+  if (!overflow) {
+    for (int sp = 0; sp < f.n_split; ++sp) {
+      const size_t lr = (size_t)sp * f.m_pad + row;
+      const int c = f.cand_cnt[lr];
+      for (int e = tid; e < c; e += FIN_THREADS) {
+        csc[n_tot + e] = __ldcg(f.cand_sc + lr * CAT_CAP + e);
+        crow[n_tot + e] = __ldcg(f.cand_row + lr * CAT_CAP + e);
+      }
+      n_tot += c;
+    }
+    if (tid == 0) s_nF = 0;
+    __syncthreads();
+    // tau = K-th largest approximate score over the union of the split lists
+    float lo = -__int_as_float(0x7f800000);
+    if (n_tot > f.K) {
+      uint32_t res = 0;
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t trial = res | (1u << bit);
+        int c = 0;
+        for (int e = tid; e < n_tot; e += FIN_THREADS) c += (fkey(csc[e]) >= trial);
+        c = __reduce_add_sync(FR_FULL, c);
+        if (lane == 0) s_red[warp] = c;
+        __syncthreads();
+        c = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        __syncthreads();
+        if (c >= f.K) res = trial;
+      }
+      lo = __fsub_rd(funkey(res), f.margin2[row]);
+    }
+    for (int e = tid; e < n_tot; e += FIN_THREADS) {
+      if (csc[e] >= lo) {
+        const int pos = atomicAdd(&s_nF, 1);
+        if (pos < CAT_FCAP) frow[pos] = crow[e];
+      }
+    }
+    __syncthreads();
+    if (s_nF > CAT_FCAP) overflow = true;
+  }
+  if (overflow) {                       // exact fallback takes this row
+    if (tid == 0) { const int slot = atomicAdd(f.ovf_count, 1); f.ovf_list[slot] = row; }
+    return;
+  }
+  const int nF = s_nF;
+  load_user_exact(user_row(f.src, row, f.D / 4), f.Cat, f.D, sP, sH, tid, FIN_THREADS);
+  for (int i = warp; i < nF; i += FIN_THREADS / 32) {
+    const int item = __ldg(f.row_item + frow[i]);
+    const float4 m = __ldg(f.item_cats + item);
+    const double s = exact_score_warp(sP, sH, f.R + (size_t)item * f.D, m, f.D, lane, f.a, f.oma);
+    if (lane == 0) { es[i] = s; eid[i] = item; }
+  }
+  int n2 = 2;
+  while (n2 < nF) n2 <<= 1;
+  for (int i = nF + tid; i < n2; i += FIN_THREADS) { es[i] = -CUDART_INF; eid[i] = 0x7fffffff; }
+  __syncthreads();
+  bitonic_rank_sort(es, eid, n2, tid, FIN_THREADS);
+  const size_t ob = (size_t)(f.src.row0 + row) * f.K;
+  for (int k = tid; k < f.K; k += FIN_THREADS) {
+    const bool has = k < nF && eid[k] != 0x7fffffff && es[k] > -CUDART_INF;
+    f.out_ids[ob + k] = has ? eid[k] * f.id_mul + f.id_add : -1;
+    if (f.out_scores) f.out_scores[ob + k] = has ? es[k] : -CUDART_INF;
+  }
+}
+
+// ------------------------------------------------------------------ exact fallback (rows the filter gave up on)
+__device__ __forceinline__ unsigned long long dkey(double d) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+
+constexpr int EX_THREADS = 1024;
+
+__global__ void __launch_bounds__(EX_THREADS) cat_exact_kernel(const FinParams f, int I, double* __restrict__ scratch) {
+  __shared__ float sP[5 * 256];
+  __shared__ double sH[4];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_need, s_ngt, wcnt[EX_THREADS / 32];
+  __shared__ double ss[CAT_MAXK];
+  __shared__ int sid[CAT_MAXK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* sc = scratch + (size_t)blockIdx.x * I;
+  const int n_ov = min(*f.ovf_count, f.m_pad);
+  const int Keff = min(f.K, I);
+  for (int slot = blockIdx.x; slot < n_ov; slot += gridDim.x) {
+    const int row = f.ovf_list[slot];
+    __syncthreads();
+    load_user_exact(user_row(f.src, row, f.D / 4), f.Cat, f.D, sP, sH, tid, EX_THREADS);
+    for (int item = warp; item < I; item += EX_THREADS / 32) {
+      const double s = exact_score_warp(sP, sH, f.R + (size_t)item * f.D, __ldg(f.item_cats + item), f.D, lane, f.a, f.oma);
+      if (lane == 0) sc[item] = s;
+    }
+    __syncthreads();
+    // radix select of the Keff-th largest 64-bit key
+    unsigned long long prefix = 0;
+    int need = Keff;
+    for (int pass = 7; pass >= 0; --pass) {
+      for (int b = tid; b < 256; b += EX_THREADS) hist[b] = 0;
+      __syncthreads();
+      for (int i = tid; i < I; i += EX_THREADS) {
+        const unsigned long long k = dkey(sc[i]);
+        if (pass == 7 || (k >> (8 * (pass + 1))) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 255ULL], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int acc = 0, b = 255;
+        for (; b > 0; --b) { if (acc + (int)hist[b] >= need) break; acc += (int)hist[b]; }
+        s_prefix = (prefix << 8) | (unsigned long long)b;
+        s_need = need - acc;
+      }
+      __syncthreads();
+      prefix = s_prefix; need = s_need;
+      __syncthreads();
+    }
+    const unsigned long long kth = prefix;      // `need` recipes with key == kth complete the top-K: lowest ids first
+    if (tid == 0) s_ngt = 0;
+    __syncthreads();
+    for (int i = tid; i < I; i += EX_THREADS)
+      if (dkey(sc[i]) > kth) { const int pos = atomicAdd(&s_ngt, 1); if (pos < CAT_MAXK) { ss[pos] = sc[i]; sid[pos] = i; } }
+    __syncthreads();
+    const int ngt = s_ngt;
+    int base = 0;
+    for (int start = 0; start < I && base < need; start += EX_THREADS) {
+      const int i = start + tid;
+      const bool flag = i < I && dkey(sc[i]) == kth;
+      const uint32_t bal = __ballot_sync(FR_FULL, flag);
+      if (lane == 0) wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int wp = 0, total = 0;
+      for (int w = 0; w < EX_THREADS / 32; ++w) { const int c = wcnt[w]; if (w < warp) wp += c; total += c; }
+      const int pos = base + wp + __popc(bal & ((1u << lane) - 1u));
+      if (flag && pos < need && ngt + pos < CAT_MAXK) { ss[ngt + pos] = sc[i]; sid[ngt + pos] = i; }
+      base += total;
+      __syncthreads();
+    }
+    int n2 = 2;
+    while (n2 < Keff) n2 <<= 1;
+    for (int i = Keff + tid; i < n2; i += EX_THREADS) { ss[i] = -CUDART_INF; sid[i] = 0x7fffffff; }
+    __syncthreads();
+    bitonic_rank_sort(ss, sid, n2, tid, EX_THREADS);
+    const size_t ob = (size_t)(f.src.row0 + row) * f.K;
+    for (int k = tid; k < f.K; k += EX_THREADS) {
+      const bool has = k < Keff && ss[k] > -CUDART_INF;
+      f.out_ids[ob + k] = has ? sid[k] * f.id_mul + f.id_add : -1;
+      if (f.out_scores) f.out_scores[ob + k] = has ? ss[k] : -CUDART_INF;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ cross-shard merge
+__global__ void __launch_bounds__(FIN_THREADS)
+cat_merge_kernel(const int32_t* __restrict__ ids, const double* __restrict__ scores, int n_lists, int n_users, int K,
+                 int32_t* __restrict__ out_ids, double* __restrict__ out_scores) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  const int n = n_lists * K;
+  int n2 = 2;
+  while (n2 < n) n2 <<= 1;
+  double* s = reinterpret_cast<double*>(msm);
+  int* id = reinterpret_cast<int*>(s + n2);
+  const int u = blockIdx.x, tid = threadIdx.x;
+  for (int e = tid; e < n2; e += FIN_THREADS) {
+    double sv = -CUDART_INF; int iv = 0x7fffffff;
+    if (e < n) {
+      const int l = e / K, k = e % K;
+      const size_t src = ((size_t)l * n_users + u) * K + k;
+      const int i0 = ids[src];
+      if (i0 >= 0) { iv = i0; sv = scores[src]; }
+    }
+    s[e] = sv; id[e] = iv;
+  }
+  __syncthreads();
+  bitonic_rank_sort(s, id, n2, tid, FIN_THREADS);
+  for (int k = tid; k < K; k += FIN_THREADS) {
+    const bool has = id[k] != 0x7fffffff;
+    out_ids[(size_t)u * K + k] = has ? id[k] : -1;
+    if (out_scores) out_scores[(size_t)u * K + k] = has ? s[k] : -CUDART_INF;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 row-major [rows, KP] -> boxes of [box_rows, 64] with the 128-byte swizzle
+static int make_tmap(fr_ctx* h, CUtensorMap* m, void* base, uint64_t rows, int KP, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(h, FR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)KP, rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)KP * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)CAT_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, FR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return FR_OK;
+}
+
+}  // namespace fr
+
+void catalog_free(fr_ctx* h) {
+  if (!h || !h->cat) return;
+  for (auto& s : h->cat->evs) for (auto& e : s) cudaEventDestroy(e);
+  delete h->cat;
+  h->cat = nullptr;
+}
+
+extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_stream s) {
+  if (!h) return FR_ERR_ARG;
+  if (!h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (!h->tab.item_cats) return fail(h, FR_ERR_STATE, "catalog scoring needs tables.item_cats (dish_to_category)");
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  cudaDeviceProp prop;
+  FR_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) return fail(h, FR_ERR_UNSUPPORTED, "catalog scoring is tcgen05 code: needs sm_100, device is sm_%d%d", prop.major, prop.minor);
+  if (!h->cat) h->cat = new CatalogWs();
+  CatalogWs& w = *h->cat;
+  const int I = h->cfg.num_items, D = h->mc.D, DV = h->mc.DV;
+  const int KP = (D + CAT_BK - 1) / CAT_BK * CAT_BK;
+  int rc;
+  if (w.I != I) {
+    if (w.I != 0) return fail(h, FR_ERR_STATE, "catalog index was built for %d recipes", w.I);
+    w.I = I; w.KP = KP; w.k_blocks = KP / CAT_BK;
+    w.tiles_cap = (I + CAT_BN - 1) / CAT_BN + 15;
+    if ((rc = dalloc(h, &w.keys, (size_t)I))) return rc;
+    if ((rc = alloc_sort(h, w.sortM, (size_t)I))) return rc;
+    if ((rc = dalloc(h, &w.gs_dev, 17))) return rc;
+    if ((rc = dalloc(h, &w.Bq, (size_t)w.tiles_cap * CAT_BN * KP))) return rc;
+    if ((rc = dalloc(h, &w.row_item, (size_t)w.tiles_cap * CAT_BN))) return rc;
+    if ((rc = dalloc(h, &w.tile_group, (size_t)w.tiles_cap))) return rc;
+    if ((rc = dalloc(h, &w.tile_valid, (size_t)w.tiles_cap))) return rc;
+    if ((rc = dalloc(h, &w.tile_pos, (size_t)w.tiles_cap))) return rc;
+    if ((rc = dalloc(h, &w.rmax, 1))) return rc;
+    FR_CUDA(h, catalog_gemm_configure());
+    FR_CUDA(h, cudaFuncSetAttribute(cat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  }
+  w.cta_group = (opts && opts->cta_group == 1) ? 1 : 2;
+  w.max_pass_rows = (opts && opts->max_pass_rows > 0) ? opts->max_pass_rows : 0;
+  w.force_splits = (opts && opts->splits > 0) ? std::min(opts->splits, CAT_SPLIT_MAX) : 0;
+
+  cat_mask_kernel<<<(I + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(h->tab.item_cats), I, w.keys);
+  ++g_launches;
+  FR_CHECK_LAUNCH(h);
+  const int r = radix_sort_pairs(w.sortM, w.keys, (uint32_t)I, nullptr, 4, st, h->sm_count);
+  cat_group_bounds_kernel<<<1, 32, 0, st>>>(w.sortM.k[r], I, w.gs_dev);
+  ++g_launches;
+  FR_CHECK_LAUNCH(h);
+  int32_t gs[17];
+  FR_CUDA(h, cudaMemcpyAsync(gs, w.gs_dev, sizeof(gs), cudaMemcpyDeviceToHost, st));
+  FR_CUDA(h, cudaStreamSynchronize(st));
+  std::vector<int32_t> tg, tv, tp;
+  w.present = 0;
+  for (int g = 1; g < 16; ++g) {
+    const int cnt = gs[g + 1] - gs[g];
+    if (cnt <= 0) continue;
+    w.present |= 1 << g;
+    for (int o = 0; o < cnt; o += CAT_BN) { tg.push_back(g); tv.push_back(std::min(CAT_BN, cnt - o)); tp.push_back(gs[g] + o); }
+  }
+  w.n_tiles = (int)tg.size();
+  w.n_valid_items = I - (gs[1] - gs[0]);
+  if (w.n_tiles > w.tiles_cap) return fail(h, FR_ERR_STATE, "catalog tile count %d exceeds capacity %d", w.n_tiles, w.tiles_cap);
+  if (w.n_tiles > 0) {
+    FR_CUDA(h, cudaMemcpyAsync(w.tile_group, tg.data(), tg.size() * 4, cudaMemcpyHostToDevice, st));
+    FR_CUDA(h, cudaMemcpyAsync(w.tile_valid, tv.data(), tv.size() * 4, cudaMemcpyHostToDevice, st));
+    FR_CUDA(h, cudaMemcpyAsync(w.tile_pos, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice, st));
+    FR_CUDA(h, cudaMemsetAsync(w.rmax, 0, 4, st));
+    const int n_rows = w.n_tiles * CAT_BN;
+    cat_pack_items_kernel<<<(n_rows + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK, FR_THREADS, 0, st>>>(
+        reinterpret_cast<const float4*>(h->tab.R), DV, KP, w.sortM.v[r], w.tile_valid, w.tile_pos, n_rows, w.Bq,
+        w.row_item, w.rmax);
+    ++g_launches;
+    FR_CHECK_LAUNCH(h);
+    FR_CUDA(h, cudaStreamSynchronize(st));     // host vectors above go out of scope
+    if ((rc = make_tmap(h, &w.tmB, w.Bq, (uint64_t)w.n_tiles * CAT_BN, KP, CAT_BN / w.cta_group))) return rc;
+  }
+  w.prepared = true;
+  return FR_OK;
+}
+
+static int catalog_ensure_pass_ws(fr_ctx* h, CatalogWs& w, int mp) {
+  if (mp <= w.mp_cap) return FR_OK;
+  if (w.mp_cap != 0) return fail(h, FR_ERR_STATE, "catalog pass workspace was sized for %d rows", w.mp_cap);
+  int rc;
+  const size_t R = (size_t)mp;
+  if ((rc = dalloc(h, &w.A, 16 * R * w.KP))) return rc;
+  if ((rc = dalloc(h, &w.bias, 16 * R))) return rc;
+  if ((rc = dalloc(h, &w.margin2, R))) return rc;
+  if ((rc = dalloc(h, &w.cand_sc, R * CAT_CAP))) return rc;
+  if ((rc = dalloc(h, &w.cand_row, R * CAT_CAP))) return rc;
+  if ((rc = dalloc(h, &w.cand_cnt, R))) return rc;
+  if ((rc = dalloc(h, &w.ovf, R))) return rc;
+  if ((rc = dalloc(h, &w.ovf_list, R))) return rc;
+  if ((rc = dalloc(h, &w.ovf_count, 1))) return rc;
+  const size_t budget = (size_t)512 << 20;
+  w.exact_blocks = (int)std::max<size_t>(2, std::min<size_t>((size_t)h->sm_count, budget / ((size_t)w.I * 8)));
+  if ((rc = dalloc(h, &w.scratch, (size_t)w.exact_blocks * w.I))) return rc;
+  w.mp_cap = mp;
+  return FR_OK;
+}
+
+extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P_rows, int32_t n_users, int32_t K,
+                               int32_t id_mul, int32_t id_add, int32_t* out_ids, double* out_scores, fr_stream s) {
+  if (!h || !out_ids || n_users < 0) return FR_ERR_ARG;
+  if (!h->cat || !h->cat->prepared) return fail(h, FR_ERR_STATE, "fr_catalog_prepare first");
+  if (K <= 0 || K > CAT_MAXK) return fail(h, FR_ERR_UNSUPPORTED, "K must be in [1,%d], got %d", CAT_MAXK, K);
+  if (n_users == 0) return FR_OK;
+  CatalogWs& w = *h->cat;
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  const int CG = w.cta_group, BMC = CAT_BM * CG;
+  const int n_clusters = std::max(1, h->sm_count / CG);
+  // rows per pass: whole waves of user blocks; small calls split the recipe sweep instead
+  const int pass_rows = w.max_pass_rows > 0 ? (w.max_pass_rows + BMC - 1) / BMC * BMC : n_clusters * BMC * 4;
+  int rc = catalog_ensure_pass_ws(h, w, std::max(pass_rows, 2 * n_clusters * BMC));
+  if (rc) return rc;
+  const int D = h->mc.D, DV = h->mc.DV;
+  const float cfac = 0.0078278f /* 2u + u^2, u = 2^-8 */ + (float)w.KP * 9.54e-7f /* fp32 accumulation, 4K*2^-22 */;
+  const bool timing = h->timing;
+
+  for (int row0 = 0; row0 < n_users; row0 += pass_rows) {
+    const int rows = std::min(pass_rows, n_users - row0);
+    const int m_blocks = (rows + BMC - 1) / BMC, m_pad = m_blocks * BMC;
+    int n_split = w.force_splits ? w.force_splits : (n_clusters + m_blocks - 1) / m_blocks;
+    n_split = std::max(1, std::min({n_split, CAT_SPLIT_MAX, std::max(1, w.n_tiles)}));
+    while (n_split > 1 && (size_t)n_split * m_pad > (size_t)w.mp_cap) --n_split;
+    const int tps = std::max(1, (w.n_tiles + n_split - 1) / n_split);
+    UserSrc src{reinterpret_cast<const float4*>(P_rows ? P_rows : h->tab.P), P_rows ? nullptr : users, row0};
+
+    std::array<cudaEvent_t, 5>* ev = nullptr;
+    if (timing) {
+      if (w.ev_used == w.evs.size()) {
+        w.evs.emplace_back();
+        for (auto& e : w.evs.back()) FR_CUDA(h, cudaEventCreate(&e));
+      }
+      ev = &w.evs[w.ev_used++];
+      FR_CUDA(h, cudaEventRecord((*ev)[0], st));
+    }
+    const int pgrid = (m_pad + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
+    if (h->NV == 1)
+      cat_pack_users_kernel<1><<<pgrid, FR_THREADS, 0, st>>>(src, rows, m_pad, reinterpret_cast<const float4*>(h->tab.Cat), DV,
+                                                            w.KP, h->mc.a, h->mc.oma, w.present, w.rmax, cfac, w.A, w.bias, w.margin2);
+    else
+      cat_pack_users_kernel<2><<<pgrid, FR_THREADS, 0, st>>>(src, rows, m_pad, reinterpret_cast<const float4*>(h->tab.Cat), DV,
+                                                            w.KP, h->mc.a, h->mc.oma, w.present, w.rmax, cfac, w.A, w.bias, w.margin2);
+    ++g_launches;
+    FR_CHECK_LAUNCH(h);
+    FR_CUDA(h, cudaMemsetAsync(w.cand_cnt, 0, (size_t)n_split * m_pad * 4, st));
+    FR_CUDA(h, cudaMemsetAsync(w.ovf, 0, (size_t)m_pad * 4, st));
+    FR_CUDA(h, cudaMemsetAsync(w.ovf_count, 0, 4, st));
+    if (ev) FR_CUDA(h, cudaEventRecord((*ev)[1], st));
+
+    if (w.n_tiles > 0) {
+      CUtensorMap tmA;
+      if ((rc = make_tmap(h, &tmA, w.A, (uint64_t)16 * m_pad, w.KP, CAT_BM))) return rc;
+      CatGemmParams p{};
+      p.m_blocks = m_blocks; p.m_pad = m_pad; p.n_rows = rows; p.n_split = n_split; p.tiles_per_split = tps;
+      p.n_tiles = w.n_tiles; p.k_blocks = w.k_blocks; p.K = K;
+      p.tile_group = w.tile_group; p.tile_valid = w.tile_valid; p.bias = w.bias; p.margin2 = w.margin2;
+      p.cand_sc = w.cand_sc; p.cand_row = w.cand_row; p.cand_cnt = w.cand_cnt; p.ovf = w.ovf;
+      launch_catalog_gemm(CG, h->sm_count, tmA, w.tmB, p, st);
+      FR_CHECK_LAUNCH(h);
+    }
+    if (ev) FR_CUDA(h, cudaEventRecord((*ev)[2], st));
+
+    FinParams f{};
+    f.src = src; f.R = h->tab.R; f.Cat = h->tab.Cat; f.item_cats = reinterpret_cast<const float4*>(h->tab.item_cats);
+    f.row_item = w.row_item; f.D = D; f.n_rows = rows; f.m_pad = m_pad; f.n_split = n_split; f.K = K;
+    f.a = (double)h->mc.a; f.oma = (double)h->mc.oma;
+    f.margin2 = w.margin2; f.cand_sc = w.cand_sc; f.cand_row = w.cand_row; f.cand_cnt = w.cand_cnt;
+    f.ovf = w.ovf; f.ovf_list = w.ovf_list; f.ovf_count = w.ovf_count;
+    f.id_mul = id_mul; f.id_add = id_add; f.out_ids = out_ids; f.out_scores = out_scores;
+    const size_t fsm = (size_t)CAT_FCAP * (8 + 4 + 4) + 32 + (size_t)5 * D * 4 + (size_t)n_split * CAT_CAP * 8;
+    cat_finalize_kernel<<<rows, FIN_THREADS, fsm, st>>>(f);
+    ++g_launches;
+    FR_CHECK_LAUNCH(h);
+    if (ev) FR_CUDA(h, cudaEventRecord((*ev)[3], st));
+    cat_exact_kernel<<<w.exact_blocks, EX_THREADS, 0, st>>>(f, w.I, w.scratch);
+    ++g_launches;
+    FR_CHECK_LAUNCH(h);
+    if (ev) FR_CUDA(h, cudaEventRecord((*ev)[4], st));
+  }
+  return FR_OK;
+}
+
+extern "C" int fr_catalog_merge(fr_handle h, const int32_t* ids, const double* scores, int32_t n_lists,
+                                int32_t n_users, int32_t K, int32_t* out_ids, double* out_scores, fr_stream s) {
+  if (!h || !ids || !scores || !out_ids || n_lists <= 0 || n_users < 0 || K <= 0) return FR_ERR_ARG;
+  if ((int64_t)n_lists * K > 4096) return fail(h, FR_ERR_UNSUPPORTED, "n_lists*K must be <= 4096");
+  if (n_users == 0) return FR_OK;
+  int n2 = 2;
+  while (n2 < n_lists * K) n2 <<= 1;
+  static bool configured = false;
+  if (!configured) {
+    FR_CUDA(h, cudaFuncSetAttribute(cat_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));
+    configured = true;
+  }
+  cat_merge_kernel<<<n_users, FIN_THREADS, (size_t)n2 * 12, static_cast<cudaStream_t>(s)>>>(ids, scores, n_lists, n_users, K,
+                                                                                         out_ids, out_scores);
+  ++g_launches;
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+extern "C" int fr_catalog_timing_read(fr_handle h, double* ms_sum, int64_t* n_passes, int32_t reset) {
+  if (!h || !ms_sum) return FR_ERR_ARG;
+  if (!h->cat) return fail(h, FR_ERR_STATE, "fr_catalog_prepare first");
+  CatalogWs& w = *h->cat;
+  for (size_t i = 0; i < w.ev_used; ++i) {
+    auto& ev = w.evs[i];
+    cudaEventSynchronize(ev[4]);
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) w.t_sum[k] += ms;
+    }
+    w.t_passes += 1;
+  }
+  w.ev_used = 0;
+  for (int k = 0; k < 4; ++k) ms_sum[k] = w.t_sum[k];
+  if (n_passes) *n_passes = w.t_passes;
+  if (reset) { for (double& t : w.t_sum) t = 0; w.t_passes = 0; }
+  return FR_OK;
+}
+
+extern "C" int fr_catalog_info(fr_handle h, int32_t* out /* [8] */) {
+  if (!h || !out) return FR_ERR_ARG;
+  if (!h->cat || !h->cat->prepared) return fail(h, FR_ERR_STATE, "fr_catalog_prepare first");
+  const CatalogWs& w = *h->cat;
+  out[0] = w.cta_group; out[1] = w.KP; out[2] = w.n_tiles; out[3] = w.present; out[4] = w.n_valid_items;
+  out[5] = CAT_BN; out[6] = CAT_CAP; out[7] = w.exact_blocks;
+  return FR_OK;
+}

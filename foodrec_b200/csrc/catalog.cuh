@@ -1,0 +1,69 @@
+// Full-catalog top-K (extension of evaluate.py: inference :56-97 over EVERY recipe).
+// Shared declarations of catalog.cu / catalog_gemm.cu.
+//
+// score(u,i) = a * sum_c w_ic <P[u,0],Cat[c]>  +  (1-a) * sum_c w_ic <P[u,1+c], R[i]>
+//            =        bias[u, mask_i]          +  < A[mask_i][u] , R[i] >
+// with mask_i the recipe's category set (<= 15 non-empty masks), w_ic = m_ic / n_i,
+//   A[g][u] = (1-a)/|g| * sum_{c in g} P[u,1+c]        (one D-vector per (mask, user))
+//   bias[g][u] = a/|g| * sum_{c in g} <P[u,0],Cat[c]>  (fp64 -> fp32)
+// Recipes are grouped by mask (stable sort, so ids ascend inside a group) and padded to
+// whole 256-row tiles; a tile therefore has ONE mask, the dense contraction is
+// [users x D] x [D x recipes] in bf16 on tcgen05 with fp32 accumulators in TMEM, and the
+// category term is a per-(row, tile) constant the epilogue folds into its threshold.
+//
+// The bf16 GEMM is a FILTER with a proven error bound, not the answer:
+//   |s_hat - s| <= E[u] = cfac * |A[g][u]| * max_i |R[i]|  (+ fp32 rounding of the bias add)
+// the epilogue keeps every recipe with s_hat >= tau_run - 2E (tau_run = K-th best s_hat so far,
+// monotone), which provably contains the exact top-K; the survivors (K + a few dozen) are
+// re-scored in fp64 from the fp32 tables and ranked by (score desc, id asc).  Rows whose
+// candidate list overflows (massive ties) fall back to an exact full scan.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fr {
+
+constexpr int CAT_BM = 128;        // user rows per CTA (TMEM lanes)
+constexpr int CAT_BN = 256;        // recipes per tile (TMEM columns per accumulator stage)
+constexpr int CAT_BK = 64;         // bf16 elements per 128-byte swizzle atom
+constexpr int CAT_KB_MAX = 4;      // D <= 256
+constexpr int CAT_CAP = 512;       // candidate slots per (split, user)
+constexpr int CAT_FCAP = 1024;     // survivors re-scored per user
+constexpr int CAT_MAXK = 256;
+constexpr int CAT_SPLIT_MAX = 16;
+constexpr int CAT_THREADS = 256;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int CAT_A_BLK = CAT_BM * CAT_BK * 2;                // 16 KB: one k-block of A
+constexpr int CAT_B_TOTAL = 128 * 1024;                       // all B stages
+constexpr int CAT_SMEM = CAT_KB_MAX * CAT_A_BLK + CAT_B_TOTAL + 1024 /*barriers*/ + 1024 /*align*/;
+
+struct CatGemmParams {
+  int m_blocks;          // user blocks of CAT_BM * CG rows in this pass
+  int m_pad;             // m_blocks * CAT_BM * CG
+  int n_rows;            // valid user rows in this pass
+  int n_split, tiles_per_split, n_tiles, k_blocks, K;
+  const int32_t* tile_group;   // [n_tiles] mask of each tile
+  const int32_t* tile_valid;   // [n_tiles] recipes in the tile (256 except a group's last tile)
+  const float* bias;           // [16][m_pad]
+  const float* margin2;        // [m_pad]  2E
+  float* cand_sc;              // [n_split*m_pad][CAT_CAP] approx total score
+  int32_t* cand_row;           // same shape: padded recipe row
+  int32_t* cand_cnt;           // [n_split*m_pad]
+  int32_t* ovf;                // [m_pad] 1 = candidate list overflowed
+};
+
+void launch_catalog_gemm(int cta_group, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const CatGemmParams& p, cudaStream_t st);
+cudaError_t catalog_gemm_configure();   // opt-in dynamic shared memory for both variants
+
+// order-preserving float <-> uint32 key
+__device__ __forceinline__ uint32_t fkey(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float funkey(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+}  // namespace fr

@@ -9,6 +9,7 @@
 #include "train.cuh"
 
 using namespace fr;
+namespace fr { struct CatalogWs; }
 
 struct fr_ctx {
   fr_config cfg{};
@@ -50,6 +51,7 @@ struct fr_ctx {
     int ru = 0, ri = 0, rs = 0;            // which sort buffer holds each result
     int mode = 0, B = 0, S = 0, group = 1;
   } sh;
+  fr::CatalogWs* cat = nullptr;     // full-catalog top-K (catalog.cu): index + pass workspace
   // staging for fr_train_step_host
   void* stage = nullptr; size_t stage_bytes = 0;
   // per-phase timing (fr_timing_*)
@@ -114,6 +116,7 @@ static inline int alloc_sort(fr_ctx* h, SortBufs& s, size_t cap) {
 }
 
 
+void catalog_free(fr_ctx* h);
 int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st);
 float adam_lr_t(const fr_ctx* h);
 fr::OptConsts make_oc(const fr_ctx* h, int64_t step);

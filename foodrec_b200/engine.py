@@ -262,6 +262,64 @@ class Engine:
         self._keep = [u, cand_d, nc, cc]
         return (ids, rank, sc) if return_scores else (ids, rank)
 
+    # ------------------------------------------------------------------ full-catalog top-K
+    def catalog_prepare(self, cta_group=0, max_pass_rows=0, splits=0):
+        """Build the recipe-side index of the catalog kernel from the current R / item_cats
+        (call again after training changed R).  Synchronises."""
+        if self.item_cats is None:
+            raise L.FoodRecError("catalog scoring needs the item_cats (dish_to_category) table")
+        self.flush()
+        o = L.fr_catalog_opts(int(cta_group), int(max_pass_rows), int(splits))
+        L.check(self.handle, self.lib.fr_catalog_prepare(self.handle, C.byref(o), self._stream()))
+        self._catalog_ready = True
+
+    def catalog_topk(self, users=None, K=100, P_rows=None, n_users=None, id_mul=1, id_add=0, return_scores=True):
+        """The K best recipes of the whole catalog per query user by (score desc, id asc):
+        ``ids`` int32 [n,K] (-1 padded), ``scores`` float64 [n,K].  Query rows are
+        ``P_rows`` [n,5,D] (device) if given, else ``users`` into Personal_Memory
+        (None = the first ``n_users`` users).  Asynchronous on the current stream."""
+        if not getattr(self, "_catalog_ready", False):
+            self.catalog_prepare()
+        self.flush()
+        pr = u = None
+        if P_rows is not None:
+            pr = self._f32(P_rows, (-1, 5, self.D))
+            n = pr.shape[0]
+        elif users is not None:
+            u = self._i32(users)
+            n = u.numel()
+        else:
+            n = self.U if n_users is None else int(n_users)
+        ids = torch.empty((n, K), dtype=torch.int32, device=self.device)
+        sc = torch.empty((n, K), dtype=torch.float64, device=self.device) if return_scores else None
+        L.check(self.handle, self.lib.fr_catalog_topk(self.handle, _ptr(u), _ptr(pr), n, int(K), int(id_mul), int(id_add),
+                                                      _ptr(ids), _ptr(sc), self._stream()))
+        self._keep = [u, pr]
+        return (ids, sc) if return_scores else ids
+
+    def catalog_merge(self, ids, scores):
+        """Merge per-shard lists [W,n,K] into the K best of their union."""
+        ids = ids.to(self.device, torch.int32).contiguous(); scores = scores.to(self.device, torch.float64).contiguous()
+        W, n, K = ids.shape
+        oi = torch.empty((n, K), dtype=torch.int32, device=self.device)
+        os_ = torch.empty((n, K), dtype=torch.float64, device=self.device)
+        L.check(self.handle, self.lib.fr_catalog_merge(self.handle, _ptr(ids), _ptr(scores), W, n, K, _ptr(oi), _ptr(os_),
+                                                       self._stream()))
+        self._keep = [ids, scores]
+        return oi, os_
+
+    def catalog_timing_read(self, reset=True):
+        ms = (C.c_double * 4)()
+        n = C.c_int64()
+        L.check(self.handle, self.lib.fr_catalog_timing_read(self.handle, ms, C.byref(n), int(bool(reset))))
+        return dict(zip(("user_operand", "gemm_filter", "rerank", "exact_fallback"), list(ms))), n.value
+
+    def catalog_info(self):
+        v = (C.c_int32 * 8)()
+        L.check(self.handle, self.lib.fr_catalog_info(self.handle, v))
+        return dict(zip(("cta_group", "k_padded", "tiles", "present_masks", "recipes_with_category", "tile_width",
+                         "list_capacity", "fallback_blocks"), list(v)))
+
     def sort_pairs(self, keys, nbits):
         k = torch.as_tensor(np.asarray(keys, np.int64).astype(np.uint32).view(np.int32)).to(self.device)
         ok = torch.empty_like(k); oi = torch.empty_like(k)

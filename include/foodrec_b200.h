@@ -193,6 +193,38 @@ int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* sh, int32_t 
 int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rreq, const float* rgrows, float* out_scalars,
                    fr_stream s);
 
+/* ---- Full-catalog top-K (extension; definition = inference :56-97 over EVERY recipe, the
+ * K best by (score desc, id asc)).  The dense contraction runs in bf16 on tcgen05 as a FILTER
+ * with a proven error bound; survivors are re-scored in fp64 from the fp32 tables, so ids are
+ * exact and scores are the fp64 value of the reference formula (see csrc/catalog.cuh).
+ * Requires tables.item_cats with 0/1 entries (dish_to_category); recipes with no category are
+ * never returned (the reference divides by zero for them, Model_Recommender.py:79,92).
+ *
+ * fr_catalog_prepare builds the recipe-side index from the CURRENT R / item_cats (recipes
+ * grouped by category mask, bf16 operand, norms).  It synchronises the stream and must be
+ * called again after R or item_cats change.  P and Cat are read at query time. */
+typedef struct {
+  int32_t cta_group;      /* 0 = default (2: CTA pairs, tcgen05 cta_group::2), 1 = single-CTA MMA */
+  int32_t max_pass_rows;  /* 0 = default; users processed per pass */
+  int32_t splits;         /* 0 = auto; pieces the recipe sweep is cut into for small user counts */
+} fr_catalog_opts;
+int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_stream s);
+/* Query rows: P_rows != NULL -> dense device rows [n_users,5,D] (e.g. all-gathered from the user
+ * owners); else users[n_users] (device) index tables.P, NULL = 0..n_users-1.
+ * out_ids [n_users,K] = local recipe row * id_mul + id_add (-1 padded); out_scores [n_users,K]
+ * fp64 or NULL.  Asynchronous on the stream. */
+int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P_rows, int32_t n_users, int32_t K,
+                    int32_t id_mul, int32_t id_add, int32_t* out_ids, double* out_scores, fr_stream s);
+/* Item-sharded merge: ids/scores [n_lists, n_users, K] (each list sorted, -1 padded) ->
+ * the K best of the union by (score desc, id asc).  n_lists*K <= 4096. */
+int fr_catalog_merge(fr_handle h, const int32_t* ids, const double* scores, int32_t n_lists, int32_t n_users,
+                     int32_t K, int32_t* out_ids, double* out_scores, fr_stream s);
+/* Device time per phase {user operand, tcgen05 GEMM+filter, exact re-rank, exact fallback},
+ * CUDA events on the call's stream, recorded while fr_timing_enable is on. */
+int fr_catalog_timing_read(fr_handle h, double* ms_sum /* [4] */, int64_t* n_passes, int32_t reset);
+/* {cta_group, padded K, tiles, present-mask bits, recipes with a category, tile width, list capacity, fallback blocks} */
+int fr_catalog_info(fr_handle h, int32_t* out /* [8] */);
+
 /* stable LSD radix sort of (key, index) pairs -- exported for tests of the
  * sort-and-segment machinery.  keys [n] (values < 2^nbits), out_keys/out_idx [n]. */
 int fr_sort_pairs(fr_handle h, const uint32_t* keys, int32_t n, int32_t nbits,
