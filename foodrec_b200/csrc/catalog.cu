@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <vector>
 
 #include "catalog.cuh"
@@ -15,7 +16,7 @@ namespace fr {
 
 struct CatalogWs {
   bool prepared = false;
-  int cta_group = 1, I = 0, KP = 0, k_blocks = 0, n_tiles = 0, present = 0, n_valid_items = 0;
+  int cta_group = 1, epi_sets = 2, I = 0, KP = 0, k_blocks = 0, n_tiles = 0, present = 0, n_valid_items = 0;
   int max_pass_rows = 0, force_splits = 0;
   // index (built by fr_catalog_prepare)
   uint32_t* keys = nullptr; SortBufs sortM; int32_t* gs_dev = nullptr;
@@ -495,11 +496,12 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_s
     if ((rc = dalloc(h, &w.tile_pos, (size_t)w.tiles_cap))) return rc;
     if ((rc = dalloc(h, &w.rmax, 1))) return rc;
     FR_CUDA(h, catalog_gemm_configure());
-    FR_CUDA(h, cudaFuncSetAttribute(cat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    FR_CUDA(h, cudaFuncSetAttribute(cat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   w.cta_group = (opts && opts->cta_group == 1) ? 1 : 2;
   w.max_pass_rows = (opts && opts->max_pass_rows > 0) ? opts->max_pass_rows : 0;
-  w.force_splits = (opts && opts->splits > 0) ? std::min(opts->splits, CAT_SPLIT_MAX) : 0;
+  w.epi_sets = (opts && (opts->epi_sets == 1 || opts->epi_sets == 2 || opts->epi_sets == 4)) ? opts->epi_sets : 2;
+  w.force_splits = (opts && opts->splits > 0) ? std::min(opts->splits, CAT_LISTS_MAX / w.epi_sets) : 0;
 
   cat_mask_kernel<<<(I + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(h->tab.item_cats), I, w.keys);
   ++g_launches;
@@ -548,9 +550,10 @@ static int catalog_ensure_pass_ws(fr_ctx* h, CatalogWs& w, int mp) {
   if ((rc = dalloc(h, &w.A, 16 * R * w.KP))) return rc;
   if ((rc = dalloc(h, &w.bias, 16 * R))) return rc;
   if ((rc = dalloc(h, &w.margin2, R))) return rc;
-  if ((rc = dalloc(h, &w.cand_sc, R * CAT_CAP))) return rc;
-  if ((rc = dalloc(h, &w.cand_row, R * CAT_CAP))) return rc;
-  if ((rc = dalloc(h, &w.cand_cnt, R))) return rc;
+  const size_t RL = R * 4;          // candidate lists: up to 4 column sets per (split, row)
+  if ((rc = dalloc(h, &w.cand_sc, RL * CAT_CAP))) return rc;
+  if ((rc = dalloc(h, &w.cand_row, RL * CAT_CAP))) return rc;
+  if ((rc = dalloc(h, &w.cand_cnt, RL))) return rc;
   if ((rc = dalloc(h, &w.ovf, R))) return rc;
   if ((rc = dalloc(h, &w.ovf_list, R))) return rc;
   if ((rc = dalloc(h, &w.ovf_count, 1))) return rc;
@@ -573,6 +576,7 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
   const int n_clusters = std::max(1, h->sm_count / CG);
   // rows per pass: whole waves of user blocks; small calls split the recipe sweep instead
   const int pass_rows = w.max_pass_rows > 0 ? (w.max_pass_rows + BMC - 1) / BMC * BMC : n_clusters * BMC * 4;
+  const int NSET = w.epi_sets;
   int rc = catalog_ensure_pass_ws(h, w, std::max(pass_rows, 2 * n_clusters * BMC));
   if (rc) return rc;
   const int D = h->mc.D, DV = h->mc.DV;
@@ -583,8 +587,9 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     const int rows = std::min(pass_rows, n_users - row0);
     const int m_blocks = (rows + BMC - 1) / BMC, m_pad = m_blocks * BMC;
     int n_split = w.force_splits ? w.force_splits : (n_clusters + m_blocks - 1) / m_blocks;
-    n_split = std::max(1, std::min({n_split, CAT_SPLIT_MAX, std::max(1, w.n_tiles)}));
+    n_split = std::max(1, std::min({n_split, CAT_LISTS_MAX / NSET, std::max(1, w.n_tiles)}));
     while (n_split > 1 && (size_t)n_split * m_pad > (size_t)w.mp_cap) --n_split;
+    const int n_lists = n_split * NSET;
     const int tps = std::max(1, (w.n_tiles + n_split - 1) / n_split);
     UserSrc src{reinterpret_cast<const float4*>(P_rows ? P_rows : h->tab.P), P_rows ? nullptr : users, row0};
 
@@ -606,7 +611,7 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
                                                             w.KP, h->mc.a, h->mc.oma, w.present, w.rmax, cfac, w.A, w.bias, w.margin2);
     ++g_launches;
     FR_CHECK_LAUNCH(h);
-    FR_CUDA(h, cudaMemsetAsync(w.cand_cnt, 0, (size_t)n_split * m_pad * 4, st));
+    FR_CUDA(h, cudaMemsetAsync(w.cand_cnt, 0, (size_t)n_lists * m_pad * 4, st));
     FR_CUDA(h, cudaMemsetAsync(w.ovf, 0, (size_t)m_pad * 4, st));
     FR_CUDA(h, cudaMemsetAsync(w.ovf_count, 0, 4, st));
     if (ev) FR_CUDA(h, cudaEventRecord((*ev)[1], st));
@@ -617,21 +622,22 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
       CatGemmParams p{};
       p.m_blocks = m_blocks; p.m_pad = m_pad; p.n_rows = rows; p.n_split = n_split; p.tiles_per_split = tps;
       p.n_tiles = w.n_tiles; p.k_blocks = w.k_blocks; p.K = K;
+      { const char* dm = getenv("FOODREC_CATALOG_DEBUG"); p.debug_mode = dm ? atoi(dm) : 0; }
       p.tile_group = w.tile_group; p.tile_valid = w.tile_valid; p.bias = w.bias; p.margin2 = w.margin2;
       p.cand_sc = w.cand_sc; p.cand_row = w.cand_row; p.cand_cnt = w.cand_cnt; p.ovf = w.ovf;
-      launch_catalog_gemm(CG, h->sm_count, tmA, w.tmB, p, st);
+      launch_catalog_gemm(CG, NSET, h->sm_count, tmA, w.tmB, p, st);
       FR_CHECK_LAUNCH(h);
     }
     if (ev) FR_CUDA(h, cudaEventRecord((*ev)[2], st));
 
     FinParams f{};
     f.src = src; f.R = h->tab.R; f.Cat = h->tab.Cat; f.item_cats = reinterpret_cast<const float4*>(h->tab.item_cats);
-    f.row_item = w.row_item; f.D = D; f.n_rows = rows; f.m_pad = m_pad; f.n_split = n_split; f.K = K;
+    f.row_item = w.row_item; f.D = D; f.n_rows = rows; f.m_pad = m_pad; f.n_split = n_lists; f.K = K;
     f.a = (double)h->mc.a; f.oma = (double)h->mc.oma;
     f.margin2 = w.margin2; f.cand_sc = w.cand_sc; f.cand_row = w.cand_row; f.cand_cnt = w.cand_cnt;
     f.ovf = w.ovf; f.ovf_list = w.ovf_list; f.ovf_count = w.ovf_count;
     f.id_mul = id_mul; f.id_add = id_add; f.out_ids = out_ids; f.out_scores = out_scores;
-    const size_t fsm = (size_t)CAT_FCAP * (8 + 4 + 4) + 32 + (size_t)5 * D * 4 + (size_t)n_split * CAT_CAP * 8;
+    const size_t fsm = (size_t)CAT_FCAP * (8 + 4 + 4) + 32 + (size_t)5 * D * 4 + (size_t)n_lists * CAT_CAP * 8;
     cat_finalize_kernel<<<rows, FIN_THREADS, fsm, st>>>(f);
     ++g_launches;
     FR_CHECK_LAUNCH(h);
@@ -683,11 +689,20 @@ extern "C" int fr_catalog_timing_read(fr_handle h, double* ms_sum, int64_t* n_pa
   return FR_OK;
 }
 
+extern "C" int fr_catalog_fallback_rows(fr_handle h, int32_t* out, fr_stream s) {
+  if (!h || !out) return FR_ERR_ARG;
+  if (!h->cat || !h->cat->ovf_count) return fail(h, FR_ERR_STATE, "no catalog pass has run");
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  FR_CUDA(h, cudaMemcpyAsync(out, h->cat->ovf_count, 4, cudaMemcpyDeviceToHost, st));
+  FR_CUDA(h, cudaStreamSynchronize(st));
+  return FR_OK;
+}
+
 extern "C" int fr_catalog_info(fr_handle h, int32_t* out /* [8] */) {
   if (!h || !out) return FR_ERR_ARG;
   if (!h->cat || !h->cat->prepared) return fail(h, FR_ERR_STATE, "fr_catalog_prepare first");
   const CatalogWs& w = *h->cat;
   out[0] = w.cta_group; out[1] = w.KP; out[2] = w.n_tiles; out[3] = w.present; out[4] = w.n_valid_items;
-  out[5] = CAT_BN; out[6] = CAT_CAP; out[7] = w.exact_blocks;
+  out[5] = w.epi_sets; out[6] = CAT_CAP; out[7] = w.exact_blocks;
   return FR_OK;
 }

@@ -32,8 +32,7 @@ constexpr int CAT_KB_MAX = 4;      // D <= 256
 constexpr int CAT_CAP = 512;       // candidate slots per (split, user)
 constexpr int CAT_FCAP = 1024;     // survivors re-scored per user
 constexpr int CAT_MAXK = 256;
-constexpr int CAT_SPLIT_MAX = 16;
-constexpr int CAT_THREADS = 256;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int CAT_LISTS_MAX = 32;    // candidate lists per user the re-rank kernel merges (splits x column sets)
 constexpr int CAT_A_BLK = CAT_BM * CAT_BK * 2;                // 16 KB: one k-block of A
 constexpr int CAT_B_TOTAL = 128 * 1024;                       // all B stages
 constexpr int CAT_SMEM = CAT_KB_MAX * CAT_A_BLK + CAT_B_TOTAL + 1024 /*barriers*/ + 1024 /*align*/;
@@ -43,17 +42,18 @@ struct CatGemmParams {
   int m_pad;             // m_blocks * CAT_BM * CG
   int n_rows;            // valid user rows in this pass
   int n_split, tiles_per_split, n_tiles, k_blocks, K;
+  int debug_mode;        // 0 = normal; 1 = epilogue only drains TMEM (pipeline ceiling measurement, results invalid)
   const int32_t* tile_group;   // [n_tiles] mask of each tile
   const int32_t* tile_valid;   // [n_tiles] recipes in the tile (256 except a group's last tile)
   const float* bias;           // [16][m_pad]
   const float* margin2;        // [m_pad]  2E
-  float* cand_sc;              // [n_split*m_pad][CAT_CAP] approx total score
+  float* cand_sc;              // [n_split*NSET*m_pad][CAT_CAP] approx total score
   int32_t* cand_row;           // same shape: padded recipe row
-  int32_t* cand_cnt;           // [n_split*m_pad]
+  int32_t* cand_cnt;           // [n_split*NSET*m_pad]
   int32_t* ovf;                // [m_pad] 1 = candidate list overflowed
 };
 
-void launch_catalog_gemm(int cta_group, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
+void launch_catalog_gemm(int cta_group, int epi_sets, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
                          const CatGemmParams& p, cudaStream_t st);
 cudaError_t catalog_gemm_configure();   // opt-in dynamic shared memory for both variants
 

@@ -11,12 +11,16 @@
 //            256-column fp32 accumulator stages in TMEM, commits free the smem stage / publish
 //            the accumulator
 //   warp 2   TMEM allocation
-//   warps 4-7 epilogue: thread r owns user row r for the whole sweep (threshold and candidate
-//            count live in its registers): tcgen05.ld 32 columns -> max-tree -> one compare;
-//            only a chunk that holds a value >= threshold takes the per-value push path.  A
-//            row whose candidate list is nearly full is compacted by its warp (exact K-th
-//            largest by bitwise binary search with warp REDUX, keep >= kth - 2E).
+//   warps 4.. epilogue, NSET sets of 4 warps; set e owns accumulator columns [e*256/NSET, ...):
+//            a thread owns one user row of its column set for the whole sweep (threshold and
+//            candidate count live in its registers): tcgen05.ld 32 columns (next chunk's load in
+//            flight) -> max-tree -> one compare; only a chunk that holds a value >= threshold
+//            takes the per-value push path.  A row whose candidate list is nearly full is
+//            compacted by its warp (exact K-th largest by bitwise binary search with warp REDUX,
+//            keep >= kth - 2E).  Several warps per scheduler hide the TMEM / ALU latencies.
 // No score matrix is ever written: HBM traffic is B once per concurrent wave plus O(K log) candidates.
+#include <algorithm>
+
 #include "catalog.cuh"
 #include "common.cuh"
 #include "internal.h"
@@ -31,13 +35,17 @@ struct CatCfg {
   static constexpr int NS = CAT_B_TOTAL / B_STAGE;      // 4 (CG=1) / 8 (CG=2)
 };
 
-// Warp-collective compaction of lane L's candidate row.  Keeps every entry >= kth - 2E.
-__device__ __noinline__ void catalog_warp_compact(const int L, const int lane, float* __restrict__ cand_sc,
-                                                  int32_t* __restrict__ cand_row, const size_t my_base, int& cnt,
-                                                  float& thr, const float my_margin2, const int K, int32_t* ovf_flag) {
+// Warp-collective compaction of lane L's candidate row: exact K-th largest of its entries by
+// bitwise binary search (warp REDUX per bit), keep everything >= kth - 2E.  Returns lane L's new
+// (count, threshold); every other lane gets its own values back.
+struct CompactOut { int cnt; float thr; };
+__device__ __noinline__ CompactOut catalog_warp_compact(const int L, const int lane, float* __restrict__ cand_sc,
+                                                        int32_t* __restrict__ cand_row, const size_t my_base,
+                                                        const int my_cnt, const float my_thr, const float my_margin2,
+                                                        const int K, int32_t* ovf_flag) {
   constexpr int NV = CAT_CAP / 32;
   const size_t base = __shfl_sync(FR_FULL, (unsigned long long)my_base, L);
-  const int n = min(__shfl_sync(FR_FULL, cnt, L), CAT_CAP);
+  const int n = min(__shfl_sync(FR_FULL, my_cnt, L), CAT_CAP);
   const float m2 = __shfl_sync(FR_FULL, my_margin2, L);
   float sc[NV]; int32_t rw[NV]; uint32_t key[NV];
 #pragma unroll
@@ -71,17 +79,83 @@ __device__ __noinline__ void catalog_warp_compact(const int L, const int lane, f
     out += __popc(bal);
   }
   __syncwarp();
+  CompactOut r{my_cnt, my_thr};
   if (lane == L) {
-    cnt = out; thr = nthr;
-    if (out > CAT_CAP - 64) { *ovf_flag = 1; thr = __int_as_float(0x7f800000); }   // too many near-ties: exact fallback
+    r.cnt = out; r.thr = nthr;
+    if (out > CAT_CAP - 64) { *ovf_flag = 1; r.thr = __int_as_float(0x7f800000); }   // too many near-ties: exact fallback
+  }
+  return r;
+}
+
+// Per-lane filter state of one (column set, user row): lives in registers for the whole sweep.
+struct RowState {
+  float thr, adj, bias, m2;
+  int cnt;
+  size_t base;
+  int32_t* ovf;
+};
+
+// One 32-column chunk of the accumulator rows held by this warp (lane = user row).
+// Fast path: 3-level max tree, one vote.  A chunk in which some row has a value >= its threshold is
+// resolved with WARP-UNIFORM control flow only (per-element divergent branches cost a
+// BSSY/BSYNC pair each and dominated the first version of this kernel): REDUX.OR finds the
+// 8-column groups, then the columns, that hold a hit in any row; each such column is re-read
+// from TMEM with a one-column tcgen05.ld (uniform address) and pushed under a predicate.
+__device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const uint32_t tchunk, const int col,
+                                                     const int nvalid, const int n0, RowState& s,
+                                                     const CatGemmParams& p, const int lane) {
+  float m[16], g8[4];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) m[j] = fmaxf(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) g8[j] = fmaxf(fmaxf(m[4 * j], m[4 * j + 1]), fmaxf(m[4 * j + 2], m[4 * j + 3]));
+  const float mx = fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3]));
+  if (!__any_sync(FR_FULL, mx >= s.adj)) return;
+  // From here on the compiler may spill / the compaction call may save registers: the prefetched
+  // chunk (an asynchronous tcgen05.ld into registers) must have landed before that can happen.
+  tc::tmem_ld_wait();
+  const uint32_t gm = (g8[0] >= s.adj ? 1u : 0u) | (g8[1] >= s.adj ? 2u : 0u) | (g8[2] >= s.adj ? 4u : 0u) |
+                      (g8[3] >= s.adj ? 8u : 0u);
+  const uint32_t gmw = __reduce_or_sync(FR_FULL, gm);
+#pragma unroll
+  for (int G = 0; G < 4; ++G) {
+    if (gmw & (1u << G)) {                                   // uniform
+      uint32_t cm = 0;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) cm |= (v[8 * G + jj] >= s.adj) ? (1u << jj) : 0u;
+      uint32_t cmw = __reduce_or_sync(FR_FULL, cm);
+      while (cmw) {                                          // uniform: columns with a hit in some row
+        const int jj = __ffs(cmw) - 1;
+        cmw &= cmw - 1;
+        const int c = col + 8 * G + jj;
+        if (c < nvalid) {                                    // zero padding at the end of a mask group is never a candidate
+          const float x = tc::tmem_ld_32x1(tchunk + 8 * G + jj);
+          if (x >= s.adj) {                                  // cnt <= CAP - 32 on entry (compaction policy): no bound check
+            __stcg(p.cand_sc + s.base + s.cnt, x + s.bias);
+            __stcg(p.cand_row + s.base + s.cnt, n0 + c);
+            ++s.cnt;
+          }
+        }
+      }
+    }
+  }
+  uint32_t need = __ballot_sync(FR_FULL, s.cnt > CAT_CAP - 32);
+  while (need) {
+    const int L = __ffs(need) - 1;
+    need &= need - 1;
+    const CompactOut o = catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, s.base, s.cnt, s.thr, s.m2, p.K, s.ovf);
+    s.cnt = o.cnt; s.thr = o.thr;
+    s.adj = __fsub_rd(s.thr, s.bias);
   }
 }
 
-template <int CG>
-__global__ void __launch_bounds__(CAT_THREADS, 1)
+template <int CG, int NSET>
+__global__ void __launch_bounds__(128 + 128 * NSET, 1)
 catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const CatGemmParams p) {
   using C = CatCfg<CG>;
+  constexpr int CW = CAT_BN / NSET;      // accumulator columns per epilogue warp set
+  constexpr int NCH = CW / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -100,7 +174,7 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::NS; ++i) { tc::mbar_init(&full[i], CG); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4 * CG); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4 * NSET * CG); }
     tc::mbar_init(a_empty, 1);
     tc::fence_barrier_init();
   }
@@ -177,9 +251,12 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================= epilogue: running top-K filter =================
-    const int q = warp & 3;
+    // warp set e = (warp-4)/4 owns accumulator columns [e*CW, (e+1)*CW); a warp can only read the
+    // TMEM lane quarter warp%4, so thread (q, lane) is user row q*32+lane for the whole sweep and
+    // keeps one candidate list per column set.
+    const int q = warp & 3, e = (warp - 4) >> 2;
     const int r_in_blk = q * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + e * CW;
     const float INF = __int_as_float(0x7f800000);
     uint32_t tcount = 0;
     for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
@@ -187,59 +264,60 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
       const int grow = mb * (CAT_BM * CG) + (int)rank * CAT_BM + r_in_blk;
       const bool valid = grow < p.n_rows;
-      const size_t base = (static_cast<size_t>(sp) * p.m_pad + grow) * CAT_CAP;
-      const float m2 = __ldg(p.margin2 + grow);
-      float thr = valid ? -INF : INF;
-      int cnt = 0;
+      const size_t list = (static_cast<size_t>(sp) * NSET + e) * p.m_pad + grow;
+      RowState s;
+      s.base = list * CAT_CAP; s.m2 = __ldg(p.margin2 + grow); s.thr = valid ? -INF : INF; s.cnt = 0; s.bias = 0.f;
+      s.adj = s.thr; s.ovf = p.ovf + grow;
       int cur_g = -1;
-      float bias = 0.f;
       for (int t = t0; t < t1; ++t, ++tcount) {
         const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
         const int g = __ldg(p.tile_group + t);
-        if (g != cur_g) { cur_g = g; bias = __ldg(p.bias + (size_t)g * p.m_pad + grow); }
-        float adj = __fsub_rd(thr, bias);            // push iff  v + bias >= thr
+        const int nvalid = __ldg(p.tile_valid + t);     // rows of this tile that hold a recipe
+        if (g != cur_g) { cur_g = g; s.bias = __ldg(p.bias + (size_t)g * p.m_pad + grow); }
+        s.adj = __fsub_rd(s.thr, s.bias);               // push iff  v + bias >= thr
         tc::mbar_wait(&tfull[as], aph);
         tc::fence_after_sync();
         const int n0 = t * CAT_BN;
-        const int nvalid = __ldg(p.tile_valid + t);     // rows of this tile that hold a recipe (the rest is zero padding)
-#pragma unroll 1
-        for (int c = 0; c < CAT_BN / 32; ++c) {
-          float v[32];
+        const uint32_t tcol = t_lane + as * CAT_BN;
+        auto release = [&]() {                          // accumulator stage fully read by this warp
+          tc::fence_before_sync();
           __syncwarp();
-          tc::tmem_ld_32x32(t_lane + as * CAT_BN + c * 32, v);
-          tc::tmem_ld_wait();
-          if (c == CAT_BN / 32 - 1) {                 // accumulator fully read: hand it back to the MMA warp
-            tc::fence_before_sync();
+          if (lane == 0) { if (CG == 1) tc::mbar_arrive(&tempty[as]); else tc::mbar_arrive_cluster(&tempty[as], 0); }
+        };
+        if (p.debug_mode == 2) { release(); continue; }     // MMA/TMA ceiling: accumulators are never read
+        if constexpr (NSET <= 2) {
+          float va[32], vb[32];
+          __syncwarp();
+          tc::tmem_ld_32x32(tcol, va);
+#pragma unroll
+          for (int c = 0; c < NCH; c += 2) {            // TMEM load of chunk c+1 is in flight while chunk c is filtered
+            tc::tmem_ld_wait();
             __syncwarp();
-            if (lane == 0) { if (CG == 1) tc::mbar_arrive(&tempty[as]); else tc::mbar_arrive_cluster(&tempty[as], 0); }
-          }
-          float m16[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m16[j] = fmaxf(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) m16[j] = fmaxf(m16[2 * j], m16[2 * j + 1]);
-          const float mx = fmaxf(fmaxf(fmaxf(m16[0], m16[1]), fmaxf(m16[2], m16[3])),
-                                 fmaxf(fmaxf(m16[4], m16[5]), fmaxf(m16[6], m16[7])));
-          if (mx >= adj) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] >= adj && c * 32 + j < nvalid) {
-                const int prow = n0 + c * 32 + j;
-                if (cnt < CAT_CAP) { __stcg(p.cand_sc + base + cnt, v[j] + bias); __stcg(p.cand_row + base + cnt, prow); }
-                ++cnt;
-              }
+            if (c + 1 < NCH) tc::tmem_ld_32x32(tcol + (c + 1) * 32, vb);
+            if (p.debug_mode == 0) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
+            else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
+            if (c + 1 < NCH) {
+              tc::tmem_ld_wait();
+              __syncwarp();
+              if (c + 2 < NCH) tc::tmem_ld_32x32(tcol + (c + 2) * 32, va);
+              if (p.debug_mode == 0) catalog_filter_chunk(vb, tcol + (c + 1) * 32, e * CW + (c + 1) * 32, nvalid, n0, s, p, lane);
+              else if (vb[0] + vb[13] + vb[31] == 12345.f) s.cnt++;
             }
           }
-          uint32_t need = __ballot_sync(FR_FULL, cnt > CAT_CAP - 32);
-          while (need) {
-            const int L = __ffs(need) - 1;
-            need &= need - 1;
-            catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, base, cnt, thr, m2, p.K, p.ovf + grow);
-            if (lane == L) adj = __fsub_rd(thr, bias);
+        } else {                                        // 16 epilogue warps: 96 registers each, no prefetch buffer
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            float va[32];
+            __syncwarp();
+            tc::tmem_ld_32x32(tcol + c * 32, va);
+            tc::tmem_ld_wait();
+            if (p.debug_mode == 0) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
+            else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
           }
         }
+        release();                                      // after the last possible re-read of this stage
       }
-      if (valid) p.cand_cnt[(size_t)sp * p.m_pad + grow] = min(cnt, CAT_CAP);
+      if (valid) p.cand_cnt[list] = min(s.cnt, CAT_CAP);
     }
   }
 
@@ -249,34 +327,50 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) tc::tmem_dealloc<CG>(tmem_base, 512);
 }
 
+template <int CG, int NSET>
+static cudaError_t configure_one() {
+  return cudaFuncSetAttribute(catalog_gemm_kernel<CG, NSET>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAT_SMEM);
+}
 cudaError_t catalog_gemm_configure() {
-  cudaError_t e = cudaFuncSetAttribute(catalog_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAT_SMEM);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(catalog_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAT_SMEM);
+  cudaError_t e;
+  if ((e = configure_one<1, 1>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 1>()) != cudaSuccess) return e;
+  if ((e = configure_one<1, 2>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 2>()) != cudaSuccess) return e;
+  if ((e = configure_one<1, 4>()) != cudaSuccess) return e;
+  return configure_one<2, 4>();
 }
 
-void launch_catalog_gemm(int cta_group, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                         const CatGemmParams& p, cudaStream_t st) {
+template <int CG, int NSET>
+static void launch_one(int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB, const CatGemmParams& p, cudaStream_t st) {
   const int n_units = p.m_blocks * p.n_split;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(CAT_THREADS);
+  cfg.blockDim = dim3(128 + 128 * NSET);
   cfg.dynamicSmemBytes = CAT_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  if (cta_group == 2) {
-    const int pairs = min(sm_count / 2, n_units);
-    cfg.gridDim = dim3(2 * (pairs < 1 ? 1 : pairs));
+  const int clusters = std::max(1, std::min(sm_count / CG, n_units));
+  cfg.gridDim = dim3(CG * clusters);
+  if (CG == 2) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, catalog_gemm_kernel<2>, tmA, tmB, p);
-  } else {
-    const int ctas = min(sm_count, n_units);
-    cfg.gridDim = dim3(ctas < 1 ? 1 : ctas);
-    cfg.attrs = nullptr; cfg.numAttrs = 0;
-    cudaLaunchKernelEx(&cfg, catalog_gemm_kernel<1>, tmA, tmB, p);
   }
+  cudaLaunchKernelEx(&cfg, catalog_gemm_kernel<CG, NSET>, tmA, tmB, p);
   ++g_launches;
+}
+
+void launch_catalog_gemm(int cta_group, int epi_sets, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const CatGemmParams& p, cudaStream_t st) {
+  if (cta_group == 2) {
+    if (epi_sets == 4) launch_one<2, 4>(sm_count, tmA, tmB, p, st);
+    else if (epi_sets == 2) launch_one<2, 2>(sm_count, tmA, tmB, p, st);
+    else launch_one<2, 1>(sm_count, tmA, tmB, p, st);
+  } else {
+    if (epi_sets == 4) launch_one<1, 4>(sm_count, tmA, tmB, p, st);
+    else if (epi_sets == 2) launch_one<1, 2>(sm_count, tmA, tmB, p, st);
+    else launch_one<1, 1>(sm_count, tmA, tmB, p, st);
+  }
 }
 
 }  // namespace fr

@@ -263,13 +263,13 @@ class Engine:
         return (ids, rank, sc) if return_scores else (ids, rank)
 
     # ------------------------------------------------------------------ full-catalog top-K
-    def catalog_prepare(self, cta_group=0, max_pass_rows=0, splits=0):
+    def catalog_prepare(self, cta_group=0, max_pass_rows=0, splits=0, epi_sets=0):
         """Build the recipe-side index of the catalog kernel from the current R / item_cats
         (call again after training changed R).  Synchronises."""
         if self.item_cats is None:
             raise L.FoodRecError("catalog scoring needs the item_cats (dish_to_category) table")
         self.flush()
-        o = L.fr_catalog_opts(int(cta_group), int(max_pass_rows), int(splits))
+        o = L.fr_catalog_opts(int(cta_group), int(max_pass_rows), int(splits), int(epi_sets))
         L.check(self.handle, self.lib.fr_catalog_prepare(self.handle, C.byref(o), self._stream()))
         self._catalog_ready = True
 
@@ -314,10 +314,15 @@ class Engine:
         L.check(self.handle, self.lib.fr_catalog_timing_read(self.handle, ms, C.byref(n), int(bool(reset))))
         return dict(zip(("user_operand", "gemm_filter", "rerank", "exact_fallback"), list(ms))), n.value
 
+    def catalog_fallback_rows(self):
+        v = C.c_int32()
+        L.check(self.handle, self.lib.fr_catalog_fallback_rows(self.handle, C.byref(v), self._stream()))
+        return v.value
+
     def catalog_info(self):
         v = (C.c_int32 * 8)()
         L.check(self.handle, self.lib.fr_catalog_info(self.handle, v))
-        return dict(zip(("cta_group", "k_padded", "tiles", "present_masks", "recipes_with_category", "tile_width",
+        return dict(zip(("cta_group", "k_padded", "tiles", "present_masks", "recipes_with_category", "epi_sets",
                          "list_capacity", "fallback_blocks"), list(v)))
 
     def sort_pairs(self, keys, nbits):

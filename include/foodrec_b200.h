@@ -207,6 +207,7 @@ typedef struct {
   int32_t cta_group;      /* 0 = default (2: CTA pairs, tcgen05 cta_group::2), 1 = single-CTA MMA */
   int32_t max_pass_rows;  /* 0 = default; users processed per pass */
   int32_t splits;         /* 0 = auto; pieces the recipe sweep is cut into for small user counts */
+  int32_t epi_sets;       /* 0 = default (2); 1, 2 or 4 epilogue warp sets (each owns 256/sets accumulator columns) */
 } fr_catalog_opts;
 int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_stream s);
 /* Query rows: P_rows != NULL -> dense device rows [n_users,5,D] (e.g. all-gathered from the user
@@ -222,8 +223,10 @@ int fr_catalog_merge(fr_handle h, const int32_t* ids, const double* scores, int3
 /* Device time per phase {user operand, tcgen05 GEMM+filter, exact re-rank, exact fallback},
  * CUDA events on the call's stream, recorded while fr_timing_enable is on. */
 int fr_catalog_timing_read(fr_handle h, double* ms_sum /* [4] */, int64_t* n_passes, int32_t reset);
-/* {cta_group, padded K, tiles, present-mask bits, recipes with a category, tile width, list capacity, fallback blocks} */
+/* {cta_group, padded K, tiles, present-mask bits, recipes with a category, epilogue sets, list capacity, fallback blocks} */
 int fr_catalog_info(fr_handle h, int32_t* out /* [8] */);
+/* rows of the LAST pass that took the exact full-scan fallback (synchronises the stream) */
+int fr_catalog_fallback_rows(fr_handle h, int32_t* out, fr_stream s);
 
 /* stable LSD radix sort of (key, index) pairs -- exported for tests of the
  * sort-and-segment machinery.  keys [n] (values < 2^nbits), out_keys/out_idx [n]. */
