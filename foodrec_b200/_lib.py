@@ -50,7 +50,7 @@ class fr_batch(C.Structure):
 
 
 class fr_catalog_opts(C.Structure):
-    _fields_ = [("cta_group", C.c_int32), ("max_pass_rows", C.c_int32), ("splits", C.c_int32), ("epi_sets", C.c_int32)]
+    _fields_ = [("cta_group", C.c_int32), ("max_pass_rows", C.c_int32), ("splits", C.c_int32), ("epi_sets", C.c_int32), ("tile_n", C.c_int32), ("a_split", C.c_int32)]
 
 
 class fr_shard(C.Structure):
@@ -83,6 +83,7 @@ _PROTOS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_catalog_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "fr_catalog_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "fr_catalog_cycle_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "fr_catalog_fallback_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "fr_shard_packed_len": (C.c_int64, [C.c_void_p]),
     "fr_shard_plan": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.POINTER(fr_shard), C.c_void_p, C.c_void_p]),

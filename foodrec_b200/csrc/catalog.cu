@@ -16,7 +16,7 @@ namespace fr {
 
 struct CatalogWs {
   bool prepared = false;
-  int cta_group = 1, epi_sets = 2, I = 0, KP = 0, k_blocks = 0, n_tiles = 0, present = 0, n_valid_items = 0;
+  int cta_group = 1, epi_sets = 2, BN = 128, a_split = 0, I = 0, KP = 0, k_blocks = 0, n_tiles = 0, present = 0, n_valid_items = 0;
   int max_pass_rows = 0, force_splits = 0;
   // index (built by fr_catalog_prepare)
   uint32_t* keys = nullptr; SortBufs sortM; int32_t* gs_dev = nullptr;
@@ -29,6 +29,9 @@ struct CatalogWs {
   __nv_bfloat16* A = nullptr; float *bias = nullptr, *margin2 = nullptr, *cand_sc = nullptr;
   int32_t *cand_row = nullptr, *cand_cnt = nullptr, *ovf = nullptr, *ovf_list = nullptr, *ovf_count = nullptr;
   double* scratch = nullptr; int exact_blocks = 0;
+  unsigned long long* dbg = nullptr;
+  uint32_t* ukeys = nullptr; SortBufs sortU; int32_t* block_first = nullptr;   // users sorted by best mask group
+  int group_lo[16] = {0}, group_hi[16] = {0}, group_last_valid[16] = {0};
   // timing
   std::vector<std::array<cudaEvent_t, 5>> evs; size_t ev_used = 0;
   double t_sum[4] = {0, 0, 0, 0}; int64_t t_passes = 0;
@@ -53,12 +56,12 @@ __global__ void cat_group_bounds_kernel(const uint32_t* __restrict__ sorted_keys
 // one warp per padded row: B[row] = bf16(R[item]) (zero rows pad a group's last tile)
 __global__ void __launch_bounds__(FR_THREADS)
 cat_pack_items_kernel(const float4* __restrict__ R, int DV, int KP, const uint32_t* __restrict__ sorted_idx,
-                      const int32_t* __restrict__ tile_valid, const int32_t* __restrict__ tile_pos, int n_rows,
+                      const int32_t* __restrict__ tile_valid, const int32_t* __restrict__ tile_pos, int n_rows, int BN,
                       __nv_bfloat16* __restrict__ Bq, int32_t* __restrict__ row_item, float* __restrict__ rmax) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= n_rows) return;
-  const int tile = r / CAT_BN, j = r % CAT_BN;
+  const int tile = r / BN, j = r % BN;
   const bool valid = j < __ldg(tile_valid + tile);
   const int item = valid ? (int)__ldg(sorted_idx + __ldg(tile_pos + tile) + j) : -1;
   if (lane == 0) row_item[r] = item;
@@ -82,17 +85,56 @@ struct UserSrc {
   const float4* P;        // table or dense query rows
   const int32_t* uidx;    // nullable: row -> user id
   int row0;               // first query row of this pass
+  const uint32_t* perm;   // nullable: pass row -> query row of the pass (users sorted by best mask group)
 };
+__device__ __forceinline__ int query_row(const UserSrc& s, int j) {      // index into the caller's user list / outputs
+  return s.row0 + (s.perm ? (int)__ldg(s.perm + j) : j);
+}
 __device__ __forceinline__ const float4* user_row(const UserSrc& s, int j, int DV) {
-  const size_t u = s.uidx ? (size_t)__ldg(s.uidx + s.row0 + j) : (size_t)(s.row0 + j);
+  const int qr = query_row(s, j);
+  const size_t u = s.uidx ? (size_t)__ldg(s.uidx + qr) : (size_t)qr;
   return s.P + u * 5 * DV;
+}
+
+// key of a query row = the mask group with the largest category term a/|g| * sum_{c in g} <P[u,0],Cat[c]>
+template <int NV>
+__global__ void __launch_bounds__(FR_THREADS)
+cat_user_key_kernel(UserSrc src, int n_rows, const float4* __restrict__ Cat, int DV, int present, uint32_t* __restrict__ keys) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (j >= n_rows) return;
+  float4 p0[NV];
+  load_row_ro<NV>(p0, user_row(src, j, DV), DV, lane);
+  float h[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < DV) acc += dot4(p0[k], __ldg(Cat + c * DV + i));
+    }
+    h[c] = warp_sum(acc);
+  }
+  float best = -__int_as_float(0x7f800000);
+  int gb = 0;
+  for (int g = 1; g < 16; ++g) {
+    if (!((present >> g) & 1)) continue;
+    float hs = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if ((g >> c) & 1) hs += h[c];
+    hs /= (float)__popc(g);
+    if (hs > best) { best = hs; gb = g; }
+  }
+  if (lane == 0) keys[j] = (uint32_t)gb;
 }
 
 template <int NV>
 __global__ void __launch_bounds__(FR_THREADS)
-cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restrict__ Cat, int DV, int KP, float a,
+cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restrict__ Cat, int DV, int KP, int a_split, float a,
                       float oma, int present, const float* __restrict__ rmax_p, float cfac,
-                      __nv_bfloat16* __restrict__ A, float* __restrict__ bias, float* __restrict__ margin2) {
+                      __nv_bfloat16* __restrict__ A, float* __restrict__ bias, float* __restrict__ margin2,
+                      int32_t* __restrict__ block_first, int block_rows) {
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (j >= m_pad) return;
@@ -123,12 +165,14 @@ cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restri
       for (int k = 0; k < NV; ++k) pr[s][k] = f4zero();
   }
   const float rmax = __ldg(rmax_p);
-  float emax = 0.f;
+  float emax = 0.f, bbest = -__int_as_float(0x7f800000);
+  int gbest = 0;
   for (int g = 1; g < 16; ++g) {
     if (!((present >> g) & 1)) continue;
     const float inv_n = 1.0f / (float)__popc(g);
     float nrm = 0.f;
-    uint2* dst = reinterpret_cast<uint2*>(A + ((size_t)g * m_pad + j) * KP);
+    const int KA = a_split ? 2 * KP : KP;       // row = [bf16 head | bf16 tail of the remainder]
+    uint2* dst = reinterpret_cast<uint2*>(A + ((size_t)g * m_pad + j) * KA);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int i = lane + 32 * k;
@@ -144,6 +188,13 @@ cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restri
         uint2 o;
         o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
         dst[i] = o;
+        if (a_split) {
+          const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
+          const __nv_bfloat162 t0 = __floats2bfloat162_rn(z.x - f0.x, z.y - f0.y), t1 = __floats2bfloat162_rn(z.z - f1.x, z.w - f1.y);
+          uint2 o2;
+          o2.x = *reinterpret_cast<const uint32_t*>(&t0); o2.y = *reinterpret_cast<const uint32_t*>(&t1);
+          dst[KP / 4 + i] = o2;
+        }
       }
     }
     nrm = warp_sum(nrm);
@@ -154,9 +205,13 @@ cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restri
     const float ar = sqrtf(nrm) * rmax;
     const float E = cfac * ar + 4.76837158e-7f * (fabsf(b) + ar);     // 2^-21: fp32 rounding of bias and of v + bias
     emax = fmaxf(emax, E);
+    if (b > bbest) { bbest = b; gbest = g; }
     if (lane == 0) bias[(size_t)g * m_pad + j] = b;
   }
-  if (lane == 0) margin2[j] = 2.0f * emax * 1.00001f;
+  if (lane == 0) {
+    margin2[j] = 2.0f * emax * 1.00001f;
+    if (block_first && j % block_rows == 0) block_first[j / block_rows] = gbest;   // the block sweeps this group first
+  }
 }
 
 // ------------------------------------------------------------------ exact scoring + ranking helpers
@@ -305,7 +360,7 @@ __global__ void __launch_bounds__(FIN_THREADS) cat_finalize_kernel(const FinPara
   for (int i = nF + tid; i < n2; i += FIN_THREADS) { es[i] = -CUDART_INF; eid[i] = 0x7fffffff; }
   __syncthreads();
   bitonic_rank_sort(es, eid, n2, tid, FIN_THREADS);
-  const size_t ob = (size_t)(f.src.row0 + row) * f.K;
+  const size_t ob = (size_t)query_row(f.src, row) * f.K;
   for (int k = tid; k < f.K; k += FIN_THREADS) {
     const bool has = k < nF && eid[k] != 0x7fffffff && es[k] > -CUDART_INF;
     f.out_ids[ob + k] = has ? eid[k] * f.id_mul + f.id_add : -1;
@@ -389,7 +444,7 @@ __global__ void __launch_bounds__(EX_THREADS) cat_exact_kernel(const FinParams f
     for (int i = Keff + tid; i < n2; i += EX_THREADS) { ss[i] = -CUDART_INF; sid[i] = 0x7fffffff; }
     __syncthreads();
     bitonic_rank_sort(ss, sid, n2, tid, EX_THREADS);
-    const size_t ob = (size_t)(f.src.row0 + row) * f.K;
+    const size_t ob = (size_t)query_row(f.src, row) * f.K;
     for (int k = tid; k < f.K; k += EX_THREADS) {
       const bool has = k < Keff && ss[k] > -CUDART_INF;
       f.out_ids[ob + k] = has ? sid[k] * f.id_mul + f.id_add : -1;
@@ -485,12 +540,12 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_s
   if (w.I != I) {
     if (w.I != 0) return fail(h, FR_ERR_STATE, "catalog index was built for %d recipes", w.I);
     w.I = I; w.KP = KP; w.k_blocks = KP / CAT_BK;
-    w.tiles_cap = (I + CAT_BN - 1) / CAT_BN + 15;
+    w.tiles_cap = (I + 127) / 128 + 15;          // sized for the narrow tile
     if ((rc = dalloc(h, &w.keys, (size_t)I))) return rc;
     if ((rc = alloc_sort(h, w.sortM, (size_t)I))) return rc;
     if ((rc = dalloc(h, &w.gs_dev, 17))) return rc;
-    if ((rc = dalloc(h, &w.Bq, (size_t)w.tiles_cap * CAT_BN * KP))) return rc;
-    if ((rc = dalloc(h, &w.row_item, (size_t)w.tiles_cap * CAT_BN))) return rc;
+    if ((rc = dalloc(h, &w.Bq, (size_t)w.tiles_cap * 128 * KP))) return rc;
+    if ((rc = dalloc(h, &w.row_item, (size_t)w.tiles_cap * 128))) return rc;
     if ((rc = dalloc(h, &w.tile_group, (size_t)w.tiles_cap))) return rc;
     if ((rc = dalloc(h, &w.tile_valid, (size_t)w.tiles_cap))) return rc;
     if ((rc = dalloc(h, &w.tile_pos, (size_t)w.tiles_cap))) return rc;
@@ -499,6 +554,9 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_s
     FR_CUDA(h, cudaFuncSetAttribute(cat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   w.cta_group = (opts && opts->cta_group == 1) ? 1 : 2;
+  w.BN = (opts && opts->tile_n == 128) ? 128 : 256;
+  w.a_split = (w.k_blocks * 2 <= CAT_KB_MAX && !(opts && opts->a_split == 1)) ? 1 : 0;   // opts->a_split: 0 default (on when it fits), 1 off
+  const int BN = w.BN;
   w.max_pass_rows = (opts && opts->max_pass_rows > 0) ? opts->max_pass_rows : 0;
   w.epi_sets = (opts && (opts->epi_sets == 1 || opts->epi_sets == 2 || opts->epi_sets == 4)) ? opts->epi_sets : 2;
   w.force_splits = (opts && opts->splits > 0) ? std::min(opts->splits, CAT_LISTS_MAX / w.epi_sets) : 0;
@@ -519,7 +577,13 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_s
     const int cnt = gs[g + 1] - gs[g];
     if (cnt <= 0) continue;
     w.present |= 1 << g;
-    for (int o = 0; o < cnt; o += CAT_BN) { tg.push_back(g); tv.push_back(std::min(CAT_BN, cnt - o)); tp.push_back(gs[g] + o); }
+    for (int o = 0; o < cnt; o += BN) { tg.push_back(g); tv.push_back(std::min(BN, cnt - o)); tp.push_back(gs[g] + o); }
+  }
+  for (int g = 0; g < 16; ++g) w.group_lo[g] = w.group_hi[g] = 0;
+  for (int t = 0; t < (int)tg.size(); ++t) {
+    if (w.group_hi[tg[t]] == 0) w.group_lo[tg[t]] = t;
+    w.group_hi[tg[t]] = t + 1;
+    w.group_last_valid[tg[t]] = tv[t];
   }
   w.n_tiles = (int)tg.size();
   w.n_valid_items = I - (gs[1] - gs[0]);
@@ -529,14 +593,14 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_s
     FR_CUDA(h, cudaMemcpyAsync(w.tile_valid, tv.data(), tv.size() * 4, cudaMemcpyHostToDevice, st));
     FR_CUDA(h, cudaMemcpyAsync(w.tile_pos, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice, st));
     FR_CUDA(h, cudaMemsetAsync(w.rmax, 0, 4, st));
-    const int n_rows = w.n_tiles * CAT_BN;
+    const int n_rows = w.n_tiles * BN;
     cat_pack_items_kernel<<<(n_rows + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK, FR_THREADS, 0, st>>>(
-        reinterpret_cast<const float4*>(h->tab.R), DV, KP, w.sortM.v[r], w.tile_valid, w.tile_pos, n_rows, w.Bq,
+        reinterpret_cast<const float4*>(h->tab.R), DV, KP, w.sortM.v[r], w.tile_valid, w.tile_pos, n_rows, BN, w.Bq,
         w.row_item, w.rmax);
     ++g_launches;
     FR_CHECK_LAUNCH(h);
     FR_CUDA(h, cudaStreamSynchronize(st));     // host vectors above go out of scope
-    if ((rc = make_tmap(h, &w.tmB, w.Bq, (uint64_t)w.n_tiles * CAT_BN, KP, CAT_BN / w.cta_group))) return rc;
+    if ((rc = make_tmap(h, &w.tmB, w.Bq, (uint64_t)w.n_tiles * BN, KP, BN / w.cta_group))) return rc;
   }
   w.prepared = true;
   return FR_OK;
@@ -547,16 +611,21 @@ static int catalog_ensure_pass_ws(fr_ctx* h, CatalogWs& w, int mp) {
   if (w.mp_cap != 0) return fail(h, FR_ERR_STATE, "catalog pass workspace was sized for %d rows", w.mp_cap);
   int rc;
   const size_t R = (size_t)mp;
-  if ((rc = dalloc(h, &w.A, 16 * R * w.KP))) return rc;
+  if ((rc = dalloc(h, &w.A, 16 * R * w.KP * 2))) return rc;
   if ((rc = dalloc(h, &w.bias, 16 * R))) return rc;
   if ((rc = dalloc(h, &w.margin2, R))) return rc;
   const size_t RL = R * 4;          // candidate lists: up to 4 column sets per (split, row)
-  if ((rc = dalloc(h, &w.cand_sc, RL * CAT_CAP))) return rc;
-  if ((rc = dalloc(h, &w.cand_row, RL * CAT_CAP))) return rc;
+  if ((rc = dalloc(h, &w.cand_sc, RL * CAT_CAP + 1024))) return rc;      // + trash slots of the branch-free push
+  if ((rc = dalloc(h, &w.cand_row, RL * CAT_CAP + 1024))) return rc;
   if ((rc = dalloc(h, &w.cand_cnt, RL))) return rc;
   if ((rc = dalloc(h, &w.ovf, R))) return rc;
   if ((rc = dalloc(h, &w.ovf_list, R))) return rc;
   if ((rc = dalloc(h, &w.ovf_count, 1))) return rc;
+  if ((rc = dalloc(h, &w.dbg, 8))) return rc;
+  FR_CUDA(h, cudaMemset(w.dbg, 0, 64));
+  if ((rc = dalloc(h, &w.ukeys, R))) return rc;
+  if ((rc = alloc_sort(h, w.sortU, R))) return rc;
+  if ((rc = dalloc(h, &w.block_first, R / CAT_BM + 1))) return rc;
   const size_t budget = (size_t)512 << 20;
   w.exact_blocks = (int)std::max<size_t>(2, std::min<size_t>((size_t)h->sm_count, budget / ((size_t)w.I * 8)));
   if ((rc = dalloc(h, &w.scratch, (size_t)w.exact_blocks * w.I))) return rc;
@@ -580,7 +649,9 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
   int rc = catalog_ensure_pass_ws(h, w, std::max(pass_rows, 2 * n_clusters * BMC));
   if (rc) return rc;
   const int D = h->mc.D, DV = h->mc.DV;
-  const float cfac = 0.0078278f /* 2u + u^2, u = 2^-8 */ + (float)w.KP * 9.54e-7f /* fp32 accumulation, 4K*2^-22 */;
+  // |s_hat - s| <= cfac * |A||R|.  bf16 rounding u = 2^-8 on both operands: 2u + u^2; with the split
+  // user operand (exact to 2^-16) only the recipe side rounds: u + 2^-15.  Plus fp32 accumulation.
+  const float cfac = (w.a_split ? 0.00390625f + 3.1e-5f : 0.0078278f) + (float)w.KP * (w.a_split ? 2.f : 1.f) * 9.54e-7f;
   const bool timing = h->timing;
 
   for (int row0 = 0; row0 < n_users; row0 += pass_rows) {
@@ -591,7 +662,7 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     while (n_split > 1 && (size_t)n_split * m_pad > (size_t)w.mp_cap) --n_split;
     const int n_lists = n_split * NSET;
     const int tps = std::max(1, (w.n_tiles + n_split - 1) / n_split);
-    UserSrc src{reinterpret_cast<const float4*>(P_rows ? P_rows : h->tab.P), P_rows ? nullptr : users, row0};
+    UserSrc src{reinterpret_cast<const float4*>(P_rows ? P_rows : h->tab.P), P_rows ? nullptr : users, row0, nullptr};
 
     std::array<cudaEvent_t, 5>* ev = nullptr;
     if (timing) {
@@ -602,13 +673,25 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
       ev = &w.evs[w.ev_used++];
       FR_CUDA(h, cudaEventRecord((*ev)[0], st));
     }
+    const float4* Cat4 = reinterpret_cast<const float4*>(h->tab.Cat);
+    const bool sorted = n_split == 1 && w.n_tiles > 0;      // whole sweeps: sort users by best mask group
+    if (sorted) {
+      const int kgrid = (rows + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
+      if (h->NV == 1) cat_user_key_kernel<1><<<kgrid, FR_THREADS, 0, st>>>(src, rows, Cat4, DV, w.present, w.ukeys);
+      else cat_user_key_kernel<2><<<kgrid, FR_THREADS, 0, st>>>(src, rows, Cat4, DV, w.present, w.ukeys);
+      ++g_launches;
+      FR_CHECK_LAUNCH(h);
+      const int r = radix_sort_pairs(w.sortU, w.ukeys, (uint32_t)rows, nullptr, 4, st, h->sm_count);
+      src.perm = w.sortU.v[r];
+    }
+    int32_t* bf = sorted ? w.block_first : nullptr;
     const int pgrid = (m_pad + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
     if (h->NV == 1)
-      cat_pack_users_kernel<1><<<pgrid, FR_THREADS, 0, st>>>(src, rows, m_pad, reinterpret_cast<const float4*>(h->tab.Cat), DV,
-                                                            w.KP, h->mc.a, h->mc.oma, w.present, w.rmax, cfac, w.A, w.bias, w.margin2);
+      cat_pack_users_kernel<1><<<pgrid, FR_THREADS, 0, st>>>(src, rows, m_pad, Cat4, DV, w.KP, w.a_split, h->mc.a, h->mc.oma, w.present,
+                                                            w.rmax, cfac, w.A, w.bias, w.margin2, bf, BMC);
     else
-      cat_pack_users_kernel<2><<<pgrid, FR_THREADS, 0, st>>>(src, rows, m_pad, reinterpret_cast<const float4*>(h->tab.Cat), DV,
-                                                            w.KP, h->mc.a, h->mc.oma, w.present, w.rmax, cfac, w.A, w.bias, w.margin2);
+      cat_pack_users_kernel<2><<<pgrid, FR_THREADS, 0, st>>>(src, rows, m_pad, Cat4, DV, w.KP, w.a_split, h->mc.a, h->mc.oma, w.present,
+                                                            w.rmax, cfac, w.A, w.bias, w.margin2, bf, BMC);
     ++g_launches;
     FR_CHECK_LAUNCH(h);
     FR_CUDA(h, cudaMemsetAsync(w.cand_cnt, 0, (size_t)n_lists * m_pad * 4, st));
@@ -618,14 +701,18 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
 
     if (w.n_tiles > 0) {
       CUtensorMap tmA;
-      if ((rc = make_tmap(h, &tmA, w.A, (uint64_t)16 * m_pad, w.KP, CAT_BM))) return rc;
+      if ((rc = make_tmap(h, &tmA, w.A, (uint64_t)16 * m_pad, w.a_split ? 2 * w.KP : w.KP, CAT_BM))) return rc;
       CatGemmParams p{};
       p.m_blocks = m_blocks; p.m_pad = m_pad; p.n_rows = rows; p.n_split = n_split; p.tiles_per_split = tps;
-      p.n_tiles = w.n_tiles; p.k_blocks = w.k_blocks; p.K = K;
+      p.n_tiles = w.n_tiles; p.k_blocks = w.k_blocks; p.K = K; p.a_split = w.a_split;
       { const char* dm = getenv("FOODREC_CATALOG_DEBUG"); p.debug_mode = dm ? atoi(dm) : 0; }
       p.tile_group = w.tile_group; p.tile_valid = w.tile_valid; p.bias = w.bias; p.margin2 = w.margin2;
+      p.block_first = bf;
+      p.dbg = getenv("FOODREC_CATALOG_CYCLES") ? w.dbg : nullptr;
+      for (int g = 0; g < 16; ++g) { p.group_lo[g] = w.group_lo[g]; p.group_hi[g] = w.group_hi[g]; p.group_last_valid[g] = w.group_last_valid[g]; }
       p.cand_sc = w.cand_sc; p.cand_row = w.cand_row; p.cand_cnt = w.cand_cnt; p.ovf = w.ovf;
-      launch_catalog_gemm(CG, NSET, h->sm_count, tmA, w.tmB, p, st);
+      p.trash = (size_t)w.mp_cap * 4 * CAT_CAP;
+      launch_catalog_gemm(CG, NSET, w.BN, h->sm_count, tmA, w.tmB, p, st);
       FR_CHECK_LAUNCH(h);
     }
     if (ev) FR_CUDA(h, cudaEventRecord((*ev)[2], st));
@@ -698,11 +785,21 @@ extern "C" int fr_catalog_fallback_rows(fr_handle h, int32_t* out, fr_stream s) 
   return FR_OK;
 }
 
+extern "C" int fr_catalog_cycle_counters(fr_handle h, uint64_t* out /* [8] */, fr_stream s) {
+  if (!h || !out) return FR_ERR_ARG;
+  if (!h->cat || !h->cat->dbg) return fail(h, FR_ERR_STATE, "no catalog pass has run");
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  FR_CUDA(h, cudaMemcpyAsync(out, h->cat->dbg, 64, cudaMemcpyDeviceToHost, st));
+  FR_CUDA(h, cudaMemsetAsync(h->cat->dbg, 0, 64, st));
+  FR_CUDA(h, cudaStreamSynchronize(st));
+  return FR_OK;
+}
+
 extern "C" int fr_catalog_info(fr_handle h, int32_t* out /* [8] */) {
   if (!h || !out) return FR_ERR_ARG;
   if (!h->cat || !h->cat->prepared) return fail(h, FR_ERR_STATE, "fr_catalog_prepare first");
   const CatalogWs& w = *h->cat;
-  out[0] = w.cta_group; out[1] = w.KP; out[2] = w.n_tiles; out[3] = w.present; out[4] = w.n_valid_items;
-  out[5] = w.epi_sets; out[6] = CAT_CAP; out[7] = w.exact_blocks;
+  out[0] = w.cta_group + 10 * w.a_split; out[1] = w.KP; out[2] = w.n_tiles; out[3] = w.present; out[4] = w.n_valid_items;
+  out[5] = w.epi_sets * 1000 + w.BN; out[6] = CAT_CAP; out[7] = w.exact_blocks;
   return FR_OK;
 }

@@ -26,7 +26,7 @@
 namespace fr {
 
 constexpr int CAT_BM = 128;        // user rows per CTA (TMEM lanes)
-constexpr int CAT_BN = 256;        // recipes per tile (TMEM columns per accumulator stage)
+constexpr int CAT_BN_MAX = 256;    // recipes per tile: 256 (2 accumulator stages in TMEM) or 128 (4 stages)
 constexpr int CAT_BK = 64;         // bf16 elements per 128-byte swizzle atom
 constexpr int CAT_KB_MAX = 4;      // D <= 256
 constexpr int CAT_CAP = 512;       // candidate slots per (split, user)
@@ -42,18 +42,25 @@ struct CatGemmParams {
   int m_pad;             // m_blocks * CAT_BM * CG
   int n_rows;            // valid user rows in this pass
   int n_split, tiles_per_split, n_tiles, k_blocks, K;
-  int debug_mode;        // 0 = normal; 1 = epilogue only drains TMEM (pipeline ceiling measurement, results invalid)
+  int a_split;           // 1: A = bf16 head + bf16 tail (two MMAs per B block; needs 2*k_blocks <= CAT_KB_MAX)
+  int debug_mode;        // 0 = normal.  Ceiling measurements (results invalid; env FOODREC_CATALOG_DEBUG): 1 = epilogue only
+                         // drains TMEM, 2 = accumulators never read (TMA+MMA alone), 3 = threshold +inf (filter fast path only)
   const int32_t* tile_group;   // [n_tiles] mask of each tile
   const int32_t* tile_valid;   // [n_tiles] recipes in the tile (256 except a group's last tile)
+  const int32_t* block_first;  // [m_blocks] mask group a user block sweeps first (nullable: natural order)
+  int group_lo[16], group_hi[16];   // tile range of each mask group
+  int group_last_valid[16];         // recipes in the last tile of each group (the others are full)
   const float* bias;           // [16][m_pad]
   const float* margin2;        // [m_pad]  2E
   float* cand_sc;              // [n_split*NSET*m_pad][CAT_CAP] approx total score
   int32_t* cand_row;           // same shape: padded recipe row
   int32_t* cand_cnt;           // [n_split*NSET*m_pad]
   int32_t* ovf;                // [m_pad] 1 = candidate list overflowed
+  unsigned long long* dbg;     // nullable: cycle counters {mma total, wait tempty, wait full, n, epi total, wait tfull, n}
+  size_t trash;                // index of a scratch region (>= blockDim entries) in cand_sc / cand_row
 };
 
-void launch_catalog_gemm(int cta_group, int epi_sets, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
+void launch_catalog_gemm(int cta_group, int epi_sets, int tile_n, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
                          const CatGemmParams& p, cudaStream_t st);
 cudaError_t catalog_gemm_configure();   // opt-in dynamic shared memory for both variants
 

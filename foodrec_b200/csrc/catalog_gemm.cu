@@ -28,12 +28,45 @@
 
 namespace fr {
 
-template <int CG>
+template <int CG, int BN>
 struct CatCfg {
-  static constexpr int B_ROWS = CAT_BN / CG;            // recipe rows this CTA loads per stage
+  static constexpr int B_ROWS = BN / CG;                // recipe rows this CTA loads per stage
   static constexpr int B_STAGE = B_ROWS * CAT_BK * 2;   // bytes
-  static constexpr int NS = CAT_B_TOTAL / B_STAGE;      // 4 (CG=1) / 8 (CG=2)
+  static constexpr int NS = CAT_B_TOTAL / B_STAGE;      // smem ring depth: 4..16
+  static constexpr int NACC = 512 / BN;                 // accumulator stages in TMEM: 2 (BN=256) / 4 (BN=128)
 };
+
+// Sweep order of one user block: the tiles of its first group [lo, hi) come first, then every other
+// tile in natural order (lo == hi: natural order).  Users are sorted by their best mask group
+// (largest category term), so a block starts where its rows' final top-K mostly lives: the
+// running thresholds are tight from the start and later groups almost never push.
+__device__ __forceinline__ int sweep_tile(const int i, const int lo, const int hi) {
+  const int len = hi - lo;
+  if (i < len) return lo + i;
+  const int r = i - len;
+  return r < lo ? r : r + len;
+}
+struct SweepRange { int i0, i1, lo, hi; };
+// mask group of a tile from the 15 group ranges in the kernel parameters (constant bank): the sweep
+// stays inside one group for thousands of tiles, so the range is cached in registers and the
+// per-tile cost is two compares -- no global load sits on the critical path of a tile.
+struct GroupCursor { int g, lo, hi; };
+__device__ __forceinline__ void group_seek(GroupCursor& c, const CatGemmParams& p, const int t) {
+  if (t >= c.lo && t < c.hi) return;
+  for (int g = 1; g < 16; ++g)
+    if (t >= p.group_lo[g] && t < p.group_hi[g]) { c.g = g; c.lo = p.group_lo[g]; c.hi = p.group_hi[g]; return; }
+}
+__device__ __forceinline__ SweepRange sweep_range(const CatGemmParams& p, const int sp, const int mb) {
+  SweepRange r;
+  r.i0 = sp * p.tiles_per_split;
+  r.i1 = min(r.i0 + p.tiles_per_split, p.n_tiles);
+  r.lo = r.hi = 0;
+  if (p.n_split == 1 && p.block_first) {
+    const int g = __ldg(p.block_first + mb);
+    r.lo = p.group_lo[g]; r.hi = p.group_hi[g];
+  }
+  return r;
+}
 
 // Warp-collective compaction of lane L's candidate row: exact K-th largest of its entries by
 // bitwise binary search (warp REDUX per bit), keep everything >= kth - 2E.  Returns lane L's new
@@ -114,6 +147,27 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
   // From here on the compiler may spill / the compaction call may save registers: the prefetched
   // chunk (an asynchronous tcgen05.ld into registers) must have landed before that can happen.
   tc::tmem_ld_wait();
+#if !defined(FR_CAT_REREAD)
+  // votes only (no REDUX / find-first-set / TMEM re-read in the dependency chain): every test is a
+  // warp-uniform predicate, the registers are indexed statically
+#pragma unroll
+  for (int G = 0; G < 4; ++G) {
+    if (__any_sync(FR_FULL, g8[G] >= s.adj)) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float x = v[8 * G + jj];
+        const bool hit = (x >= s.adj) && (col + 8 * G + jj < nvalid);   // zero padding is never a candidate
+        if (__any_sync(FR_FULL, hit)) {
+          if (hit) {                                       // cnt <= CAP - 32 on entry (compaction policy): no bound check
+            __stcg(p.cand_sc + s.base + s.cnt, x + s.bias);
+            __stcg(p.cand_row + s.base + s.cnt, n0 + col + 8 * G + jj);
+            ++s.cnt;
+          }
+        }
+      }
+    }
+  }
+#else
   const uint32_t gm = (g8[0] >= s.adj ? 1u : 0u) | (g8[1] >= s.adj ? 2u : 0u) | (g8[2] >= s.adj ? 4u : 0u) |
                       (g8[3] >= s.adj ? 8u : 0u);
   const uint32_t gmw = __reduce_or_sync(FR_FULL, gm);
@@ -139,6 +193,7 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
       }
     }
   }
+#endif
   uint32_t need = __ballot_sync(FR_FULL, s.cnt > CAT_CAP - 32);
   while (need) {
     const int L = __ffs(need) - 1;
@@ -149,12 +204,13 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
   }
 }
 
-template <int CG, int NSET>
+template <int CG, int NSET, int BN>
 __global__ void __launch_bounds__(128 + 128 * NSET, 1)
 catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const CatGemmParams p) {
-  using C = CatCfg<CG>;
-  constexpr int CW = CAT_BN / NSET;      // accumulator columns per epilogue warp set
+  using C = CatCfg<CG, BN>;
+  constexpr int NACC = C::NACC;
+  constexpr int CW = BN / NSET;      // accumulator columns per epilogue warp set
   constexpr int NCH = CW / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -163,8 +219,8 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + CAT_B_TOTAL);
   uint64_t* empty = full + C::NS;
   uint64_t* tfull = empty + C::NS;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* a_empty = tempty + 2;
+  uint64_t* tempty = tfull + NACC;
+  uint64_t* a_empty = tempty + NACC;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,7 +230,7 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::NS; ++i) { tc::mbar_init(&full[i], CG); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4 * NSET * CG); }
+    for (int i = 0; i < NACC; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4 * NSET * CG); }
     tc::mbar_init(a_empty, 1);
     tc::fence_barrier_init();
   }
@@ -188,58 +244,77 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_units = p.m_blocks * p.n_split;
   const int cluster_id = blockIdx.x / CG, n_clusters = gridDim.x / CG;
   const int kbn = p.k_blocks;
+  const int kan = p.a_split ? 2 * kbn : kbn;     // A blocks resident in shared memory
 
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
     uint32_t stage = 0, phase = 0, a_loads = 0;
     for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
       const int sp = unit / p.m_blocks, mb = unit % p.m_blocks;
-      const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+      const SweepRange sr = sweep_range(p, sp, mb);
       int prev_g = -1;
-      for (int t = t0; t < t1; ++t) {
-        const int g = __ldg(p.tile_group + t);
+      GroupCursor gc{0, 0, 0};
+      for (int i = sr.i0; i < sr.i1; ++i) {
+        const int t = sweep_tile(i, sr.lo, sr.hi);
+        group_seek(gc, p, t);
+        const int g = gc.g;
         const bool loadA = g != prev_g;
         prev_g = g;
         if (loadA) { tc::mbar_wait(a_empty, (a_loads & 1u) ^ 1u); ++a_loads; }   // MMAs of the previous A are done
         for (int kb = 0; kb < kbn; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1u);
           uint32_t bytes = C::B_STAGE;
-          if (loadA && kb == 0) bytes += kbn * CAT_A_BLK;
+          if (loadA && kb == 0) bytes += kan * CAT_A_BLK;
           if (CG == 1) tc::mbar_arrive_expect_tx(&full[stage], bytes);
           else if (leader) tc::mbar_arrive_expect_tx(&full[stage], 2 * bytes);
           else tc::mbar_arrive_cluster(&full[stage], 0);
           if (loadA && kb == 0) {
             const int arow = g * p.m_pad + mb * (CAT_BM * CG) + rank * CAT_BM;
-            for (int k2 = 0; k2 < kbn; ++k2)
+            for (int k2 = 0; k2 < kan; ++k2)      // split operand: blocks [0,kbn) = bf16 head, [kbn,2kbn) = bf16 tail
               tc::tma_load_2d<CG>(sA + k2 * CAT_A_BLK, &tmA, &full[stage], k2 * CAT_BK, arow);
           }
           tc::tma_load_2d<CG>(sB + stage * C::B_STAGE, &tmB, &full[stage], kb * CAT_BK,
-                              t * CAT_BN + (int)rank * C::B_ROWS);
+                              t * BN + (int)rank * C::B_ROWS);
           if (++stage == C::NS) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ================= MMA issuer (one thread of the leader CTA) =================
-    constexpr uint32_t idesc = tc::umma_idesc_bf16(CAT_BM * CG, CAT_BN);
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(CAT_BM * CG, BN);
     uint32_t stage = 0, phase = 0, tcount = 0;
+    long long dbg_tempty = 0, dbg_full = 0;
+    const long long dbg_t0 = clock64();
     for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
-      const int sp = unit / p.m_blocks;
-      const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-      for (int t = t0; t < t1; ++t, ++tcount) {
-        const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
-        const bool a_last = (t + 1 == t1) || (__ldg(p.tile_group + t + 1) != __ldg(p.tile_group + t));
+      const int sp = unit / p.m_blocks, mb = unit % p.m_blocks;
+      const SweepRange sr = sweep_range(p, sp, mb);
+      GroupCursor gc{0, 0, 0};
+      for (int i = sr.i0; i < sr.i1; ++i, ++tcount) {
+        const uint32_t as = tcount % NACC, aph = (tcount / NACC) & 1u;
+        const int t = sweep_tile(i, sr.lo, sr.hi);
+        group_seek(gc, p, t);
+        const int tn = sweep_tile(i + 1, sr.lo, sr.hi);
+        const bool a_last = (i + 1 == sr.i1) || tn < gc.lo || tn >= gc.hi;
+        const long long c0 = p.dbg ? clock64() : 0;
         tc::mbar_wait(&tempty[as], aph ^ 1u);          // epilogue drained this accumulator stage
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + as * CAT_BN;
+        if (p.dbg) dbg_tempty += clock64() - c0;
+        const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < kbn; ++kb) {
+          const long long c1 = p.dbg ? clock64() : 0;
           tc::mbar_wait(&full[stage], phase);
           tc::fence_after_sync();
+          if (p.dbg) dbg_full += clock64() - c1;
           const uint64_t ad = tc::umma_desc_sw128(sA + kb * CAT_A_BLK);
           const uint64_t bd = tc::umma_desc_sw128(sB + stage * C::B_STAGE);
 #pragma unroll
           for (int k = 0; k < CAT_BK / 16; ++k)      // +32 B per k16 step inside the swizzle atom (addr field is >>4)
             tc::mma_bf16<CG>(d_tmem, ad + 2u * k, bd + 2u * k, idesc, (kb | k) ? 1u : 0u);
+          if (p.a_split) {                           // + (A - bf16(A)) . B : the user operand is exact to 2^-16
+            const uint64_t al = tc::umma_desc_sw128(sA + (kbn + kb) * CAT_A_BLK);
+#pragma unroll
+            for (int k = 0; k < CAT_BK / 16; ++k) tc::mma_bf16<CG>(d_tmem, al + 2u * k, bd + 2u * k, idesc, 1u);
+          }
           tc::mma_commit<CG>(&empty[stage]);
           if (kb == kbn - 1) {
             tc::mma_commit<CG>(&tfull[as]);
@@ -248,6 +323,12 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == C::NS) { stage = 0; phase ^= 1u; }
         }
       }
+    }
+    if (p.dbg) {
+      atomicAdd(p.dbg + 0, (unsigned long long)(clock64() - dbg_t0));
+      atomicAdd(p.dbg + 1, (unsigned long long)dbg_tempty);
+      atomicAdd(p.dbg + 2, (unsigned long long)dbg_full);
+      atomicAdd(p.dbg + 3, 1ULL);
     }
   } else if (warp >= 4) {
     // ================= epilogue: running top-K filter =================
@@ -259,26 +340,33 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + e * CW;
     const float INF = __int_as_float(0x7f800000);
     uint32_t tcount = 0;
+    long long dbg_tfull = 0;
+    const long long dbg_e0 = clock64();
     for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
       const int sp = unit / p.m_blocks, mb = unit % p.m_blocks;
-      const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+      const SweepRange sr = sweep_range(p, sp, mb);
       const int grow = mb * (CAT_BM * CG) + (int)rank * CAT_BM + r_in_blk;
       const bool valid = grow < p.n_rows;
       const size_t list = (static_cast<size_t>(sp) * NSET + e) * p.m_pad + grow;
       RowState s;
-      s.base = list * CAT_CAP; s.m2 = __ldg(p.margin2 + grow); s.thr = valid ? -INF : INF; s.cnt = 0; s.bias = 0.f;
+      s.base = list * CAT_CAP; s.m2 = __ldg(p.margin2 + grow); s.thr = (valid && p.debug_mode != 3) ? -INF : INF; s.cnt = 0; s.bias = 0.f;
       s.adj = s.thr; s.ovf = p.ovf + grow;
       int cur_g = -1;
-      for (int t = t0; t < t1; ++t, ++tcount) {
-        const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
-        const int g = __ldg(p.tile_group + t);
-        const int nvalid = __ldg(p.tile_valid + t);     // rows of this tile that hold a recipe
+      GroupCursor gc{0, 0, 0};
+      for (int i = sr.i0; i < sr.i1; ++i, ++tcount) {
+        const uint32_t as = tcount % NACC, aph = (tcount / NACC) & 1u;
+        const int t = sweep_tile(i, sr.lo, sr.hi);
+        group_seek(gc, p, t);
+        const int g = gc.g;
+        const int nvalid = (t == gc.hi - 1) ? p.group_last_valid[g] : BN;     // rows of this tile that hold a recipe
         if (g != cur_g) { cur_g = g; s.bias = __ldg(p.bias + (size_t)g * p.m_pad + grow); }
         s.adj = __fsub_rd(s.thr, s.bias);               // push iff  v + bias >= thr
+        const long long c2 = p.dbg ? clock64() : 0;
         tc::mbar_wait(&tfull[as], aph);
         tc::fence_after_sync();
-        const int n0 = t * CAT_BN;
-        const uint32_t tcol = t_lane + as * CAT_BN;
+        if (p.dbg) dbg_tfull += clock64() - c2;
+        const int n0 = t * BN;
+        const uint32_t tcol = t_lane + as * BN;
         auto release = [&]() {                          // accumulator stage fully read by this warp
           tc::fence_before_sync();
           __syncwarp();
@@ -289,18 +377,18 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float va[32], vb[32];
           __syncwarp();
           tc::tmem_ld_32x32(tcol, va);
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < NCH; c += 2) {            // TMEM load of chunk c+1 is in flight while chunk c is filtered
             tc::tmem_ld_wait();
             __syncwarp();
             if (c + 1 < NCH) tc::tmem_ld_32x32(tcol + (c + 1) * 32, vb);
-            if (p.debug_mode == 0) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
+            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
             else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
             if (c + 1 < NCH) {
               tc::tmem_ld_wait();
               __syncwarp();
               if (c + 2 < NCH) tc::tmem_ld_32x32(tcol + (c + 2) * 32, va);
-              if (p.debug_mode == 0) catalog_filter_chunk(vb, tcol + (c + 1) * 32, e * CW + (c + 1) * 32, nvalid, n0, s, p, lane);
+              if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(vb, tcol + (c + 1) * 32, e * CW + (c + 1) * 32, nvalid, n0, s, p, lane);
               else if (vb[0] + vb[13] + vb[31] == 12345.f) s.cnt++;
             }
           }
@@ -311,13 +399,18 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             tc::tmem_ld_32x32(tcol + c * 32, va);
             tc::tmem_ld_wait();
-            if (p.debug_mode == 0) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
+            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
             else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
           }
         }
         release();                                      // after the last possible re-read of this stage
       }
       if (valid) p.cand_cnt[list] = min(s.cnt, CAT_CAP);
+    }
+    if (p.dbg && lane == 0) {
+      atomicAdd(p.dbg + 4, (unsigned long long)(clock64() - dbg_e0));
+      atomicAdd(p.dbg + 5, (unsigned long long)dbg_tfull);
+      atomicAdd(p.dbg + 6, 1ULL);
     }
   }
 
@@ -327,21 +420,27 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) tc::tmem_dealloc<CG>(tmem_base, 512);
 }
 
-template <int CG, int NSET>
+template <int CG, int NSET, int BN>
 static cudaError_t configure_one() {
-  return cudaFuncSetAttribute(catalog_gemm_kernel<CG, NSET>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAT_SMEM);
+  return cudaFuncSetAttribute(catalog_gemm_kernel<CG, NSET, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAT_SMEM);
+}
+template <int BN>
+static cudaError_t configure_bn() {
+  cudaError_t e;
+  if ((e = configure_one<1, 1, BN>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 1, BN>()) != cudaSuccess) return e;
+  if ((e = configure_one<1, 2, BN>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 2, BN>()) != cudaSuccess) return e;
+  if ((e = configure_one<1, 4, BN>()) != cudaSuccess) return e;
+  return configure_one<2, 4, BN>();
 }
 cudaError_t catalog_gemm_configure() {
-  cudaError_t e;
-  if ((e = configure_one<1, 1>()) != cudaSuccess) return e;
-  if ((e = configure_one<2, 1>()) != cudaSuccess) return e;
-  if ((e = configure_one<1, 2>()) != cudaSuccess) return e;
-  if ((e = configure_one<2, 2>()) != cudaSuccess) return e;
-  if ((e = configure_one<1, 4>()) != cudaSuccess) return e;
-  return configure_one<2, 4>();
+  cudaError_t e = configure_bn<256>();
+  if (e != cudaSuccess) return e;
+  return configure_bn<128>();
 }
 
-template <int CG, int NSET>
+template <int CG, int NSET, int BN>
 static void launch_one(int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB, const CatGemmParams& p, cudaStream_t st) {
   const int n_units = p.m_blocks * p.n_split;
   cudaLaunchConfig_t cfg = {};
@@ -356,21 +455,28 @@ static void launch_one(int sm_count, const CUtensorMap& tmA, const CUtensorMap& 
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
   }
-  cudaLaunchKernelEx(&cfg, catalog_gemm_kernel<CG, NSET>, tmA, tmB, p);
+  cudaLaunchKernelEx(&cfg, catalog_gemm_kernel<CG, NSET, BN>, tmA, tmB, p);
   ++g_launches;
 }
 
-void launch_catalog_gemm(int cta_group, int epi_sets, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                         const CatGemmParams& p, cudaStream_t st) {
+template <int BN>
+static void launch_bn(int cta_group, int epi_sets, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                      const CatGemmParams& p, cudaStream_t st) {
   if (cta_group == 2) {
-    if (epi_sets == 4) launch_one<2, 4>(sm_count, tmA, tmB, p, st);
-    else if (epi_sets == 2) launch_one<2, 2>(sm_count, tmA, tmB, p, st);
-    else launch_one<2, 1>(sm_count, tmA, tmB, p, st);
+    if (epi_sets == 4) launch_one<2, 4, BN>(sm_count, tmA, tmB, p, st);
+    else if (epi_sets == 2) launch_one<2, 2, BN>(sm_count, tmA, tmB, p, st);
+    else launch_one<2, 1, BN>(sm_count, tmA, tmB, p, st);
   } else {
-    if (epi_sets == 4) launch_one<1, 4>(sm_count, tmA, tmB, p, st);
-    else if (epi_sets == 2) launch_one<1, 2>(sm_count, tmA, tmB, p, st);
-    else launch_one<1, 1>(sm_count, tmA, tmB, p, st);
+    if (epi_sets == 4) launch_one<1, 4, BN>(sm_count, tmA, tmB, p, st);
+    else if (epi_sets == 2) launch_one<1, 2, BN>(sm_count, tmA, tmB, p, st);
+    else launch_one<1, 1, BN>(sm_count, tmA, tmB, p, st);
   }
+}
+
+void launch_catalog_gemm(int cta_group, int epi_sets, int tile_n, int sm_count, const CUtensorMap& tmA,
+                         const CUtensorMap& tmB, const CatGemmParams& p, cudaStream_t st) {
+  if (tile_n == 128) launch_bn<128>(cta_group, epi_sets, sm_count, tmA, tmB, p, st);
+  else launch_bn<256>(cta_group, epi_sets, sm_count, tmA, tmB, p, st);
 }
 
 }  // namespace fr

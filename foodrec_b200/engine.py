@@ -263,13 +263,13 @@ class Engine:
         return (ids, rank, sc) if return_scores else (ids, rank)
 
     # ------------------------------------------------------------------ full-catalog top-K
-    def catalog_prepare(self, cta_group=0, max_pass_rows=0, splits=0, epi_sets=0):
+    def catalog_prepare(self, cta_group=0, max_pass_rows=0, splits=0, epi_sets=0, tile_n=0, a_split=0):
         """Build the recipe-side index of the catalog kernel from the current R / item_cats
         (call again after training changed R).  Synchronises."""
         if self.item_cats is None:
             raise L.FoodRecError("catalog scoring needs the item_cats (dish_to_category) table")
         self.flush()
-        o = L.fr_catalog_opts(int(cta_group), int(max_pass_rows), int(splits), int(epi_sets))
+        o = L.fr_catalog_opts(int(cta_group), int(max_pass_rows), int(splits), int(epi_sets), int(tile_n), int(a_split))
         L.check(self.handle, self.lib.fr_catalog_prepare(self.handle, C.byref(o), self._stream()))
         self._catalog_ready = True
 
@@ -313,6 +313,17 @@ class Engine:
         n = C.c_int64()
         L.check(self.handle, self.lib.fr_catalog_timing_read(self.handle, ms, C.byref(n), int(bool(reset))))
         return dict(zip(("user_operand", "gemm_filter", "rerank", "exact_fallback"), list(ms))), n.value
+
+    def catalog_cycle_counters(self):
+        v = (C.c_uint64 * 8)()
+        L.check(self.handle, self.lib.fr_catalog_cycle_counters(self.handle, v, self._stream()))
+        v = list(v)
+        out = {}
+        if v[3]:
+            out.update(mma_cycles=v[0] / v[3], mma_wait_accumulator=v[1] / v[3], mma_wait_operands=v[2] / v[3])
+        if v[6]:
+            out.update(epilogue_cycles=v[4] / v[6], epilogue_wait_accumulator=v[5] / v[6])
+        return out
 
     def catalog_fallback_rows(self):
         v = C.c_int32()

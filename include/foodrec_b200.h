@@ -207,7 +207,10 @@ typedef struct {
   int32_t cta_group;      /* 0 = default (2: CTA pairs, tcgen05 cta_group::2), 1 = single-CTA MMA */
   int32_t max_pass_rows;  /* 0 = default; users processed per pass */
   int32_t splits;         /* 0 = auto; pieces the recipe sweep is cut into for small user counts */
-  int32_t epi_sets;       /* 0 = default (2); 1, 2 or 4 epilogue warp sets (each owns 256/sets accumulator columns) */
+  int32_t epi_sets;       /* 0 = default (2); 1, 2 or 4 epilogue warp sets (each owns tile_n/sets accumulator columns) */
+  int32_t tile_n;         /* 0 = default (256: 2 accumulator stages in TMEM); 128: 4 stages */
+  int32_t a_split;        /* 0 = default: user operand as bf16 head + tail (two MMAs per recipe block, halves the
+                             filter's error bound) when D <= 128; 1 = single bf16 operand */
 } fr_catalog_opts;
 int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_stream s);
 /* Query rows: P_rows != NULL -> dense device rows [n_users,5,D] (e.g. all-gathered from the user
@@ -225,6 +228,10 @@ int fr_catalog_merge(fr_handle h, const int32_t* ids, const double* scores, int3
 int fr_catalog_timing_read(fr_handle h, double* ms_sum /* [4] */, int64_t* n_passes, int32_t reset);
 /* {cta_group, padded K, tiles, present-mask bits, recipes with a category, epilogue sets, list capacity, fallback blocks} */
 int fr_catalog_info(fr_handle h, int32_t* out /* [8] */);
+/* in-kernel cycle counters of the GEMM kernel (collected while the environment variable
+ * FOODREC_CATALOG_CYCLES is set): {MMA thread total, waiting for a free accumulator, waiting for
+ * operands, #MMA threads, epilogue warp total, waiting for an accumulator, #epilogue warps, 0}; resets. */
+int fr_catalog_cycle_counters(fr_handle h, uint64_t* out /* [8] */, fr_stream s);
 /* rows of the LAST pass that took the exact full-scan fallback (synchronises the stream) */
 int fr_catalog_fallback_rows(fr_handle h, int32_t* out, fr_stream s);
 

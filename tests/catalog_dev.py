@@ -13,13 +13,13 @@ from oracle import evaluate_oracle, synth  # noqa: E402
 from oracle.recommender_oracle import Hyper as OHyper, OracleModel  # noqa: E402
 
 
-def run(cg, U, I, D, K, splits=0, sets=0, seed=7, check=True):
+def run(cg, U, I, D, K, splits=0, sets=0, tn=0, asp=0, seed=7, check=True):
     from foodrec_b200 import Engine, Hyper
     tb = synth.make_tables(U, I, 9, D, seed=seed)
     ic = synth.make_item_categories(I, seed=seed + 1)
     e = Engine(Hyper(), tb.P, tb.R, tb.Cat, tb.G, max_rows=256, item_cats=ic)
     t0 = time.time()
-    e.catalog_prepare(cta_group=cg, splits=splits, epi_sets=sets)
+    e.catalog_prepare(cta_group=cg, splits=splits, epi_sets=sets, tile_n=tn, a_split=asp)
     torch.cuda.synchronize()
     t1 = time.time()
     e.timing_enable(True)
@@ -50,10 +50,11 @@ if __name__ == "__main__":
         ok = run(*a)
     else:
         ok = True
-        for cg in (1, 2):
+        for cg, tn, asp in ((1, 256, 0), (2, 256, 0), (2, 128, 0), (2, 256, 1)):
             for sets in (1, 2, 4):
-                ok &= run(cg, 300, 3000, 64, 10, sets=sets)
-                ok &= run(cg, 300, 5000, 128, 100, sets=sets)
-                ok &= run(cg, 1000, 20000, 128, 100, splits=3, sets=sets)
+                ok &= run(cg, 300, 3000, 64, 10, sets=sets, tn=tn, asp=asp)
+                ok &= run(cg, 300, 5000, 128, 100, sets=sets, tn=tn, asp=asp)
+                ok &= run(cg, 1000, 20000, 128, 100, splits=3, sets=sets, tn=tn, asp=asp)
+                ok &= run(cg, 700, 9000, 128, 50, splits=1, sets=sets)      # whole sweeps: users sorted by best group
     print("OK" if ok else "FAILED")
     sys.exit(0 if ok else 1)

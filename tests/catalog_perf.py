@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import synth_data as synth  # noqa: E402
 
 
-def run(cg, U, I, D, K, reps=3, sets=0, seed=11):
+def run(cg, U, I, D, K, reps=3, sets=0, tn=0, asp=0, seed=11):
     from foodrec_b200 import Engine, Hyper
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev); g.manual_seed(seed)
@@ -22,17 +22,20 @@ def run(cg, U, I, D, K, reps=3, sets=0, seed=11):
     ic = synth.make_item_categories(I, seed=seed + 1)
     e = Engine(Hyper(), P, R, Cat, G, max_rows=256, item_cats=ic)
     del P, R
-    e.catalog_prepare(cta_group=cg, epi_sets=sets)
+    e.catalog_prepare(cta_group=cg, epi_sets=sets, tile_n=tn, a_split=asp)
     info = e.catalog_info()
     e.timing_enable(True)
     for r in range(reps):
+        if os.environ.get("FOODREC_CATALOG_CYCLES") and r: e.catalog_cycle_counters()
         torch.cuda.synchronize(); t0 = time.time()
         ids, sc = e.catalog_topk(K=K)
         torch.cuda.synchronize(); t1 = time.time()
         ms, npass = e.catalog_timing_read()
-        flop = 2.0 * U * info["tiles"] * 256 * info["k_padded"]
+        flop = 2.0 * U * info["tiles"] * (info["epi_sets"] % 1000) * info["k_padded"] * (2 if info["cta_group"] >= 10 else 1)
         print(f"cg={cg} U={U} I={I} D={D} K={K} rep{r}: wall {1e3 * (t1 - t0):.2f} ms  phases {dict((k, round(v, 3)) for k, v in ms.items())} passes={npass} "
               f"gemm {flop / ms['gemm_filter'] / 1e9:.1f} TFLOP/s executed; users/s {U / (t1 - t0):.0f}", flush=True)
+    if os.environ.get("FOODREC_CATALOG_CYCLES"):
+        print("cycles:", {k: round(v / 1e6, 2) for k, v in e.catalog_cycle_counters().items()}, "(M cycles, last rep)", flush=True)
     print("fallback rows in last pass:", e.catalog_fallback_rows(), flush=True)
     # spot check a few users against a torch fp64 full scan (dev check only)
     ic_d = torch.as_tensor(ic, device=dev, dtype=torch.float64)
