@@ -376,7 +376,29 @@ __device__ __forceinline__ unsigned long long dkey(double d) {
 
 constexpr int EX_THREADS = 1024;
 
-__global__ void __launch_bounds__(EX_THREADS) cat_exact_kernel(const FinParams f, int I, double* __restrict__ scratch) {
+// Phase A of the parallel fallback: exact scores of EVERY recipe for up to gridDim.y fallback rows
+// [slot0, slot0 + gridDim.y), spread over the whole GPU (blockIdx.x = recipe slice).
+constexpr int EXS_THREADS = 256, EXS_ITEMS = 4096;
+__global__ void __launch_bounds__(EXS_THREADS) cat_exact_scores_kernel(const FinParams f, int I, int slot0,
+                                                                      double* __restrict__ scratch) {
+  __shared__ float sP[5 * 256];
+  __shared__ double sH[4];
+  const int slot = slot0 + blockIdx.y;
+  if (slot >= min(*f.ovf_count, f.m_pad)) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  load_user_exact(user_row(f.src, f.ovf_list[slot], f.D / 4), f.Cat, f.D, sP, sH, tid, EXS_THREADS);
+  double* sc = scratch + (size_t)blockIdx.y * I;
+  const int i0 = blockIdx.x * EXS_ITEMS, i1 = min(I, i0 + EXS_ITEMS);
+  for (int item = i0 + warp; item < i1; item += EXS_THREADS / 32) {
+    const double s = exact_score_warp(sP, sH, f.R + (size_t)item * f.D, __ldg(f.item_cats + item), f.D, lane, f.a, f.oma);
+    if (lane == 0) sc[item] = s;
+  }
+}
+
+// Phase B (scores_ready: one block per row of the round, scores in scratch[blockIdx.x]) or the
+// self-contained tail (one block scores and selects row after row: complete but slow).
+__global__ void __launch_bounds__(EX_THREADS) cat_exact_kernel(const FinParams f, int I, double* __restrict__ scratch,
+                                                               int slot0, int scores_ready) {
   __shared__ float sP[5 * 256];
   __shared__ double sH[4];
   __shared__ unsigned hist[256];
@@ -388,13 +410,15 @@ __global__ void __launch_bounds__(EX_THREADS) cat_exact_kernel(const FinParams f
   double* sc = scratch + (size_t)blockIdx.x * I;
   const int n_ov = min(*f.ovf_count, f.m_pad);
   const int Keff = min(f.K, I);
-  for (int slot = blockIdx.x; slot < n_ov; slot += gridDim.x) {
+  for (int slot = slot0 + blockIdx.x; slot < n_ov; slot += scores_ready ? (1 << 30) : gridDim.x) {
     const int row = f.ovf_list[slot];
     __syncthreads();
-    load_user_exact(user_row(f.src, row, f.D / 4), f.Cat, f.D, sP, sH, tid, EX_THREADS);
-    for (int item = warp; item < I; item += EX_THREADS / 32) {
-      const double s = exact_score_warp(sP, sH, f.R + (size_t)item * f.D, __ldg(f.item_cats + item), f.D, lane, f.a, f.oma);
-      if (lane == 0) sc[item] = s;
+    if (!scores_ready) {
+      load_user_exact(user_row(f.src, row, f.D / 4), f.Cat, f.D, sP, sH, tid, EX_THREADS);
+      for (int item = warp; item < I; item += EX_THREADS / 32) {
+        const double s = exact_score_warp(sP, sH, f.R + (size_t)item * f.D, __ldg(f.item_cats + item), f.D, lane, f.a, f.oma);
+        if (lane == 0) sc[item] = s;
+      }
     }
     __syncthreads();
     // radix select of the Keff-th largest 64-bit key
@@ -540,7 +564,7 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_s
   if (w.I != I) {
     if (w.I != 0) return fail(h, FR_ERR_STATE, "catalog index was built for %d recipes", w.I);
     w.I = I; w.KP = KP; w.k_blocks = KP / CAT_BK;
-    w.tiles_cap = (I + 127) / 128 + 15;          // sized for the narrow tile
+    w.tiles_cap = (I + 16 * CAT_BN_MAX) / 128 + 1;   // every mask group pads its last tile: <= 15 * 255 extra rows; sized in narrow tiles
     if ((rc = dalloc(h, &w.keys, (size_t)I))) return rc;
     if ((rc = alloc_sort(h, w.sortM, (size_t)I))) return rc;
     if ((rc = dalloc(h, &w.gs_dev, 17))) return rc;
@@ -729,7 +753,17 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     ++g_launches;
     FR_CHECK_LAUNCH(h);
     if (ev) FR_CUDA(h, cudaEventRecord((*ev)[3], st));
-    cat_exact_kernel<<<w.exact_blocks, EX_THREADS, 0, st>>>(f, w.I, w.scratch);
+    // Rows the filter gave up on (massive ties): a few rounds of whole-GPU exact scoring + one-block
+    // selection per row, then a self-contained tail for anything beyond (blocks exit at once when
+    // there is nothing to do -- the common case).
+    constexpr int EX_ROUNDS = 4;
+    const int xs = (w.I + EXS_ITEMS - 1) / EXS_ITEMS;
+    for (int r = 0; r < EX_ROUNDS; ++r) {
+      cat_exact_scores_kernel<<<dim3(xs, w.exact_blocks), EXS_THREADS, 0, st>>>(f, w.I, r * w.exact_blocks, w.scratch);
+      cat_exact_kernel<<<w.exact_blocks, EX_THREADS, 0, st>>>(f, w.I, w.scratch, r * w.exact_blocks, 1);
+      g_launches += 2;
+    }
+    cat_exact_kernel<<<w.exact_blocks, EX_THREADS, 0, st>>>(f, w.I, w.scratch, EX_ROUNDS * w.exact_blocks, 0);
     ++g_launches;
     FR_CHECK_LAUNCH(h);
     if (ev) FR_CUDA(h, cudaEventRecord((*ev)[4], st));

@@ -372,6 +372,11 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) { if (CG == 1) tc::mbar_arrive(&tempty[as]); else tc::mbar_arrive_cluster(&tempty[as], 0); }
         };
+#if defined(FR_CAT_REREAD)
+        auto release_early = [&]() {};
+#else
+        auto release_early = release;                   // the accumulator is in registers once its last load has landed
+#endif
         if (p.debug_mode == 2) { release(); continue; }     // MMA/TMA ceiling: accumulators are never read
         if constexpr (NSET <= 2) {
           float va[32], vb[32];
@@ -381,13 +386,13 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int c = 0; c < NCH; c += 2) {            // TMEM load of chunk c+1 is in flight while chunk c is filtered
             tc::tmem_ld_wait();
             __syncwarp();
-            if (c + 1 < NCH) tc::tmem_ld_32x32(tcol + (c + 1) * 32, vb);
+            if (c + 1 < NCH) tc::tmem_ld_32x32(tcol + (c + 1) * 32, vb); else release_early();
             if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
             else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
             if (c + 1 < NCH) {
               tc::tmem_ld_wait();
               __syncwarp();
-              if (c + 2 < NCH) tc::tmem_ld_32x32(tcol + (c + 2) * 32, va);
+              if (c + 2 < NCH) tc::tmem_ld_32x32(tcol + (c + 2) * 32, va); else release_early();
               if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(vb, tcol + (c + 1) * 32, e * CW + (c + 1) * 32, nvalid, n0, s, p, lane);
               else if (vb[0] + vb[13] + vb[31] == 12345.f) s.cnt++;
             }
@@ -399,11 +404,14 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             tc::tmem_ld_32x32(tcol + c * 32, va);
             tc::tmem_ld_wait();
+            if (c == NCH - 1) release_early();
             if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
             else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
           }
         }
+#if defined(FR_CAT_REREAD)
         release();                                      // after the last possible re-read of this stage
+#endif
       }
       if (valid) p.cand_cnt[list] = min(s.cnt, CAT_CAP);
     }
