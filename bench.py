@@ -37,6 +37,64 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["bf16_tflops"]), float(j["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops burst / sustained)"
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s burst, ~1.4 sustained)"
+
+
+def bench_catalog(eng, dev, label, n_users, K=100, reps=2):
+    """Full-catalog top-K users/s (fr_catalog_topk): device-timed with resident inputs, per-phase CUDA
+    events from inside the library, and end to end from a pinned host user list to host ids."""
+    import torch
+    eng.catalog_prepare()
+    info = eng.catalog_info()
+    tile_n, sets, split = info["epi_sets"] % 1000, info["epi_sets"] // 1000, info["cta_group"] >= 10
+    eng.timing_enable(True)
+    eng.catalog_topk(n_users=n_users, K=K)                         # warm-up (workspace allocation, code load)
+    torch.cuda.synchronize(); eng.catalog_timing_read()
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ids, sc = eng.catalog_topk(n_users=n_users, K=K); e1.record(); torch.cuda.synchronize()
+        ph, passes = eng.catalog_timing_read()
+        ms = e0.elapsed_time(e1)
+        if best is None or ms < best[0]:
+            best = (ms, ph, passes)
+    ms, ph, passes = best
+    fallback = eng.catalog_fallback_rows()
+    eng.timing_enable(False)
+    # e2e: pinned host user ids -> device, top-K, ids back to pinned host memory
+    hu = torch.arange(n_users, dtype=torch.int32).pin_memory()
+    hout = torch.empty((n_users, K), dtype=torch.int32).pin_memory()
+    du = torch.empty(n_users, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    du.copy_(hu, non_blocking=True)
+    ids = eng.catalog_topk(users=du, K=K, return_scores=False)
+    hout.copy_(ids, non_blocking=True)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    burst, sustained, src = tensor_peaks()
+    executed = 2.0 * n_users * info["tiles"] * tile_n * info["k_padded"] * (2 if split else 1)
+    dense = 2.0 * n_users * eng.I * 5 * eng.D                     # SURVEY 8(d): the K=5D contraction this replaces
+    gemm_s = ph["gemm_filter"] * 1e-3
+    return {
+        "metric": "catalog_topk_users_per_sec", "workload": label, "value": n_users / (ms * 1e-3), "unit": "users/s",
+        "users": n_users, "recipes": eng.I, "K": K, "ms": ms, "passes": passes, "phases_ms": ph, "fallback_rows": fallback,
+        "kernel": {"cta_group": info["cta_group"] % 10, "epilogue_sets": sets, "tile_n": tile_n, "k_padded": info["k_padded"],
+                   "split_user_operand": bool(split), "tiles": info["tiles"]},
+        "roofline": {"bound": "tensor", "kernel": "catalog_gemm_kernel", "achieved": executed / gemm_s / 1e12, "peak": sustained,
+                     "unit": "TFLOP/s", "frac": executed / gemm_s / 1e12 / sustained, "peak_burst": burst, "peak_source": src,
+                     "traffic": None, "flop_per_launch_executed": executed, "ms_per_launch": ph["gemm_filter"] / max(passes, 1),
+                     "dense_equivalent_tflops": dense / gemm_s / 1e12,
+                     "note": "executed = bf16 MMA flops issued (mask-grouped K=D contraction, x2 for the split user operand); "
+                             "dense_equivalent = SURVEY 8(d)'s 2*U*I*5D over the same time"},
+        "e2e": {"value": n_users / dt, "unit": "users/s", "h2d_bytes": 4 * n_users, "d2h_bytes": 4 * n_users * K,
+                "feed": "user ids from pinned host memory, top-K ids back to pinned host memory"},
+    }
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -168,6 +226,23 @@ def cpu_baseline_leg(cfg, B, budget_steps=3):
             "sample": "failed: " + out.stderr[-300:]}
 
 
+def cpu_catalog_leg(cfg, K=100, n_users=512):
+    """CPU side of the catalog metric: the oracle's catalog_topk (float32 GEMM form on all host
+    cores via BLAS + per-user lexsort) on a bounded sample of users over the full recipe table."""
+    from oracle import evaluate_oracle
+    from oracle.recommender_oracle import Hyper, OracleModel
+    import synth_data as synth
+    I, D = cfg["I"], cfg["D"]
+    tb = synth.make_tables(n_users, I, 2, D, seed=3)
+    ic = synth.make_item_categories(I)
+    om = OracleModel(tb.P, tb.R, tb.Cat, tb.G, Hyper(), dtype=np.float32)
+    t0 = time.perf_counter()
+    evaluate_oracle.catalog_topk(om, np.arange(n_users), ic, K, dtype=np.float32)
+    dt = time.perf_counter() - t0
+    return {"value": n_users / dt, "unit": "users/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+            "sample": f"{n_users} users x {I} recipes, K={K}, float32 (oracle/evaluate_oracle.catalog_topk)"}
+
+
 # ----------------------------------------------------------------------------- GPU arm, N > 1
 def run_sharded(args, cfg, B):
     """N GPUs of one node, one process per GPU: tables row-sharded (P by user % N, R by
@@ -242,11 +317,29 @@ def run_sharded(args, cfg, B):
         loss = float(out[L.FR_OUT_LOSS])                      # D2H + sync
     dist.barrier(); torch.cuda.synchronize()
     t = torch.tensor([time.perf_counter() - t0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+    # ---- item-sharded full-catalog top-100: n_q query users PER GPU (weak scaling), recipes sharded by id % N:
+    # all-gather of the query rows, per-shard tcgen05 top-K, all-to-all of the lists, exact merge
+    catalog = None
+    if not args.no_catalog:
+        n_q = min(18_944, Ul)
+        eng.catalog_prepare()
+        ul = torch.arange(n_q, dtype=torch.int32, device=dev)
+        run.catalog_topk(ul, K=100)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        c0.record(); cid, csc = run.catalog_topk(ul, K=100); c1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([c0.elapsed_time(c1)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); cms = float(t.item())
+        catalog = {"metric": "catalog_topk_users_per_sec", "value": world * n_q / (cms * 1e-3), "unit": "users/s",
+                   "workload": f"{n_q} query users per GPU x {I} recipes sharded by id % {world}, D={D}, K=100",
+                   "ms": cms, "fallback_rows_rank0": eng.e.catalog_fallback_rows(),
+                   "exchange_bytes_per_gpu": {"all_gather_rows": (world - 1) * n_q * 5 * D * 4,
+                                              "all_to_all_lists": (world - 1) * n_q * 100 * 12}}
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32", "data": "synthetic", "catalog_topk": catalog,
             "config": {"workload": workload_name(cfg, B) + f" PER GPU (global batch {world * B})", "batch_triples": B,
                        "optimizer": (f"adam (TF-1.x semantics, {args.adam_mode})" if args.learner.lower() == "adam" else args.learner),
                        "l2": "per-step working set >> 126 MB L2; 8 distinct batches cycled", "preroll_steps": args.preroll,
@@ -388,6 +481,26 @@ def run_ours(args, cfg, B):
     eval_ms = e0.elapsed_time(e1)
     eval_alg = NU * (20 * D + 51 * 4 * D + 51 * 12)
 
+    # ---- full-catalog top-100 users/s (tcgen05 GEMM + fused top-K filter): every user of cfg2, then a
+    # cfg4-shaped sample (10M recipes) on fresh tables
+    catalog = []
+    if not args.no_catalog:
+        launches_c0 = eng.lib.fr_launch_count()
+        catalog.append(bench_catalog(eng, dev, f"cfg2: all {U} users x {I} recipes, D={D}, K=100", U))
+        if not args.small:
+            eng.close()
+            del eng
+            torch.cuda.empty_cache()
+            I4, U4 = 10_000_000, 75_776
+            g4 = torch.Generator(device=dev); g4.manual_seed(4)
+            e4 = Engine(Hyper(learner="sgd"), torch.randn((U4, 5, D), device=dev, generator=g4) * 0.1,
+                        torch.randn((I4, D), device=dev, generator=g4) * 0.1, Cat, G, device=dev, max_rows=256,
+                        item_cats=synth.make_item_categories(I4))
+            catalog.append(bench_catalog(e4, dev, f"cfg4 sample: {U4} of 1M users x {I4} recipes, D={D}, K=100 "
+                                                  "(one pass = 4 waves of user blocks; cfg4 = 13.2 such passes per GPU)", U4))
+            eng = e4
+        catalog_launches = eng.lib.fr_launch_count() - launches_c0
+
     if rank == 0:
         cpu = cpu_baseline_leg(cfg, B) if (world == 1 and not args.no_cpu) else None
         line = {
@@ -412,6 +525,11 @@ def run_ours(args, cfg, B):
                                   "frac": eval_alg / (eval_ms * 1e-3) / 1e9 / peak}},
             "uniq_users_per_step": uniq_users, "uniq_items_per_step": uniq_items,
         }
+        if catalog:
+            if world == 1 and not args.no_cpu:
+                catalog[0]["cpu_baseline"] = cpu_catalog_leg(cfg)
+            line["catalog_topk"] = catalog
+            line["catalog_gpu_launches"] = int(catalog_launches)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -429,6 +547,7 @@ def main():
     ap.add_argument("--preroll", type=int, default=40)
     ap.add_argument("--small", action="store_true", help="tiny tables: harness check only, not a bench number")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-catalog", action="store_true", help="skip the full-catalog top-K legs")
     ap.add_argument("--learner", default="adam", help="adam (reference default) | adagrad | rmsprop | sgd")
     ap.add_argument("--adam-mode", default="lazy", choices=["lazy", "lazy_exact", "dense"])
     args = ap.parse_args()

@@ -22,6 +22,7 @@ struct CatalogWs {
   uint32_t* keys = nullptr; SortBufs sortM; int32_t* gs_dev = nullptr;
   __nv_bfloat16* Bq = nullptr; int32_t *row_item = nullptr, *tile_group = nullptr, *tile_valid = nullptr, *tile_pos = nullptr;
   float* rmax = nullptr;
+  const float4* item_cats = nullptr;      // [I,4] masks of THIS table's recipes (tables.item_cats unless overridden)
   int tiles_cap = 0;
   CUtensorMap tmB;
   // per-pass workspace
@@ -548,16 +549,19 @@ void catalog_free(fr_ctx* h) {
   h->cat = nullptr;
 }
 
-extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_stream s) {
+extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, const float* item_cats, fr_stream s) {
   if (!h) return FR_ERR_ARG;
   if (!h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
-  if (!h->tab.item_cats) return fail(h, FR_ERR_STATE, "catalog scoring needs tables.item_cats (dish_to_category)");
+  if (!item_cats) item_cats = h->tab.item_cats;
+  if (!item_cats) return fail(h, FR_ERR_STATE, "catalog scoring needs the recipes' category masks (dish_to_category)");
+  if ((uintptr_t)item_cats & 15) return fail(h, FR_ERR_ARG, "item_cats must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(s);
   cudaDeviceProp prop;
   FR_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
   if (prop.major != 10) return fail(h, FR_ERR_UNSUPPORTED, "catalog scoring is tcgen05 code: needs sm_100, device is sm_%d%d", prop.major, prop.minor);
   if (!h->cat) h->cat = new CatalogWs();
   CatalogWs& w = *h->cat;
+  w.item_cats = reinterpret_cast<const float4*>(item_cats);
   const int I = h->cfg.num_items, D = h->mc.D, DV = h->mc.DV;
   const int KP = (D + CAT_BK - 1) / CAT_BK * CAT_BK;
   int rc;
@@ -585,7 +589,7 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_s
   w.epi_sets = (opts && (opts->epi_sets == 1 || opts->epi_sets == 2 || opts->epi_sets == 4)) ? opts->epi_sets : 2;
   w.force_splits = (opts && opts->splits > 0) ? std::min(opts->splits, CAT_LISTS_MAX / w.epi_sets) : 0;
 
-  cat_mask_kernel<<<(I + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(h->tab.item_cats), I, w.keys);
+  cat_mask_kernel<<<(I + 255) / 256, 256, 0, st>>>(w.item_cats, I, w.keys);
   ++g_launches;
   FR_CHECK_LAUNCH(h);
   const int r = radix_sort_pairs(w.sortM, w.keys, (uint32_t)I, nullptr, 4, st, h->sm_count);
@@ -742,7 +746,7 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     if (ev) FR_CUDA(h, cudaEventRecord((*ev)[2], st));
 
     FinParams f{};
-    f.src = src; f.R = h->tab.R; f.Cat = h->tab.Cat; f.item_cats = reinterpret_cast<const float4*>(h->tab.item_cats);
+    f.src = src; f.R = h->tab.R; f.Cat = h->tab.Cat; f.item_cats = w.item_cats;
     f.row_item = w.row_item; f.D = D; f.n_rows = rows; f.m_pad = m_pad; f.n_split = n_lists; f.K = K;
     f.a = (double)h->mc.a; f.oma = (double)h->mc.oma;
     f.margin2 = w.margin2; f.cand_sc = w.cand_sc; f.cand_row = w.cand_row; f.cand_cnt = w.cand_cnt;

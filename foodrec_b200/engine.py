@@ -263,14 +263,20 @@ class Engine:
         return (ids, rank, sc) if return_scores else (ids, rank)
 
     # ------------------------------------------------------------------ full-catalog top-K
-    def catalog_prepare(self, cta_group=0, max_pass_rows=0, splits=0, epi_sets=0, tile_n=0, a_split=0):
+    def catalog_prepare(self, cta_group=0, max_pass_rows=0, splits=0, epi_sets=0, tile_n=0, a_split=0, item_cats=None):
         """Build the recipe-side index of the catalog kernel from the current R / item_cats
-        (call again after training changed R).  Synchronises."""
-        if self.item_cats is None:
+        (call again after training changed R).  ``item_cats`` [I,4]: the masks of THIS table's
+        rows when the resident table is a global map (row-sharded engines).  Synchronises."""
+        if item_cats is not None:
+            self._catalog_cats = torch.as_tensor(np.asarray(item_cats, np.float32).reshape(-1, 4)).to(self.device).contiguous()
+            assert self._catalog_cats.shape[0] == self.I
+        elif self.item_cats is None:
             raise L.FoodRecError("catalog scoring needs the item_cats (dish_to_category) table")
+        else:
+            self._catalog_cats = None
         self.flush()
         o = L.fr_catalog_opts(int(cta_group), int(max_pass_rows), int(splits), int(epi_sets), int(tile_n), int(a_split))
-        L.check(self.handle, self.lib.fr_catalog_prepare(self.handle, C.byref(o), self._stream()))
+        L.check(self.handle, self.lib.fr_catalog_prepare(self.handle, C.byref(o), _ptr(self._catalog_cats), self._stream()))
         self._catalog_ready = True
 
     def catalog_topk(self, users=None, K=100, P_rows=None, n_users=None, id_mul=1, id_add=0, return_scores=True):

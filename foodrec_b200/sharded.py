@@ -158,6 +158,29 @@ class ShardedEngine:
         return e.out
 
 
+    # full-catalog top-K, item-sharded -------------------------------------------
+    def catalog_prepare(self, **opts):
+        """Index of THIS rank's recipe shard (local row k = recipe rank + k*W; rows past the
+        catalog end carry no category and are never returned)."""
+        e = self.e
+        cats = e.item_cats.cpu().numpy() if e.item_cats is not None else None
+        if cats is None:
+            raise L.FoodRecError("catalog scoring needs the global item_cats map")
+        e.catalog_prepare(item_cats=shard_rows(cats, self.rank, self.world), **opts)
+
+    def catalog_query_rows(self, users_local):
+        """This rank's query users as dense [n,5,D] rows (what the all-gather moves)."""
+        self.e.flush()
+        return self.e.P[self.e._i32(users_local).long()].contiguous()
+
+    def catalog_local(self, P_rows_all, K):
+        """Top-K of THIS rank's recipe shard for every gathered query row, ids global."""
+        return self.e.catalog_topk(P_rows=P_rows_all, K=K, id_mul=self.world, id_add=self.rank)
+
+    def catalog_merge(self, ids, scores):
+        return self.e.catalog_merge(ids, scores)
+
+
 # ---------------------------------------------------------------------------- runners
 class DistRunner:
     """This process is rank `dist.get_rank()`; NCCL (or gloo on CPU tensors in tests)."""
@@ -178,6 +201,23 @@ class DistRunner:
         g.update(write_personal)
         d.all_to_all_single(g.rgrows, g.grows)           # finished gradient rows -> owners
         return g.apply()
+
+
+    def catalog_topk(self, users_local, K=100):
+        """Item-sharded full-catalog top-K for this rank's ``users_local`` (same count on every rank):
+        all-gather of the query rows, local top-K per recipe shard, all-to-all of the (id, score)
+        lists back to the user owners, exact merge.  Returns ids int32 [n,K], scores float64 [n,K]."""
+        d, g = self.dist, self.eng
+        W = g.world
+        rows = g.catalog_query_rows(users_local)
+        n = rows.shape[0]
+        allrows = torch.empty((W * n,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        d.all_gather_into_tensor(allrows, rows)
+        ids, sc = g.catalog_local(allrows, K)                 # [W*n, K]: block s = users of rank s
+        rid, rsc = torch.empty_like(ids), torch.empty_like(sc)
+        d.all_to_all_single(rid, ids)                         # block w <- rank w's list for MY users
+        d.all_to_all_single(rsc, sc)
+        return g.catalog_merge(rid.view(W, n, K), rsc.view(W, n, K))
 
 
 class LocalRunner:
@@ -206,3 +246,18 @@ class LocalRunner:
         for g in self.engs: g.update(write_personal)
         self._all_to_all("grows", "rgrows")
         return [g.apply() for g in self.engs]
+
+    def catalog_topk(self, users_local_per_rank, K=100):
+        """Same protocol as DistRunner.catalog_topk with the collectives as tensor shuffles."""
+        W = self.W
+        rows = [g.catalog_query_rows(u) for g, u in zip(self.engs, users_local_per_rank)]
+        n = rows[0].shape[0]
+        assert all(r.shape[0] == n for r in rows)
+        allrows = torch.cat(rows, 0)
+        lists = [g.catalog_local(allrows, K) for g in self.engs]          # per recipe shard: [W*n, K]
+        out = []
+        for r, g in enumerate(self.engs):
+            ids = torch.stack([lists[w][0][r * n:(r + 1) * n] for w in range(W)])
+            sc = torch.stack([lists[w][1][r * n:(r + 1) * n] for w in range(W)])
+            out.append(g.catalog_merge(ids, sc))
+        return out

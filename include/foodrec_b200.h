@@ -212,7 +212,9 @@ typedef struct {
   int32_t a_split;        /* 0 = default: user operand as bf16 head + tail (two MMAs per recipe block, halves the
                              filter's error bound) when D <= 128; 1 = single bf16 operand */
 } fr_catalog_opts;
-int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, fr_stream s);
+int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, const float* item_cats /* [num_items,4] of THIS
+                       table's rows, or NULL = tables.item_cats (a row-sharded table passes its local slice) */,
+                       fr_stream s);
 /* Query rows: P_rows != NULL -> dense device rows [n_users,5,D] (e.g. all-gathered from the user
  * owners); else users[n_users] (device) index tables.P, NULL = 0..n_users-1.
  * out_ids [n_users,K] = local recipe row * id_mul + id_add (-1 padded); out_scores [n_users,K]

@@ -108,3 +108,26 @@ def test_capacity_overflow_is_reported():
         g.set_batch(f["user_input"][idx[r]] // 2, f["item_input"][idx[r]], labels=f["labels"][idx[r]], global_batch=200)
     outs = run.step()
     assert outs[0].cpu().numpy()[9] == 2.0
+
+
+@pytest.mark.parametrize("W", [2, 3])
+def test_sharded_catalog_topk_equals_unsharded(W):
+    """Item-sharded full-catalog top-K (query rows gathered, per-shard top-K with global ids,
+    lists back to the user owners, fr_catalog_merge) == the unsharded engine, bit for bit."""
+    from foodrec_b200 import Engine, Hyper
+    p = Problem(300, 4001, 9, 128, seed=17)           # 4001 recipes: padded shards
+    K, n = 40, 24
+    single = Engine(Hyper(), p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=256, item_cats=p.item_cats)
+    engs = [sharded.ShardedEngine(Hyper(), sharded.shard_rows(p.tb.P, r, W), sharded.shard_rows(p.tb.R, r, W),
+                                  p.tb.Cat, p.tb.G, r, W, max_rows=256, item_cats_global=p.item_cats)
+            for r in range(W)]
+    for g in engs:
+        g.catalog_prepare()
+    rng = np.random.default_rng(3)
+    local_users = [rng.integers(0, len(range(r, p.U, W)), n).astype(np.int32) for r in range(W)]
+    outs = sharded.LocalRunner(engs).catalog_topk(local_users, K=K)
+    for r in range(W):
+        gu = local_users[r].astype(np.int64) * W + r          # global user ids of rank r's queries
+        ids, sc = single.catalog_topk(users=gu.astype(np.int32), K=K)
+        assert torch.equal(outs[r][0], ids) and torch.equal(outs[r][1], sc), r
+    assert int(outs[0][0].max()) < p.I                        # pad rows of the last shard are never returned

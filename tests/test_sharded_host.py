@@ -89,3 +89,41 @@ def test_dist_runner_wiring_gloo_world2(tmp_path):
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("WIRING_OK_") == 2, out.stdout
+
+
+CATALOG_WIRING = textwrap.dedent("""
+    import os, sys, torch, torch.distributed as dist
+    sys.path.insert(0, "__ROOT__")
+    from foodrec_b200.sharded import DistRunner
+    dist.init_process_group("gloo")
+    r, W, n, K, D = dist.get_rank(), dist.get_world_size(), 3, 2, 2
+    class Stub:                       # item-sharded catalog protocol on CPU tensors with recognisable payloads
+        rank, world = r, W
+        def catalog_query_rows(s, users):          # my query j carries 10*me + j
+            return torch.tensor([[10.0 * r + j] * D for j in range(n)]).view(n, 1, D)
+        def catalog_local(s, allrows, K_):          # gathered rows arrive in rank order, block q = rank q's queries
+            assert allrows.shape == (W * n, 1, D)
+            assert allrows[:, 0, 0].tolist() == [10.0 * q + j for q in range(W) for j in range(n)]
+            ids = torch.tensor([[1000 * r + int(v), 1000 * r + int(v) + 500] for v in allrows[:, 0, 0]], dtype=torch.int32)
+            return ids, ids.double() + 0.25        # "my shard's list" for every query
+        def catalog_merge(s, ids, sc):               # [W, n, K]: list w = shard w's answer for MY queries
+            assert ids.shape == (W, n, K)
+            for w in range(W):
+                assert ids[w, :, 0].tolist() == [1000 * w + 10 * r + j for j in range(n)], ids
+            assert torch.equal(sc, ids.double() + 0.25)
+            return "merged"
+    assert DistRunner(Stub()).catalog_topk(None, K=K) == "merged"
+    sys.stdout.write("CATALOG_WIRING_OK_%d\\n" % r); sys.stdout.flush()
+""")
+
+
+def test_dist_runner_catalog_wiring_gloo_world2(tmp_path):
+    """all-gather of query rows -> per-shard lists -> all-to-all back to the user owners."""
+    script = tmp_path / "catalog_wiring.py"
+    script.write_text(CATALOG_WIRING.replace("__ROOT__", ROOT))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29633", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("CATALOG_WIRING_OK_") == 2, out.stdout
