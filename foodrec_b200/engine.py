@@ -342,6 +342,33 @@ class Engine:
         return dict(zip(("cta_group", "k_padded", "tiles", "present_masks", "recipes_with_category", "epi_sets",
                          "list_capacity", "fallback_blocks"), list(v)))
 
+    # ------------------------------------------------------------------ 1:N negative sampling
+    def sample_negatives(self, pos_items, n_neg, seed, sample_offset=0):
+        """int32 [n, n_neg] device: counter-based (Philox4x32-10) uniform negatives != positive;
+        the same ids oracle/sampler_oracle.sample_negatives draws for (seed, sample index)."""
+        pos = self._i32(pos_items)
+        out = torch.empty((pos.numel(), int(n_neg)), dtype=torch.int32, device=self.device)
+        L.check(self.handle, self.lib.fr_sample_negatives(self.handle, _ptr(pos), pos.numel(), int(n_neg), int(seed) & (2**64 - 1),
+                                                          int(sample_offset), _ptr(out), self._stream()))
+        self._keep = [pos]
+        return out
+
+    def train_step_sampled(self, users, pos_items, n_neg, seed, sample_offset=0, **kw):
+        """One BPR step with n_neg sampled negatives per positive: the batch of B positives becomes
+        B*n_neg triples (u, i+, i-_j) drawn on the device (resident side tables required)."""
+        u, pos = self._i32(users), self._i32(pos_items)
+        neg = self.sample_negatives(pos, n_neg, seed, sample_offset)
+        items = torch.stack([pos.unsqueeze(1).expand(-1, n_neg), neg], 2).reshape(-1).contiguous()
+        uu = u.unsqueeze(1).expand(-1, n_neg).reshape(-1).contiguous()
+        return self._step_dev(L.FR_BPR, uu.numel(), uu, items, None, None, None, None, **kw)
+
+    def philox(self, ctr_key):
+        ck = torch.as_tensor(np.ascontiguousarray(np.asarray(ctr_key, np.uint32)).view(np.int32)).to(self.device)
+        n = ck.numel() // 6
+        out = torch.empty(4 * n, dtype=torch.int32, device=self.device)
+        L.check(self.handle, self.lib.fr_philox4x32_10(self.handle, _ptr(ck), n, _ptr(out), self._stream()))
+        return out.cpu().numpy().view(np.uint32).reshape(n, 4)
+
     def sort_pairs(self, keys, nbits):
         k = torch.as_tensor(np.asarray(keys, np.int64).astype(np.uint32).view(np.int32)).to(self.device)
         ok = torch.empty_like(k); oi = torch.empty_like(k)

@@ -237,6 +237,16 @@ int fr_catalog_cycle_counters(fr_handle h, uint64_t* out /* [8] */, fr_stream s)
 /* rows of the LAST pass that took the exact full-scan fallback (synchronises the stream) */
 int fr_catalog_fallback_rows(fr_handle h, int32_t* out, fr_stream s);
 
+/* ---- Negative sampling for 1:N BPR (extension; the reference only takes listed negatives,
+ * Train_recommender.py:86-93).  Counter-based so host and device agree bit for bit:
+ * Philox4x32-10 with counter (sample_lo, sample_hi, j, attempt), key = seed; item = mulhi32(x0, I);
+ * a draw equal to the positive is re-drawn (<= 16 attempts, then (positive+1) % I).
+ * pos_items [n] device; out [n, n_neg] device; sample index = sample_offset + row. */
+int fr_sample_negatives(fr_handle h, const int32_t* pos_items, int64_t n, int32_t n_neg, uint64_t seed,
+                        uint64_t sample_offset, int32_t* out, fr_stream s);
+/* The raw generator (known-answer tests): ctr_key [n,6] = counter[4], key[2] -> out [n,4]. */
+int fr_philox4x32_10(fr_handle h, const uint32_t* ctr_key, int32_t n, uint32_t* out, fr_stream s);
+
 /* stable LSD radix sort of (key, index) pairs -- exported for tests of the
  * sort-and-segment machinery.  keys [n] (values < 2^nbits), out_keys/out_idx [n]. */
 int fr_sort_pairs(fr_handle h, const uint32_t* keys, int32_t n, int32_t nbits,

@@ -161,3 +161,32 @@ def test_get_train_instances_shape():
     first = [k for k in range(len(u)) if u[k] == "0"]
     assert first == list(range(len(first)))                # user-contiguous
     assert y[len(train["0"])] == 0 and ws[len(train["0"])] == [-1.0]
+
+
+# ---------------------------------------------------------------- negative sampler
+def test_philox_matches_random123_known_answers():
+    """The sampler's generator is pinned to the PUBLISHED Philox4x32-10 known-answer vectors
+    (Random123 v1.09 kat_vectors) -- the one part of this oracle with real golden vectors."""
+    from oracle import sampler_oracle as so
+    for ctr, key, want in so.KAT:
+        got = so.philox4x32_10(np.array(ctr, np.uint32), np.array(key, np.uint32))
+        assert got.tolist() == list(want)
+
+
+def test_negative_sampler_properties_and_golden():
+    from oracle import sampler_oracle as so
+    rng = np.random.default_rng(1)
+    pos = rng.integers(0, 50, 4000)
+    neg = so.sample_negatives(pos, 8, 50, seed=20260105)
+    assert neg.shape == (4000, 8) and neg.dtype == np.int32
+    assert ((neg >= 0) & (neg < 50)).all() and (neg != pos[:, None]).all()          # never the positive
+    cnt = np.bincount(neg.reshape(-1), minlength=50)
+    assert cnt.min() > 0.7 * cnt.mean() and cnt.max() < 1.3 * cnt.mean()            # uniform over the catalog
+    # a window of the stream equals the same rows of the whole stream (counter-based: no hidden state)
+    np.testing.assert_array_equal(so.sample_negatives(pos[100:160], 8, 50, seed=20260105, sample_offset=100), neg[100:160])
+    g = np.load(os.path.join(GOLD, "negative_sampler.npz"))
+    np.testing.assert_array_equal(so.sample_negatives(g["pos"], int(g["n_neg"]), int(g["num_items"]), int(g["seed"]),
+                                                      int(g["offset"])), g["neg"])
+    # two recipes: every draw that hits the positive is re-drawn, the answer is forced
+    two = so.sample_negatives(np.array([0, 1, 1, 0]), 4, 2, seed=3)
+    np.testing.assert_array_equal(two, np.array([[1] * 4, [0] * 4, [0] * 4, [1] * 4], np.int32))
