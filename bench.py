@@ -558,7 +558,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--batch", type=int, default=262144)
     ap.add_argument("--preroll", type=int, default=40)
     ap.add_argument("--small", action="store_true", help="tiny tables: harness check only, not a bench number")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -193,6 +193,7 @@ class Engine:
         L.check(self.handle, self.lib.fr_train_step(self.handle, C.byref(b), int(bool(write_personal)),
                                                     _ptr(self.out), _ptr(scores), self._stream()))
         self._dirty = True
+        self._catalog_ready = False                             # the catalog index follows Recipe_Embedding
         self._keep = [users, items, cats, labels, ws, ulab]    # alive until the next step is queued
         return (self.out, scores) if return_scores else self.out
 
@@ -206,6 +207,7 @@ class Engine:
         L.check(self.handle, self.lib.fr_train_step_host(self.handle, C.byref(b), int(bool(write_personal)),
                                                          C.c_void_p(self.out_host.data_ptr()), self._stream()))
         self._dirty = True
+        self._catalog_ready = False
         self._keep = [users, items, cats, labels, ws, ulab]
         return self.out_host
 
@@ -261,6 +263,14 @@ class Engine:
                                                            _ptr(cc), K, _ptr(ids), _ptr(rank), _ptr(sc), self._stream()))
         self._keep = [u, cand_d, nc, cc]
         return (ids, rank, sc) if return_scores else (ids, rank)
+
+    def set_item_cats(self, item_cats):
+        """(Re)place the resident dish_to_category table [I,4] (compact feed, catalog scoring)."""
+        ic = torch.as_tensor(np.asarray(item_cats, np.float32).reshape(-1, 4)).to(self.device).contiguous()
+        torch.cuda.synchronize(self.device)          # kernels in flight may still read the old table
+        self.item_cats = ic
+        self._set_tables()
+        self._catalog_ready = False
 
     # ------------------------------------------------------------------ full-catalog top-K
     def catalog_prepare(self, cta_group=0, max_pass_rows=0, splits=0, epi_sets=0, tile_n=0, a_split=0, item_cats=None):

@@ -96,6 +96,24 @@ class Model:
     def score(self, feed):
         return self.engine.score(feed[self.user_input], feed[self.item_input], feed[self.categories])
 
+    def catalog_topk(self, user_ids, K, dish_to_category=None):
+        """The K best recipes of the WHOLE catalog for each user, by (``model.logits`` desc, id asc) --
+        ``evaluate.py:55-63`` with every recipe as a candidate.  ``dish_to_category`` is the reference's
+        json map (``Train_recommender.py:132``: item -> [[m0],[m1],[m2],[m3]]); it is only needed on the
+        first call or when it changed.  Returns (ids int32 [n,K], scores float64 [n,K]) as numpy; ids of
+        recipes beyond the catalog are -1."""
+        e = self.engine
+        if dish_to_category is not None:
+            ic = np.zeros((e.I, 4), np.float32)
+            for it, m in dish_to_category.items():
+                if 0 <= int(it) < e.I:
+                    ic[int(it)] = np.asarray(m, np.float32).reshape(4)
+            e.set_item_cats(ic)
+        # (the engine rebuilds its recipe index by itself when a training step has run since)
+        users = np.asarray([int(u) for u in user_ids], np.int32)
+        ids, sc = e.catalog_topk(users=users, K=int(K))
+        return ids.cpu().numpy(), sc.cpu().numpy()
+
 
 class _Initializer:
     pass

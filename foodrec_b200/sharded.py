@@ -155,6 +155,7 @@ class ShardedEngine:
         L.check(e.handle, e.lib.fr_shard_apply(e.handle, C.byref(self._sh), _ptr(self.rreq), _ptr(self.rgrows), _ptr(e.out),
                                                e._stream()))
         e._dirty = True
+        e._catalog_ready = False
         return e.out
 
 

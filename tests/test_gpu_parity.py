@@ -377,6 +377,12 @@ def test_session_protocol_runs_the_reference_loop():
                 assert lr == np.float32(0.001)
         sess.run(model.epoch_increment)
         assert sess.run(model.epoch_step) == 1
+        # full-catalog top-K through the model object, fed with the reference's json map (extension)
+        cid, csc = model.catalog_topk(["3", "17", "3"], 7, d2c)
+        t = model.engine.tables()
+        oc = OracleModel(t["P"], t["R"], t["Cat"], t["G"], OHyper(), dtype=np.float32)
+        rid, rsc = evaluate_oracle.catalog_topk(oc, np.array([3, 17, 3]), p.item_cats, 7)
+        assert np.array_equal(cid, rid) and np.abs(csc - rsc).max() <= 1e-12 * np.abs(rsc).max()
         hits, ndcgs = evaluate_model(sess, model, tr, tn, 10, d2c)
         oh, on, _ = evaluate_oracle.evaluate_model(om, tr, tn, 10, p.item_cats)
         assert len(hits) == len(tr) and abs(np.mean(hits) - np.mean(oh)) <= 2 / len(tr)
