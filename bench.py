@@ -335,6 +335,28 @@ def run_sharded(args, cfg, B):
                    "ms": cms, "fallback_rows_rank0": eng.e.catalog_fallback_rows(),
                    "exchange_bytes_per_gpu": {"all_gather_rows": (world - 1) * n_q * 5 * D * 4,
                                               "all_to_all_lists": (world - 1) * n_q * 100 * 12}}
+        # cfg4 shape (BASELINE configs[3]): 10M recipes item-sharded over the N GPUs, n_q query users per GPU
+        if not args.small:
+            I4 = 10_000_000
+            Il4 = local_rows(I4, world)
+            g4 = torch.Generator(device=dev); g4.manual_seed(40 + rank)
+            e4 = ShardedEngine(Hyper(learner="sgd"), torch.randn((n_q, 5, D), device=dev, generator=g4) * 0.1,
+                               torch.randn((Il4, D), device=dev, generator=g4) * 0.1, Cat, G, rank, world, device=dev,
+                               max_rows=256, item_cats_global=synth.make_item_categories(I4))
+            e4.e.I_global = I4
+            e4.catalog_prepare()
+            run4 = DistRunner(e4)
+            run4.catalog_topk(ul, K=100)
+            dist.barrier(); torch.cuda.synchronize()
+            c0.record(); run4.catalog_topk(ul, K=100); c1.record()
+            dist.barrier(); torch.cuda.synchronize()
+            t = torch.tensor([c0.elapsed_time(c1)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); cms4 = float(t.item())
+            catalog = [catalog, {
+                "metric": "catalog_topk_users_per_sec", "value": world * n_q / (cms4 * 1e-3), "unit": "users/s",
+                "workload": f"cfg4 shape: {n_q} query users per GPU x {I4} recipes sharded by id % {world}, D={D}, K=100 "
+                            f"(weak scaling: every GPU scores all {world * n_q} gathered users against its {Il4} recipes)",
+                "ms": cms4, "fallback_rows_rank0": e4.e.catalog_fallback_rows(),
+                "dense_equivalent_tflops_per_gpu": 2.0 * world * n_q * Il4 * 5 * D / (cms4 * 1e-3) / 1e12}]
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
