@@ -16,7 +16,7 @@ namespace fr {
 
 struct CatalogWs {
   bool prepared = false;
-  int cta_group = 1, epi_sets = 2, BN = 128, a_split = 0, I = 0, KP = 0, k_blocks = 0, n_tiles = 0, present = 0, n_valid_items = 0;
+  int cta_group = 1, epi_sets = 1, BN = 128, a_split = 0, I = 0, KP = 0, k_blocks = 0, n_tiles = 0, present = 0, n_valid_items = 0;
   int max_pass_rows = 0, force_splits = 0;
   // index (built by fr_catalog_prepare)
   uint32_t* keys = nullptr; SortBufs sortM; int32_t* gs_dev = nullptr;
@@ -586,7 +586,7 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, cons
   w.a_split = (w.k_blocks * 2 <= CAT_KB_MAX && !(opts && opts->a_split == 1)) ? 1 : 0;   // opts->a_split: 0 default (on when it fits), 1 off
   const int BN = w.BN;
   w.max_pass_rows = (opts && opts->max_pass_rows > 0) ? opts->max_pass_rows : 0;
-  w.epi_sets = (opts && (opts->epi_sets == 1 || opts->epi_sets == 2 || opts->epi_sets == 4)) ? opts->epi_sets : 2;
+  w.epi_sets = (opts && (opts->epi_sets == 1 || opts->epi_sets == 2 || opts->epi_sets == 4)) ? opts->epi_sets : 1;
   w.force_splits = (opts && opts->splits > 0) ? std::min(opts->splits, CAT_LISTS_MAX / w.epi_sets) : 0;
 
   cat_mask_kernel<<<(I + 255) / 256, 256, 0, st>>>(w.item_cats, I, w.keys);
@@ -736,6 +736,7 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
       { const char* dm = getenv("FOODREC_CATALOG_DEBUG"); p.debug_mode = dm ? atoi(dm) : 0; }
       p.tile_group = w.tile_group; p.tile_valid = w.tile_valid; p.bias = w.bias; p.margin2 = w.margin2;
       p.block_first = bf;
+      { const char* dmn = getenv("FOODREC_CATALOG_DENSE_MIN"); p.dense_min = dmn ? atoi(dmn) : 3; }
       p.dbg = getenv("FOODREC_CATALOG_CYCLES") ? w.dbg : nullptr;
       for (int g = 0; g < 16; ++g) { p.group_lo[g] = w.group_lo[g]; p.group_hi[g] = w.group_hi[g]; p.group_last_valid[g] = w.group_last_valid[g]; }
       p.cand_sc = w.cand_sc; p.cand_row = w.cand_row; p.cand_cnt = w.cand_cnt; p.ovf = w.ovf;

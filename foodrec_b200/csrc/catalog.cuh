@@ -35,13 +35,15 @@ constexpr int CAT_MAXK = 256;
 constexpr int CAT_LISTS_MAX = 32;    // candidate lists per user the re-rank kernel merges (splits x column sets)
 constexpr int CAT_A_BLK = CAT_BM * CAT_BK * 2;                // 16 KB: one k-block of A
 constexpr int CAT_B_TOTAL = 128 * 1024;                       // all B stages
-constexpr int CAT_SMEM = CAT_KB_MAX * CAT_A_BLK + CAT_B_TOTAL + 1024 /*barriers*/ + 1024 /*align*/;
+constexpr int CAT_STAGE_WARPS = 8;                              // epilogue warps that own a 32x32 fp32 staging tile
+constexpr int CAT_SMEM = CAT_KB_MAX * CAT_A_BLK + CAT_B_TOTAL + 1024 /*barriers*/ + CAT_STAGE_WARPS * 4096 + 1024 /*align*/;
 
 struct CatGemmParams {
   int m_blocks;          // user blocks of CAT_BM * CG rows in this pass
   int m_pad;             // m_blocks * CAT_BM * CG
   int n_rows;            // valid user rows in this pass
   int n_split, tiles_per_split, n_tiles, k_blocks, K;
+  int dense_min;         // rows of a warp with a hit in a chunk from which the per-lane (shared staging) resolution is used
   int a_split;           // 1: A = bf16 head + bf16 tail (two MMAs per B block; needs 2*k_blocks <= CAT_KB_MAX)
   int debug_mode;        // 0 = normal.  Ceiling measurements (results invalid; env FOODREC_CATALOG_DEBUG): 1 = epilogue only
                          // drains TMEM, 2 = accumulators never read (TMA+MMA alone), 3 = threshold +inf (filter fast path only)

@@ -136,7 +136,7 @@ struct RowState {
 // from TMEM with a one-column tcgen05.ld (uniform address) and pushed under a predicate.
 __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const uint32_t tchunk, const int col,
                                                      const int nvalid, const int n0, RowState& s,
-                                                     const CatGemmParams& p, const int lane) {
+                                                     const CatGemmParams& p, const int lane, float* stage) {
   float m[16], g8[4];
 #pragma unroll
   for (int j = 0; j < 16; ++j) m[j] = fmaxf(v[2 * j], v[2 * j + 1]);
@@ -148,8 +148,29 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
   // chunk (an asynchronous tcgen05.ld into registers) must have landed before that can happen.
   tc::tmem_ld_wait();
 #if !defined(FR_CAT_REREAD)
-  // votes only (no REDUX / find-first-set / TMEM re-read in the dependency chain): every test is a
-  // warp-uniform predicate, the registers are indexed statically
+  // Dense regime (threshold ramp-up: several rows of the warp have hits in this chunk): every lane
+  // resolves its own row.  The chunk is parked in a conflict-free [column][lane] shared tile so a lane
+  // can index its values dynamically; the hit mask is built branch-free and popped bit by bit.
+  if (stage != nullptr && __popc(__ballot_sync(FR_FULL, mx >= s.adj)) >= p.dense_min) {
+    uint32_t hm = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      stage[j * 32 + lane] = v[j];
+      hm |= (v[j] >= s.adj) ? (1u << j) : 0u;
+    }
+    if (col + 32 > nvalid) hm &= (nvalid > col) ? ((1u << (nvalid - col)) - 1u) : 0u;   // zero padding is never a candidate
+    while (hm) {                                         // cnt <= CAP - 32 on entry (compaction policy): no bound check
+      const int j = __ffs(hm) - 1;
+      hm &= hm - 1;
+      __stcg(p.cand_sc + s.base + s.cnt, stage[j * 32 + lane] + s.bias);
+      __stcg(p.cand_row + s.base + s.cnt, n0 + col + j);
+      ++s.cnt;
+    }
+    __syncwarp();
+  } else
+  // Sparse regime: votes only (no REDUX / find-first-set / TMEM re-read in the dependency chain): every
+  // test is a warp-uniform predicate, the registers are indexed statically
+  {
 #pragma unroll
   for (int G = 0; G < 4; ++G) {
     if (__any_sync(FR_FULL, g8[G] >= s.adj)) {
@@ -166,6 +187,7 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
         }
       }
     }
+  }
   }
 #else
   const uint32_t gm = (g8[0] >= s.adj ? 1u : 0u) | (g8[1] >= s.adj ? 2u : 0u) | (g8[2] >= s.adj ? 4u : 0u) |
@@ -336,6 +358,8 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // TMEM lane quarter warp%4, so thread (q, lane) is user row q*32+lane for the whole sweep and
     // keeps one candidate list per column set.
     const int q = warp & 3, e = (warp - 4) >> 2;
+    float* stage = (warp - 4 < CAT_STAGE_WARPS)
+                       ? reinterpret_cast<float*>(sB + CAT_B_TOTAL + 1024) + (warp - 4) * 1024 : nullptr;
     const int r_in_blk = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + e * CW;
     const float INF = __int_as_float(0x7f800000);
@@ -387,13 +411,13 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc::tmem_ld_wait();
             __syncwarp();
             if (c + 1 < NCH) tc::tmem_ld_32x32(tcol + (c + 1) * 32, vb); else release_early();
-            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
+            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane, stage);
             else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
             if (c + 1 < NCH) {
               tc::tmem_ld_wait();
               __syncwarp();
               if (c + 2 < NCH) tc::tmem_ld_32x32(tcol + (c + 2) * 32, va); else release_early();
-              if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(vb, tcol + (c + 1) * 32, e * CW + (c + 1) * 32, nvalid, n0, s, p, lane);
+              if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(vb, tcol + (c + 1) * 32, e * CW + (c + 1) * 32, nvalid, n0, s, p, lane, stage);
               else if (vb[0] + vb[13] + vb[31] == 12345.f) s.cnt++;
             }
           }
@@ -405,7 +429,7 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc::tmem_ld_32x32(tcol + c * 32, va);
             tc::tmem_ld_wait();
             if (c == NCH - 1) release_early();
-            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane);
+            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane, stage);
             else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
           }
         }

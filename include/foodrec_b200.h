@@ -207,7 +207,8 @@ typedef struct {
   int32_t cta_group;      /* 0 = default (2: CTA pairs, tcgen05 cta_group::2), 1 = single-CTA MMA */
   int32_t max_pass_rows;  /* 0 = default; users processed per pass */
   int32_t splits;         /* 0 = auto; pieces the recipe sweep is cut into for small user counts */
-  int32_t epi_sets;       /* 0 = default (2); 1, 2 or 4 epilogue warp sets (each owns tile_n/sets accumulator columns) */
+  int32_t epi_sets;       /* 0 = default (1); 1, 2 or 4 epilogue warp sets (each owns tile_n/sets accumulator columns
+                             and keeps its own candidate list per user) */
   int32_t tile_n;         /* 0 = default (256: 2 accumulator stages in TMEM); 128: 4 stages */
   int32_t a_split;        /* 0 = default: user operand as bf16 head + tail (two MMAs per recipe block, halves the
                              filter's error bound) when D <= 128; 1 = single bf16 operand */
