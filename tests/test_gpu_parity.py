@@ -496,3 +496,34 @@ def test_sampled_1_to_8_step_matches_oracle():
                                neg_categories=p.item_cats[nn], user_one_hot_label=p.user_labels[uu]))
     compare_tables(e, om, "sampled 1:8 ")
     e.close()
+
+
+def test_device_resident_instance_stream_equals_the_dense_feed_loop():
+    """instance arrays + side tables resident on the device, batches are device slices.  One epoch
+    of Train_recommender.py:163-199 (first batch = 16 personal-memory steps of 8 rows) must leave exactly the
+    tables the reference-format dense feed leaves."""
+    from foodrec_b200 import Engine, Hyper
+    from foodrec_b200.data import InstanceStream, build_instances, side_tables
+    p = Problem(60, 400, 7, 32, seed=71)
+    train, tr, tn = synth.make_reference_dataset(60, 400, seed=8, pos_range=(3, 12))
+    d2c, u2l = synth.reference_side_maps(p.item_cats, p.user_labels)
+    ui, ii, y, c, ws, ul = synth.get_train_instances(train, tn, d2c, u2l, seed=3)
+    h = Hyper(learner="adam", lr=0.001)
+    dense = Engine(h, p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=256, max_label_entries=256 * p.L)
+    B, n = 128, len(ui)
+    users = np.asarray(ui).astype(np.int32)
+    for b in range(n // B):
+        s0, s1 = b * B, (b + 1) * B
+        spans = [(s0 + k * 8, s0 + (k + 1) * 8, True) for k in range(16)] if b == 0 else [(s0, s1, False)]
+        for lo, hi, personal in spans:
+            dense.train_step(users[lo:hi], ii[lo:hi], labels=y[lo:hi], categories=c[lo:hi], write_sign=ws[lo:hi],
+                             user_one_hot_label=ul[lo:hi], write_personal=personal)
+    ic, ulab = side_tables(d2c, u2l, p.I, p.U, p.L)
+    res = Engine(h, p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=256, item_cats=ic, user_labels=ulab)
+    stream = InstanceStream(res, build_instances(train, tn, seed=3))
+    assert stream.n == n
+    assert stream.run_epoch(B, epoch=0) == n // B - 1 + 16
+    ta, tb_ = dense.tables(), res.tables()
+    for k in ("P", "R", "Cat", "G"):
+        np.testing.assert_array_equal(ta[k], tb_[k], err_msg=k)
+    dense.close(); res.close()
