@@ -487,13 +487,22 @@ def run_ours(args, cfg, B):
         return eng.train_step_host(L.FR_BPR, B, b["users"], b["items"], b["cats"] if dense else None, None, None,
                                    b["ulab"] if dense else None)
 
-    def e2e_run(dense):
+    def eprefetch(k, dense=True):
+        b = hb[k % NB]
+        eng.feed_prefetch(L.FR_BPR, B, b["users"], b["items"], b["cats"] if dense else None, None, None,
+                          b["ulab"] if dense else None)
+
+    def e2e_run(dense, prefetch=True):
         for k in range(3):
             estep(k, dense)
         barrier()
         t0 = time.perf_counter()
         loss_sum = 0.0
+        if prefetch:
+            eprefetch(0, dense)
         for k in range(args.steps):
+            if prefetch:
+                eprefetch(k + 1, dense)                    # H2D of the next feed overlaps this step's kernels
             out = estep(k, dense)
             torch.cuda.current_stream().synchronize()      # the step's loss is read on the host every step
             loss_sum += float(out[L.FR_OUT_LOSS])
@@ -503,6 +512,7 @@ def run_ours(args, cfg, B):
             t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         return world * B * args.steps / dt, loss_sum / args.steps
     e2e_val, e2e_loss = e2e_run(True)
+    e2e_serial, _ = e2e_run(True, prefetch=False)
     e2e_cval, _ = e2e_run(False)
 
     # ---- top-K users/s: sampled evaluation (51 candidates, K=10: evaluate.py) over NU users
@@ -553,7 +563,9 @@ def run_ours(args, cfg, B):
             "roofline": roofline, "kernels": kern, "phases_ms": phases,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
                     "feed": "reference dense feed (user_input,item_input,categories,user_one_hot_label), pinned, "
-                            "host read of the loss every step", "mean_loss": e2e_loss},
+                            "host read of the loss every step; the copy of feed k+1 (fr_feed_prefetch, library copy "
+                            "stream) overlaps the kernels of step k", "mean_loss": e2e_loss,
+                    "without_prefetch": e2e_serial},
             "e2e_compact": {"value": e2e_cval, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                             "feed": "ids only; dish_to_category / user labels resident on device"},
             "topk": {"metric": "sampled_topk_users_per_sec", "value": NU / (eval_ms * 1e-3), "unit": "users/s",

@@ -69,6 +69,7 @@ _PROTOS = {
     "fr_fwd_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "fr_train_step": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_train_step_host": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.c_int32, C.c_void_p, C.c_void_p]),
+    "fr_feed_prefetch": (C.c_int, [C.c_void_p, C.POINTER(fr_batch)]),
     "fr_adam_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fr_launch_count": (C.c_int64, []),
     "fr_timing_enable": (C.c_int, [C.c_void_p, C.c_int32]),

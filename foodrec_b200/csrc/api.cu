@@ -85,6 +85,8 @@ extern "C" int fr_destroy(fr_handle h) {
   catalog_free(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->stage) cudaFree(h->stage);
+  for (auto& sl : h->feed) { if (sl.buf) cudaFree(sl.buf); if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->pieces_personal) cudaFree(h->pieces_personal);
   delete h;
   return FR_OK;
@@ -410,9 +412,90 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   return FR_OK;
 }
 
+// byte layout of a batch image in a staging buffer
+struct FeedLayout { size_t users, items, cats, labels, ws, ul, out, total; int group; size_t S; };
+static FeedLayout feed_layout(const fr_ctx* h, const fr_batch* hb) {
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  FeedLayout f;
+  f.group = hb->mode == FR_BPR ? 2 : 1;
+  const size_t B = (size_t)hb->n_groups, L = (size_t)h->mc.L;
+  f.S = B * f.group;
+  f.users = 0;
+  f.items = f.users + al(B * 4);
+  f.cats = f.items + al(f.S * 4);
+  f.labels = f.cats + al(hb->cats ? f.S * 16 : 0);
+  f.ws = f.labels + al(hb->labels ? B * 4 : 0);
+  f.ul = f.ws + al(hb->write_sign ? f.S * 4 : 0);
+  f.out = f.ul + al(hb->user_labels ? B * L * 4 : 0);
+  f.total = f.out + al(FR_OUT_COUNT * 4);
+  return f;
+}
+static int feed_copy(fr_ctx* h, const fr_batch* hb, const FeedLayout& f, char* base, fr_batch* db, cudaStream_t st) {
+  const size_t B = (size_t)hb->n_groups, L = (size_t)h->mc.L;
+  *db = *hb;
+#define H2D(field, off, bytes) if (hb->field) { \
+    FR_CUDA(h, cudaMemcpyAsync(base + (off), hb->field, (bytes), cudaMemcpyHostToDevice, st)); \
+    db->field = reinterpret_cast<decltype(db->field)>(base + (off)); }
+  H2D(users, f.users, B * 4)
+  H2D(items, f.items, f.S * 4)
+  H2D(cats, f.cats, f.S * 16)
+  H2D(labels, f.labels, B * 4)
+  H2D(write_sign, f.ws, f.S * 4)
+  H2D(user_labels, f.ul, B * L * 4)
+#undef H2D
+  return FR_OK;
+}
+
+extern "C" int fr_feed_prefetch(fr_handle h, const fr_batch* hb) {
+  if (!h || !hb) return FR_ERR_ARG;
+  if (hb->n_groups <= 0) return fail(h, FR_ERR_ARG, "empty batch");
+  if (!h->copy_stream) {
+    FR_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto& sl : h->feed) {
+      FR_CUDA(h, cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+      FR_CUDA(h, cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
+    }
+  }
+  fr_ctx::FeedSlot& sl = h->feed[h->feed_next];
+  h->feed_next ^= 1;
+  const FeedLayout f = feed_layout(h, hb);
+  if (sl.used) FR_CUDA(h, cudaStreamWaitEvent(h->copy_stream, sl.consumed, 0));   // the step that read this slot is done
+  if (f.total > sl.bytes) {
+    if (sl.buf) { FR_CUDA(h, cudaDeviceSynchronize()); cudaFree(sl.buf); sl.buf = nullptr; }
+    FR_CUDA(h, cudaMalloc(&sl.buf, f.total));
+    sl.bytes = f.total;
+  }
+  int rc = feed_copy(h, hb, f, static_cast<char*>(sl.buf), &sl.dev, h->copy_stream);
+  if (rc) return rc;
+  sl.dout = reinterpret_cast<float*>(static_cast<char*>(sl.buf) + f.out);
+  FR_CUDA(h, cudaEventRecord(sl.copied, h->copy_stream));
+  sl.host = *hb;
+  sl.valid = true;
+  return FR_OK;
+}
+
+static bool same_batch(const fr_batch& a, const fr_batch& b) {
+  return a.mode == b.mode && a.n_groups == b.n_groups && a.users == b.users && a.items == b.items && a.cats == b.cats &&
+         a.labels == b.labels && a.write_sign == b.write_sign && a.user_labels == b.user_labels;
+}
+
 extern "C" int fr_train_step_host(fr_handle h, const fr_batch* hb, int32_t write_personal,
                                   float* host_out_scalars, fr_stream s) {
   if (!h || !hb) return FR_ERR_ARG;
+  for (auto& sl : h->feed) {
+    if (sl.valid && same_batch(sl.host, *hb)) {          // staged by fr_feed_prefetch: only wait for its copy
+      cudaStream_t st = (cudaStream_t)s;
+      FR_CUDA(h, cudaStreamWaitEvent(st, sl.copied, 0));
+      sl.valid = false;
+      int rc = fr_train_step(h, &sl.dev, write_personal, sl.dout, nullptr, s);
+      if (rc) return rc;
+      if (host_out_scalars)
+        FR_CUDA(h, cudaMemcpyAsync(host_out_scalars, sl.dout, FR_OUT_COUNT * sizeof(float), cudaMemcpyDeviceToHost, st));
+      FR_CUDA(h, cudaEventRecord(sl.consumed, st));
+      sl.used = true;
+      return FR_OK;
+    }
+  }
   const int group = hb->mode == FR_BPR ? 2 : 1;
   const int B = hb->n_groups;
   if (B <= 0) return fail(h, FR_ERR_ARG, "empty batch");

@@ -54,6 +54,16 @@ struct fr_ctx {
   fr::CatalogWs* cat = nullptr;     // full-catalog top-K (catalog.cu): index + pass workspace
   // staging for fr_train_step_host
   void* stage = nullptr; size_t stage_bytes = 0;
+  // fr_feed_prefetch: two staging slots filled on a private copy stream while the previous step computes
+  struct FeedSlot {
+    void* buf = nullptr; size_t bytes = 0;
+    fr_batch host{}, dev{};            // identity of the staged host batch / its device image
+    float* dout = nullptr;
+    bool valid = false, used = false;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+  } feed[2];
+  cudaStream_t copy_stream = nullptr;
+  int feed_next = 0;
   // per-phase timing (fr_timing_*)
   bool timing = false;
   struct TimingSet { cudaEvent_t ev[FR_T_COUNT + 1]; bool used = false; };

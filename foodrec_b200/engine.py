@@ -211,6 +211,14 @@ class Engine:
         self._keep = [users, items, cats, labels, ws, ulab]
         return self.out_host
 
+    def feed_prefetch(self, mode, B, users, items, cats=None, labels=None, ws=None, ulab=None):
+        """fr_feed_prefetch: start the H2D copy of a FUTURE batch (same host buffers later passed to
+        train_step_host) on the library's copy stream, overlapping the step in flight."""
+        hp = lambda x: C.c_void_p(0) if x is None else C.c_void_p(x.data_ptr() if torch.is_tensor(x) else x.ctypes.data)
+        b = L.fr_batch(mode, B, hp(users), hp(items), hp(cats), hp(labels), hp(ws), hp(ulab))
+        L.check(self.handle, self.lib.fr_feed_prefetch(self.handle, C.byref(b)))
+        self._keep_prefetch = [users, items, cats, labels, ws, ulab]
+
     def read_scalars(self):
         v = self.out.cpu().numpy()       # synchronises
         if v[L.FR_OUT_OVERFLOW] == 2:

@@ -133,6 +133,13 @@ int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_personal,
 int fr_train_step_host(fr_handle h, const fr_batch* host_batch, int32_t write_personal,
                        float* host_out_scalars, fr_stream s);
 
+/* Input prefetch for the host-buffer path: starts the host->device copy of a FUTURE batch on the library's
+ * own copy stream (two staging slots) and returns at once; the next fr_train_step_host call that is given the
+ * same fr_batch (same host pointers, mode and size) skips its own copies and only waits for that one.  Lets the
+ * PCIe transfer of batch k+1 overlap the kernels of batch k.  The host buffers must stay untouched (and should
+ * be pinned) until that step has been queued. */
+int fr_feed_prefetch(fr_handle h, const fr_batch* host_batch);
+
 /* Per-phase device time of fr_train_step, measured with CUDA events recorded on the
  * step's stream (the measurement bench.py's roofline uses).  fr_timing_read waits for
  * the outstanding events and returns, per phase, the summed milliseconds over n_steps. */

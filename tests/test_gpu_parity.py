@@ -527,3 +527,34 @@ def test_device_resident_instance_stream_equals_the_dense_feed_loop():
     for k in ("P", "R", "Cat", "G"):
         np.testing.assert_array_equal(ta[k], tb_[k], err_msg=k)
     dense.close(); res.close()
+
+
+def test_feed_prefetch_overlap_gives_identical_results():
+    """fr_feed_prefetch stages batch k+1 on the library's copy stream while step k runs; the step that
+    consumes the staged image must be indistinguishable from the unstaged host path."""
+    from foodrec_b200 import _lib as L
+    p = Problem(500, 800, 9, 64, seed=91)
+    ea = make_engine(p, learner="adam", lr=0.01, max_rows=1024)
+    eb = make_engine(p, learner="adam", lr=0.01, max_rows=1024)
+    pin = lambda x, dt: torch.as_tensor(np.ascontiguousarray(np.asarray(x).astype(dt))).pin_memory()
+    feeds = []
+    for s in range(5):
+        f = p.bpr(300, seed=200 + s)
+        items = np.stack([f["item_input"], f["neg_item_input"]], 1).reshape(-1)
+        cats = np.stack([f["categories"].reshape(-1, 4), f["neg_categories"].reshape(-1, 4)], 1).reshape(-1, 4)
+        feeds.append((pin(f["user_input"], np.int32), pin(items, np.int32), pin(cats, np.float32),
+                      pin(f["user_one_hot_label"], np.float32)))
+    outs_a, outs_b = [], []
+    ea.feed_prefetch(L.FR_BPR, 300, feeds[0][0], feeds[0][1], feeds[0][2], None, None, feeds[0][3])
+    for s, (u, it, c, ul) in enumerate(feeds):
+        if s + 1 < len(feeds):
+            n = feeds[s + 1]
+            ea.feed_prefetch(L.FR_BPR, 300, n[0], n[1], n[2], None, None, n[3])
+        oa = ea.train_step_host(L.FR_BPR, 300, u, it, c, None, None, ul); torch.cuda.synchronize(); outs_a.append(oa.clone())
+        ob = eb.train_step_host(L.FR_BPR, 300, u, it, c, None, None, ul); torch.cuda.synchronize(); outs_b.append(ob.clone())
+    for oa, ob in zip(outs_a, outs_b):
+        assert torch.equal(oa, ob)
+    ta, tb_ = ea.tables(), eb.tables()
+    for k in ("P", "R", "Cat", "G"):
+        np.testing.assert_array_equal(ta[k], tb_[k], err_msg=k)
+    ea.close(); eb.close()
