@@ -159,6 +159,22 @@ class ShardedEngine:
         return e.out
 
 
+    # checkpoint: one .npz per rank, the layout tf.train.Saver's single file would have had ------
+    def save(self, path_prefix):
+        """``<prefix>.rank<r>of<W>.npz``: this rank's rows of P / R (+ optimizer slots), the replicated Cat / G and
+        the step.  Every rank writes its own file; rank 0's Cat / G are the ones restore() trusts."""
+        sd = self.e.state_dict()
+        sd["rank"], sd["world"] = np.int64(self.rank), np.int64(self.world)
+        f = f"{path_prefix}.rank{self.rank}of{self.world}.npz"
+        np.savez(f, **sd)
+        return f
+
+    def restore(self, path_prefix):
+        sd = dict(np.load(f"{path_prefix}.rank{self.rank}of{self.world}.npz"))
+        if int(sd.pop("world")) != self.world or int(sd.pop("rank")) != self.rank:
+            raise ValueError("checkpoint was written for a different sharding")
+        self.e.load_state_dict(sd)
+
     # full-catalog top-K, item-sharded (SURVEY 8e) -------------------------------------------
     def catalog_prepare(self, **opts):
         """Index of THIS rank's recipe shard (local row k = recipe rank + k*W; rows past the
