@@ -350,22 +350,82 @@ __global__ void __launch_bounds__(FIN_THREADS) cat_finalize_kernel(const FinPara
   }
   const int nF = s_nF;
   load_user_exact(user_row(f.src, row, f.D / 4), f.Cat, f.D, sP, sH, tid, FIN_THREADS);
-  for (int i = warp; i < nF; i += FIN_THREADS / 32) {
+  // Re-score, ONE THREAD PER SURVIVOR.  (A warp per survivor made this stage a chain of dependent
+  // L2/HBM reads -- id, mask, row -- per survivor: 35 % of a cfg2 run.)  Ids and masks of all survivors
+  // are fetched first; the fp64 user row sum_{c in g} P[u,1+c] is built once per mask that occurs; then
+  // every thread streams its survivor's recipe row with independent 16-byte loads.
+  double* Z = reinterpret_cast<double*>(crow + f.n_split * CAT_CAP);      // [16][D], after the candidate arrays
+  __shared__ int s_masks;
+  if (tid == 0) s_masks = 0;
+  __syncthreads();
+  for (int i = tid; i < nF; i += FIN_THREADS) {
     const int item = __ldg(f.row_item + frow[i]);
     const float4 m = __ldg(f.item_cats + item);
-    const double s = exact_score_warp(sP, sH, f.R + (size_t)item * f.D, m, f.D, lane, f.a, f.oma);
-    if (lane == 0) { es[i] = s; eid[i] = item; }
+    const int g = (m.x != 0.f ? 1 : 0) | (m.y != 0.f ? 2 : 0) | (m.z != 0.f ? 4 : 0) | (m.w != 0.f ? 8 : 0);
+    eid[i] = item;
+    frow[i] = g;                                   // the padded row is no longer needed: keep the mask
+    atomicOr(&s_masks, 1 << g);
   }
-  int n2 = 2;
-  while (n2 < nF) n2 <<= 1;
-  for (int i = nF + tid; i < n2; i += FIN_THREADS) { es[i] = -CUDART_INF; eid[i] = 0x7fffffff; }
   __syncthreads();
-  bitonic_rank_sort(es, eid, n2, tid, FIN_THREADS);
+  const int present = s_masks;
+  for (int e = tid; e < 16 * f.D; e += FIN_THREADS) {
+    const int g = e / f.D, d = e % f.D;
+    if ((present >> g) & 1) {
+      double z = 0.0;
+      if (g & 1) z += (double)sP[f.D + d];
+      if (g & 2) z += (double)sP[2 * f.D + d];
+      if (g & 4) z += (double)sP[3 * f.D + d];
+      if (g & 8) z += (double)sP[4 * f.D + d];
+      Z[e] = z;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nF; i += FIN_THREADS) {
+    const int g = frow[i], n = __popc(g);
+    const float4* rr = reinterpret_cast<const float4*>(f.R + (size_t)eid[i] * f.D);
+    const double* zg = Z + g * f.D;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int q = 0; q < f.D / 4; ++q) {
+      const float4 r = __ldg(rr + q);
+      acc = fma(zg[4 * q], (double)r.x, acc);
+      acc = fma(zg[4 * q + 1], (double)r.y, acc);
+      acc = fma(zg[4 * q + 2], (double)r.z, acc);
+      acc = fma(zg[4 * q + 3], (double)r.w, acc);
+    }
+    double hs = 0.0;
+    if (g & 1) hs += sH[0];
+    if (g & 2) hs += sH[1];
+    if (g & 4) hs += sH[2];
+    if (g & 8) hs += sH[3];
+    es[i] = n ? f.a * (hs / n) + f.oma * (acc / n) : -CUDART_INF;
+  }
+  __syncthreads();
+  // Final order by counting: the rank of a survivor is the number of survivors that come before it in
+  // (score desc, id asc) -- a strict total order, ids are distinct.  nF is a few hundred: nF^2/128 broadcast
+  // shared loads per thread and no barrier, against ~40 barrier-separated bitonic stages.
   const size_t ob = (size_t)query_row(f.src, row) * f.K;
-  for (int k = tid; k < f.K; k += FIN_THREADS) {
-    const bool has = k < nF && eid[k] != 0x7fffffff && es[k] > -CUDART_INF;
-    f.out_ids[ob + k] = has ? eid[k] * f.id_mul + f.id_add : -1;
-    if (f.out_scores) f.out_scores[ob + k] = has ? es[k] : -CUDART_INF;
+  int n_real = 0;
+  for (int i = tid; i < nF; i += FIN_THREADS) {
+    const double si = es[i];
+    const int ii = eid[i];
+    if (si > -CUDART_INF) {
+      int rank = 0;
+      for (int j = 0; j < nF; ++j) rank += ranks_before(es[j], eid[j], si, ii) ? 1 : 0;
+      if (rank < f.K) {
+        f.out_ids[ob + rank] = ii * f.id_mul + f.id_add;
+        if (f.out_scores) f.out_scores[ob + rank] = si;
+      }
+    }
+  }
+  for (int i = tid; i < nF; i += FIN_THREADS) n_real += es[i] > -CUDART_INF ? 1 : 0;
+  n_real = __reduce_add_sync(FR_FULL, n_real);
+  if (lane == 0) s_red[warp] = n_real;
+  __syncthreads();
+  n_real = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+  for (int k = n_real + tid; k < f.K; k += FIN_THREADS) {        // fewer recipes than K: pad
+    f.out_ids[ob + k] = -1;
+    if (f.out_scores) f.out_scores[ob + k] = -CUDART_INF;
   }
 }
 
@@ -753,7 +813,8 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     f.margin2 = w.margin2; f.cand_sc = w.cand_sc; f.cand_row = w.cand_row; f.cand_cnt = w.cand_cnt;
     f.ovf = w.ovf; f.ovf_list = w.ovf_list; f.ovf_count = w.ovf_count;
     f.id_mul = id_mul; f.id_add = id_add; f.out_ids = out_ids; f.out_scores = out_scores;
-    const size_t fsm = (size_t)CAT_FCAP * (8 + 4 + 4) + 32 + (size_t)5 * D * 4 + (size_t)n_lists * CAT_CAP * 8;
+    const size_t fsm = (size_t)CAT_FCAP * (8 + 4 + 4) + 32 + (size_t)5 * D * 4 + (size_t)n_lists * CAT_CAP * 8 +
+                       (size_t)16 * D * 8 + 8;      // + the per-mask fp64 user rows of the re-rank
     cat_finalize_kernel<<<rows, FIN_THREADS, fsm, st>>>(f);
     ++g_launches;
     FR_CHECK_LAUNCH(h);

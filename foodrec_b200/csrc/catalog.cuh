@@ -30,7 +30,7 @@ constexpr int CAT_BN_MAX = 256;    // recipes per tile: 256 (2 accumulator stage
 constexpr int CAT_BK = 64;         // bf16 elements per 128-byte swizzle atom
 constexpr int CAT_KB_MAX = 4;      // D <= 256
 constexpr int CAT_CAP = 512;       // candidate slots per (split, user)
-constexpr int CAT_FCAP = 1024;     // survivors re-scored per user
+constexpr int CAT_FCAP = 512;      // survivors re-scored per user (more: exact fallback)
 constexpr int CAT_MAXK = 256;
 constexpr int CAT_LISTS_MAX = 32;    // candidate lists per user the re-rank kernel merges (splits x column sets)
 constexpr int CAT_A_BLK = CAT_BM * CAT_BK * 2;                // 16 KB: one k-block of A
