@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG2 = dict(U=1_000_000, I=200_000, L=95, D=128)
+CFG3 = dict(U=100_000_000, I=10_000_000, L=95, D=128)   # BASELINE configs[2]: needs the 8-GPU row-sharded path
 SMALL = dict(U=20_000, I=5_000, L=95, D=128)       # --small: functional check of the harness only
 METRIC, UNIT = "bpr_train_triples_per_sec", "triples/s"
 
@@ -209,7 +210,8 @@ def run_reference(args, cfg, B):
 
 
 def workload_name(cfg, B):
-    return (f"cfg2: {cfg['U']} users x {cfg['I']} recipes x {cfg['L']} labels, D={cfg['D']}, "
+    name = "cfg3" if cfg["U"] == CFG3["U"] else "cfg2"
+    return (f"{name}: {cfg['U']} users x {cfg['I']} recipes x {cfg['L']} labels, D={cfg['D']}, "
             f"BPR B={B} triples/step, shuffled users, Zipf(1.05) positives")
 
 
@@ -263,13 +265,13 @@ def run_sharded(args, cfg, B):
     U, I, Lb, D = cfg["U"], cfg["I"], cfg["L"], cfg["D"]
     Ul, Il = local_rows(U, world), local_rows(I, world)
     g = torch.Generator(device=dev); g.manual_seed(1 + rank)
-    P = torch.randn((Ul, 5, D), device=dev, generator=g) * 0.1; R = torch.randn((Il, D), device=dev, generator=g) * 0.1
+    P = torch.randn((Ul, 5, D), device=dev, generator=g).mul_(0.1); R = torch.randn((Il, D), device=dev, generator=g).mul_(0.1)
     g2 = torch.Generator(device=dev); g2.manual_seed(99)          # replicated tables: same on every rank
     Cat = torch.randn((4, D), device=dev, generator=g2) * 0.1; G = torch.randn((Lb, 5, D), device=dev, generator=g2) * 0.1
     item_cats = synth.make_item_categories(I)
     lab = synth.make_user_label_csr(Ul, Lb, seed=synth.BASE_SEED + 200 + rank)
     eng = ShardedEngine(Hyper(learner=args.learner, lr=0.001), P, R, Cat, G, rank, world, device=dev, max_rows=2 * B,
-                        adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab)
+                        adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab, adopt=True)
     del P
     run = DistRunner(eng)
     NB = 8
@@ -595,13 +597,16 @@ def main():
     ap.add_argument("--batch", type=int, default=262144)
     ap.add_argument("--preroll", type=int, default=40)
     ap.add_argument("--small", action="store_true", help="tiny tables: harness check only, not a bench number")
+    ap.add_argument("--cfg3", action="store_true", help="100M users / 10M recipes (row-sharded, 8 GPUs: 96 GB of tables+slots per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-catalog", action="store_true", help="skip the full-catalog top-K legs")
     ap.add_argument("--learner", default="adam", help="adam (reference default) | adagrad | rmsprop | sgd")
     ap.add_argument("--adam-mode", default="lazy", choices=["lazy", "lazy_exact", "dense"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    cfg = SMALL if args.small else CFG2
+    cfg = SMALL if args.small else (CFG3 if args.cfg3 else CFG2)
+    if args.cfg3 and int(os.environ.get("WORLD_SIZE", "1")) < 8:
+        sys.exit("--cfg3 needs the 8-GPU row-sharded run (torchrun --nproc-per-node 8)")
     if args.impl == "reference":
         run_reference(args, cfg, args.batch)
     elif int(os.environ.get("WORLD_SIZE", "1")) > 1:

@@ -45,15 +45,20 @@ def _ptr(t):
 class Engine:
     def __init__(self, hyper: Hyper, P, R, Cat, G, device="cuda:0", max_rows=1 << 16,
                  max_label_entries=None, adam_mode="lazy", item_cats=None, user_labels=None,
-                 user_label_csr=None):
+                 user_label_csr=None, adopt=False):
         self.lib = L.lib()                       # raises if the .so is missing
         if not torch.cuda.is_available():
             raise RuntimeError("foodrec_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.h = hyper
-        dev = lambda x: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x,
-                                        dtype=torch.float32).to(self.device).contiguous().clone()
+        # adopt=True: float32 tensors that already live on the device are used in place (no second copy of a
+        # table that fills a third of the HBM: cfg3 shards)
+        def dev(x):
+            if adopt and torch.is_tensor(x) and x.dtype == torch.float32 and x.device == self.device and x.is_contiguous():
+                return x
+            return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x,
+                                   dtype=torch.float32).to(self.device).contiguous().clone()
         self.P, self.R, self.Cat, self.G = dev(P), dev(R), dev(Cat), dev(G)
         self.U, five, self.D = self.P.shape
         assert five == 5 and self.Cat.shape == (4, self.D) and self.R.shape[1] == self.D
