@@ -92,10 +92,27 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   return FR_OK;
 }
 
+// ---------------------------------------------------------------- peer-memory exchange
+extern "C" int fr_shard_set_peers(fr_handle h, const fr_shard* sh, float* const* peer_rbuf, float* const* peer_rgrows) {
+  int rc = shard_check(h, sh); if (rc) return rc;
+  if (!peer_rbuf || !peer_rgrows) return fail(h, FR_ERR_ARG, "null peer table");
+  auto& w = h->sh;
+  for (int r = 0; r < sh->world; ++r) {
+    if (!peer_rbuf[r] || !peer_rgrows[r]) return fail(h, FR_ERR_ARG, "null peer buffer for rank %d", r);
+    w.peer_rbuf.dst[r] = reinterpret_cast<float4*>(peer_rbuf[r]);
+    w.peer_rgrows.dst[r] = reinterpret_cast<float4*>(peer_rgrows[r]);
+  }
+  w.peer_rbuf.world = w.peer_rgrows.world = sh->world;
+  w.peer_rbuf.rank = w.peer_rgrows.rank = sh->rank;
+  w.peer_rbuf.cap = w.peer_rgrows.cap = sh->cap;
+  return FR_OK;
+}
+
 // ---------------------------------------------------------------- 2. serve
 extern "C" int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rreq, float* rows, fr_stream s) {
   int rc = shard_check(h, sh); if (rc) return rc;
-  if (!rreq || !rows) return fail(h, FR_ERR_ARG, "null rreq/rows");
+  if (!rreq) return fail(h, FR_ERR_ARG, "null rreq");
+  if (!rows && h->sh.peer_rbuf.world != sh->world) return fail(h, FR_ERR_ARG, "rows is NULL but fr_shard_set_peers has not been called for this world");
   const size_t n = (size_t)sh->world * sh->cap;
   if ((rc = shard_ensure(h, 0, n))) return rc;
   cudaStream_t st = (cudaStream_t)s;
@@ -110,7 +127,8 @@ extern "C" int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rr
   if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE)    // requested rows must be current
     launch_item_catchup(h->NV, w.sortS.k[w.rs], (uint32_t)n, (float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R, T.last_R,
                         h->mc.DV, oc, l, w.n_valid);
-  launch_gather_rows((const float4*)T.R, rreq, (uint32_t)n, h->mc.DV, (float4*)rows, l);
+  PeerPtrs none{}; none.world = 0;
+  launch_gather_rows((const float4*)T.R, rreq, (uint32_t)n, h->mc.DV, (float4*)rows, rows ? none : w.peer_rbuf, l);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -177,8 +195,9 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
                                const float* rbuf, const float* packed_reduced, float* grows, float* out_scalars,
                                fr_stream s) {
   int rc = shard_check(h, sh); if (rc) return rc;
-  if (!b || !rbuf || !packed_reduced || !grows) return fail(h, FR_ERR_ARG, "null argument");
+  if (!b || !rbuf || !packed_reduced) return fail(h, FR_ERR_ARG, "null argument");
   auto& w = h->sh;
+  if (!grows && w.peer_rgrows.world != sh->world) return fail(h, FR_ERR_ARG, "grows is NULL but fr_shard_set_peers has not been called for this world");
   if (w.S <= 0 || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_update");
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
@@ -226,7 +245,8 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   ci.pieces = h->pieces_i; ci.uniq_counter = h->counters + 1;
   ItemPolParams ip{};
   ip.z = h->z; ip.g = h->g; ip.out = out; ip.mc = h->mc; ip.oc = oc;
-  launch_item_grad_pass(NV, ci, ip, (float4*)grows, l);
+  PeerPtrs none{}; none.world = 0;
+  launch_item_grad_pass(NV, ci, ip, (float4*)grows, grows ? none : w.peer_rgrows, l);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }

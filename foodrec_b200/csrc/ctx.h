@@ -50,6 +50,7 @@ struct fr_ctx {
     float4* pieces_s = nullptr;
     int ru = 0, ri = 0, rs = 0;            // which sort buffer holds each result
     int mode = 0, B = 0, S = 0, group = 1;
+    fr::PeerPtrs peer_rbuf{}, peer_rgrows{};   // fr_shard_set_peers: NVLink P2P exchange instead of all-to-alls
   } sh;
   fr::CatalogWs* cat = nullptr;     // full-catalog top-K (catalog.cu): index + pass workspace
   // staging for fr_train_step_host

@@ -87,7 +87,11 @@ void launch_series_rebuild(double* cser, const float* lr_hist, int step, float b
 void launch_item_catchup(int NV, const uint32_t* keys, uint32_t n, float4* R, float4* m, float4* v,
                          int32_t* last, int DV, const OptConsts& oc, const Launch& l,
                          const uint32_t* n_dev = nullptr);
-void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, float4* gbuf, const Launch& l);
+// Peer-memory exchange (NVLink P2P): instead of staging rows for an all-to-all, the producing kernel stores each
+// row straight into the consumer rank's buffer.  dst[w] = rank w's buffer [W*cap, DV]; a row for rank w's slot j goes
+// to dst[w] + (my_rank*cap + j)*DV -- exactly where the all-to-all would have put it.  world == 0: not in use.
+struct PeerPtrs { float4* dst[8]; int world, rank, cap; };
+void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, float4* gbuf, const PeerPtrs& peers, const Launch& l);
 
 // ---- row-sharded training helpers (train_shard.cu)
 struct ShardPlanParams {
@@ -110,7 +114,7 @@ void launch_shard_heads(const ShardPlanParams& p, const Launch& l);
 void launch_shard_fill(const ShardPlanParams& p, const Launch& l);
 void launch_serve_keys(const int32_t* rreq, uint32_t n, uint32_t items_per_rank, uint32_t* keys, uint32_t* n_valid,
                        const Launch& l);
-void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const Launch& l);
+void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const PeerPtrs& peers, const Launch& l);
 void launch_add_inplace(float4* dst, const float4* src, int64_t n4, const Launch& l);
 void launch_mean(const float4* x, int64_t n4, double* partials, float* out_slot, double count, const Launch& l);
 void launch_write_counters(const uint32_t* counters, float* out, const Launch& l);

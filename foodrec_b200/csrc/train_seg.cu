@@ -412,15 +412,21 @@ struct ItemPol {
 template <int NVV>
 struct ItemGradPol : ItemPol<NVV, OPT_GENERIC> {
   float4* gbuf;                       // [W*cap, DV], key = slot
+  PeerPtrs peers;                     // world > 0: the finished row goes straight to its owner's receive buffer
   struct State {};
   __device__ __forceinline__ void prefetch_state(uint32_t, int) const {}
   __device__ __forceinline__ void load_state(State&, uint32_t, int) const {}
   __device__ __forceinline__ void apply(State&, uint32_t key, float4 (&acc)[1][NVV], int lane) const {
     const int DVv = this->p.mc.DV;
+    float4* dst = gbuf + (size_t)key * DVv;
+    if (peers.world > 0) {
+      const uint32_t o = key / (uint32_t)peers.cap, j = key % (uint32_t)peers.cap;
+      dst = peers.dst[o] + ((size_t)peers.rank * peers.cap + j) * DVv;
+    }
 #pragma unroll
     for (int k = 0; k < NVV; ++k) {
       const int i = lane + 32 * k;
-      if (i < DVv) gbuf[(size_t)key * DVv + i] = acc[0][k];
+      if (i < DVv) dst[i] = acc[0][k];
     }
   }
 };
@@ -708,9 +714,10 @@ void launch_item_pass(int NV, const SegCommon& c, const ItemPolParams& p, const 
   const int opt = opt_of(p.oc.learner, p.oc.adam_mode);
   FR_DISPATCH_NV_OPT(NV, opt, { ItemPol<NV_, OPT_> pol{p}; launch_seg(c, pol, p.mc.DV, false, l); });
 }
-void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, float4* gbuf, const Launch& l) {
-  if (NV == 1) { ItemGradPol<1> pol{{p}, gbuf}; launch_seg(c, pol, p.mc.DV, false, l); }
-  else { ItemGradPol<2> pol{{p}, gbuf}; launch_seg(c, pol, p.mc.DV, false, l); }
+void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, float4* gbuf, const PeerPtrs& peers,
+                           const Launch& l) {
+  if (NV == 1) { ItemGradPol<1> pol{{p}, gbuf, peers}; launch_seg(c, pol, p.mc.DV, false, l); }
+  else { ItemGradPol<2> pol{{p}, gbuf, peers}; launch_seg(c, pol, p.mc.DV, false, l); }
 }
 void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, const Launch& l) {
   // <= ~100 labels, runs of thousands of entries: 8 chunks per warp-tile

@@ -133,9 +133,22 @@ class ShardedEngine:
         L.check(e.handle, e.lib.fr_shard_plan(e.handle, C.byref(self._b), C.byref(self._sh), _ptr(self.req), e._stream()))
         return self.req
 
+    def set_peers(self, rbuf_ptrs, rgrows_ptrs):
+        """fr_shard_set_peers: device pointers of every rank's rbuf / rgrows as mapped into THIS process (own
+        buffers at index rank).  From then on serve() / update() store rows straight into the consumer's buffer
+        over NVLink and the runner replaces the two row all-to-alls by barriers."""
+        W = self.world
+        assert len(rbuf_ptrs) == W and len(rgrows_ptrs) == W
+        a = (C.c_void_p * W)(*[C.c_void_p(int(x)) for x in rbuf_ptrs])
+        b = (C.c_void_p * W)(*[C.c_void_p(int(x)) for x in rgrows_ptrs])
+        sh = self._shard(1)
+        L.check(self.e.handle, self.e.lib.fr_shard_set_peers(self.e.handle, C.byref(sh), a, b))
+        self.p2p = True
+
     def serve(self):
         e = self.e
-        L.check(e.handle, e.lib.fr_shard_serve(e.handle, C.byref(self._sh), _ptr(self.rreq), _ptr(self.rows), e._stream()))
+        rows = None if getattr(self, "p2p", False) else self.rows
+        L.check(e.handle, e.lib.fr_shard_serve(e.handle, C.byref(self._sh), _ptr(self.rreq), _ptr(rows), e._stream()))
         return self.rows
 
     def forward(self):
@@ -146,8 +159,9 @@ class ShardedEngine:
 
     def update(self, write_personal=False):
         e = self.e
+        grows = None if getattr(self, "p2p", False) else self.grows
         L.check(e.handle, e.lib.fr_shard_update(e.handle, C.byref(self._b), C.byref(self._sh), int(bool(write_personal)),
-                                                _ptr(self.rbuf), _ptr(self.packed), _ptr(self.grows), _ptr(e.out), e._stream()))
+                                                _ptr(self.rbuf), _ptr(self.packed), _ptr(grows), _ptr(e.out), e._stream()))
         return self.grows
 
     def apply(self):
@@ -207,16 +221,45 @@ class DistRunner:
         self.dist, self.eng = dist, engine
         assert dist.get_world_size() == engine.world and dist.get_rank() == engine.rank
 
+    def enable_p2p(self):
+        """Fuse the two row exchanges into the producing kernels: rbuf / rgrows are re-allocated as symmetric
+        memory (torch.distributed._symmetric_memory: one CUDA IPC rendezvous over the group), every rank learns the
+        peers' device pointers, and gather / gradient kernels store rows straight into the consumer's buffer over
+        NVLink.  The all-to-alls become barriers.  Same results bit for bit (same rows in the same places)."""
+        import torch.distributed._symmetric_memory as symm
+        g = self.eng
+        n = g.world * g.cap
+        group = self.dist.group.WORLD
+        bufs = []
+        for name in ("rbuf", "rgrows"):
+            t = symm.empty((n, g.e.D), dtype=torch.float32, device=g.device)
+            hdl = symm.rendezvous(t, group.group_name)
+            setattr(g, name, t)
+            bufs.append(hdl)
+        self._symm = bufs
+        g.set_peers(list(bufs[0].buffer_ptrs), list(bufs[1].buffer_ptrs))
+        self._sync = torch.zeros(1, device=g.device)
+
+    def _barrier(self):
+        self.dist.all_reduce(self._sync)                 # stream-ordered: every rank has finished the phase before
+
     def step(self, write_personal=False):
         d, g = self.dist, self.eng
+        p2p = getattr(g, "p2p", False)
         g.plan()
         d.all_to_all_single(g.rreq, g.req)               # requests -> owners
-        g.serve()
-        d.all_to_all_single(g.rbuf, g.rows)              # recipe rows -> requesters (NVLink)
+        g.serve()                                        # p2p: rows land in the requesters' rbuf from inside the kernel
+        if p2p:
+            self._barrier()
+        else:
+            d.all_to_all_single(g.rbuf, g.rows)          # recipe rows -> requesters (NVLink)
         g.forward()
         d.all_reduce(g.packed)                           # loss, sum|g|^2, dCat, dG
-        g.update(write_personal)
-        d.all_to_all_single(g.rgrows, g.grows)           # finished gradient rows -> owners
+        g.update(write_personal)                         # p2p: gradient rows land in the owners' rgrows
+        if p2p:
+            self._barrier()
+        else:
+            d.all_to_all_single(g.rgrows, g.grows)       # finished gradient rows -> owners
         return g.apply()
 
 
@@ -252,16 +295,25 @@ class LocalRunner:
             for s, gs in enumerate(self.engs):
                 dst[s].copy_(getattr(gs, src_attr).view(W, gs.cap, -1)[r])
 
+    def enable_p2p(self):
+        """Same kernels and peer tables as DistRunner.enable_p2p; here every "peer" is another engine of this
+        process, so the pointers are plain device pointers and the barriers are stream order."""
+        rb = [g.rbuf.data_ptr() for g in self.engs]
+        rg = [g.rgrows.data_ptr() for g in self.engs]
+        for g in self.engs:
+            g.set_peers(rb, rg)
+
     def step(self, write_personal=False):
+        p2p = getattr(self.engs[0], "p2p", False)
         for g in self.engs: g.plan()
         self._all_to_all("req", "rreq")
         for g in self.engs: g.serve()
-        self._all_to_all("rows", "rbuf")
+        if not p2p: self._all_to_all("rows", "rbuf")
         for g in self.engs: g.forward()
         total = torch.stack([g.packed for g in self.engs]).sum(0)       # rank order, like a ring on W=2
         for g in self.engs: g.packed.copy_(total)
         for g in self.engs: g.update(write_personal)
-        self._all_to_all("grows", "rgrows")
+        if not p2p: self._all_to_all("grows", "rgrows")
         return [g.apply() for g in self.engs]
 
     def catalog_topk(self, users_local_per_rank, K=100):

@@ -191,6 +191,12 @@ typedef struct {
   int32_t global_batch;     /* groups summed over ranks: the loss mean divides by it */
 } fr_shard;
 int64_t fr_shard_packed_len(fr_handle h);
+/* Peer-memory exchange over NVLink instead of the two row all-to-alls: peer_rbuf[w] / peer_rgrows[w] are rank w's
+ * receive buffers ([W*cap, D] each) mapped into this process (CUDA IPC; the caller's own buffers at index rank).
+ * Afterwards fr_shard_serve(rows = NULL) stores every gathered recipe row straight into the requester's rbuf and
+ * fr_shard_update(grows = NULL) every finished gradient row into its owner's rgrows -- the place the all-to-all
+ * would have put it.  The caller replaces each all-to-all by a barrier (all ranks have finished the phase). */
+int fr_shard_set_peers(fr_handle h, const fr_shard* sh, float* const* peer_rbuf, float* const* peer_rgrows);
 int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh, int32_t* req, fr_stream s);
 int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rreq, float* rows, fr_stream s);
 int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* sh, const float* rbuf, float* packed,

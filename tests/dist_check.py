@@ -36,6 +36,8 @@ def main():
                                 user_label_csr_local=sharded.shard_label_csr(off, cols.astype(np.int32), rank, W, p.U),
                                 max_label_entries=4096 * p.L)
     run = sharded.DistRunner(eng)
+    if os.environ.get("DIST_CHECK_P2P"):
+        run.enable_p2p()                     # fused gather/gradient + NVLink peer stores instead of the row all-to-alls
     single = None
     if rank == 0:
         single = Engine(h, p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, device=dev, max_rows=4096, adam_mode="lazy",

@@ -171,3 +171,27 @@ def test_sharded_checkpoint_resume(tmp_path, adam_mode):
         else:
             assert_close(tc[k], ta[k], rtol=1e-6, what=k)
     assert a[0].e.step == c[0].e.step == 4
+
+
+@pytest.mark.parametrize("W,bpr", [(2, True), (4, False)])
+def test_peer_store_exchange_equals_all_to_all(W, bpr):
+    """fr_shard_set_peers: gather and gradient kernels store rows straight into the consumer rank's buffer (the
+    NVLink P2P path; here the peers are engines of this process).  Bit-identical to the staged all-to-all path."""
+    p = Problem(403, 257, 9, 64, seed=62)
+    _, a = build(p, W, "adam", "lazy")
+    _, b = build(p, W, "adam", "lazy")
+    ra, rb = sharded.LocalRunner(a), sharded.LocalRunner(b)
+    rb.enable_p2p()
+    for s in range(4):
+        f = p.bpr(300, seed=500 + s) if bpr else p.pointwise(300, seed=500 + s)
+        idx = sharded.route_batch(f["user_input"], W)
+        for engs in (a, b):
+            for r, g in enumerate(engs):
+                ix = idx[r]
+                g.set_batch(f["user_input"][ix] // W, f["item_input"][ix], labels=None if bpr else f["labels"][ix],
+                            neg_items=f["neg_item_input"][ix] if bpr else None, global_batch=300)
+        oa = ra.step(write_personal=(s == 0)); ob = rb.step(write_personal=(s == 0))
+        assert torch.equal(oa[0], ob[0])
+    ta, tb_ = gather(a, p), gather(b, p)
+    for k in ("P", "R", "Cat", "G"):
+        np.testing.assert_array_equal(ta[k], tb_[k], err_msg=k)
