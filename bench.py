@@ -274,8 +274,14 @@ def run_sharded(args, cfg, B):
                         adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab, adopt=True)
     del P
     run = DistRunner(eng)
-    if args.p2p:
-        run.enable_p2p()
+    p2p = False
+    if not args.no_p2p:
+        try:
+            run.enable_p2p()
+            p2p = True
+        except Exception as ex:             # no symmetric memory on this box: the staged all-to-all path
+            if rank == 0:
+                print(f"peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using all-to-alls", file=sys.stderr)
     NB = 8
     pin, devb = [], []
     for k in range(NB):
@@ -371,7 +377,7 @@ def run_sharded(args, cfg, B):
                        "l2": "per-step working set >> 126 MB L2; 8 distinct batches cycled", "preroll_steps": args.preroll,
                        "parallelism": f"row-sharded x{world}: P by user%N (samples loaded at the user owner), R by recipe%N; " + (
                            f"id all-to-all + recipe rows / gradient rows stored into peer memory over NVLink by the gather / "
-                           f"gradient kernels (cap {eng.cap}/pair, 2 barriers) + 1 packed all-reduce per step" if args.p2p else
+                           f"gradient kernels (cap {eng.cap}/pair, 2 barriers) + 1 packed all-reduce per step" if p2p else
                            f"3 all-to-alls (ids, rows, grad rows, cap {eng.cap}/pair) + 1 packed all-reduce per step")},
             "clocks": clk, "gpu_launches": int(launches), "roofline": None,
             "e2e": {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
@@ -601,8 +607,8 @@ def main():
     ap.add_argument("--batch", type=int, default=262144)
     ap.add_argument("--preroll", type=int, default=40)
     ap.add_argument("--small", action="store_true", help="tiny tables: harness check only, not a bench number")
-    ap.add_argument("--p2p", action="store_true", help="N>1: store exchanged rows straight into peer memory (NVLink) from the "
-                    "gather / gradient kernels instead of the two row all-to-alls")
+    ap.add_argument("--no-p2p", action="store_true", help="N>1: stage exchanged rows and move them with NCCL all-to-alls instead "
+                    "of storing them straight into peer memory (NVLink) from the gather / gradient kernels")
     ap.add_argument("--cfg3", action="store_true", help="100M users / 10M recipes (row-sharded, 8 GPUs: 96 GB of tables+slots per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-catalog", action="store_true", help="skip the full-catalog top-K legs")

@@ -14,6 +14,7 @@ Two runners drive the five C-ABI phases (``fr_shard_*``):
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -239,9 +240,15 @@ class DistRunner:
         self._symm = bufs
         g.set_peers(list(bufs[0].buffer_ptrs), list(bufs[1].buffer_ptrs))
         self._sync = torch.zeros(1, device=g.device)
+        self._symm_barrier = hasattr(bufs[0], "barrier") and os.environ.get("FOODREC_P2P_NCCL_BARRIER") is None
 
     def _barrier(self):
-        self.dist.all_reduce(self._sync)                 # stream-ordered: every rank has finished the phase before
+        # stream-ordered: when it completes every rank has finished the phase before it.  The symmetric-memory
+        # handle offers a signal-pad barrier (a few microseconds, no NCCL launch); fall back to a 1-element all-reduce.
+        if self._symm_barrier:
+            self._symm[0].barrier(channel=0)
+        else:
+            self.dist.all_reduce(self._sync)
 
     def step(self, write_personal=False):
         d, g = self.dist, self.eng
