@@ -66,6 +66,7 @@ _PROTOS = {
     "fr_set_tables": (C.c_int, [C.c_void_p, C.POINTER(fr_tables)]),
     "fr_get_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "fr_set_step": (C.c_int, [C.c_void_p, C.c_int64]),
+    "fr_set_health_blend": (C.c_int, [C.c_void_p, C.c_int32]),
     "fr_fwd_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "fr_train_step": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_train_step_host": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.c_int32, C.c_void_p, C.c_void_p]),

@@ -173,6 +173,14 @@ OptConsts make_oc(const fr_ctx* h, int64_t step) {
   return oc;
 }
 
+extern "C" int fr_set_health_blend(fr_handle h, int32_t enable) {
+  if (!h) return FR_ERR_ARG;
+  if (enable && (!h->has_tables || !h->tab.user_label_off || !h->tab.user_label_idx))
+    return fail(h, FR_ERR_STATE, "the health term needs the resident user-label CSR (tables.user_label_off/idx)");
+  h->health_blend = enable != 0;
+  return FR_OK;
+}
+
 extern "C" int fr_fwd_score(fr_handle h, const int32_t* users, const int32_t* items, const float* cats,
                             int32_t n, float* scores, fr_stream s) {
   if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
@@ -180,7 +188,7 @@ extern "C" int fr_fwd_score(fr_handle h, const int32_t* users, const int32_t* it
   if (!cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cats is NULL and no item_cats table");
   Launch l{h->sm_count, (cudaStream_t)s};
   launch_fwd_score(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, items,
-                   (const float4*)(cats ? cats : h->tab.item_cats), cats ? 0 : 1, n, scores, l);
+                   (const float4*)(cats ? cats : h->tab.item_cats), cats ? 0 : 1, n, scores, health_of(h), l);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -195,7 +203,7 @@ extern "C" int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int
   Launch l{h->sm_count, (cudaStream_t)s};
   launch_eval_sampled(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, cand,
                       n_cand, n_users, cand_stride, (const float4*)cand_cats, (const float4*)h->tab.item_cats, K,
-                      topk_ids, gt_rank, scores, l);
+                      topk_ids, gt_rank, scores, health_of(h), l);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }

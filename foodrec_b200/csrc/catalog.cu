@@ -87,14 +87,17 @@ struct UserSrc {
   const int32_t* uidx;    // nullable: row -> user id
   int row0;               // first query row of this pass
   const uint32_t* perm;   // nullable: pass row -> query row of the pass (users sorted by best mask group)
+  HealthBlend hb;         // G != nullptr: rows are scored with the health term (table queries only)
 };
 __device__ __forceinline__ int query_row(const UserSrc& s, int j) {      // index into the caller's user list / outputs
   return s.row0 + (s.perm ? (int)__ldg(s.perm + j) : j);
 }
-__device__ __forceinline__ const float4* user_row(const UserSrc& s, int j, int DV) {
+__device__ __forceinline__ int user_of(const UserSrc& s, int j) {
   const int qr = query_row(s, j);
-  const size_t u = s.uidx ? (size_t)__ldg(s.uidx + qr) : (size_t)qr;
-  return s.P + u * 5 * DV;
+  return s.uidx ? __ldg(s.uidx + qr) : qr;
+}
+__device__ __forceinline__ const float4* user_row(const UserSrc& s, int j, int DV) {
+  return s.P + (size_t)user_of(s, j) * 5 * DV;
 }
 
 // key of a query row = the mask group with the largest category term a/|g| * sum_{c in g} <P[u,0],Cat[c]>
@@ -104,8 +107,11 @@ cat_user_key_kernel(UserSrc src, int n_rows, const float4* __restrict__ Cat, int
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (j >= n_rows) return;
-  float4 p0[NV];
-  load_row_ro<NV>(p0, user_row(src, j, DV), DV, lane);
+  float4 pr5[5][NV];
+#pragma unroll
+  for (int s5 = 0; s5 < 5; ++s5) load_row_ro<NV>(pr5[s5], user_row(src, j, DV) + (size_t)s5 * DV, DV, lane);
+  health_blend_rows<NV>(pr5, src.hb, user_of(src, j), DV, lane);
+  float4 (&p0)[NV] = pr5[0];
   float h[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -146,6 +152,7 @@ cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restri
     const float4* prow = user_row(src, j, DV);
 #pragma unroll
     for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], prow + (size_t)s * DV, DV, lane);
+    health_blend_rows<NV>(pr, src.hb, user_of(src, j), DV, lane);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       double acc = 0.0;
@@ -241,11 +248,12 @@ __device__ __forceinline__ double exact_score_warp(const float* sP, const double
   return a * (hs / n) + oma * (acc / n);
 }
 
-__device__ __forceinline__ void load_user_exact(const float4* prow, const float* __restrict__ Cat, int D, float* sP,
+__device__ __forceinline__ void load_user_exact(const UserSrc& src, int row, const float* __restrict__ Cat, int D, float* sP,
                                                 double* sH, int tid, int nthreads) {
-  const float* pf = reinterpret_cast<const float*>(prow);
+  const float* pf = reinterpret_cast<const float*>(user_row(src, row, D / 4));
   for (int i = tid; i < 5 * D; i += nthreads) sP[i] = __ldg(pf + i);
   __syncthreads();
+  if (src.hb.G) { health_blend_flat(sP, src.hb, user_of(src, row), D, tid, nthreads); __syncthreads(); }
   const int warp = tid >> 5, lane = tid & 31;
   if (warp < 4) {
     double acc = 0.0;
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(FIN_THREADS) cat_finalize_kernel(const FinPara
     return;
   }
   const int nF = s_nF;
-  load_user_exact(user_row(f.src, row, f.D / 4), f.Cat, f.D, sP, sH, tid, FIN_THREADS);
+  load_user_exact(f.src, row, f.Cat, f.D, sP, sH, tid, FIN_THREADS);
   // Re-score, ONE THREAD PER SURVIVOR.  (A warp per survivor made this stage a chain of dependent
   // L2/HBM reads -- id, mask, row -- per survivor: 35 % of a cfg2 run.)  Ids and masks of all survivors
   // are fetched first; the fp64 user row sum_{c in g} P[u,1+c] is built once per mask that occurs; then
@@ -447,7 +455,7 @@ __global__ void __launch_bounds__(EXS_THREADS) cat_exact_scores_kernel(const Fin
   const int slot = slot0 + blockIdx.y;
   if (slot >= min(*f.ovf_count, f.m_pad)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  load_user_exact(user_row(f.src, f.ovf_list[slot], f.D / 4), f.Cat, f.D, sP, sH, tid, EXS_THREADS);
+  load_user_exact(f.src, f.ovf_list[slot], f.Cat, f.D, sP, sH, tid, EXS_THREADS);
   double* sc = scratch + (size_t)blockIdx.y * I;
   const int i0 = blockIdx.x * EXS_ITEMS, i1 = min(I, i0 + EXS_ITEMS);
   for (int item = i0 + warp; item < i1; item += EXS_THREADS / 32) {
@@ -475,7 +483,7 @@ __global__ void __launch_bounds__(EX_THREADS) cat_exact_kernel(const FinParams f
     const int row = f.ovf_list[slot];
     __syncthreads();
     if (!scores_ready) {
-      load_user_exact(user_row(f.src, row, f.D / 4), f.Cat, f.D, sP, sH, tid, EX_THREADS);
+      load_user_exact(f.src, row, f.Cat, f.D, sP, sH, tid, EX_THREADS);
       for (int item = warp; item < I; item += EX_THREADS / 32) {
         const double s = exact_score_warp(sP, sH, f.R + (size_t)item * f.D, __ldg(f.item_cats + item), f.D, lane, f.a, f.oma);
         if (lane == 0) sc[item] = s;
@@ -727,6 +735,7 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
   if (!h->cat || !h->cat->prepared) return fail(h, FR_ERR_STATE, "fr_catalog_prepare first");
   if (K <= 0 || K > CAT_MAXK) return fail(h, FR_ERR_UNSUPPORTED, "K must be in [1,%d], got %d", CAT_MAXK, K);
   if (n_users == 0) return FR_OK;
+  if (P_rows && h->health_blend) return fail(h, FR_ERR_ARG, "the health term needs user ids (labels): pass users, not dense P_rows");
   CatalogWs& w = *h->cat;
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const int CG = w.cta_group, BMC = CAT_BM * CG;
@@ -750,7 +759,7 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     while (n_split > 1 && (size_t)n_split * m_pad > (size_t)w.mp_cap) --n_split;
     const int n_lists = n_split * NSET;
     const int tps = std::max(1, (w.n_tiles + n_split - 1) / n_split);
-    UserSrc src{reinterpret_cast<const float4*>(P_rows ? P_rows : h->tab.P), P_rows ? nullptr : users, row0, nullptr};
+    UserSrc src{reinterpret_cast<const float4*>(P_rows ? P_rows : h->tab.P), P_rows ? nullptr : users, row0, nullptr, health_of(h)};
 
     std::array<cudaEvent_t, 5>* ev = nullptr;
     if (timing) {

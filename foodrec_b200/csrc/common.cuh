@@ -35,6 +35,9 @@ __device__ __forceinline__ void mad4_rn(float4& acc, const float s, const float4
   acc.x = __fadd_rn(acc.x, __fmul_rn(s, v.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(s, v.y));
   acc.z = __fadd_rn(acc.z, __fmul_rn(s, v.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(s, v.w));
 }
+__device__ __forceinline__ float4 div4_rn(const float4 v, const float n) {
+  return make_float4(__fdiv_rn(v.x, n), __fdiv_rn(v.y, n), __fdiv_rn(v.z, n), __fdiv_rn(v.w, n));
+}
 __device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
@@ -97,6 +100,44 @@ __device__ __forceinline__ void store_row(float4* row, const float4 (&src)[NV], 
   for (int k = 0; k < NV; ++k) {
     const int i = lane + 32 * k;
     if (i < DV) st_stream(row + i, src[k]);
+  }
+}
+
+// health term: pr += alpha * (sum_l G[l]) / n over the labels of user u (see internal.h:HealthBlend)
+template <int NV, class HB>
+__device__ __forceinline__ void health_blend_rows(float4 (&pr)[5][NV], const HB& hb, int u, int DV, int lane) {
+  if (!hb.G) return;
+  const int b = hb.lab_off[u], e = hb.lab_off[u + 1];
+  if (e <= b) return;
+  const float n = (float)(e - b);
+#pragma unroll
+  for (int s = 0; s < 5; ++s)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < DV) {
+        float4 acc = f4zero();
+        for (int x = b; x < e; ++x) acc = add4(acc, __ldg(hb.G + ((size_t)hb.lab_idx[x] * 5 + s) * DV + i));
+        float4 q = div4_rn(acc, n);
+        pr[s][k].x = __fadd_rn(pr[s][k].x, __fmul_rn(hb.alpha, q.x));
+        pr[s][k].y = __fadd_rn(pr[s][k].y, __fmul_rn(hb.alpha, q.y));
+        pr[s][k].z = __fadd_rn(pr[s][k].z, __fmul_rn(hb.alpha, q.z));
+        pr[s][k].w = __fadd_rn(pr[s][k].w, __fmul_rn(hb.alpha, q.w));
+      }
+    }
+}
+// the same on a flat [5*D] float row in shared memory (block-wide)
+template <class HB>
+__device__ __forceinline__ void health_blend_flat(float* sP, const HB& hb, int u, int D, int tid, int nthreads) {
+  if (!hb.G) return;
+  const int b = hb.lab_off[u], e = hb.lab_off[u + 1];
+  if (e <= b) return;
+  const float n = (float)(e - b);
+  const float* Gf = reinterpret_cast<const float*>(hb.G);
+  for (int i = tid; i < 5 * D; i += nthreads) {
+    float acc = 0.f;
+    for (int x = b; x < e; ++x) acc = __fadd_rn(acc, __ldg(Gf + (size_t)hb.lab_idx[x] * 5 * D + i));
+    sP[i] = __fadd_rn(sP[i], __fmul_rn(hb.alpha, __fdiv_rn(acc, n)));
   }
 }
 

@@ -52,6 +52,7 @@ struct fr_ctx {
     int mode = 0, B = 0, S = 0, group = 1;
     fr::PeerPtrs peer_rbuf{}, peer_rgrows{};   // fr_shard_set_peers: NVLink P2P exchange instead of all-to-alls
   } sh;
+  bool health_blend = false;        // fr_set_health_blend: inference scores P[u] + alpha * mean G[labels(u)]
   fr::CatalogWs* cat = nullptr;     // full-catalog top-K (catalog.cu): index + pass workspace
   // staging for fr_train_step_host
   void* stage = nullptr; size_t stage_bytes = 0;
@@ -128,6 +129,11 @@ static inline int alloc_sort(fr_ctx* h, SortBufs& s, size_t cap) {
 
 
 void catalog_free(fr_ctx* h);
+static inline fr::HealthBlend health_of(const fr_ctx* h) {
+  fr::HealthBlend hb{nullptr, nullptr, nullptr, 0.f};
+  if (h->health_blend) { hb.G = reinterpret_cast<const float4*>(h->tab.G); hb.lab_off = h->tab.user_label_off; hb.lab_idx = h->tab.user_label_idx; hb.alpha = h->mc.alpha; }
+  return hb;
+}
 int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st);
 float adam_lr_t(const fr_ctx* h);
 fr::OptConsts make_oc(const fr_ctx* h, int64_t step);

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(FR_THREADS)
 fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, const float4* __restrict__ Cat,
                  int DV, const int32_t* __restrict__ users, const int32_t* __restrict__ items,
                  const float4* __restrict__ cats, int cats_by_item, int n, float a, float oma,
-                 float* __restrict__ scores) {
+                 float* __restrict__ scores, const HealthBlend hb) {
   extern __shared__ float4 sCat[];
   for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) sCat[i] = Cat[i];
   __syncthreads();
@@ -54,6 +54,7 @@ fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, con
       if (u != cur_u) {
 #pragma unroll
         for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
+        health_blend_rows<NV>(pr, hb, u, DV, lane);
         cur_u = u;
       }
       const int it = items[r];
@@ -66,16 +67,16 @@ fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, con
 
 void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                       const int32_t* users, const int32_t* items, const float4* cats,
-                      int cats_by_item, int n, float* scores, const Launch& l) {
+                      int cats_by_item, int n, float* scores, const HealthBlend& hb, const Launch& l) {
   if (n <= 0) return;
   int grid = (n + 8 * FR_WARPS_PER_BLOCK - 1) / (8 * FR_WARPS_PER_BLOCK);
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   const size_t smem = (size_t)4 * mc.DV * sizeof(float4);
   ++g_launches;
   if (mc.DV <= 32)
-    fwd_score_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores);
+    fwd_score_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb);
   else
-    fwd_score_kernel<2><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores);
+    fwd_score_kernel<2><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb);
 }
 
 // One warp per test user.  Candidate j lives in lane j&31, slot j>>5 (<= 128 candidates).
@@ -88,7 +89,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
                     const int32_t* __restrict__ cand, const int32_t* __restrict__ n_cand, int n_users,
                     int stride, const float4* __restrict__ cand_cats, const float4* __restrict__ item_cats,
                     int K, int32_t* __restrict__ topk_ids, int32_t* __restrict__ gt_rank,
-                    float* __restrict__ scores_out) {
+                    float* __restrict__ scores_out, const HealthBlend hb) {
   extern __shared__ float4 sCat[];
   for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) sCat[i] = Cat[i];
   __syncthreads();
@@ -101,6 +102,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
     float4 pr[5][NV];
 #pragma unroll
     for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
+    health_blend_rows<NV>(pr, hb, u, DV, lane);
     int id[EVAL_SLOTS]; float sc[EVAL_SLOTS]; bool alive[EVAL_SLOTS];
 #pragma unroll
     for (int q = 0; q < EVAL_SLOTS; ++q) {
@@ -166,7 +168,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
 void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                          const int32_t* users, const int32_t* cand, const int32_t* n_cand, int n_users,
                          int stride, const float4* cand_cats, const float4* item_cats, int K,
-                         int32_t* topk_ids, int32_t* gt_rank, float* scores, const Launch& l) {
+                         int32_t* topk_ids, int32_t* gt_rank, float* scores, const HealthBlend& hb, const Launch& l) {
   if (n_users <= 0) return;
   int grid = (n_users + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
@@ -174,10 +176,10 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   ++g_launches;
   if (mc.DV <= 32)
     eval_sampled_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, mc.a, mc.oma, users, cand, n_cand, n_users,
-                                                             stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores);
+                                                             stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb);
   else
     eval_sampled_kernel<2><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, mc.a, mc.oma, users, cand, n_cand, n_users,
-                                                             stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores);
+                                                             stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb);
 }
 
 }  // namespace fr

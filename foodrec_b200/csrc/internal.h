@@ -84,13 +84,19 @@ extern unsigned long long g_launches;   // kernels launched by this library (ben
 
 struct Launch { int sm_count; cudaStream_t st; cudaEvent_t mid = nullptr; /* recorded between chunk and combine */ };
 
+// Health term at inference (fr_set_health_blend): the user row is scored as
+//   P'[u] = P[u] + alpha * (sum_{l in labels(u)} G[l]) / |labels(u)|
+// i.e. what Write_Memory materialises on a personal step (Model_Recommender.py:170-198), without writing it.
+// G == nullptr: off.  Products and sums are rounded separately (no FMA) so the host restatement is bit-exact.
+struct HealthBlend { const float4* G; const int32_t* lab_off; const int32_t* lab_idx; float alpha; };
+
 void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                       const int32_t* users, const int32_t* items, const float4* cats,
-                      int cats_by_item, int n, float* scores, const Launch& l);
+                      int cats_by_item, int n, float* scores, const HealthBlend& hb, const Launch& l);
 
 void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                          const int32_t* users, const int32_t* cand, const int32_t* n_cand, int n_users,
                          int stride, const float4* cand_cats, const float4* item_cats, int K,
-                         int32_t* topk_ids, int32_t* gt_rank, float* scores, const Launch& l);
+                         int32_t* topk_ids, int32_t* gt_rank, float* scores, const HealthBlend& hb, const Launch& l);
 
 }  // namespace fr

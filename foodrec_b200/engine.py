@@ -251,6 +251,10 @@ class Engine:
             L.check(self.handle, self.lib.fr_adam_flush(self.handle, self._stream()))
         self._dirty = False
 
+    def set_health_blend(self, on=True):
+        """Score users as P[u] + alpha * mean G[labels(u)] at inference (score, eval_sampled_topk, catalog_topk)."""
+        L.check(self.handle, self.lib.fr_set_health_blend(self.handle, int(bool(on))))
+
     def score(self, users, items, categories=None):
         self.flush()
         u, it = self._i32(users), self._i32(items)

@@ -116,6 +116,12 @@ int fr_set_tables(fr_handle h, const fr_tables* t);
 int fr_get_step(fr_handle h, int64_t* step);
 int fr_set_step(fr_handle h, int64_t step);
 
+/* Health term at inference (BASELINE configs[4]): when enabled, fr_fwd_score, fr_eval_sampled_topk and
+ * fr_catalog_topk score every user with  P'[u] = P[u] + alpha * mean_{l in labels(u)} G[l]  -- the row
+ * Write_Memory materialises on a personal step (Model_Recommender.py:170-198) -- gathered and blended inside
+ * the kernels, nothing is written.  Needs tables.user_label_off/idx.  Training is unaffected. */
+int fr_set_health_blend(fr_handle h, int32_t enable);
+
 /* inference, Model_Recommender.py:56-97 -> scores[n].  cats NULL -> item_cats table. */
 int fr_fwd_score(fr_handle h, const int32_t* users, const int32_t* items, const float* cats,
                  int32_t n, float* scores, fr_stream s);

@@ -73,6 +73,26 @@ def _segment_sum(idx, values):
     return uniq, out
 
 
+def health_rows(P, G, user_labels, alpha, users=None):
+    """Inference-time health term (extension, BASELINE configs[4]): the rows Write_Memory would materialise
+    on a personal step (``Model_Recommender.py:170-198``), ``P[u] + alpha * (sum_l lam_ul G[l]) / sum_l lam_ul``,
+    in float32 with the operation order of the CUDA helper (labels ascending; sum, divide, scale, add -- each
+    rounded), so the result is bit-identical.  Users without labels keep their row."""
+    P = np.asarray(P, np.float32); G = np.asarray(G, np.float32)
+    users = np.arange(P.shape[0]) if users is None else np.asarray(users, np.int64)
+    out = P[users].copy()
+    a = np.float32(alpha)
+    for k, u in enumerate(users):
+        labs = np.nonzero(np.asarray(user_labels[u]))[0]
+        if labs.size == 0:
+            continue
+        acc = np.zeros_like(G[0])
+        for l in labs:
+            acc = acc + G[l]
+        out[k] = out[k] + a * (acc / np.float32(labs.size))
+    return out
+
+
 class OracleModel:
     def __init__(self, P, R, Cat, G, hyper: Hyper | None = None, dtype=np.float32):
         self.h = hyper or Hyper()

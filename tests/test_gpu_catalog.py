@@ -214,3 +214,43 @@ def test_catalog_cfg2_properties():
         assert torch.equal(torch.sort(top.indices).values, torch.sort(ids[u].long()).values)
         assert float((top.values - sc[u]).abs().max()) <= 1e-12
     e.close()
+
+
+def test_health_term_at_inference_matches_oracle():
+    """fr_set_health_blend: score / sampled evaluation / catalog top-K use P[u] + alpha * mean G[labels(u)]
+    (the row Write_Memory materialises, Model_Recommender.py:170-198) gathered inside the kernels.  The oracle
+    applies the same blend to its tables; catalog ids and fp64 scores must then be identical."""
+    from foodrec_b200 import Engine, Hyper
+    from oracle.recommender_oracle import health_rows
+    from tests.util import Problem
+    p = Problem(300, 4000, 9, 128, seed=44)
+    alpha = 0.35                                    # large enough to reorder the rankings
+    e = Engine(Hyper(alpha=alpha), p.tb.P, p.tb.R, p.tb.Cat, p.tb.G * 5, max_rows=256, item_cats=p.item_cats,
+               user_labels=p.user_labels)
+    G = (p.tb.G * 5).astype(np.float32)
+    Pb = health_rows(p.tb.P, G, p.user_labels, alpha)
+    om = OracleModel(Pb, p.tb.R, p.tb.Cat, G, OHyper(alpha=alpha), dtype=np.float32)
+    om_plain = OracleModel(p.tb.P, p.tb.R, p.tb.Cat, G, OHyper(alpha=alpha), dtype=np.float32)
+    plain_ids, _ = e.catalog_topk(K=20)
+    e.set_health_blend(True)
+    ids, sc = check(e, om, p.item_cats, 20, U=p.U)
+    assert not np.array_equal(ids, plain_ids.cpu().numpy())          # the term really changes the ranking
+    # inference kernel
+    f = p.pointwise(512, seed=9)
+    s = e.score(f["user_input"], f["item_input"], f["categories"]).cpu().numpy()
+    ref = OracleModel(Pb, p.tb.R, p.tb.Cat, G, OHyper(alpha=alpha), dtype=np.float64).scores(f["user_input"], f["item_input"], f["categories"])
+    assert np.abs(s - ref).max() <= 1e-5 * np.abs(ref).max()
+    # sampled evaluation: same top-K as the oracle on the blended rows
+    rng = np.random.default_rng(3)
+    users = np.arange(64, dtype=np.int32)
+    cand = np.stack([rng.permutation(p.I)[:51] for _ in users]).astype(np.int32)
+    tk, rank = e.eval_sampled_topk(users, cand, np.full(64, 51, np.int32), 10)
+    tk = tk.cpu().numpy()
+    for r, u in enumerate(users):
+        sr = om.scores(np.full(51, u), cand[r], p.item_cats[cand[r]])
+        want = [int(cand[r][j]) for j in sorted(range(51), key=lambda j: (-sr[j], j))[:10]]
+        assert tk[r].tolist() == want
+    e.set_health_blend(False)
+    ids2, _ = e.catalog_topk(K=20)
+    assert torch.equal(ids2, plain_ids)
+    e.close()
