@@ -806,6 +806,12 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
       p.tile_group = w.tile_group; p.tile_valid = w.tile_valid; p.bias = w.bias; p.margin2 = w.margin2;
       p.block_first = bf;
       { const char* dmn = getenv("FOODREC_CATALOG_DENSE_MIN"); p.dense_min = dmn ? atoi(dmn) : 3; }
+      {   // bootstrap length: as many tiles as chunk maxima fit one candidate list (64 tiles = 16k recipes by default)
+        const int chunks_per_tile = (w.BN / NSET) / 32;
+        const char* bt = getenv("FOODREC_CATALOG_BOOT_TILES");
+        p.boot_tiles = bt ? atoi(bt) : CAT_CAP / chunks_per_tile;
+        p.boot_tiles = std::max(0, std::min(p.boot_tiles, CAT_CAP / chunks_per_tile));
+      }
       p.dbg = getenv("FOODREC_CATALOG_CYCLES") ? w.dbg : nullptr;
       for (int g = 0; g < 16; ++g) { p.group_lo[g] = w.group_lo[g]; p.group_hi[g] = w.group_hi[g]; p.group_last_valid[g] = w.group_last_valid[g]; }
       p.cand_sc = w.cand_sc; p.cand_row = w.cand_row; p.cand_cnt = w.cand_cnt; p.ovf = w.ovf;

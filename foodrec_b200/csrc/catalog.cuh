@@ -43,6 +43,7 @@ struct CatGemmParams {
   int m_pad;             // m_blocks * CAT_BM * CG
   int n_rows;            // valid user rows in this pass
   int n_split, tiles_per_split, n_tiles, k_blocks, K;
+  int boot_tiles;        // tiles of the bootstrap pass that seeds the thresholds (0: none); chunks recorded must fit a list
   int dense_min;         // rows of a warp with a hit in a chunk from which the per-lane (shared staging) resolution is used
   int a_split;           // 1: A = bf16 head + bf16 tail (two MMAs per B block; needs 2*k_blocks <= CAT_KB_MAX)
   int debug_mode;        // 0 = normal.  Ceiling measurements (results invalid; env FOODREC_CATALOG_DEBUG): 1 = epilogue only

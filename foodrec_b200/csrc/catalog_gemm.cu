@@ -46,7 +46,14 @@ __device__ __forceinline__ int sweep_tile(const int i, const int lo, const int h
   const int r = i - len;
   return r < lo ? r : r + len;
 }
-struct SweepRange { int i0, i1, lo, hi; };
+// A sweep is preceded by a BOOTSTRAP over its first `boot` tiles: the epilogue only records the maximum of every
+// 32-column chunk (no pushes).  K distinct chunk maxima are K distinct recipes, so the K-th largest of them is a
+// valid lower bound of the final K-th best score: the real sweep (which starts over at its first tile) begins with a
+// threshold near the top 1 % instead of -inf and skips the steep part of the ramp-up (~5x fewer pushes on a
+// 200k-recipe catalog for ~8 % more MMA work).  Extended index e in [0, boot + n): tile index = e < boot ? e : e - boot.
+struct SweepRange { int i0, i1, lo, hi, boot; };
+__device__ __forceinline__ int sweep_index(const SweepRange& r, const int e) { return r.i0 + (e < r.boot ? e : e - r.boot); }
+__device__ __forceinline__ int sweep_len(const SweepRange& r) { return r.boot + (r.i1 - r.i0); }
 // mask group of a tile from the 15 group ranges in the kernel parameters (constant bank): the sweep
 // stays inside one group for thousands of tiles, so the range is cached in registers and the
 // per-tile cost is two compares -- no global load sits on the critical path of a tile.
@@ -61,6 +68,8 @@ __device__ __forceinline__ SweepRange sweep_range(const CatGemmParams& p, const 
   r.i0 = sp * p.tiles_per_split;
   r.i1 = min(r.i0 + p.tiles_per_split, p.n_tiles);
   r.lo = r.hi = 0;
+  r.boot = min(p.boot_tiles, (r.i1 - r.i0) / 2);
+  if (r.boot < 4) r.boot = 0;
   if (p.n_split == 1 && p.block_first) {
     const int g = __ldg(p.block_first + mb);
     r.lo = p.group_lo[g]; r.hi = p.group_hi[g];
@@ -75,7 +84,7 @@ struct CompactOut { int cnt; float thr; };
 __device__ __noinline__ CompactOut catalog_warp_compact(const int L, const int lane, float* __restrict__ cand_sc,
                                                         int32_t* __restrict__ cand_row, const size_t my_base,
                                                         const int my_cnt, const float my_thr, const float my_margin2,
-                                                        const int K, int32_t* ovf_flag) {
+                                                        const int K, int32_t* ovf_flag, const bool drop_all) {
   constexpr int NV = CAT_CAP / 32;
   const size_t base = __shfl_sync(FR_FULL, (unsigned long long)my_base, L);
   const int n = min(__shfl_sync(FR_FULL, my_cnt, L), CAT_CAP);
@@ -99,6 +108,11 @@ __device__ __noinline__ CompactOut catalog_warp_compact(const int L, const int l
     if (c >= K) res = trial;
   }
   const float nthr = __fsub_rd(funkey(res), m2);
+  if (drop_all) {                      // bootstrap: the entries were chunk maxima, only the bound is kept
+    CompactOut r{my_cnt, my_thr};
+    if (lane == L) { r.cnt = 0; if (n >= K) r.thr = nthr; }
+    return r;
+  }
   int out = 0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -136,13 +150,20 @@ struct RowState {
 // from TMEM with a one-column tcgen05.ld (uniform address) and pushed under a predicate.
 __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const uint32_t tchunk, const int col,
                                                      const int nvalid, const int n0, RowState& s,
-                                                     const CatGemmParams& p, const int lane, float* stage) {
+                                                     const CatGemmParams& p, const int lane, float* stage, const bool boot) {
   float m[16], g8[4];
 #pragma unroll
   for (int j = 0; j < 16; ++j) m[j] = fmaxf(v[2 * j], v[2 * j + 1]);
 #pragma unroll
   for (int j = 0; j < 4; ++j) g8[j] = fmaxf(fmaxf(m[4 * j], m[4 * j + 1]), fmaxf(m[4 * j + 2], m[4 * j + 3]));
   const float mx = fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3]));
+  if (boot) {                                    // bootstrap pass: one value per chunk, no candidates
+    if (col + 32 <= nvalid && s.thr < __int_as_float(0x7f800000)) {
+      __stcg(p.cand_sc + s.base + s.cnt, mx + s.bias);
+      ++s.cnt;
+    }
+    return;
+  }
   if (!__any_sync(FR_FULL, mx >= s.adj)) return;
   // From here on the compiler may spill / the compaction call may save registers: the prefetched
   // chunk (an asynchronous tcgen05.ld into registers) must have landed before that can happen.
@@ -220,7 +241,7 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
   while (need) {
     const int L = __ffs(need) - 1;
     need &= need - 1;
-    const CompactOut o = catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, s.base, s.cnt, s.thr, s.m2, p.K, s.ovf);
+    const CompactOut o = catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, s.base, s.cnt, s.thr, s.m2, p.K, s.ovf, false);
     s.cnt = o.cnt; s.thr = o.thr;
     s.adj = __fsub_rd(s.thr, s.bias);
   }
@@ -276,8 +297,8 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const SweepRange sr = sweep_range(p, sp, mb);
       int prev_g = -1;
       GroupCursor gc{0, 0, 0};
-      for (int i = sr.i0; i < sr.i1; ++i) {
-        const int t = sweep_tile(i, sr.lo, sr.hi);
+      for (int e = 0; e < sweep_len(sr); ++e) {
+        const int t = sweep_tile(sweep_index(sr, e), sr.lo, sr.hi);
         group_seek(gc, p, t);
         const int g = gc.g;
         const bool loadA = g != prev_g;
@@ -311,12 +332,13 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int sp = unit / p.m_blocks, mb = unit % p.m_blocks;
       const SweepRange sr = sweep_range(p, sp, mb);
       GroupCursor gc{0, 0, 0};
-      for (int i = sr.i0; i < sr.i1; ++i, ++tcount) {
+      const int elen = sweep_len(sr);
+      for (int e = 0; e < elen; ++e, ++tcount) {
         const uint32_t as = tcount % NACC, aph = (tcount / NACC) & 1u;
-        const int t = sweep_tile(i, sr.lo, sr.hi);
+        const int t = sweep_tile(sweep_index(sr, e), sr.lo, sr.hi);
         group_seek(gc, p, t);
-        const int tn = sweep_tile(i + 1, sr.lo, sr.hi);
-        const bool a_last = (i + 1 == sr.i1) || tn < gc.lo || tn >= gc.hi;
+        const int tn = sweep_tile(sweep_index(sr, e + 1), sr.lo, sr.hi);
+        const bool a_last = (e + 1 == elen) || tn < gc.lo || tn >= gc.hi;
         const long long c0 = p.dbg ? clock64() : 0;
         tc::mbar_wait(&tempty[as], aph ^ 1u);          // epilogue drained this accumulator stage
         tc::fence_after_sync();
@@ -377,9 +399,16 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       s.adj = s.thr; s.ovf = p.ovf + grow;
       int cur_g = -1;
       GroupCursor gc{0, 0, 0};
-      for (int i = sr.i0; i < sr.i1; ++i, ++tcount) {
+      for (int e2 = 0; e2 < sweep_len(sr); ++e2, ++tcount) {
         const uint32_t as = tcount % NACC, aph = (tcount / NACC) & 1u;
-        const int t = sweep_tile(i, sr.lo, sr.hi);
+        const bool boot = e2 < sr.boot;
+        if (e2 == sr.boot && sr.boot > 0) {             // bootstrap done: K-th largest chunk maximum of every row -> threshold
+          for (int L = 0; L < 32; ++L) {
+            const CompactOut o = catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, s.base, s.cnt, s.thr, s.m2, p.K, s.ovf, true);
+            s.cnt = o.cnt; s.thr = o.thr;
+          }
+        }
+        const int t = sweep_tile(sweep_index(sr, e2), sr.lo, sr.hi);
         group_seek(gc, p, t);
         const int g = gc.g;
         const int nvalid = (t == gc.hi - 1) ? p.group_last_valid[g] : BN;     // rows of this tile that hold a recipe
@@ -411,13 +440,13 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc::tmem_ld_wait();
             __syncwarp();
             if (c + 1 < NCH) tc::tmem_ld_32x32(tcol + (c + 1) * 32, vb); else release_early();
-            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane, stage);
+            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane, stage, boot);
             else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
             if (c + 1 < NCH) {
               tc::tmem_ld_wait();
               __syncwarp();
               if (c + 2 < NCH) tc::tmem_ld_32x32(tcol + (c + 2) * 32, va); else release_early();
-              if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(vb, tcol + (c + 1) * 32, e * CW + (c + 1) * 32, nvalid, n0, s, p, lane, stage);
+              if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(vb, tcol + (c + 1) * 32, e * CW + (c + 1) * 32, nvalid, n0, s, p, lane, stage, boot);
               else if (vb[0] + vb[13] + vb[31] == 12345.f) s.cnt++;
             }
           }
@@ -429,7 +458,7 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc::tmem_ld_32x32(tcol + c * 32, va);
             tc::tmem_ld_wait();
             if (c == NCH - 1) release_early();
-            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane, stage);
+            if (p.debug_mode == 0 || p.debug_mode == 3) catalog_filter_chunk(va, tcol + c * 32, e * CW + c * 32, nvalid, n0, s, p, lane, stage, boot);
             else if (va[0] + va[13] + va[31] == 12345.f) s.cnt++;
           }
         }
