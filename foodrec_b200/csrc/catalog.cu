@@ -711,8 +711,8 @@ static int catalog_ensure_pass_ws(fr_ctx* h, CatalogWs& w, int mp) {
   if ((rc = dalloc(h, &w.bias, 16 * R))) return rc;
   if ((rc = dalloc(h, &w.margin2, R))) return rc;
   const size_t RL = R * 4;          // candidate lists: up to 4 column sets per (split, row)
-  if ((rc = dalloc(h, &w.cand_sc, RL * CAT_CAP + 1024))) return rc;      // + trash slots of the branch-free push
-  if ((rc = dalloc(h, &w.cand_row, RL * CAT_CAP + 1024))) return rc;
+  if ((rc = dalloc(h, &w.cand_sc, RL * CAT_CAP))) return rc;
+  if ((rc = dalloc(h, &w.cand_row, RL * CAT_CAP))) return rc;
   if ((rc = dalloc(h, &w.cand_cnt, RL))) return rc;
   if ((rc = dalloc(h, &w.ovf, R))) return rc;
   if ((rc = dalloc(h, &w.ovf_list, R))) return rc;
@@ -802,6 +802,8 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
       CatGemmParams p{};
       p.m_blocks = m_blocks; p.m_pad = m_pad; p.n_rows = rows; p.n_split = n_split; p.tiles_per_split = tps;
       p.n_tiles = w.n_tiles; p.k_blocks = w.k_blocks; p.K = K; p.a_split = w.a_split;
+      // diagnostics / tuning switches (environment; never needed for results): FOODREC_CATALOG_DEBUG = ceiling
+      // measurements (catalog.cuh), _DENSE_MIN / _BOOT_TILES = epilogue regime knobs, _CYCLES = in-kernel cycle counters
       { const char* dm = getenv("FOODREC_CATALOG_DEBUG"); p.debug_mode = dm ? atoi(dm) : 0; }
       p.tile_group = w.tile_group; p.tile_valid = w.tile_valid; p.bias = w.bias; p.margin2 = w.margin2;
       p.block_first = bf;
@@ -815,7 +817,6 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
       p.dbg = getenv("FOODREC_CATALOG_CYCLES") ? w.dbg : nullptr;
       for (int g = 0; g < 16; ++g) { p.group_lo[g] = w.group_lo[g]; p.group_hi[g] = w.group_hi[g]; p.group_last_valid[g] = w.group_last_valid[g]; }
       p.cand_sc = w.cand_sc; p.cand_row = w.cand_row; p.cand_cnt = w.cand_cnt; p.ovf = w.ovf;
-      p.trash = (size_t)w.mp_cap * 4 * CAT_CAP;
       launch_catalog_gemm(CG, NSET, w.BN, h->sm_count, tmA, w.tmB, p, st);
       FR_CHECK_LAUNCH(h);
     }

@@ -60,7 +60,6 @@ struct CatGemmParams {
   int32_t* cand_cnt;           // [n_split*NSET*m_pad]
   int32_t* ovf;                // [m_pad] 1 = candidate list overflowed
   unsigned long long* dbg;     // nullable: cycle counters {mma total, wait tempty, wait full, n, epi total, wait tfull, n}
-  size_t trash;                // index of a scratch region (>= blockDim entries) in cand_sc / cand_row
 };
 
 void launch_catalog_gemm(int cta_group, int epi_sets, int tile_n, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,
