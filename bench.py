@@ -473,8 +473,9 @@ def run_ours(args, cfg, B):
         # reads are compulsory for TF-1.x-exact results without the dense sweep, but are not in SURVEY 8(d)'s figure.
         full = B * (28 * D + 16 + 2 * 20 * D + 2 * 4 * D)          # + m,v rows of P[u] + the two z-stash row writes
         kern["fwd"].update(bytes_incl_adam_state=full, gbs_incl_adam_state=full / (phases["fwd"] * 1e-3) / 1e9,
-                           ncu_dram_bytes_per_launch=551_159_040,
-                           ncu_note="profiles/r01_ncu_full_fwd_and_user_chunk.csv launch3: dram read 524.8 MB + write 26.4 MB")
+                           ncu_dram_bytes_per_launch={65536: 551_159_040, 262144: 2_450_635_000}.get(B),
+                           ncu_note="dram__bytes_read+write of one launch: profiles/r01_ncu_full_train_B262144.csv launch1 "
+                                    "(B=262144: 2.193 GB + 0.258 GB), r01_ncu_full_fwd_and_user_chunk.csv launch3 (B=65536)")
     dom = max(alg, key=lambda k: phases[k])
     roofline = {"bound": "hbm", "kernel": {"fwd": "fwd_train_kernel", "user_chunk": "seg_chunk_kernel<UserPol>",
                                            "item_chunk": "seg_chunk_kernel<ItemPol>"}[dom],
