@@ -1,7 +1,15 @@
 """Closed-form / scatter restatement of the reference Recommender train step.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``) -- PARITY UNPINNED: the
-reference needs TF 1.x (absent here) and ships no golden vectors.
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
+
+PARITY: pinned to the reference's own program, TensorFlow itself substituted.  The reference needs
+TF 1.x (absent here) and ships no golden vectors, so ``tests/golden/make_reference_run_golden.py`` EXECUTES
+the unmodified ``Train_recommender.py`` / ``Model_Recommender.py`` / ``evaluate.py`` / ``Dataset.py`` end to end
+against ``tests/golden/tf1_standin/tensorflow`` (the ~30 ``tf.*`` names the reference touches, on torch-CPU)
+and records every ``sess.run``; ``tests/test_reference_run.py`` replays those traces through this oracle
+(all four optimizers, personal-write steps, clipping active, evaluation; <= 3e-7 in fp32, 1e-11 with the
+stand-in in float64).  What remains restated rather than executed is TensorFlow's own arithmetic
+(clip_by_global_norm, the optimizers' apply kernels) -- written twice, independently, here and in the stand-in.
 
 Follows, line by line, ``/root/reference/Code/Recommender``:
 
@@ -204,6 +212,9 @@ class OracleModel:
         dPslices, dR, dCat = dPslices * scale, dR * scale, dCat * scale
         # ---- memory write reads pre-step tables (race rule) ----
         wm = self._write_memory(feed, row_users, items, cats, Ri, n, write_personal)
+        # the value of the assign tensor the `personal` fetch averages (:167,:198,:218) -- it does not contain
+        # this step's optimizer update, which the variable itself has by the time the run ends (`personal` below)
+        personal_assign = f(((self.P + wm["bias"]) + wm["general_bias"]).mean(dtype=np.float64)) if write_personal else None
         # ---- apply_gradients (:240) ----
         self.t += 1
         if self.learner == "sgd":
@@ -225,7 +236,8 @@ class OracleModel:
         if write_personal:
             self.P += wm["bias"]              # :167
             self.P += wm["general_bias"]      # :198
-            out["personal"] = f(self.P.mean(dtype=np.float64))   # :218
+            out["personal"] = f(self.P.mean(dtype=np.float64))   # :218, read when the run has ended
+            out["personal_assign"] = personal_assign
         self.G += wm["dG"]                    # :215
         out["general"] = f(self.G.mean(dtype=np.float64))        # :219
         return out
