@@ -44,6 +44,8 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   A(h->packed, 4 + 4 * (size_t)D + 5 * (size_t)cfg->num_labels * D);   // loss, |g|^2, dCat (+ dG when sharded)
   const size_t chS = S / 32 + 2, chE = E / 32 + 2;
   A(h->pieces_u, chS * 2 * 5 * DV); A(h->pieces_i, chS * 2 * DV); A(h->pieces_g, chE * 2 * 5 * DV);
+  h->long_cap = (uint32_t)((chS > chE ? chS : chE) / FR_LONG_CHAIN + 2);
+  A(h->long_list, h->long_cap);
   A(h->counts, S + 1); A(h->offs, S + 1); A(h->ent_key, E); A(h->ent_row, E); A(h->ent_coef, E); A(h->n_entries, 1);
   A(h->counters, 4); A(h->cat_pre, 4 * DV); A(h->mean_partials, 1024); A(h->out_internal, FR_OUT_COUNT);
   A(h->scan_tmp, S / 4096 + 2);
@@ -362,6 +364,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     SegCommon c{};
     c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
     c.pieces = h->pieces_g; c.uniq_counter = nullptr;
+    c.long_list = h->long_list; c.long_count = h->counters + 2; c.long_cap = h->long_cap;
     LabelPolParams lp{};
     lp.G = (float4*)T.G; lp.R = (const float4*)T.R; lp.cat = h->cat_pre;
     lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = b->items; lp.cats = cats;
@@ -377,6 +380,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     SegCommon c{};
     c.keys = h->sortI.k[ri]; c.perm = h->sortI.v[ri]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
     c.pieces = h->pieces_i; c.uniq_counter = h->counters + 1;
+    c.long_list = h->long_list; c.long_count = h->counters + 3; c.long_cap = h->long_cap;
     ItemPolParams ip{};
     ip.R = (float4*)T.R; ip.s1 = (float4*)T.s1_R; ip.s2 = (float4*)T.s2_R; ip.last = T.last_R;
     ip.z = h->z; ip.g = h->g; ip.out = out; ip.mc = h->mc; ip.oc = oc;

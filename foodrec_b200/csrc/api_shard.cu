@@ -181,6 +181,7 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   SegCommon c{};
   c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
   c.pieces = h->pieces_g; c.uniq_counter = nullptr;
+  c.long_list = h->long_list; c.long_count = h->counters + 2; c.long_cap = h->long_cap;
   LabelPolParams lp{};
   lp.G = (float4*)dG; lp.R = (const float4*)rbuf; lp.cat = h->cat_pre;
   lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = w.slot_of_row; lp.cats = w.cats_row;
@@ -243,6 +244,7 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   SegCommon ci{};
   ci.keys = w.slot_sorted; ci.perm = h->sortI.v[w.ri]; ci.n_dev = nullptr; ci.n_host = (uint32_t)S;
   ci.pieces = h->pieces_i; ci.uniq_counter = h->counters + 1;
+  ci.long_list = h->long_list; ci.long_count = h->counters + 3; ci.long_cap = h->long_cap;
   ItemPolParams ip{};
   ip.z = h->z; ip.g = h->g; ip.out = out; ip.mc = h->mc; ip.oc = oc;
   PeerPtrs none{}; none.world = 0;

@@ -32,7 +32,8 @@ struct fr_ctx {
   size_t pieces_personal_chunks = 0;
   uint32_t *counts = nullptr, *offs = nullptr, *ent_key = nullptr, *ent_row = nullptr, *n_entries = nullptr;
   float* ent_coef = nullptr;
-  uint32_t* counters = nullptr;
+  uint32_t* counters = nullptr;        // [0] unique users, [1] unique recipes, [2]/[3] long chains (label / recipe pass)
+  uint4* long_list = nullptr; uint32_t long_cap = 0;   // work list of seg_combine_long_kernel (train.cuh)
   float4* cat_pre = nullptr;
   float* lr_hist = nullptr; int64_t lr_hist_cap = 0;
   double* cser = nullptr;          // LAZY_SERIES coefficient table [lr_hist_cap * SERIES_TERMS]

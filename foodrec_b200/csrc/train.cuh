@@ -35,8 +35,12 @@ struct SegCommon {
   const uint32_t* n_dev; uint32_t n_host;
   float4* pieces;              // [(chunk*2+slot) * NR*DV]
   uint32_t* uniq_counter;      // nullable
-  uint32_t* head_chunk_flags;  // unused
+  // Long crossing runs (a hot recipe, every label): the per-warp combine hands a chain of more than
+  // FR_LONG_CHAIN pieces to seg_combine_long_kernel (one block per chain) through this list.  Nullable.
+  uint4* long_list;            // {first piece index, its slot, last piece index, key}
+  uint32_t* long_count; uint32_t long_cap;
 };
+constexpr uint32_t FR_LONG_CHAIN = 16;
 
 struct UserPolParams {
   float4 *P, *s1, *s2; int32_t* last;

@@ -43,6 +43,7 @@ void launch_prep_rows(int mode, int B, const int32_t* users, const float* labels
 // (1-a)/n * sum_c m_c P[u,1+c] so the recipe-gradient pass never re-reads P.
 // LAZY = 0 (rows in memory are current) | OPT_ADAM_EXACT | OPT_ADAM_SERIES: P[u] in memory may
 // be stale and is brought to step-1 in registers from (m, v) before it is scored.
+// (__launch_bounds__(FR_THREADS, 3) -> 80 registers, 24 warps/SM: measured SLOWER, 0.78 vs 0.65 ms, spills)
 template <int NV, int GROUP, int LAZY>
 __global__ void __launch_bounds__(FR_THREADS)
 fwd_train_kernel(const FwdParams p) {
@@ -63,25 +64,60 @@ fwd_train_kernel(const FwdParams p) {
     for (int k = 0; k < NV; ++k) gc[c][k] = f4zero();
   float lossacc = 0.f, nrmacc = 0.f;
 
+  // Software pipeline over this warp's groups.  The chain  id -> stamp / category mask -> rows  is three dependent
+  // loads; the profile (profiles/r01_ncu_full_train_B262144.csv, source page) showed the warp parked on each of
+  // them.  Ids are therefore loaded TWO groups ahead and the stamp, the masks and an L2 prefetch of the rows ONE
+  // group ahead, so that the current group only waits for its row loads.
+  int u = 0, lastu = 0, it[GROUP]; float4 mc[GROUP];       // current group
+  int u1 = 0, it1[GROUP];                                   // ids of the next group
+#pragma unroll
+  for (int j = 0; j < GROUP; ++j) { it[j] = 0; it1[j] = 0; mc[j] = make_float4(1.f, 0.f, 0.f, 0.f); }
+  if (gw < p.B) {
+    u = p.users[gw];
+    if constexpr (LAZY != 0) lastu = p.lastP[u];
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) {
+      it[j] = p.items[gw * GROUP + j];
+      mc[j] = __ldg(p.cats + (p.cats_by_item ? it[j] : gw * GROUP + j));
+    }
+    if (gw + nw < p.B) {
+      u1 = p.users[gw + nw];
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) it1[j] = p.items[(gw + nw) * GROUP + j];
+    }
+  }
   for (int grp = gw; grp < p.B; grp += nw) {
-    const int u = p.users[grp];
+    const int gn = grp + nw, gnn = grp + 2 * nw;
+    int u2 = 0, it2[GROUP], last1 = 0; float4 mc1[GROUP];
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) { it2[j] = 0; mc1[j] = make_float4(1.f, 0.f, 0.f, 0.f); }
+    if (gnn < p.B) {            // ids two groups ahead: nothing below depends on them
+      u2 = p.users[gnn];
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) it2[j] = p.items[gnn * GROUP + j];
+    }
+    if (gn < p.B) {             // next group: stamp, masks, and its rows into L2 (no registers held)
+      if constexpr (LAZY != 0) last1 = p.lastP[u1];
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) mc1[j] = __ldg(p.cats + (p.cats_by_item ? it1[j] : gn * GROUP + j));
 #ifndef FR_NO_FWD_PREFETCH
-    if (grp + nw < p.B) {       // L2-prefetch the rows of this warp's next group (no registers held)
-      const int gn = grp + nw;
       const uint32_t ub = 5u * (uint32_t)DV * 16u, rb = (uint32_t)DV * 16u;
-      const size_t uo = (size_t)p.users[gn] * 5 * DV;
+      const size_t uo = (size_t)u1 * 5 * DV;
       prefetch_l2_warp(p.P + uo, ub, lane);
       if (LAZY != 0) { prefetch_l2_warp(p.mP + uo, ub, (lane + 31) & 31); prefetch_l2_warp(p.vP + uo, ub, (lane + 30) & 31); }
 #pragma unroll
       for (int j = 0; j < GROUP; ++j)
-        prefetch_l2_warp(p.R + (size_t)p.items[gn * GROUP + j] * DV, rb, (lane + 29 - j) & 31);
-    }
+        prefetch_l2_warp(p.R + (size_t)it1[j] * DV, rb, (lane + 29 - j) & 31);
 #endif
+    }
     float4 pr[5][NV];
 #pragma unroll
     for (int s = 0; s < 5; ++s) load_row<NV>(pr[s], p.P + ((size_t)u * 5 + s) * DV, DV, lane);
+    float4 rr[GROUP][NV], pcn[GROUP][NV];   // R rows, pooledCat (normalised)
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) load_row_ro<NV>(rr[j], p.R + (size_t)it[j] * DV, DV, lane);
     if constexpr (LAZY != 0) {
-      const int lastu = p.lastP[u], to = p.oc.step - 1;
+      const int to = p.oc.step - 1;
       if (lastu < to) {
         float4 mm[5][NV], vv[5][NV];
 #pragma unroll
@@ -92,16 +128,18 @@ fwd_train_kernel(const FwdParams p) {
         adam_catchup<LAZY, 5 * NV>(&pr[0][0], &mm[0][0], &vv[0][0], lastu, to, p.oc);
       }
     }
-    float4 rr[GROUP][NV], pcn[GROUP][NV];   // R rows, pooledCat (normalised)
     float4 mm[GROUP];
-    float sc[GROUP], nn[GROUP], nzq[GROUP], nRq[GROUP], npcq[GROUP];
+    // hs, ls are reduced across the warp (the score needs them); the squared norms stay per-lane partials and are
+    // reduced once, at the end of the kernel
+    float sc[GROUP], rnn[GROUP], nzq[GROUP], nRq[GROUP], npcq[GROUP];
 #pragma unroll
     for (int j = 0; j < GROUP; ++j) {
       const int r = grp * GROUP + j;
-      const int it = p.items[r];
-      const float4 m = __ldg(p.cats + (p.cats_by_item ? it : r));
+      const float4 m = mc[j];
       const float n = ((m.x + m.y) + m.z) + m.w;                    // :77
-      load_row_ro<NV>(rr[j], p.R + (size_t)it * DV, DV, lane);
+      // one IEEE reciprocal per item row; x * (1/n) is x / n exactly for n = 1, 2, 4 and within 1 ulp for n = 3
+      // (same rule as row_terms in train_seg.cu) -- eleven divisions less per row
+      const float rn = __frcp_rn(n);
       float4 pcs[NV], zs[NV];
       pooled_cat<NV>(pcs, sCat, m, DV, lane);
       float hs = 0.f, ls = 0.f, nz = 0.f, nR = 0.f, npc = 0.f;
@@ -114,21 +152,20 @@ fwd_train_kernel(const FwdParams p) {
         hs += dot4(pr[0][k], pcs[k]);
         ls += dot4(zs[k], rr[j][k]);
         nz += dot4(zs[k], zs[k]);
-        nR += dot4(rr[j][k], rr[j][k]);
-        npc += dot4(pcs[k], pcs[k]);
+        if constexpr (GROUP == 1) { nR += dot4(rr[j][k], rr[j][k]); npc += dot4(pcs[k], pcs[k]); }
       }
-      hs = warp_sum(hs); ls = warp_sum(ls); nz = warp_sum(nz); nR = warp_sum(nR); npc = warp_sum(npc);
-      const float high = hs / n, low = ls / n;                      // :79, :92
+      hs = warp_sum(hs); ls = warp_sum(ls);
+      const float high = hs * rn, low = ls * rn;                    // :79, :92
       sc[j] = a * high + oma * low;                                 // :95-96
-      const float zc = oma / n;
+      const float zc = oma * rn;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int i = lane + 32 * k;
         if (i < DV) __stcg(p.z + (size_t)r * DV + i, scale4(zc, zs[k]));
-        pcn[j][k] = div4(pcs[k], n);
+        pcn[j][k] = scale4(rn, pcs[k]);
       }
-      mm[j] = m; nn[j] = n;
-      const float inv2 = 1.f / (n * n);
+      mm[j] = m; rnn[j] = rn;
+      const float inv2 = rn * rn;
       nzq[j] = nz * inv2; nRq[j] = nR * inv2; npcq[j] = npc * inv2;
     }
     if constexpr (GROUP == 1) {
@@ -140,11 +177,11 @@ fwd_train_kernel(const FwdParams p) {
       const float4 m = mm[0];
       const float sumsq_m = m.x * m.x + m.y * m.y + m.z * m.z + m.w * m.w;
       const float nrm = g * g * (a * a * npcq[0] + oma * oma * (nRq[0] * sumsq_m + nzq[0]));
-      const float ga = g * a, n = nn[0];
+      const float ga = g * a, rn = rnn[0];
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        fma4(gc[0][k], ga * (m.x / n), pr[0][k]); fma4(gc[1][k], ga * (m.y / n), pr[0][k]);
-        fma4(gc[2][k], ga * (m.z / n), pr[0][k]); fma4(gc[3][k], ga * (m.w / n), pr[0][k]);
+        fma4(gc[0][k], ga * (m.x * rn), pr[0][k]); fma4(gc[1][k], ga * (m.y * rn), pr[0][k]);
+        fma4(gc[2][k], ga * (m.z * rn), pr[0][k]); fma4(gc[3][k], ga * (m.w * rn), pr[0][k]);
       }
       lossacc += loss; nrmacc += nrm;
       if (lane == 0) { p.g[grp] = g; p.scores[grp] = s; }
@@ -155,9 +192,7 @@ fwd_train_kernel(const FwdParams p) {
       const float sig = s >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
       const float h = (sig - 1.f) / Bf;
       const float4 m0 = mm[0], m1 = mm[GROUP - 1];
-      const float n0 = nn[0], n1 = nn[GROUP - 1];
-      const float4 w0 = make_float4(m0.x / n0, m0.y / n0, m0.z / n0, m0.w / n0);
-      const float4 w1 = make_float4(m1.x / n1, m1.y / n1, m1.z / n1, m1.w / n1);
+      const float4 w0 = scale4(rnn[0], m0), w1 = scale4(rnn[GROUP - 1], m1);
       // || h (q0 - q1) ||^2 of the P slice of this triple
       float dq = 0.f;
 #pragma unroll
@@ -173,8 +208,7 @@ fwd_train_kernel(const FwdParams p) {
           dq += oma * oma * dot4(d, d);
         }
       }
-      dq = warp_sum(dq);
-      const float nrm = h * h * (dq + oma * oma * (nzq[0] + nzq[GROUP - 1]));
+      const float nrm = h * h * (dq + oma * oma * (nzq[0] + nzq[GROUP - 1]));     // per-lane partial
       const float ha = h * a;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
@@ -187,6 +221,9 @@ fwd_train_kernel(const FwdParams p) {
         p.scores[grp * GROUP] = sc[0]; p.scores[grp * GROUP + 1] = sc[GROUP - 1];
       }
     }
+      u = u1; lastu = last1; u1 = u2;
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) { it[j] = it1[j]; mc[j] = mc1[j]; it1[j] = it2[j]; }
   }
   // deterministic block reduction (fixed warp order), one partial per block
 #pragma unroll
@@ -196,6 +233,7 @@ fwd_train_kernel(const FwdParams p) {
       const int i = lane + 32 * k;
       if (i < DV) red[(warp * 4 + c) * DV + i] = gc[c][k];
     }
+  nrmacc = warp_sum(nrmacc);
   if (lane == 0) { red_loss[warp] = lossacc; red_nrm[warp] = nrmacc; }
   __syncthreads();
   for (int j = threadIdx.x; j < 4 * DV; j += blockDim.x) {
@@ -395,17 +433,47 @@ label_emit_kernel(const LabelEmitParams p) {
   }
 }
 
+// Resident label CSR (ids-only feed): a row has 1-3 labels, so one THREAD per item row (a warp per row spends
+// three dependent loads of latency on <= 3 useful lanes: 2 x 100 us per 524k rows, measured).
+__global__ void __launch_bounds__(256)
+label_count_csr_kernel(const LabelEmitParams p) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.S; r += gridDim.x * blockDim.x) {
+    const int u = p.users[r / p.group];
+    p.counts[r] = (uint32_t)(p.lab_off[u + 1] - p.lab_off[u]);
+  }
+}
+__global__ void __launch_bounds__(256)
+label_emit_csr_kernel(const LabelEmitParams p) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint32_t tot = *p.n_entries;
+    p.out[FR_OUT_LABEL_ENTRIES] = (float)tot;
+    if (tot > p.cap) p.out[FR_OUT_OVERFLOW] = 1.f;
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.S; r += gridDim.x * blockDim.x) {
+    const int u = p.users[r / p.group];
+    const int b = p.lab_off[u], cnt = p.lab_off[u + 1] - b;
+    const float ws = p.ws_row[r];
+    const uint32_t off = p.offs[r];
+    for (int q = 0; q < cnt; ++q) {
+      const uint32_t dst = off + q;
+      if (dst < p.cap) { p.ent_key[dst] = (uint32_t)p.lab_idx[b + q]; p.ent_row[dst] = (uint32_t)r; p.ent_coef[dst] = ws; }
+    }
+  }
+}
+
 static int warp_grid(int nwarps_needed, int sm_count) {
   int grid = (nwarps_needed + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
   if (grid > sm_count * 8) grid = sm_count * 8;
   return grid < 1 ? 1 : grid;
 }
 void launch_label_count(const LabelEmitParams& p, const Launch& l) {
-  label_count_kernel<<<warp_grid(p.S, l.sm_count), FR_THREADS, 0, l.st>>>(p);
+  if (!p.user_labels) label_count_csr_kernel<<<max(1, min((p.S + 255) / 256, l.sm_count * 8)), 256, 0, l.st>>>(p);
+  else label_count_kernel<<<warp_grid(p.S, l.sm_count), FR_THREADS, 0, l.st>>>(p);
   ++g_launches;
 }
 void launch_label_emit(const LabelEmitParams& p, const Launch& l) {
-  label_emit_kernel<<<warp_grid(p.S, l.sm_count), FR_THREADS, 0, l.st>>>(p);
+  if (!p.user_labels) label_emit_csr_kernel<<<max(1, min((p.S + 255) / 256, l.sm_count * 8)), 256, 0, l.st>>>(p);
+  else label_emit_kernel<<<warp_grid(p.S, l.sm_count), FR_THREADS, 0, l.st>>>(p);
   ++g_launches;
 }
 

@@ -136,6 +136,13 @@ seg_combine_kernel(const SegCommon c, const Pol pol) {
       if (c.keys[mid] == lastKey) lo = mid + 1; else hi = mid;
     }
     const uint32_t kend = (lo - 1) >> 5;          // last chunk holding an entry of the run
+    if (c.long_list && kend - chunk >= FR_LONG_CHAIN) {   // a long chain: one block sums it (seg_combine_long_kernel)
+      if (lane == 0) {
+        const uint32_t w = atomicAdd(c.long_count, 1u);
+        if (w < c.long_cap) c.long_list[w] = make_uint4(chunk, s0 == 0 ? 0u : 1u, kend, lastKey);
+      }
+      continue;
+    }
     constexpr int PF = (NR * NV <= 2) ? 8 : (NR * NV <= 5 ? 4 : 2);
     for (uint32_t kc = chunk + 1; kc <= kend; kc += PF) {
       float4 buf[PF][NR][NV];
@@ -453,10 +460,34 @@ struct LabelPol {
     }
     return e;
   }
+  // The pass is issue-bound, not bandwidth-bound (1M entries re-read 512-byte recipe rows that sit in L2), so
+  // the per-entry instruction count is what matters:
+  //  * slot 0 (beta_2 * coef * pooledCat) is linear in the four category rows: the per-category weights
+  //    sum_j coef_j m_jc / n_j of the entries [e0, e1) are reduced across the warp ONCE per call and applied
+  //    as four row FMAs, instead of a pooledCat evaluation per entry;
+  //  * slots 1..4: a recipe has one or two categories, the others contribute acc + 0 -- skipped by a
+  //    warp-uniform branch (bit-identical).
   __device__ __forceinline__ void accumulate(float4 (&acc)[5][NV], const Entry& e, int e0, int e1, int lane,
                                              const float4* sCat) const {
     const int DVv = p.mc.DV;
-    constexpr int PF = 4;                       // recipe rows in flight
+    {
+      const bool in = lane >= e0 && lane < e1;
+      const float s = in ? e.coef * __frcp_rn(((e.m.x + e.m.y) + e.m.z) + e.m.w) : 0.f;
+      const float w0 = p.mc.beta_2 * warp_sum(s * e.m.x), w1 = p.mc.beta_2 * warp_sum(s * e.m.y);
+      const float w2 = p.mc.beta_2 * warp_sum(s * e.m.z), w3 = p.mc.beta_2 * warp_sum(s * e.m.w);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < DVv) {
+          mad4_rn(acc[0][k], w0, sCat[i]); mad4_rn(acc[0][k], w1, sCat[DVv + i]);
+          mad4_rn(acc[0][k], w2, sCat[2 * DVv + i]); mad4_rn(acc[0][k], w3, sCat[3 * DVv + i]);
+        }
+      }
+    }
+#ifndef FR_LABEL_PF
+#define FR_LABEL_PF 8
+#endif
+    constexpr int PF = FR_LABEL_PF;             // recipe rows in flight
     for (int j0 = e0; j0 < e1; j0 += PF) {
       float4 rr4[PF][NV];
 #pragma unroll
@@ -466,15 +497,23 @@ struct LabelPol {
       for (int u = 0; u < PF; ++u) {
         const int j = j0 + u;
         if (j >= e1) break;
-        const float coef = __shfl_sync(FR_FULL, e.coef, j);
+        const float lc = p.mc.beta_1 * __shfl_sync(FR_FULL, e.coef, j);
         const float4 m = shfl4(e.m, j);
-        const RowTerms<NV> t = row_terms<NV>(m, sCat, DVv, lane);
-        const float hc = p.mc.beta_2 * coef, lc = p.mc.beta_1 * coef;
+        if (m.x != 0.f) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          mad4_rn(acc[0][k], hc, t.pc[k]);
-          mad4_rn(acc[1][k], lc, scale4(m.x, rr4[u][k])); mad4_rn(acc[2][k], lc, scale4(m.y, rr4[u][k]));
-          mad4_rn(acc[3][k], lc, scale4(m.z, rr4[u][k])); mad4_rn(acc[4][k], lc, scale4(m.w, rr4[u][k]));
+          for (int k = 0; k < NV; ++k) mad4_rn(acc[1][k], lc, scale4(m.x, rr4[u][k]));
+        }
+        if (m.y != 0.f) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) mad4_rn(acc[2][k], lc, scale4(m.y, rr4[u][k]));
+        }
+        if (m.z != 0.f) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) mad4_rn(acc[3][k], lc, scale4(m.z, rr4[u][k]));
+        }
+        if (m.w != 0.f) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) mad4_rn(acc[4][k], lc, scale4(m.w, rr4[u][k]));
         }
       }
     }
@@ -615,6 +654,13 @@ seg_tile_combine_kernel(const SegCommon c, const Pol pol) {
       if (c.keys[mid] == lastKey) lo = mid + 1; else hi = mid;
     }
     const uint32_t tend = (lo - 1) / TL;                    // last tile holding an entry of the run
+    if (c.long_list && tend - tile >= FR_LONG_CHAIN) {
+      if (lane == 0) {
+        const uint32_t w = atomicAdd(c.long_count, 1u);
+        if (w < c.long_cap) c.long_list[w] = make_uint4(tile, start == tbase ? 0u : 1u, tend, lastKey);
+      }
+      continue;
+    }
     float4 acc[NR][NV];
     {
       const float4* src = c.pieces + ((size_t)tile * 2 + (start == tbase ? 0 : 1)) * NR * DV;
@@ -653,6 +699,84 @@ seg_tile_combine_kernel(const SegCommon c, const Pol pol) {
   }
 }
 
+// ---- long chains: ONE BLOCK per crossing run.  Warp w sums a contiguous share of the run's pieces in piece
+// order, the shares are then summed in warp order and the run is applied once -- a fixed summation tree that
+// depends only on the chain's length, so the result is deterministic; the per-warp chain is WARPS times shorter
+// (the hottest Zipf recipe of a 262,144-triple batch leaves ~940 pieces, every label of the label pass ~170).
+template <class Pol>
+__global__ void __launch_bounds__(FR_THREADS)
+seg_combine_long_kernel(const SegCommon c, const Pol pol) {
+  extern __shared__ float4 smem[];                          // [WARPS][NR*DV]
+  constexpr int NR = Pol::NR, NV = Pol::NV;
+  const int DV = pol.DV();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t cnt = min(*c.long_count, c.long_cap);
+  for (uint32_t w = blockIdx.x; w < cnt; w += gridDim.x) {
+    const uint4 d = c.long_list[w];
+    const uint32_t first = d.x, slot0 = d.y, last = d.z, key = d.w;
+    const uint32_t per = (last - first + FR_WARPS_PER_BLOCK) / FR_WARPS_PER_BLOCK;
+    const uint32_t b = first + (uint32_t)warp * per, e = min(b + per, last + 1);
+    float4 acc[NR][NV];
+#pragma unroll
+    for (int s = 0; s < NR; ++s)
+#pragma unroll
+      for (int q = 0; q < NV; ++q) acc[s][q] = f4zero();
+    constexpr int PF = (NR * NV <= 2) ? 8 : (NR * NV <= 5 ? 4 : 2);
+    for (uint32_t k = b; k < e; k += PF) {
+      float4 buf[PF][NR][NV];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const uint32_t pi = k + u;
+        const float4* src = c.pieces + ((size_t)pi * 2 + (pi == first ? slot0 : 0u)) * NR * DV;
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const int i = lane + 32 * q;
+            buf[u][s][q] = (pi < e && i < DV) ? __ldcg(src + s * DV + i) : f4zero();
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u)
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) acc[s][q] = add4(acc[s][q], buf[u][s][q]);
+    }
+#pragma unroll
+    for (int s = 0; s < NR; ++s)
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        const int i = lane + 32 * q;
+        if (i < DV) smem[((size_t)warp * NR + s) * DV + i] = acc[s][q];
+      }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll 1
+      for (int ww = 1; ww < FR_WARPS_PER_BLOCK; ++ww)
+#pragma unroll
+        for (int s = 0; s < NR; ++s)
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const int i = lane + 32 * q;
+            if (i < DV) acc[s][q] = add4(acc[s][q], smem[((size_t)ww * NR + s) * DV + i]);
+          }
+      typename Pol::State st;
+      pol.load_state(st, key, lane);
+      pol.apply(st, key, acc, lane);
+    }
+    __syncthreads();
+  }
+}
+
+template <class Pol>
+static void launch_combine_long(const SegCommon& c, const Pol& pol, int DV, const Launch& l) {
+  if (!c.long_list) return;
+  const size_t smem = (size_t)FR_WARPS_PER_BLOCK * Pol::NR * DV * sizeof(float4);
+  seg_combine_long_kernel<Pol><<<l.sm_count, FR_THREADS, smem, l.st>>>(c, pol);
+  ++g_launches;
+}
+
 template <class Pol, int TC>
 static void launch_seg_tiled(const SegCommon& c, const Pol& pol, int DV, bool needs_cat, const Launch& l) {
   const uint32_t ntiles = (c.n_host + 32 * TC - 1) / (32 * TC);
@@ -665,6 +789,7 @@ static void launch_seg_tiled(const SegCommon& c, const Pol& pol, int DV, bool ne
   if (l.mid) cudaEventRecord(l.mid, l.st);
   seg_tile_combine_kernel<Pol, TC><<<grid, FR_THREADS, 0, l.st>>>(c, pol);
   g_launches += 2;
+  launch_combine_long(c, pol, DV, l);
 }
 
 template <class Pol>
@@ -681,6 +806,7 @@ static void launch_seg(const SegCommon& c, const Pol& pol, int DV, bool needs_ca
   if (l.mid) cudaEventRecord(l.mid, l.st);
   seg_combine_kernel<Pol><<<grid, FR_THREADS, 0, l.st>>>(c, pol);
   g_launches += 2;
+  launch_combine_long(c, pol, DV, l);
 }
 
 #define FR_DISPATCH_NV_OPT(NVx, OPTx, ...)                                                  \
@@ -720,9 +846,12 @@ void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, f
   else { ItemGradPol<2> pol{{p}, gbuf, peers}; launch_seg(c, pol, p.mc.DV, false, l); }
 }
 void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, const Launch& l) {
-  // <= ~100 labels, runs of thousands of entries: 8 chunks per warp-tile
-  if (NV == 1) { LabelPol<1> pol{p}; launch_seg_tiled<LabelPol<1>, 8>(c, pol, p.mc.DV, true, l); }
-  else { LabelPol<2> pol{p}; launch_seg_tiled<LabelPol<2>, 8>(c, pol, p.mc.DV, true, l); }
+  // <= ~100 labels, runs of thousands of entries: FR_LABEL_TC chunks per warp-tile
+#ifndef FR_LABEL_TC
+#define FR_LABEL_TC 8
+#endif
+  if (NV == 1) { LabelPol<1> pol{p}; launch_seg_tiled<LabelPol<1>, FR_LABEL_TC>(c, pol, p.mc.DV, true, l); }
+  else { LabelPol<2> pol{p}; launch_seg_tiled<LabelPol<2>, FR_LABEL_TC>(c, pol, p.mc.DV, true, l); }
 }
 
 // ---- lazy Adam: the batch's unique recipe rows are brought to step-1 before anything
