@@ -30,6 +30,16 @@ SMALL = dict(U=20_000, I=5_000, L=95, D=128)       # --small: functional check o
 METRIC, UNIT = "bpr_train_triples_per_sec", "triples/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures of bench.py's
+# own command (key: batch, learner, adam mode).  262144/adam/lazy: profiles/r01_ncu_full_train_B262144.csv (launch1 =
+# forward of the earlier build, launch2 = user pass, launch3 = recipe pass; the forward's bytes are set by the rows it
+# must read and did not change with the software pipelining); 65536: r01_ncu_full_fwd_and_user_chunk.csv launch3.
+NCU_TRAFFIC = {
+    (262144, "adam", "lazy"): {"fwd": 2_450_635_000, "user_chunk": 3_649_721_000, "item_chunk": 160_502_000},
+    (65536, "adam", "lazy"): {"fwd": 551_159_040},
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -473,17 +483,21 @@ def run_ours(args, cfg, B):
         # reads are compulsory for TF-1.x-exact results without the dense sweep, but are not in SURVEY 8(d)'s figure.
         full = B * (28 * D + 16 + 2 * 20 * D + 2 * 4 * D)          # + m,v rows of P[u] + the two z-stash row writes
         kern["fwd"].update(bytes_incl_adam_state=full, gbs_incl_adam_state=full / (phases["fwd"] * 1e-3) / 1e9,
-                           ncu_dram_bytes_per_launch={65536: 551_159_040, 262144: 2_450_635_000}.get(B),
-                           ncu_note="dram__bytes_read+write of one launch: profiles/r01_ncu_full_train_B262144.csv launch1 "
-                                    "(B=262144: 2.193 GB + 0.258 GB), r01_ncu_full_fwd_and_user_chunk.csv launch3 (B=65536)")
+                           )
     dom = max(alg, key=lambda k: phases[k])
     roofline = {"bound": "hbm", "kernel": {"fwd": "fwd_train_kernel", "user_chunk": "seg_chunk_kernel<UserPol>",
                                            "item_chunk": "seg_chunk_kernel<ItemPol>"}[dom],
                 "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
                 "peak_source": peak_src, "traffic": None,
                 "alg_bytes_per_launch": alg[dom], "ms_per_launch": phases[dom]}
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of each kernel at this batch, from the committed
+    # `ncu --set full` captures (profiles/NCU_TRAFFIC: which file / launch each figure comes from)
+    ncu_traffic = NCU_TRAFFIC.get((B, args.learner.lower(), args.adam_mode), {})
+    for k, v in ncu_traffic.items():
+        if k in kern:
+            kern[k]["ncu_dram_bytes_per_launch"] = v
+    roofline["traffic"] = ncu_traffic.get(dom)
     if dom == "fwd" and "gbs_incl_adam_state" in kern["fwd"]:
-        roofline["traffic"] = kern["fwd"]["ncu_dram_bytes_per_launch"]
         roofline["achieved_incl_adam_state"] = kern["fwd"]["gbs_incl_adam_state"]
         roofline["frac_incl_adam_state"] = kern["fwd"]["gbs_incl_adam_state"] / peak
         roofline["note"] = ("achieved/frac use SURVEY 8(d)'s 28D+16 B per triple; the lazy-Adam forward also has to read "

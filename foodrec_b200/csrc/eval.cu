@@ -79,10 +79,13 @@ void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, c
     fwd_score_kernel<2><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb);
 }
 
-// One warp per test user.  Candidate j lives in lane j&31, slot j>>5 (<= 128 candidates).
-constexpr int EVAL_SLOTS = 4;
-
-template <int NV>
+// One warp per test user.  Candidate j lives in lane j&31, slot j>>5 (<= 128 candidates; SLOTS = 2 covers the
+// reference's 51).  Scoring is LANE-PER-CANDIDATE: the user's five rows are staged in shared memory, and lane j walks
+// the recipe row of ITS candidate, so a score costs no warp reduction at all (the row-per-warp form spent two
+// 5-step shuffle reductions and two IEEE divisions on every candidate: ~110 warp instructions each, 22 ms per 1M
+// users while the recipe table sits in L2).  The category term a/n * sum_c m_c <P[u,0], Cat[c]> needs the four dot
+// products <P[u,0], Cat[c]> once per user; the recipe term is sum_d (sum_c m_c P[u,1+c]_d) R[i]_d accumulated by the lane.
+template <int NV, int SLOTS>
 __global__ void __launch_bounds__(FR_THREADS)
 eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, const float4* __restrict__ Cat,
                     int DV, float a, float oma, const int32_t* __restrict__ users,
@@ -90,74 +93,142 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
                     int stride, const float4* __restrict__ cand_cats, const float4* __restrict__ item_cats,
                     int K, int32_t* __restrict__ topk_ids, int32_t* __restrict__ gt_rank,
                     float* __restrict__ scores_out, const HealthBlend hb) {
-  extern __shared__ float4 sCat[];
+  extern __shared__ float4 smem[];
+  float4* sCat = smem;                                              // [4*DV]
   for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) sCat[i] = Cat[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  float4* sP = smem + 4 * DV + (threadIdx.x >> 5) * 5 * DV;         // this warp's user rows [5*DV]
   const int gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5), nw = gridDim.x * FR_WARPS_PER_BLOCK;
   for (int w = gw; w < n_users; w += nw) {
     const int u = users[w];
     int nc = n_cand[w];
     if (nc > stride) nc = stride;
-    float4 pr[5][NV];
+    if (nc > 32 * SLOTS) nc = 32 * SLOTS;
+    int id[SLOTS]; float sc[SLOTS]; bool alive[SLOTS]; float4 mq[SLOTS];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
-    health_blend_rows<NV>(pr, hb, u, DV, lane);
-    int id[EVAL_SLOTS]; float sc[EVAL_SLOTS]; bool alive[EVAL_SLOTS];
-#pragma unroll
-    for (int q = 0; q < EVAL_SLOTS; ++q) {
+    for (int q = 0; q < SLOTS; ++q) {
       const int j = q * 32 + lane;
       id[q] = j < nc ? cand[(size_t)w * stride + j] : -1;
       sc[q] = 0.f; alive[q] = j < nc;
     }
-    for (int j = 0; j < nc; ++j) {
-      int it = 0;
 #pragma unroll
-      for (int q = 0; q < EVAL_SLOTS; ++q) if ((j >> 5) == q) it = __shfl_sync(FR_FULL, id[q], j & 31);
-      const float4 m = cand_cats ? __ldg(cand_cats + (size_t)w * stride + j) : __ldg(item_cats + it);
-      const float s = score_pair<NV>(pr, R + (size_t)it * DV, m, sCat, DV, lane, a, oma);
-#pragma unroll
-      for (int q = 0; q < EVAL_SLOTS; ++q) if ((j >> 5) == q && (j & 31) == lane) sc[q] = s;
-      if (scores_out && lane == 0) scores_out[(size_t)w * stride + j] = s;
+    for (int q = 0; q < SLOTS; ++q) {
+      const int j = q * 32 + lane;
+      mq[q] = make_float4(1.f, 0.f, 0.f, 0.f);
+      if (j < nc) mq[q] = cand_cats ? __ldg(cand_cats + (size_t)w * stride + j) : __ldg(item_cats + id[q]);
     }
-    // dict semantics (evaluate.py:60-61): the first position of an id survives and takes
-    // the score of its last occurrence.
-    for (int j2 = 0; j2 < nc; ++j2) {
-      int idb = 0; float sb = 0.f;
+    float b0, b1, b2, b3;
+    {
+      float4 pr[5][NV];
 #pragma unroll
-      for (int q = 0; q < EVAL_SLOTS; ++q) if ((j2 >> 5) == q) {
-        idb = __shfl_sync(FR_FULL, id[q], j2 & 31);
-        sb = __shfl_sync(FR_FULL, sc[q], j2 & 31);
+      for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
+      health_blend_rows<NV>(pr, hb, u, DV, lane);
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+      __syncwarp();                                                  // the previous user's rows are no longer read
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < DV) {
+#pragma unroll
+          for (int s = 1; s < 5; ++s) sP[s * DV + i] = pr[s][k];
+          t0 += dot4(pr[0][k], sCat[i]); t1 += dot4(pr[0][k], sCat[DV + i]);
+          t2 += dot4(pr[0][k], sCat[2 * DV + i]); t3 += dot4(pr[0][k], sCat[3 * DV + i]);
+        }
       }
+      b0 = warp_sum(t0); b1 = warp_sum(t1); b2 = warp_sum(t2); b3 = warp_sum(t3);
+      __syncwarp();
+    }
 #pragma unroll
-      for (int q = 0; q < EVAL_SLOTS; ++q) {
-        const int j = q * 32 + lane;
-        if (j < nc && id[q] == idb) {
-          if (j2 < j) alive[q] = false;
-          else if (j2 > j) sc[q] = sb;
+    for (int q = 0; q < SLOTS; ++q) {
+      if (q * 32 >= nc) break;
+      const int j = q * 32 + lane;
+      const bool valid = j < nc;
+      const float4 m = mq[q];
+      const float rn = __frcp_rn(((m.x + m.y) + m.z) + m.w);         // x * (1/n): exact for n = 1, 2, 4
+      const float4* rp = R + (size_t)(valid ? id[q] : 0) * DV;
+      float acc0 = 0.f, acc1 = 0.f;
+      auto step = [&](int i, float& acc) {
+        const float4 r = __ldg(rp + i);
+        const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
+        float4 z;
+        z.x = m.x * p1.x + m.y * p2.x + m.z * p3.x + m.w * p4.x;
+        z.y = m.x * p1.y + m.y * p2.y + m.z * p3.y + m.w * p4.y;
+        z.z = m.x * p1.z + m.y * p2.z + m.z * p3.z + m.w * p4.z;
+        z.w = m.x * p1.w + m.y * p2.w + m.z * p3.w + m.w * p4.w;
+        acc += dot4(z, r);
+      };
+      const int DVe = DV & ~1;
+#pragma unroll 4
+      for (int i = 0; i < DVe; i += 2) { step(i, acc0); step(i + 1, acc1); }
+      if (DV & 1) step(DV - 1, acc0);
+      const float high = (((m.x * b0 + m.y * b1) + m.z * b2) + m.w * b3) * rn;   // :67-79
+      const float low = (acc0 + acc1) * rn;                                        // :82-92
+      const float s = a * high + oma * low;                                        // :95-96
+      if (valid) {
+        sc[q] = s;
+        if (scores_out) scores_out[(size_t)w * stride + j] = s;
+      }
+    }
+    // dict semantics (evaluate.py:60-61): the first position of an id survives and takes the score of its last
+    // occurrence.  Repeated ids are rare (0.65 % of users at 51 of 200k), so they are DETECTED first -- match.any
+    // inside a slot, one rotation of slot 0 against slot 1 -- and the O(n) fix-up below only runs for those users.
+    bool dup = true;
+    if constexpr (SLOTS == 2) {
+      const uint32_t m0 = __match_any_sync(FR_FULL, id[0]), m1 = __match_any_sync(FR_FULL, id[1]);
+      dup = (id[0] >= 0 && m0 != (1u << lane)) || (id[1] >= 0 && m1 != (1u << lane));
+      if (nc > 32) {
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int o = __shfl_sync(FR_FULL, id[0], (lane + r) & 31);
+          dup |= (id[1] >= 0) & (o == id[1]);
+        }
+      }
+      dup = __any_sync(FR_FULL, dup);
+    }
+    if (dup) {
+      for (int j2 = 0; j2 < nc; ++j2) {
+        int idb = 0; float sb = 0.f;
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) if ((j2 >> 5) == q) {
+          idb = __shfl_sync(FR_FULL, id[q], j2 & 31);
+          sb = __shfl_sync(FR_FULL, sc[q], j2 & 31);
+        }
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) {
+          const int j = q * 32 + lane;
+          if (j < nc && id[q] == idb) {
+            if (j2 < j) alive[q] = false;
+            else if (j2 > j) sc[q] = sb;
+          }
         }
       }
     }
+    // heapq.nlargest (evaluate.py:63): score desc, ties -> insertion order.  Scores become order-preserving
+    // unsigned keys (-0 folded onto +0 so that float equality is key equality); per pick: the lane's own best, one
+    // REDUX max over the keys, one REDUX min over the positions of the lanes that hold it.
+    uint32_t key[SLOTS];
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      const uint32_t b = __float_as_uint(sc[q] + 0.0f);
+      key[q] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    }
     const int gt = __shfl_sync(FR_FULL, id[0], 0);
     int rank_gt = -1;
-    for (int k = 0; k < K; ++k) {       // heapq.nlargest: score desc, ties -> insertion order
-      float best = 0.f; int bpos = 0x7fffffff; int bid = -1;
+    for (int k = 0; k < K; ++k) {
+      uint32_t bk = 0u; int bpos = 0x7fffffff;
 #pragma unroll
-      for (int q = 0; q < EVAL_SLOTS; ++q) {
-        const int j = q * 32 + lane;
-        if (alive[q] && (bpos == 0x7fffffff || sc[q] > best)) { best = sc[q]; bpos = j; bid = id[q]; }
-      }
+      for (int q = 0; q < SLOTS; ++q)
+        if (alive[q] && (bpos == 0x7fffffff || key[q] > bk)) { bk = key[q]; bpos = q * 32 + lane; }
+      if (!__any_sync(FR_FULL, bpos != 0x7fffffff)) { if (lane == 0) topk_ids[(size_t)w * K + k] = -1; continue; }
+      const uint32_t top = __reduce_max_sync(FR_FULL, bpos != 0x7fffffff ? bk : 0u);
+      // (an alive key is >= 0x00800000 unless the score is NaN; lanes without a candidate offer position "none")
+      const int wpos = (int)__reduce_min_sync(FR_FULL, (bpos != 0x7fffffff && bk == top) ? (uint32_t)bpos : 0x7fffffffu);
+      int bid = 0;
 #pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const float ob = __shfl_xor_sync(FR_FULL, best, o);
-        const int op = __shfl_xor_sync(FR_FULL, bpos, o);
-        const int oi = __shfl_xor_sync(FR_FULL, bid, o);
-        const bool take = (op != 0x7fffffff) && (bpos == 0x7fffffff || ob > best || (ob == best && op < bpos));
-        if (take) { best = ob; bpos = op; bid = oi; }
-      }
-      if (bpos == 0x7fffffff) { if (lane == 0) topk_ids[(size_t)w * K + k] = -1; continue; }
+      for (int q = 0; q < SLOTS; ++q) if ((wpos >> 5) == q) bid = __shfl_sync(FR_FULL, id[q], wpos & 31);
 #pragma unroll
-      for (int q = 0; q < EVAL_SLOTS; ++q) if (q * 32 + lane == bpos) alive[q] = false;
+      for (int q = 0; q < SLOTS; ++q) if (q * 32 + lane == wpos) alive[q] = false;
       if (bid == gt && rank_gt < 0) rank_gt = k;
       if (lane == 0) topk_ids[(size_t)w * K + k] = bid;
     }
@@ -172,14 +243,14 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   if (n_users <= 0) return;
   int grid = (n_users + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
-  const size_t smem = (size_t)4 * mc.DV * sizeof(float4);
+  const size_t smem = (size_t)(4 + 5 * FR_WARPS_PER_BLOCK) * mc.DV * sizeof(float4);
   ++g_launches;
-  if (mc.DV <= 32)
-    eval_sampled_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, mc.a, mc.oma, users, cand, n_cand, n_users,
-                                                             stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb);
-  else
-    eval_sampled_kernel<2><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, mc.a, mc.oma, users, cand, n_cand, n_users,
-                                                             stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb);
+#define FR_EVAL(NVV, SL) eval_sampled_kernel<NVV, SL><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, mc.a, mc.oma, users, cand, \
+    n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb)
+  const bool two = stride <= 64;
+  if (mc.DV <= 32) { if (two) FR_EVAL(1, 2); else FR_EVAL(1, 4); }
+  else             { if (two) FR_EVAL(2, 2); else FR_EVAL(2, 4); }
+#undef FR_EVAL
 }
 
 }  // namespace fr

@@ -1,13 +1,13 @@
 #!/bin/bash
 # A/B harness (run on the GPU box): train parity tests, then phases_ms per library variant, then an ncu launch list
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_sharded.py tests/test_reference_run.py -m gpu -x -q > gpurun_out/ab_tests.log 2>&1; tail -3 gpurun_out/ab_tests.log
+python -m pytest tests -m gpu -x -q > gpurun_out/ab_tests.log 2>&1; tail -3 gpurun_out/ab_tests.log
 for v in "" $AB_VARIANTS; do
   FOODREC_B200_LIB=$PWD/foodrec_b200/csrc/libfoodrec_b200$v.so python bench.py --no-cpu --no-catalog --steps 30 --warmup 5 > gpurun_out/ab$v.json 2> gpurun_out/ab$v.err
   python - <<PY
 import json
 d=json.loads([l for l in open("gpurun_out/ab$v.json") if l.startswith("{")][-1])
-print("variant '$v'", round(d["ms_per_step"],4), {k:round(x,4) for k,x in d["phases_ms"].items()})
+print("variant '$v'", round(d["ms_per_step"],4), {k:round(x,4) for k,x in d["phases_ms"].items()}, "topk ms", round(d["topk"]["ms"],3), "e2e", round(d["e2e"]["value"]/1e6,1), round(d["e2e_compact"]["value"]/1e6,1))
 PY
 done
 if [ -n "$AB_NCU" ]; then

@@ -332,6 +332,43 @@ def test_sampled_eval_tie_break_is_insertion_order():
     assert list(ids.cpu().numpy()[0]) == [9, 3, 7, 1, 2] and int(rank.cpu()[0]) == 0
 
 
+@pytest.mark.parametrize("ncand", [51, 64, 100])
+def test_sampled_eval_duplicates_across_slots(ncand):
+    """Repeated ids anywhere in the candidate list -- inside the first 32 positions, beyond them, and straddling
+    the two (the kernel detects them per 32-wide slot and across slots before it runs the dict fix-up) -- against
+    evaluate.py's dict + nlargest, on integer-valued scores so that ties are exact (a = 0, one-hot recipe rows)."""
+    rng = np.random.default_rng(ncand)
+    U, I, D = 37, 120, 120
+    p = Problem(U, I, 3, D, seed=3)
+    p.tb.P[:] = 0; p.tb.P[:, 1, :I] = rng.integers(-3, 4, (U, I)).astype(np.float32)
+    p.tb.R[:] = 0; p.tb.R[np.arange(I), np.arange(I)] = 1.0
+    p.item_cats[:] = 0; p.item_cats[:, 0] = 1.0
+    from foodrec_b200 import Engine, Hyper
+    e = Engine(Hyper(learner="sgd", lr=0.01, high_level_score_coefficient=0.0), p.tb.P, p.tb.R, p.tb.Cat, p.tb.G,
+               max_rows=256, max_label_entries=256 * p.L)
+    cand = rng.integers(0, I, (U, ncand)).astype(np.int32)
+    for u in range(U):            # plant repeats: within slot 0, within the upper slots, across them, of the positive
+        k = u % 5
+        if k == 0: cand[u, 20] = cand[u, 3]
+        if k == 1: cand[u, ncand - 1] = cand[u, 33]
+        if k == 2: cand[u, 40] = cand[u, 5]; cand[u, 45] = cand[u, 5]
+        if k == 3: cand[u, ncand - 2] = cand[u, 0]
+    nc = np.full(U, ncand, np.int32); nc[7] = 33; nc[8] = 32; nc[9] = 1
+    ids, rank, sc = e.eval_sampled_topk(np.arange(U), cand, nc, 10, cand_cats=p.item_cats[cand], return_scores=True)
+    ids, rank = ids.cpu().numpy(), rank.cpu().numpy()
+    S = p.tb.P[:, 1, :I]
+    for u in range(U):
+        c = cand[u, :nc[u]].tolist()
+        m = {}
+        for it in c:
+            m[it] = S[u, it]
+        import heapq
+        want = heapq.nlargest(10, m, key=m.get)
+        got = [int(x) for x in ids[u] if x >= 0]
+        assert got == want, (u, got, want)
+        assert int(rank[u]) == (want.index(c[0]) if c[0] in want else -1)
+
+
 # ---------------------------------------------------------------- reference driver protocol
 def test_session_protocol_runs_the_reference_loop():
     """Train_recommender.py:156-205 + evaluate.py through the shim, with the reference's own
