@@ -94,6 +94,14 @@ __device__ __forceinline__ void load_row_ro(float4 (&dst)[NV], const float4* __r
     dst[k] = (i < DV) ? __ldg(row + i) : f4zero();
   }
 }
+template <int NV>     // read-once rows that must not displace an L2-resident table: ld.global.cs (evict-first)
+__device__ __forceinline__ void load_row_cs(float4 (&dst)[NV], const float4* row, int DV, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    dst[k] = (i < DV) ? __ldcs(row + i) : f4zero();
+  }
+}
 template <int NV>
 __device__ __forceinline__ void store_row(float4* row, const float4 (&src)[NV], int DV, int lane) {
 #pragma unroll

@@ -122,7 +122,8 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
     {
       float4 pr[5][NV];
 #pragma unroll
-      for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
+      // read-once rows: streamed (evict-first) so that the recipe table, which every user re-reads, stays in L2
+      for (int s = 0; s < 5; ++s) load_row_cs<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
       health_blend_rows<NV>(pr, hb, u, DV, lane);
       float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
       __syncwarp();                                                  // the previous user's rows are no longer read
@@ -139,35 +140,61 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       b0 = warp_sum(t0); b1 = warp_sum(t1); b2 = warp_sum(t2); b3 = warp_sum(t3);
       __syncwarp();
     }
+    // two slots per walk: the shared-memory reads of the user rows serve both candidates and twice as many recipe
+    // row loads are in flight per lane
 #pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
+    for (int q = 0; q < SLOTS; q += 2) {
       if (q * 32 >= nc) break;
-      const int j = q * 32 + lane;
-      const bool valid = j < nc;
-      const float4 m = mq[q];
-      const float rn = __frcp_rn(((m.x + m.y) + m.z) + m.w);         // x * (1/n): exact for n = 1, 2, 4
-      const float4* rp = R + (size_t)(valid ? id[q] : 0) * DV;
-      float acc0 = 0.f, acc1 = 0.f;
-      auto step = [&](int i, float& acc) {
-        const float4 r = __ldg(rp + i);
-        const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
-        float4 z;
-        z.x = m.x * p1.x + m.y * p2.x + m.z * p3.x + m.w * p4.x;
-        z.y = m.x * p1.y + m.y * p2.y + m.z * p3.y + m.w * p4.y;
-        z.z = m.x * p1.z + m.y * p2.z + m.z * p3.z + m.w * p4.z;
-        z.w = m.x * p1.w + m.y * p2.w + m.z * p3.w + m.w * p4.w;
-        acc += dot4(z, r);
-      };
-      const int DVe = DV & ~1;
+      const bool vA = q * 32 + lane < nc, vB = (q + 1) * 32 + lane < nc;
+      const float4 mA = mq[q], mB = mq[q + 1];
+      const float4* rpA = R + (size_t)(vA ? id[q] : 0) * DV;
+      const float4* rpB = R + (size_t)(vB ? id[q + 1] : 0) * DV;
+      float accA = 0.f, accB = 0.f;
+      if ((q + 1) * 32 < nc) {
 #pragma unroll 4
-      for (int i = 0; i < DVe; i += 2) { step(i, acc0); step(i + 1, acc1); }
-      if (DV & 1) step(DV - 1, acc0);
-      const float high = (((m.x * b0 + m.y * b1) + m.z * b2) + m.w * b3) * rn;   // :67-79
-      const float low = (acc0 + acc1) * rn;                                        // :82-92
-      const float s = a * high + oma * low;                                        // :95-96
-      if (valid) {
-        sc[q] = s;
-        if (scores_out) scores_out[(size_t)w * stride + j] = s;
+        for (int i = 0; i < DV; ++i) {
+          const float4 ra = __ldg(rpA + i), rb = __ldg(rpB + i);
+          const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
+          float4 za, zb;
+          za.x = mA.x * p1.x + mA.y * p2.x + mA.z * p3.x + mA.w * p4.x;
+          za.y = mA.x * p1.y + mA.y * p2.y + mA.z * p3.y + mA.w * p4.y;
+          za.z = mA.x * p1.z + mA.y * p2.z + mA.z * p3.z + mA.w * p4.z;
+          za.w = mA.x * p1.w + mA.y * p2.w + mA.z * p3.w + mA.w * p4.w;
+          zb.x = mB.x * p1.x + mB.y * p2.x + mB.z * p3.x + mB.w * p4.x;
+          zb.y = mB.x * p1.y + mB.y * p2.y + mB.z * p3.y + mB.w * p4.y;
+          zb.z = mB.x * p1.z + mB.y * p2.z + mB.z * p3.z + mB.w * p4.z;
+          zb.w = mB.x * p1.w + mB.y * p2.w + mB.z * p3.w + mB.w * p4.w;
+          accA += dot4(za, ra); accB += dot4(zb, rb);
+        }
+      } else {
+        float acc1 = 0.f;
+        auto step = [&](int i, float& acc) {
+          const float4 r = __ldg(rpA + i);
+          const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
+          float4 z;
+          z.x = mA.x * p1.x + mA.y * p2.x + mA.z * p3.x + mA.w * p4.x;
+          z.y = mA.x * p1.y + mA.y * p2.y + mA.z * p3.y + mA.w * p4.y;
+          z.z = mA.x * p1.z + mA.y * p2.z + mA.z * p3.z + mA.w * p4.z;
+          z.w = mA.x * p1.w + mA.y * p2.w + mA.z * p3.w + mA.w * p4.w;
+          acc += dot4(z, r);
+        };
+        const int DVe = DV & ~1;
+#pragma unroll 4
+        for (int i = 0; i < DVe; i += 2) { step(i, accA); step(i + 1, acc1); }
+        if (DV & 1) step(DV - 1, accA);
+        accA += acc1;
+      }
+      {
+        const float rn = __frcp_rn(((mA.x + mA.y) + mA.z) + mA.w);     // x * (1/n): exact for n = 1, 2, 4
+        const float high = (((mA.x * b0 + mA.y * b1) + mA.z * b2) + mA.w * b3) * rn;   // :67-79
+        const float s = a * high + oma * (accA * rn);                                  // :82-96
+        if (vA) { sc[q] = s; if (scores_out) scores_out[(size_t)w * stride + q * 32 + lane] = s; }
+      }
+      {
+        const float rn = __frcp_rn(((mB.x + mB.y) + mB.z) + mB.w);
+        const float high = (((mB.x * b0 + mB.y * b1) + mB.z * b2) + mB.w * b3) * rn;
+        const float s = a * high + oma * (accB * rn);
+        if (vB) { sc[q + 1] = s; if (scores_out) scores_out[(size_t)w * stride + (q + 1) * 32 + lane] = s; }
       }
     }
     // dict semantics (evaluate.py:60-61): the first position of an id survives and takes the score of its last
