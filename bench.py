@@ -31,11 +31,12 @@ METRIC, UNIT = "bpr_train_triples_per_sec", "triples/s"
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures of bench.py's
-# own command (key: batch, learner, adam mode).  262144/adam/lazy: profiles/r01_ncu_full_train_B262144.csv (launch1 =
-# forward of the earlier build, launch2 = user pass, launch3 = recipe pass; the forward's bytes are set by the rows it
-# must read and did not change with the software pipelining); 65536: r01_ncu_full_fwd_and_user_chunk.csv launch3.
+# own command (key: batch, learner, adam mode).  262144/adam/lazy: profiles/r01b_ncu_full_train_B262144.csv (launch1 =
+# forward, launch2 = user pass, launch3 = label pass, launch4 = recipe pass; tests/prof_capture.sh is the command);
+# 65536: r01_ncu_full_fwd_and_user_chunk.csv launch3.
 NCU_TRAFFIC = {
-    (262144, "adam", "lazy"): {"fwd": 2_450_635_000, "user_chunk": 3_649_721_000, "item_chunk": 160_502_000},
+    (262144, "adam", "lazy"): {"fwd": 2_452_224_000, "user_chunk": 3_649_241_000, "label_tile": 163_581_000,
+                               "item_chunk": 711_604_000},
     (65536, "adam", "lazy"): {"fwd": 551_159_040},
 }
 
@@ -323,6 +324,26 @@ def run_sharded(args, cfg, B):
     clocks.mark_end()
     launches = eng.e.lib.fr_launch_count() - launches0
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    # roofline of the dominant kernel (the user pass: same kernel, same per-GPU work as at N=1), from CUDA events the
+    # library records around it inside fr_shard_update -- a few extra steps after the timed region, rank 0's numbers
+    eng.e.timing_enable(True)
+    for k in range(min(args.steps, 10)):
+        step(k)
+    torch.cuda.synchronize()
+    sphases, _ = eng.e.timing_read()
+    eng.e.timing_enable(False)
+    v = eng.e.read_scalars()
+    peak, peak_src = peaks()
+    adam_k = {"adam": 6, "adagrad": 4, "rmsprop": 6, "sgd": 2}.get(args.learner.lower(), 2)
+    ualg = float(v[L.FR_OUT_UNIQ_USERS]) * adam_k * 20 * D
+    sroof = None
+    if sphases.get("user_chunk", 0) > 0:
+        ugbs = ualg / (sphases["user_chunk"] * 1e-3) / 1e9
+        sroof = {"bound": "hbm", "kernel": "seg_chunk_kernel<UserPol>", "achieved": ugbs, "peak": peak, "unit": "GB/s",
+                 "frac": ugbs / peak, "peak_source": peak_src, "alg_bytes_per_launch": ualg,
+                 "ms_per_launch": sphases["user_chunk"], "scope": "per GPU (rank 0)",
+                 "traffic": NCU_TRAFFIC.get((B, args.learner.lower(), args.adam_mode), {}).get("user_chunk") if world == 1 else None,
+                 "update_phase_ms": {k: sphases[k] for k in ("finalize", "user_chunk", "user_combine", "label", "item_chunk", "item_combine")}}
     clk = clocks.stop()
     value = world * B * args.steps / (ms / 1e3)
     # e2e: ids from pinned host memory every step, loss read on the host every step
@@ -389,7 +410,7 @@ def run_sharded(args, cfg, B):
                            f"id all-to-all + recipe rows / gradient rows stored into peer memory over NVLink by the gather / "
                            f"gradient kernels (cap {eng.cap}/pair, 2 barriers) + 1 packed all-reduce per step" if p2p else
                            f"3 all-to-alls (ids, rows, grad rows, cap {eng.cap}/pair) + 1 packed all-reduce per step")},
-            "clocks": clk, "gpu_launches": int(launches), "roofline": None,
+            "clocks": clk, "gpu_launches": int(launches), "roofline": sroof,
             "e2e": {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                     "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
                     "feed": "ids only (user, pos, neg) from pinned host memory; side tables resident; loss read every step",

@@ -210,6 +210,16 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   if (out != h->out_internal)   // flags raised by plan/forward (capacity / label overflow)
     FR_CUDA(h, cudaMemcpyAsync(out, h->out_internal, FR_OUT_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
+  // fr_timing_*: the events of this phase's kernels (user pass, personal pass + dG add as "label", local recipe-gradient
+  // pass); the phases that live in other fr_shard_* calls read as zero
+  fr_ctx::TimingSet* ts = nullptr;
+  if (h->timing) {
+    ts = &h->tsets[h->ts_next++ % h->tsets.size()];
+    timing_collect(h, *ts);
+    ts->used = true;
+  }
+#define FR_MARK(i) do { if (ts) cudaEventRecord(ts->ev[i], st); } while (0)
+  FR_MARK(FR_T_SORT); FR_MARK(FR_T_FWD); FR_MARK(FR_T_FINALIZE);
   FinalizeParams fin{};
   fin.DV = DV; fin.B = (float)sh->global_batch; fin.packed = const_cast<float*>(packed_reduced);
   fin.do_reduce = 0; fin.do_apply = 1;
@@ -226,7 +236,11 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   up.items = w.slot_of_row; up.g = h->g; up.cats = w.cats_row; up.cats_by_item = 0;
   up.ws_row = h->ws_row; up.out = out; up.group = w.group; up.mc = h->mc; up.oc = oc;
   up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = b->users;
+  FR_MARK(FR_T_USER_CHUNK);
+  l.mid = ts ? ts->ev[FR_T_USER_COMBINE] : nullptr;
   launch_user_pass(NV, c, up, l);
+  l.mid = nullptr;
+  FR_MARK(FR_T_LABEL);
   if (write_personal) {
     const size_t need = (size_t)S / 32 + 2;
     if (need > h->pieces_personal_chunks) {
@@ -248,7 +262,12 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   ItemPolParams ip{};
   ip.z = h->z; ip.g = h->g; ip.out = out; ip.mc = h->mc; ip.oc = oc;
   PeerPtrs none{}; none.world = 0;
+  FR_MARK(FR_T_ITEM_CHUNK);
+  l.mid = ts ? ts->ev[FR_T_ITEM_COMBINE] : nullptr;
   launch_item_grad_pass(NV, ci, ip, (float4*)grows, grows ? none : w.peer_rgrows, l);
+  l.mid = nullptr;
+  FR_MARK(FR_T_SWEEP); FR_MARK(FR_T_MISC); FR_MARK(FR_T_COUNT);
+#undef FR_MARK
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }

@@ -268,6 +268,48 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t*
   g_launches += 3;
 }
 
+// Two independent scans sharing their three launches (the two sort jobs of a step: blockIdx.y picks the job).
+struct Scan2 { const uint32_t* in[2]; uint32_t* out[2]; uint32_t n[2]; uint32_t* tmp[2]; };
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan2_tile_sums_kernel(const Scan2 s) {
+  const int j = blockIdx.y;
+  if (blockIdx.x * SCAN_TILE >= s.n[j]) return;
+  uint32_t v[SCAN_ITEMS];
+  scan_load(s.in[j], blockIdx.x * SCAN_TILE, s.n[j], v);
+  const uint32_t tot = block_scan_tile(v, 0);
+  if (threadIdx.x == 0) s.tmp[j][blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan2_single_kernel(const Scan2 s) {
+  const int j = blockIdx.y;
+  const uint32_t n = (s.n[j] + SCAN_TILE - 1) / SCAN_TILE;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n; base += SCAN_TILE) {
+    uint32_t v[SCAN_ITEMS];
+    scan_load(s.tmp[j], base, n, v);
+    const uint32_t tot = block_scan_tile(v, carry);
+    scan_store(s.tmp[j], base, n, v);
+    carry += tot;
+  }
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan2_apply_kernel(const Scan2 s) {
+  const int j = blockIdx.y;
+  if (blockIdx.x * SCAN_TILE >= s.n[j]) return;
+  uint32_t v[SCAN_ITEMS];
+  scan_load(s.in[j], blockIdx.x * SCAN_TILE, s.n[j], v);
+  block_scan_tile(v, s.tmp[j][blockIdx.x]);
+  scan_store(s.out[j], blockIdx.x * SCAN_TILE, s.n[j], v);
+}
+static void exclusive_scan2_u32(const Scan2& s, cudaStream_t st) {
+  const uint32_t nmax = s.n[0] > s.n[1] ? s.n[0] : s.n[1];
+  const uint32_t nb = (nmax + SCAN_TILE - 1) / SCAN_TILE;
+  scan2_tile_sums_kernel<<<dim3(nb, 2), SCAN_THREADS, 0, st>>>(s);
+  scan2_single_kernel<<<dim3(1, 2), SCAN_THREADS, 0, st>>>(s);
+  scan2_apply_kernel<<<dim3(nb, 2), SCAN_THREADS, 0, st>>>(s);
+  g_launches += 3;
+}
+
 // ---------------------------------------------------------------- host side
 static void plan_digits(int nbits, int& passes, int& bits_per_pass) {
   if (nbits < 1) nbits = 1;
@@ -310,10 +352,20 @@ void radix_sort_jobs(SortJob* jobs, int njobs, cudaStream_t st, int sm_count) {
     }
     radix_hist_kernel<<<dim3(gx, njobs), FR_THREADS, 0, st>>>(pj);
     ++g_launches;
-    for (int i = 0; i < njobs; ++i)
-      if (pj.j[i].bits && !pj.j[i].fused)
-        exclusive_scan_u32(pj.j[i].tile_hist, pj.j[i].tile_hist, (uint32_t)(1u << pj.j[i].bits) * pj.j[i].ntiles,
-                           jobs[i].bufs->scan_tmp, nullptr, st);
+    const bool need0 = pj.j[0].bits && !pj.j[0].fused, need1 = njobs > 1 && pj.j[1].bits && !pj.j[1].fused;
+    if (need0 && need1) {      // both jobs: one set of launches
+      Scan2 sc{};
+      for (int i = 0; i < 2; ++i) {
+        sc.in[i] = pj.j[i].tile_hist; sc.out[i] = pj.j[i].tile_hist;
+        sc.n[i] = (uint32_t)(1u << pj.j[i].bits) * pj.j[i].ntiles; sc.tmp[i] = jobs[i].bufs->scan_tmp;
+      }
+      exclusive_scan2_u32(sc, st);
+    } else {
+      for (int i = 0; i < njobs; ++i)
+        if (pj.j[i].bits && !pj.j[i].fused)
+          exclusive_scan_u32(pj.j[i].tile_hist, pj.j[i].tile_hist, (uint32_t)(1u << pj.j[i].bits) * pj.j[i].ntiles,
+                             jobs[i].bufs->scan_tmp, nullptr, st);
+    }
     radix_scatter_kernel<<<dim3(gx, njobs), FR_THREADS, 0, st>>>(pj);
     ++g_launches;
     for (int i = 0; i < njobs; ++i) {

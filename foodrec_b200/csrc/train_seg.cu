@@ -487,7 +487,7 @@ struct LabelPol {
 #ifndef FR_LABEL_PF
 #define FR_LABEL_PF 8
 #endif
-    constexpr int PF = FR_LABEL_PF;             // recipe rows in flight
+    constexpr int PF = NV == 1 ? FR_LABEL_PF : FR_LABEL_PF / 2;   // recipe rows in flight (register budget: 128)
     for (int j0 = e0; j0 < e1; j0 += PF) {
       float4 rr4[PF][NV];
 #pragma unroll
@@ -570,17 +570,30 @@ seg_tile_kernel(const SegCommon c, const Pol pol) {
       for (int q = 0; q < NV; ++q) acc[s][q] = f4zero();
     bool started_in_tile = false;      // the open run's head lies inside this tile
     bool has_first = true;             // the open run holds the tile's first entry
+    // the key / permutation / entry of the NEXT 32-entry chunk are requested while the current one is reduced
+    // (key -> permutation -> row -> recipe id -> mask is a chain of dependent loads)
+    uint32_t key_n = 0xffffffffu; typename Pol::Entry e_n;
+    {
+      const bool v0 = tbase + lane < n;
+      key_n = v0 ? c.keys[tbase + lane] : 0xffffffffu;
+      e_n = pol.load_entry(v0 ? c.perm[tbase + lane] : 0u, v0);
+    }
     for (int sub = 0; sub < TC; ++sub) {
       const uint32_t base = tbase + (uint32_t)sub * 32u;
       if (base >= n) break;
       const int cnt = (int)min(32u, n - base);
       const bool valid = lane < cnt;
-      const uint32_t key = valid ? c.keys[base + lane] : 0xffffffffu;
-      const uint32_t ent = valid ? c.perm[base + lane] : 0u;
+      const uint32_t key = key_n;
+      const typename Pol::Entry e = e_n;
+      if (sub + 1 < TC) {
+        const uint32_t nb = base + 32u;
+        const bool v1 = nb + lane < n;
+        key_n = v1 ? c.keys[nb + lane] : 0xffffffffu;
+        e_n = pol.load_entry(v1 ? c.perm[nb + lane] : 0u, v1);
+      }
       const uint32_t prevKey = base > 0 ? c.keys[base - 1] : 0u;
       const bool has_next = base + 32 < n;
       const uint32_t nextKey = has_next ? c.keys[base + 32] : 0u;
-      const typename Pol::Entry e = pol.load_entry(ent, valid);
       const uint32_t up = __shfl_up_sync(FR_FULL, key, 1);
       const bool head = valid && (lane == 0 ? (base == 0 || prevKey != key) : (up != key));
       const uint32_t hm = __ballot_sync(FR_FULL, head);
