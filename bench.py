@@ -332,6 +332,16 @@ def run_sharded(args, cfg, B):
     torch.cuda.synchronize()
     sphases, _ = eng.e.timing_read()
     eng.e.timing_enable(False)
+    # per-phase times of the sharded step (events on the step's stream around every fr_shard_* call and collective)
+    shard_ms = {}
+    for k in range(min(args.steps, 10)):
+        u, it = devb[k % NB]
+        eng.set_batch_dev(L.FR_BPR, B, u, it, global_batch=world * B)
+        evs = []
+        run.step(phase_events=evs)
+        torch.cuda.synchronize()
+        for (name, e0), (_, e1) in zip(evs[:-1], evs[1:]):
+            shard_ms[name] = shard_ms.get(name, 0.0) + e0.elapsed_time(e1) / min(args.steps, 10)
     v = eng.e.read_scalars()
     peak, peak_src = peaks()
     adam_k = {"adam": 6, "adagrad": 4, "rmsprop": 6, "sgd": 2}.get(args.learner.lower(), 2)
@@ -410,7 +420,7 @@ def run_sharded(args, cfg, B):
                            f"id all-to-all + recipe rows / gradient rows stored into peer memory over NVLink by the gather / "
                            f"gradient kernels (cap {eng.cap}/pair, 2 barriers) + 1 packed all-reduce per step" if p2p else
                            f"3 all-to-alls (ids, rows, grad rows, cap {eng.cap}/pair) + 1 packed all-reduce per step")},
-            "clocks": clk, "gpu_launches": int(launches), "roofline": sroof,
+            "clocks": clk, "gpu_launches": int(launches), "roofline": sroof, "shard_phases_ms": shard_ms,
             "e2e": {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                     "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
                     "feed": "ids only (user, pos, neg) from pinned host memory; side tables resident; loss read every step",
@@ -563,6 +573,38 @@ def run_ours(args, cfg, B):
     e2e_serial, _ = e2e_run(True, prefetch=False)
     e2e_cval, _ = e2e_run(False)
 
+    # ---- pointwise instances/s: the reference's own objective (sigmoid cross-entropy on (user, item, label) rows,
+    # Model_Recommender.py:99-104) -- the mode the reference traces pin; same tables, B rows per step, ids resident
+    pw = None
+    if world == 1:
+        rng = np.random.default_rng(77)
+        pwb = []
+        for k in range(NB):
+            pu = torch.as_tensor(rng.integers(0, U, B).astype(np.int32)).to(dev)
+            pi = torch.as_tensor(synth.zipf_items(rng, I, B).astype(np.int32)).to(dev)
+            py = torch.as_tensor((rng.random(B) < 0.8).astype(np.float32)).to(dev)
+            pwb.append((pu, pi, py))
+
+        def pstep(k):
+            pu, pi, py = pwb[k % NB]
+            eng._step_dev(L.FR_POINTWISE, B, pu, pi, None, py, None, None)
+        for k in range(max(args.warmup, 3)):
+            pstep(k)
+        torch.cuda.synchronize()
+        eng.timing_read()
+        eng.timing_enable(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for k in range(args.steps):
+            pstep(k)
+        p1.record(); torch.cuda.synchronize()
+        pph, _ = eng.timing_read()
+        eng.timing_enable(False)
+        pms = p0.elapsed_time(p1) / args.steps
+        pw = {"metric": "pointwise_train_instances_per_sec", "value": B / (pms * 1e-3), "unit": "instances/s",
+              "ms_per_step": pms, "batch": B, "phases_ms": pph,
+              "fwd_gbs_incl_adam_state": B * (24 * D + 32 + 2 * 20 * D + 4 * D) / (pph["fwd"] * 1e-3) / 1e9 if pph["fwd"] > 0 else None}
+
     # ---- top-K users/s: sampled evaluation (51 candidates, K=10: evaluate.py) over NU users
     NU = min(U, 1 << 20)
     rng = np.random.default_rng(5)
@@ -620,6 +662,7 @@ def run_ours(args, cfg, B):
                      "candidates": 51, "K": 10, "users": NU, "ms": eval_ms,
                      "roofline": {"bound": "hbm", "achieved": eval_alg / (eval_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": eval_alg / (eval_ms * 1e-3) / 1e9 / peak}},
+            "pointwise": pw,
             "uniq_users_per_step": uniq_users, "uniq_items_per_step": uniq_items,
         }
         if catalog:

@@ -27,7 +27,7 @@ __device__ __forceinline__ uint32_t resolve_n(const uint32_t* n_dev, uint32_t n_
 
 constexpr int MAX_DIGIT_BITS = 10;
 constexpr int MAX_BINS = 1 << MAX_DIGIT_BITS;
-constexpr int FUSED_SCAN_MAX_TILES = 128;
+constexpr int FUSED_SCAN_MAX_TILES = 16;   // every block re-reads bins x tiles counters: measured 0.30 ms per step at 128 tiles vs 0.145 ms with the separate scan at 256
 
 struct PassJob {
   const uint32_t* keys_in; const uint32_t* vals_in;   // vals_in == nullptr: identity

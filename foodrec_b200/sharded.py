@@ -250,24 +250,37 @@ class DistRunner:
         else:
             self.dist.all_reduce(self._sync)
 
-    def step(self, write_personal=False):
+    def step(self, write_personal=False, phase_events=None):
+        """One training step.  ``phase_events`` (a list) receives (name, torch.cuda.Event) marks recorded on the
+        step's stream before every phase and after the last one -- bench.py's per-phase timing; None: no overhead."""
         d, g = self.dist, self.eng
         p2p = getattr(g, "p2p", False)
-        g.plan()
-        d.all_to_all_single(g.rreq, g.req)               # requests -> owners
-        g.serve()                                        # p2p: rows land in the requesters' rbuf from inside the kernel
+
+        def mark(name):
+            if phase_events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                phase_events.append((name, ev))
+
+        mark("plan"); g.plan()
+        mark("ids_all_to_all"); d.all_to_all_single(g.rreq, g.req)               # requests -> owners
+        mark("serve"); g.serve()                         # p2p: rows land in the requesters' rbuf from inside the kernel
+        mark("rows_exchange")
         if p2p:
             self._barrier()
         else:
             d.all_to_all_single(g.rbuf, g.rows)          # recipe rows -> requesters (NVLink)
-        g.forward()
-        d.all_reduce(g.packed)                           # loss, sum|g|^2, dCat, dG
-        g.update(write_personal)                         # p2p: gradient rows land in the owners' rgrows
+        mark("forward"); g.forward()
+        mark("all_reduce"); d.all_reduce(g.packed)       # loss, sum|g|^2, dCat, dG
+        mark("update"); g.update(write_personal)         # p2p: gradient rows land in the owners' rgrows
+        mark("grads_exchange")
         if p2p:
             self._barrier()
         else:
             d.all_to_all_single(g.rgrows, g.grows)       # finished gradient rows -> owners
-        return g.apply()
+        mark("apply"); out = g.apply()
+        mark("end")
+        return out
 
 
     def catalog_topk(self, users_local, K=100):
