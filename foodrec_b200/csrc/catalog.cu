@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(FIN_THREADS) cat_finalize_kernel(const FinPara
   int* crow = reinterpret_cast<int*>(csc + f.n_split * CAT_CAP);
   __shared__ int s_red[FIN_THREADS / 32];
   __shared__ int s_nF;
+  __shared__ uint32_t s_hist[256], s_sel[2];
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   bool overflow = f.ovf[row] != 0;
@@ -329,17 +330,40 @@ __global__ void __launch_bounds__(FIN_THREADS) cat_finalize_kernel(const FinPara
     // tau = K-th largest approximate score over the union of the split lists
     float lo = -__int_as_float(0x7f800000);
     if (n_tot > f.K) {
-      uint32_t res = 0;
-      for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t trial = res | (1u << bit);
-        int c = 0;
-        for (int e = tid; e < n_tot; e += FIN_THREADS) c += (fkey(csc[e]) >= trial);
-        c = __reduce_add_sync(FR_FULL, c);
-        if (lane == 0) s_red[warp] = c;
+      // exact K-th largest key by 8-bit radix select over a shared-memory histogram: 4 passes x 3 barriers (the
+      // bit-by-bit search it replaces cost 64 barriers and 32 sweeps over the list: 18 % of this kernel's instructions)
+      uint32_t res = 0; uint32_t need = (uint32_t)f.K;
+      for (int pass = 3; pass >= 0; --pass) {
+        for (int b = tid; b < 256; b += FIN_THREADS) s_hist[b] = 0u;
         __syncthreads();
-        c = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        const int sh = 8 * pass;
+        for (int e = tid; e < n_tot; e += FIN_THREADS) {
+          const uint32_t k = fkey(csc[e]);
+          if (pass == 3 || (k >> (sh + 8)) == (res >> (sh + 8))) atomicAdd(&s_hist[(k >> sh) & 255u], 1u);
+        }
         __syncthreads();
-        if (c >= f.K) res = trial;
+        if (warp == 0) {                       // lane l owns bins [8l, 8l+8); counts are taken from the top bin down
+          uint32_t loc[8], sum = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { loc[q] = s_hist[8 * lane + q]; sum += loc[q]; }
+          uint32_t incl = sum;                 // sum over lanes >= this one
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_down_sync(FR_FULL, incl, o);
+            if (lane + o < 32) incl += y;
+          }
+          uint32_t a = incl - sum;             // entries in higher bins than this lane's
+          if (a < need && need <= incl) {
+#pragma unroll
+            for (int q = 7; q >= 0; --q) {
+              if (a + loc[q] >= need) { s_sel[0] = (uint32_t)(8 * lane + q); s_sel[1] = need - a; break; }
+              a += loc[q];
+            }
+          }
+        }
+        __syncthreads();
+        res |= s_sel[0] << sh;
+        need = s_sel[1];
       }
       lo = __fsub_rd(funkey(res), f.margin2[row]);
     }
