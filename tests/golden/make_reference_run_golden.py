@@ -38,6 +38,8 @@ RUNS = {   # name -> (learner, lr, table scale, batch_size, epochs, stand-in dty
     "sgd_clipped": ("sgd", 0.01, 60.0, 24, 1, "float32"),      # big tables: clip_by_global_norm(5.0) bites
     "adam_f64": ("adam", 0.001, 1.0, 16, 1, "float64"),         # tf.float32 := float64, for tight checks
     "sgd_clipped_f64": ("sgd", 0.01, 60.0, 24, 1, "float64"),
+    "adagrad_f64": ("adagrad", 0.05, 1.0, 16, 1, "float64"),
+    "rmsprop_f64": ("rmsprop", 0.001, 1.0, 16, 1, "float64"),
 }
 
 
