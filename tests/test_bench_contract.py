@@ -1,0 +1,59 @@
+"""bench.py's output contract: the reference arm is RUN here (small tables, CPU: the oracle port is what that arm
+times), and the committed B200 lines under profiles/ are checked for the keys the driver and the judge read."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config"}
+
+
+def last_json_line(text):
+    lines = [l for l in text.splitlines() if l.startswith("{")]
+    assert lines, text[-2000:]
+    return json.loads(lines[-1])
+
+
+def test_reference_arm_runs_and_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--small", "--steps", "1",
+                        "--warmup", "1", "--batch", "4096"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = last_json_line(r.stdout)
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"] == "bpr_train_triples_per_sec" and d["unit"] == "triples/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["value"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r01c_bench_*gpu.json"))))
+def test_committed_gpu_lines_carry_the_contract(path):
+    d = last_json_line(open(path).read())
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "bpr_train_triples_per_sec" and d["scaling"] == "weak" and d["dtype"] == "f32"
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"]
+    clk = d["clocks"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(clk)
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clk["reasons"])
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert 0.5 < rf["frac"] < 1.0          # the user pass: ~86 % of the measured copy bandwidth
+    e = d["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e) and e["h2d_bytes_per_step"] > 0
+    assert e["value"] != d["value"]        # measured separately, host buffers inside the timed region
+    if d["n_gpus"] == 1:
+        assert rf["traffic"] and rf["traffic"] >= 0.9 * rf["alg_bytes_per_launch"]     # ncu DRAM bytes vs algorithmic
+        cb = d["cpu_baseline"]
+        assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+        assert d["topk"]["value"] > 0 and d["pointwise"]["value"] > 0 and len(d["catalog_topk"]) == 2
+        for c in d["catalog_topk"]:
+            assert c["roofline"]["bound"] == "tensor" and c["fallback_rows"] == 0
+    else:
+        assert d["shard_phases_ms"] and d["value"] > 0.7 * d["n_gpus"] * 158e6     # weak scaling >= 70 %
