@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B harness (run on the GPU box): train parity tests, then phases_ms per library variant, then an ncu launch list
+# A/B harness (run on the GPU box): the GPU test suite, then phases_ms / top-K / e2e per library variant
+#   AB_VARIANTS="_pf8 _tc4" bash tests/ab_variants.sh   (variants built with foodrec_b200._build.build_variant)
+#   AB_NCU=1 adds an ncu launch list of the same bench command
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 python -m pytest tests -m gpu -x -q > gpurun_out/ab_tests.log 2>&1; tail -3 gpurun_out/ab_tests.log
 for v in "" $AB_VARIANTS; do
