@@ -28,9 +28,9 @@ import numpy as np
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/Code/Recommender"
-D, L, U, I = 8, 5, 14, 90
+L, U, I = 5, 14, 90
 
-RUNS = {   # name -> (learner, lr, table scale, batch_size, epochs, stand-in dtype)
+RUNS = {   # name -> (learner, lr, table scale, batch_size, epochs, stand-in dtype[, extra argv, embed size])
     "adam": ("adam", 0.001, 1.0, 16, 2, "float32"),
     "adagrad": ("adagrad", 0.05, 1.0, 16, 2, "float32"),
     "rmsprop": ("rmsprop", 0.001, 1.0, 16, 2, "float32"),
@@ -40,11 +40,18 @@ RUNS = {   # name -> (learner, lr, table scale, batch_size, epochs, stand-in dty
     "sgd_clipped_f64": ("sgd", 0.01, 60.0, 24, 1, "float64"),
     "adagrad_f64": ("adagrad", 0.05, 1.0, 16, 1, "float64"),
     "rmsprop_f64": ("rmsprop", 0.001, 1.0, 16, 1, "float64"),
+    # other hyper-parameters than the argparse defaults, an embed size whose rows are not a multiple of 8 floats
+    "adam_hyper_f64": ("adam", 0.01, 1.0, 32, 1, "float64",
+                       ["--high_level_score_coefficient", "0.5", "--beta_1", "0.2", "--beta_2", "0.3", "--alpha", "0.4"], 12),
+    "rmsprop_hyper_f64": ("rmsprop", 0.003, 1.0, 128, 2, "float64",
+                          ["--high_level_score_coefficient", "0.25", "--beta_1", "0.05", "--beta_2", "0.5", "--alpha", "1.5"], 20),
 }
 
 
 def one_run(name):
-    learner, lr, scale, bs, epochs, dt = RUNS[name]
+    learner, lr, scale, bs, epochs, dt = RUNS[name][:6]
+    extra = list(RUNS[name][6]) if len(RUNS[name]) > 6 else []
+    D = RUNS[name][7] if len(RUNS[name]) > 7 else 8
     os.environ["FOODREC_TF_STANDIN_DTYPE"] = dt
     sys.path[:0] = [os.path.join(OUT, "tf1_standin"), REF]
     import tensorflow as tf
@@ -78,7 +85,7 @@ def one_run(name):
 
     argv = ["Train_recommender.py", "--path", data, "--dataset", "toy", "--epochs", str(epochs), "--batch_size", str(bs),
             "--lr", str(lr), "--learner", learner, "--out", "0", "--num_dish_images", str(I), "--num_users", str(U),
-            "--num_labels", str(L), "--embed_size", str(D)]
+            "--num_labels", str(L), "--embed_size", str(D)] + extra
     cwd = os.getcwd()
     os.chdir(work)
     sys.argv = argv
@@ -131,6 +138,7 @@ def one_run(name):
     np.savez_compressed(
         os.path.join(OUT, f"reference_run_{name}.npz"),
         argv=np.array(argv[1:]), dtype=dt, learner=learner, lr=lr, batch_size=bs, epochs=epochs,
+        hyper=np.array([glob["args"].high_level_score_coefficient, glob["args"].beta_1, glob["args"].beta_2, glob["args"].alpha]),
         P0=tabs["Personal_Memory"], R0=tabs["Recipe_Embedding"], Cat0=tabs["Category_Embedding"], G0=tabs["General_Memory"],
         P1=fin["P"], R1=fin["R"], Cat1=fin["Cat"], G1=fin["G"], epoch_step=int(final["Epoch_Step"]),
         global_step=int(final["Global_Step"]), kind=kind, off=off, printed_hr_ndcg_loss=np.array(hr),

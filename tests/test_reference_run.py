@@ -41,7 +41,8 @@ def runs(t):
 
 
 def test_traces_cover_the_reference_program():
-    assert {"adam", "adagrad", "rmsprop", "sgd", "sgd_clipped", "adam_f64", "sgd_clipped_f64"} <= set(TRACES)
+    assert {"adam", "adagrad", "rmsprop", "sgd", "sgd_clipped", "adam_f64", "sgd_clipped_f64", "adagrad_f64", "rmsprop_f64",
+            "adam_hyper_f64", "rmsprop_hyper_f64"} <= set(TRACES)
     t = load("adam")
     k = t["kind"]
     # Train_recommender.py:169-187: epoch 0 opens with 16 mini-batches of 8 that fetch `personal`
@@ -59,7 +60,10 @@ def test_oracle_reproduces_the_reference_program(name):
     wide = str(t["dtype"]) == "float64"
     dt = np.float64 if wide else np.float32
     rtol = 1e-11 if wide else 1e-5
-    om = OracleModel(t["P0"], t["R0"], t["Cat0"], t["G0"], OHyper(learner=str(t["learner"]), lr=float(t["lr"])), dtype=dt)
+    a, b1, b2, al = (float(x) for x in t["hyper"])
+    om = OracleModel(t["P0"], t["R0"], t["Cat0"], t["G0"],
+                     OHyper(learner=str(t["learner"]), lr=float(t["lr"]), high_level_score_coefficient=a, beta_1=b1, beta_2=b2,
+                            alpha=al), dtype=dt)
     clipped = 0
     for r, (kind, feed, out) in enumerate(runs(t)):
         if kind == 2:
@@ -101,10 +105,11 @@ def test_dropin_session_reproduces_the_reference_program(name):
     import foodrec_b200 as fb
     t = load(name)
     B = int(np.diff(t["off"]).max())
+    a, b1, b2, al = (float(x) for x in t["hyper"])
     args = types.SimpleNamespace(learner=str(t["learner"]), num_categories=4, num_users=t["P0"].shape[0],
                                  num_labels=t["G0"].shape[0], embed_size=t["P0"].shape[2], lr=float(t["lr"]),
-                                 decay_steps=1000, decay_rate=1.0, high_level_score_coefficient=0.99,
-                                 beta_1=0.01, beta_2=0.01, alpha=0.01, batch_size=B)
+                                 decay_steps=1000, decay_rate=1.0, high_level_score_coefficient=a,
+                                 beta_1=b1, beta_2=b2, alpha=al, batch_size=B)
     model = fb.Model(args, t["P0"], t["R0"], t["Cat0"], t["G0"])
     sess = fb.Session()
     sess.run(fb.global_variables_initializer())
@@ -139,3 +144,20 @@ def test_dropin_session_reproduces_the_reference_program(name):
     hits, ndcgs = fb.evaluate_model(sess, model, d.testRatings, d.testNegatives, 10, d2c)
     assert [int(h) for h in hits] == t["last_hits"].tolist()
     assert [float(x) for x in ndcgs] == t["last_ndcgs"].tolist()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Code/Recommender/Train_recommender.py"),
+                    reason="the reference only exists in the authoring container")
+def test_traces_are_reproducible_from_the_reference(tmp_path):
+    """Re-run the reference's program under the stand-in and compare with the committed trace, array for array."""
+    import shutil
+    import subprocess
+    import sys
+    work = tmp_path / "golden"
+    shutil.copytree(GOLD, work, ignore=shutil.ignore_patterns("reference_run_*.npz", "train_*.npz", "__pycache__"))
+    subprocess.check_call([sys.executable, str(work / "make_reference_run_golden.py"), "sgd_clipped"])
+    new, old = np.load(work / "reference_run_sgd_clipped.npz"), np.load(os.path.join(GOLD, "reference_run_sgd_clipped.npz"))
+    assert set(new.files) == set(old.files)
+    for k in old.files:
+        if k != "argv":                          # (holds the temporary data path)
+            assert np.array_equal(new[k], old[k], equal_nan=old[k].dtype.kind == "f"), k
