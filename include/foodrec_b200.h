@@ -148,7 +148,9 @@ int fr_feed_prefetch(fr_handle h, const fr_batch* host_batch);
 
 /* Per-phase device time of fr_train_step, measured with CUDA events recorded on the
  * step's stream (the measurement bench.py's roofline uses).  fr_timing_read waits for
- * the outstanding events and returns, per phase, the summed milliseconds over n_steps. */
+ * the outstanding events and returns, per phase, the summed milliseconds over n_steps.
+ * fr_shard_update records the same set for its own kernels (user pass and its combine, local recipe-gradient pass;
+ * FR_T_LABEL there = personal pass + dG add); phases that live in other fr_shard_* calls read as zero. */
 enum { FR_T_SORT = 0, FR_T_FWD = 1, FR_T_FINALIZE = 2, FR_T_USER_CHUNK = 3, FR_T_USER_COMBINE = 4,
        FR_T_LABEL = 5, FR_T_ITEM_CHUNK = 6, FR_T_ITEM_COMBINE = 7, FR_T_SWEEP = 8, FR_T_MISC = 9,
        FR_T_COUNT = 10 };
