@@ -28,7 +28,7 @@ import numpy as np
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/Code/Recommender"
-L, U, I = 5, 14, 90
+L, U, I = 5, 14, 90          # (a run may override L: the toy rating files fix U and I)
 
 RUNS = {   # name -> (learner, lr, table scale, batch_size, epochs, stand-in dtype[, extra argv, embed size])
     "adam": ("adam", 0.001, 1.0, 16, 2, "float32"),
@@ -45,6 +45,8 @@ RUNS = {   # name -> (learner, lr, table scale, batch_size, epochs, stand-in dty
                        ["--high_level_score_coefficient", "0.5", "--beta_1", "0.2", "--beta_2", "0.3", "--alpha", "0.4"], 12),
     "rmsprop_hyper_f64": ("rmsprop", 0.003, 1.0, 128, 2, "float64",
                           ["--high_level_score_coefficient", "0.25", "--beta_1", "0.05", "--beta_2", "0.5", "--alpha", "1.5"], 20),
+    # the reference's own defaults where the toy data allows: 95 labels, embed_size 200, batch 128, Adam 0.001
+    "adam_defaults_f64": ("adam", 0.001, 1.0, 128, 2, "float64", [], 200, 95),
 }
 
 
@@ -52,6 +54,7 @@ def one_run(name):
     learner, lr, scale, bs, epochs, dt = RUNS[name][:6]
     extra = list(RUNS[name][6]) if len(RUNS[name]) > 6 else []
     D = RUNS[name][7] if len(RUNS[name]) > 7 else 8
+    L = RUNS[name][8] if len(RUNS[name]) > 8 else globals()["L"]
     os.environ["FOODREC_TF_STANDIN_DTYPE"] = dt
     sys.path[:0] = [os.path.join(OUT, "tf1_standin"), REF]
     import tensorflow as tf

@@ -42,7 +42,7 @@ def runs(t):
 
 def test_traces_cover_the_reference_program():
     assert {"adam", "adagrad", "rmsprop", "sgd", "sgd_clipped", "adam_f64", "sgd_clipped_f64", "adagrad_f64", "rmsprop_f64",
-            "adam_hyper_f64", "rmsprop_hyper_f64"} <= set(TRACES)
+            "adam_hyper_f64", "rmsprop_hyper_f64", "adam_defaults_f64"} <= set(TRACES)
     t = load("adam")
     k = t["kind"]
     # Train_recommender.py:169-187: epoch 0 opens with 16 mini-batches of 8 that fetch `personal`
