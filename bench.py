@@ -386,19 +386,8 @@ def run_sharded(args, cfg, B):
                  "update_phase_ms": {k: sphases[k] for k in ("finalize", "user_chunk", "user_combine", "label", "item_chunk", "item_combine")}}
     clk = clocks.stop()
     value = world * B * args.steps / (ms / 1e3)
-    # e2e: ids from pinned host memory every step, loss read on the host every step
-    ubuf = torch.empty(B, dtype=torch.int32, device=dev); ibuf = torch.empty(2 * B, dtype=torch.int32, device=dev)
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        hu, hi = pin[k % NB]
-        ubuf.copy_(hu, non_blocking=True); ibuf.copy_(hi, non_blocking=True)
-        eng.set_batch_dev(L.FR_BPR, B, ubuf, ibuf, global_batch=world * B)
-        out = run.step()
-        loss = float(out[L.FR_OUT_LOSS])                      # D2H + sync
-    dist.barrier(); torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
-    # ---- item-sharded full-catalog top-100: n_q query users PER GPU (weak scaling), recipes sharded by id % N:
+    # ---- item-sharded full-catalog top-100: n_q query users PER GPU (weak scaling), recipes sharded by id % N
+    # (before the e2e leg trains the tables further: see the note at the single-GPU catalog leg):
     # all-gather of the query rows, per-shard tcgen05 top-K, all-to-all of the lists, exact merge
     catalog = None
     if not args.no_catalog:
@@ -438,6 +427,18 @@ def run_sharded(args, cfg, B):
                             f"(weak scaling: every GPU scores all {world * n_q} gathered users against its {Il4} recipes)",
                 "ms": cms4, "fallback_rows_rank0": e4.e.catalog_fallback_rows(),
                 "dense_equivalent_tflops_per_gpu": 2.0 * world * n_q * Il4 * 5 * D / (cms4 * 1e-3) / 1e12}]
+    # e2e: ids from pinned host memory every step, loss read on the host every step
+    ubuf = torch.empty(B, dtype=torch.int32, device=dev); ibuf = torch.empty(2 * B, dtype=torch.int32, device=dev)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        hu, hi = pin[k % NB]
+        ubuf.copy_(hu, non_blocking=True); ibuf.copy_(hi, non_blocking=True)
+        eng.set_batch_dev(L.FR_BPR, B, ubuf, ibuf, global_batch=world * B)
+        out = run.step()
+        loss = float(out[L.FR_OUT_LOSS])                      # D2H + sync
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
