@@ -356,13 +356,13 @@ def test_sampled_eval_duplicates_across_slots(ncand):
     nc = np.full(U, ncand, np.int32); nc[7] = 33; nc[8] = 32; nc[9] = 1
     ids, rank, sc = e.eval_sampled_topk(np.arange(U), cand, nc, 10, cand_cats=p.item_cats[cand], return_scores=True)
     ids, rank = ids.cpu().numpy(), rank.cpu().numpy()
+    import heapq
     S = p.tb.P[:, 1, :I]
     for u in range(U):
         c = cand[u, :nc[u]].tolist()
         m = {}
         for it in c:
             m[it] = S[u, it]
-        import heapq
         want = heapq.nlargest(10, m, key=m.get)
         got = [int(x) for x in ids[u] if x >= 0]
         assert got == want, (u, got, want)
