@@ -14,6 +14,12 @@
 
 namespace fr {
 
+#ifdef FR_CAT_TILE_BOUND
+#define FR_CAT_M2R(w) , (w).margin2r
+#else
+#define FR_CAT_M2R(w)
+#endif
+
 struct CatalogWs {
   bool prepared = false;
   int cta_group = 1, epi_sets = 1, BN = 128, a_split = 0, I = 0, KP = 0, k_blocks = 0, n_tiles = 0, present = 0, n_valid_items = 0;
@@ -22,6 +28,9 @@ struct CatalogWs {
   uint32_t* keys = nullptr; SortBufs sortM; int32_t* gs_dev = nullptr;
   __nv_bfloat16* Bq = nullptr; int32_t *row_item = nullptr, *tile_group = nullptr, *tile_valid = nullptr, *tile_pos = nullptr;
   float* rmax = nullptr;
+#ifdef FR_CAT_TILE_BOUND
+  float *tile_rn = nullptr, *tile_rho = nullptr, *margin2r = nullptr;    // staged per-tile bound (catalog.cuh)
+#endif
   const float4* item_cats = nullptr;      // [I,4] masks of THIS table's recipes (tables.item_cats unless overridden)
   int tiles_cap = 0;
   CUtensorMap tmB;
@@ -58,7 +67,11 @@ __global__ void cat_group_bounds_kernel(const uint32_t* __restrict__ sorted_keys
 __global__ void __launch_bounds__(FR_THREADS)
 cat_pack_items_kernel(const float4* __restrict__ R, int DV, int KP, const uint32_t* __restrict__ sorted_idx,
                       const int32_t* __restrict__ tile_valid, const int32_t* __restrict__ tile_pos, int n_rows, int BN,
-                      __nv_bfloat16* __restrict__ Bq, int32_t* __restrict__ row_item, float* __restrict__ rmax) {
+                      __nv_bfloat16* __restrict__ Bq, int32_t* __restrict__ row_item, float* __restrict__ rmax
+#ifdef FR_CAT_TILE_BOUND
+                      , float* __restrict__ tile_rn
+#endif
+                      ) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= n_rows) return;
@@ -79,7 +92,21 @@ cat_pack_items_kernel(const float4* __restrict__ R, int DV, int KP, const uint32
   }
   nrm = warp_sum(nrm);
   if (lane == 0 && valid) atomicMax(reinterpret_cast<int*>(rmax), __float_as_int(sqrtf(nrm) * 1.000001f));
+#ifdef FR_CAT_TILE_BOUND
+  if (lane == 0 && valid) atomicMax(reinterpret_cast<int*>(tile_rn + tile), __float_as_int(sqrtf(nrm) * 1.000001f));
+#endif
 }
+
+#ifdef FR_CAT_TILE_BOUND
+// rho[t] = (largest recipe norm of tile t) / (largest of the catalog), rounded up and clamped to (0, 1]
+__global__ void cat_tile_rho_kernel(const float* __restrict__ tile_rn, const float* __restrict__ rmax, int n_tiles,
+                                    float* __restrict__ rho) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const float m = *rmax;
+  rho[t] = m > 0.f ? fminf(1.0f, __fmul_ru(__fdiv_ru(tile_rn[t], m), 1.000001f)) : 1.0f;
+}
+#endif
 
 // ------------------------------------------------------------------ per-pass user operand
 struct UserSrc {
@@ -141,7 +168,11 @@ __global__ void __launch_bounds__(FR_THREADS)
 cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restrict__ Cat, int DV, int KP, int a_split, float a,
                       float oma, int present, const float* __restrict__ rmax_p, float cfac,
                       __nv_bfloat16* __restrict__ A, float* __restrict__ bias, float* __restrict__ margin2,
-                      int32_t* __restrict__ block_first, int block_rows) {
+                      int32_t* __restrict__ block_first, int block_rows
+#ifdef FR_CAT_TILE_BOUND
+                      , float* __restrict__ margin2r
+#endif
+                      ) {
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (j >= m_pad) return;
@@ -174,6 +205,9 @@ cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restri
   }
   const float rmax = __ldg(rmax_p);
   float emax = 0.f, bbest = -__int_as_float(0x7f800000);
+#ifdef FR_CAT_TILE_BOUND
+  float eround = 0.f;
+#endif
   int gbest = 0;
   for (int g = 1; g < 16; ++g) {
     if (!((present >> g) & 1)) continue;
@@ -211,13 +245,21 @@ cat_pack_users_kernel(UserSrc src, int n_rows, int m_pad, const float4* __restri
     for (int c = 0; c < 4; ++c) if ((g >> c) & 1) hs += h[c];
     const float b = (float)((double)a * (hs / (double)__popc(g)));
     const float ar = sqrtf(nrm) * rmax;
+#ifdef FR_CAT_TILE_BOUND
+    emax = fmaxf(emax, cfac * ar);                                    // scales with the tile's largest recipe norm
+    eround = fmaxf(eround, 4.76837158e-7f * (fabsf(b) + ar));         // 2^-21: the fp32 roundings of bias, bias - E, v + bias
+#else
     const float E = cfac * ar + 4.76837158e-7f * (fabsf(b) + ar);     // 2^-21: fp32 rounding of bias and of v + bias
     emax = fmaxf(emax, E);
+#endif
     if (b > bbest) { bbest = b; gbest = g; }
     if (lane == 0) bias[(size_t)g * m_pad + j] = b;
   }
   if (lane == 0) {
     margin2[j] = 2.0f * emax * 1.00001f;
+#ifdef FR_CAT_TILE_BOUND
+    margin2r[j] = 2.0f * eround * 1.00001f;
+#endif
     if (block_first && j % block_rows == 0) block_first[j / block_rows] = gbest;   // the block sweeps this group first
   }
 }
@@ -292,6 +334,9 @@ struct FinParams {
   int D, n_rows, m_pad, n_split, K;
   double a, oma;
   const float* margin2; const float* cand_sc; const int32_t* cand_row; const int32_t* cand_cnt;
+#ifdef FR_CAT_TILE_BOUND
+  const float* margin2r; const float* tile_rho; int bn_shift;
+#endif
   const int32_t* ovf; int32_t* ovf_list; int32_t* ovf_count;
   int id_mul, id_add;
   int32_t* out_ids; double* out_scores;     // [n_users, K]
@@ -365,10 +410,18 @@ __global__ void __launch_bounds__(FIN_THREADS) cat_finalize_kernel(const FinPara
         res |= s_sel[0] << sh;
         need = s_sel[1];
       }
+#ifdef FR_CAT_TILE_BOUND
+      lo = funkey(res);                 // K-th largest LOWER bound over the union of the lists
+#else
       lo = __fsub_rd(funkey(res), f.margin2[row]);
+#endif
     }
     for (int e = tid; e < n_tot; e += FIN_THREADS) {
+#ifdef FR_CAT_TILE_BOUND
+      if (__fadd_ru(__fmaf_ru(f.margin2[row], __ldg(f.tile_rho + (crow[e] >> f.bn_shift)), csc[e]), f.margin2r[row]) >= lo) {
+#else
       if (csc[e] >= lo) {
+#endif
         const int pos = atomicAdd(&s_nF, 1);
         if (pos < CAT_FCAP) frow[pos] = crow[e];
       }
@@ -670,6 +723,10 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, cons
     if ((rc = dalloc(h, &w.tile_valid, (size_t)w.tiles_cap))) return rc;
     if ((rc = dalloc(h, &w.tile_pos, (size_t)w.tiles_cap))) return rc;
     if ((rc = dalloc(h, &w.rmax, 1))) return rc;
+#ifdef FR_CAT_TILE_BOUND
+    if ((rc = dalloc(h, &w.tile_rn, (size_t)w.tiles_cap))) return rc;
+    if ((rc = dalloc(h, &w.tile_rho, (size_t)w.tiles_cap))) return rc;
+#endif
     FR_CUDA(h, catalog_gemm_configure());
     FR_CUDA(h, cudaFuncSetAttribute(cat_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
@@ -713,11 +770,22 @@ extern "C" int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, cons
     FR_CUDA(h, cudaMemcpyAsync(w.tile_valid, tv.data(), tv.size() * 4, cudaMemcpyHostToDevice, st));
     FR_CUDA(h, cudaMemcpyAsync(w.tile_pos, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice, st));
     FR_CUDA(h, cudaMemsetAsync(w.rmax, 0, 4, st));
+#ifdef FR_CAT_TILE_BOUND
+    FR_CUDA(h, cudaMemsetAsync(w.tile_rn, 0, (size_t)w.n_tiles * 4, st));
+#endif
     const int n_rows = w.n_tiles * BN;
     cat_pack_items_kernel<<<(n_rows + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK, FR_THREADS, 0, st>>>(
         reinterpret_cast<const float4*>(h->tab.R), DV, KP, w.sortM.v[r], w.tile_valid, w.tile_pos, n_rows, BN, w.Bq,
-        w.row_item, w.rmax);
+        w.row_item, w.rmax
+#ifdef FR_CAT_TILE_BOUND
+        , w.tile_rn
+#endif
+        );
     ++g_launches;
+#ifdef FR_CAT_TILE_BOUND
+    cat_tile_rho_kernel<<<(w.n_tiles + 255) / 256, 256, 0, st>>>(w.tile_rn, w.rmax, w.n_tiles, w.tile_rho);
+    ++g_launches;
+#endif
     FR_CHECK_LAUNCH(h);
     FR_CUDA(h, cudaStreamSynchronize(st));     // host vectors above go out of scope
     if ((rc = make_tmap(h, &w.tmB, w.Bq, (uint64_t)w.n_tiles * BN, KP, BN / w.cta_group))) return rc;
@@ -734,6 +802,9 @@ static int catalog_ensure_pass_ws(fr_ctx* h, CatalogWs& w, int mp) {
   if ((rc = dalloc(h, &w.A, 16 * R * w.KP * 2))) return rc;
   if ((rc = dalloc(h, &w.bias, 16 * R))) return rc;
   if ((rc = dalloc(h, &w.margin2, R))) return rc;
+#ifdef FR_CAT_TILE_BOUND
+  if ((rc = dalloc(h, &w.margin2r, R))) return rc;
+#endif
   const size_t RL = R * 4;          // candidate lists: up to 4 column sets per (split, row)
   if ((rc = dalloc(h, &w.cand_sc, RL * CAT_CAP))) return rc;
   if ((rc = dalloc(h, &w.cand_row, RL * CAT_CAP))) return rc;
@@ -809,10 +880,10 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     const int pgrid = (m_pad + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
     if (h->NV == 1)
       cat_pack_users_kernel<1><<<pgrid, FR_THREADS, 0, st>>>(src, rows, m_pad, Cat4, DV, w.KP, w.a_split, h->mc.a, h->mc.oma, w.present,
-                                                            w.rmax, cfac, w.A, w.bias, w.margin2, bf, BMC);
+                                                            w.rmax, cfac, w.A, w.bias, w.margin2, bf, BMC FR_CAT_M2R(w));
     else
       cat_pack_users_kernel<2><<<pgrid, FR_THREADS, 0, st>>>(src, rows, m_pad, Cat4, DV, w.KP, w.a_split, h->mc.a, h->mc.oma, w.present,
-                                                            w.rmax, cfac, w.A, w.bias, w.margin2, bf, BMC);
+                                                            w.rmax, cfac, w.A, w.bias, w.margin2, bf, BMC FR_CAT_M2R(w));
     ++g_launches;
     FR_CHECK_LAUNCH(h);
     FR_CUDA(h, cudaMemsetAsync(w.cand_cnt, 0, (size_t)n_lists * m_pad * 4, st));
@@ -830,6 +901,9 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
       // measurements (catalog.cuh), _DENSE_MIN / _BOOT_TILES = epilogue regime knobs, _CYCLES = in-kernel cycle counters
       { const char* dm = getenv("FOODREC_CATALOG_DEBUG"); p.debug_mode = dm ? atoi(dm) : 0; }
       p.tile_group = w.tile_group; p.tile_valid = w.tile_valid; p.bias = w.bias; p.margin2 = w.margin2;
+#ifdef FR_CAT_TILE_BOUND
+      p.tile_rho = w.tile_rho; p.margin2r = w.margin2r; p.bn_shift = w.BN == 256 ? 8 : 7;
+#endif
       p.block_first = bf;
       { const char* dmn = getenv("FOODREC_CATALOG_DENSE_MIN"); p.dense_min = dmn ? atoi(dmn) : 3; }
       {   // bootstrap length: as many tiles as chunk maxima fit one candidate list (64 tiles = 16k recipes by default)
@@ -851,6 +925,9 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     f.row_item = w.row_item; f.D = D; f.n_rows = rows; f.m_pad = m_pad; f.n_split = n_lists; f.K = K;
     f.a = (double)h->mc.a; f.oma = (double)h->mc.oma;
     f.margin2 = w.margin2; f.cand_sc = w.cand_sc; f.cand_row = w.cand_row; f.cand_cnt = w.cand_cnt;
+#ifdef FR_CAT_TILE_BOUND
+    f.margin2r = w.margin2r; f.tile_rho = w.tile_rho; f.bn_shift = w.BN == 256 ? 8 : 7;
+#endif
     f.ovf = w.ovf; f.ovf_list = w.ovf_list; f.ovf_count = w.ovf_count;
     f.id_mul = id_mul; f.id_add = id_add; f.out_ids = out_ids; f.out_scores = out_scores;
     const size_t fsm = (size_t)CAT_FCAP * (8 + 4 + 4) + 32 + (size_t)5 * D * 4 + (size_t)n_lists * CAT_CAP * 8 +

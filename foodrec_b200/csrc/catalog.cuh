@@ -60,6 +60,15 @@ struct CatGemmParams {
   int32_t* cand_cnt;           // [n_split*NSET*m_pad]
   int32_t* ovf;                // [m_pad] 1 = candidate list overflowed
   unsigned long long* dbg;     // nullable: cycle counters {mma total, wait tempty, wait full, n, epi total, wait tfull, n}
+#ifdef FR_CAT_TILE_BOUND
+  // STAGED FOR ROUND 2, NOT PART OF THE DEFAULT BUILD, NOT YET RUN ON A GPU (build_variant("tilebound", ["FR_CAT_TILE_BOUND"])).
+  // Per-tile error bound: E[u,t] = 0.5 * (margin2[u] * tile_rho[t] + margin2r[u]); the lists hold LOWER bounds
+  // s_hat - E[u,t] and a recipe is kept iff its upper bound s_hat + E[u,t] reaches the K-th largest lower bound so far
+  // (oracle/catalog_filter_model.py states and tests the rule).
+  const float* tile_rho;       // [n_tiles] largest recipe norm of the tile / largest of the catalog, rounded up, <= 1
+  const float* margin2r;       // [m_pad]  the part of 2E that does not scale with the recipe norm (fp32 roundings)
+  int bn_shift;                // log2(tile width): padded recipe row -> tile
+#endif
 };
 
 void launch_catalog_gemm(int cta_group, int epi_sets, int tile_n, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmB,

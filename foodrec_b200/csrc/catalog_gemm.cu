@@ -84,7 +84,12 @@ struct CompactOut { int cnt; float thr; };
 __device__ __noinline__ CompactOut catalog_warp_compact(const int L, const int lane, float* __restrict__ cand_sc,
                                                         int32_t* __restrict__ cand_row, const size_t my_base,
                                                         const int my_cnt, const float my_thr, const float my_margin2,
-                                                        const int K, int32_t* ovf_flag, const bool drop_all) {
+                                                        const int K, int32_t* ovf_flag, const bool drop_all
+#ifdef FR_CAT_TILE_BOUND
+                                                        , const float my_margin2r, const float* __restrict__ tile_rho,
+                                                        const int bn_shift
+#endif
+                                                        ) {
   constexpr int NV = CAT_CAP / 32;
   const size_t base = __shfl_sync(FR_FULL, (unsigned long long)my_base, L);
   const int n = min(__shfl_sync(FR_FULL, my_cnt, L), CAT_CAP);
@@ -107,7 +112,12 @@ __device__ __noinline__ CompactOut catalog_warp_compact(const int L, const int l
     c = __reduce_add_sync(FR_FULL, c);
     if (c >= K) res = trial;
   }
+#ifdef FR_CAT_TILE_BOUND
+  const float m2r = __shfl_sync(FR_FULL, my_margin2r, L);
+  const float nthr = funkey(res);      // the entries are LOWER bounds: their K-th largest bounds the K-th best true score from below
+#else
   const float nthr = __fsub_rd(funkey(res), m2);
+#endif
   if (drop_all) {                      // bootstrap: the entries were chunk maxima, only the bound is kept
     CompactOut r{my_cnt, my_thr};
     if (lane == L) { r.cnt = 0; if (n >= K) r.thr = nthr; }
@@ -116,7 +126,13 @@ __device__ __noinline__ CompactOut catalog_warp_compact(const int L, const int l
   int out = 0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
+#ifdef FR_CAT_TILE_BOUND
+    // keep iff the entry's UPPER bound (lower bound + 2E of its own tile, rounded up) reaches the threshold
+    const bool keep = (i * 32 + lane < n) &&
+                      (__fadd_ru(__fmaf_ru(m2, __ldg(tile_rho + (rw[i] >> bn_shift)), sc[i]), m2r) >= nthr);
+#else
     const bool keep = (i * 32 + lane < n) && (sc[i] >= nthr);
+#endif
     const uint32_t bal = __ballot_sync(FR_FULL, keep);
     if (keep) {
       const int pos = out + __popc(bal & ((1u << lane) - 1u));
@@ -137,6 +153,16 @@ __device__ __noinline__ CompactOut catalog_warp_compact(const int L, const int l
 // Per-lane filter state of one (column set, user row): lives in registers for the whole sweep.
 struct RowState {
   float thr, adj, bias, m2;
+#ifdef FR_CAT_TILE_BOUND
+  float m2r, er, bt;       // rounding part of 2E; E of (row, current tile); bias - E: what is added to a stored value
+#define FR_CAT_SBIAS(s) ((s).bt)
+#define FR_CAT_ADJ(s) __fsub_rd(__fsub_rd((s).thr, (s).bias), (s).er)            /* push iff v + bias + E >= thr */
+#define FR_CAT_COMPACT_EXTRA(s, p) , (s).m2r, (p).tile_rho, (p).bn_shift
+#else
+#define FR_CAT_SBIAS(s) ((s).bias)
+#define FR_CAT_ADJ(s) __fsub_rd((s).thr, (s).bias)
+#define FR_CAT_COMPACT_EXTRA(s, p)
+#endif
   int cnt;
   size_t base;
   int32_t* ovf;
@@ -159,7 +185,7 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
   const float mx = fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3]));
   if (boot) {                                    // bootstrap pass: one value per chunk, no candidates
     if (col + 32 <= nvalid && s.thr < __int_as_float(0x7f800000)) {
-      __stcg(p.cand_sc + s.base + s.cnt, mx + s.bias);
+      __stcg(p.cand_sc + s.base + s.cnt, mx + FR_CAT_SBIAS(s));
       ++s.cnt;
     }
     return;
@@ -183,7 +209,7 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
     while (hm) {                                         // cnt <= CAP - 32 on entry (compaction policy): no bound check
       const int j = __ffs(hm) - 1;
       hm &= hm - 1;
-      __stcg(p.cand_sc + s.base + s.cnt, stage[j * 32 + lane] + s.bias);
+      __stcg(p.cand_sc + s.base + s.cnt, stage[j * 32 + lane] + FR_CAT_SBIAS(s));
       __stcg(p.cand_row + s.base + s.cnt, n0 + col + j);
       ++s.cnt;
     }
@@ -201,7 +227,7 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
         const bool hit = (x >= s.adj) && (col + 8 * G + jj < nvalid);   // zero padding is never a candidate
         if (__any_sync(FR_FULL, hit)) {
           if (hit) {                                       // cnt <= CAP - 32 on entry (compaction policy): no bound check
-            __stcg(p.cand_sc + s.base + s.cnt, x + s.bias);
+            __stcg(p.cand_sc + s.base + s.cnt, x + FR_CAT_SBIAS(s));
             __stcg(p.cand_row + s.base + s.cnt, n0 + col + 8 * G + jj);
             ++s.cnt;
           }
@@ -228,7 +254,7 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
         if (c < nvalid) {                                    // zero padding at the end of a mask group is never a candidate
           const float x = tc::tmem_ld_32x1(tchunk + 8 * G + jj);
           if (x >= s.adj) {                                  // cnt <= CAP - 32 on entry (compaction policy): no bound check
-            __stcg(p.cand_sc + s.base + s.cnt, x + s.bias);
+            __stcg(p.cand_sc + s.base + s.cnt, x + FR_CAT_SBIAS(s));
             __stcg(p.cand_row + s.base + s.cnt, n0 + c);
             ++s.cnt;
           }
@@ -241,9 +267,10 @@ __device__ __forceinline__ void catalog_filter_chunk(const float (&v)[32], const
   while (need) {
     const int L = __ffs(need) - 1;
     need &= need - 1;
-    const CompactOut o = catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, s.base, s.cnt, s.thr, s.m2, p.K, s.ovf, false);
+    const CompactOut o = catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, s.base, s.cnt, s.thr, s.m2, p.K, s.ovf, false
+                                              FR_CAT_COMPACT_EXTRA(s, p));
     s.cnt = o.cnt; s.thr = o.thr;
-    s.adj = __fsub_rd(s.thr, s.bias);
+    s.adj = FR_CAT_ADJ(s);
   }
 }
 
@@ -397,6 +424,9 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       RowState s;
       s.base = list * CAT_CAP; s.m2 = __ldg(p.margin2 + grow); s.thr = (valid && p.debug_mode != 3) ? -INF : INF; s.cnt = 0; s.bias = 0.f;
       s.adj = s.thr; s.ovf = p.ovf + grow;
+#ifdef FR_CAT_TILE_BOUND
+      s.m2r = __ldg(p.margin2r + grow); s.er = 0.f; s.bt = 0.f;
+#endif
       int cur_g = -1;
       GroupCursor gc{0, 0, 0};
       for (int e2 = 0; e2 < sweep_len(sr); ++e2, ++tcount) {
@@ -404,7 +434,8 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool boot = e2 < sr.boot;
         if (e2 == sr.boot && sr.boot > 0) {             // bootstrap done: K-th largest chunk maximum of every row -> threshold
           for (int L = 0; L < 32; ++L) {
-            const CompactOut o = catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, s.base, s.cnt, s.thr, s.m2, p.K, s.ovf, true);
+            const CompactOut o = catalog_warp_compact(L, lane, p.cand_sc, p.cand_row, s.base, s.cnt, s.thr, s.m2, p.K, s.ovf, true
+                                                      FR_CAT_COMPACT_EXTRA(s, p));
             s.cnt = o.cnt; s.thr = o.thr;
           }
         }
@@ -413,7 +444,11 @@ catalog_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int g = gc.g;
         const int nvalid = (t == gc.hi - 1) ? p.group_last_valid[g] : BN;     // rows of this tile that hold a recipe
         if (g != cur_g) { cur_g = g; s.bias = __ldg(p.bias + (size_t)g * p.m_pad + grow); }
-        s.adj = __fsub_rd(s.thr, s.bias);               // push iff  v + bias >= thr
+#ifdef FR_CAT_TILE_BOUND
+        s.er = __fmaf_ru(0.5f * s.m2, __ldg(p.tile_rho + t), 0.5f * s.m2r);    // E[row, tile], rounded up
+        s.bt = __fsub_rd(s.bias, s.er);
+#endif
+        s.adj = FR_CAT_ADJ(s);                          // push iff  v + bias (+ E) >= thr
         const long long c2 = p.dbg ? clock64() : 0;
         tc::mbar_wait(&tfull[as], aph);
         tc::fence_after_sync();
