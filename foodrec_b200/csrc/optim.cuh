@@ -118,13 +118,28 @@ __device__ __forceinline__ void adam_touch(float& var, float& m, float& v, float
   r = r * fmaf(-d, r, 2.0f);
   var = fmaf(-__fmul_rn(oc.lr_t, m), r, var);
 }
+// TF-1.15 core/kernels/training_ops.cc uses DIFFERENT arithmetic forms for its sparse and its dense apply ops
+// (oracle/recommender_oracle.py:_adagrad/_rmsprop restate both): SPARSE = the rows of P and R (SparseApply*Op),
+// dense = Category_Embedding (Apply*<CPUDevice>, finalize_kernel).  rsqrt(x) is the IEEE 1/sqrt(x).
+template <bool SPARSE>
 __device__ __forceinline__ void adagrad_touch(float& var, float& acc, float g, const OptConsts& oc) {
-  acc = __fadd_rn(acc, __fmul_rn(g, g));
-  var = __fsub_rn(var, __fdiv_rn(__fmul_rn(oc.lr, g), __fsqrt_rn(acc)));
+  acc = __fadd_rn(acc, __fmul_rn(g, g));                       // a += g.square()
+  const float rs = __frcp_rn(__fsqrt_rn(acc));
+  // sparse: v -= (lr * g) * a.rsqrt();  dense: var -= (grad * lr) * accum.rsqrt()  (the products commute)
+  var = __fsub_rn(var, __fmul_rn(__fmul_rn(oc.lr, g), rs));
 }
+template <bool SPARSE>
 __device__ __forceinline__ void rmsprop_touch(float& var, float& ms, float& mom, float g, const OptConsts& oc) {
-  ms = __fadd_rn(ms, __fmul_rn(__fsub_rn(__fmul_rn(g, g), ms), oc.omrho));
-  mom = __fadd_rn(__fmul_rn(mom, 0.f), __fdiv_rn(__fmul_rn(oc.lr, g), __fsqrt_rn(__fadd_rn(ms, oc.rms_eps))));
+  if constexpr (SPARSE) {
+    // ms = ms * rho + grad.square() * (1 - rho);  mom = mom * momentum + (ms + eps).rsqrt() * lr * grad
+    ms = __fadd_rn(__fmul_rn(ms, oc.rho), __fmul_rn(__fmul_rn(g, g), oc.omrho));
+    const float rs = __frcp_rn(__fsqrt_rn(__fadd_rn(ms, oc.rms_eps)));
+    mom = __fadd_rn(__fmul_rn(mom, 0.f), __fmul_rn(__fmul_rn(rs, oc.lr), g));
+  } else {
+    // ms += (grad.square() - ms) * (1 - rho);  mom = mom * momentum + (grad * lr) / (ms + eps).sqrt()
+    ms = __fadd_rn(ms, __fmul_rn(__fsub_rn(__fmul_rn(g, g), ms), oc.omrho));
+    mom = __fadd_rn(__fmul_rn(mom, 0.f), __fdiv_rn(__fmul_rn(g, oc.lr), __fsqrt_rn(__fadd_rn(ms, oc.rms_eps))));
+  }
   var = __fsub_rn(var, mom);
 }
 __device__ __forceinline__ void sgd_touch(float& var, float g, const OptConsts& oc) {
@@ -180,11 +195,11 @@ __device__ __forceinline__ void apply_and_store(RowState<NR, NV>& st, float4* va
         adam_touch(var.x, a.x, b.x, g.x, oc); adam_touch(var.y, a.y, b.y, g.y, oc);
         adam_touch(var.z, a.z, b.z, g.z, oc); adam_touch(var.w, a.w, b.w, g.w, oc);
       } else if (oc.learner == FR_ADAGRAD) {
-        adagrad_touch(var.x, a.x, g.x, oc); adagrad_touch(var.y, a.y, g.y, oc);
-        adagrad_touch(var.z, a.z, g.z, oc); adagrad_touch(var.w, a.w, g.w, oc);
+        adagrad_touch<true>(var.x, a.x, g.x, oc); adagrad_touch<true>(var.y, a.y, g.y, oc);
+        adagrad_touch<true>(var.z, a.z, g.z, oc); adagrad_touch<true>(var.w, a.w, g.w, oc);
       } else if (oc.learner == FR_RMSPROP) {
-        rmsprop_touch(var.x, a.x, b.x, g.x, oc); rmsprop_touch(var.y, a.y, b.y, g.y, oc);
-        rmsprop_touch(var.z, a.z, b.z, g.z, oc); rmsprop_touch(var.w, a.w, b.w, g.w, oc);
+        rmsprop_touch<true>(var.x, a.x, b.x, g.x, oc); rmsprop_touch<true>(var.y, a.y, b.y, g.y, oc);
+        rmsprop_touch<true>(var.z, a.z, b.z, g.z, oc); rmsprop_touch<true>(var.w, a.w, b.w, g.w, oc);
       } else {
         sgd_touch(var.x, g.x, oc); sgd_touch(var.y, g.y, oc); sgd_touch(var.z, g.z, oc); sgd_touch(var.w, g.w, oc);
       }

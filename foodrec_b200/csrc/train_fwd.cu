@@ -330,9 +330,9 @@ finalize_kernel(const FinalizeParams p) {
       x = __fsub_rn(x, __fdiv_rn(__fmul_rn(m, oc.lr_t), __fadd_rn(__fsqrt_rn(v), oc.eps)));
       s1[j] = m; s2[j] = v;
     } else if (oc.learner == FR_ADAGRAD) {
-      float acc = s1[j]; adagrad_touch(x, acc, g, oc); s1[j] = acc;
+      float acc = s1[j]; adagrad_touch<false>(x, acc, g, oc); s1[j] = acc;
     } else if (oc.learner == FR_RMSPROP) {
-      float ms = s1[j], mom = s2[j]; rmsprop_touch(x, ms, mom, g, oc); s1[j] = ms; s2[j] = mom;
+      float ms = s1[j], mom = s2[j]; rmsprop_touch<false>(x, ms, mom, g, oc); s1[j] = ms; s2[j] = mom;
     } else {
       sgd_touch(x, g, oc);
     }

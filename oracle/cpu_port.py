@@ -114,24 +114,26 @@ class CpuPort:
         self.Cat.addcdiv_(m, v.sqrt() + eps, value=-lr_t)
         self.b1p, self.b2p = np.float32(self.b1p * np.float32(b1)), np.float32(self.b2p * np.float32(b2))
 
-    def _adagrad(self, uu, gP, ui, gR, dCat):
+    def _adagrad(self, uu, gP, ui, gR, dCat):          # TF-1.15 forms: recommender_oracle.OracleModel._adagrad
         lr = self.h.lr
         for name, var, idx, g in (("P", self.P, uu, gP), ("R", self.R, ui, gR)):
             acc = self.acc[name]
             a = acc[idx] + g * g
             acc[idx] = a
-            var[idx] -= lr * g / a.sqrt()
+            var[idx] -= (lr * g) * a.rsqrt()
         self.acc["Cat"] += dCat * dCat
-        self.Cat -= lr * dCat / self.acc["Cat"].sqrt()
+        self.Cat -= (dCat * lr) * self.acc["Cat"].rsqrt()
 
-    def _rmsprop(self, uu, gP, ui, gR, dCat):
+    def _rmsprop(self, uu, gP, ui, gR, dCat):          # sparse / dense forms: recommender_oracle.OracleModel._rmsprop
         lr, rho, eps = self.h.lr, self.h.rms_decay, self.h.rms_eps
-        for name, var, idx, g in (("P", self.P, uu, gP), ("R", self.R, ui, gR),
-                                  ("Cat", self.Cat, torch.arange(4), dCat)):
+        for name, var, idx, g in (("P", self.P, uu, gP), ("R", self.R, ui, gR)):
             ms = self.ms[name]
-            msi = ms[idx] + (g * g - ms[idx]) * (1 - rho)
+            msi = ms[idx] * rho + (g * g) * (1 - rho)
             ms[idx] = msi
-            var[idx] -= lr * g / (msi + eps).sqrt()
+            var[idx] -= ((msi + eps).rsqrt() * lr) * g
+        ms = self.ms["Cat"]
+        ms += (dCat * dCat - ms) * (1 - rho)
+        self.Cat -= (dCat * lr) / (ms + eps).sqrt()
 
     @torch.no_grad()
     def scores(self, users, items, cats):

@@ -271,23 +271,36 @@ class OracleModel:
         return f(f(self.h.lr) * np.sqrt(f(1) - b2p) / (f(1) - b1p))
 
     def _adagrad(self, uu, gP, ui, gR, dCat):
-        lr = self.dt.type(self.h.lr)
+        """TF-1.15 ``core/kernels/training_ops.cc``.  Sparse rows (``SparseApplyAdagradOp``, P and R):
+        ``a += g.square(); v -= g.constant(lr) * g * a.rsqrt()``.  Dense (``ApplyAdagrad<CPUDevice>``, Cat):
+        ``accum += grad.square(); var -= grad * lr() * accum.rsqrt()``.  ``rsqrt`` is restated as the IEEE
+        ``1/sqrt`` (Eigen's vectorised rsqrt is an approximation + Newton step: a few ulp, not restatable)."""
+        f = self.dt.type
+        lr = f(self.h.lr)
         for name, var, idx, g in (("P", self.P, uu, gP), ("R", self.R, ui, gR)):
             acc = self.acc[name]
             acc[idx] += g * g
-            var[idx] -= lr * g / np.sqrt(acc[idx])
+            var[idx] -= (lr * g) * (f(1) / np.sqrt(acc[idx]))
         self.acc["Cat"] += dCat * dCat
-        self.Cat -= lr * dCat / np.sqrt(self.acc["Cat"])
+        self.Cat -= (dCat * lr) * (f(1) / np.sqrt(self.acc["Cat"]))
 
     def _rmsprop(self, uu, gP, ui, gR, dCat):
+        """TF-1.15 ``core/kernels/training_ops.cc``; the sparse and the dense op use DIFFERENT arithmetic forms.
+        Sparse rows (``SparseApplyRMSPropOp``, P and R): ``ms = ms * rho + grad.square() * (1 - rho);
+        mom = mom * momentum + (ms + epsilon).rsqrt() * lr * grad; v -= mom``.
+        Dense (``ApplyRMSProp<CPUDevice>``, Cat): ``ms += (grad.square() - ms) * (1 - rho);
+        mom = mom * momentum + (grad * lr) / (ms + epsilon).sqrt(); var -= mom``.  momentum = 0 (rmsprop.py default)."""
         f = self.dt.type
         lr, rho, eps = f(self.h.lr), f(self.h.rms_decay), f(self.h.rms_eps)
-        for name, var, idx, g in (("P", self.P, uu, gP), ("R", self.R, ui, gR),
-                                  ("Cat", self.Cat, slice(None), dCat)):
+        for name, var, idx, g in (("P", self.P, uu, gP), ("R", self.R, ui, gR)):
             ms, mom = self.ms[name], self.mom[name]
-            ms[idx] += (g * g - ms[idx]) * (f(1) - rho)
-            mom[idx] = mom[idx] * f(0) + lr * g / np.sqrt(ms[idx] + eps)
+            ms[idx] = ms[idx] * rho + (g * g) * (f(1) - rho)
+            mom[idx] = mom[idx] * f(0) + ((f(1) / np.sqrt(ms[idx] + eps)) * lr) * g
             var[idx] -= mom[idx]
+        ms, mom = self.ms["Cat"], self.mom["Cat"]
+        ms += (dCat * dCat - ms) * (f(1) - rho)
+        mom[...] = mom * f(0) + (dCat * lr) / np.sqrt(ms + eps)
+        self.Cat -= mom
 
     # --------------------------------------------------------- Write_Memory
     def _write_memory(self, feed, row_users, items, cats, Ri, n, write_personal):

@@ -56,9 +56,15 @@ def one_run(name):
     D = RUNS[name][7] if len(RUNS[name]) > 7 else 8
     L = RUNS[name][8] if len(RUNS[name]) > 8 else globals()["L"]
     os.environ["FOODREC_TF_STANDIN_DTYPE"] = dt
-    sys.path[:0] = [os.path.join(OUT, "tf1_standin"), REF]
-    import tensorflow as tf
-    assert "tf1_standin" in tf.__file__
+    if os.environ.get("FOODREC_TF_REAL"):        # a box WITH TensorFlow: record its own kernels (tf_real_recorder.py)
+        assert dt == "float32", "real TensorFlow computes the graph in float32: only the float32 runs can be re-recorded"
+        sys.path[:0] = [OUT, REF]
+        import tf_real_recorder
+        tf = tf_real_recorder.install()
+    else:
+        sys.path[:0] = [os.path.join(OUT, "tf1_standin"), REF]
+        import tensorflow as tf
+        assert "tf1_standin" in tf.__file__
 
     rng = np.random.default_rng(20260301)
     # side tables in the reference's json formats; every recipe has >= 1 category and every user >= 1 label
@@ -156,5 +162,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         one_run(sys.argv[1])
     else:
+        real = bool(os.environ.get("FOODREC_TF_REAL"))
         for name in RUNS:       # one process per run: the stand-in keeps module-level graph state, like TF's default graph
+            if real and RUNS[name][5] != "float32":
+                continue
             subprocess.check_call([sys.executable, os.path.abspath(__file__), name])

@@ -380,16 +380,19 @@ class AdagradOptimizer(_Optimizer):
     def _create_slots(self, var):
         self.slots.setdefault(var, torch.full_like(var.value, self.init))
 
-    def _apply_dense(self, g, var, lr):                   # ApplyAdagrad: accum += g*g; var -= lr*g*rsqrt(accum)
+    def _apply_dense(self, g, var, lr):
+        # training_ops.cc ApplyAdagrad<CPUDevice>: accum += grad.square(); var -= grad * lr() * accum.rsqrt()
         acc = self.slots[var]
         acc += g * g
-        var.value -= lr * g / torch.sqrt(acc)
+        var.value -= (g * lr) * (1 / torch.sqrt(acc))
 
-    def _apply_sparse_duplicate_indices(self, g, var, lr):  # dedup, then SparseApplyAdagrad row by row
+    def _apply_sparse_duplicate_indices(self, g, var, lr):
+        # dedup, then training_ops.cc SparseApplyAdagradOp row by row:
+        #   a += g.square(); v -= g.constant(lr) * g * a.rsqrt()
         vals, idx = _dedup(g)
         acc = self.slots[var]
         acc[idx] += vals * vals
-        var.value[idx] -= lr * vals / torch.sqrt(acc[idx])
+        var.value[idx] -= (lr * vals) * (1 / torch.sqrt(acc[idx]))
 
 
 class RMSPropOptimizer(_Optimizer):
@@ -400,21 +403,28 @@ class RMSPropOptimizer(_Optimizer):
     def _create_slots(self, var):                         # rmsprop.py: rms = ones, momentum = zeros
         self.slots.setdefault(var, (torch.ones_like(var.value), torch.zeros_like(var.value)))
 
-    def _rows(self, g, var, lr, idx):
-        # ApplyRMSProp / SparseApplyRMSProp: ms += (g*g - ms)*(1-rho); mom = mom*momentum + lr*g*rsqrt(ms+eps); var -= mom
-        ms, mom = self.slots[var]
-        dt = g.dtype
-        rho, mu, eps = (torch.tensor(x, dtype=dt) for x in (self.decay, self.momentum, self.eps))
-        ms[idx] += (g * g - ms[idx]) * (1 - rho)
-        mom[idx] = mom[idx] * mu + lr * g / torch.sqrt(ms[idx] + eps)
-        var.value[idx] -= mom[idx]
+    def _consts(self, dt):
+        return (torch.tensor(x, dtype=dt) for x in (self.decay, self.momentum, self.eps))
 
     def _apply_dense(self, g, var, lr):
-        self._rows(g, var, lr, slice(None))
+        # training_ops.cc ApplyRMSProp<CPUDevice>: ms += (grad.square() - ms) * (1 - rho);
+        #   mom = mom * momentum + (grad * lr) / (ms + epsilon).sqrt(); var -= mom
+        ms, mom = self.slots[var]
+        rho, mu, eps = self._consts(g.dtype)
+        ms += (g * g - ms) * (1 - rho)
+        mom.copy_(mom * mu + (g * lr) / torch.sqrt(ms + eps))
+        var.value -= mom
 
     def _apply_sparse_duplicate_indices(self, g, var, lr):
+        # dedup, then training_ops.cc SparseApplyRMSPropOp row by row (a different arithmetic form from the dense op):
+        #   ms = ms * rho + grad.square() * (1 - rho);
+        #   mom = mom * momentum + (ms + epsilon).rsqrt() * lr * grad; var -= mom
         vals, idx = _dedup(g)
-        self._rows(vals, var, lr, idx)
+        ms, mom = self.slots[var]
+        rho, mu, eps = self._consts(vals.dtype)
+        ms[idx] = ms[idx] * rho + (vals * vals) * (1 - rho)
+        mom[idx] = mom[idx] * mu + ((1 / torch.sqrt(ms[idx] + eps)) * lr) * vals
+        var.value[idx] -= mom[idx]
 
 
 class AdamOptimizer(_Optimizer):
