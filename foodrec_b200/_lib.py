@@ -8,6 +8,7 @@ import os
 from . import _build
 
 FR_OK = 0
+FR_ERR_ARG, FR_ERR_CUDA, FR_ERR_STATE, FR_ERR_UNSUPPORTED = -1, -2, -3, -4
 FR_SGD, FR_ADAGRAD, FR_RMSPROP, FR_ADAM = 0, 1, 2, 3
 FR_ADAM_DENSE, FR_ADAM_LAZY_EXACT, FR_ADAM_LAZY_SERIES = 0, 1, 2
 FR_POINTWISE, FR_BPR = 0, 1

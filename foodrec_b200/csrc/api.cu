@@ -16,6 +16,24 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   if (cfg->num_users <= 0 || cfg->num_items <= 0 || cfg->num_labels <= 0 || cfg->max_rows <= 0)
     return fail(h, FR_ERR_ARG, "num_users/num_items/num_labels/max_rows must be positive");
   if (cfg->learner < FR_SGD || cfg->learner > FR_ADAM) return fail(h, FR_ERR_ARG, "bad learner %d", cfg->learner);
+  if (cfg->learner == FR_ADAM && cfg->adam_mode == FR_ADAM_LAZY_SERIES) {
+    // The closed-form catch-up keeps SERIES_TERMS terms over a window of SERIES_WINDOW steps; both are sized for
+    // the TF default betas.  For the configured betas: the skipped tail b1^WINDOW must be negligible and the
+    // truncated terms  sum_j b1^j d_j^5 / (1 - d_j),  d_j = 1 - b2^(j/2),  must stay below fp32 round-off of the
+    // leading term  sum_j b1^j -- otherwise rows that sat out many steps would be caught up wrongly, silently.
+    const double b1 = cfg->adam_beta1, b2 = cfg->adam_beta2;
+    if (!(b1 >= 0.0 && b1 < 1.0 && b2 > 0.0 && b2 < 1.0)) return fail(h, FR_ERR_ARG, "adam betas must lie in [0,1) / (0,1)");
+    double lead = 0.0, rem = 0.0, p1 = 1.0;
+    for (int j = 1; j <= SERIES_WINDOW; ++j) {
+      p1 *= b1;
+      const double d = 1.0 - pow(b2, 0.5 * j);
+      lead += p1;
+      rem += p1 * pow(d, SERIES_TERMS) / (1.0 - d);
+    }
+    if (p1 > 1e-12 || (lead > 0.0 && rem / lead > 1e-7))
+      return fail(h, FR_ERR_UNSUPPORTED, "adam_mode LAZY_SERIES does not cover beta1=%g beta2=%g (tail %.1e, truncation %.1e): "
+                  "use FR_ADAM_LAZY_EXACT", b1, b2, p1, lead > 0.0 ? rem / lead : 0.0);
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -35,7 +53,7 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   const size_t DV = h->mc.DV;
   int rc;
 #define A(p, n) if ((rc = dalloc(h, &(p), (n)))) return rc
-  A(h->ukeys, S); A(h->ws_row, S); A(h->g, S); A(h->scores, S); A(h->z, S * DV);
+  A(h->ukeys, S); A(h->users_s, S); A(h->items_s, S); A(h->ws_row, S); A(h->g, S); A(h->scores, S); A(h->z, S * DV);
   if ((rc = alloc_sort(h, h->sortU, S))) return rc;
   if ((rc = alloc_sort(h, h->sortI, S))) return rc;
   if ((rc = alloc_sort(h, h->sortL, E))) return rc;
@@ -190,7 +208,8 @@ extern "C" int fr_fwd_score(fr_handle h, const int32_t* users, const int32_t* it
   if (!cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cats is NULL and no item_cats table");
   Launch l{h->sm_count, (cudaStream_t)s};
   launch_fwd_score(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, items,
-                   (const float4*)(cats ? cats : h->tab.item_cats), cats ? 0 : 1, n, scores, health_of(h), l);
+                   (const float4*)(cats ? cats : h->tab.item_cats), cats ? 0 : 1, n, scores, health_of(h), l,
+                   h->cfg.num_users, h->cfg.num_items);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -205,7 +224,7 @@ extern "C" int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int
   Launch l{h->sm_count, (cudaStream_t)s};
   launch_eval_sampled(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, cand,
                       n_cand, n_users, cand_stride, (const float4*)cand_cats, (const float4*)h->tab.item_cats, K,
-                      topk_ids, gt_rank, scores, health_of(h), l);
+                      topk_ids, gt_rank, scores, health_of(h), l, h->cfg.num_users, h->cfg.num_items);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -278,9 +297,11 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   FR_CUDA(h, cudaMemsetAsync(out + FR_OUT_OVERFLOW, 0, sizeof(float), st));
 
   // 1. row keys, write sign; sort item rows by user and by recipe
-  launch_prep_rows(b->mode, B, b->users, b->labels, b->write_sign, h->ukeys, h->ws_row, l);
+  launch_prep_rows(b->mode, B, b->users, b->items, b->labels, b->write_sign, h->cfg.num_users, h->cfg.num_items, h->ukeys,
+                   h->ws_row, h->users_s, h->items_s, out + FR_OUT_OVERFLOW, l);
+  const int32_t *users = h->users_s, *items = h->items_s;      // range-checked: every kernel below reads these
   SortJob sj[2] = {{&h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), 0},
-                   {&h->sortI, (const uint32_t*)b->items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), 0}};
+                   {&h->sortI, (const uint32_t*)items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), 0}};
   radix_sort_jobs(sj, 2, st, h->sm_count);      // by user and by recipe, sharing their launches
   const int ru = sj[0].result, ri = sj[1].result;
   FR_CHECK_LAUNCH(h);
@@ -295,7 +316,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   // 2. forward, loss, per-slice norms, dCat partials, z stash
   FwdParams fp{};
   fp.P = (const float4*)T.P; fp.R = (const float4*)T.R; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B; fp.Bnorm = (float)B;
-  fp.users = b->users; fp.items = b->items; fp.cats = cats; fp.cats_by_item = cats_by_item;
+  fp.users = users; fp.items = items; fp.cats = cats; fp.cats_by_item = cats_by_item;
   fp.labels = b->labels; fp.a = h->mc.a; fp.oma = h->mc.oma;
   fp.g = h->g; fp.z = h->z; fp.scores = out_scores ? out_scores : h->scores;
   fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
@@ -325,9 +346,9 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     UserPolParams up{};
     up.P = (float4*)T.P; up.s1 = (float4*)T.s1_P; up.s2 = (float4*)T.s2_P; up.last = T.last_P;
     up.R = (const float4*)T.R; up.G = (const float4*)T.G; up.cat = h->cat_pre;
-    up.items = b->items; up.g = h->g; up.cats = cats; up.cats_by_item = cats_by_item;
+    up.items = items; up.g = h->g; up.cats = cats; up.cats_by_item = cats_by_item;
     up.ws_row = h->ws_row; up.out = out; up.group = group; up.mc = h->mc; up.oc = oc;
-    up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = b->users;
+    up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = users;
     launch_user_pass(NV, c, up, l);
     FR_CHECK_LAUNCH(h);
     if (write_personal) {     // Write_Memory :149-198 on the optimizer's output; reads pre-step R, Cat, G
@@ -350,7 +371,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   {
     l.mid = nullptr;
     LabelEmitParams ep{};
-    ep.S = S; ep.group = group; ep.L = h->mc.L; ep.users = b->users;
+    ep.S = S; ep.group = group; ep.L = h->mc.L; ep.users = users;
     ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
     ep.ws_row = h->ws_row; ep.counts = h->counts; ep.offs = h->offs;
     ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
@@ -367,7 +388,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     c.long_list = h->long_list; c.long_count = h->counters + 2; c.long_cap = h->long_cap;
     LabelPolParams lp{};
     lp.G = (float4*)T.G; lp.R = (const float4*)T.R; lp.cat = h->cat_pre;
-    lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = b->items; lp.cats = cats;
+    lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = items; lp.cats = cats;
     lp.cats_by_item = cats_by_item; lp.mc = h->mc;
     launch_label_pass(NV, c, lp, l);
     FR_CHECK_LAUNCH(h);

@@ -22,13 +22,13 @@ static int ws_alloc(fr_ctx* h, T** p, size_t n) {
 static int shard_ensure(fr_ctx* h, size_t S, size_t n) {
   auto& w = h->sh;
   int rc;
+  if (!w.owner_counts && (rc = dalloc(h, &w.owner_counts, 8))) return rc;     // (needed even by a rank with no rows)
+  if (!w.n_valid && (rc = dalloc(h, &w.n_valid, 1))) return rc;
   if (S > w.s_cap) {
     if ((rc = ws_alloc(h, &w.okeys, S)) || (rc = ws_alloc(h, &w.flags, S)) || (rc = ws_alloc(h, &w.excl, S)) ||
         (rc = ws_alloc(h, &w.slot_sorted, S)) || (rc = ws_alloc(h, &w.slot_of_row, S)) ||
         (rc = ws_alloc(h, &w.cats_row, S)))
       return rc;
-    if (!w.owner_counts && (rc = dalloc(h, &w.owner_counts, 8))) return rc;
-    if (!w.n_valid && (rc = dalloc(h, &w.n_valid, 1))) return rc;
     w.s_cap = S;
   }
   if (n > w.n_cap) {
@@ -50,10 +50,14 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   if (!b || !req) return fail(h, FR_ERR_ARG, "null batch/req");
   if (b->mode != FR_POINTWISE && b->mode != FR_BPR) return fail(h, FR_ERR_ARG, "bad mode %d", b->mode);
   const int group = b->mode == FR_BPR ? 2 : 1, B = b->n_groups;
-  if (B <= 0) return fail(h, FR_ERR_ARG, "empty batch");
+  // B == 0 is a first-class case: samples are routed to their user's owner, so with the reference's user-contiguous,
+  // unshuffled instance stream (Train_recommender.py:74-96: up to 250 consecutive rows of ONE user) most ranks own no
+  // row of a 128-row global batch.  Such a rank requests nothing, contributes zeros to the packed all-reduce, and
+  // still serves its peers' requests, applies the replicated Cat / G update and the gradient rows it receives.
+  if (B < 0) return fail(h, FR_ERR_ARG, "negative batch size %d", B);
   if ((int64_t)B * group > h->cfg.max_rows) return fail(h, FR_ERR_ARG, "batch exceeds max_rows=%d", h->cfg.max_rows);
-  if (!b->users || !b->items) return fail(h, FR_ERR_ARG, "users/items are required");
-  if (b->mode == FR_POINTWISE && !b->labels) return fail(h, FR_ERR_ARG, "labels are required in pointwise mode");
+  if (B > 0 && (!b->users || !b->items)) return fail(h, FR_ERR_ARG, "users/items are required");
+  if (B > 0 && b->mode == FR_POINTWISE && !b->labels) return fail(h, FR_ERR_ARG, "labels are required in pointwise mode");
   if (!b->cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cats is NULL and no (global) item_cats table");
   if (!b->user_labels && !(h->tab.user_label_off && h->tab.user_label_idx))
     return fail(h, FR_ERR_ARG, "user_labels is NULL and no user-label CSR table");
@@ -63,7 +67,7 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
   auto& w = h->sh;
-  w.mode = b->mode; w.B = B; w.S = S; w.group = group;
+  w.mode = b->mode; w.B = B; w.S = S; w.group = group; w.planned = true;
   const fr_tables& T = h->tab;
 
   FR_CUDA(h, cudaMemcpyAsync(h->cat_pre, T.Cat, (size_t)4 * h->mc.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -71,11 +75,16 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   FR_CUDA(h, cudaMemsetAsync(w.owner_counts, 0, 8 * sizeof(uint32_t), st));
   FR_CUDA(h, cudaMemsetAsync(req, 0xff, n * sizeof(int32_t), st));
   FR_CUDA(h, cudaMemsetAsync(h->out_internal, 0, FR_OUT_COUNT * sizeof(float), st));
-  launch_prep_rows(b->mode, B, b->users, b->labels, b->write_sign, h->ukeys, h->ws_row, l);
+  if (S == 0) return FR_OK;                       // nothing to request: req stays all -1
+  // users are LOCAL rows, items GLOBAL recipe ids (< W * items_per_rank; ids in the padding of the last shard are
+  // zero rows of their owner): range-checked copies, read by every later phase
+  launch_prep_rows(b->mode, B, b->users, b->items, b->labels, b->write_sign, h->cfg.num_users,
+                   (int64_t)W * sh->items_per_rank, h->ukeys, h->ws_row, h->users_s, h->items_s,
+                   h->out_internal + FR_OUT_OVERFLOW, l);
 
   ShardPlanParams p{};
   p.S = S; p.W = W; p.cap = sh->cap; p.items_per_rank = (uint32_t)sh->items_per_rank;
-  p.items = b->items; p.item_cats = (const float4*)T.item_cats; p.cats_in = (const float4*)b->cats;
+  p.items = h->items_s; p.item_cats = (const float4*)T.item_cats; p.cats_in = (const float4*)b->cats;
   p.okeys = w.okeys; p.cats_row = w.cats_row;
   p.flags = w.flags; p.excl = w.excl; p.owner_counts = w.owner_counts;
   p.req = req; p.slot_of_row = w.slot_of_row; p.slot_sorted = w.slot_sorted; p.out = h->out_internal;
@@ -139,8 +148,12 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   int rc = shard_check(h, sh); if (rc) return rc;
   if (!b || !rbuf || !packed) return fail(h, FR_ERR_ARG, "null argument");
   auto& w = h->sh;
-  if (w.S <= 0 || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_forward");
+  if (!w.planned || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_forward");
   cudaStream_t st = (cudaStream_t)s;
+  if (w.S == 0) {     // a rank without rows adds nothing to {loss, sum|g|^2, dCat, dG}
+    FR_CUDA(h, cudaMemsetAsync(packed, 0, (size_t)fr_shard_packed_len(h) * sizeof(float), st));
+    return FR_OK;
+  }
   Launch l{h->sm_count, st, nullptr};
   const fr_tables& T = h->tab;
   const int DV = h->mc.DV, NV = h->NV, S = w.S, B = w.B;
@@ -150,7 +163,7 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   FwdParams fp{};
   fp.P = (const float4*)T.P; fp.R = (const float4*)rbuf; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B;
   fp.Bnorm = (float)sh->global_batch;
-  fp.users = b->users; fp.items = w.slot_of_row; fp.cats = w.cats_row; fp.cats_by_item = 0;
+  fp.users = h->users_s; fp.items = w.slot_of_row; fp.cats = w.cats_row; fp.cats_by_item = 0;
   fp.labels = b->labels; fp.a = h->mc.a; fp.oma = h->mc.oma;
   fp.g = h->g; fp.z = h->z; fp.scores = h->scores;
   fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
@@ -168,7 +181,7 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   float* dG = packed + 4 + 4 * (size_t)h->mc.D;
   FR_CUDA(h, cudaMemsetAsync(dG, 0, 5 * (size_t)h->mc.L * h->mc.D * sizeof(float), st));
   LabelEmitParams ep{};
-  ep.S = S; ep.group = w.group; ep.L = h->mc.L; ep.users = b->users;
+  ep.S = S; ep.group = w.group; ep.L = h->mc.L; ep.users = h->users_s;
   ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
   ep.ws_row = h->ws_row; ep.counts = h->counts; ep.offs = h->offs;
   ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
@@ -199,7 +212,7 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   if (!b || !rbuf || !packed_reduced) return fail(h, FR_ERR_ARG, "null argument");
   auto& w = h->sh;
   if (!grows && w.peer_rgrows.world != sh->world) return fail(h, FR_ERR_ARG, "grows is NULL but fr_shard_set_peers has not been called for this world");
-  if (w.S <= 0 || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_update");
+  if (!w.planned || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_update");
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
   const fr_tables& T = h->tab;
@@ -235,13 +248,14 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   up.R = (const float4*)rbuf; up.G = (const float4*)T.G; up.cat = h->cat_pre;
   up.items = w.slot_of_row; up.g = h->g; up.cats = w.cats_row; up.cats_by_item = 0;
   up.ws_row = h->ws_row; up.out = out; up.group = w.group; up.mc = h->mc; up.oc = oc;
-  up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = b->users;
+  up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = h->users_s;
   FR_MARK(FR_T_USER_CHUNK);
   l.mid = ts ? ts->ev[FR_T_USER_COMBINE] : nullptr;
-  launch_user_pass(NV, c, up, l);
+  if (S > 0) launch_user_pass(NV, c, up, l);
+  else if (l.mid) cudaEventRecord(l.mid, st);
   l.mid = nullptr;
   FR_MARK(FR_T_LABEL);
-  if (write_personal) {
+  if (write_personal && S > 0) {
     const size_t need = (size_t)S / 32 + 2;
     if (need > h->pieces_personal_chunks) {
       if (h->pieces_personal) { FR_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->pieces_personal); h->pieces_personal = nullptr; }
@@ -264,7 +278,8 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   PeerPtrs none{}; none.world = 0;
   FR_MARK(FR_T_ITEM_CHUNK);
   l.mid = ts ? ts->ev[FR_T_ITEM_COMBINE] : nullptr;
-  launch_item_grad_pass(NV, ci, ip, (float4*)grows, grows ? none : w.peer_rgrows, l);
+  if (S > 0) launch_item_grad_pass(NV, ci, ip, (float4*)grows, grows ? none : w.peer_rgrows, l);
+  else if (l.mid) cudaEventRecord(l.mid, st);
   l.mid = nullptr;
   FR_MARK(FR_T_SWEEP); FR_MARK(FR_T_MISC); FR_MARK(FR_T_COUNT);
 #undef FR_MARK
@@ -278,7 +293,7 @@ extern "C" int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rr
   int rc = shard_check(h, sh); if (rc) return rc;
   if (!rreq || !rgrows) return fail(h, FR_ERR_ARG, "null argument");
   auto& w = h->sh;
-  if (w.S <= 0) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_apply");
+  if (!w.planned) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_apply");
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
   const fr_tables& T = h->tab;
@@ -307,7 +322,7 @@ extern "C" int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rr
               (double)h->mc.L * 5.0 * h->mc.D, l);
   launch_write_counters(h->counters, out, l);
   FR_CHECK_LAUNCH(h);
-  w.S = 0;
+  w.S = 0; w.planned = false;
   h->step = step;
   h->b1p *= h->cfg.adam_beta1;
   h->b2p *= h->cfg.adam_beta2;

@@ -115,13 +115,17 @@ struct UserSrc {
   int row0;               // first query row of this pass
   const uint32_t* perm;   // nullable: pass row -> query row of the pass (users sorted by best mask group)
   HealthBlend hb;         // G != nullptr: rows are scored with the health term (table queries only)
+  uint32_t n_table;       // rows of Personal_Memory when uidx indexes it: an id outside the table reads row 0 (never OOB;
+                          // host lists are range-checked by the Python layer, which raises like tf.gather)
 };
 __device__ __forceinline__ int query_row(const UserSrc& s, int j) {      // index into the caller's user list / outputs
   return s.row0 + (s.perm ? (int)__ldg(s.perm + j) : j);
 }
 __device__ __forceinline__ int user_of(const UserSrc& s, int j) {
   const int qr = query_row(s, j);
-  return s.uidx ? __ldg(s.uidx + qr) : qr;
+  if (!s.uidx) return qr;
+  const int u = __ldg(s.uidx + qr);
+  return (uint32_t)u < s.n_table ? u : 0;
 }
 __device__ __forceinline__ const float4* user_row(const UserSrc& s, int j, int DV) {
   return s.P + (size_t)user_of(s, j) * 5 * DV;
@@ -831,6 +835,8 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
   if (K <= 0 || K > CAT_MAXK) return fail(h, FR_ERR_UNSUPPORTED, "K must be in [1,%d], got %d", CAT_MAXK, K);
   if (n_users == 0) return FR_OK;
   if (P_rows && h->health_blend) return fail(h, FR_ERR_ARG, "the health term needs user ids (labels): pass users, not dense P_rows");
+  if (!P_rows && !users && n_users > h->cfg.num_users)
+    return fail(h, FR_ERR_ARG, "n_users=%d exceeds the %d rows of Personal_Memory", n_users, h->cfg.num_users);
   CatalogWs& w = *h->cat;
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const int CG = w.cta_group, BMC = CAT_BM * CG;
@@ -854,7 +860,8 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
     while (n_split > 1 && (size_t)n_split * m_pad > (size_t)w.mp_cap) --n_split;
     const int n_lists = n_split * NSET;
     const int tps = std::max(1, (w.n_tiles + n_split - 1) / n_split);
-    UserSrc src{reinterpret_cast<const float4*>(P_rows ? P_rows : h->tab.P), P_rows ? nullptr : users, row0, nullptr, health_of(h)};
+    UserSrc src{reinterpret_cast<const float4*>(P_rows ? P_rows : h->tab.P), P_rows ? nullptr : users, row0, nullptr, health_of(h),
+                (uint32_t)h->cfg.num_users};
 
     std::array<cudaEvent_t, 5>* ev = nullptr;
     if (timing) {

@@ -18,6 +18,11 @@
 // re-scored in fp64 from the fp32 tables and ranked by (score desc, id asc).  Rows whose
 // candidate list overflows (massive ties) fall back to an exact full scan.
 #pragma once
+// Per-tile filter bound (default).  -DFR_CAT_GLOBAL_BOUND builds the round-1 filter whose margin uses the largest
+// recipe norm of the WHOLE catalog (kept for A/B runs: foodrec_b200._build.build_variant("globalbound", [...])).
+#if !defined(FR_CAT_GLOBAL_BOUND) && !defined(FR_CAT_TILE_BOUND)
+#define FR_CAT_TILE_BOUND 1
+#endif
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -61,7 +66,6 @@ struct CatGemmParams {
   int32_t* ovf;                // [m_pad] 1 = candidate list overflowed
   unsigned long long* dbg;     // nullable: cycle counters {mma total, wait tempty, wait full, n, epi total, wait tfull, n}
 #ifdef FR_CAT_TILE_BOUND
-  // STAGED FOR ROUND 2, NOT PART OF THE DEFAULT BUILD, NOT YET RUN ON A GPU (build_variant("tilebound", ["FR_CAT_TILE_BOUND"])).
   // Per-tile error bound: E[u,t] = 0.5 * (margin2[u] * tile_rho[t] + margin2r[u]); the lists hold LOWER bounds
   // s_hat - E[u,t] and a recipe is kept iff its upper bound s_hat + E[u,t] reaches the K-th largest lower bound so far
   // (oracle/catalog_filter_model.py states and tests the rule).

@@ -23,7 +23,8 @@ struct fr_ctx {
   std::vector<void*> allocs;
 
   // workspace (device)
-  uint32_t* ukeys = nullptr; float* ws_row = nullptr; float* g = nullptr; float* scores = nullptr;
+  uint32_t* ukeys = nullptr; int32_t *users_s = nullptr, *items_s = nullptr;   // range-checked copies of the step's ids
+  float* ws_row = nullptr; float* g = nullptr; float* scores = nullptr;
   float4* z = nullptr;
   SortBufs sortU, sortI, sortL;
   float *part_loss = nullptr, *part_nrm = nullptr; float4* part_gcat = nullptr; int fwd_grid_cap = 0;
@@ -51,6 +52,7 @@ struct fr_ctx {
     float4* pieces_s = nullptr;
     int ru = 0, ri = 0, rs = 0;            // which sort buffer holds each result
     int mode = 0, B = 0, S = 0, group = 1;
+    bool planned = false;                  // fr_shard_plan has run for the step in flight (S may be 0: a rank that owns no row of the batch)
     fr::PeerPtrs peer_rbuf{}, peer_rgrows{};   // fr_shard_set_peers: NVLink P2P exchange instead of all-to-alls
   } sh;
   bool health_blend = false;        // fr_set_health_blend: inference scores P[u] + alpha * mean G[labels(u)]

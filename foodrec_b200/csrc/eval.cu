@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(FR_THREADS)
 fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, const float4* __restrict__ Cat,
                  int DV, const int32_t* __restrict__ users, const int32_t* __restrict__ items,
                  const float4* __restrict__ cats, int cats_by_item, int n, float a, float oma,
-                 float* __restrict__ scores, const HealthBlend hb) {
+                 float* __restrict__ scores, const HealthBlend hb, uint32_t n_users, uint32_t n_items) {
   extern __shared__ float4 sCat[];
   for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) sCat[i] = Cat[i];
   __syncthreads();
@@ -51,13 +51,18 @@ fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, con
       const int r = blk * RPW + q;
       if (r >= n) break;
       const int u = users[r];
+      const int it = items[r];
+      // an id outside its table (tf.gather raises for it on the CPU): no row is read, the score is NaN
+      if ((uint32_t)u >= n_users || (uint32_t)it >= n_items) {
+        if (lane == 0) scores[r] = __int_as_float(0x7fc00000);
+        continue;
+      }
       if (u != cur_u) {
 #pragma unroll
         for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
         health_blend_rows<NV>(pr, hb, u, DV, lane);
         cur_u = u;
       }
-      const int it = items[r];
       const float4 m = __ldg(cats + (cats_by_item ? it : r));
       const float s = score_pair<NV>(pr, R + (size_t)it * DV, m, sCat, DV, lane, a, oma);
       if (lane == 0) scores[r] = s;
@@ -67,16 +72,17 @@ fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, con
 
 void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                       const int32_t* users, const int32_t* items, const float4* cats,
-                      int cats_by_item, int n, float* scores, const HealthBlend& hb, const Launch& l) {
+                      int cats_by_item, int n, float* scores, const HealthBlend& hb, const Launch& l,
+                      int64_t n_users, int64_t n_items) {
   if (n <= 0) return;
   int grid = (n + 8 * FR_WARPS_PER_BLOCK - 1) / (8 * FR_WARPS_PER_BLOCK);
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   const size_t smem = (size_t)4 * mc.DV * sizeof(float4);
   ++g_launches;
   if (mc.DV <= 32)
-    fwd_score_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb);
+    fwd_score_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb, (uint32_t)n_users, (uint32_t)n_items);
   else
-    fwd_score_kernel<2><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb);
+    fwd_score_kernel<2><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb, (uint32_t)n_users, (uint32_t)n_items);
 }
 
 // One warp per test user.  Candidate j lives in lane j&31, slot j>>5 (<= 128 candidates; SLOTS = 2 covers the
@@ -92,7 +98,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
                     const int32_t* __restrict__ cand, const int32_t* __restrict__ n_cand, int n_users,
                     int stride, const float4* __restrict__ cand_cats, const float4* __restrict__ item_cats,
                     int K, int32_t* __restrict__ topk_ids, int32_t* __restrict__ gt_rank,
-                    float* __restrict__ scores_out, const HealthBlend hb) {
+                    float* __restrict__ scores_out, const HealthBlend hb, uint32_t n_table_users, uint32_t n_items) {
   extern __shared__ float4 smem[];
   float4* sCat = smem;                                              // [4*DV]
   for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) sCat[i] = Cat[i];
@@ -105,18 +111,24 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
     int nc = n_cand[w];
     if (nc > stride) nc = stride;
     if (nc > 32 * SLOTS) nc = 32 * SLOTS;
+    if ((uint32_t)u >= n_table_users) {          // a user id outside Personal_Memory: empty rank list, no row is read
+      for (int k = lane; k < K; k += 32) topk_ids[(size_t)w * K + k] = -1;
+      if (lane == 0) gt_rank[w] = -1;
+      continue;
+    }
     int id[SLOTS]; float sc[SLOTS]; bool alive[SLOTS]; float4 mq[SLOTS];
 #pragma unroll
     for (int q = 0; q < SLOTS; ++q) {
       const int j = q * 32 + lane;
       id[q] = j < nc ? cand[(size_t)w * stride + j] : -1;
-      sc[q] = 0.f; alive[q] = j < nc;
+      if ((uint32_t)id[q] >= n_items) id[q] = -1;      // a candidate outside Recipe_Embedding is dropped (never ranked)
+      sc[q] = 0.f; alive[q] = id[q] >= 0;
     }
 #pragma unroll
     for (int q = 0; q < SLOTS; ++q) {
       const int j = q * 32 + lane;
       mq[q] = make_float4(1.f, 0.f, 0.f, 0.f);
-      if (j < nc) mq[q] = cand_cats ? __ldg(cand_cats + (size_t)w * stride + j) : __ldg(item_cats + id[q]);
+      if (id[q] >= 0) mq[q] = cand_cats ? __ldg(cand_cats + (size_t)w * stride + j) : __ldg(item_cats + id[q]);
     }
     float b0, b1, b2, b3;
     {
@@ -145,7 +157,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
 #pragma unroll
     for (int q = 0; q < SLOTS; q += 2) {
       if (q * 32 >= nc) break;
-      const bool vA = q * 32 + lane < nc, vB = (q + 1) * 32 + lane < nc;
+      const bool vA = id[q] >= 0, vB = id[q + 1] >= 0;
       const float4 mA = mq[q], mB = mq[q + 1];
       const float4* rpA = R + (size_t)(vA ? id[q] : 0) * DV;
       const float4* rpB = R + (size_t)(vB ? id[q + 1] : 0) * DV;
@@ -266,14 +278,15 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
 void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                          const int32_t* users, const int32_t* cand, const int32_t* n_cand, int n_users,
                          int stride, const float4* cand_cats, const float4* item_cats, int K,
-                         int32_t* topk_ids, int32_t* gt_rank, float* scores, const HealthBlend& hb, const Launch& l) {
+                         int32_t* topk_ids, int32_t* gt_rank, float* scores, const HealthBlend& hb, const Launch& l,
+                         int64_t n_table_users, int64_t n_items) {
   if (n_users <= 0) return;
   int grid = (n_users + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   const size_t smem = (size_t)(4 + 5 * FR_WARPS_PER_BLOCK) * mc.DV * sizeof(float4);
   ++g_launches;
 #define FR_EVAL(NVV, SL) eval_sampled_kernel<NVV, SL><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, mc.a, mc.oma, users, cand, \
-    n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb)
+    n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb, (uint32_t)n_table_users, (uint32_t)n_items)
   const bool two = stride <= 64;
   if (mc.DV <= 32) { if (two) FR_EVAL(1, 2); else FR_EVAL(1, 4); }
   else             { if (two) FR_EVAL(2, 2); else FR_EVAL(2, 4); }

@@ -72,8 +72,9 @@ struct LabelEmitParams {
   uint32_t* n_entries; float* out;
 };
 
-void launch_prep_rows(int mode, int B, const int32_t* users, const float* labels, const float* ws_in,
-                      uint32_t* ukeys, float* ws_row, const Launch& l);
+void launch_prep_rows(int mode, int B, const int32_t* users, const int32_t* items, const float* labels, const float* ws_in,
+                      int64_t n_users, int64_t n_items, uint32_t* ukeys, float* ws_row, int32_t* users_s, int32_t* items_s,
+                      float* flag, const Launch& l);
 void launch_fwd_train(int NV, int group, const FwdParams& p, int grid, const Launch& l);
 int fwd_train_grid(int B, int sm_count);
 void launch_finalize(const FinalizeParams& p, const Launch& l);

@@ -11,14 +11,28 @@
 namespace fr {
 
 // ------------------------------------------------------------------ prep
-__global__ void prep_rows_kernel(int mode, int B, const int32_t* __restrict__ users,
+// Also the id range check of the step (the reference's tf.gather raises on the CPU for an id outside its table,
+// Model_Recommender.py:57,63): every later kernel reads users_s / items_s, in which an out-of-range id is replaced
+// by row 0 and FR_OUT_OVERFLOW is set to 3 -- nothing is ever read or written outside a table, and the step's
+// result is reported as invalid (Engine.read_scalars raises) instead of silently corrupting rows.
+__global__ void prep_rows_kernel(int mode, int B, const int32_t* __restrict__ users, const int32_t* __restrict__ items,
                                  const float* __restrict__ labels, const float* __restrict__ ws_in,
-                                 uint32_t* __restrict__ ukeys, float* __restrict__ ws_row) {
+                                 uint32_t n_users, uint32_t n_items,
+                                 uint32_t* __restrict__ ukeys, float* __restrict__ ws_row,
+                                 int32_t* __restrict__ users_s, int32_t* __restrict__ items_s, float* __restrict__ flag) {
   const int group = mode == FR_BPR ? 2 : 1;
   const int S = B * group;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < S; r += gridDim.x * blockDim.x) {
     const int grp = r / group;
-    ukeys[r] = (uint32_t)users[grp];
+    uint32_t u = (uint32_t)users[grp], it = (uint32_t)items[r];
+    if (u >= n_users || it >= n_items) {
+      *flag = 3.f;
+      if (u >= n_users) u = 0;
+      if (it >= n_items) it = 0;
+    }
+    ukeys[r] = u;
+    if (r == grp * group) users_s[grp] = (int32_t)u;
+    items_s[r] = (int32_t)it;
     float w;
     if (ws_in) w = ws_in[r];
     else if (mode == FR_BPR) w = (r & 1) ? -1.f : 1.f;
@@ -27,13 +41,15 @@ __global__ void prep_rows_kernel(int mode, int B, const int32_t* __restrict__ us
   }
 }
 
-void launch_prep_rows(int mode, int B, const int32_t* users, const float* labels, const float* ws_in,
-                      uint32_t* ukeys, float* ws_row, const Launch& l) {
+void launch_prep_rows(int mode, int B, const int32_t* users, const int32_t* items, const float* labels, const float* ws_in,
+                      int64_t n_users, int64_t n_items, uint32_t* ukeys, float* ws_row, int32_t* users_s, int32_t* items_s,
+                      float* flag, const Launch& l) {
   const int S = B * (mode == FR_BPR ? 2 : 1);
   int grid = (S + 255) / 256;
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   if (grid < 1) grid = 1;
-  prep_rows_kernel<<<grid, 256, 0, l.st>>>(mode, B, users, labels, ws_in, ukeys, ws_row);
+  prep_rows_kernel<<<grid, 256, 0, l.st>>>(mode, B, users, items, labels, ws_in, (uint32_t)n_users, (uint32_t)n_items, ukeys,
+                                           ws_row, users_s, items_s, flag);
   ++g_launches;
 }
 

@@ -100,6 +100,8 @@ class Engine:
         elif user_label_csr is not None:   # (offsets [U+1], label ids [nnz]) built by the caller
             off, idx = (np.asarray(x, np.int32) for x in user_label_csr)
             assert off.shape == (self.U + 1,) and off[-1] == idx.shape[0]
+            if idx.size and (idx.min() < 0 or idx.max() >= self.Lb) or (np.diff(off) < 0).any():
+                raise IndexError(f"user-label CSR: label ids must lie in [0, {self.Lb}) and offsets be non-decreasing")
             self.lab_off = torch.as_tensor(off).to(self.device)
             self.lab_idx = torch.as_tensor(idx).to(self.device)
             self.max_labels_per_user = int(np.diff(off).max())
@@ -113,6 +115,14 @@ class Engine:
                           hyper.adam_beta1, hyper.adam_beta2, hyper.adam_eps, hyper.rms_decay, hyper.rms_eps)
         self.handle = C.c_void_p()
         rc = self.lib.fr_create(C.byref(cfg), C.byref(self.handle))
+        if rc == L.FR_ERR_UNSUPPORTED and adam_mode == "lazy":
+            # "lazy" = the fastest exact-to-fp32 scheme: the closed-form catch-up where its truncation bound covers
+            # the configured betas (fr_create checks), else the step-by-step replay (bit-identical to the dense sweep)
+            import warnings
+            warnings.warn("foodrec_b200: " + self.lib.fr_last_error(self.handle).decode() + " -- falling back to lazy_exact")
+            self.lib.fr_destroy(self.handle); self.handle = C.c_void_p()
+            self.adam_mode = cfg.adam_mode = L.FR_ADAM_LAZY_EXACT
+            rc = self.lib.fr_create(C.byref(cfg), C.byref(self.handle))
         if rc != L.FR_OK:
             msg = self.lib.fr_last_error(self.handle).decode() if self.handle else "fr_create failed"
             self.lib.fr_destroy(self.handle); self.handle = None
@@ -161,6 +171,23 @@ class Engine:
             return x.to(self.device, torch.int32).contiguous().reshape(-1)
         return torch.as_tensor(np.ascontiguousarray(np.asarray(x).astype(np.int32)).reshape(-1)).to(self.device)
 
+    def _check_ids(self, x, n, what):
+        """Host-side range check of ids that arrive as host data (lists / numpy / CPU tensors): the reference's
+        tf.gather raises for an id outside its table.  Device tensors are checked on the device by the kernels
+        (train step: FR_OUT_OVERFLOW = 3 -> read_scalars raises; inference: NaN score / empty rank list)."""
+        if torch.is_tensor(x):
+            if x.is_cuda or x.numel() == 0:
+                return
+            lo, hi = int(x.min()), int(x.max())
+        else:
+            a = np.asarray(x)
+            if a.size == 0:
+                return
+            a = a.astype(np.int64)
+            lo, hi = int(a.min()), int(a.max())
+        if lo < 0 or hi >= n:
+            raise IndexError(f"{what}: ids must lie in [0, {n}), got [{lo}, {hi}]")
+
     def _f32(self, x, shape=None):
         if x is None:
             return None
@@ -177,19 +204,37 @@ class Engine:
         """One optimizer step on device-resident (or host, copied here) feed tensors.
         Pointwise when ``neg_items`` is None, else BPR.  Returns the device scalar
         vector (FR_OUT_*); nothing is synchronised."""
+        self._check_ids(users, self.U, "user_input"); self._check_ids(items, self.I, "item_input")
         u = self._i32(users)
         B = u.numel()
         bpr = neg_items is not None
         if bpr:
+            self._check_ids(neg_items, self.I, "neg_item_input")
             it = torch.stack([self._i32(items), self._i32(neg_items)], 1).reshape(-1).contiguous()
             cats = None
             if categories is not None:
+                if neg_categories is None:
+                    raise ValueError("BPR step: `categories` was given without `neg_categories` (pass both, or neither "
+                                     "to use the resident dish_to_category table)")
                 cats = torch.stack([self._f32(categories, (B, 4)), self._f32(neg_categories, (B, 4))], 1).reshape(-1, 4).contiguous()
         else:
             it = self._i32(items)
             cats = self._f32(categories, (B, 4))
-        return self._step_dev(L.FR_BPR if bpr else L.FR_POINTWISE, B, u, it, cats, self._f32(labels, (-1,)),
-                              self._f32(write_sign, (-1,)), self._f32(user_one_hot_label, (B, self.Lb)),
+        S = it.numel()
+        ws = self._f32(write_sign, (-1,))
+        if ws is not None and ws.numel() != S:
+            if bpr and ws.numel() == B:
+                # one sign per TRIPLE: the C ABI wants one per item row (S = 2B, interleaved pos/neg); the sign of a
+                # triple applies to its positive row and is negated for its negative row (the +1/-1 default pattern)
+                ws = torch.stack([ws, -ws], 1).reshape(-1).contiguous()
+            else:
+                raise ValueError(f"write_sign has {ws.numel()} entries; the step has {S} item rows"
+                                 + (f" ({B} triples)" if bpr else ""))
+        lab = self._f32(labels, (-1,))
+        if not bpr and (lab is None or lab.numel() != B):
+            raise ValueError(f"labels must have one entry per row ({B})")
+        return self._step_dev(L.FR_BPR if bpr else L.FR_POINTWISE, B, u, it, cats, lab,
+                              ws, self._f32(user_one_hot_label, (B, self.Lb)),
                               write_personal, return_scores)
 
     def _step_dev(self, mode, B, users, items, cats, labels, ws, ulab, write_personal=False, return_scores=False):
@@ -226,6 +271,9 @@ class Engine:
 
     def read_scalars(self):
         v = self.out.cpu().numpy()       # synchronises
+        if v[L.FR_OUT_OVERFLOW] == 3:
+            raise IndexError("train step: a user or recipe id of the batch lies outside its table (tf.gather would "
+                             "raise); the offending rows were redirected to row 0, the step's results are invalid")
         if v[L.FR_OUT_OVERFLOW] == 2:
             raise L.FoodRecError("row-sharded step: a rank needed more distinct recipes from one owner than "
                                  "fr_shard.cap; raise ShardedEngine(cap=...)")
@@ -257,6 +305,7 @@ class Engine:
 
     def score(self, users, items, categories=None):
         self.flush()
+        self._check_ids(users, self.U, "user_input"); self._check_ids(items, self.I, "item_input")
         u, it = self._i32(users), self._i32(items)
         cats = self._f32(categories, (u.numel(), 4))
         out = torch.empty(u.numel(), dtype=torch.float32, device=self.device)
@@ -266,6 +315,7 @@ class Engine:
 
     def eval_sampled_topk(self, users, cand, n_cand, K, cand_cats=None, return_scores=False):
         self.flush()
+        self._check_ids(users, self.U, "test users"); self._check_ids(cand, self.I, "candidates")
         u = self._i32(users)
         n = u.numel()
         cand = torch.as_tensor(np.asarray(cand, np.int32)) if not torch.is_tensor(cand) else cand
@@ -319,6 +369,7 @@ class Engine:
             pr = self._f32(P_rows, (-1, 5, self.D))
             n = pr.shape[0]
         elif users is not None:
+            self._check_ids(users, self.U, "catalog_topk users")
             u = self._i32(users)
             n = u.numel()
         else:
@@ -427,3 +478,9 @@ class Engine:
         self.last_P.fill_(step); self.last_R.fill_(step)
         L.check(self.handle, self.lib.fr_set_step(self.handle, step))
         self._dirty = False
+        self._catalog_ready = False      # the catalog index (bf16 operand, norms, filter bound) was built from the OLD R
+
+    def tables_modified(self):
+        """Call after writing P / R / Cat / G (the tensors this engine holds: ``adopt=True`` shares them with the
+        caller) outside train_step / load_state_dict: derived state (the catalog index) is rebuilt on next use."""
+        self._catalog_ready = False

@@ -47,6 +47,30 @@ def test_fr_create_fails_loudly_without_gpu(built_lib):
     lib.fr_destroy(h)
 
 
+def test_fr_create_rejects_betas_the_series_catchup_does_not_cover(built_lib):
+    """LAZY_SERIES keeps 5 terms over a 2048-step window, sized for the TF default betas.  fr_create must refuse
+    betas for which the truncated terms / the skipped tail are not below fp32 round-off (checked before any device
+    work, so this runs without a GPU) instead of catching rows up wrongly."""
+    from foodrec_b200 import _lib as L
+    lib = L.lib()
+
+    def create(b1, b2, mode):
+        cfg = L.fr_config(64, 10, 10, 5, L.FR_ADAM, mode, 128, 1024, 1e-3, 0.99, 0.01, 0.01, 0.01, 5.0,
+                          b1, b2, 1e-8, 0.9, 1e-10)
+        h = ctypes.c_void_p()
+        rc = lib.fr_create(ctypes.byref(cfg), ctypes.byref(h))
+        msg = lib.fr_last_error(h)
+        lib.fr_destroy(h)
+        return rc, msg
+    rc, msg = create(0.999, 0.999, L.FR_ADAM_LAZY_SERIES)          # b1^2048 = 0.13: the window does not cover the tail
+    assert rc == L.FR_ERR_UNSUPPORTED and b"LAZY_EXACT" in msg, (rc, msg)
+    rc, msg = create(0.9, 0.9, L.FR_ADAM_LAZY_SERIES)              # fast v decay: 5 terms do not converge
+    assert rc == L.FR_ERR_UNSUPPORTED, (rc, msg)
+    for mode in (L.FR_ADAM_LAZY_EXACT, L.FR_ADAM_DENSE):           # the replay modes take any betas
+        assert create(0.999, 0.999, mode)[0] != L.FR_ERR_UNSUPPORTED
+    assert create(0.9, 0.999, L.FR_ADAM_LAZY_SERIES)[0] != L.FR_ERR_UNSUPPORTED     # TF defaults: covered
+
+
 def test_model_needs_gpu_no_fallback(built_lib):
     import torch
     if torch.cuda.is_available():

@@ -181,6 +181,55 @@ def test_catalog_follows_training():
     e.close()
 
 
+def test_catalog_survives_a_thousand_training_steps_without_fallback():
+    """cfg2 tables (1M users x 200k recipes, D=128) trained for 1,000 Zipf BPR steps with Adam: the hottest recipes'
+    norms grow ~10x, which inflated the round-1 filter's GLOBAL margin (largest recipe norm of the catalog) until
+    candidate lists overflowed and rows took the exact fallback (DESIGN.md, round-1 limitation).  With the per-tile
+    bound a heavy recipe only widens the margin of its own tile: ids stay exact (checked against the oracle for a
+    sample of users) and no row of the whole 1M-user query falls back."""
+    from foodrec_b200 import Engine, Hyper, _lib as L
+    U, I, Lb, D, B, K = 1_000_000, 200_000, 95, 128, 262_144, 100
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    P = torch.randn((U, 5, D), generator=g, device=dev) * 0.1
+    R = torch.randn((I, D), generator=g, device=dev) * 0.1
+    Cat = torch.randn((4, D), generator=g, device=dev) * 0.1
+    G = torch.randn((Lb, 5, D), generator=g, device=dev) * 0.1
+    ic = synth.make_item_categories(I)
+    e = Engine(Hyper(learner="adam", lr=0.001), P, R, Cat, G, device=dev, max_rows=2 * B, item_cats=ic,
+               user_label_csr=synth.make_user_label_csr(U, Lb), adopt=True)
+    r0 = float(e.R.norm(dim=1).max())
+    batches = []
+    for k in range(8):
+        rng = np.random.default_rng(900 + k)
+        users = rng.integers(0, U, B).astype(np.int32)
+        pos = synth.zipf_items(rng, I, B)
+        neg = rng.integers(0, I, B).astype(np.int32); neg[neg == pos] = (neg[neg == pos] + 1) % I
+        batches.append((torch.as_tensor(users).to(dev), torch.as_tensor(np.stack([pos, neg], 1).reshape(-1).copy()).to(dev)))
+    for s in range(1000):
+        u, it = batches[s % 8]
+        e._step_dev(L.FR_BPR, B, u, it, None, None, None, None)
+    e.read_scalars()
+    e.flush()
+    r1 = float(e.R.norm(dim=1).max())
+    assert r1 > 3 * r0, (r0, r1)                       # the stream did grow a heavy recipe
+    e.timing_enable(True)
+    ids, sc = e.catalog_topk(n_users=U, K=K)
+    torch.cuda.synchronize()
+    assert e.catalog_fallback_rows() == 0
+    ph, passes = e.catalog_timing_read()
+    assert ph["exact_fallback"] < 0.25 * ph["gemm_filter"], ph
+    rng = np.random.default_rng(1)
+    sample = np.sort(rng.choice(U, 192, replace=False))
+    ts = torch.as_tensor(sample).to(dev)
+    om = OracleModel(e.P[ts].cpu().numpy(), e.R.cpu().numpy(), e.Cat.cpu().numpy(), e.G.cpu().numpy(), OHyper(), dtype=np.float32)
+    rid, rsc = evaluate_oracle.catalog_topk(om, np.arange(len(sample)), ic, K)
+    got_i, got_s = ids[ts].cpu().numpy(), sc[ts].cpu().numpy()
+    assert np.array_equal(got_i, rid), f"{int((got_i != rid).sum())} ids differ"
+    assert np.abs(got_s - rsc).max() <= 1e-12 * np.abs(rsc).max()
+    e.close()
+
+
 def test_catalog_cfg2_properties():
     """cfg2 width and catalog size (200k recipes, D=128, K=100) on 4096 users: sortedness, agreement
     with the inference kernel on the returned pairs, and completeness against a float64 full scan

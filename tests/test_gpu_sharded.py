@@ -84,6 +84,39 @@ def test_sharded_equals_unsharded(W, learner, adam_mode, bpr):
         assert_close(ts[k], tr[k], rtol=rt, what=f"W={W} {learner}/{adam_mode} {k}")
 
 
+@pytest.mark.parametrize("learner,adam_mode", [("adam", "lazy"), ("rmsprop", "dense"), ("sgd", "dense")])
+def test_rank_without_rows_is_a_first_class_case(learner, adam_mode):
+    """The reference's instance stream is user-contiguous and never shuffled (Train_recommender.py:74-96): a
+    128-row batch holds one or two users, so with samples routed to the user owner most ranks own NO row of a
+    step.  Such a rank must still walk the five phases (serve its peers, take the all-reduced Cat / G update,
+    apply the gradient rows it receives); results equal the unsharded engine."""
+    W = 4
+    p = Problem(203, 157, 9, 64, seed=71)
+    single, engs = build(p, W, learner, adam_mode)
+    run = sharded.LocalRunner(engs)
+    for s in range(4):
+        B = 128
+        base = 4 * (3 + s) + (s % W)                     # one or two users per batch, like the reference stream
+        users = np.where(np.arange(B) < 100, base, base + W * (s % 2)).astype(np.int32)
+        f = p.pointwise(B, seed=700 + s, users=users)
+        single.train_step(f["user_input"], f["item_input"], labels=f["labels"], categories=f["categories"],
+                          user_one_hot_label=f["user_one_hot_label"], write_personal=(s == 0))
+        v1 = single.read_scalars().copy()
+        idx = sharded.route_batch(f["user_input"], W)
+        assert sum(len(ix) == 0 for ix in idx) >= W - 2
+        for r, g in enumerate(engs):
+            ix = idx[r]
+            g.set_batch(f["user_input"][ix] // W, f["item_input"][ix], labels=f["labels"][ix], global_batch=B)
+        outs = run.step(write_personal=(s == 0))
+        for o in outs:
+            v = o.cpu().numpy()
+            assert v[9] == 0
+            assert v[0] == pytest.approx(v1[0], rel=1e-5) and v[1] == pytest.approx(v1[1], rel=1e-5)
+    ts, tr = gather(engs, p), single.tables()
+    for k in ("P", "R", "Cat", "G"):
+        assert_close(ts[k], tr[k], rtol=1e-5 if learner != "adam" else 1e-4, what=f"{learner} {k}")
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
 def test_nccl_sharded_equals_unsharded():
     """The same comparison across real processes: torchrun x2, NCCL all-to-all / all-reduce."""

@@ -97,13 +97,26 @@ def test_oracle_reproduces_the_reference_program(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", [n for n in TRACES if not n.endswith("_f64")])
+@pytest.mark.parametrize("name", TRACES)
 def test_dropin_session_reproduces_the_reference_program(name):
     """The same ``sess.run`` calls, in the same order with the same fetch lists, through the drop-in
     ``Model`` / ``Session`` and the CUDA kernels; 1e-5 relative (north_star) on losses, logits and the
-    tables the program ends with."""
+    tables the program ends with.  Every trace is replayed, including the ones recorded with the stand-in in
+    float64 (the reference's default shapes -- 95 labels, embed_size 200, batch 128 -- and the non-default
+    hyper-parameters): there the recorded values are the float64 ground truth of the graph and the CUDA path
+    (float32) is judged against them directly."""
     import foodrec_b200 as fb
+    from tests.util import assert_close_adam
     t = load(name)
+    wide = str(t["dtype"]) == "float64"
+    # Adam against a float64 trace: ill-conditioned entries (|summed gradient| ~ eps/sqrt(1-beta2)) are excused only
+    # where the float32 numpy oracle, replayed alongside, is itself off by a comparable amount (tests/util.py)
+    om32 = None
+    if wide and str(t["learner"]) == "adam":
+        a_, b1_, b2_, al_ = (float(x) for x in t["hyper"])
+        om32 = OracleModel(t["P0"], t["R0"], t["Cat0"], t["G0"],
+                           OHyper(learner="adam", lr=float(t["lr"]), high_level_score_coefficient=a_, beta_1=b1_, beta_2=b2_,
+                                  alpha=al_), dtype=np.float32)
     B = int(np.diff(t["off"]).max())
     a, b1, b2, al = (float(x) for x in t["hyper"])
     args = types.SimpleNamespace(learner=str(t["learner"]), num_categories=4, num_users=t["P0"].shape[0],
@@ -123,6 +136,8 @@ def test_dropin_session_reproduces_the_reference_program(name):
             continue
         fd[model.user_one_hot_label] = feed["user_one_hot_label"].tolist()
         fd[model.write_sign] = feed["write_sign"].tolist()
+        if om32 is not None:
+            om32.train_step(feed, write_personal=kind == 1)
         if kind == 1:
             loss, lr, personal, general, _ = sess.run([model.loss_value, model.learning_rate, model.personal, model.general,
                                                        model.train_op], fd)
@@ -131,12 +146,15 @@ def test_dropin_session_reproduces_the_reference_program(name):
         else:
             loss, lr, general, _ = sess.run([model.loss_value, model.learning_rate, model.general, model.train_op], fd)
         assert_close(loss, out["loss"], what=f"{name} run {r} loss")
-        assert float(lr) == float(out["lr"])
+        assert float(lr) == float(np.float32(out["lr"]))
         assert abs(float(general) - out["general"]) <= 1e-5 * np.abs(t["G1"]).mean()
     assert sess.run(model.epoch_step) == 0          # the replay does not call epoch_increment
     tabs = model.engine.tables()
     for k in ("P", "R", "Cat", "G"):
-        assert_close(tabs[k], t[k + "1"], what=f"{name} final {k}")
+        if om32 is not None and k != "G":
+            assert_close_adam(tabs[k], t[k + "1"], getattr(om32, k), what=f"{name} final {k}")
+        else:
+            assert_close(tabs[k], t[k + "1"], what=f"{name} final {k}")
     # evaluate_model (evaluate.py:13) on the tables the replay ended with: the reference's own per-user lists
     from foodrec_b200.data import Dataset
     d = Dataset(os.path.join(GOLD, "ref_dataset", "toy"))
