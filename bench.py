@@ -539,9 +539,20 @@ def run_ours(args, cfg, B):
         "user_chunk": uniq_users * adam_k * 20 * D,
         "item_chunk": uniq_items * adam_k * 4 * D,
     }
+    fused = bool(getattr(eng, "single_pass", False)) and not os.environ.get("FOODREC_TWO_PASS")
+    if fused:
+        # single-pass step: ONE kernel scores and updates (phase "fwd"; "user_chunk" is the 2 MB commit pass).  Its
+        # compulsory bytes: P, m, v read + written once per unique user, the two recipe rows, ids and the two z-stash
+        # rows per triple.  SURVEY 8(d) counts the P row once more per triple (its forward figure, 28D+16) on top of
+        # the update figure: that sum is reported as survey_alg_bytes, the roofline uses the smaller compulsory figure.
+        alg["fwd"] = uniq_users * adam_k * 20 * D + B * (2 * 4 * D + 16) + B * 2 * 4 * D
+        alg.pop("user_chunk")
     kern = {k: {"ms": phases[k], "alg_bytes": alg[k], "gbs": alg[k] / (phases[k] * 1e-3) / 1e9 if phases[k] > 0 else None}
             for k in alg}
-    if args.learner.lower() == "adam" and args.adam_mode != "dense":
+    if fused:
+        kern["fwd"]["survey_alg_bytes"] = B * (28 * D + 16) + uniq_users * adam_k * 20 * D
+        kern["fwd"]["gbs_survey"] = kern["fwd"]["survey_alg_bytes"] / (phases["fwd"] * 1e-3) / 1e9
+    if args.learner.lower() == "adam" and args.adam_mode != "dense" and not fused:
         # lazy Adam: a user row that was not touched last step is caught up IN REGISTERS before it is scored, which
         # needs its m and v rows too (2 x 20D more bytes per triple; at cfg2 practically every row is stale).  Those
         # reads are compulsory for TF-1.x-exact results without the dense sweep, but are not in SURVEY 8(d)'s figure.
@@ -549,7 +560,7 @@ def run_ours(args, cfg, B):
         kern["fwd"].update(bytes_incl_adam_state=full, gbs_incl_adam_state=full / (phases["fwd"] * 1e-3) / 1e9,
                            )
     dom = max(alg, key=lambda k: phases[k])
-    roofline = {"bound": "hbm", "kernel": {"fwd": "fwd_train_kernel", "user_chunk": "seg_chunk_kernel<UserPol>",
+    roofline = {"bound": "hbm", "kernel": {"fwd": "user_fused_kernel" if fused else "fwd_train_kernel", "user_chunk": "seg_chunk_kernel<UserPol>",
                                            "item_chunk": "seg_chunk_kernel<ItemPol>"}[dom],
                 "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
                 "peak_source": peak_src, "traffic": None,
@@ -698,7 +709,7 @@ def run_ours(args, cfg, B):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(cfg, B), "batch_triples": B, "optimizer": (f"adam (TF-1.x semantics, {args.adam_mode})" if args.learner.lower() == "adam" else args.learner),
                        "l2": "per-step working set (~%.1f GB of table rows) >> 126 MB L2; %d distinct batches cycled" % (
-                           (alg["fwd"] + alg["user_chunk"] + alg["item_chunk"]) / 1e9, NB),
+                           sum(alg.values()) / 1e9, NB),
                        "preroll_steps": preroll,
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (sharded path: see DESIGN.md)"},
             "clocks": clk, "gpu_launches": int(launches),

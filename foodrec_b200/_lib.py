@@ -65,6 +65,7 @@ _PROTOS = {
     "fr_destroy": (C.c_int, [C.c_void_p]),
     "fr_last_error": (C.c_char_p, [C.c_void_p]),
     "fr_set_tables": (C.c_int, [C.c_void_p, C.POINTER(fr_tables)]),
+    "fr_set_shadow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_get_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "fr_set_step": (C.c_int, [C.c_void_p, C.c_int64]),
     "fr_set_health_blend": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -42,6 +42,9 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   cudaDeviceProp prop;
   FR_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
   h->sm_count = prop.multiProcessorCount;
+  h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+  h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+  if (getenv("FOODREC_NO_L2_PIN")) h->l2_persist_max = 0;
   h->mc.D = D; h->mc.DV = D / 4; h->mc.L = cfg->num_labels;
   h->mc.a = cfg->high_level_score_coefficient;
   h->mc.oma = 1.0f - cfg->high_level_score_coefficient;     // fp32 (1 - a), Model_Recommender.py:96
@@ -67,6 +70,7 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   A(h->counts, S + 1); A(h->offs, S + 1); A(h->ent_key, E); A(h->ent_row, E); A(h->ent_coef, E); A(h->n_entries, 1);
   A(h->counters, 4); A(h->cat_pre, 4 * DV); A(h->mean_partials, 1024); A(h->out_internal, FR_OUT_COUNT);
   A(h->scan_tmp, S / 4096 + 2);
+  A(h->label_partial, (size_t)h->sm_count * cfg->num_labels * 5 * DV);
   h->lr_hist_cap = 1 << 16;
   A(h->lr_hist, (size_t)h->lr_hist_cap);
   A(h->cser, (size_t)h->lr_hist_cap * SERIES_TERMS);
@@ -78,6 +82,35 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
 }
 
 extern "C" int64_t fr_launch_count(void) { return (int64_t)fr::g_launches; }
+
+// A table that every work item of a kernel re-reads at random (Recipe_Embedding in sampled evaluation: 51 rows per
+// user) must stay in L2 while a much larger read-once stream (the user rows) passes through it.  Evict-first hints on
+// the stream were not enough (ncu, round 1: 12 GB of DRAM reads for 2.8 GB compulsory, the 102 MB table kept being
+// evicted); a persisting access-policy window on the table is: hits in the window are marked persisting, everything
+// else is streaming.  If the table is larger than the persisting carve-out, hitRatio pins that fraction of it.
+void l2_pin(fr_ctx* h, const void* ptr, size_t bytes, cudaStream_t st) {
+  if (!h->l2_persist_max || !h->l2_window_max || !bytes) return;
+  static bool limit_set = false;
+  if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max); limit_set = true; }
+  cudaStreamAttrValue a{};
+  const size_t win = bytes < h->l2_window_max ? bytes : h->l2_window_max;
+  a.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+  a.accessPolicyWindow.num_bytes = win;
+  const double r = (double)h->l2_persist_max / (double)win;
+  a.accessPolicyWindow.hitRatio = r >= 1.0 ? 1.0f : (float)r;
+  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) == cudaSuccess) h->l2_window_set = true;
+  else cudaGetLastError();
+}
+void l2_unpin(fr_ctx* h, cudaStream_t st) {
+  if (!h->l2_window_set) return;
+  cudaStreamAttrValue a{};
+  a.accessPolicyWindow.num_bytes = 0;                       // kernels queued from here on run without a window
+  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+  cudaGetLastError();
+  h->l2_window_set = false;
+}
 
 extern "C" int fr_timing_enable(fr_handle h, int32_t enable) {
   if (!h) return FR_ERR_ARG;
@@ -127,6 +160,34 @@ extern "C" int fr_set_tables(fr_handle h, const fr_tables* t) {
   if (al & 15) return fail(h, FR_ERR_ARG, "table pointers must be 16-byte aligned");
   h->tab = *t;
   h->has_tables = true;
+  return FR_OK;
+}
+
+extern "C" int fr_set_shadow(fr_handle h, float* P_alt, float* s1_alt, float* s2_alt) {
+  if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (!P_alt && !s1_alt && !s2_alt) {             // switch the single-pass step off again
+    int rc = shadow_sync(h, 0); if (rc) return rc;
+    FR_CUDA(h, cudaDeviceSynchronize());
+    h->shP = h->shM = h->shV = nullptr;
+    return FR_OK;
+  }
+  if (h->cfg.learner != FR_ADAM || h->cfg.adam_mode == FR_ADAM_DENSE)
+    return fail(h, FR_ERR_UNSUPPORTED, "the single-pass step exists for lazy Adam only (FR_ADAM with FR_ADAM_LAZY_*)");
+  if (!P_alt || !s1_alt || !s2_alt) return fail(h, FR_ERR_ARG, "all three shadow tables are required");
+  if (((uintptr_t)P_alt | (uintptr_t)s1_alt | (uintptr_t)s2_alt) & 15) return fail(h, FR_ERR_ARG, "shadow tables must be 16-byte aligned");
+  if ((int64_t)h->cfg.num_users >= (int64_t)FR_SHADOW_BIT) return fail(h, FR_ERR_UNSUPPORTED, "too many rows");
+  h->shP = P_alt; h->shM = s1_alt; h->shV = s2_alt;
+  return FR_OK;
+}
+
+int shadow_sync(fr_ctx* h, cudaStream_t st) {
+  if (!h->shadow_dirty || !h->shP) return FR_OK;
+  Launch l{h->sm_count, st, nullptr};
+  launch_shadow_consolidate(h->tab.last_P, h->cfg.num_users, 5 * h->mc.DV, (float4*)h->tab.P, (float4*)h->tab.s1_P,
+                            (float4*)h->tab.s2_P, (const float4*)h->shP, (const float4*)h->shM, (const float4*)h->shV,
+                            nullptr, l);
+  FR_CHECK_LAUNCH(h);
+  h->shadow_dirty = false;
   return FR_OK;
 }
 
@@ -206,6 +267,7 @@ extern "C" int fr_fwd_score(fr_handle h, const int32_t* users, const int32_t* it
   if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
   if (n < 0 || (n > 0 && (!users || !items || !scores))) return fail(h, FR_ERR_ARG, "null batch pointer");
   if (!cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cats is NULL and no item_cats table");
+  { int rc = shadow_sync(h, (cudaStream_t)s); if (rc) return rc; }
   Launch l{h->sm_count, (cudaStream_t)s};
   launch_fwd_score(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, items,
                    (const float4*)(cats ? cats : h->tab.item_cats), cats ? 0 : 1, n, scores, health_of(h), l,
@@ -221,10 +283,15 @@ extern "C" int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int
   if (n_users < 0 || cand_stride <= 0 || cand_stride > 128 || K <= 0) return fail(h, FR_ERR_ARG, "need 0<cand_stride<=128, K>0");
   if (n_users > 0 && (!users || !cand || !n_cand || !topk_ids || !gt_rank)) return fail(h, FR_ERR_ARG, "null pointer");
   if (!cand_cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cand_cats is NULL and no item_cats table");
+  { int rc = shadow_sync(h, (cudaStream_t)s); if (rc) return rc; }
   Launch l{h->sm_count, (cudaStream_t)s};
+  l2_pin(h, h->tab.R, (size_t)h->cfg.num_items * h->mc.D * sizeof(float), l.st);
   launch_eval_sampled(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, cand,
                       n_cand, n_users, cand_stride, (const float4*)cand_cats, (const float4*)h->tab.item_cats, K,
                       topk_ids, gt_rank, scores, health_of(h), l, h->cfg.num_users, h->cfg.num_items);
+  l2_unpin(h, l.st);       // (the window travels with the launch; lines it marked persisting age out under later windows /
+                           //  are demoted by cudaCtxResetPersistingL2Cache in fr_train_step)
+  h->l2_lines_pinned = true;
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -244,6 +311,7 @@ extern "C" int fr_sort_pairs(fr_handle h, const uint32_t* keys, int32_t n, int32
 
 extern "C" int fr_adam_flush(fr_handle h, fr_stream s) {
   if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  { int rc = shadow_sync(h, (cudaStream_t)s); if (rc) return rc; }
   if (h->cfg.learner != FR_ADAM || h->step == 0) return FR_OK;
   Launch l{h->sm_count, (cudaStream_t)s};
   const OptConsts oc = make_oc(h, h->step);
@@ -273,6 +341,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   if (!b->user_labels && !(h->tab.user_label_off && h->tab.user_label_idx))
     return fail(h, FR_ERR_ARG, "user_labels is NULL and no user-label CSR table");
   cudaStream_t st = (cudaStream_t)s;
+  if (h->l2_lines_pinned) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); h->l2_lines_pinned = false; }
   Launch l{h->sm_count, st, nullptr};
   const fr_tables& T = h->tab;
   const int DV = h->mc.DV, NV = h->NV;
@@ -306,6 +375,10 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   const int ru = sj[0].result, ri = sj[1].result;
   FR_CHECK_LAUNCH(h);
   const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
+  // single-pass step: forward + Personal_Memory update in one kernel on the double-buffered table (train_seg.cu).
+  // Personal-write steps (16 per run of the reference, Train_recommender.py:169-187) take the two-pass path.
+  const bool fused = lazy && h->shP && !write_personal && !getenv("FOODREC_TWO_PASS");
+  if (!fused) { rc = shadow_sync(h, st); if (rc) return rc; }
   if (lazy) {   // recipe rows of this batch must be current before anything reads them
     launch_item_catchup(NV, h->sortI.k[ri], (uint32_t)S, (float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R,
                         T.last_R, DV, oc, l);
@@ -313,6 +386,27 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   }
 
   FR_MARK(FR_T_FWD);
+  int fgrid;
+  SegCommon cu{};
+  cu.keys = h->sortU.k[ru]; cu.perm = h->sortU.v[ru]; cu.n_dev = nullptr; cu.n_host = (uint32_t)S;
+  cu.uniq_counter = h->counters + 0; cu.pieces = h->pieces_u;
+  if (fused) {
+    // 2'. forward + loss + norms + dCat partials + z stash + segment reduce + Adam (clip scale speculated = 1), new rows
+    //     into the other copy of the double-buffered Personal_Memory
+    FusedParams fz{};
+    fz.P[0] = (float4*)T.P; fz.m[0] = (float4*)T.s1_P; fz.v[0] = (float4*)T.s2_P;
+    fz.P[1] = (float4*)h->shP; fz.m[1] = (float4*)h->shM; fz.v[1] = (float4*)h->shV;
+    fz.last = T.last_P; fz.R = (const float4*)T.R; fz.cat = h->cat_pre;
+    fz.items = items; fz.cats = cats; fz.cats_by_item = cats_by_item; fz.labels = b->labels;
+    fz.a = h->mc.a; fz.oma = h->mc.oma; fz.Bnorm = (float)B;
+    fz.g = h->g; fz.z = h->z; fz.scores = out_scores ? out_scores : h->scores;
+    fz.part_loss = h->part_loss; fz.part_nrm = h->part_nrm; fz.part_gcat = h->part_gcat;
+    fz.mc = h->mc; fz.oc = oc;
+    fgrid = user_fused_grid((uint32_t)S, h->sm_count);
+    launch_user_fused(NV, group, cu, fz, fgrid, l);
+    FR_CHECK_LAUNCH(h);
+    h->shadow_dirty = true;
+  } else {
   // 2. forward, loss, per-slice norms, dCat partials, z stash
   FwdParams fp{};
   fp.P = (const float4*)T.P; fp.R = (const float4*)T.R; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B; fp.Bnorm = (float)B;
@@ -321,9 +415,10 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   fp.g = h->g; fp.z = h->z; fp.scores = out_scores ? out_scores : h->scores;
   fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
   fp.lazy = lazy ? 1 : 0; fp.mP = (const float4*)T.s1_P; fp.vP = (const float4*)T.s2_P; fp.lastP = T.last_P; fp.oc = oc;
-  const int fgrid = fwd_train_grid(B, h->sm_count);
+  fgrid = fwd_train_grid(B, h->sm_count);
   launch_fwd_train(NV, group, fp, fgrid, l);
   FR_CHECK_LAUNCH(h);
+  }
 
   FR_MARK(FR_T_FINALIZE);
   // 3. global norm -> clip scale; dense optimizer on Cat
@@ -339,16 +434,23 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   // 4. Personal_Memory: segment-reduce by user + optimizer (+ personal write)
   {
     l.mid = ts ? ts->ev[FR_T_USER_COMBINE] : nullptr;
-    SegCommon c{};
-    c.keys = h->sortU.k[ru]; c.perm = h->sortU.v[ru]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
-    c.uniq_counter = h->counters + 0;
-    c.pieces = h->pieces_u;
+    SegCommon c = cu;
     UserPolParams up{};
     up.P = (float4*)T.P; up.s1 = (float4*)T.s1_P; up.s2 = (float4*)T.s2_P; up.last = T.last_P;
     up.R = (const float4*)T.R; up.G = (const float4*)T.G; up.cat = h->cat_pre;
     up.items = items; up.g = h->g; up.cats = cats; up.cats_by_item = cats_by_item;
     up.ws_row = h->ws_row; up.out = out; up.group = group; up.mc = h->mc; up.oc = oc;
     up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = users;
+    if (fused) {
+      // 4'. the norm is known.  scale == 1 exactly: the speculative rows become current (stamp bits flipped).  Otherwise
+      //     nothing was committed: every row goes back to the caller's tables and the ordinary update pass runs with
+      //     the true scale on the g / z the single-pass kernel left (both launches exit at once in the common case).
+      launch_user_commit(cu.keys, (uint32_t)S, T.last_P, out, (int)step, l);
+      launch_shadow_consolidate(T.last_P, h->cfg.num_users, 5 * DV, (float4*)T.P, (float4*)T.s1_P, (float4*)T.s2_P,
+                                (const float4*)h->shP, (const float4*)h->shM, (const float4*)h->shV, out, l);
+      c.uniq_counter = nullptr;          // (counted by the single-pass kernel)
+      c.only_if_scaled = out;
+    }
     launch_user_pass(NV, c, up, l);
     FR_CHECK_LAUNCH(h);
     if (write_personal) {     // Write_Memory :149-198 on the optimizer's output; reads pre-step R, Cat, G
@@ -367,9 +469,22 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   }
 
   FR_MARK(FR_T_LABEL);
-  // 5. General_Memory: label feed -> entries -> sort by label -> segment-reduce (reads pre-step R)
+  // 5. General_Memory (Write_Memory :201-215; reads pre-step R): shared-memory scatter with one owner warp per label
+  //    (train_label.cu); the sort-by-label segment reduce is the fallback for tables too wide for shared memory
   {
     l.mid = nullptr;
+    int n_parts = 1, Lp = h->mc.L;
+    if (!getenv("FOODREC_LABEL_SORT") && label_scatter_plan(h->mc.L, DV, h->sm_count, &n_parts, &Lp)) {
+      LabelScatterParams sp{};
+      sp.G = (float4*)T.G; sp.R = (const float4*)T.R; sp.cat = h->cat_pre;
+      sp.items = items; sp.cats = cats; sp.cats_by_item = cats_by_item;
+      sp.users = users; sp.group = group; sp.S = S;
+      sp.user_labels = b->user_labels; sp.lab_off = T.user_label_off; sp.lab_idx = T.user_label_idx;
+      sp.ws_row = h->ws_row; sp.mc = h->mc; sp.partial = h->label_partial;
+      sp.n_entries = h->n_entries; sp.out = out; sp.n_parts = n_parts; sp.Lp = Lp;
+      launch_label_scatter(NV, sp, l);
+      FR_CHECK_LAUNCH(h);
+    } else {
     LabelEmitParams ep{};
     ep.S = S; ep.group = group; ep.L = h->mc.L; ep.users = users;
     ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
@@ -392,6 +507,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     lp.cats_by_item = cats_by_item; lp.mc = h->mc;
     launch_label_pass(NV, c, lp, l);
     FR_CHECK_LAUNCH(h);
+    }
   }
 
   FR_MARK(FR_T_ITEM_CHUNK);

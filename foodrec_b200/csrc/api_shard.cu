@@ -65,6 +65,7 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   const size_t n = (size_t)W * sh->cap;
   if ((rc = shard_ensure(h, (size_t)S, n))) return rc;
   cudaStream_t st = (cudaStream_t)s;
+  if ((rc = shadow_sync(h, st))) return rc;
   Launch l{h->sm_count, st, nullptr};
   auto& w = h->sh;
   w.mode = b->mode; w.B = B; w.S = S; w.group = group; w.planned = true;
@@ -180,6 +181,19 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   // General_Memory delta of this rank's rows -> packed (G itself is updated after the all-reduce)
   float* dG = packed + 4 + 4 * (size_t)h->mc.D;
   FR_CUDA(h, cudaMemsetAsync(dG, 0, 5 * (size_t)h->mc.L * h->mc.D * sizeof(float), st));
+  int n_parts = 1, Lp = h->mc.L;
+  if (!getenv("FOODREC_LABEL_SORT") && label_scatter_plan(h->mc.L, DV, h->sm_count, &n_parts, &Lp)) {
+    LabelScatterParams sp{};
+    sp.G = (float4*)dG; sp.R = (const float4*)rbuf; sp.cat = h->cat_pre;
+    sp.items = w.slot_of_row; sp.cats = w.cats_row; sp.cats_by_item = 0;
+    sp.users = h->users_s; sp.group = w.group; sp.S = S;
+    sp.user_labels = b->user_labels; sp.lab_off = T.user_label_off; sp.lab_idx = T.user_label_idx;
+    sp.ws_row = h->ws_row; sp.mc = h->mc; sp.partial = h->label_partial;
+    sp.n_entries = h->n_entries; sp.out = h->out_internal; sp.n_parts = n_parts; sp.Lp = Lp;
+    launch_label_scatter(NV, sp, l);
+    FR_CHECK_LAUNCH(h);
+    return FR_OK;
+  }
   LabelEmitParams ep{};
   ep.S = S; ep.group = w.group; ep.L = h->mc.L; ep.users = h->users_s;
   ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;

@@ -17,6 +17,9 @@ struct fr_ctx {
   bool has_tables = false;
   ModelConsts mc{};
   int NV = 1, sm_count = 148, device = 0;
+  size_t l2_persist_max = 0, l2_window_max = 0;   // device limits for a persisting-L2 access window (0: unsupported)
+  bool l2_lines_pinned = false;                   // a kernel ran with a persisting window since the last reset
+  bool l2_window_set = false;                     // a window was installed on some stream; cleared lazily (l2_release)
   int64_t step = 0;
   float b1p = 0.f, b2p = 0.f;
   char err[512] = {0};
@@ -36,6 +39,7 @@ struct fr_ctx {
   uint32_t* counters = nullptr;        // [0] unique users, [1] unique recipes, [2]/[3] long chains (label / recipe pass)
   uint4* long_list = nullptr; uint32_t long_cap = 0;   // work list of seg_combine_long_kernel (train.cuh)
   float4* cat_pre = nullptr;
+  float4* label_partial = nullptr;     // per-CTA General_Memory partials of label_scatter_kernel [sm_count][L*5*DV]
   float* lr_hist = nullptr; int64_t lr_hist_cap = 0;
   double* cser = nullptr;          // LAZY_SERIES coefficient table [lr_hist_cap * SERIES_TERMS]
   double* mean_partials = nullptr;
@@ -55,6 +59,9 @@ struct fr_ctx {
     bool planned = false;                  // fr_shard_plan has run for the step in flight (S may be 0: a rank that owns no row of the batch)
     fr::PeerPtrs peer_rbuf{}, peer_rgrows{};   // fr_shard_set_peers: NVLink P2P exchange instead of all-to-alls
   } sh;
+  // single-pass training (fr_set_shadow): second copy of Personal_Memory + Adam slots; shadow_dirty = some row's current
+  // copy may be the shadow (cleared by shadow_sync, which every reader of the caller's tables runs first)
+  float *shP = nullptr, *shM = nullptr, *shV = nullptr; bool shadow_dirty = false;
   bool health_blend = false;        // fr_set_health_blend: inference scores P[u] + alpha * mean G[labels(u)]
   fr::CatalogWs* cat = nullptr;     // full-catalog top-K (catalog.cu): index + pass workspace
   // staging for fr_train_step_host
@@ -132,11 +139,15 @@ static inline int alloc_sort(fr_ctx* h, SortBufs& s, size_t cap) {
 
 
 void catalog_free(fr_ctx* h);
+// Persisting-L2 access window over [ptr, ptr+bytes) for the kernels queued next on `st` (api.cu)
+void l2_pin(fr_ctx* h, const void* ptr, size_t bytes, cudaStream_t st);
+void l2_unpin(fr_ctx* h, cudaStream_t st);
 static inline fr::HealthBlend health_of(const fr_ctx* h) {
   fr::HealthBlend hb{nullptr, nullptr, nullptr, 0.f};
   if (h->health_blend) { hb.G = reinterpret_cast<const float4*>(h->tab.G); hb.lab_off = h->tab.user_label_off; hb.lab_idx = h->tab.user_label_idx; hb.alpha = h->mc.alpha; }
   return hb;
 }
 int ensure_lr_hist(fr_ctx* h, int64_t need, cudaStream_t st);
+int shadow_sync(fr_ctx* h, cudaStream_t st);     // rows whose current copy is the shadow go back to the caller's tables
 float adam_lr_t(const fr_ctx* h);
 fr::OptConsts make_oc(const fr_ctx* h, int64_t step);

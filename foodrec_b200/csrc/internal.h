@@ -49,6 +49,10 @@ struct OptConsts {
   float l2b1, l2b2;    // log2(beta1), log2(beta2)
 };
 
+// single-pass training (train_seg.cu, user_fused_kernel): bit 30 of a Personal_Memory stamp says which copy of the
+// double-buffered row is current (0: the caller's table, 1: the shadow of fr_set_shadow)
+constexpr uint32_t FR_SHADOW_BIT = 1u << 30;
+
 constexpr int SERIES_TERMS = 5;
 constexpr int SERIES_WINDOW = 2048;   // TF default betas: b1^j underflows fp32 long before j = 2048; fr_create checks the configured ones
 

@@ -39,6 +39,8 @@ struct SegCommon {
   // FR_LONG_CHAIN pieces to seg_combine_long_kernel (one block per chain) through this list.  Nullable.
   uint4* long_list;            // {first piece index, its slot, last piece index, key}
   uint32_t* long_count; uint32_t long_cap;
+  const float* only_if_scaled; // nullable: out scalars; the pass exits at once if out[FR_OUT_SCALE] == 1 (the update pass
+                               // that follows a single-pass step whose clip speculation held has nothing to do)
 };
 constexpr uint32_t FR_LONG_CHAIN = 16;
 
@@ -50,6 +52,24 @@ struct UserPolParams {
   int group; ModelConsts mc; OptConsts oc;
   const float* user_labels; const int32_t *lab_off, *lab_idx; const int32_t* users;
 };
+// single-pass step (user_fused_kernel, train_seg.cu): forward + segment reduce + Adam in one walk over the user-sorted rows
+struct FusedParams {
+  float4 *P[2], *m[2], *v[2];        // [0] the caller's tables, [1] the shadow copies (fr_set_shadow)
+  int32_t* last;                      // bit 30: which copy holds the row; low bits: lazy-Adam stamp
+  const float4 *R, *cat;
+  const int32_t* items; const float4* cats; int cats_by_item;
+  const float* labels;                // pointwise: y of each row
+  float a, oma, Bnorm;
+  float* g; float4* z; float* scores;
+  float *part_loss, *part_nrm; float4* part_gcat;     // one slot per block
+  ModelConsts mc; OptConsts oc;
+};
+int user_fused_grid(uint32_t n_rows, int sm_count);
+void launch_user_fused(int NV, int group, const SegCommon& c, const FusedParams& p, int grid, const Launch& l);
+void launch_user_commit(const uint32_t* keys, uint32_t n, int32_t* last, const float* out, int step, const Launch& l);
+void launch_shadow_consolidate(int32_t* last, int64_t n_users, int rowDV, float4* P, float4* m, float4* v, const float4* Pa,
+                               const float4* ma, const float4* va, const float* pred, const Launch& l);
+
 struct ItemPolParams {
   float4 *R, *s1, *s2; int32_t* last;
   const float4* z; const float* g; const float* out;
@@ -61,6 +81,23 @@ struct LabelPolParams {
   const int32_t* items; const float4* cats; int cats_by_item;
   ModelConsts mc;
 };
+
+// General_Memory write as a shared-memory scatter (train_label.cu); the sort-by-label pass above remains for tables
+// whose [L][4][D] accumulator does not fit shared memory even in 8 label ranges.
+struct LabelScatterParams {
+  float4* G;                       // [L,5,DV], += (General_Memory, or the dG block of the packed all-reduce buffer)
+  const float4 *R, *cat;           // pre-step recipe rows / Category_Embedding snapshot
+  const int32_t* items; const float4* cats; int cats_by_item;
+  const int32_t* users; int group, S;
+  const float* user_labels; const int32_t *lab_off, *lab_idx;
+  const float* ws_row;
+  ModelConsts mc;
+  float4* partial;                 // [CTAs per label range][L*5*DV]
+  uint32_t* n_entries; float* out; // non-zeros of the label feed -> out[FR_OUT_LABEL_ENTRIES]
+  int n_parts, Lp;                 // label ranges, labels per range
+};
+bool label_scatter_plan(int L, int DV, int sm_count, int* n_parts, int* Lp);
+void launch_label_scatter(int NV, LabelScatterParams p, const Launch& l);
 
 struct LabelEmitParams {
   int S, group, L; const int32_t* users;

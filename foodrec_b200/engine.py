@@ -45,7 +45,7 @@ def _ptr(t):
 class Engine:
     def __init__(self, hyper: Hyper, P, R, Cat, G, device="cuda:0", max_rows=1 << 16,
                  max_label_entries=None, adam_mode="lazy", item_cats=None, user_labels=None,
-                 user_label_csr=None, adopt=False):
+                 user_label_csr=None, adopt=False, single_pass=None):
         self.lib = L.lib()                       # raises if the .so is missing
         if not torch.cuda.is_available():
             raise RuntimeError("foodrec_b200 needs a CUDA device (no CPU fallback)")
@@ -128,6 +128,18 @@ class Engine:
             self.lib.fr_destroy(self.handle); self.handle = None
             raise L.FoodRecError(msg)
         self._set_tables()
+        # Single-pass step (fr_set_shadow): a second copy of Personal_Memory + its Adam slots lets the library score and
+        # update a user's rows in ONE kernel (the two-pass step reads them twice: 6.1 -> 4.0 GB of DRAM traffic per
+        # cfg2 step).  Default: on for lazy Adam when the extra 3 x |P| bytes leave half of the free memory untouched.
+        lazy_adam = self.learner == L.FR_ADAM and self.adam_mode != L.FR_ADAM_DENSE
+        if single_pass is None:
+            need = 3 * self.P.numel() * 4
+            single_pass = lazy_adam and need < 0.5 * torch.cuda.mem_get_info(self.device)[0]
+        self.single_pass = bool(single_pass) and lazy_adam
+        self._shadow = None
+        if self.single_pass:
+            self._shadow = [torch.empty_like(self.P) for _ in range(3)]
+            L.check(self.handle, self.lib.fr_set_shadow(self.handle, *[_ptr(t) for t in self._shadow]))
         self.out = torch.zeros(L.FR_OUT_COUNT, dtype=torch.float32, device=self.device)
         self.out_host = torch.zeros(L.FR_OUT_COUNT, dtype=torch.float32).pin_memory()
         self._dirty = False          # lazy Adam rows pending a flush

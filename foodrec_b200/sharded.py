@@ -77,7 +77,7 @@ class ShardedEngine:
         self.rank, self.world = rank, world
         self.e = Engine(hyper, P_loc, R_loc, Cat, G, device=device, max_rows=max_rows, adam_mode=adam_mode,
                         item_cats=item_cats_global, user_label_csr=user_label_csr_local,
-                        max_label_entries=max_label_entries, adopt=adopt)
+                        max_label_entries=max_label_entries, adopt=adopt, single_pass=False)
         e = self.e
         self.device = e.device
         if cap is None:

@@ -63,7 +63,8 @@ typedef struct {
   int32_t learner;      /* FR_SGD.. */
   int32_t adam_mode;    /* FR_ADAM_* */
   int32_t max_rows;     /* capacity: item rows per step (B pointwise, 2B BPR) */
-  int32_t max_label_entries; /* capacity: non-zeros of the label feed per step */
+  int32_t max_label_entries; /* capacity: non-zeros of the label feed per step (sort-by-label fallback pass only: the
+                                shared-memory scatter that normally writes General_Memory has no capacity) */
   float lr;                             /* args.lr (global_step never advances: lr is constant, :224-226) */
   float high_level_score_coefficient;   /* a, :17 ; low coefficient = 1-a, :96 */
   float beta_1, beta_2, alpha;          /* write coefficients :115,:140,:196 */
@@ -103,7 +104,9 @@ typedef struct {
 /* Device scalars written by fr_train_step (index into float out[FR_OUT_COUNT]). */
 enum { FR_OUT_LOSS = 0, FR_OUT_NORM = 1, FR_OUT_SCALE = 2, FR_OUT_GENERAL = 3,
        FR_OUT_PERSONAL = 4, FR_OUT_LR = 5, FR_OUT_UNIQ_USERS = 6, FR_OUT_UNIQ_ITEMS = 7,
-       FR_OUT_LABEL_ENTRIES = 8, FR_OUT_OVERFLOW = 9 /* !=0: label feed exceeded max_label_entries */,
+       FR_OUT_LABEL_ENTRIES = 8,
+       FR_OUT_OVERFLOW = 9 /* 1: label feed exceeded max_label_entries; 2: fr_shard.cap exceeded; 3: a user / recipe id
+                              outside its table (the row was redirected to row 0: the step's results are invalid) */,
        FR_OUT_COUNT = 12 };
 
 int fr_abi_version(void);
@@ -111,6 +114,17 @@ int fr_create(const fr_config* cfg, fr_handle* out);
 int fr_destroy(fr_handle h);
 const char* fr_last_error(fr_handle h);
 int fr_set_tables(fr_handle h, const fr_tables* t);
+
+/* Single-pass training step (lazy Adam only).  The two-pass step reads Personal_Memory and its Adam slots twice per
+ * step -- once to score, once to update -- because tf.clip_by_global_norm (Model_Recommender.py:237) separates the
+ * gradient from apply_gradients.  With a second, caller-owned copy of P / m / v ([U,5,D] each, contents irrelevant)
+ * fr_train_step scores AND updates a user's rows in one kernel, speculating that the clip is inactive (scale == 1):
+ * new rows go to the other copy and become current (one bit of the row's last_P stamp) only once the norm is known;
+ * if the clip is active the step falls back to the two-pass update with the true scale -- results are those of the
+ * two-pass step either way.  While enabled, the caller's P / s1_P / s2_P may be stale for some rows between calls:
+ * every library entry point that reads them brings them up to date first, and fr_adam_flush does so for the caller.
+ * Passing three NULLs switches it off again.  Not used by the row-sharded phases (fr_shard_*). */
+int fr_set_shadow(fr_handle h, float* P_alt, float* s1_P_alt, float* s2_P_alt);
 
 /* Optimizer step counter (TF: the beta-power accumulators of adam.py); set on restore. */
 int fr_get_step(fr_handle h, int64_t* step);

@@ -111,12 +111,15 @@ def test_dropin_session_reproduces_the_reference_program(name):
     wide = str(t["dtype"]) == "float64"
     # Adam against a float64 trace: ill-conditioned entries (|summed gradient| ~ eps/sqrt(1-beta2)) are excused only
     # where the float32 numpy oracle, replayed alongside, is itself off by a comparable amount (tests/util.py)
+    # The float32 numpy oracle is also the yardstick for the LOSS of a float64 trace: a loss of 1e-4 (scores near 9
+    # after a few lr = 0.01 steps) is exp(-s), so the 1e-6 float32 rounding of s alone moves it by 1e-5 relative.
     om32 = None
-    if wide and str(t["learner"]) == "adam":
+    if wide:
         a_, b1_, b2_, al_ = (float(x) for x in t["hyper"])
         om32 = OracleModel(t["P0"], t["R0"], t["Cat0"], t["G0"],
-                           OHyper(learner="adam", lr=float(t["lr"]), high_level_score_coefficient=a_, beta_1=b1_, beta_2=b2_,
-                                  alpha=al_), dtype=np.float32)
+                           OHyper(learner=str(t["learner"]), lr=float(t["lr"]), high_level_score_coefficient=a_, beta_1=b1_,
+                                  beta_2=b2_, alpha=al_), dtype=np.float32)
+    adam32 = om32 if str(t["learner"]) == "adam" else None
     B = int(np.diff(t["off"]).max())
     a, b1, b2, al = (float(x) for x in t["hyper"])
     args = types.SimpleNamespace(learner=str(t["learner"]), num_categories=4, num_users=t["P0"].shape[0],
@@ -136,8 +139,7 @@ def test_dropin_session_reproduces_the_reference_program(name):
             continue
         fd[model.user_one_hot_label] = feed["user_one_hot_label"].tolist()
         fd[model.write_sign] = feed["write_sign"].tolist()
-        if om32 is not None:
-            om32.train_step(feed, write_personal=kind == 1)
+        o32 = om32.train_step(feed, write_personal=kind == 1) if om32 is not None else None
         if kind == 1:
             loss, lr, personal, general, _ = sess.run([model.loss_value, model.learning_rate, model.personal, model.general,
                                                        model.train_op], fd)
@@ -145,14 +147,18 @@ def test_dropin_session_reproduces_the_reference_program(name):
             assert abs(float(personal) - out["personal_at_run_end"]) <= 1e-5 * np.abs(t["P1"]).mean()
         else:
             loss, lr, general, _ = sess.run([model.loss_value, model.learning_rate, model.general, model.train_op], fd)
-        assert_close(loss, out["loss"], what=f"{name} run {r} loss")
+        if o32 is not None:
+            assert abs(float(loss) - out["loss"]) <= max(1e-5 * abs(out["loss"]), 8 * abs(float(o32["loss"]) - out["loss"])), \
+                f"{name} run {r} loss {loss} vs {out['loss']} (float32 oracle {o32['loss']})"
+        else:
+            assert_close(loss, out["loss"], what=f"{name} run {r} loss")
         assert float(lr) == float(np.float32(out["lr"]))
         assert abs(float(general) - out["general"]) <= 1e-5 * np.abs(t["G1"]).mean()
     assert sess.run(model.epoch_step) == 0          # the replay does not call epoch_increment
     tabs = model.engine.tables()
     for k in ("P", "R", "Cat", "G"):
-        if om32 is not None and k != "G":
-            assert_close_adam(tabs[k], t[k + "1"], getattr(om32, k), what=f"{name} final {k}")
+        if adam32 is not None and k != "G":
+            assert_close_adam(tabs[k], t[k + "1"], getattr(adam32, k), what=f"{name} final {k}")
         else:
             assert_close(tabs[k], t[k + "1"], what=f"{name} final {k}")
     # evaluate_model (evaluate.py:13) on the tables the replay ended with: the reference's own per-user lists
