@@ -45,6 +45,9 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
   h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
   if (getenv("FOODREC_NO_L2_PIN")) h->l2_persist_max = 0;
+  if (getenv("FOODREC_DEBUG_L2"))
+    fprintf(stderr, "foodrec_b200: L2 %d MB, persisting max %zu MB, access window max %zu MB\n", prop.l2CacheSize >> 20,
+            h->l2_persist_max >> 20, h->l2_window_max >> 20);
   h->mc.D = D; h->mc.DV = D / 4; h->mc.L = cfg->num_labels;
   h->mc.a = cfg->high_level_score_coefficient;
   h->mc.oma = 1.0f - cfg->high_level_score_coefficient;     // fp32 (1 - a), Model_Recommender.py:96
@@ -88,28 +91,18 @@ extern "C" int64_t fr_launch_count(void) { return (int64_t)fr::g_launches; }
 // the stream were not enough (ncu, round 1: 12 GB of DRAM reads for 2.8 GB compulsory, the 102 MB table kept being
 // evicted); a persisting access-policy window on the table is: hits in the window are marked persisting, everything
 // else is streaming.  If the table is larger than the persisting carve-out, hitRatio pins that fraction of it.
-void l2_pin(fr_ctx* h, const void* ptr, size_t bytes, cudaStream_t st) {
-  if (!h->l2_persist_max || !h->l2_window_max || !bytes) return;
+bool l2_window(fr_ctx* h, const void* ptr, size_t bytes, cudaAccessPolicyWindow* w) {
+  if (!h->l2_persist_max || !h->l2_window_max || !bytes) return false;
   static bool limit_set = false;
-  if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max); limit_set = true; }
-  cudaStreamAttrValue a{};
+  if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max); cudaGetLastError(); limit_set = true; }
   const size_t win = bytes < h->l2_window_max ? bytes : h->l2_window_max;
-  a.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
-  a.accessPolicyWindow.num_bytes = win;
+  w->base_ptr = const_cast<void*>(ptr);
+  w->num_bytes = win;
   const double r = (double)h->l2_persist_max / (double)win;
-  a.accessPolicyWindow.hitRatio = r >= 1.0 ? 1.0f : (float)r;
-  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) == cudaSuccess) h->l2_window_set = true;
-  else cudaGetLastError();
-}
-void l2_unpin(fr_ctx* h, cudaStream_t st) {
-  if (!h->l2_window_set) return;
-  cudaStreamAttrValue a{};
-  a.accessPolicyWindow.num_bytes = 0;                       // kernels queued from here on run without a window
-  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
-  cudaGetLastError();
-  h->l2_window_set = false;
+  w->hitRatio = r >= 1.0 ? 1.0f : (float)r;
+  w->hitProp = cudaAccessPropertyPersisting;
+  w->missProp = cudaAccessPropertyStreaming;
+  return true;
 }
 
 extern "C" int fr_timing_enable(fr_handle h, int32_t enable) {
@@ -160,6 +153,8 @@ extern "C" int fr_set_tables(fr_handle h, const fr_tables* t) {
   if (al & 15) return fail(h, FR_ERR_ARG, "table pointers must be 16-byte aligned");
   h->tab = *t;
   h->has_tables = true;
+  h->csr_max_labels = (t->user_label_off && t->user_label_idx)
+                          ? csr_max_count(t->user_label_off, h->cfg.num_users, reinterpret_cast<int32_t*>(h->n_entries), 0) : 0;
   return FR_OK;
 }
 
@@ -285,13 +280,12 @@ extern "C" int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int
   if (!cand_cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cand_cats is NULL and no item_cats table");
   { int rc = shadow_sync(h, (cudaStream_t)s); if (rc) return rc; }
   Launch l{h->sm_count, (cudaStream_t)s};
-  l2_pin(h, h->tab.R, (size_t)h->cfg.num_items * h->mc.D * sizeof(float), l.st);
+  cudaAccessPolicyWindow win{};
+  if (l2_window(h, h->tab.R, (size_t)h->cfg.num_items * h->mc.D * sizeof(float), &win)) { l.win = &win; h->l2_lines_pinned = true; }
   launch_eval_sampled(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, cand,
                       n_cand, n_users, cand_stride, (const float4*)cand_cats, (const float4*)h->tab.item_cats, K,
                       topk_ids, gt_rank, scores, health_of(h), l, h->cfg.num_users, h->cfg.num_items);
-  l2_unpin(h, l.st);       // (the window travels with the launch; lines it marked persisting age out under later windows /
-                           //  are demoted by cudaCtxResetPersistingL2Cache in fr_train_step)
-  h->l2_lines_pinned = true;
+  // (lines the window marked persisting are demoted by cudaCtxResetPersistingL2Cache at the next fr_train_step)
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -474,7 +468,8 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   {
     l.mid = nullptr;
     int n_parts = 1, Lp = h->mc.L;
-    if (!getenv("FOODREC_LABEL_SORT") && label_scatter_plan(h->mc.L, DV, h->sm_count, &n_parts, &Lp)) {
+    const bool csr = !b->user_labels && h->csr_max_labels <= 8 && !getenv("FOODREC_LABEL_GENERAL");
+    if (!getenv("FOODREC_LABEL_SORT") && label_scatter_plan(h->mc.L, DV, h->sm_count, csr, &n_parts, &Lp)) {
       LabelScatterParams sp{};
       sp.G = (float4*)T.G; sp.R = (const float4*)T.R; sp.cat = h->cat_pre;
       sp.items = items; sp.cats = cats; sp.cats_by_item = cats_by_item;
@@ -482,7 +477,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
       sp.user_labels = b->user_labels; sp.lab_off = T.user_label_off; sp.lab_idx = T.user_label_idx;
       sp.ws_row = h->ws_row; sp.mc = h->mc; sp.partial = h->label_partial;
       sp.n_entries = h->n_entries; sp.out = out; sp.n_parts = n_parts; sp.Lp = Lp;
-      launch_label_scatter(NV, sp, l);
+      launch_label_scatter(NV, sp, csr, l);
       FR_CHECK_LAUNCH(h);
     } else {
     LabelEmitParams ep{};

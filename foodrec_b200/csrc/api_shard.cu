@@ -65,7 +65,8 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   const size_t n = (size_t)W * sh->cap;
   if ((rc = shard_ensure(h, (size_t)S, n))) return rc;
   cudaStream_t st = (cudaStream_t)s;
-  if ((rc = shadow_sync(h, st))) return rc;
+  const bool lazy_adam = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
+  if (!(lazy_adam && h->shP) && (rc = shadow_sync(h, st))) return rc;
   Launch l{h->sm_count, st, nullptr};
   auto& w = h->sh;
   w.mode = b->mode; w.B = B; w.S = S; w.group = group; w.planned = true;
@@ -153,6 +154,7 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   cudaStream_t st = (cudaStream_t)s;
   if (w.S == 0) {     // a rank without rows adds nothing to {loss, sum|g|^2, dCat, dG}
     FR_CUDA(h, cudaMemsetAsync(packed, 0, (size_t)fr_shard_packed_len(h) * sizeof(float), st));
+    w.fused = false;
     return FR_OK;
   }
   Launch l{h->sm_count, st, nullptr};
@@ -161,6 +163,27 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   const OptConsts oc = make_oc(h, h->step + 1);
   const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
 
+  int fgrid;
+  w.fused = lazy && h->shP && !getenv("FOODREC_TWO_PASS");
+  if (w.fused) {
+    // single-pass step (train_seg.cu): forward AND the speculative Personal_Memory update, before the all-reduce that
+    // makes the global norm known; fr_shard_update commits the rows (scale == 1) or redoes the update with the true scale
+    SegCommon cu{};
+    cu.keys = h->sortU.k[w.ru]; cu.perm = h->sortU.v[w.ru]; cu.n_dev = nullptr; cu.n_host = (uint32_t)S;
+    cu.uniq_counter = h->counters + 0; cu.pieces = h->pieces_u;
+    FusedParams fz{};
+    fz.P[0] = (float4*)T.P; fz.m[0] = (float4*)T.s1_P; fz.v[0] = (float4*)T.s2_P;
+    fz.P[1] = (float4*)h->shP; fz.m[1] = (float4*)h->shM; fz.v[1] = (float4*)h->shV;
+    fz.last = T.last_P; fz.R = (const float4*)rbuf; fz.cat = h->cat_pre;
+    fz.items = w.slot_of_row; fz.cats = w.cats_row; fz.cats_by_item = 0; fz.labels = b->labels;
+    fz.a = h->mc.a; fz.oma = h->mc.oma; fz.Bnorm = (float)sh->global_batch;
+    fz.g = h->g; fz.z = h->z; fz.scores = h->scores;
+    fz.part_loss = h->part_loss; fz.part_nrm = h->part_nrm; fz.part_gcat = h->part_gcat;
+    fz.mc = h->mc; fz.oc = oc;
+    fgrid = user_fused_grid((uint32_t)S, h->sm_count);
+    launch_user_fused(NV, w.group, cu, fz, fgrid, l);
+    h->shadow_dirty = true;
+  } else {
   FwdParams fp{};
   fp.P = (const float4*)T.P; fp.R = (const float4*)rbuf; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B;
   fp.Bnorm = (float)sh->global_batch;
@@ -169,8 +192,9 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   fp.g = h->g; fp.z = h->z; fp.scores = h->scores;
   fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
   fp.lazy = lazy ? 1 : 0; fp.mP = (const float4*)T.s1_P; fp.vP = (const float4*)T.s2_P; fp.lastP = T.last_P; fp.oc = oc;
-  const int fgrid = fwd_train_grid(B, h->sm_count);
+  fgrid = fwd_train_grid(B, h->sm_count);
   launch_fwd_train(NV, w.group, fp, fgrid, l);
+  }
 
   FinalizeParams fin{};
   fin.part_loss = h->part_loss; fin.part_nrm = h->part_nrm; fin.part_gcat = h->part_gcat; fin.nblk = fgrid;
@@ -182,7 +206,8 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   float* dG = packed + 4 + 4 * (size_t)h->mc.D;
   FR_CUDA(h, cudaMemsetAsync(dG, 0, 5 * (size_t)h->mc.L * h->mc.D * sizeof(float), st));
   int n_parts = 1, Lp = h->mc.L;
-  if (!getenv("FOODREC_LABEL_SORT") && label_scatter_plan(h->mc.L, DV, h->sm_count, &n_parts, &Lp)) {
+  const bool csr = !b->user_labels && h->csr_max_labels <= 8 && !getenv("FOODREC_LABEL_GENERAL");
+  if (!getenv("FOODREC_LABEL_SORT") && label_scatter_plan(h->mc.L, DV, h->sm_count, csr, &n_parts, &Lp)) {
     LabelScatterParams sp{};
     sp.G = (float4*)dG; sp.R = (const float4*)rbuf; sp.cat = h->cat_pre;
     sp.items = w.slot_of_row; sp.cats = w.cats_row; sp.cats_by_item = 0;
@@ -190,7 +215,7 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
     sp.user_labels = b->user_labels; sp.lab_off = T.user_label_off; sp.lab_idx = T.user_label_idx;
     sp.ws_row = h->ws_row; sp.mc = h->mc; sp.partial = h->label_partial;
     sp.n_entries = h->n_entries; sp.out = h->out_internal; sp.n_parts = n_parts; sp.Lp = Lp;
-    launch_label_scatter(NV, sp, l);
+    launch_label_scatter(NV, sp, csr, l);
     FR_CHECK_LAUNCH(h);
     return FR_OK;
   }
@@ -265,11 +290,21 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = h->users_s;
   FR_MARK(FR_T_USER_CHUNK);
   l.mid = ts ? ts->ev[FR_T_USER_COMBINE] : nullptr;
+  if (S > 0 && w.fused) {
+    // the all-reduce made the norm known: commit the speculative rows (scale == 1), else bring every row back to the
+    // caller's tables and run the ordinary update pass with the true scale (both exit at once in the common case)
+    launch_user_commit(c.keys, (uint32_t)S, T.last_P, out, (int)step, l);
+    launch_shadow_consolidate(T.last_P, h->cfg.num_users, 5 * DV, (float4*)T.P, (float4*)T.s1_P, (float4*)T.s2_P,
+                              (const float4*)h->shP, (const float4*)h->shM, (const float4*)h->shV, out, l);
+    c.uniq_counter = nullptr;
+    c.only_if_scaled = out;
+  }
   if (S > 0) launch_user_pass(NV, c, up, l);
   else if (l.mid) cudaEventRecord(l.mid, st);
   l.mid = nullptr;
   FR_MARK(FR_T_LABEL);
   if (write_personal && S > 0) {
+    if (w.fused) { rc = shadow_sync(h, st); if (rc) return rc; }     // the personal pass works on the caller's table
     const size_t need = (size_t)S / 32 + 2;
     if (need > h->pieces_personal_chunks) {
       if (h->pieces_personal) { FR_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->pieces_personal); h->pieces_personal = nullptr; }

@@ -19,7 +19,6 @@ struct fr_ctx {
   int NV = 1, sm_count = 148, device = 0;
   size_t l2_persist_max = 0, l2_window_max = 0;   // device limits for a persisting-L2 access window (0: unsupported)
   bool l2_lines_pinned = false;                   // a kernel ran with a persisting window since the last reset
-  bool l2_window_set = false;                     // a window was installed on some stream; cleared lazily (l2_release)
   int64_t step = 0;
   float b1p = 0.f, b2p = 0.f;
   char err[512] = {0};
@@ -39,6 +38,7 @@ struct fr_ctx {
   uint32_t* counters = nullptr;        // [0] unique users, [1] unique recipes, [2]/[3] long chains (label / recipe pass)
   uint4* long_list = nullptr; uint32_t long_cap = 0;   // work list of seg_combine_long_kernel (train.cuh)
   float4* cat_pre = nullptr;
+  int csr_max_labels = 0;              // labels of the busiest user in tables.user_label_* (fr_set_tables)
   float4* label_partial = nullptr;     // per-CTA General_Memory partials of label_scatter_kernel [sm_count][L*5*DV]
   float* lr_hist = nullptr; int64_t lr_hist_cap = 0;
   double* cser = nullptr;          // LAZY_SERIES coefficient table [lr_hist_cap * SERIES_TERMS]
@@ -56,6 +56,7 @@ struct fr_ctx {
     float4* pieces_s = nullptr;
     int ru = 0, ri = 0, rs = 0;            // which sort buffer holds each result
     int mode = 0, B = 0, S = 0, group = 1;
+    bool fused = false;                    // the step in flight ran the single-pass forward (fr_shard_forward)
     bool planned = false;                  // fr_shard_plan has run for the step in flight (S may be 0: a rank that owns no row of the batch)
     fr::PeerPtrs peer_rbuf{}, peer_rgrows{};   // fr_shard_set_peers: NVLink P2P exchange instead of all-to-alls
   } sh;
@@ -140,8 +141,7 @@ static inline int alloc_sort(fr_ctx* h, SortBufs& s, size_t cap) {
 
 void catalog_free(fr_ctx* h);
 // Persisting-L2 access window over [ptr, ptr+bytes) for the kernels queued next on `st` (api.cu)
-void l2_pin(fr_ctx* h, const void* ptr, size_t bytes, cudaStream_t st);
-void l2_unpin(fr_ctx* h, cudaStream_t st);
+bool l2_window(fr_ctx* h, const void* ptr, size_t bytes, cudaAccessPolicyWindow* w);
 static inline fr::HealthBlend health_of(const fr_ctx* h) {
   fr::HealthBlend hb{nullptr, nullptr, nullptr, 0.f};
   if (h->health_blend) { hb.G = reinterpret_cast<const float4*>(h->tab.G); hb.lab_off = h->tab.user_label_off; hb.lab_idx = h->tab.user_label_idx; hb.alpha = h->mc.alpha; }

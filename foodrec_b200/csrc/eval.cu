@@ -285,8 +285,21 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   const size_t smem = (size_t)(4 + 5 * FR_WARPS_PER_BLOCK) * mc.DV * sizeof(float4);
   ++g_launches;
-#define FR_EVAL(NVV, SL) eval_sampled_kernel<NVV, SL><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, mc.a, mc.oma, users, cand, \
-    n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb, (uint32_t)n_table_users, (uint32_t)n_items)
+  // launched with cudaLaunchKernelEx so that a persisting-L2 access-policy window (Recipe_Embedding: every user re-reads
+  // 51 random rows of it while 2.5 KB of read-once user rows per user stream past) can ride on the LAUNCH: a stream
+  // attribute does not take on the legacy default stream the Python layer hands over
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FR_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = l.st;
+  cudaLaunchAttribute attr[1];
+  if (l.win) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow = *l.win;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  const int DVv = mc.DV; const float av = mc.a, omav = mc.oma;
+  const uint32_t ntu = (uint32_t)n_table_users, nit = (uint32_t)n_items;
+#define FR_EVAL(NVV, SL) cudaLaunchKernelEx(&cfg, eval_sampled_kernel<NVV, SL>, P, R, Cat, DVv, av, omav, users, cand, \
+    n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb, ntu, nit)
   const bool two = stride <= 64;
   if (mc.DV <= 32) { if (two) FR_EVAL(1, 2); else FR_EVAL(1, 4); }
   else             { if (two) FR_EVAL(2, 2); else FR_EVAL(2, 4); }

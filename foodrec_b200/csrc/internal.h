@@ -86,7 +86,8 @@ struct StepView {
 
 extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
-struct Launch { int sm_count; cudaStream_t st; cudaEvent_t mid = nullptr; /* recorded between chunk and combine */ };
+struct Launch { int sm_count; cudaStream_t st; cudaEvent_t mid = nullptr; /* recorded between chunk and combine */
+                const cudaAccessPolicyWindow* win = nullptr; /* persisting-L2 window for the launch (kernels that take one) */ };
 
 // Health term at inference (fr_set_health_blend): the user row is scored as
 //   P'[u] = P[u] + alpha * (sum_{l in labels(u)} G[l]) / |labels(u)|

@@ -96,8 +96,9 @@ struct LabelScatterParams {
   uint32_t* n_entries; float* out; // non-zeros of the label feed -> out[FR_OUT_LABEL_ENTRIES]
   int n_parts, Lp;                 // label ranges, labels per range
 };
-bool label_scatter_plan(int L, int DV, int sm_count, int* n_parts, int* Lp);
-void launch_label_scatter(int NV, LabelScatterParams p, const Launch& l);
+bool label_scatter_plan(int L, int DV, int sm_count, bool csr, int* n_parts, int* Lp);
+void launch_label_scatter(int NV, LabelScatterParams p, bool csr, const Launch& l);
+int csr_max_count(const int32_t* off, int64_t n, int32_t* scratch, cudaStream_t st);
 
 struct LabelEmitParams {
   int S, group, L; const int32_t* users;

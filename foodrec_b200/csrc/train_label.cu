@@ -191,6 +191,171 @@ label_scatter_kernel(const LabelScatterParams p) {
   }
 }
 
+// ---- resident label CSR with <= LS2_MAXL labels per user (the normal case: 1-3): a pipelined variant.
+// The general kernel above is latency-bound: staging a tile is a chain of dependent loads (row -> recipe -> mask,
+// row -> user -> CSR offsets -> labels) that every warp waits for at a block-wide barrier, and an owner warp finds only
+// ~2 of its entries in a 32-entry window, so its recipe-row loads go out two at a time (measured: 0.40 ms per
+// 524k-row step, slower than the sort-by-label pass it was meant to replace).  Here
+//   * warps 0..7 are STAGERS: they fill one of two staging buffers with tile k+1 (recipe id, sign, mask, the row's
+//     labels packed as bytes) while
+//   * warps 8..31 are OWNERS (label % 24): an owner first collects ITS (row, label) entries of tile k into a private
+//     queue with ballots, then works the queue off eight recipe rows at a time;
+//   * one barrier per tile.  Same single-writer / fixed-order rule, so the result is deterministic.
+constexpr int LS2_THREADS = 1024;
+constexpr int LS2_STAGERS = 8;                       // warps
+constexpr int LS2_OWNERS = LS2_THREADS / 32 - LS2_STAGERS;
+constexpr int LS2_TILE = LS2_STAGERS * 32;           // rows per tile: one per stager thread
+constexpr int LS2_MAXL = 8;                          // labels per row (two packed words)
+constexpr int LS2_QCAP = 96;
+
+template <int NV>
+__global__ void __launch_bounds__(LS2_THREADS, 1)
+label_scatter_csr_kernel(const LabelScatterParams p) {
+  extern __shared__ float4 smem[];
+  const int DV = p.mc.DV, Lp = p.Lp;
+  float4* acc = smem;                                  // [Lp][4][DV]
+  float4* sCat = acc + (size_t)Lp * 4 * DV;            // [4][DV]
+  float4* row_mask = sCat + 4 * DV;                    // [2][TILE]
+  float* cw = reinterpret_cast<float*>(row_mask + 2 * LS2_TILE);   // [Lp][4]
+  int* row_item = reinterpret_cast<int*>(cw + Lp * 4); // [2][TILE]
+  float* row_ws = reinterpret_cast<float*>(row_item + 2 * LS2_TILE);
+  uint32_t* row_labs = reinterpret_cast<uint32_t*>(row_ws + 2 * LS2_TILE);   // [2][TILE][2]: 8 label bytes, 0xff = none
+  uint32_t* queue = row_labs + 4 * LS2_TILE;           // [OWNERS][QCAP]: row << 8 | label
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int part = blockIdx.x % p.n_parts, cta = blockIdx.x / p.n_parts, ctas = gridDim.x / p.n_parts;
+  const int l0 = part * Lp, l1 = min(p.mc.L, l0 + Lp);
+  for (int i = tid; i < Lp * 4 * DV; i += LS2_THREADS) acc[i] = f4zero();
+  for (int i = tid; i < Lp * 4; i += LS2_THREADS) cw[i] = 0.f;
+  for (int i = tid; i < 4 * DV; i += LS2_THREADS) sCat[i] = p.cat[i];
+
+  const int ntiles = (p.S + LS2_TILE - 1) / LS2_TILE;
+  const bool stager = warp < LS2_STAGERS;
+  unsigned my_entries = 0;
+
+  auto stage = [&](int tile, int buf) {                // one row per stager thread
+    const int r = tile * LS2_TILE + tid;
+    uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
+    if (r < p.S) {
+      const int item = p.items[r];
+      const int u = p.users[r / p.group];
+      const int b = p.lab_off[u], e = p.lab_off[u + 1];
+      row_item[buf * LS2_TILE + tid] = item;
+      row_ws[buf * LS2_TILE + tid] = p.ws_row[r];
+      row_mask[buf * LS2_TILE + tid] = __ldg(p.cats + (p.cats_by_item ? item : r));
+      int k = 0;
+      for (int q = b; q < e && k < LS2_MAXL; ++q) {
+        const int l = p.lab_idx[q];
+        if (l >= l0 && l < l1) {
+          const uint32_t v = (uint32_t)(l - l0);
+          if (k < 4) w0 = (w0 & ~(0xffu << (8 * k))) | (v << (8 * k));
+          else w1 = (w1 & ~(0xffu << (8 * (k - 4)))) | (v << (8 * (k - 4)));
+          ++k;
+        }
+      }
+      my_entries += (unsigned)k;
+    }
+    row_labs[(buf * LS2_TILE + tid) * 2] = w0;
+    row_labs[(buf * LS2_TILE + tid) * 2 + 1] = w1;
+  };
+
+  auto drain = [&](const uint32_t* q, int qn, int buf) {     // this owner's entries, eight recipe rows in flight
+    constexpr int PF = NV == 1 ? 8 : 4;
+    for (int i0 = 0; i0 < qn; i0 += PF) {
+      uint32_t ent[PF]; float4 rr[PF][NV];
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        ent[k] = q[min(i0 + k, qn - 1)];
+        load_row_ro<NV>(rr[k], p.R + (size_t)row_item[buf * LS2_TILE + (ent[k] >> 8)] * DV, DV, lane);
+      }
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        if (i0 + k >= qn) break;
+        const int row = (int)(ent[k] >> 8), lab = (int)(ent[k] & 0xffu);
+        const float coef = row_ws[buf * LS2_TILE + row];
+        const float4 m = row_mask[buf * LS2_TILE + row];
+        if (lane < 4) {
+          const float rn = __frcp_rn(((m.x + m.y) + m.z) + m.w);
+          cw[lab * 4 + lane] = __fadd_rn(cw[lab * 4 + lane], __fmul_rn(__fmul_rn(coef, rn), comp(m, lane)));
+        }
+        const float lc = p.mc.beta_1 * coef;
+        float4* a = acc + (size_t)lab * 4 * DV;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float mcv = comp(m, c);
+          if (mcv != 0.f) {
+#pragma unroll
+            for (int x = 0; x < NV; ++x) {
+              const int i = lane + 32 * x;
+              if (i < DV) { float4 v = a[c * DV + i]; mad4_rn(v, lc, scale4(mcv, rr[k][x])); a[c * DV + i] = v; }
+            }
+          }
+        }
+      }
+    }
+  };
+
+  int tile = cta;
+  if (stager && tile < ntiles) stage(tile, 0);
+  __syncthreads();
+  for (int k = 0; tile < ntiles; ++k, tile += ctas) {
+    const int buf = k & 1;
+    if (stager) {
+      if (tile + ctas < ntiles) stage(tile + ctas, buf ^ 1);
+    } else {
+      const int o = warp - LS2_STAGERS;
+      uint32_t* q = queue + o * LS2_QCAP;
+      int qn = 0;
+      const int nrows = min(LS2_TILE, p.S - tile * LS2_TILE);
+      for (int base = 0; base < nrows; base += 32) {
+        const int row = base + lane;
+        const uint32_t w0 = row < nrows ? row_labs[(buf * LS2_TILE + row) * 2] : 0xffffffffu;
+        const uint32_t w1 = row < nrows ? row_labs[(buf * LS2_TILE + row) * 2 + 1] : 0xffffffffu;
+        if (__all_sync(FR_FULL, w1 == 0xffffffffu && (w0 >> 24) == 0xffu)) {   // <= 3 labels everywhere (the usual case)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const uint32_t lab = (w0 >> (8 * s)) & 0xffu;
+            const bool mine = lab != 0xffu && (int)(lab % LS2_OWNERS) == o;
+            const uint32_t bal = __ballot_sync(FR_FULL, mine);
+            if (mine) q[qn + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)row << 8) | lab;
+            qn += __popc(bal);
+            if (qn > LS2_QCAP - 32) { __syncwarp(); drain(q, qn, buf); __syncwarp(); qn = 0; }
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < LS2_MAXL; ++s) {
+            const uint32_t lab = ((s < 4 ? w0 : w1) >> (8 * (s & 3))) & 0xffu;
+            const bool mine = lab != 0xffu && (int)(lab % LS2_OWNERS) == o;
+            const uint32_t bal = __ballot_sync(FR_FULL, mine);
+            if (mine) q[qn + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)row << 8) | lab;
+            qn += __popc(bal);
+            if (qn > LS2_QCAP - 32) { __syncwarp(); drain(q, qn, buf); __syncwarp(); qn = 0; }
+          }
+        }
+      }
+      __syncwarp();
+      drain(q, qn, buf);
+    }
+    __syncthreads();
+  }
+  if (stager) {
+    my_entries = __reduce_add_sync(FR_FULL, my_entries);
+    if (lane == 0 && my_entries) atomicAdd(p.n_entries, my_entries);
+  }
+  float4* dst = p.partial + (size_t)cta * p.mc.L * 5 * DV;
+  for (int i = tid; i < (l1 - l0) * 4 * DV; i += LS2_THREADS) {
+    const int l = i / (4 * DV), rem = i % (4 * DV);
+    dst[((size_t)(l0 + l) * 5 + 1) * DV + rem] = acc[i];
+  }
+  for (int i = tid; i < (l1 - l0) * DV; i += LS2_THREADS) {
+    const int l = i / DV, d = i % DV;
+    float4 v = f4zero();
+    mad4_rn(v, p.mc.beta_2 * cw[l * 4 + 0], sCat[d]); mad4_rn(v, p.mc.beta_2 * cw[l * 4 + 1], sCat[DV + d]);
+    mad4_rn(v, p.mc.beta_2 * cw[l * 4 + 2], sCat[2 * DV + d]); mad4_rn(v, p.mc.beta_2 * cw[l * 4 + 3], sCat[3 * DV + d]);
+    dst[((size_t)(l0 + l) * 5) * DV + d] = v;
+  }
+}
+
 // G += partials, summed in CTA order (fixed tree: deterministic)
 __global__ void __launch_bounds__(256)
 label_reduce_kernel(float4* __restrict__ G, const float4* __restrict__ partial, int n4, int n_partials,
@@ -213,39 +378,72 @@ size_t label_scatter_smem(int Lp, int DV) {
   return ((size_t)Lp * 4 * DV + 4 * DV + LS_TILE) * sizeof(float4) +
          ((size_t)Lp * 4 + 3 * LS_TILE + 1 + LS_WARPS + 3 * LS_ECAP) * 4;
 }
+size_t label_scatter_csr_smem(int Lp, int DV) {
+  return ((size_t)Lp * 4 * DV + 4 * DV + 2 * LS2_TILE) * sizeof(float4) +
+         ((size_t)Lp * 4 + 2 * LS2_TILE * 2 + 4 * LS2_TILE + (size_t)LS2_OWNERS * LS2_QCAP) * 4;
+}
 
 // Returns false when the accumulator does not fit shared memory even in 8 label ranges (caller takes the sort path).
-bool label_scatter_plan(int L, int DV, int sm_count, int* n_parts, int* Lp) {
+// csr: the pipelined kernel (resident label CSR, <= LS2_MAXL labels per user, label ranges of <= 255 labels).
+bool label_scatter_plan(int L, int DV, int sm_count, bool csr, int* n_parts, int* Lp) {
   static int max_smem = -1;
   if (max_smem < 0) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncSetAttribute(label_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(label_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(label_scatter_csr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(label_scatter_csr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   }
   for (int np = 1; np <= 8 && np <= sm_count; ++np) {
     const int lp = (L + np - 1) / np;
-    if (label_scatter_smem(lp, DV) <= (size_t)max_smem) { *n_parts = np; *Lp = lp; return true; }
+    if (csr && lp > 255) continue;
+    const size_t need = csr ? label_scatter_csr_smem(lp, DV) : label_scatter_smem(lp, DV);
+    if (need <= (size_t)max_smem) { *n_parts = np; *Lp = lp; return true; }
   }
   return false;
 }
 
-int label_scatter_ctas(int S, int n_parts, int sm_count) {       // CTAs per label range (= partials to reduce)
-  const int ntiles = (S + LS_TILE - 1) / LS_TILE;
+int label_scatter_ctas(int S, int n_parts, int sm_count, int tile) {       // CTAs per label range (= partials to reduce)
+  const int ntiles = (S + tile - 1) / tile;
   int c = sm_count / n_parts;
   if (c > ntiles) c = ntiles;
   return c < 1 ? 1 : c;
 }
 
-void launch_label_scatter(int NV, LabelScatterParams p, const Launch& l) {
-  const int ctas = label_scatter_ctas(p.S, p.n_parts, l.sm_count);
-  const size_t smem = label_scatter_smem(p.Lp, p.mc.DV);
+void launch_label_scatter(int NV, LabelScatterParams p, bool csr, const Launch& l) {
+  const int ctas = label_scatter_ctas(p.S, p.n_parts, l.sm_count, csr ? LS2_TILE : LS_TILE);
   cudaMemsetAsync(p.n_entries, 0, sizeof(uint32_t), l.st);
-  if (NV == 1) label_scatter_kernel<1><<<ctas * p.n_parts, LS_THREADS, smem, l.st>>>(p);
-  else label_scatter_kernel<2><<<ctas * p.n_parts, LS_THREADS, smem, l.st>>>(p);
+  if (csr) {
+    const size_t smem = label_scatter_csr_smem(p.Lp, p.mc.DV);
+    if (NV == 1) label_scatter_csr_kernel<1><<<ctas * p.n_parts, LS2_THREADS, smem, l.st>>>(p);
+    else label_scatter_csr_kernel<2><<<ctas * p.n_parts, LS2_THREADS, smem, l.st>>>(p);
+  } else {
+    const size_t smem = label_scatter_smem(p.Lp, p.mc.DV);
+    if (NV == 1) label_scatter_kernel<1><<<ctas * p.n_parts, LS_THREADS, smem, l.st>>>(p);
+    else label_scatter_kernel<2><<<ctas * p.n_parts, LS_THREADS, smem, l.st>>>(p);
+  }
   const int n4 = p.mc.L * 5 * p.mc.DV;
   label_reduce_kernel<<<(n4 + 255) / 256, 256, 0, l.st>>>(p.G, p.partial, n4, ctas, p.n_entries, p.out);
   g_launches += 2;
+}
+
+// largest number of labels any user has in the resident CSR (fr_set_tables; synchronises)
+__global__ void csr_max_count_kernel(const int32_t* __restrict__ off, int64_t n, int32_t* __restrict__ out) {
+  int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, off[i + 1] - off[i]);
+  m = __reduce_max_sync(FR_FULL, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+int csr_max_count(const int32_t* off, int64_t n, int32_t* scratch, cudaStream_t st) {
+  if (n <= 0) return 0;
+  cudaMemsetAsync(scratch, 0, sizeof(int32_t), st);
+  csr_max_count_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, st>>>(off, n, scratch);
+  int v = 0;
+  cudaMemcpyAsync(&v, scratch, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  return v;
 }
 
 }  // namespace fr

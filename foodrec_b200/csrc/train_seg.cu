@@ -12,6 +12,8 @@
 // Every kernel here is an HBM-bound row mover: one warp holds one table row at a time, a
 // row of D floats moves as 16-byte vectors (lane l <-> float4 l, l+32, ...), the four
 // category rows live in shared memory.
+#include <cstdlib>
+
 #include "optim.cuh"
 #include "train.cuh"
 
@@ -957,6 +959,12 @@ user_fused_kernel(const SegCommon c, const FusedUserPol<NV, OPT> pol) {
             st.s2[s][q] = ok ? __ldcs(vs + s * DV + i) : f4zero();
           }
       }
+      // the recipe rows of the run's first group do not depend on the user's state: requested before the catch-up
+      // arithmetic so that both are in flight together (the next group's rows are requested while this one is scored)
+      float4 rr[GROUP][NV];
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j)
+        load_row_ro<NV>(rr[j], p.R + (size_t)__shfl_sync(FR_FULL, e_item, e0 + j) * DV, DV, lane);
       // the rows TF would see at this step: decay-only steps the user sat out
       adam_catchup<OPT, 5 * NV>(&st.var[0][0], &st.s1[0][0], &st.s2[0][0], st.last, p.oc.step - 1, p.oc);
       float4 acc[5][NV];
@@ -965,13 +973,12 @@ user_fused_kernel(const SegCommon c, const FusedUserPol<NV, OPT> pol) {
 #pragma unroll
         for (int q = 0; q < NV; ++q) acc[s][q] = f4zero();
       for (int j0 = e0; j0 < e1; j0 += GROUP) {
-        float4 rr[GROUP][NV], pcn[GROUP][NV];
+        float4 pcn[GROUP][NV];
         float4 mm[GROUP]; float sc[GROUP], rnn[GROUP], nzq[GROUP], nRq[GROUP], npcq[GROUP];
         uint32_t row[GROUP];
 #pragma unroll
         for (int j = 0; j < GROUP; ++j) {
           row[j] = __shfl_sync(FR_FULL, ent, j0 + j);
-          load_row_ro<NV>(rr[j], p.R + (size_t)__shfl_sync(FR_FULL, e_item, j0 + j) * DV, DV, lane);
           mm[j] = shfl4(e_m, j0 + j);
         }
 #pragma unroll
@@ -1085,6 +1092,11 @@ user_fused_kernel(const SegCommon c, const FusedUserPol<NV, OPT> pol) {
             mad4_rn(acc[3][q], go * wj.z, rr[j][q]); mad4_rn(acc[4][q], go * wj.w, rr[j][q]);
           }
         }
+        if (j0 + GROUP < e1) {
+#pragma unroll
+          for (int j = 0; j < GROUP; ++j)
+            load_row_ro<NV>(rr[j], p.R + (size_t)__shfl_sync(FR_FULL, e_item, j0 + GROUP + j) * DV, DV, lane);
+        }
       }
       if (contained) {
         pol.apply_to_other(st, k, acc, lane, true);
@@ -1170,7 +1182,12 @@ void launch_shadow_consolidate(int32_t* last, int64_t n_users, int rowDV, float4
 int user_fused_grid(uint32_t n_rows, int sm_count) {
   const uint32_t nchunks = (n_rows + 31) / 32;
   int grid = (int)((nchunks + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
-  const int cap = sm_count * 4;          // one dCat / loss / norm partial per block: the workspace is sized for 4 per SM
+  // exactly the CTAs that are resident (two per SM): with a static grid-stride assignment a second, partial wave
+  // would leave SMs idle at the end (4 per SM measured 0.83 ms: 592 CTAs in two waves, 3 or 4 chunks per warp);
+  // FOODREC_FUSED_CTAS_PER_SM overrides (<= 4: the dCat / loss / norm partial workspace holds 4 per SM)
+  static int per_sm = -1;
+  if (per_sm < 0) { const char* e = getenv("FOODREC_FUSED_CTAS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1 || per_sm > 4) per_sm = 2; }
+  const int cap = sm_count * per_sm;
   if (grid > cap) grid = cap;
   return grid < 1 ? 1 : grid;
 }

@@ -71,13 +71,13 @@ class ShardedEngine:
 
     def __init__(self, hyper: Hyper, P_loc, R_loc, Cat, G, rank, world, device="cuda:0", max_rows=1 << 16,
                  cap=None, adam_mode="lazy", item_cats_global=None, user_label_csr_local=None,
-                 max_label_entries=None, adopt=False):
+                 max_label_entries=None, adopt=False, single_pass=None):
         if not (1 <= world <= 8):
             raise ValueError("1 <= world <= 8")
         self.rank, self.world = rank, world
         self.e = Engine(hyper, P_loc, R_loc, Cat, G, device=device, max_rows=max_rows, adam_mode=adam_mode,
                         item_cats=item_cats_global, user_label_csr=user_label_csr_local,
-                        max_label_entries=max_label_entries, adopt=adopt, single_pass=False)
+                        max_label_entries=max_label_entries, adopt=adopt, single_pass=single_pass)
         e = self.e
         self.device = e.device
         if cap is None:
