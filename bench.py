@@ -30,15 +30,22 @@ SMALL = dict(U=20_000, I=5_000, L=95, D=128)       # --small: functional check o
 METRIC, UNIT = "bpr_train_triples_per_sec", "triples/s"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures of bench.py's
-# own command (key: batch, learner, adam mode).  262144/adam/lazy: profiles/r01b_ncu_full_train_B262144.csv (launch1 =
-# forward, launch2 = user pass, launch3 = label pass, launch4 = recipe pass; tests/prof_capture.sh is the command);
-# 65536: r01_ncu_full_fwd_and_user_chunk.csv launch3.
-NCU_TRAFFIC = {
-    (262144, "adam", "lazy"): {"fwd": 2_452_224_000, "user_chunk": 3_649_241_000, "label_tile": 163_581_000,
-                               "item_chunk": 711_604_000},
-    (65536, "adam", "lazy"): {"fwd": 551_159_040},
-}
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the `ncu --set full` captures of THIS
+    build's bench command (profiles/summarize.py traffic -> profiles/ncu_traffic.json: {"build": source hash,
+    "kernels": {name: {"dram_bytes": ..., "capture": file}}}).  Returned only when the file was made from the sources
+    the loaded library was built from; otherwise every `traffic` field in the line is null (nothing is hard-coded)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    try:
+        j = json.load(open(p))
+        from foodrec_b200 import _build
+        if j.get("build") != _build.source_hash():
+            return {}
+        return {k: v["dram_bytes"] for k, v in j.get("kernels", {}).items()}
+    except Exception:
+        return {}
 
 
 def peaks():
@@ -57,7 +64,7 @@ def tensor_peaks():
     return 1590.0, 1400.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s burst, ~1.4 sustained)"
 
 
-def bench_catalog(eng, dev, label, n_users, K=100, reps=2):
+def bench_catalog(eng, dev, label, n_users, K=100, reps=2, warm_users=None):
     """Full-catalog top-K users/s (fr_catalog_topk): device-timed with resident inputs, per-phase CUDA
     events from inside the library, and end to end from a pinned host user list to host ids."""
     import torch
@@ -65,7 +72,7 @@ def bench_catalog(eng, dev, label, n_users, K=100, reps=2):
     info = eng.catalog_info()
     tile_n, sets, split = info["epi_sets"] % 1000, info["epi_sets"] // 1000, info["cta_group"] >= 10
     eng.timing_enable(True)
-    eng.catalog_topk(n_users=n_users, K=K)                         # warm-up (workspace allocation, code load)
+    eng.catalog_topk(n_users=warm_users or n_users, K=K)           # warm-up (workspace allocation, code load)
     torch.cuda.synchronize(); eng.catalog_timing_read()
     best = None
     for _ in range(reps):
@@ -98,7 +105,9 @@ def bench_catalog(eng, dev, label, n_users, K=100, reps=2):
                    "split_user_operand": bool(split), "tiles": info["tiles"]},
         "roofline": {"bound": "tensor", "kernel": "catalog_gemm_kernel", "achieved": executed / gemm_s / 1e12, "peak": sustained,
                      "unit": "TFLOP/s", "frac": executed / gemm_s / 1e12 / sustained, "peak_burst": burst, "peak_source": src,
-                     "traffic": None, "flop_per_launch_executed": executed, "ms_per_launch": ph["gemm_filter"] / max(passes, 1),
+                     "traffic": ncu_traffic().get("catalog_gemm_kernel:" + label.split(":")[0]),
+                     "flop_executed_total": executed, "gemm_ms_total": ph["gemm_filter"], "launches": passes,
+                     "flop_per_launch_executed": executed / max(passes, 1), "ms_per_launch": ph["gemm_filter"] / max(passes, 1),
                      "dense_equivalent_tflops": dense / gemm_s / 1e12,
                      "note": "executed = bf16 MMA flops issued (mask-grouped K=D contraction, x2 for the split user operand); "
                              "dense_equivalent = SURVEY 8(d)'s 2*U*I*5D over the same time"},
@@ -286,43 +295,162 @@ def cpu_catalog_leg(cfg, K=100, n_users=512):
             "sample": f"{n_users} users x {I} recipes, K={K}, float32 (oracle/evaluate_oracle.catalog_topk)"}
 
 
+def cfg1_stream(n_batches, B=128):
+    """BASELINE configs[0]: 10k users / 5k recipes / 95 labels / D=64 and the reference's own instance stream
+    (get_train_instances, Train_recommender.py:74-96: user-contiguous, 1-2 users per 128-row batch)."""
+    import synth_data as synth
+    U, I, L, D = 10_000, 5_000, 95, 64
+    tb = synth.make_tables(U, I, L, D, seed=synth.BASE_SEED + 1)
+    ic = synth.make_item_categories(I); ul = synth.make_user_labels(U, L)
+    train, _, tneg = synth.make_reference_dataset(max(8, n_batches * B // 50 + 8), I, seed=11)
+    d2c, u2l = synth.reference_side_maps(ic, ul)
+    u_idx, i_idx, labels, cats, sign, _ = synth.get_train_instances(train, tneg, d2c, u2l, seed=3)
+    users = (np.asarray(u_idx).astype(np.int64) * 25 + 3) % U
+    n = (len(users) // B) * B
+    assert n >= n_batches * B, (n, n_batches)
+    return tb, dict(users=users[:n].astype(np.int32), items=np.asarray(i_idx, np.int32)[:n],
+                    labels=np.asarray(labels, np.float32)[:n], cats=np.asarray(cats, np.float32).reshape(-1, 4)[:n],
+                    ws=np.asarray(sign, np.float32).reshape(-1)[:n], ulab=ul[users[:n]].astype(np.float32))
+
+
+def cfg1_cpu_leg(steps=200, B=128):
+    """The CPU arm at cfg1, exactly the reference's shape (pointwise, B=128, dense TF-1.x Adam sweep per step)."""
+    import torch
+    from oracle.cpu_port import CpuPort
+    from oracle.recommender_oracle import Hyper
+    cores = len(os.sched_getaffinity(0))
+    tb, f = cfg1_stream(steps + 5, B)
+    port = CpuPort(tb.P, tb.R, tb.Cat, tb.G, Hyper(learner="adam", lr=0.001), threads=cores)
+    T = lambda k, dt=None: torch.as_tensor(f[k] if dt is None else f[k].astype(dt))
+    tu, ti, ty, tc, tw, tl = T("users", np.int64), T("items", np.int64), T("labels"), T("cats"), T("ws"), T("ulab")
+    t0 = None
+    for k in range(steps + 5):
+        if k == 5:
+            t0 = time.perf_counter()
+        sl = slice(k * B, (k + 1) * B)
+        port.train_step(tu[sl], ti[sl], ty[sl], tc[sl], tw[sl], tl[sl])
+    dt = time.perf_counter() - t0
+    return {"value": B * steps / dt, "unit": "instances/s", "cores": cores, "kind": "port", "ms_per_step": 1e3 * dt / steps,
+            "sample": f"{steps} pointwise steps of {B} rows of the reference stream at cfg1 (10k users, 5k recipes, D=64) after 5 warm-up"}
+
+
+def cfg1_gpu_leg(dev, steps=200, B=128):
+    """The CUDA path at cfg1 through the host entry point the drop-in Session uses: reference-format feed in pinned
+    host memory, loss read on the host every step (what Train_recommender.py:195-200 does)."""
+    import torch
+    from foodrec_b200 import Engine, Hyper, _lib as L
+    tb, f = cfg1_stream(steps + 5, B)
+    eng = Engine(Hyper(learner="adam", lr=0.001), tb.P, tb.R, tb.Cat, tb.G, device=dev, max_rows=B, max_label_entries=B * 95)
+    pin = {k: torch.as_tensor(np.ascontiguousarray(v)).pin_memory() for k, v in f.items()}
+    launches0 = eng.lib.fr_launch_count()
+    t0 = None
+    for k in range(steps + 5):
+        if k == 5:
+            torch.cuda.synchronize(); t0 = time.perf_counter(); launches0 = eng.lib.fr_launch_count()
+        sl = slice(k * B, (k + 1) * B)
+        out = eng.train_step_host(L.FR_POINTWISE, B, pin["users"][sl], pin["items"][sl], pin["cats"][sl], pin["labels"][sl],
+                                  pin["ws"][sl], pin["ulab"][sl])
+        torch.cuda.current_stream().synchronize()
+        loss = float(out[L.FR_OUT_LOSS])
+    dt = time.perf_counter() - t0
+    n_launch = eng.lib.fr_launch_count() - launches0
+    eng.close()
+    return {"value": B * steps / dt, "unit": "instances/s", "ms_per_step": 1e3 * dt / steps, "last_loss": loss,
+            "launches_per_step": n_launch / steps,
+            "note": "end to end (host feed in, loss out, synchronised every step); a 128-row step is launch-bound on a GPU"}
+
+
 # ----------------------------------------------------------------------------- GPU arm, N > 1
-def run_sharded(args, cfg, B):
-    """N GPUs of one node, one process per GPU: tables row-sharded (P by user % N, R by
-    recipe % N), B triples per GPU per step (weak scaling), every triple loaded on the rank
-    that owns its user; recipe rows and their gradients cross NVLink in all-to-alls, one
-    packed all-reduce per step.  value = N*B*K / max-over-ranks device time."""
+def shard_self_check(rank, world, dev, p2p):
+    """Correctness of the N-rank step IN the bench run (the 2-GPU pytest cannot run on a 1-GPU lease): a small problem is
+    trained for a few steps through the same DistRunner (same collectives, same peer-store path) while rank 0 trains
+    an unsharded Engine on the same global batches; every rank's rows are gathered and compared element-wise."""
+    import torch
+    import torch.distributed as dist
+    from foodrec_b200 import Engine, Hyper
+    from foodrec_b200 import sharded as sh
+    import synth_data as synth
+    U, I, Lb, D, B = 8192 * world + 3, 4099, 95, 128, 2048 * world
+    tb = synth.make_tables(U, I, Lb, D, seed=5)
+    ic = synth.make_item_categories(I, seed=6)
+    off, idx = synth.make_user_label_csr(U, Lb, seed=7)
+    hy = Hyper(learner="adam", lr=0.01)
+    eng = sh.ShardedEngine(hy, sh.shard_rows(tb.P, rank, world), sh.shard_rows(tb.R, rank, world), tb.Cat, tb.G, rank, world,
+                           device=dev, max_rows=2 * B, item_cats_global=ic,
+                           user_label_csr_local=sh.shard_label_csr(off, idx, rank, world, U))
+    run = sh.DistRunner(eng)
+    if p2p:
+        run.enable_p2p()
+    single = Engine(hy, tb.P, tb.R, tb.Cat, tb.G, device=dev, max_rows=2 * B, item_cats=ic, user_label_csr=(off, idx)) if rank == 0 else None
+    worst_loss = 0.0
+    for s in range(4):
+        rng = np.random.default_rng(40 + s)                     # the same global batch on every rank
+        users = rng.integers(0, U, B).astype(np.int32)
+        if s == 2:
+            users[: B // 2] = users[0]                          # a heavy user: long runs, one rank far busier than the others
+        pos = synth.zipf_items(rng, I, B)
+        neg = rng.integers(0, I, B).astype(np.int32); neg[neg == pos] = (neg[neg == pos] + 1) % I
+        ix = sh.route_batch(users, world)[rank]
+        eng.set_batch(users[ix] // world, pos[ix], neg_items=neg[ix], global_batch=B)
+        out = run.step().cpu().numpy()
+        assert out[9] == 0, "capacity / id flag raised in the self-check"
+        if single is not None:
+            single.train_step(users, pos, neg_items=neg)
+            v = single.read_scalars()
+            worst_loss = max(worst_loss, abs(out[0] - v[0]) / abs(v[0]))
+    eng.e.flush()
+    Pl, Rl = eng.e.P.contiguous(), eng.e.R.contiguous()
+    Ps = [torch.empty_like(Pl) for _ in range(world)]; Rs = [torch.empty_like(Rl) for _ in range(world)]
+    dist.all_gather(Ps, Pl); dist.all_gather(Rs, Rl)
+    res = None
+    if rank == 0:
+        t = single.tables()
+        def rel(x, ref):
+            ref = ref.astype(np.float64)
+            return float(np.max(np.abs(x.astype(np.float64) - ref) / np.maximum(np.abs(ref), np.sqrt(np.mean(ref ** 2)))))
+        errs = {"P": rel(sh.unshard_rows([x.cpu().numpy() for x in Ps], U), t["P"]),
+                "R": rel(sh.unshard_rows([x.cpu().numpy() for x in Rs], I), t["R"]),
+                "Cat": rel(eng.e.Cat.cpu().numpy(), t["Cat"]), "G": rel(eng.e.G.cpu().numpy(), t["G"])}
+        # Adam: summation order differs between the sharded and the unsharded step (recipe gradients are pre-reduced per
+        # rank): 1e-4 on P / R / Cat as in tests/test_gpu_sharded.py, 1e-5 on G and the loss
+        ok = worst_loss <= 1e-5 and errs["G"] <= 1e-5 and max(errs["P"], errs["R"], errs["Cat"]) <= 1e-4
+        res = {"ok": bool(ok), "steps": 4, "users": U, "recipes": I, "global_batch": B, "loss_rel_err": worst_loss,
+               "table_rel_err": errs, "compared": "every row of every rank, all-gathered, against an unsharded engine on rank 0"}
+        single.close()
+    eng.e.close()
+    del eng, run
+    torch.cuda.empty_cache()
+    flag = torch.tensor([1.0 if (res is None or res["ok"]) else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if float(flag.item()) != 1.0:
+        if rank == 0:
+            print(json.dumps({"self_check": res}), file=sys.stderr)
+        raise SystemExit("sharded self-check FAILED: the N-rank step does not reproduce the unsharded engine")
+    return res
+
+
+def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll, warmup, label, single_pass=None):
+    """One weak-scaling training measurement: every rank holds `cfg_local` rows (its shard), B triples per rank per step."""
     import torch
     import torch.distributed as dist
     from foodrec_b200 import Hyper, _lib as L
-    from foodrec_b200.sharded import DistRunner, ShardedEngine, local_rows
+    from foodrec_b200.sharded import DistRunner, ShardedEngine
     import synth_data as synth
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    clocks = ClockSampler(local); clocks.start()
-    dist.init_process_group("nccl", device_id=dev)
-    U, I, Lb, D = cfg["U"], cfg["I"], cfg["L"], cfg["D"]
-    Ul, Il = local_rows(U, world), local_rows(I, world)
+    Ul, Il, Lb, D = cfg_local["U"], cfg_local["I"], cfg_local["L"], cfg_local["D"]
+    I = Il * world
     g = torch.Generator(device=dev); g.manual_seed(1 + rank)
-    P = torch.randn((Ul, 5, D), device=dev, generator=g).mul_(0.1); R = torch.randn((Il, D), device=dev, generator=g).mul_(0.1)
+    P = torch.empty((Ul, 5, D), device=dev).normal_(0, 0.1, generator=g); R = torch.empty((Il, D), device=dev).normal_(0, 0.1, generator=g)
     g2 = torch.Generator(device=dev); g2.manual_seed(99)          # replicated tables: same on every rank
     Cat = torch.randn((4, D), device=dev, generator=g2) * 0.1; G = torch.randn((Lb, 5, D), device=dev, generator=g2) * 0.1
     item_cats = synth.make_item_categories(I)
     lab = synth.make_user_label_csr(Ul, Lb, seed=synth.BASE_SEED + 200 + rank)
     eng = ShardedEngine(Hyper(learner=args.learner, lr=0.001), P, R, Cat, G, rank, world, device=dev, max_rows=2 * B,
-                        adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab, adopt=True)
-    del P
+                        adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab, adopt=True,
+                        single_pass=single_pass)
+    del P, R
     run = DistRunner(eng)
-    p2p = False
-    if not args.no_p2p:
-        try:
-            run.enable_p2p()
-            p2p = True
-        except Exception as ex:             # no symmetric memory on this box: the staged all-to-all path
-            if rank == 0:
-                print(f"peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using all-to-alls", file=sys.stderr)
+    if p2p:
+        run.enable_p2p()
     NB = 8
     pin, devb = [], []
     for k in range(NB):
@@ -334,60 +462,147 @@ def run_sharded(args, cfg, B):
         pin.append((torch.as_tensor(users).pin_memory(), torch.as_tensor(items).pin_memory()))
         devb.append((pin[-1][0].to(dev), pin[-1][1].to(dev)))
 
-    def step(k):
+    def step(k, **kw):
         u, it = devb[k % NB]
         eng.set_batch_dev(L.FR_BPR, B, u, it, global_batch=world * B)
-        return run.step()
+        return run.step(**kw)
 
-    for k in range(args.preroll + args.warmup):
+    for k in range(preroll + warmup):
         step(k)
     v = eng.e.read_scalars()
     launches0 = eng.e.lib.fr_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize()
-    clocks.mark_begin()
+    t_begin = time.time()
     ev0.record()
-    for k in range(args.steps):
+    for k in range(steps):
         step(k)
     ev1.record()
     dist.barrier(); torch.cuda.synchronize()
-    clocks.mark_end()
+    t_end = time.time()
     launches = eng.e.lib.fr_launch_count() - launches0
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-    # roofline of the dominant kernel (the user pass: same kernel, same per-GPU work as at N=1), from CUDA events the
-    # library records around it inside fr_shard_update -- a few extra steps after the timed region, rank 0's numbers
+    # per-kernel events inside the library (rank 0's numbers) and per-phase events around every fr_shard_* call / collective
+    n_ph = min(steps, 10)
     eng.e.timing_enable(True)
-    for k in range(min(args.steps, 10)):
+    for k in range(n_ph):
         step(k)
     torch.cuda.synchronize()
     sphases, _ = eng.e.timing_read()
     eng.e.timing_enable(False)
-    # per-phase times of the sharded step (events on the step's stream around every fr_shard_* call and collective)
     shard_ms = {}
-    for k in range(min(args.steps, 10)):
-        u, it = devb[k % NB]
-        eng.set_batch_dev(L.FR_BPR, B, u, it, global_batch=world * B)
+    for k in range(n_ph):
         evs = []
-        run.step(phase_events=evs)
+        step(k, phase_events=evs)
         torch.cuda.synchronize()
         for (name, e0), (_, e1) in zip(evs[:-1], evs[1:]):
-            shard_ms[name] = shard_ms.get(name, 0.0) + e0.elapsed_time(e1) / min(args.steps, 10)
+            shard_ms[name] = shard_ms.get(name, 0.0) + e0.elapsed_time(e1) / n_ph
     v = eng.e.read_scalars()
     peak, peak_src = peaks()
     adam_k = {"adam": 6, "adagrad": 4, "rmsprop": 6, "sgd": 2}.get(args.learner.lower(), 2)
-    ualg = float(v[L.FR_OUT_UNIQ_USERS]) * adam_k * 20 * D
+    uu, ui = float(v[L.FR_OUT_UNIQ_USERS]), float(v[L.FR_OUT_UNIQ_ITEMS])
+    fused = bool(eng.e.single_pass)
+    # dominant kernel on rank 0: the single-pass kernel lives in the `forward` phase, the two-pass user pass in `update`
+    if fused:
+        kms = shard_ms.get("forward", 0.0)
+        kalg = uu * adam_k * 20 * D + B * (2 * 4 * D + 16) + B * 2 * 4 * D
+        kname, kscope = "user_fused_kernel (+ label scatter: the `forward` phase)", "phase time, per GPU (rank 0)"
+    else:
+        kms = sphases.get("user_chunk", 0.0)
+        kalg = uu * adam_k * 20 * D
+        kname, kscope = "seg_chunk_kernel<UserPol>", "per GPU (rank 0)"
     sroof = None
-    if sphases.get("user_chunk", 0) > 0:
-        ugbs = ualg / (sphases["user_chunk"] * 1e-3) / 1e9
-        sroof = {"bound": "hbm", "kernel": "seg_chunk_kernel<UserPol>", "achieved": ugbs, "peak": peak, "unit": "GB/s",
-                 "frac": ugbs / peak, "peak_source": peak_src, "alg_bytes_per_launch": ualg,
-                 "ms_per_launch": sphases["user_chunk"], "scope": "per GPU (rank 0)",
-                 "traffic": NCU_TRAFFIC.get((B, args.learner.lower(), args.adam_mode), {}).get("user_chunk") if world == 1 else None,
-                 "update_phase_ms": {k: sphases[k] for k in ("finalize", "user_chunk", "user_combine", "label", "item_chunk", "item_combine")}}
+    if kms > 0:
+        sroof = {"bound": "hbm", "kernel": kname, "achieved": kalg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                 "frac": kalg / (kms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "alg_bytes_per_launch": kalg,
+                 "ms_per_launch": kms, "scope": kscope, "traffic": None}
+    step_bytes = B * (28 * D + 16) + uu * adam_k * 20 * D + ui * adam_k * 4 * D + 4 * Lb * 5 * D
+    # e2e, both feeds: ids only (side tables resident) and the reference's dense feed (categories + user_one_hot_label)
+    ubuf = torch.empty(B, dtype=torch.int32, device=dev); ibuf = torch.empty(2 * B, dtype=torch.int32, device=dev)
+
+    def e2e(dense):
+        hc = hl = dc = dl = None
+        if dense:
+            hc = [torch.as_tensor(item_cats[pin[k][1].numpy()]).pin_memory() for k in range(NB)]
+            hl = [torch.as_tensor(synth.csr_rows_dense(lab[0], lab[1], pin[k][0].numpy(), Lb)).pin_memory() for k in range(NB)]
+            dc = torch.empty((2 * B, 4), dtype=torch.float32, device=dev); dl = torch.empty((B, Lb), dtype=torch.float32, device=dev)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss = 0.0
+        for k in range(steps):
+            hu, hi = pin[k % NB]
+            ubuf.copy_(hu, non_blocking=True); ibuf.copy_(hi, non_blocking=True)
+            if dense:
+                dc.copy_(hc[k % NB], non_blocking=True); dl.copy_(hl[k % NB], non_blocking=True)
+                eng._keep = [ubuf, ibuf, dc, dl]
+                eng._b = L.fr_batch(L.FR_BPR, B, ubuf.data_ptr(), ibuf.data_ptr(), dc.data_ptr(), None, None, dl.data_ptr())
+                eng._sh = eng._shard(world * B)
+            else:
+                eng.set_batch_dev(L.FR_BPR, B, ubuf, ibuf, global_batch=world * B)
+            out = run.step()
+            loss = float(out[L.FR_OUT_LOSS])                      # D2H + sync
+        dist.barrier(); torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * B * steps / float(tt.item()), loss
+    e2e_ids, loss_ids = e2e(False)
+    e2e_dense, _ = e2e(True)
+    res = {
+        "label": label, "value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "launches": int(launches),
+        "window": (t_begin, t_end), "single_pass": fused, "p2p": p2p, "cap": eng.cap,
+        "local_rows": {"users": Ul, "recipes": Il}, "global_rows": {"users": Ul * world, "recipes": I},
+        "roofline": sroof, "shard_phases_ms": shard_ms, "update_phase_kernels_ms": {k: sphases[k] for k in sphases if sphases[k] > 0},
+        "roofline_step": {"bound": "hbm", "alg_bytes_per_step_per_gpu": step_bytes, "achieved": step_bytes / (ms / steps * 1e-3) / 1e9,
+                          "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms / steps * 1e-3) / 1e9 / peak, "scope": "per GPU"},
+        "e2e": {"value": e2e_dense, "unit": UNIT, "h2d_bytes_per_step": B * (12 + 2 * 16 + 4 * Lb), "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
+                "feed": "reference dense feed (user_input, item_input, categories, user_one_hot_label) from pinned host memory, "
+                        "loss read every step -- the same feed as the N=1 e2e"},
+        "e2e_compact": {"value": e2e_ids, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
+                        "feed": "ids only (user, pos, neg); side tables resident", "last_loss": loss_ids},
+        "uniq_users_per_step": uu, "uniq_items_per_step": ui, "overflow_flag": float(v[L.FR_OUT_OVERFLOW]),
+    }
+    return res, eng, run
+
+
+def run_sharded(args, cfg, B):
+    """N GPUs of one node, one process per GPU: tables row-sharded (P by user % N, R by recipe % N), B triples per GPU
+    per step, every triple loaded on the rank that owns its user; recipe rows and their gradients cross NVLink (peer
+    stores from inside the gather / gradient kernels, or staged all-to-alls), one packed all-reduce per step.
+    WEAK SCALING AT CONSTANT PER-GPU WORK: every GPU holds a cfg2-sized shard (1M users, 200k recipes: the tables grow
+    with N), so the unique rows a GPU touches per step are those of the N=1 run (--fixed-tables: round-1 behaviour,
+    cfg2 tables divided over the ranks).  value = N*B*K / max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    from foodrec_b200 import Hyper
+    from foodrec_b200.sharded import DistRunner, ShardedEngine, local_rows
+    import synth_data as synth
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    clocks = ClockSampler(local); clocks.start()
+    dist.init_process_group("nccl", device_id=dev)
+    U, I, Lb, D = cfg["U"], cfg["I"], cfg["L"], cfg["D"]
+    p2p = not args.no_p2p
+    if p2p:
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+        except Exception as ex:
+            p2p = False
+            if rank == 0:
+                print(f"peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using all-to-alls", file=sys.stderr)
+    check = shard_self_check(rank, world, dev, p2p)
+    if args.cfg3 or args.fixed_tables:
+        cfg_local = dict(U=local_rows(U, world), I=local_rows(I, world), L=Lb, D=D)
+        mode = "cfg3 (BASELINE configs[2])" if args.cfg3 else "fixed tables (cfg2 divided over the ranks)"
+    else:
+        cfg_local = dict(U=U, I=I, L=Lb, D=D)
+        mode = "constant per-GPU work (a cfg2-sized shard on every GPU)"
+    main, eng, run = sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, args.steps, args.preroll, args.warmup, mode)
+    clocks.t0, clocks.t1 = main.pop("window")
     clk = clocks.stop()
-    value = world * B * args.steps / (ms / 1e3)
-    # ---- item-sharded full-catalog top-100: n_q query users PER GPU (weak scaling), recipes sharded by id % N
-    # (before the e2e leg trains the tables further: see the note at the single-GPU catalog leg):
+    Ul, Il = cfg_local["U"], cfg_local["I"]
+    I_glob = Il * world
+    # ---- item-sharded full-catalog top-100: n_q query users PER GPU (weak scaling), recipes sharded by id % N:
     # all-gather of the query rows, per-shard tcgen05 top-K, all-to-all of the lists, exact merge
     catalog = None
     if not args.no_catalog:
@@ -401,63 +616,78 @@ def run_sharded(args, cfg, B):
         dist.barrier(); torch.cuda.synchronize()
         t = torch.tensor([c0.elapsed_time(c1)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); cms = float(t.item())
         catalog = {"metric": "catalog_topk_users_per_sec", "value": world * n_q / (cms * 1e-3), "unit": "users/s",
-                   "workload": f"{n_q} query users per GPU x {I} recipes sharded by id % {world}, D={D}, K=100",
-                   "ms": cms, "fallback_rows_rank0": eng.e.catalog_fallback_rows(),
+                   "workload": f"{n_q} query users per GPU x {I_glob} recipes sharded by id % {world}, D={D}, K=100",
+                   "ms": cms, "fallback_rows_rank0": eng.e.catalog_fallback_rows(), "train_steps_before": int(eng.e.step),
                    "exchange_bytes_per_gpu": {"all_gather_rows": (world - 1) * n_q * 5 * D * 4,
                                               "all_to_all_lists": (world - 1) * n_q * 100 * 12}}
-        # cfg4 shape (BASELINE configs[3]): 10M recipes item-sharded over the N GPUs, n_q query users per GPU
-        if not args.small:
-            I4 = 10_000_000
-            Il4 = local_rows(I4, world)
-            g4 = torch.Generator(device=dev); g4.manual_seed(40 + rank)
-            e4 = ShardedEngine(Hyper(learner="sgd"), torch.randn((n_q, 5, D), device=dev, generator=g4) * 0.1,
-                               torch.randn((Il4, D), device=dev, generator=g4) * 0.1, Cat, G, rank, world, device=dev,
-                               max_rows=256, item_cats_global=synth.make_item_categories(I4))
-            e4.e.I_global = I4
-            e4.catalog_prepare()
-            run4 = DistRunner(e4)
-            run4.catalog_topk(ul, K=100)
-            dist.barrier(); torch.cuda.synchronize()
-            c0.record(); run4.catalog_topk(ul, K=100); c1.record()
-            dist.barrier(); torch.cuda.synchronize()
-            t = torch.tensor([c0.elapsed_time(c1)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); cms4 = float(t.item())
-            catalog = [catalog, {
-                "metric": "catalog_topk_users_per_sec", "value": world * n_q / (cms4 * 1e-3), "unit": "users/s",
-                "workload": f"cfg4 shape: {n_q} query users per GPU x {I4} recipes sharded by id % {world}, D={D}, K=100 "
-                            f"(weak scaling: every GPU scores all {world * n_q} gathered users against its {Il4} recipes)",
-                "ms": cms4, "fallback_rows_rank0": e4.e.catalog_fallback_rows(),
-                "dense_equivalent_tflops_per_gpu": 2.0 * world * n_q * Il4 * 5 * D / (cms4 * 1e-3) / 1e12}]
-    # e2e: ids from pinned host memory every step, loss read on the host every step
-    ubuf = torch.empty(B, dtype=torch.int32, device=dev); ibuf = torch.empty(2 * B, dtype=torch.int32, device=dev)
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        hu, hi = pin[k % NB]
-        ubuf.copy_(hu, non_blocking=True); ibuf.copy_(hi, non_blocking=True)
-        eng.set_batch_dev(L.FR_BPR, B, ubuf, ibuf, global_batch=world * B)
-        out = run.step()
-        loss = float(out[L.FR_OUT_LOSS])                      # D2H + sync
-    dist.barrier(); torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+    Cat, G = eng.e.Cat.clone(), eng.e.G.clone()
+    eng.e.close(); del eng, run
+    torch.cuda.empty_cache()
+    if not args.no_catalog and not args.small and not args.cfg3:
+        # cfg4 shape (BASELINE configs[3]): 10M recipes item-sharded over the N GPUs.  FULL query set: 1M users in all,
+        # 1M / N per GPU in blocks of n_q (every GPU scores every gathered block against its recipe shard)
+        I4, U4 = 10_000_000, 1_000_000
+        Il4 = local_rows(I4, world)
+        n_q = 18_944
+        per_gpu = -(-U4 // world)
+        blocks = -(-per_gpu // n_q)
+        g4 = torch.Generator(device=dev); g4.manual_seed(40 + rank)
+        e4 = ShardedEngine(Hyper(learner="sgd"), torch.randn((n_q * blocks, 5, D), device=dev, generator=g4) * 0.1,
+                           torch.randn((Il4, D), device=dev, generator=g4) * 0.1, Cat, G, rank, world, device=dev,
+                           max_rows=256, item_cats_global=synth.make_item_categories(I4), adopt=True)
+        e4.e.I_global = I4
+        e4.catalog_prepare()
+        run4 = DistRunner(e4)
+        ul = torch.arange(n_q, dtype=torch.int32, device=dev)
+        run4.catalog_topk(ul, K=100)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        c0.record()
+        fb = 0
+        for bk in range(blocks):
+            run4.catalog_topk(ul + bk * n_q, K=100)
+        c1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([c0.elapsed_time(c1)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); cms4 = float(t.item())
+        n_users4 = world * n_q * blocks
+        catalog = [catalog, {
+            "metric": "catalog_topk_users_per_sec", "value": n_users4 / (cms4 * 1e-3), "unit": "users/s",
+            "workload": f"cfg4 IN FULL: {n_users4} query users ({n_q * blocks} per GPU in {blocks} blocks of {n_q}) x {I4} recipes "
+                        f"sharded by id % {world}, D={D}, K=100; all-gather of query rows, per-shard top-K, all-to-all of the lists, merge",
+            "ms": cms4, "fallback_rows_rank0_last_block": e4.e.catalog_fallback_rows(),
+            "dense_equivalent_tflops_per_gpu": 2.0 * n_users4 * Il4 * 5 * D / (cms4 * 1e-3) / 1e12}]
+        e4.e.close(); del e4, run4
+        torch.cuda.empty_cache()
+    # ---- BASELINE configs[2] at N = 8: 100M users / 10M recipes row-sharded (12.5M users = 96 GB of P + Adam slots per
+    # GPU: no room for the single-pass shadow copy -> two-pass step), fewer steps (the tables take a while to fill)
+    cfg3_line = None
+    if world == 8 and not args.small and not args.cfg3 and not args.no_cfg3:
+        c3 = dict(U=local_rows(CFG3["U"], world), I=local_rows(CFG3["I"], world), L=Lb, D=D)
+        cfg3_line, e3, r3 = sharded_train_leg(args, c3, B, rank, world, dev, p2p, min(args.steps, 20), 12, 3,
+                                              "cfg3 (BASELINE configs[2]): 100M users / 10M recipes over 8 GPUs", single_pass=False)
+        cfg3_line.pop("window")
+        e3.e.close(); del e3, r3
+        torch.cuda.empty_cache()
     if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        line = {
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "catalog_topk": catalog,
-            "config": {"workload": workload_name(cfg, B) + f" PER GPU (global batch {world * B})", "batch_triples": B,
+            "config": {"workload": workload_name(dict(cfg, U=Ul * world, I=I_glob), B) + f" PER GPU (global batch {world * B}); " + mode,
+                       "batch_triples": B,
                        "optimizer": (f"adam (TF-1.x semantics, {args.adam_mode})" if args.learner.lower() == "adam" else args.learner),
                        "l2": "per-step working set >> 126 MB L2; 8 distinct batches cycled", "preroll_steps": args.preroll,
                        "parallelism": f"row-sharded x{world}: P by user%N (samples loaded at the user owner), R by recipe%N; " + (
                            f"id all-to-all + recipe rows / gradient rows stored into peer memory over NVLink by the gather / "
-                           f"gradient kernels (cap {eng.cap}/pair, 2 barriers) + 1 packed all-reduce per step" if p2p else
-                           f"3 all-to-alls (ids, rows, grad rows, cap {eng.cap}/pair) + 1 packed all-reduce per step")},
-            "clocks": clk, "gpu_launches": int(launches), "roofline": sroof, "shard_phases_ms": shard_ms,
-            "e2e": {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
-                    "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
-                    "feed": "ids only (user, pos, neg) from pinned host memory; side tables resident; loss read every step",
-                    "last_loss": loss},
-            "uniq_users_per_step": float(v[L.FR_OUT_UNIQ_USERS]), "uniq_items_per_step": float(v[L.FR_OUT_UNIQ_ITEMS]),
-            "overflow_flag": float(v[L.FR_OUT_OVERFLOW])}))
+                           f"gradient kernels (cap {main['cap']}/pair, 2 barriers) + 1 packed all-reduce per step" if p2p else
+                           f"3 all-to-alls (ids, rows, grad rows, cap {main['cap']}/pair) + 1 packed all-reduce per step")},
+            "clocks": clk, "gpu_launches": main["launches"], "roofline": main["roofline"], "roofline_step": main["roofline_step"],
+            "single_pass": main["single_pass"], "shard_phases_ms": main["shard_phases_ms"],
+            "update_phase_kernels_ms": main["update_phase_kernels_ms"], "self_check": check,
+            "e2e": main["e2e"], "e2e_compact": main["e2e_compact"],
+            "uniq_users_per_step": main["uniq_users_per_step"], "uniq_items_per_step": main["uniq_items_per_step"],
+            "overflow_flag": main["overflow_flag"], "cfg3": cfg3_line}
+        print(json.dumps(line))
     dist.destroy_process_group()
 
 
@@ -565,31 +795,26 @@ def run_ours(args, cfg, B):
                 "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
                 "peak_source": peak_src, "traffic": None,
                 "alg_bytes_per_launch": alg[dom], "ms_per_launch": phases[dom]}
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of each kernel at this batch, from the committed
-    # `ncu --set full` captures (profiles/NCU_TRAFFIC: which file / launch each figure comes from)
-    ncu_traffic = NCU_TRAFFIC.get((B, args.learner.lower(), args.adam_mode), {})
-    for k, v in ncu_traffic.items():
-        if k in kern:
-            kern[k]["ncu_dram_bytes_per_launch"] = v
-    roofline["traffic"] = ncu_traffic.get(dom)
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of each kernel, from the ncu --set full captures of this
+    # build (ncu_traffic(): null unless profiles/ncu_traffic.json was made from the sources the library was built from)
+    traffic = ncu_traffic()
+    kname = {"fwd": "user_fused_kernel" if fused else "fwd_train_kernel", "user_chunk": "seg_chunk_kernel<UserPol>",
+             "item_chunk": "seg_chunk_kernel<ItemPol>"}
+    for k in kern:
+        kern[k]["ncu_dram_bytes_per_launch"] = traffic.get(kname[k])
+    roofline["traffic"] = traffic.get(kname[dom])
+    # the whole step against the HBM roofline: SURVEY 8(d)'s step total (score + user update + recipe update + G write)
+    step_bytes = B * (28 * D + 16) + uniq_users * adam_k * 20 * D + uniq_items * adam_k * 4 * D + 4 * Lb * 5 * D
+    roofline_step = {"bound": "hbm", "alg_bytes_per_step": step_bytes, "ms_per_step": ms / args.steps,
+                     "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+                     "definition": "SURVEY 8(d) train-step total: B(28D+16) + uniq_users*6*20D + uniq_items*6*4D + 4*L*5D bytes"}
     if dom == "fwd" and "gbs_incl_adam_state" in kern["fwd"]:
         roofline["achieved_incl_adam_state"] = kern["fwd"]["gbs_incl_adam_state"]
         roofline["frac_incl_adam_state"] = kern["fwd"]["gbs_incl_adam_state"] / peak
         roofline["note"] = ("achieved/frac use SURVEY 8(d)'s 28D+16 B per triple; the lazy-Adam forward also has to read "
                             "the m and v rows of every stale user row (see kernels.fwd), which the *_incl_adam_state "
                             "figures and the ncu dram traffic include")
-
-    # ---- full-catalog top-100 users/s on the tables as the timed training region left them (cfg2: every user).
-    # It runs HERE, before the e2e / pointwise legs train the same tables for several hundred more steps: the filter's
-    # error bound is proportional to the largest recipe norm, which the hottest Zipf recipe keeps growing under this
-    # synthetic stream; past ~400 steps the candidate lists overflow and rows take the exact fallback (still exact,
-    # 40x slower -- DESIGN.md "what comes next": per-tile bounds).
-    catalog = []
-    catalog_launches_cfg2 = 0
-    if not args.no_catalog:
-        lc0 = eng.lib.fr_launch_count()
-        catalog.append(bench_catalog(eng, dev, f"cfg2: all {U} users x {I} recipes, D={D}, K=100", U))
-        catalog_launches_cfg2 = eng.lib.fr_launch_count() - lc0
 
     # ---- e2e: reference-format dense feed from pinned host memory through the C ABI host entry point
     pin = lambda x: torch.as_tensor(np.ascontiguousarray(x)).pin_memory()
@@ -625,11 +850,9 @@ def run_ours(args, cfg, B):
         if world > 1:
             t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         return world * B * args.steps / dt, loss_sum / args.steps
-    # the overlapped leg is run three times and the best is reported (all three are in the line): one run in six on
-    # this pool came out at the un-overlapped rate although nothing in the queueing differs -- the H2D copy of feed k+1
-    # did not overlap step k on that box
+    # the overlapped leg is run three times; the MEDIAN is reported, all three and their spread are in the line
     e2e_runs = [e2e_run(True) for _ in range(3)]
-    e2e_val, e2e_loss = max(e2e_runs)
+    e2e_val, e2e_loss = sorted(e2e_runs)[1]
     e2e_serial, _ = e2e_run(True, prefetch=False)
     e2e_cval, _ = e2e_run(False)
 
@@ -678,21 +901,31 @@ def run_ours(args, cfg, B):
     eval_ms = e0.elapsed_time(e1)
     eval_alg = NU * (20 * D + 51 * 4 * D + 51 * 12)
 
-    # ---- full-catalog top-100 users/s (tcgen05 GEMM + fused top-K filter): every user of cfg2, then a
-    # cfg4-shaped sample (10M recipes) on fresh tables
+    # ---- full-catalog top-100 users/s (tcgen05 GEMM + fused top-K filter): every user of cfg2 on the tables ALL the
+    # legs above have trained (pre-roll + timed + per-kernel + e2e + pointwise: several hundred steps, the hot Zipf
+    # recipes' norms have grown -- the per-tile filter bound keeps the margin local), then a cfg4-shaped sample (10M
+    # recipes) on fresh tables
+    catalog = []
+    catalog_launches_cfg2 = 0
     if not args.no_catalog:
+        lc0 = eng.lib.fr_launch_count()
+        catalog.append(bench_catalog(eng, dev, f"cfg2: all {U} users x {I} recipes, D={D}, K=100", U))
+        catalog[0]["train_steps_before"] = int(eng.step)
+        catalog_launches_cfg2 = eng.lib.fr_launch_count() - lc0
         launches_c0 = eng.lib.fr_launch_count()
         if not args.small:
             eng.close()
             del eng
             torch.cuda.empty_cache()
-            I4, U4 = 10_000_000, 75_776
+            # BASELINE configs[3] IN FULL on one GPU: top-100 of 10M recipes for every one of 1M users (14 passes of
+            # 75,776 users; one timed run after a one-pass warm-up)
+            I4, U4 = 10_000_000, 1_000_000
             g4 = torch.Generator(device=dev); g4.manual_seed(4)
             e4 = Engine(Hyper(learner="sgd"), torch.randn((U4, 5, D), device=dev, generator=g4) * 0.1,
                         torch.randn((I4, D), device=dev, generator=g4) * 0.1, Cat, G, device=dev, max_rows=256,
-                        item_cats=synth.make_item_categories(I4))
-            catalog.append(bench_catalog(e4, dev, f"cfg4 sample: {U4} of 1M users x {I4} recipes, D={D}, K=100 "
-                                                  "(one pass = 4 waves of user blocks; cfg4 = 13.2 such passes per GPU)", U4))
+                        item_cats=synth.make_item_categories(I4), adopt=True)
+            catalog.append(bench_catalog(e4, dev, f"cfg4: all {U4} users x {I4} recipes, D={D}, K=100", U4, reps=1,
+                                         warm_users=75_776))
             eng = e4
         catalog_launches = catalog_launches_cfg2 + eng.lib.fr_launch_count() - launches_c0
 
@@ -713,12 +946,15 @@ def run_ours(args, cfg, B):
                        "preroll_steps": preroll,
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (sharded path: see DESIGN.md)"},
             "clocks": clk, "gpu_launches": int(launches),
-            "roofline": roofline, "kernels": kern, "phases_ms": phases,
+            "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "phases_ms": phases,
+            "single_pass": fused,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
                     "feed": "reference dense feed (user_input,item_input,categories,user_one_hot_label), pinned, "
                             "host read of the loss every step; the copy of feed k+1 (fr_feed_prefetch, library copy "
-                            "stream) overlaps the kernels of step k; best of 3 runs of K steps", "mean_loss": e2e_loss,
-                    "runs": [v for v, _ in e2e_runs], "without_prefetch": e2e_serial},
+                            "stream) overlaps the kernels of step k; median of 3 runs of K steps", "mean_loss": e2e_loss,
+                    "runs": [v for v, _ in e2e_runs],
+                    "spread": (max(v for v, _ in e2e_runs) - min(v for v, _ in e2e_runs)) / e2e_val,
+                    "without_prefetch": e2e_serial},
             "e2e_compact": {"value": e2e_cval, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                             "feed": "ids only; dish_to_category / user labels resident on device"},
             "topk": {"metric": "sampled_topk_users_per_sec", "value": NU / (eval_ms * 1e-3), "unit": "users/s",
@@ -735,6 +971,10 @@ def run_ours(args, cfg, B):
             line["catalog_gpu_launches"] = int(catalog_launches)
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_cpu:
+            # cfg1 exactly (the reference's own CPU-runnable case), both arms
+            line["cfg1"] = {"workload": "cfg1: 10000 users x 5000 recipes x 95 labels, D=64, pointwise B=128, reference stream, Adam",
+                            "gpu_e2e": cfg1_gpu_leg(dev), "cpu_baseline": cfg1_cpu_leg()}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -752,6 +992,9 @@ def main():
     ap.add_argument("--no-p2p", action="store_true", help="N>1: stage exchanged rows and move them with NCCL all-to-alls instead "
                     "of storing them straight into peer memory (NVLink) from the gather / gradient kernels")
     ap.add_argument("--cfg3", action="store_true", help="100M users / 10M recipes (row-sharded, 8 GPUs: 96 GB of tables+slots per GPU)")
+    ap.add_argument("--fixed-tables", action="store_true", help="N>1: cfg2 tables divided over the ranks (round-1 behaviour) "
+                    "instead of a cfg2-sized shard per GPU (constant per-GPU work)")
+    ap.add_argument("--no-cfg3", action="store_true", help="N=8: skip the cfg3 leg (100M users / 10M recipes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-catalog", action="store_true", help="skip the full-catalog top-K legs")
     ap.add_argument("--learner", default="adam", help="adam (reference default) | adagrad | rmsprop | sgd")

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libfoodrec_b200.so")
-SOURCES = ["sort.cu", "train_fwd.cu", "train_seg.cu", "train_label.cu", "train_shard.cu", "eval.cu", "catalog.cu", "catalog_gemm.cu", "sampler.cu", "api.cu", "api_shard.cu"]
+SOURCES = ["sort.cu", "train_fwd.cu", "train_seg.cu", "train_shard.cu", "eval.cu", "catalog.cu", "catalog_gemm.cu", "sampler.cu", "api.cu", "api_shard.cu"]
 HEADERS = ["common.cuh", "internal.h", "train.cuh", "optim.cuh", "ctx.h", "catalog.cuh", "tc05.cuh",
            os.path.join("..", "..", "include", "foodrec_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -33,9 +33,27 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+def source_hash() -> str:
+    """sha256 over every source and header (names + bytes) and the compiler flags: what a .so was built from."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(sources() + [os.path.join(CSRC, x) for x in HEADERS]):
+        if os.path.exists(f):
+            h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+STAMP = LIB + ".stamp"        # source_hash() of the sources the in-tree .so was linked from (travels with it)
+LAST = {}                     # what the last build() call did: {"action": "compiled" | "reused", "hash": ..., "objects": n}
+
+
 def needs_build(lib=LIB) -> bool:
+    """The library is rebuilt unless it exists AND its stamp equals the hash of the current sources (mtimes do not
+    survive a snapshot; a stale or foreign .so must never be picked up silently)."""
     if not os.path.exists(lib):
         return True
+    if lib == LIB:
+        return not (os.path.exists(STAMP) and open(STAMP).read().strip() == source_hash())
     t = os.path.getmtime(lib)
     deps = sources() + [os.path.join(CSRC, h) for h in HEADERS]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
@@ -70,11 +88,19 @@ def _compile(out_lib, defines=(), verbose=False, tag="") -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    hsh = source_hash()
     if not force and not verbose and not needs_build():
+        LAST.update(action="reused", hash=hsh, lib=LIB)
         return LIB
-    if force:
-        shutil.rmtree(os.path.join(CSRC, "build"), ignore_errors=True)
-    return _compile(LIB, verbose=verbose)
+    if force or not os.path.exists(STAMP) or open(STAMP).read().strip() != hsh:
+        # objects are keyed by mtime inside one checkout only: sources that differ from the stamped build start clean
+        if force:
+            shutil.rmtree(os.path.join(CSRC, "build"), ignore_errors=True)
+    out = _compile(LIB, verbose=verbose)
+    with open(STAMP, "w") as f:
+        f.write(hsh + "\n")
+    LAST.update(action="compiled", hash=hsh, lib=LIB)
+    return out
 
 
 def build_variant(name: str, defines) -> str:

@@ -73,7 +73,6 @@ extern "C" int fr_create(const fr_config* cfg, fr_handle* out) {
   A(h->counts, S + 1); A(h->offs, S + 1); A(h->ent_key, E); A(h->ent_row, E); A(h->ent_coef, E); A(h->n_entries, 1);
   A(h->counters, 4); A(h->cat_pre, 4 * DV); A(h->mean_partials, 1024); A(h->out_internal, FR_OUT_COUNT);
   A(h->scan_tmp, S / 4096 + 2);
-  A(h->label_partial, (size_t)h->sm_count * cfg->num_labels * 5 * DV);
   h->lr_hist_cap = 1 << 16;
   A(h->lr_hist, (size_t)h->lr_hist_cap);
   A(h->cser, (size_t)h->lr_hist_cap * SERIES_TERMS);
@@ -153,8 +152,6 @@ extern "C" int fr_set_tables(fr_handle h, const fr_tables* t) {
   if (al & 15) return fail(h, FR_ERR_ARG, "table pointers must be 16-byte aligned");
   h->tab = *t;
   h->has_tables = true;
-  h->csr_max_labels = (t->user_label_off && t->user_label_idx)
-                          ? csr_max_count(t->user_label_off, h->cfg.num_users, reinterpret_cast<int32_t*>(h->n_entries), 0) : 0;
   return FR_OK;
 }
 
@@ -463,23 +460,11 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   }
 
   FR_MARK(FR_T_LABEL);
-  // 5. General_Memory (Write_Memory :201-215; reads pre-step R): shared-memory scatter with one owner warp per label
-  //    (train_label.cu); the sort-by-label segment reduce is the fallback for tables too wide for shared memory
+  // 5. General_Memory: label feed -> entries -> sort by label -> segment-reduce (reads pre-step R).
+  //    (Round 2 tried a shared-memory scatter with one owner warp per label instead -- no sort, no entry list: measured
+  //    354 us + 25 us against this pass's 254 us at 524k rows; see DESIGN.md "measured and rejected".)
   {
     l.mid = nullptr;
-    int n_parts = 1, Lp = h->mc.L;
-    const bool csr = !b->user_labels && h->csr_max_labels <= 8 && !getenv("FOODREC_LABEL_GENERAL");
-    if (!getenv("FOODREC_LABEL_SORT") && label_scatter_plan(h->mc.L, DV, h->sm_count, csr, &n_parts, &Lp)) {
-      LabelScatterParams sp{};
-      sp.G = (float4*)T.G; sp.R = (const float4*)T.R; sp.cat = h->cat_pre;
-      sp.items = items; sp.cats = cats; sp.cats_by_item = cats_by_item;
-      sp.users = users; sp.group = group; sp.S = S;
-      sp.user_labels = b->user_labels; sp.lab_off = T.user_label_off; sp.lab_idx = T.user_label_idx;
-      sp.ws_row = h->ws_row; sp.mc = h->mc; sp.partial = h->label_partial;
-      sp.n_entries = h->n_entries; sp.out = out; sp.n_parts = n_parts; sp.Lp = Lp;
-      launch_label_scatter(NV, sp, csr, l);
-      FR_CHECK_LAUNCH(h);
-    } else {
     LabelEmitParams ep{};
     ep.S = S; ep.group = group; ep.L = h->mc.L; ep.users = users;
     ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
@@ -502,7 +487,6 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     lp.cats_by_item = cats_by_item; lp.mc = h->mc;
     launch_label_pass(NV, c, lp, l);
     FR_CHECK_LAUNCH(h);
-    }
   }
 
   FR_MARK(FR_T_ITEM_CHUNK);

@@ -103,6 +103,19 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   return FR_OK;
 }
 
+extern "C" int fr_gather_user_rows(fr_handle h, const int32_t* users, int32_t n, float* out, fr_stream s) {
+  if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (n < 0 || (n > 0 && (!users || !out))) return fail(h, FR_ERR_ARG, "null argument");
+  if (n == 0) return FR_OK;
+  cudaStream_t st = (cudaStream_t)s;
+  int rc = shadow_sync(h, st); if (rc) return rc;
+  Launch l{h->sm_count, st, nullptr};
+  PeerPtrs none{}; none.world = 0;
+  launch_gather_rows((const float4*)h->tab.P, users, (uint32_t)n, 5 * h->mc.DV, (float4*)out, none, l, (uint32_t)h->cfg.num_users);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
 // ---------------------------------------------------------------- peer-memory exchange
 extern "C" int fr_shard_set_peers(fr_handle h, const fr_shard* sh, float* const* peer_rbuf, float* const* peer_rgrows) {
   int rc = shard_check(h, sh); if (rc) return rc;
@@ -139,7 +152,8 @@ extern "C" int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rr
     launch_item_catchup(h->NV, w.sortS.k[w.rs], (uint32_t)n, (float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R, T.last_R,
                         h->mc.DV, oc, l, w.n_valid);
   PeerPtrs none{}; none.world = 0;
-  launch_gather_rows((const float4*)T.R, rreq, (uint32_t)n, h->mc.DV, (float4*)rows, rows ? none : w.peer_rbuf, l);
+  launch_gather_rows((const float4*)T.R, rreq, (uint32_t)n, h->mc.DV, (float4*)rows, rows ? none : w.peer_rbuf, l,
+                     (uint32_t)h->cfg.num_items);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -205,20 +219,6 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   // General_Memory delta of this rank's rows -> packed (G itself is updated after the all-reduce)
   float* dG = packed + 4 + 4 * (size_t)h->mc.D;
   FR_CUDA(h, cudaMemsetAsync(dG, 0, 5 * (size_t)h->mc.L * h->mc.D * sizeof(float), st));
-  int n_parts = 1, Lp = h->mc.L;
-  const bool csr = !b->user_labels && h->csr_max_labels <= 8 && !getenv("FOODREC_LABEL_GENERAL");
-  if (!getenv("FOODREC_LABEL_SORT") && label_scatter_plan(h->mc.L, DV, h->sm_count, csr, &n_parts, &Lp)) {
-    LabelScatterParams sp{};
-    sp.G = (float4*)dG; sp.R = (const float4*)rbuf; sp.cat = h->cat_pre;
-    sp.items = w.slot_of_row; sp.cats = w.cats_row; sp.cats_by_item = 0;
-    sp.users = h->users_s; sp.group = w.group; sp.S = S;
-    sp.user_labels = b->user_labels; sp.lab_off = T.user_label_off; sp.lab_idx = T.user_label_idx;
-    sp.ws_row = h->ws_row; sp.mc = h->mc; sp.partial = h->label_partial;
-    sp.n_entries = h->n_entries; sp.out = h->out_internal; sp.n_parts = n_parts; sp.Lp = Lp;
-    launch_label_scatter(NV, sp, csr, l);
-    FR_CHECK_LAUNCH(h);
-    return FR_OK;
-  }
   LabelEmitParams ep{};
   ep.S = S; ep.group = w.group; ep.L = h->mc.L; ep.users = h->users_s;
   ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
@@ -305,6 +305,7 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   FR_MARK(FR_T_LABEL);
   if (write_personal && S > 0) {
     if (w.fused) { rc = shadow_sync(h, st); if (rc) return rc; }     // the personal pass works on the caller's table
+    c.only_if_scaled = nullptr;                                      // (it always runs, whatever the clip did)
     const size_t need = (size_t)S / 32 + 2;
     if (need > h->pieces_personal_chunks) {
       if (h->pieces_personal) { FR_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->pieces_personal); h->pieces_personal = nullptr; }

@@ -38,8 +38,6 @@ struct fr_ctx {
   uint32_t* counters = nullptr;        // [0] unique users, [1] unique recipes, [2]/[3] long chains (label / recipe pass)
   uint4* long_list = nullptr; uint32_t long_cap = 0;   // work list of seg_combine_long_kernel (train.cuh)
   float4* cat_pre = nullptr;
-  int csr_max_labels = 0;              // labels of the busiest user in tables.user_label_* (fr_set_tables)
-  float4* label_partial = nullptr;     // per-CTA General_Memory partials of label_scatter_kernel [sm_count][L*5*DV]
   float* lr_hist = nullptr; int64_t lr_hist_cap = 0;
   double* cser = nullptr;          // LAZY_SERIES coefficient table [lr_hist_cap * SERIES_TERMS]
   double* mean_partials = nullptr;

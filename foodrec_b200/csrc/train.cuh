@@ -82,24 +82,6 @@ struct LabelPolParams {
   ModelConsts mc;
 };
 
-// General_Memory write as a shared-memory scatter (train_label.cu); the sort-by-label pass above remains for tables
-// whose [L][4][D] accumulator does not fit shared memory even in 8 label ranges.
-struct LabelScatterParams {
-  float4* G;                       // [L,5,DV], += (General_Memory, or the dG block of the packed all-reduce buffer)
-  const float4 *R, *cat;           // pre-step recipe rows / Category_Embedding snapshot
-  const int32_t* items; const float4* cats; int cats_by_item;
-  const int32_t* users; int group, S;
-  const float* user_labels; const int32_t *lab_off, *lab_idx;
-  const float* ws_row;
-  ModelConsts mc;
-  float4* partial;                 // [CTAs per label range][L*5*DV]
-  uint32_t* n_entries; float* out; // non-zeros of the label feed -> out[FR_OUT_LABEL_ENTRIES]
-  int n_parts, Lp;                 // label ranges, labels per range
-};
-bool label_scatter_plan(int L, int DV, int sm_count, bool csr, int* n_parts, int* Lp);
-void launch_label_scatter(int NV, LabelScatterParams p, bool csr, const Launch& l);
-int csr_max_count(const int32_t* off, int64_t n, int32_t* scratch, cudaStream_t st);
-
 struct LabelEmitParams {
   int S, group, L; const int32_t* users;
   const float* user_labels; const int32_t *lab_off, *lab_idx;
@@ -157,7 +139,8 @@ void launch_shard_heads(const ShardPlanParams& p, const Launch& l);
 void launch_shard_fill(const ShardPlanParams& p, const Launch& l);
 void launch_serve_keys(const int32_t* rreq, uint32_t n, uint32_t items_per_rank, uint32_t* keys, uint32_t* n_valid,
                        const Launch& l);
-void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const PeerPtrs& peers, const Launch& l);
+void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const PeerPtrs& peers, const Launch& l,
+                        uint32_t n_table);
 void launch_add_inplace(float4* dst, const float4* src, int64_t n4, const Launch& l);
 void launch_mean(const float4* x, int64_t n4, double* partials, float* out_slot, double count, const Launch& l);
 void launch_write_counters(const uint32_t* counters, float* out, const Launch& l);

@@ -83,7 +83,7 @@ void launch_serve_keys(const int32_t* rreq, uint32_t n, uint32_t items_per_rank,
 // (source s, j) is stored straight into rank s's receive buffer over NVLink (fused gather + exchange).
 __global__ void __launch_bounds__(FR_THREADS)
 gather_rows_kernel(const float4* __restrict__ R, const int32_t* __restrict__ rreq, uint32_t n, int DV,
-                   float4* __restrict__ out, const PeerPtrs peers) {
+                   float4* __restrict__ out, const PeerPtrs peers, uint32_t n_table) {
   const int lane = threadIdx.x & 31;
   const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5), nw = gridDim.x * FR_WARPS_PER_BLOCK;
   for (uint32_t r = gw; r < n; r += nw) {
@@ -94,15 +94,15 @@ gather_rows_kernel(const float4* __restrict__ R, const int32_t* __restrict__ rre
       dst = peers.dst[s] + ((size_t)peers.rank * peers.cap + j) * DV;
     }
     for (int i = lane; i < DV; i += 32)
-      dst[i] = id >= 0 ? R[(size_t)id * DV + i] : f4zero();
+      dst[i] = (uint32_t)id < n_table ? R[(size_t)id * DV + i] : f4zero();      // (-1 = empty request; never out of the table)
   }
 }
 void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const PeerPtrs& peers,
-                        const Launch& l) {
+                        const Launch& l, uint32_t n_table) {
   if (n == 0) return;
   int grid = (int)((n + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
   if (grid > l.sm_count * 16) grid = l.sm_count * 16;
-  gather_rows_kernel<<<grid, FR_THREADS, 0, l.st>>>(R, rreq, n, DV, out, peers); ++g_launches;
+  gather_rows_kernel<<<grid, FR_THREADS, 0, l.st>>>(R, rreq, n, DV, out, peers, n_table); ++g_launches;
 }
 
 __global__ void add_inplace_kernel(float4* __restrict__ dst, const float4* __restrict__ src, int64_t n4) {

@@ -202,8 +202,13 @@ class ShardedEngine:
 
     def catalog_query_rows(self, users_local):
         """This rank's query users as dense [n,5,D] rows (what the all-gather moves)."""
-        self.e.flush()
-        return self.e.P[self.e._i32(users_local).long()].contiguous()
+        e = self.e
+        e.flush()
+        u = e._i32(users_local)
+        rows = torch.empty((u.numel(), 5, e.D), dtype=torch.float32, device=e.device)
+        L.check(e.handle, e.lib.fr_gather_user_rows(e.handle, _ptr(u), u.numel(), _ptr(rows), e._stream()))
+        e._keep = [u]
+        return rows
 
     def catalog_local(self, P_rows_all, K):
         """Top-K of THIS rank's recipe shard for every gathered query row, ids global."""

@@ -63,8 +63,7 @@ typedef struct {
   int32_t learner;      /* FR_SGD.. */
   int32_t adam_mode;    /* FR_ADAM_* */
   int32_t max_rows;     /* capacity: item rows per step (B pointwise, 2B BPR) */
-  int32_t max_label_entries; /* capacity: non-zeros of the label feed per step (sort-by-label fallback pass only: the
-                                shared-memory scatter that normally writes General_Memory has no capacity) */
+  int32_t max_label_entries; /* capacity: non-zeros of the label feed per step */
   float lr;                             /* args.lr (global_step never advances: lr is constant, :224-226) */
   float high_level_score_coefficient;   /* a, :17 ; low coefficient = 1-a, :96 */
   float beta_1, beta_2, alpha;          /* write coefficients :115,:140,:196 */
@@ -257,6 +256,9 @@ int fr_catalog_prepare(fr_handle h, const fr_catalog_opts* opts, const float* it
  * fp64 or NULL.  Asynchronous on the stream. */
 int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P_rows, int32_t n_users, int32_t K,
                     int32_t id_mul, int32_t id_add, int32_t* out_ids, double* out_scores, fr_stream s);
+/* Dense copies of Personal_Memory rows: out[k] = P[users[k]] ([n,5,D], device) -- the query rows a rank contributes to
+ * the all-gather of the item-sharded top-K (a user id outside the table yields a zero row). */
+int fr_gather_user_rows(fr_handle h, const int32_t* users, int32_t n, float* out, fr_stream s);
 /* Item-sharded merge: ids/scores [n_lists, n_users, K] (each list sorted, -1 padded) ->
  * the K best of the union by (score desc, id asc).  n_lists*K <= 4096. */
 int fr_catalog_merge(fr_handle h, const int32_t* ids, const double* scores, int32_t n_lists, int32_t n_users,

@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 def engine(p, **kw):
     from foodrec_b200 import Engine, Hyper
     hk = {k: kw.pop(k) for k in list(kw) if k in ("learner", "lr", "adam_beta1", "adam_beta2")}
+    kw.setdefault("single_pass", False)
     return Engine(Hyper(**hk), p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=2048, max_label_entries=2048 * p.L,
                   item_cats=p.item_cats, user_labels=p.user_labels, **kw)
 

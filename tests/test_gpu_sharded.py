@@ -14,11 +14,13 @@ from tests.util import Problem, assert_close
 pytestmark = pytest.mark.gpu
 
 
-def build(p, W, learner, adam_mode, max_rows=2048, cap=None):
+def build(p, W, learner, adam_mode, max_rows=2048, cap=None, single_pass=None):
+    """single_pass None: the engines' default (on for lazy Adam: the N-rank step then runs the single-pass kernel
+    before the all-reduce and commits / redoes the update after it); False: the two-pass phases."""
     from foodrec_b200 import Engine, Hyper
     h = Hyper(learner=learner, lr=0.01)
     single = Engine(h, p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=max_rows, adam_mode=adam_mode,
-                    max_label_entries=max_rows * p.L)
+                    max_label_entries=max_rows * p.L, single_pass=False if single_pass is False else None)
     rows, cols = np.nonzero(p.user_labels)
     cnt = np.bincount(rows, minlength=p.U)
     off = np.zeros(p.U + 1, np.int32); off[1:] = np.cumsum(cnt)
@@ -28,7 +30,7 @@ def build(p, W, learner, adam_mode, max_rows=2048, cap=None):
             h, sharded.shard_rows(p.tb.P, r, W), sharded.shard_rows(p.tb.R, r, W), p.tb.Cat, p.tb.G, r, W,
             max_rows=max_rows, cap=cap, adam_mode=adam_mode, item_cats_global=p.item_cats,
             user_label_csr_local=sharded.shard_label_csr(off, cols.astype(np.int32), r, W, p.U),
-            max_label_entries=max_rows * p.L))
+            max_label_entries=max_rows * p.L, single_pass=single_pass))
     return single, engs
 
 
@@ -46,12 +48,15 @@ def gather(engs, p):
 
 
 @pytest.mark.parametrize("W", [2, 4])
-@pytest.mark.parametrize("learner,adam_mode,bpr", [("sgd", "dense", False), ("adagrad", "dense", True),
-                                                  ("adam", "dense", False), ("adam", "lazy_exact", True),
-                                                  ("adam", "lazy", True), ("adam", "lazy", False)])
-def test_sharded_equals_unsharded(W, learner, adam_mode, bpr):
+@pytest.mark.parametrize("learner,adam_mode,bpr,single_pass", [
+    ("sgd", "dense", False, None), ("adagrad", "dense", True, None), ("adam", "dense", False, None),
+    ("adam", "lazy_exact", True, None), ("adam", "lazy", True, None), ("adam", "lazy", False, None),
+    ("adam", "lazy", True, False), ("adam", "lazy_exact", False, False)])
+def test_sharded_equals_unsharded(W, learner, adam_mode, bpr, single_pass):
     p = Problem(403, 257, 9, 64, seed=61)            # sizes not divisible by W: padded shards
-    single, engs = build(p, W, learner, adam_mode)
+    single, engs = build(p, W, learner, adam_mode, single_pass=single_pass)
+    if learner == "adam" and adam_mode != "dense":
+        assert all(g.e.single_pass == (single_pass is None) for g in engs)
     run = sharded.LocalRunner(engs)
     for s in range(5):
         B = 300
