@@ -936,36 +936,13 @@ user_fused_kernel(const SegCommon c, const FusedUserPol<NV, OPT> pol) {
     const bool from_prev = !(hm & 1u);
     const bool to_next = has_next && nextKey == lastKey;
     if (c.uniq_counter && lane == 0) atomicAdd(c.uniq_counter, (uint32_t)__popc(hm));
-    // A warp holds one user's P, m, v at a time (60 of its 128 registers), so its demand loads are a dependent chain
-    // and with 16 warps per SM the kernel is latency-bound (ncu: long_scoreboard is the top stall, DRAM at 65 %).  The
-    // state rows of the runs AHEAD are therefore pulled into L2 by TMA bulk prefetches (no registers held): run 2 of
-    // the chunk now, and the run after next at the start of every run.
-    auto prefetch_run = [&](int pos) {
-      const uint32_t pk = __shfl_sync(FR_FULL, key, pos);
-      const int pl = __shfl_sync(FR_FULL, e_last, pos);
-      const int psh = (pl >> 30) & 1;
-      const size_t off = (size_t)pk * 5 * DV;
-      const uint32_t bytes = 5u * (uint32_t)DV * 16u;
-      prefetch_l2_warp(p.P[psh] + off, bytes, lane);
-      prefetch_l2_warp(p.m[psh] + off, bytes, (lane + 31) & 31);
-      prefetch_l2_warp(p.v[psh] + off, bytes, (lane + 30) & 31);
-    };
-#ifndef FR_NO_FUSED_PREFETCH
-    {
-      const uint32_t r1 = hm & ~1u;                            // heads after position 0
-      if (r1) prefetch_run(__ffs(r1) - 1);
-    }
-#endif
+    // (Measured and rejected: TMA bulk prefetches of the NEXT runs' P / m / v into L2 -- the kernel is latency-bound,
+    //  16 warps per SM each holding one user's state in 60 registers -- made it slower, 0.88 vs 0.80 ms: the prefetch
+    //  traffic competes with the demand loads for the same DRAM queues; same finding as FR_PREFETCH_SEG in round 1.)
     int e0 = 0;
     while (e0 < cnt) {
       const uint32_t rest = (e0 >= 31) ? 0u : (hm & ~((2u << e0) - 1u));
       const int e1 = rest ? (__ffs(rest) - 1) : cnt;
-#ifndef FR_NO_FUSED_PREFETCH
-      {
-        const uint32_t r2 = rest & (rest - 1u);                // the head after the next one
-        if (r2) prefetch_run(__ffs(r2) - 1);
-      }
-#endif
       const bool contained = ((e0 > 0) || !from_prev) && ((e1 < cnt) || !to_next);
       const uint32_t k = __shfl_sync(FR_FULL, key, e0);
       typename FusedUserPol<NV, OPT>::State st;

@@ -6,6 +6,8 @@
 
 `launches` = the `--metrics gpu__time_duration.sum` pass (cold-cache, serialised: read SHARES).
 `full`     = one `--set full` capture; keeps the metrics the roofline argument needs.
+`traffic`  = profiles/ncu_traffic.json (DRAM bytes per launch of each captured kernel, stamped with the source hash):
+  python profiles/summarize.py traffic profiles/ncu_traffic.json gpurun_out/a.ncu-rep gpurun_out/b.ncu-rep=cfg2 ...
 """
 import collections
 import csv
@@ -61,8 +63,47 @@ def full(path):
             w.writerow([k, rows[1][i]] + [r[i] for r in rows[2:]])
 
 
+def short_name(k):
+    """`void fr::seg_chunk_kernel<fr::UserPol<1, 3>>(...)` -> `seg_chunk_kernel<UserPol>`; other kernels: bare name."""
+    import re
+    k = k.replace("void ", "").replace("fr::", "").split("(")[0]
+    m = re.match(r"(seg_\w+)<(\w+)", k)
+    return f"{m.group(1)}<{m.group(2)}>" if m else k.split("<")[0]
+
+
+def traffic(out_path, reps):
+    """profiles/ncu_traffic.json from `ncu --set full` captures: per kernel (first launch in each capture) the DRAM
+    bytes read + written, stamped with the hash of the sources of the CURRENT tree (bench.py only uses the file while
+    that hash matches the library it runs).  A capture argument may be `file.ncu-rep=suffix`: the suffix is appended to
+    the kernel name (`catalog_gemm_kernel:cfg2`)."""
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from foodrec_b200 import _build
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    kernels = {}
+    for rep in reps:
+        rep, _, suffix = rep.partition("=")
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        H, U = rows[0], rows[1]
+        ir, iw, ik = H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("Kernel Name")
+        it = H.index("gpu__time_duration.sum")
+        for r in rows[2:]:
+            name = short_name(r[ik]) + (":" + suffix if suffix else "")
+            if name in kernels:
+                continue
+            b = float(r[ir].replace(",", "")) * unit[U[ir]] + float(r[iw].replace(",", "")) * unit[U[iw]]
+            kernels[name] = {"dram_bytes": b, "dram_read": float(r[ir].replace(",", "")) * unit[U[ir]],
+                             "duration": r[it] + " " + U[it], "capture": os.path.basename(rep)}
+    json.dump({"build": _build.source_hash(), "kernels": kernels}, open(out_path, "w"), indent=1)
+    print(json.dumps(kernels, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], float(sys.argv[3]))
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3:])
     else:
         full(sys.argv[2])

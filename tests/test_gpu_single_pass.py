@@ -131,9 +131,12 @@ def test_readers_and_personal_steps_see_current_rows():
     for e in (a, b, c):
         step(e, g, False)
     ta, tb, tc = a.tables(), b.tables(), c.tables()
+    # (a test of WHICH rows every reader sees, not of precision: eight lr = 0.01 Adam steps apart, the two step
+    #  implementations agree to ~1e-5 on all but a few ill-conditioned entries -- see assert_close_adam; a stale row
+    #  would be off by the size of an update, 1e-2)
     for k in ("P", "R", "Cat", "G"):
-        assert_close(ta[k], tb[k], rtol=5e-5, what=k)
-        assert_close(tc[k], ta[k], rtol=5e-5, what="resumed " + k)
+        assert_close(ta[k], tb[k], rtol=2e-4, what=k)
+        assert_close(tc[k], ta[k], rtol=2e-4, what="resumed " + k)
     a.close(); b.close(); c.close()
 
 
