@@ -444,9 +444,9 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
     Cat = torch.randn((4, D), device=dev, generator=g2) * 0.1; G = torch.randn((Lb, 5, D), device=dev, generator=g2) * 0.1
     item_cats = synth.make_item_categories(I)
     lab = synth.make_user_label_csr(Ul, Lb, seed=synth.BASE_SEED + 200 + rank)
-    eng = ShardedEngine(Hyper(learner=args.learner, lr=0.001), P, R, Cat, G, rank, world, device=dev, max_rows=2 * B,
+    eng = ShardedEngine(Hyper(learner=args.learner, lr=0.001), P, R, Cat, G, rank, world, device=dev, max_rows=2 * B + 16384,
                         adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab, adopt=True,
-                        single_pass=single_pass)
+                        single_pass=single_pass)       # (+16384 rows: an un-routed batch lands B +- a few hundred groups per rank)
     del P, R
     run = DistRunner(eng)
     if p2p:
@@ -546,6 +546,40 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
         return world * B * steps / float(tt.item()), loss
     e2e_ids, loss_ids = e2e(False)
     e2e_dense, _ = e2e(True)
+    # un-routed stream: every rank receives B triples of ARBITRARY users (global ids); fr_shard_route buckets them by
+    # owner, one all-to-all moves them, fr_shard_unroute compacts -- then the same step.  Device-timed, max over ranks.
+    gb = []
+    for k in range(NB):
+        rng = np.random.default_rng(7000 + 100 * rank + k)
+        users = rng.integers(0, Ul * world, B).astype(np.int32)
+        pos = synth.zipf_items(rng, I, B)
+        neg = rng.integers(0, I, B).astype(np.int32); neg[neg == pos] = (neg[neg == pos] + 1) % I
+        gb.append((torch.as_tensor(users).to(dev), torch.as_tensor(np.stack([pos, neg], 1).reshape(-1).copy()).to(dev)))
+
+    def ustep(k, evs=None):
+        u, it = gb[k % NB]
+        if evs is not None:
+            a = torch.cuda.Event(enable_timing=True); a.record()
+        run.set_batch_unrouted(L.FR_BPR, u, it, global_batch=world * B)
+        if evs is not None:
+            b_ = torch.cuda.Event(enable_timing=True); b_.record(); evs.append((a, b_))
+        return run.step()
+    for k in range(3):
+        ustep(k)
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize()
+    u0.record()
+    revs = []
+    for k in range(steps):
+        ustep(k, revs)
+    u1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    tt = torch.tensor([u0.elapsed_time(u1)], device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ums = float(tt.item())
+    route_ms = sum(a.elapsed_time(b_) for a, b_ in revs) / max(len(revs), 1)
+    unrouted = {"value": world * B * steps / (ums / 1e3), "unit": UNIT, "ms_per_step": ums / steps, "route_ms_per_step_rank0": route_ms,
+                "exchange_bytes_per_gpu": int(eng._rsend.numel() * 4 * (world - 1) / world),
+                "note": "samples arrive on a random rank: bucket by owner + ONE all-to-all + compaction (fr_shard_route / "
+                        "fr_shard_unroute) inside the timed region; the routed size is read on the host every step"}
     res = {
         "label": label, "value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "launches": int(launches),
         "window": (t_begin, t_end), "single_pass": fused, "p2p": p2p, "cap": eng.cap,
@@ -558,7 +592,7 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
                         "loss read every step -- the same feed as the N=1 e2e"},
         "e2e_compact": {"value": e2e_ids, "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                         "feed": "ids only (user, pos, neg); side tables resident", "last_loss": loss_ids},
-        "uniq_users_per_step": uu, "uniq_items_per_step": ui, "overflow_flag": float(v[L.FR_OUT_OVERFLOW]),
+        "unrouted": unrouted, "uniq_users_per_step": uu, "uniq_items_per_step": ui, "overflow_flag": float(v[L.FR_OUT_OVERFLOW]),
     }
     return res, eng, run
 
@@ -684,7 +718,7 @@ def run_sharded(args, cfg, B):
             "clocks": clk, "gpu_launches": main["launches"], "roofline": main["roofline"], "roofline_step": main["roofline_step"],
             "single_pass": main["single_pass"], "shard_phases_ms": main["shard_phases_ms"],
             "update_phase_kernels_ms": main["update_phase_kernels_ms"], "self_check": check,
-            "e2e": main["e2e"], "e2e_compact": main["e2e_compact"],
+            "e2e": main["e2e"], "e2e_compact": main["e2e_compact"], "unrouted": main["unrouted"],
             "uniq_users_per_step": main["uniq_users_per_step"], "uniq_items_per_step": main["uniq_items_per_step"],
             "overflow_flag": main["overflow_flag"], "cfg3": cfg3_line}
         print(json.dumps(line))

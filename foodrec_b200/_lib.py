@@ -93,6 +93,10 @@ _PROTOS = {
     "fr_sample_negatives": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "fr_philox4x32_10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "fr_shard_packed_len": (C.c_int64, [C.c_void_p]),
+    "fr_shard_route_block": (C.c_int64, [C.POINTER(fr_batch), C.c_int32]),
+    "fr_shard_route": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fr_shard_unroute": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fr_shard_set_peers": (C.c_int, [C.c_void_p, C.POINTER(fr_shard), C.c_void_p, C.c_void_p]),
     "fr_shard_plan": (C.c_int, [C.c_void_p, C.POINTER(fr_batch), C.POINTER(fr_shard), C.c_void_p, C.c_void_p]),
     "fr_shard_serve": (C.c_int, [C.c_void_p, C.POINTER(fr_shard), C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -103,6 +103,57 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
   return FR_OK;
 }
 
+// ---------------------------------------------------------------- routing of an un-routed batch
+extern "C" int64_t fr_shard_route_block(const fr_batch* b, int32_t rcap) {
+  if (!b || rcap < 1) return 0;
+  const int group = b->mode == FR_BPR ? 2 : 1;
+  return (int64_t)rcap * (1 + group + (b->mode == FR_POINTWISE ? 1 : 0));
+}
+
+extern "C" int fr_shard_route(fr_handle h, const fr_batch* b, int32_t world, int32_t rcap, int32_t* send, float* out_flag,
+                              fr_stream s) {
+  if (!h) return FR_ERR_ARG;
+  if (!b || !send || world < 1 || world > 8 || rcap < 1) return fail(h, FR_ERR_ARG, "bad fr_shard_route arguments");
+  if (b->mode != FR_POINTWISE && b->mode != FR_BPR) return fail(h, FR_ERR_ARG, "bad mode %d", b->mode);
+  const int B = b->n_groups, group = b->mode == FR_BPR ? 2 : 1;
+  if (B < 0 || (int64_t)B * group > h->cfg.max_rows) return fail(h, FR_ERR_ARG, "batch exceeds max_rows=%d", h->cfg.max_rows);
+  if (B > 0 && (!b->users || !b->items || (b->mode == FR_POINTWISE && !b->labels))) return fail(h, FR_ERR_ARG, "users/items/labels are required");
+  int rc;
+  if ((rc = shard_ensure(h, (size_t)B * group, 0))) return rc;
+  cudaStream_t st = (cudaStream_t)s;
+  Launch l{h->sm_count, st, nullptr};
+  auto& w = h->sh;
+  const int64_t blk = fr_shard_route_block(b, rcap);
+  FR_CUDA(h, cudaMemsetAsync(send, 0xff, (size_t)world * blk * sizeof(int32_t), st));
+  FR_CUDA(h, cudaMemsetAsync(w.owner_counts, 0, 8 * sizeof(uint32_t), st));
+  if (B == 0) return FR_OK;
+  float* flag = out_flag ? out_flag : h->out_internal + FR_OUT_OVERFLOW;
+  launch_route_keys(b->users, B, world, w.okeys, w.owner_counts, l);
+  const int r = radix_sort_pairs(h->sortI, w.okeys, (uint32_t)B, nullptr, 3, st, h->sm_count);
+  launch_route_fill(b->users, b->items, b->mode == FR_POINTWISE ? b->labels : nullptr, B, world, group, rcap, h->sortI.k[r],
+                    h->sortI.v[r], w.owner_counts, send, flag, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
+extern "C" int fr_shard_unroute(fr_handle h, int32_t mode, int32_t world, int32_t rcap, const int32_t* recv, int32_t cap_out,
+                                int32_t* users, int32_t* items, float* labels, int32_t* n_out, float* out_flag, fr_stream s) {
+  if (!h) return FR_ERR_ARG;
+  if (!recv || !users || !items || !n_out || world < 1 || world > 8 || rcap < 1 || cap_out < 1) return fail(h, FR_ERR_ARG, "bad fr_shard_unroute arguments");
+  if (mode == FR_POINTWISE && !labels) return fail(h, FR_ERR_ARG, "labels buffer required in pointwise mode");
+  int rc;
+  if ((rc = shard_ensure(h, 0, 0))) return rc;
+  cudaStream_t st = (cudaStream_t)s;
+  Launch l{h->sm_count, st, nullptr};
+  const int group = mode == FR_BPR ? 2 : 1;
+  const int blk = rcap * (1 + group + (mode == FR_POINTWISE ? 1 : 0));
+  float* flag = out_flag ? out_flag : h->out_internal + FR_OUT_OVERFLOW;
+  launch_route_unpack(recv, world, blk, rcap, group, mode == FR_POINTWISE, h->sh.owner_counts, cap_out, users, items, labels,
+                      n_out, flag, l);
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
 extern "C" int fr_gather_user_rows(fr_handle h, const int32_t* users, int32_t n, float* out, fr_stream s) {
   if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
   if (n < 0 || (n > 0 && (!users || !out))) return fail(h, FR_ERR_ARG, "null argument");

@@ -152,73 +152,66 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       b0 = warp_sum(t0); b1 = warp_sum(t1); b2 = warp_sum(t2); b3 = warp_sum(t3);
       __syncwarp();
     }
-    // EIGHT LANES PER CANDIDATE.  Round 1 gave every lane its own candidate row to walk: no reduction, but each 16-byte
-    // load of a warp then touched 32 different 128-byte lines -- 32 L1 tag wavefronts per instruction, and the kernel
-    // sat at the L1's one-wavefront-per-cycle limit (ncu: 2.9 G instructions, DRAM at 17 %, long-scoreboard stalls)
-    // with L1 thrashing on 32 rows x 2 slots per warp.  Now a group of 8 lanes reads one candidate row as four full
-    // lines (lane `sub` takes float4 sub, sub+8, ...): 4 wavefronts per load instruction instead of 32, every byte
-    // of a fetched line is used at once, and a score costs one 3-step shuffle reduction per FOUR candidates.  Two
-    // rounds (8 candidates, 8 row loads per lane) are in flight together.
-    {
-      const int grp = lane >> 3, sub = lane & 7;
-      const int nrounds = (nc + 3) >> 2;
-      for (int r0 = 0; r0 < nrounds; r0 += 2) {
-        float acc[2]; float4 mk[2]; int cj[2]; bool ok[2];
-        const float4* rp[2];
+    // two slots per walk: the shared-memory reads of the user rows serve both candidates and twice as many recipe
+    // row loads are in flight per lane.
+    // (Round 2 measured an alternative -- eight lanes per candidate row, i.e. four full 128-byte lines per load
+    //  instruction instead of 32 partial ones, one 3-step shuffle reduction per four candidates: 9.4 ms per 1M users
+    //  against this form's 7.5 ms; the extra shuffles and shared-memory reads cost more than the coalescing saves.)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = 4 * (r0 + h) + grp;                      // this group's candidate in round r0 + h
-          const int src = j & 31, slot = (j >> 5);               // (4 | 32: the four groups of a round share the slot)
-          int idj = -1; float4 mj = make_float4(1.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int q = 0; q < SLOTS; ++q) {
-            const int t = __shfl_sync(FR_FULL, id[q], src);
-            const float4 tm = shfl4(mq[q], src);
-            if (q == slot) { idj = t; mj = tm; }
-          }
-          ok[h] = (r0 + h) < nrounds && j < nc && idj >= 0;
-          cj[h] = j; mk[h] = mj; acc[h] = 0.f;
-          rp[h] = R + (size_t)(ok[h] ? idj : 0) * DV;
+    for (int q = 0; q < SLOTS; q += 2) {
+      if (q * 32 >= nc) break;
+      const bool vA = id[q] >= 0, vB = id[q + 1] >= 0;
+      const float4 mA = mq[q], mB = mq[q + 1];
+      const float4* rpA = R + (size_t)(vA ? id[q] : 0) * DV;
+      const float4* rpB = R + (size_t)(vB ? id[q + 1] : 0) * DV;
+      float accA = 0.f, accB = 0.f;
+      if ((q + 1) * 32 < nc) {
+#pragma unroll 4
+        for (int i = 0; i < DV; ++i) {
+          const float4 ra = __ldg(rpA + i), rb = __ldg(rpB + i);
+          const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
+          float4 za, zb;
+          za.x = mA.x * p1.x + mA.y * p2.x + mA.z * p3.x + mA.w * p4.x;
+          za.y = mA.x * p1.y + mA.y * p2.y + mA.z * p3.y + mA.w * p4.y;
+          za.z = mA.x * p1.z + mA.y * p2.z + mA.z * p3.z + mA.w * p4.z;
+          za.w = mA.x * p1.w + mA.y * p2.w + mA.z * p3.w + mA.w * p4.w;
+          zb.x = mB.x * p1.x + mB.y * p2.x + mB.z * p3.x + mB.w * p4.x;
+          zb.y = mB.x * p1.y + mB.y * p2.y + mB.z * p3.y + mB.w * p4.y;
+          zb.z = mB.x * p1.z + mB.y * p2.z + mB.z * p3.z + mB.w * p4.z;
+          zb.w = mB.x * p1.w + mB.y * p2.w + mB.z * p3.w + mB.w * p4.w;
+          accA += dot4(za, ra); accB += dot4(zb, rb);
         }
-        for (int i0 = 0; i0 < DV; i0 += 8) {
-          const int i = i0 + sub;
-          if (i < DV) {
-            const float4 ra = __ldg(rp[0] + i), rb = __ldg(rp[1] + i);
-            const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
-            float4 za, zb;
-            za.x = mk[0].x * p1.x + mk[0].y * p2.x + mk[0].z * p3.x + mk[0].w * p4.x;
-            za.y = mk[0].x * p1.y + mk[0].y * p2.y + mk[0].z * p3.y + mk[0].w * p4.y;
-            za.z = mk[0].x * p1.z + mk[0].y * p2.z + mk[0].z * p3.z + mk[0].w * p4.z;
-            za.w = mk[0].x * p1.w + mk[0].y * p2.w + mk[0].z * p3.w + mk[0].w * p4.w;
-            zb.x = mk[1].x * p1.x + mk[1].y * p2.x + mk[1].z * p3.x + mk[1].w * p4.x;
-            zb.y = mk[1].x * p1.y + mk[1].y * p2.y + mk[1].z * p3.y + mk[1].w * p4.y;
-            zb.z = mk[1].x * p1.z + mk[1].y * p2.z + mk[1].z * p3.z + mk[1].w * p4.z;
-            zb.w = mk[1].x * p1.w + mk[1].y * p2.w + mk[1].z * p3.w + mk[1].w * p4.w;
-            acc[0] += dot4(za, ra); acc[1] += dot4(zb, rb);
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float v = acc[h];
-          v += __shfl_xor_sync(FR_FULL, v, 4); v += __shfl_xor_sync(FR_FULL, v, 2); v += __shfl_xor_sync(FR_FULL, v, 1);
-          const float4 m = mk[h];
-          const float rn = __frcp_rn(((m.x + m.y) + m.z) + m.w);       // x * (1/n): exact for n = 1, 2, 4
-          const float high = (((m.x * b0 + m.y * b1) + m.z * b2) + m.w * b3) * rn;     // :67-79
-          const float sv = a * high + oma * (v * rn);                                  // :82-96
-          // hand the score to the lane that owns candidate j (lane j & 31, slot j >> 5): it sits in group lane - base
-          const int base = (4 * (r0 + h)) & 31, slot = (4 * (r0 + h)) >> 5;
-          const int gsel = (lane - base) & 31;
-          const float got = __shfl_sync(FR_FULL, sv, (gsel & 3) * 8);
-          const int jmine = slot * 32 + lane;
-          if (gsel < 4 && (r0 + h) < nrounds && jmine < nc) {
-#pragma unroll
-            for (int q = 0; q < SLOTS; ++q)
-              if (q == slot && id[q] >= 0) { sc[q] = got; if (scores_out) scores_out[(size_t)w * stride + jmine] = got; }
-          }
-        }
+      } else {
+        float acc1 = 0.f;
+        auto step = [&](int i, float& acc) {
+          const float4 r = __ldg(rpA + i);
+          const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
+          float4 z;
+          z.x = mA.x * p1.x + mA.y * p2.x + mA.z * p3.x + mA.w * p4.x;
+          z.y = mA.x * p1.y + mA.y * p2.y + mA.z * p3.y + mA.w * p4.y;
+          z.z = mA.x * p1.z + mA.y * p2.z + mA.z * p3.z + mA.w * p4.z;
+          z.w = mA.x * p1.w + mA.y * p2.w + mA.z * p3.w + mA.w * p4.w;
+          acc += dot4(z, r);
+        };
+        const int DVe = DV & ~1;
+#pragma unroll 4
+        for (int i = 0; i < DVe; i += 2) { step(i, accA); step(i + 1, acc1); }
+        if (DV & 1) step(DV - 1, accA);
+        accA += acc1;
+      }
+      {
+        const float rn = __frcp_rn(((mA.x + mA.y) + mA.z) + mA.w);     // x * (1/n): exact for n = 1, 2, 4
+        const float high = (((mA.x * b0 + mA.y * b1) + mA.z * b2) + mA.w * b3) * rn;   // :67-79
+        const float s = a * high + oma * (accA * rn);                                  // :82-96
+        if (vA) { sc[q] = s; if (scores_out) scores_out[(size_t)w * stride + q * 32 + lane] = s; }
+      }
+      {
+        const float rn = __frcp_rn(((mB.x + mB.y) + mB.z) + mB.w);
+        const float high = (((mB.x * b0 + mB.y * b1) + mB.z * b2) + mB.w * b3) * rn;
+        const float s = a * high + oma * (accB * rn);
+        if (vB) { sc[q + 1] = s; if (scores_out) scores_out[(size_t)w * stride + (q + 1) * 32 + lane] = s; }
       }
     }
-
     // dict semantics (evaluate.py:60-61): the first position of an id survives and takes the score of its last
     // occurrence.  Repeated ids are rare (0.65 % of users at 51 of 200k), so they are DETECTED first -- match.any
     // inside a slot, one rotation of slot 0 against slot 1 -- and the O(n) fix-up below only runs for those users.

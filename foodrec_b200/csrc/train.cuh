@@ -142,6 +142,12 @@ void launch_serve_keys(const int32_t* rreq, uint32_t n, uint32_t items_per_rank,
 void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const PeerPtrs& peers, const Launch& l,
                         uint32_t n_table);
 void launch_add_inplace(float4* dst, const float4* src, int64_t n4, const Launch& l);
+void launch_route_keys(const int32_t* users, int B, int W, uint32_t* keys, uint32_t* owner_counts, const Launch& l);
+void launch_route_fill(const int32_t* users, const int32_t* items, const float* labels, int B, int W, int group, int rcap,
+                       const uint32_t* okeys_sorted, const uint32_t* perm, const uint32_t* owner_counts, int32_t* send,
+                       float* flag, const Launch& l);
+void launch_route_unpack(const int32_t* recv, int W, int blk, int rcap, int group, int has_labels, uint32_t* counts, int cap_out,
+                         int32_t* users, int32_t* items, float* labels, int32_t* n_out, float* flag, const Launch& l);
 void launch_mean(const float4* x, int64_t n4, double* partials, float* out_slot, double count, const Launch& l);
 void launch_write_counters(const uint32_t* counters, float* out, const Launch& l);
 

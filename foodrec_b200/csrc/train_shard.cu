@@ -105,6 +105,80 @@ void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV
   gather_rows_kernel<<<grid, FR_THREADS, 0, l.st>>>(R, rreq, n, DV, out, peers, n_table); ++g_launches;
 }
 
+// ---- routing of an UN-routed batch: a rank received arbitrary users; every group (sample / BPR triple) must reach
+// the rank that owns its user (user % W).  Groups are bucketed by owner in batch order (stable sort by user % W),
+// written front-packed into one fixed-capacity block per destination -- [rcap local user rows | rcap*group recipe
+// ids | (pointwise) rcap labels], -1 padded -- exchanged with ONE all-to-all, and compacted in (source, position)
+// order at the receiver.
+__global__ void route_keys_kernel(const int32_t* __restrict__ users, int B, int W, uint32_t* __restrict__ keys,
+                                  uint32_t* __restrict__ owner_counts) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    const uint32_t o = (uint32_t)users[i] % (uint32_t)W;
+    keys[i] = o;
+    atomicAdd(owner_counts + o, 1u);                      // integer: order-independent
+  }
+}
+__global__ void route_fill_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ items,
+                                  const float* __restrict__ labels, int B, int W, int group, int rcap,
+                                  const uint32_t* __restrict__ okeys_sorted, const uint32_t* __restrict__ perm,
+                                  const uint32_t* __restrict__ owner_counts, int32_t* __restrict__ send, float* __restrict__ flag) {
+  uint32_t start[9]; start[0] = 0;
+  for (int o = 0; o < W && o < 8; ++o) start[o + 1] = start[o] + owner_counts[o];
+  const int blk = rcap * (1 + group + (labels ? 1 : 0));
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < B; q += gridDim.x * blockDim.x) {
+    const uint32_t o = okeys_sorted[q], src = perm[q];
+    const uint32_t j = (uint32_t)q - start[o];
+    if (j >= (uint32_t)rcap) { *flag = 2.f; continue; }   // capacity of a (source, destination) pair exceeded
+    int32_t* b = send + (size_t)o * blk;
+    b[j] = users[src] / W;                                // LOCAL row at the owner
+    for (int g = 0; g < group; ++g) b[rcap + j * group + g] = items[src * group + g];
+    if (labels) b[rcap + rcap * group + j] = __float_as_int(labels[src]);
+  }
+}
+// receiver: blocks are front-packed; count the valid groups of every source, then gather in (source, position) order
+__global__ void route_count_kernel(const int32_t* __restrict__ recv, int W, int blk, int rcap, uint32_t* __restrict__ counts) {
+  const int s = blockIdx.x;
+  uint32_t c = 0;
+  for (int j = threadIdx.x; j < rcap; j += blockDim.x) c += recv[(size_t)s * blk + j] >= 0;
+  c = __reduce_add_sync(FR_FULL, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + s, c);
+}
+__global__ void route_gather_kernel(const int32_t* __restrict__ recv, int W, int blk, int rcap, int group, int has_labels,
+                                    const uint32_t* __restrict__ counts, int cap_out, int32_t* __restrict__ users,
+                                    int32_t* __restrict__ items, float* __restrict__ labels, int32_t* __restrict__ n_out,
+                                    float* __restrict__ flag) {
+  uint32_t start[9]; start[0] = 0;
+  for (int s = 0; s < W && s < 8; ++s) start[s + 1] = start[s] + counts[s];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *n_out = (int32_t)min(start[W], (uint32_t)cap_out); if (start[W] > (uint32_t)cap_out) *flag = 2.f; }
+  for (int s = 0; s < W; ++s) {
+    const int32_t* b = recv + (size_t)s * blk;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < counts[s]; j += gridDim.x * blockDim.x) {
+      const uint32_t d = start[s] + j;
+      if (d >= (uint32_t)cap_out) continue;
+      users[d] = b[j];
+      for (int g = 0; g < group; ++g) items[d * group + g] = b[rcap + j * group + g];
+      if (has_labels) labels[d] = __int_as_float(b[rcap + rcap * group + j]);
+    }
+  }
+}
+void launch_route_keys(const int32_t* users, int B, int W, uint32_t* keys, uint32_t* owner_counts, const Launch& l) {
+  route_keys_kernel<<<lin_grid(B, l.sm_count), 256, 0, l.st>>>(users, B, W, keys, owner_counts); ++g_launches;
+}
+void launch_route_fill(const int32_t* users, const int32_t* items, const float* labels, int B, int W, int group, int rcap,
+                       const uint32_t* okeys_sorted, const uint32_t* perm, const uint32_t* owner_counts, int32_t* send,
+                       float* flag, const Launch& l) {
+  route_fill_kernel<<<lin_grid(B, l.sm_count), 256, 0, l.st>>>(users, items, labels, B, W, group, rcap, okeys_sorted, perm,
+                                                             owner_counts, send, flag); ++g_launches;
+}
+void launch_route_unpack(const int32_t* recv, int W, int blk, int rcap, int group, int has_labels, uint32_t* counts, int cap_out,
+                         int32_t* users, int32_t* items, float* labels, int32_t* n_out, float* flag, const Launch& l) {
+  cudaMemsetAsync(counts, 0, 8 * sizeof(uint32_t), l.st);
+  route_count_kernel<<<W, 256, 0, l.st>>>(recv, W, blk, rcap, counts);
+  route_gather_kernel<<<lin_grid(rcap, l.sm_count), 256, 0, l.st>>>(recv, W, blk, rcap, group, has_labels, counts, cap_out, users,
+                                                                    items, labels, n_out, flag);
+  g_launches += 2;
+}
+
 __global__ void add_inplace_kernel(float4* __restrict__ dst, const float4* __restrict__ src, int64_t n4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = add4(dst[i], src[i]);

@@ -128,6 +128,53 @@ class ShardedEngine:
         self._b = L.fr_batch(mode, B, _ptr(users_local), _ptr(items), _ptr(None), _ptr(labels), _ptr(None), _ptr(None))
         self._sh = self._shard(global_batch if global_batch is not None else B)
 
+    # un-routed batches ------------------------------------------------------------------
+    def route(self, mode, users_global, items, labels=None, rcap=None):
+        """fr_shard_route: bucket a batch that arrived on THIS rank (global user ids, any owner) by owner rank into
+        one fixed-capacity block per destination.  Returns the send buffer [W, block] for ONE all-to-all."""
+        e = self.e
+        u = e._i32(users_global)
+        B = u.numel()
+        group = 2 if mode == L.FR_BPR else 1
+        it = e._i32(items)
+        assert it.numel() == B * group
+        lab = e._f32(labels, (-1,)) if mode == L.FR_POINTWISE else None
+        if rcap is None:
+            rcap = max(getattr(self, "_rcap", 0), int(1.25 * B / self.world) + 256)
+        b = L.fr_batch(mode, B, _ptr(u), _ptr(it), _ptr(None), _ptr(lab), _ptr(None), _ptr(None))
+        blk = int(e.lib.fr_shard_route_block(C.byref(b), int(rcap)))
+        if getattr(self, "_rcap", None) != rcap or getattr(self, "_rmode", None) != mode:
+            self._rcap, self._rmode, self._rblk = rcap, mode, blk
+            self._rsend = torch.empty((self.world, blk), dtype=torch.int32, device=self.device)
+            self._rrecv = torch.empty_like(self._rsend)
+            cap_out = e.max_rows // group
+            self._ru = torch.empty(cap_out, dtype=torch.int32, device=self.device)
+            self._ri = torch.empty(cap_out * group, dtype=torch.int32, device=self.device)
+            self._ry = torch.empty(cap_out, dtype=torch.float32, device=self.device)
+            self._rn = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._rflag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._rflag.zero_()
+        L.check(e.handle, e.lib.fr_shard_route(e.handle, C.byref(b), self.world, int(rcap), _ptr(self._rsend), _ptr(self._rflag), e._stream()))
+        self._keep_route = [u, it, lab]
+        return self._rsend
+
+    def unroute(self, global_batch):
+        """fr_shard_unroute on the received blocks (self._rrecv) + set_batch_dev with what arrived.  Reads the routed
+        batch size on the host (one 8-byte device->host copy: the phases take the row count as a host integer)."""
+        e = self.e
+        mode = self._rmode
+        group = 2 if mode == L.FR_BPR else 1
+        L.check(e.handle, e.lib.fr_shard_unroute(e.handle, mode, self.world, int(self._rcap), _ptr(self._rrecv), self._ru.numel(),
+                                                 _ptr(self._ru), _ptr(self._ri), _ptr(self._ry), _ptr(self._rn), _ptr(self._rflag),
+                                                 e._stream()))
+        n, flag = (int(x) for x in torch.stack([self._rn.float().squeeze(0), self._rflag.squeeze(0)]).cpu())
+        if flag:
+            raise L.FoodRecError("routing: more groups for one destination than the block capacity (raise rcap) or more "
+                                 "arrived than max_rows holds")
+        self.set_batch_dev(mode, n, self._ru[:n], self._ri[:n * group], self._ry[:n] if mode == L.FR_POINTWISE else None,
+                           global_batch=global_batch)
+        return n
+
     # the five phases ------------------------------------------------------------------
     def plan(self):
         e = self.e
@@ -255,6 +302,14 @@ class DistRunner:
         else:
             self.dist.all_reduce(self._sync)
 
+    def set_batch_unrouted(self, mode, users_global, items, labels=None, global_batch=None, rcap=None):
+        """A batch whose groups were NOT loaded at their users' owners: bucket by owner, ONE all-to-all of the blocks,
+        compact what arrives.  ``global_batch`` = groups summed over all ranks (the loss mean divides by it)."""
+        g = self.eng
+        send = g.route(mode, users_global, items, labels, rcap)
+        self.dist.all_to_all_single(g._rrecv, send)
+        return g.unroute(global_batch)
+
     def step(self, write_personal=False, phase_events=None):
         """One training step.  ``phase_events`` (a list) receives (name, torch.cuda.Event) marks recorded on the
         step's stream before every phase and after the last one -- bench.py's per-phase timing; None: no overhead."""
@@ -327,6 +382,14 @@ class LocalRunner:
         rg = [g.rgrows.data_ptr() for g in self.engs]
         for g in self.engs:
             g.set_peers(rb, rg)
+
+    def set_batches_unrouted(self, mode, batches, global_batch, rcap=None):
+        """batches[r] = (users_global, items, labels) as they arrived on rank r.  Same kernels as DistRunner."""
+        sends = [g.route(mode, *b, rcap=rcap) for g, b in zip(self.engs, batches)]
+        for r, g in enumerate(self.engs):
+            for s_, gs in enumerate(self.engs):
+                g._rrecv[s_].copy_(sends[s_][r])
+        return [g.unroute(global_batch) for g in self.engs]
 
     def step(self, write_personal=False):
         p2p = getattr(self.engs[0], "p2p", False)

@@ -212,6 +212,17 @@ typedef struct {
   int32_t global_batch;     /* groups summed over ranks: the loss mean divides by it */
 } fr_shard;
 int64_t fr_shard_packed_len(fr_handle h);
+/* Routing of a batch that was NOT loaded at its users' owners (batch.users = GLOBAL user ids): every group is written,
+ * in batch order, into the block of the rank that owns its user (user % world): send [world][block], block =
+ * fr_shard_route_block(batch, rcap) int32 = [rcap local user rows | rcap*group recipe ids | (pointwise) rcap labels as
+ * bits], -1 padded.  The caller exchanges the blocks with ONE all-to-all; fr_shard_unroute compacts what arrived, in
+ * (source rank, position) order, into a routed batch (users = local rows) and writes its size to n_out (device int32:
+ * the caller reads it to call fr_shard_plan).  More than rcap groups for one destination, or more than cap_out
+ * received, raise *out_flag = 2 (NULL: the step's FR_OUT_OVERFLOW). */
+int64_t fr_shard_route_block(const fr_batch* b, int32_t rcap);
+int fr_shard_route(fr_handle h, const fr_batch* b, int32_t world, int32_t rcap, int32_t* send, float* out_flag, fr_stream s);
+int fr_shard_unroute(fr_handle h, int32_t mode, int32_t world, int32_t rcap, const int32_t* recv, int32_t cap_out,
+                     int32_t* users, int32_t* items, float* labels, int32_t* n_out, float* out_flag, fr_stream s);
 /* Peer-memory exchange over NVLink instead of the two row all-to-alls: peer_rbuf[w] / peer_rgrows[w] are rank w's
  * receive buffers ([W*cap, D] each) mapped into this process (CUDA IPC; the caller's own buffers at index rank).
  * Afterwards fr_shard_serve(rows = NULL) stores every gathered recipe row straight into the requester's rbuf and

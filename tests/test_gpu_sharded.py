@@ -136,6 +136,45 @@ def test_nccl_sharded_equals_unsharded():
     assert out.returncode == 0 and out.stdout.count("DIST_CHECK_OK_") == 2, out.stdout[-1500:] + out.stderr[-3000:]
 
 
+@pytest.mark.parametrize("bpr", [True, False])
+def test_unrouted_batches_are_routed_to_their_owners(bpr):
+    """Samples arrive on an arbitrary rank (global user ids).  fr_shard_route / one all-to-all / fr_shard_unroute must
+    deliver every group to its user's owner: the step then equals the unsharded engine on the concatenated batch."""
+    from foodrec_b200 import _lib as L
+    W = 4
+    p = Problem(403, 257, 9, 64, seed=63)
+    single, engs = build(p, W, "adam", "lazy")
+    run = sharded.LocalRunner(engs)
+    for s in range(3):
+        B = 4 * 90
+        f = p.bpr(B, seed=180 + s) if bpr else p.pointwise(B, seed=180 + s)
+        kw = dict(neg_items=f["neg_item_input"], neg_categories=f["neg_categories"]) if bpr else {}
+        # the unsharded engine sees the groups in the order they END UP in: by owner rank, then source rank, then position
+        parts = np.array_split(np.arange(B), W)                       # what arrived where
+        order = np.concatenate([[i for src in range(W) for i in parts[src] if f["user_input"][i] % W == r] for r in range(W)]).astype(int)
+        fo = {k: v[order] for k, v in f.items()}
+        kwo = dict(neg_items=fo["neg_item_input"], neg_categories=fo["neg_categories"]) if bpr else {}
+        single.train_step(fo["user_input"], fo["item_input"], labels=None if bpr else fo["labels"], categories=fo["categories"],
+                          user_one_hot_label=fo["user_one_hot_label"], **kwo)
+        v1 = single.read_scalars().copy()
+        batches = []
+        for r in range(W):
+            ix = parts[r]
+            items = np.stack([f["item_input"][ix], f["neg_item_input"][ix]], 1).reshape(-1) if bpr else f["item_input"][ix]
+            batches.append((f["user_input"][ix], items, None if bpr else f["labels"][ix]))
+        ns = run.set_batches_unrouted(L.FR_BPR if bpr else L.FR_POINTWISE, batches, global_batch=B)
+        assert ns == [int((f["user_input"] % W == r).sum()) for r in range(W)]
+        outs = run.step()
+        v = outs[0].cpu().numpy()
+        assert v[9] == 0 and v[0] == pytest.approx(v1[0], rel=1e-5) and v[1] == pytest.approx(v1[1], rel=1e-5)
+    ts, tr = gather(engs, p), single.tables()
+    for k in ("P", "R", "Cat", "G"):
+        assert_close(ts[k], tr[k], rtol=1e-4, what=k)
+    # capacity: a block too small for what one destination receives is reported, not truncated silently
+    with pytest.raises(L.FoodRecError, match="routing"):
+        run.set_batches_unrouted(L.FR_BPR if bpr else L.FR_POINTWISE, batches, global_batch=B, rcap=8)
+
+
 def test_capacity_overflow_is_reported():
     p = Problem(64, 200, 5, 16, seed=3)
     single, engs = build(p, 2, "sgd", "dense", max_rows=512, cap=4)     # far too small
