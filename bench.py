@@ -601,9 +601,9 @@ def run_sharded(args, cfg, B):
     """N GPUs of one node, one process per GPU: tables row-sharded (P by user % N, R by recipe % N), B triples per GPU
     per step, every triple loaded on the rank that owns its user; recipe rows and their gradients cross NVLink (peer
     stores from inside the gather / gradient kernels, or staged all-to-alls), one packed all-reduce per step.
-    WEAK SCALING AT CONSTANT PER-GPU WORK: every GPU holds a cfg2-sized shard (1M users, 200k recipes: the tables grow
-    with N), so the unique rows a GPU touches per step are those of the N=1 run (--fixed-tables: round-1 behaviour,
-    cfg2 tables divided over the ranks).  value = N*B*K / max-over-ranks device time."""
+    WEAK SCALING AT CONSTANT PER-GPU WORK: every GPU holds a cfg2-sized Personal_Memory shard (1M users per GPU: the
+    user table grows with N, the 200k-recipe catalog is sharded), so the unique user rows a GPU touches per step are
+    those of the N=1 run (--fixed-tables: round-1 behaviour, the 1M users divided over the ranks).  value = N*B*K / max-over-ranks device time."""
     import torch
     import torch.distributed as dist
     from foodrec_b200 import Hyper
@@ -629,8 +629,8 @@ def run_sharded(args, cfg, B):
         cfg_local = dict(U=local_rows(U, world), I=local_rows(I, world), L=Lb, D=D)
         mode = "cfg3 (BASELINE configs[2])" if args.cfg3 else "fixed tables (cfg2 divided over the ranks)"
     else:
-        cfg_local = dict(U=U, I=I, L=Lb, D=D)
-        mode = "constant per-GPU work (a cfg2-sized shard on every GPU)"
+        cfg_local = dict(U=U, I=local_rows(I, world), L=Lb, D=D)
+        mode = f"constant per-GPU work: {U} users PER GPU ({U * world} in all), the {I}-recipe catalog sharded over the ranks"
     main, eng, run = sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, args.steps, args.preroll, args.warmup, mode)
     clocks.t0, clocks.t1 = main.pop("window")
     clk = clocks.stop()
@@ -721,7 +721,7 @@ def run_sharded(args, cfg, B):
             "e2e": main["e2e"], "e2e_compact": main["e2e_compact"], "unrouted": main["unrouted"],
             "uniq_users_per_step": main["uniq_users_per_step"], "uniq_items_per_step": main["uniq_items_per_step"],
             "overflow_flag": main["overflow_flag"], "cfg3": cfg3_line}
-        print(json.dumps(line))
+        print(json.dumps(line, default=float))
     dist.destroy_process_group()
 
 
@@ -1009,7 +1009,7 @@ def run_ours(args, cfg, B):
             # cfg1 exactly (the reference's own CPU-runnable case), both arms
             line["cfg1"] = {"workload": "cfg1: 10000 users x 5000 recipes x 95 labels, D=64, pointwise B=128, reference stream, Adam",
                             "gpu_e2e": cfg1_gpu_leg(dev), "cpu_baseline": cfg1_cpu_leg()}
-        print(json.dumps(line))
+        print(json.dumps(line, default=float))
     if world > 1:
         dist.destroy_process_group()
 

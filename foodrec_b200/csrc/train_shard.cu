@@ -79,7 +79,7 @@ void launch_serve_keys(const int32_t* rreq, uint32_t n, uint32_t items_per_rank,
   serve_keys_kernel<<<lin_grid(n, l.sm_count), 256, 0, l.st>>>(rreq, n, items_per_rank, keys, n_valid); ++g_launches;
 }
 
-// one warp per requested row; an empty request yields a zero row.  With peers the row of request slot
+// one warp per requested row; an empty request yields a zero row (staged path).  With peers the row of request slot
 // (source s, j) is stored straight into rank s's receive buffer over NVLink (fused gather + exchange).
 __global__ void __launch_bounds__(FR_THREADS)
 gather_rows_kernel(const float4* __restrict__ R, const int32_t* __restrict__ rreq, uint32_t n, int DV,
@@ -93,8 +93,9 @@ gather_rows_kernel(const float4* __restrict__ R, const int32_t* __restrict__ rre
       const uint32_t s = r / (uint32_t)peers.cap, j = r % (uint32_t)peers.cap;
       dst = peers.dst[s] + ((size_t)peers.rank * peers.cap + j) * DV;
     }
+    if (id < 0 && peers.world > 0) continue;          // empty request slot: the consumer never reads it -- no store over NVLink
     for (int i = lane; i < DV; i += 32)
-      dst[i] = (uint32_t)id < n_table ? R[(size_t)id * DV + i] : f4zero();      // (-1 = empty request; never out of the table)
+      dst[i] = (uint32_t)id < n_table ? R[(size_t)id * DV + i] : f4zero();      // (never out of the table)
   }
 }
 void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const PeerPtrs& peers,
