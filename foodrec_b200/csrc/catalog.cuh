@@ -12,11 +12,13 @@
 // category term is a per-(row, tile) constant the epilogue folds into its threshold.
 //
 // The bf16 GEMM is a FILTER with a proven error bound, not the answer:
-//   |s_hat - s| <= E[u] = cfac * |A[g][u]| * max_i |R[i]|  (+ fp32 rounding of the bias add)
-// the epilogue keeps every recipe with s_hat >= tau_run - 2E (tau_run = K-th best s_hat so far,
-// monotone), which provably contains the exact top-K; the survivors (K + a few dozen) are
-// re-scored in fp64 from the fp32 tables and ranked by (score desc, id asc).  Rows whose
-// candidate list overflows (massive ties) fall back to an exact full scan.
+//   |s_hat - s| <= E[u,t] = cfac * |A[g][u]| * max_{i in tile t} |R[i]|  (+ fp32 rounding of the bias add)
+// The candidate lists hold LOWER bounds s_hat - E[u,t]; tau_run = the K-th largest lower bound so far (monotone, never
+// above the true K-th best score); the epilogue keeps every recipe whose UPPER bound s_hat + E[u,t] reaches tau_run,
+// which provably contains the exact top-K (oracle/catalog_filter_model.py states and property-tests the rule).  The
+// bound is PER TILE: one heavy recipe (a hot item after training) widens the margin of its own 256-recipe tile only.
+// The survivors (K + a few dozen) are re-scored in fp64 from the fp32 tables and ranked by (score desc, id asc).  Rows
+// whose candidate list overflows (massive ties) fall back to an exact full scan.
 #pragma once
 // Per-tile filter bound (default).  -DFR_CAT_GLOBAL_BOUND builds the round-1 filter whose margin uses the largest
 // recipe norm of the WHOLE catalog (kept for A/B runs: foodrec_b200._build.build_variant("globalbound", [...])).
