@@ -462,10 +462,15 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
         pin.append((torch.as_tensor(users).pin_memory(), torch.as_tensor(items).pin_memory()))
         devb.append((pin[-1][0].to(dev), pin[-1][1].to(dev)))
 
-    def step(k, **kw):
+    def setb(k):
         u, it = devb[k % NB]
         eng.set_batch_dev(L.FR_BPR, B, u, it, global_batch=world * B)
-        return run.step(**kw)
+
+    def step(k, **kw):
+        # the NEXT step's fr_shard_plan + id all-to-all ride on a side stream under this step's update / apply
+        if not eng.planned():
+            setb(k)
+        return run.step(next_batch=None if args.no_plan_ahead else (lambda: setb(k + 1)), **kw)
 
     for k in range(preroll + warmup):
         step(k)
@@ -532,11 +537,12 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
         for k in range(steps):
             hu, hi = pin[k % NB]
             ubuf.copy_(hu, non_blocking=True); ibuf.copy_(hi, non_blocking=True)
+            if eng.planned():                                   # a plan left over from a pipelined leg: run it out
+                run.step()
             if dense:
                 dc.copy_(hc[k % NB], non_blocking=True); dl.copy_(hl[k % NB], non_blocking=True)
-                eng._keep = [ubuf, ibuf, dc, dl]
-                eng._b = L.fr_batch(L.FR_BPR, B, ubuf.data_ptr(), ibuf.data_ptr(), dc.data_ptr(), None, None, dl.data_ptr())
-                eng._sh = eng._shard(world * B)
+                eng.set_batch_raw(L.fr_batch(L.FR_BPR, B, ubuf.data_ptr(), ibuf.data_ptr(), dc.data_ptr(), None, None, dl.data_ptr()),
+                                  [ubuf, ibuf, dc, dl], world * B)
             else:
                 eng.set_batch_dev(L.FR_BPR, B, ubuf, ibuf, global_batch=world * B)
             out = run.step()
@@ -557,6 +563,8 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
         gb.append((torch.as_tensor(users).to(dev), torch.as_tensor(np.stack([pos, neg], 1).reshape(-1).copy()).to(dev)))
 
     def ustep(k, evs=None):
+        if eng.planned():
+            run.step()
         u, it = gb[k % NB]
         if evs is not None:
             a = torch.cuda.Event(enable_timing=True); a.record()
@@ -1029,6 +1037,7 @@ def main():
     ap.add_argument("--fixed-tables", action="store_true", help="N>1: cfg2 tables divided over the ranks (round-1 behaviour) "
                     "instead of a cfg2-sized shard per GPU (constant per-GPU work)")
     ap.add_argument("--no-cfg3", action="store_true", help="N=8: skip the cfg3 leg (100M users / 10M recipes)")
+    ap.add_argument("--no-plan-ahead", action="store_true", help="N>1: plan every step in sequence instead of one step ahead on a side stream")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-catalog", action="store_true", help="skip the full-catalog top-K legs")
     ap.add_argument("--learner", default="adam", help="adam (reference default) | adagrad | rmsprop | sgd")

@@ -19,18 +19,40 @@ static int ws_alloc(fr_ctx* h, T** p, size_t n) {
   return dalloc(h, p, n);
 }
 
-static int shard_ensure(fr_ctx* h, size_t S, size_t n) {
+// Buffers of plan slot `idx` for S item rows.  Slot 0 aliases the single-GPU step's workspace (sized max_rows at
+// fr_create); slot 1 gets its own on first use.
+static int plan_slot_ensure(fr_ctx* h, int idx, size_t S) {
+  auto& ps = h->sh.ps[idx];
+  int rc;
+  if (!ps.owner_counts && (rc = dalloc(h, &ps.owner_counts, 8))) return rc;     // (needed even by a rank with no rows)
+  if (!ps.flag_out) {
+    if (idx == 0) {
+      ps.flag_out = h->out_internal; ps.ukeys = h->ukeys; ps.users_s = h->users_s; ps.items_s = h->items_s; ps.ws_row = h->ws_row;
+      ps.sortU = h->sortU; ps.sortI = h->sortI;
+      if ((rc = dalloc(h, &ps.scan_tmp, (size_t)h->cfg.max_rows / 4096 + 2))) return rc;   // (h->scan_tmp belongs to forward's label scan)
+    } else {
+      const size_t M = (size_t)h->cfg.max_rows;
+      if ((rc = dalloc(h, &ps.flag_out, FR_OUT_COUNT)) || (rc = dalloc(h, &ps.ukeys, M)) || (rc = dalloc(h, &ps.users_s, M)) ||
+          (rc = dalloc(h, &ps.items_s, M)) || (rc = dalloc(h, &ps.ws_row, M)) || (rc = alloc_sort(h, ps.sortU, M)) ||
+          (rc = alloc_sort(h, ps.sortI, M)) || (rc = dalloc(h, &ps.scan_tmp, M / 4096 + 2)))
+        return rc;
+    }
+  }
+  if (S > ps.s_cap) {
+    if ((rc = ws_alloc(h, &ps.okeys, S)) || (rc = ws_alloc(h, &ps.flags, S)) || (rc = ws_alloc(h, &ps.excl, S)) ||
+        (rc = ws_alloc(h, &ps.slot_sorted, S)) || (rc = ws_alloc(h, &ps.slot_of_row, S)) ||
+        (rc = ws_alloc(h, &ps.cats_row, S)))
+      return rc;
+    ps.s_cap = S;
+  }
+  return FR_OK;
+}
+
+static int owner_ensure(fr_ctx* h, size_t n) {            // owner-side buffers for W*cap request slots
   auto& w = h->sh;
   int rc;
-  if (!w.owner_counts && (rc = dalloc(h, &w.owner_counts, 8))) return rc;     // (needed even by a rank with no rows)
   if (!w.n_valid && (rc = dalloc(h, &w.n_valid, 1))) return rc;
-  if (S > w.s_cap) {
-    if ((rc = ws_alloc(h, &w.okeys, S)) || (rc = ws_alloc(h, &w.flags, S)) || (rc = ws_alloc(h, &w.excl, S)) ||
-        (rc = ws_alloc(h, &w.slot_sorted, S)) || (rc = ws_alloc(h, &w.slot_of_row, S)) ||
-        (rc = ws_alloc(h, &w.cats_row, S)))
-      return rc;
-    w.s_cap = S;
-  }
+  if (!w.route_counts && (rc = dalloc(h, &w.route_counts, 8))) return rc;
   if (n > w.n_cap) {
     if ((rc = ws_alloc(h, &w.serve_keys, n))) return rc;
     if ((rc = alloc_sort(h, w.sortS, n))) return rc;       // (old buffers stay in allocs until fr_destroy)
@@ -63,41 +85,44 @@ extern "C" int fr_shard_plan(fr_handle h, const fr_batch* b, const fr_shard* sh,
     return fail(h, FR_ERR_ARG, "user_labels is NULL and no user-label CSR table");
   const int S = B * group, W = sh->world;
   const size_t n = (size_t)W * sh->cap;
-  if ((rc = shard_ensure(h, (size_t)S, n))) return rc;
+  auto& w = h->sh;
+  if (w.n_plan - w.n_apply >= 2) return fail(h, FR_ERR_STATE, "fr_shard_plan: both plan slots are in use (plan may run at most one step ahead)");
+  const int slot = (int)(w.n_plan & 1);
+  if ((rc = plan_slot_ensure(h, slot, (size_t)S)) || (rc = owner_ensure(h, n))) return rc;
+  auto& ps = w.ps[slot];
   cudaStream_t st = (cudaStream_t)s;
   const bool lazy_adam = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
   if (!(lazy_adam && h->shP) && (rc = shadow_sync(h, st))) return rc;
   Launch l{h->sm_count, st, nullptr};
-  auto& w = h->sh;
-  w.mode = b->mode; w.B = B; w.S = S; w.group = group; w.planned = true;
+  ps.mode = b->mode; ps.B = B; ps.S = S; ps.group = group; ps.planned = true; ps.fused = false;
+  ++w.n_plan;
   const fr_tables& T = h->tab;
-
-  FR_CUDA(h, cudaMemcpyAsync(h->cat_pre, T.Cat, (size_t)4 * h->mc.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  FR_CUDA(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(uint32_t), st));
-  FR_CUDA(h, cudaMemsetAsync(w.owner_counts, 0, 8 * sizeof(uint32_t), st));
+  // (everything written here belongs to the plan slot: this call may overlap the previous step's update / apply.  The
+  //  Category_Embedding snapshot and the step counters are taken by fr_shard_forward, after the previous step is done)
+  FR_CUDA(h, cudaMemsetAsync(ps.owner_counts, 0, 8 * sizeof(uint32_t), st));
   FR_CUDA(h, cudaMemsetAsync(req, 0xff, n * sizeof(int32_t), st));
-  FR_CUDA(h, cudaMemsetAsync(h->out_internal, 0, FR_OUT_COUNT * sizeof(float), st));
+  FR_CUDA(h, cudaMemsetAsync(ps.flag_out, 0, FR_OUT_COUNT * sizeof(float), st));
   if (S == 0) return FR_OK;                       // nothing to request: req stays all -1
   // users are LOCAL rows, items GLOBAL recipe ids (< W * items_per_rank; ids in the padding of the last shard are
   // zero rows of their owner): range-checked copies, read by every later phase
   launch_prep_rows(b->mode, B, b->users, b->items, b->labels, b->write_sign, h->cfg.num_users,
-                   (int64_t)W * sh->items_per_rank, h->ukeys, h->ws_row, h->users_s, h->items_s,
-                   h->out_internal + FR_OUT_OVERFLOW, l);
+                   (int64_t)W * sh->items_per_rank, ps.ukeys, ps.ws_row, ps.users_s, ps.items_s,
+                   ps.flag_out + FR_OUT_OVERFLOW, l);
 
   ShardPlanParams p{};
   p.S = S; p.W = W; p.cap = sh->cap; p.items_per_rank = (uint32_t)sh->items_per_rank;
-  p.items = h->items_s; p.item_cats = (const float4*)T.item_cats; p.cats_in = (const float4*)b->cats;
-  p.okeys = w.okeys; p.cats_row = w.cats_row;
-  p.flags = w.flags; p.excl = w.excl; p.owner_counts = w.owner_counts;
-  p.req = req; p.slot_of_row = w.slot_of_row; p.slot_sorted = w.slot_sorted; p.out = h->out_internal;
+  p.items = ps.items_s; p.item_cats = (const float4*)T.item_cats; p.cats_in = (const float4*)b->cats;
+  p.okeys = ps.okeys; p.cats_row = ps.cats_row;
+  p.flags = ps.flags; p.excl = ps.excl; p.owner_counts = ps.owner_counts;
+  p.req = req; p.slot_of_row = ps.slot_of_row; p.slot_sorted = ps.slot_sorted; p.out = ps.flag_out;
   launch_shard_prep(p, l);
-  SortJob sj[2] = {{&h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), 0},
-                   {&h->sortI, w.okeys, (uint32_t)S, nullptr, bits_for((int64_t)W * sh->items_per_rank), 0}};
+  SortJob sj[2] = {{&ps.sortU, ps.ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), 0},
+                   {&ps.sortI, ps.okeys, (uint32_t)S, nullptr, bits_for((int64_t)W * sh->items_per_rank), 0}};
   radix_sort_jobs(sj, 2, st, h->sm_count);
-  w.ru = sj[0].result; w.ri = sj[1].result;
-  p.okeys_sorted = h->sortI.k[w.ri]; p.perm = h->sortI.v[w.ri];
+  ps.ru = sj[0].result; ps.ri = sj[1].result;
+  p.okeys_sorted = ps.sortI.k[ps.ri]; p.perm = ps.sortI.v[ps.ri];
   launch_shard_heads(p, l);
-  exclusive_scan_u32(w.flags, w.excl, (uint32_t)S, h->scan_tmp, nullptr, st);
+  exclusive_scan_u32(ps.flags, ps.excl, (uint32_t)S, ps.scan_tmp, nullptr, st);
   launch_shard_fill(p, l);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
@@ -119,19 +144,21 @@ extern "C" int fr_shard_route(fr_handle h, const fr_batch* b, int32_t world, int
   if (B < 0 || (int64_t)B * group > h->cfg.max_rows) return fail(h, FR_ERR_ARG, "batch exceeds max_rows=%d", h->cfg.max_rows);
   if (B > 0 && (!b->users || !b->items || (b->mode == FR_POINTWISE && !b->labels))) return fail(h, FR_ERR_ARG, "users/items/labels are required");
   int rc;
-  if ((rc = shard_ensure(h, (size_t)B * group, 0))) return rc;
+  auto& w = h->sh;
+  const int slot = (int)(w.n_plan & 1);              // the slot the NEXT fr_shard_plan will use: routing belongs to that step
+  if ((rc = plan_slot_ensure(h, slot, (size_t)B * group))) return rc;
+  auto& ps = w.ps[slot];
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
-  auto& w = h->sh;
   const int64_t blk = fr_shard_route_block(b, rcap);
   FR_CUDA(h, cudaMemsetAsync(send, 0xff, (size_t)world * blk * sizeof(int32_t), st));
-  FR_CUDA(h, cudaMemsetAsync(w.owner_counts, 0, 8 * sizeof(uint32_t), st));
+  FR_CUDA(h, cudaMemsetAsync(ps.owner_counts, 0, 8 * sizeof(uint32_t), st));
   if (B == 0) return FR_OK;
-  float* flag = out_flag ? out_flag : h->out_internal + FR_OUT_OVERFLOW;
-  launch_route_keys(b->users, B, world, w.okeys, w.owner_counts, l);
-  const int r = radix_sort_pairs(h->sortI, w.okeys, (uint32_t)B, nullptr, 3, st, h->sm_count);
-  launch_route_fill(b->users, b->items, b->mode == FR_POINTWISE ? b->labels : nullptr, B, world, group, rcap, h->sortI.k[r],
-                    h->sortI.v[r], w.owner_counts, send, flag, l);
+  float* flag = out_flag ? out_flag : ps.flag_out + FR_OUT_OVERFLOW;
+  launch_route_keys(b->users, B, world, ps.okeys, ps.owner_counts, l);
+  const int r = radix_sort_pairs(ps.sortI, ps.okeys, (uint32_t)B, nullptr, 3, st, h->sm_count);
+  launch_route_fill(b->users, b->items, b->mode == FR_POINTWISE ? b->labels : nullptr, B, world, group, rcap, ps.sortI.k[r],
+                    ps.sortI.v[r], ps.owner_counts, send, flag, l);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -142,13 +169,14 @@ extern "C" int fr_shard_unroute(fr_handle h, int32_t mode, int32_t world, int32_
   if (!recv || !users || !items || !n_out || world < 1 || world > 8 || rcap < 1 || cap_out < 1) return fail(h, FR_ERR_ARG, "bad fr_shard_unroute arguments");
   if (mode == FR_POINTWISE && !labels) return fail(h, FR_ERR_ARG, "labels buffer required in pointwise mode");
   int rc;
-  if ((rc = shard_ensure(h, 0, 0))) return rc;
+  if ((rc = owner_ensure(h, 0))) return rc;
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
   const int group = mode == FR_BPR ? 2 : 1;
   const int blk = rcap * (1 + group + (mode == FR_POINTWISE ? 1 : 0));
-  float* flag = out_flag ? out_flag : h->out_internal + FR_OUT_OVERFLOW;
-  launch_route_unpack(recv, world, blk, rcap, group, mode == FR_POINTWISE, h->sh.owner_counts, cap_out, users, items, labels,
+  if (!out_flag) return fail(h, FR_ERR_ARG, "fr_shard_unroute needs out_flag");
+  float* flag = out_flag;
+  launch_route_unpack(recv, world, blk, rcap, group, mode == FR_POINTWISE, h->sh.route_counts, cap_out, users, items, labels,
                       n_out, flag, l);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
@@ -189,7 +217,7 @@ extern "C" int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rr
   if (!rreq) return fail(h, FR_ERR_ARG, "null rreq");
   if (!rows && h->sh.peer_rbuf.world != sh->world) return fail(h, FR_ERR_ARG, "rows is NULL but fr_shard_set_peers has not been called for this world");
   const size_t n = (size_t)sh->world * sh->cap;
-  if ((rc = shard_ensure(h, 0, n))) return rc;
+  if ((rc = owner_ensure(h, n))) return rc;
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
   auto& w = h->sh;
@@ -215,67 +243,71 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   int rc = shard_check(h, sh); if (rc) return rc;
   if (!b || !rbuf || !packed) return fail(h, FR_ERR_ARG, "null argument");
   auto& w = h->sh;
-  if (!w.planned || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_forward");
+  auto& ps = w.ps[w.n_apply & 1];
+  if (!ps.planned || b->n_groups != ps.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_forward");
   cudaStream_t st = (cudaStream_t)s;
-  if (w.S == 0) {     // a rank without rows adds nothing to {loss, sum|g|^2, dCat, dG}
+  FR_CUDA(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(uint32_t), st));
+  if (ps.S == 0) {     // a rank without rows adds nothing to {loss, sum|g|^2, dCat, dG}
     FR_CUDA(h, cudaMemsetAsync(packed, 0, (size_t)fr_shard_packed_len(h) * sizeof(float), st));
-    w.fused = false;
+    ps.fused = false;
     return FR_OK;
   }
+  // pre-step snapshot of Category_Embedding (every read of Cat in this step sees it)
+  FR_CUDA(h, cudaMemcpyAsync(h->cat_pre, h->tab.Cat, (size_t)4 * h->mc.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   Launch l{h->sm_count, st, nullptr};
   const fr_tables& T = h->tab;
-  const int DV = h->mc.DV, NV = h->NV, S = w.S, B = w.B;
+  const int DV = h->mc.DV, NV = h->NV, S = ps.S, B = ps.B;
   const OptConsts oc = make_oc(h, h->step + 1);
   const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
 
   int fgrid;
-  w.fused = lazy && h->shP && !getenv("FOODREC_TWO_PASS");
-  if (w.fused) {
+  ps.fused = lazy && h->shP && !getenv("FOODREC_TWO_PASS");
+  if (ps.fused) {
     // single-pass step (train_seg.cu): forward AND the speculative Personal_Memory update, before the all-reduce that
     // makes the global norm known; fr_shard_update commits the rows (scale == 1) or redoes the update with the true scale
     SegCommon cu{};
-    cu.keys = h->sortU.k[w.ru]; cu.perm = h->sortU.v[w.ru]; cu.n_dev = nullptr; cu.n_host = (uint32_t)S;
+    cu.keys = ps.sortU.k[ps.ru]; cu.perm = ps.sortU.v[ps.ru]; cu.n_dev = nullptr; cu.n_host = (uint32_t)S;
     cu.uniq_counter = h->counters + 0; cu.pieces = h->pieces_u;
     FusedParams fz{};
     fz.P[0] = (float4*)T.P; fz.m[0] = (float4*)T.s1_P; fz.v[0] = (float4*)T.s2_P;
     fz.P[1] = (float4*)h->shP; fz.m[1] = (float4*)h->shM; fz.v[1] = (float4*)h->shV;
     fz.last = T.last_P; fz.R = (const float4*)rbuf; fz.cat = h->cat_pre;
-    fz.items = w.slot_of_row; fz.cats = w.cats_row; fz.cats_by_item = 0; fz.labels = b->labels;
+    fz.items = ps.slot_of_row; fz.cats = ps.cats_row; fz.cats_by_item = 0; fz.labels = b->labels;
     fz.a = h->mc.a; fz.oma = h->mc.oma; fz.Bnorm = (float)sh->global_batch;
     fz.g = h->g; fz.z = h->z; fz.scores = h->scores;
     fz.part_loss = h->part_loss; fz.part_nrm = h->part_nrm; fz.part_gcat = h->part_gcat;
     fz.mc = h->mc; fz.oc = oc;
     fgrid = user_fused_grid((uint32_t)S, h->sm_count);
-    launch_user_fused(NV, w.group, cu, fz, fgrid, l);
+    launch_user_fused(NV, ps.group, cu, fz, fgrid, l);
     h->shadow_dirty = true;
   } else {
   FwdParams fp{};
   fp.P = (const float4*)T.P; fp.R = (const float4*)rbuf; fp.cat = h->cat_pre; fp.DV = DV; fp.B = B;
   fp.Bnorm = (float)sh->global_batch;
-  fp.users = h->users_s; fp.items = w.slot_of_row; fp.cats = w.cats_row; fp.cats_by_item = 0;
+  fp.users = ps.users_s; fp.items = ps.slot_of_row; fp.cats = ps.cats_row; fp.cats_by_item = 0;
   fp.labels = b->labels; fp.a = h->mc.a; fp.oma = h->mc.oma;
   fp.g = h->g; fp.z = h->z; fp.scores = h->scores;
   fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
   fp.lazy = lazy ? 1 : 0; fp.mP = (const float4*)T.s1_P; fp.vP = (const float4*)T.s2_P; fp.lastP = T.last_P; fp.oc = oc;
   fgrid = fwd_train_grid(B, h->sm_count);
-  launch_fwd_train(NV, w.group, fp, fgrid, l);
+  launch_fwd_train(NV, ps.group, fp, fgrid, l);
   }
 
   FinalizeParams fin{};
   fin.part_loss = h->part_loss; fin.part_nrm = h->part_nrm; fin.part_gcat = h->part_gcat; fin.nblk = fgrid;
   fin.DV = DV; fin.B = (float)sh->global_batch; fin.packed = packed; fin.do_reduce = 1; fin.do_apply = 0;
-  fin.oc = oc; fin.clip = h->cfg.clip_norm; fin.out = h->out_internal; fin.lr_hist = nullptr;
+  fin.oc = oc; fin.clip = h->cfg.clip_norm; fin.out = ps.flag_out; fin.lr_hist = nullptr;
   launch_finalize(fin, l);
 
   // General_Memory delta of this rank's rows -> packed (G itself is updated after the all-reduce)
   float* dG = packed + 4 + 4 * (size_t)h->mc.D;
   FR_CUDA(h, cudaMemsetAsync(dG, 0, 5 * (size_t)h->mc.L * h->mc.D * sizeof(float), st));
   LabelEmitParams ep{};
-  ep.S = S; ep.group = w.group; ep.L = h->mc.L; ep.users = h->users_s;
+  ep.S = S; ep.group = ps.group; ep.L = h->mc.L; ep.users = ps.users_s;
   ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
-  ep.ws_row = h->ws_row; ep.counts = h->counts; ep.offs = h->offs;
+  ep.ws_row = ps.ws_row; ep.counts = h->counts; ep.offs = h->offs;
   ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
-  ep.cap = (uint32_t)h->sortL.cap; ep.n_entries = h->n_entries; ep.out = h->out_internal;
+  ep.cap = (uint32_t)h->sortL.cap; ep.n_entries = h->n_entries; ep.out = ps.flag_out;
   launch_label_count(ep, l);
   exclusive_scan_u32(h->counts, h->offs, (uint32_t)S, h->scan_tmp, h->n_entries, st);
   launch_label_emit(ep, l);
@@ -287,7 +319,7 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   c.long_list = h->long_list; c.long_count = h->counters + 2; c.long_cap = h->long_cap;
   LabelPolParams lp{};
   lp.G = (float4*)dG; lp.R = (const float4*)rbuf; lp.cat = h->cat_pre;
-  lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = w.slot_of_row; lp.cats = w.cats_row;
+  lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = ps.slot_of_row; lp.cats = ps.cats_row;
   lp.cats_by_item = 0; lp.mc = h->mc;
   launch_label_pass(NV, c, lp, l);
   FR_CHECK_LAUNCH(h);
@@ -301,17 +333,18 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   int rc = shard_check(h, sh); if (rc) return rc;
   if (!b || !rbuf || !packed_reduced) return fail(h, FR_ERR_ARG, "null argument");
   auto& w = h->sh;
+  auto& ps = w.ps[w.n_apply & 1];
   if (!grows && w.peer_rgrows.world != sh->world) return fail(h, FR_ERR_ARG, "grows is NULL but fr_shard_set_peers has not been called for this world");
-  if (!w.planned || b->n_groups != w.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_update");
+  if (!ps.planned || b->n_groups != ps.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_update");
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
   const fr_tables& T = h->tab;
-  const int DV = h->mc.DV, NV = h->NV, S = w.S;
+  const int DV = h->mc.DV, NV = h->NV, S = ps.S;
   const int64_t step = h->step + 1;
   const OptConsts oc = make_oc(h, step);
-  float* out = out_scalars ? out_scalars : h->out_internal;
-  if (out != h->out_internal)   // flags raised by plan/forward (capacity / label overflow)
-    FR_CUDA(h, cudaMemcpyAsync(out, h->out_internal, FR_OUT_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  float* out = out_scalars ? out_scalars : ps.flag_out;
+  if (out != ps.flag_out)   // flags raised by plan/forward (capacity / label overflow / id range)
+    FR_CUDA(h, cudaMemcpyAsync(out, ps.flag_out, FR_OUT_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   // fr_timing_*: the events of this phase's kernels (user pass, personal pass + dG add as "label", local recipe-gradient
   // pass); the phases that live in other fr_shard_* calls read as zero
@@ -331,17 +364,17 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   launch_finalize(fin, l);
 
   SegCommon c{};
-  c.keys = h->sortU.k[w.ru]; c.perm = h->sortU.v[w.ru]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
+  c.keys = ps.sortU.k[ps.ru]; c.perm = ps.sortU.v[ps.ru]; c.n_dev = nullptr; c.n_host = (uint32_t)S;
   c.uniq_counter = h->counters + 0; c.pieces = h->pieces_u;
   UserPolParams up{};
   up.P = (float4*)T.P; up.s1 = (float4*)T.s1_P; up.s2 = (float4*)T.s2_P; up.last = T.last_P;
   up.R = (const float4*)rbuf; up.G = (const float4*)T.G; up.cat = h->cat_pre;
-  up.items = w.slot_of_row; up.g = h->g; up.cats = w.cats_row; up.cats_by_item = 0;
-  up.ws_row = h->ws_row; up.out = out; up.group = w.group; up.mc = h->mc; up.oc = oc;
-  up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = h->users_s;
+  up.items = ps.slot_of_row; up.g = h->g; up.cats = ps.cats_row; up.cats_by_item = 0;
+  up.ws_row = ps.ws_row; up.out = out; up.group = ps.group; up.mc = h->mc; up.oc = oc;
+  up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = ps.users_s;
   FR_MARK(FR_T_USER_CHUNK);
   l.mid = ts ? ts->ev[FR_T_USER_COMBINE] : nullptr;
-  if (S > 0 && w.fused) {
+  if (S > 0 && ps.fused) {
     // the all-reduce made the norm known: commit the speculative rows (scale == 1), else bring every row back to the
     // caller's tables and run the ordinary update pass with the true scale (both exit at once in the common case)
     launch_user_commit(c.keys, (uint32_t)S, T.last_P, out, (int)step, l);
@@ -355,7 +388,7 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   l.mid = nullptr;
   FR_MARK(FR_T_LABEL);
   if (write_personal && S > 0) {
-    if (w.fused) { rc = shadow_sync(h, st); if (rc) return rc; }     // the personal pass works on the caller's table
+    if (ps.fused) { rc = shadow_sync(h, st); if (rc) return rc; }     // the personal pass works on the caller's table
     c.only_if_scaled = nullptr;                                      // (it always runs, whatever the clip did)
     const size_t need = (size_t)S / 32 + 2;
     if (need > h->pieces_personal_chunks) {
@@ -371,7 +404,7 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
 
   // finished gradient rows of the recipes this rank touched, in the owners' slot order
   SegCommon ci{};
-  ci.keys = w.slot_sorted; ci.perm = h->sortI.v[w.ri]; ci.n_dev = nullptr; ci.n_host = (uint32_t)S;
+  ci.keys = ps.slot_sorted; ci.perm = ps.sortI.v[ps.ri]; ci.n_dev = nullptr; ci.n_host = (uint32_t)S;
   ci.pieces = h->pieces_i; ci.uniq_counter = h->counters + 1;
   ci.long_list = h->long_list; ci.long_count = h->counters + 3; ci.long_cap = h->long_cap;
   ItemPolParams ip{};
@@ -394,14 +427,15 @@ extern "C" int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rr
   int rc = shard_check(h, sh); if (rc) return rc;
   if (!rreq || !rgrows) return fail(h, FR_ERR_ARG, "null argument");
   auto& w = h->sh;
-  if (!w.planned) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_apply");
+  auto& ps = w.ps[w.n_apply & 1];
+  if (!ps.planned) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_apply");
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
   const fr_tables& T = h->tab;
   const int DV = h->mc.DV, NV = h->NV;
   const int64_t step = h->step + 1;
   const OptConsts oc = make_oc(h, step);
-  float* out = out_scalars ? out_scalars : h->out_internal;
+  float* out = out_scalars ? out_scalars : ps.flag_out;
   const uint32_t n = (uint32_t)((size_t)sh->world * sh->cap);
 
   // received (recipe, gradient row) pairs, sorted by recipe at serve time (stable: rank order)
@@ -423,7 +457,8 @@ extern "C" int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rr
               (double)h->mc.L * 5.0 * h->mc.D, l);
   launch_write_counters(h->counters, out, l);
   FR_CHECK_LAUNCH(h);
-  w.S = 0; w.planned = false;
+  ps.S = 0; ps.planned = false;
+  ++w.n_apply;
   h->step = step;
   h->b1p *= h->cfg.adam_beta1;
   h->b2p *= h->cfg.adam_beta2;

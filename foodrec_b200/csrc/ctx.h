@@ -44,18 +44,31 @@ struct fr_ctx {
   float* out_internal = nullptr;
   uint32_t* scan_tmp = nullptr;
   // row-sharded training (api_shard.cu): allocated on first use
-  struct ShardWs {
-    size_t s_cap = 0, n_cap = 0;          // item rows / W*cap the buffers are sized for
-    uint32_t *okeys = nullptr, *flags = nullptr, *excl = nullptr, *owner_counts = nullptr, *slot_sorted = nullptr;
+  // Per-step plan state of the row-sharded step.  TWO slots: fr_shard_plan of step k+1 may be issued (on another
+  // stream) while forward / update / apply of step k are still running -- plan depends only on the batch ids, and with
+  // the id all-to-all it is ~0.3 ms of small latency-bound kernels that hide under the previous step's update.
+  // Slot 0 aliases the single-GPU step's buffers (ukeys, users_s, items_s, ws_row, sortU, sortI, out_internal).
+  struct PlanSlot {
+    size_t s_cap = 0;
+    uint32_t* ukeys = nullptr; int32_t *users_s = nullptr, *items_s = nullptr; float* ws_row = nullptr;
+    SortBufs sortU, sortI;
+    uint32_t *okeys = nullptr, *flags = nullptr, *excl = nullptr, *owner_counts = nullptr, *slot_sorted = nullptr, *scan_tmp = nullptr;
     int32_t* slot_of_row = nullptr;
     float4* cats_row = nullptr;
-    uint32_t *serve_keys = nullptr, *n_valid = nullptr;
+    float* flag_out = nullptr;             // [FR_OUT_COUNT]: flags raised while planning / in forward, copied to `out` in update
+    int ru = 0, ri = 0;                    // which sort buffer holds each result
+    int mode = 0, B = 0, S = 0, group = 1;
+    bool fused = false;                    // the step ran the single-pass forward (fr_shard_forward)
+    bool planned = false;                  // fr_shard_plan has run for this slot's step (S may be 0: a rank that owns no row of the batch)
+  };
+  struct ShardWs {
+    PlanSlot ps[2];
+    uint64_t n_plan = 0, n_apply = 0;      // plan k writes slot k & 1; forward / update / apply of step k read slot k & 1
+    size_t n_cap = 0;                      // W*cap the owner-side buffers are sized for
+    uint32_t *serve_keys = nullptr, *n_valid = nullptr, *route_counts = nullptr;
     SortBufs sortS;                        // owner side: received requests
     float4* pieces_s = nullptr;
-    int ru = 0, ri = 0, rs = 0;            // which sort buffer holds each result
-    int mode = 0, B = 0, S = 0, group = 1;
-    bool fused = false;                    // the step in flight ran the single-pass forward (fr_shard_forward)
-    bool planned = false;                  // fr_shard_plan has run for the step in flight (S may be 0: a rank that owns no row of the batch)
+    int rs = 0;
     fr::PeerPtrs peer_rbuf{}, peer_rgrows{};   // fr_shard_set_peers: NVLink P2P exchange instead of all-to-alls
   } sh;
   // single-pass training (fr_set_shadow): second copy of Personal_Memory + Adam slots; shadow_dirty = some row's current

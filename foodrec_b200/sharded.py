@@ -89,15 +89,29 @@ class ShardedEngine:
         self.cap = int(cap)
         n = world * self.cap
         dev = self.device
-        self.req = torch.empty(n, dtype=torch.int32, device=dev)
-        self.rreq = torch.empty(n, dtype=torch.int32, device=dev)
+        # two plan slots (fr_shard_plan of step k+1 may overlap update / apply of step k): request buffers and batch
+        # descriptors are per slot; slot of a step = its index & 1 (counters mirror the library's)
+        self._req = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+        self._rreq = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+        self._n_plan = self._n_apply = 0
+        self._slots = [None, None]
+        self._pending = None
         self.rows = torch.empty((n, e.D), dtype=torch.float32, device=dev)
         self.rbuf = torch.empty((n, e.D), dtype=torch.float32, device=dev)
         self.grows = torch.empty((n, e.D), dtype=torch.float32, device=dev)
         self.rgrows = torch.empty((n, e.D), dtype=torch.float32, device=dev)
         self.packed = torch.zeros(int(e.lib.fr_shard_packed_len(e.handle)), dtype=torch.float32, device=dev)
-        self._sh = None
-        self._b = None
+
+    # the request buffers of the step being planned / the step being executed
+    @property
+    def req(self): return self._req[(self._n_plan - 1) & 1] if self._n_plan > self._n_apply else self._req[self._n_plan & 1]
+    @property
+    def rreq(self): return self._rreq[self._n_apply & 1]
+    @property
+    def _b(self): return self._slots[self._n_apply & 1][0]
+    @property
+    def _sh(self): return self._slots[self._n_apply & 1][1]
+    def planned(self): return self._n_plan > self._n_apply
 
     def _shard(self, global_batch):
         return L.fr_shard(self.world, self.rank, self.cap, self.e.I, int(global_batch))
@@ -117,16 +131,18 @@ class ShardedEngine:
             cats = e._f32(categories, (B, 4))
         lab, ws = e._f32(labels, (-1,)), e._f32(write_sign, (-1,))
         ul = e._f32(user_one_hot_label, (B, e.Lb))
-        self._keep = [u, it, cats, lab, ws, ul]
-        self._b = L.fr_batch(L.FR_BPR if bpr else L.FR_POINTWISE, B, _ptr(u), _ptr(it), _ptr(cats), _ptr(lab), _ptr(ws), _ptr(ul))
-        self._sh = self._shard(global_batch if global_batch is not None else B)
+        self._pending = (L.fr_batch(L.FR_BPR if bpr else L.FR_POINTWISE, B, _ptr(u), _ptr(it), _ptr(cats), _ptr(lab), _ptr(ws), _ptr(ul)),
+                         self._shard(global_batch if global_batch is not None else B), [u, it, cats, lab, ws, ul])
 
     def set_batch_dev(self, mode, B, users_local, items, labels=None, global_batch=None):
         """Device tensors already in the C-ABI layout (int32 users [B]; int32 items [S],
         BPR rows interleaved pos/neg): nothing is copied or reshaped."""
-        self._keep = [users_local, items, labels]
-        self._b = L.fr_batch(mode, B, _ptr(users_local), _ptr(items), _ptr(None), _ptr(labels), _ptr(None), _ptr(None))
-        self._sh = self._shard(global_batch if global_batch is not None else B)
+        self._pending = (L.fr_batch(mode, B, _ptr(users_local), _ptr(items), _ptr(None), _ptr(labels), _ptr(None), _ptr(None)),
+                         self._shard(global_batch if global_batch is not None else B), [users_local, items, labels])
+
+    def set_batch_raw(self, batch, keep, global_batch):
+        """An fr_batch built by the caller (device pointers) -- e.g. the reference's dense feed."""
+        self._pending = (batch, self._shard(global_batch), keep)
 
     # un-routed batches ------------------------------------------------------------------
     def route(self, mode, users_global, items, labels=None, rcap=None):
@@ -177,9 +193,20 @@ class ShardedEngine:
 
     # the five phases ------------------------------------------------------------------
     def plan(self):
+        """fr_shard_plan of the batch last given to set_batch*.  May be called while the previous step's update / apply
+        are still queued (on another stream): it writes only its own plan slot."""
         e = self.e
-        L.check(e.handle, e.lib.fr_shard_plan(e.handle, C.byref(self._b), C.byref(self._sh), _ptr(self.req), e._stream()))
-        return self.req
+        if self._pending is None:
+            raise L.FoodRecError("plan(): no batch was set")
+        if self._n_plan - self._n_apply >= 2:
+            raise L.FoodRecError("plan(): both plan slots are in use")
+        slot = self._n_plan & 1
+        b, sh, keep = self._pending
+        L.check(e.handle, e.lib.fr_shard_plan(e.handle, C.byref(b), C.byref(sh), _ptr(self._req[slot]), e._stream()))
+        self._slots[slot] = (b, sh, keep)
+        self._pending = None
+        self._n_plan += 1
+        return self._req[slot]
 
     def set_peers(self, rbuf_ptrs, rgrows_ptrs):
         """fr_shard_set_peers: device pointers of every rank's rbuf / rgrows as mapped into THIS process (own
@@ -216,6 +243,7 @@ class ShardedEngine:
         e = self.e
         L.check(e.handle, e.lib.fr_shard_apply(e.handle, C.byref(self._sh), _ptr(self.rreq), _ptr(self.rgrows), _ptr(e.out),
                                                e._stream()))
+        self._n_apply += 1
         e._dirty = True
         e._catalog_ready = False
         return e.out
@@ -310,11 +338,18 @@ class DistRunner:
         self.dist.all_to_all_single(g._rrecv, send)
         return g.unroute(global_batch)
 
-    def step(self, write_personal=False, phase_events=None):
+    def step(self, write_personal=False, phase_events=None, next_batch=None):
         """One training step.  ``phase_events`` (a list) receives (name, torch.cuda.Event) marks recorded on the
-        step's stream before every phase and after the last one -- bench.py's per-phase timing; None: no overhead."""
+        step's stream before every phase and after the last one -- bench.py's per-phase timing; None: no overhead.
+
+        ``next_batch`` (a callable that gives the NEXT step's batch to ``set_batch*``): its fr_shard_plan and the id
+        all-to-all are issued on a side stream as soon as this step's all-reduce is queued, so they overlap this step's
+        update / apply (they depend only on the batch ids; the library keeps two plan slots).  The next call to step()
+        then starts at ``serve``."""
         d, g = self.dist, self.eng
         p2p = getattr(g, "p2p", False)
+        cuda = torch.device(getattr(g, "device", "cpu")).type == "cuda"     # (the gloo wiring test drives CPU stubs)
+        main = torch.cuda.current_stream(g.device) if cuda else None
 
         def mark(name):
             if phase_events is not None:
@@ -322,8 +357,14 @@ class DistRunner:
                 ev.record()
                 phase_events.append((name, ev))
 
-        mark("plan"); g.plan()
-        mark("ids_all_to_all"); d.all_to_all_single(g.rreq, g.req)               # requests -> owners
+        if g.planned():                                  # planned one step ahead on the side stream
+            mark("plan")
+            if cuda:
+                main.wait_stream(self._side)
+            mark("ids_all_to_all")
+        else:
+            mark("plan"); req = g.plan()
+            mark("ids_all_to_all"); d.all_to_all_single(g._rreq[g._n_apply & 1], req)          # requests -> owners
         mark("serve"); g.serve()                         # p2p: rows land in the requesters' rbuf from inside the kernel
         mark("rows_exchange")
         if p2p:
@@ -332,6 +373,20 @@ class DistRunner:
             d.all_to_all_single(g.rbuf, g.rows)          # recipe rows -> requesters (NVLink)
         mark("forward"); g.forward()
         mark("all_reduce"); d.all_reduce(g.packed)       # loss, sum|g|^2, dCat, dG
+        if next_batch is not None and cuda:
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(device=g.device)
+            # the slot plan(k+1) writes (and its rreq) were last read by step k-1, which ended before this step began
+            if getattr(self, "_step_end", None) is not None:
+                self._side.wait_event(self._step_end)
+            with torch.cuda.stream(self._side):
+                next_batch()
+                req = g.plan()
+                d.all_to_all_single(g._rreq[(g._n_plan - 1) & 1], req)
+        elif next_batch is not None:
+            next_batch()
+            req = g.plan()
+            d.all_to_all_single(g._rreq[(g._n_plan - 1) & 1], req)
         mark("update"); g.update(write_personal)         # p2p: gradient rows land in the owners' rgrows
         mark("grads_exchange")
         if p2p:
@@ -340,6 +395,8 @@ class DistRunner:
             d.all_to_all_single(g.rgrows, g.grows)       # finished gradient rows -> owners
         mark("apply"); out = g.apply()
         mark("end")
+        if cuda:
+            self._step_end = torch.cuda.Event(); self._step_end.record(main)
         return out
 
 
@@ -391,18 +448,36 @@ class LocalRunner:
                 g._rrecv[s_].copy_(sends[s_][r])
         return [g.unroute(global_batch) for g in self.engs]
 
-    def step(self, write_personal=False):
+    def step(self, write_personal=False, plan_ahead=None):
+        """``plan_ahead`` (a callable that sets the NEXT batch on every engine): the next step's plan + request exchange
+        are issued after this step's forward, before its update -- the order DistRunner's side stream allows."""
         p2p = getattr(self.engs[0], "p2p", False)
-        for g in self.engs: g.plan()
-        self._all_to_all("req", "rreq")
+        if not self.engs[0].planned():
+            for g in self.engs: g.plan()
+            self._exchange_requests()
+        self._step_tail(write_personal, p2p, plan_ahead)
+        return self._outs
+
+    def _exchange_requests(self):
+        W = self.W
+        for r, g in enumerate(self.engs):
+            dst = g._rreq[(g._n_plan - 1) & 1].view(W, g.cap)
+            for s_, gs in enumerate(self.engs):
+                dst[s_].copy_(gs._req[(gs._n_plan - 1) & 1].view(W, gs.cap)[r])
+
+    def _step_tail(self, write_personal, p2p, plan_ahead):
         for g in self.engs: g.serve()
         if not p2p: self._all_to_all("rows", "rbuf")
         for g in self.engs: g.forward()
         total = torch.stack([g.packed for g in self.engs]).sum(0)       # rank order, like a ring on W=2
         for g in self.engs: g.packed.copy_(total)
+        if plan_ahead is not None:
+            plan_ahead()
+            for g in self.engs: g.plan()
+            self._exchange_requests()
         for g in self.engs: g.update(write_personal)
         if not p2p: self._all_to_all("grows", "rgrows")
-        return [g.apply() for g in self.engs]
+        self._outs = [g.apply() for g in self.engs]
 
     def catalog_topk(self, users_local_per_rank, K=100):
         """Same protocol as DistRunner.catalog_topk with the collectives as tensor shuffles."""

@@ -175,6 +175,39 @@ def test_unrouted_batches_are_routed_to_their_owners(bpr):
         run.set_batches_unrouted(L.FR_BPR if bpr else L.FR_POINTWISE, batches, global_batch=B, rcap=8)
 
 
+@pytest.mark.parametrize("single_pass", [None, False])
+def test_plan_one_step_ahead_equals_sequential(single_pass):
+    """fr_shard_plan of step k+1 issued between forward and update of step k (what DistRunner's side stream does): the
+    library's two plan slots keep the steps apart -- bit-identical to planning every step in sequence, including a
+    personal-write step and a step in which one rank has no rows."""
+    W = 4
+    p = Problem(403, 257, 9, 64, seed=64)
+    _, a = build(p, W, "adam", "lazy", single_pass=single_pass)
+    _, b = build(p, W, "adam", "lazy", single_pass=single_pass)
+    ra, rb = sharded.LocalRunner(a), sharded.LocalRunner(b)
+    feeds = [p.bpr(300, seed=600 + s, users=None if s != 3 else np.repeat(np.arange(0, 48, 4), 25)) for s in range(6)]
+
+    def setter(engs, s):
+        def f():
+            fd = feeds[s]
+            idx = sharded.route_batch(fd["user_input"], W)
+            for r, g in enumerate(engs):
+                ix = idx[r]
+                g.set_batch(fd["user_input"][ix] // W, fd["item_input"][ix], neg_items=fd["neg_item_input"][ix], global_batch=300)
+        return f
+    for s in range(6):
+        setter(a, s)(); oa = ra.step(write_personal=(s == 1))
+    setter(b, 0)()
+    for s in range(6):
+        ob = rb.step(write_personal=(s == 1), plan_ahead=setter(b, s + 1) if s < 5 else None)
+    assert all(torch.equal(x, y) for x, y in zip(oa, ob))
+    ta, tb_ = gather(a, p), gather(b, p)
+    for k in ("P", "R", "Cat", "G"):
+        np.testing.assert_array_equal(ta[k], tb_[k], err_msg=k)
+    with pytest.raises(Exception, match="plan slots"):
+        setter(b, 0)(); b[0].plan(); setter(b, 1)(); b[0].plan(); setter(b, 2)(); b[0].plan()
+
+
 def test_capacity_overflow_is_reported():
     p = Problem(64, 200, 5, 16, seed=3)
     single, engs = build(p, 2, "sgd", "dense", max_rows=512, cap=4)     # far too small

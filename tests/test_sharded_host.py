@@ -50,32 +50,49 @@ WIRING = textwrap.dedent("""
     dist.init_process_group("gloo")
     r, W, cap, D = dist.get_rank(), dist.get_world_size(), 3, 2
     log = []
-    class Stub:                                   # the five phases, CPU tensors, recognisable payloads
-        rank, world = r, W
+    class Stub:                                   # the five phases, CPU tensors, recognisable payloads; two plan slots
+        rank, world, device = r, W, "cpu"
         def __init__(s):
             n = W * cap
             s.cap = cap
-            s.req = torch.empty(n, dtype=torch.int32); s.rreq = torch.empty(n, dtype=torch.int32)
+            s._req = [torch.empty(n, dtype=torch.int32) for _ in range(2)]; s._rreq = [torch.empty(n, dtype=torch.int32) for _ in range(2)]
+            s._n_plan = s._n_apply = 0; s.batch = None; s.batches = [None, None]
             s.rows = torch.empty(n, D); s.rbuf = torch.empty(n, D)
             s.grows = torch.empty(n, D); s.rgrows = torch.empty(n, D)
             s.packed = torch.zeros(5)
-        def plan(s):                              # request j to owner o carries 100*me + 10*o + j
-            s.req.copy_(torch.tensor([100 * r + 10 * o + j for o in range(W) for j in range(cap)], dtype=torch.int32)); log.append("plan")
-        def serve(s):                             # I am the owner: every request must be addressed to me
+        rreq = property(lambda s: s._rreq[s._n_apply & 1])
+        def planned(s): return s._n_plan > s._n_apply
+        def plan(s):                              # request j to owner o carries 1000*batch + 100*me + 10*o + j
+            slot = s._n_plan & 1; s.batches[slot] = s.batch
+            s._req[slot].copy_(torch.tensor([1000 * s.batch + 100 * r + 10 * o + j for o in range(W) for j in range(cap)], dtype=torch.int32))
+            s._n_plan += 1; log.append("plan%d" % s.batch); return s._req[slot]
+        def serve(s):                             # I am the owner: every request must be addressed to me, for THIS step's batch
+            k = s.batches[s._n_apply & 1]
             v = s.rreq.view(W, cap)
             for src in range(W):
-                assert v[src].tolist() == [100 * src + 10 * r + j for j in range(cap)], v
-            s.rows.copy_((s.rreq.float() + 0.5).unsqueeze(1).expand(-1, D)); log.append("serve")
+                assert v[src].tolist() == [1000 * k + 100 * src + 10 * r + j for j in range(cap)], v
+            s.rows.copy_((s.rreq.float() + 0.5).unsqueeze(1).expand(-1, D)); log.append("serve%d" % k)
         def forward(s):                           # rows come back in MY slot order o*cap + j
-            assert s.rbuf[:, 0].tolist() == [100 * r + 10 * o + j + 0.5 for o in range(W) for j in range(cap)]
-            s.packed.fill_(r + 1.0); log.append("forward")
+            k = s.batches[s._n_apply & 1]
+            assert s.rbuf[:, 0].tolist() == [1000 * k + 100 * r + 10 * o + j + 0.5 for o in range(W) for j in range(cap)]
+            s.packed.fill_(r + 1.0); log.append("forward%d" % k)
         def update(s, wp):
             assert s.packed.tolist() == [sum(range(1, W + 1))] * 5      # all-reduce SUM
-            s.grows.copy_(s.rbuf * -1.0); log.append("update")
-        def apply(s):                             # gradient rows aligned with the requests I received
+            s.grows.copy_(s.rbuf * -1.0); log.append("update%d" % s.batches[s._n_apply & 1])
+        def apply(s):                             # gradient rows aligned with the requests I received for this step
             assert torch.equal(s.rgrows[:, 0], -(s.rreq.float() + 0.5))
-            log.append("apply"); return "done"
-    assert DistRunner(Stub()).step() == "done" and log == ["plan", "serve", "forward", "update", "apply"]
+            log.append("apply%d" % s.batches[s._n_apply & 1]); s._n_apply += 1; return "done"
+    g = Stub(); run = DistRunner(g)
+    def batch(k):
+        def f(): g.batch = k
+        return f
+    batch(0)()
+    assert run.step() == "done" and log == ["plan0", "serve0", "forward0", "update0", "apply0"]
+    # pipelined: the NEXT step's plan + request exchange are issued between this step's forward and update
+    del log[:]; batch(1)()
+    assert run.step(next_batch=batch(2)) == "done" and run.step(next_batch=batch(3)) == "done" and run.step() == "done"
+    assert log == ["plan1", "serve1", "forward1", "plan2", "update1", "apply1", "serve2", "forward2", "plan3", "update2", "apply2",
+                   "serve3", "forward3", "update3", "apply3"], log
     sys.stdout.write("WIRING_OK_%d\\n" % r); sys.stdout.flush()
 """)
 
