@@ -562,32 +562,42 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
         neg = rng.integers(0, I, B).astype(np.int32); neg[neg == pos] = (neg[neg == pos] + 1) % I
         gb.append((torch.as_tensor(users).to(dev), torch.as_tensor(np.stack([pos, neg], 1).reshape(-1).copy()).to(dev)))
 
-    def ustep(k, evs=None):
-        if eng.planned():
-            run.step()
+    def uset(k):
         u, it = gb[k % NB]
-        if evs is not None:
-            a = torch.cuda.Event(enable_timing=True); a.record()
         run.set_batch_unrouted(L.FR_BPR, u, it, global_batch=world * B)
-        if evs is not None:
-            b_ = torch.cuda.Event(enable_timing=True); b_.record(); evs.append((a, b_))
-        return run.step()
+
+    def ustep(k):
+        # routing of batch k+1 (bucket, all-to-all, compaction, the host read of its size) rides on the side stream
+        # under step k, like the plan: the timed region contains every routing call
+        if not eng.planned() and eng._pending is None:
+            uset(k)
+        return run.step(next_batch=None if args.no_plan_ahead else (lambda: uset(k + 1)))
+    while eng.planned():                                    # a plan left over from the pipelined legs: run it out
+        run.step()
     for k in range(3):
         ustep(k)
     u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize()
     u0.record()
-    revs = []
     for k in range(steps):
-        ustep(k, revs)
+        ustep(k)
     u1.record()
     dist.barrier(); torch.cuda.synchronize()
     tt = torch.tensor([u0.elapsed_time(u1)], device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ums = float(tt.item())
-    route_ms = sum(a.elapsed_time(b_) for a, b_ in revs) / max(len(revs), 1)
-    unrouted = {"value": world * B * steps / (ums / 1e3), "unit": UNIT, "ms_per_step": ums / steps, "route_ms_per_step_rank0": route_ms,
+    while eng.planned():
+        run.step()
+    ra, rb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)       # routing alone, un-overlapped
+    torch.cuda.synchronize(); ra.record()
+    for k in range(5):
+        uset(k)
+    rb.record(); torch.cuda.synchronize()
+    route_ms = ra.elapsed_time(rb) / 5
+    eng._pending = None
+    unrouted = {"value": world * B * steps / (ums / 1e3), "unit": UNIT, "ms_per_step": ums / steps, "route_ms_alone_rank0": route_ms,
                 "exchange_bytes_per_gpu": int(eng._rsend.numel() * 4 * (world - 1) / world),
                 "note": "samples arrive on a random rank: bucket by owner + ONE all-to-all + compaction (fr_shard_route / "
-                        "fr_shard_unroute) inside the timed region; the routed size is read on the host every step"}
+                        "fr_shard_unroute) inside the timed region, issued one step ahead on the side stream like the plan; "
+                        "the routed size is read on the host every step"}
     res = {
         "label": label, "value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "launches": int(launches),
         "window": (t_begin, t_end), "single_pass": fused, "p2p": p2p, "cap": eng.cap,

@@ -39,6 +39,8 @@ static int plan_slot_ensure(fr_ctx* h, int idx, size_t S) {
     }
   }
   if (S > ps.s_cap) {
+    if (S < (size_t)h->cfg.max_rows) S = (size_t)h->cfg.max_rows;     // once, at capacity: the row count of an un-routed
+                                                                      // batch changes every step and a regrow synchronises
     if ((rc = ws_alloc(h, &ps.okeys, S)) || (rc = ws_alloc(h, &ps.flags, S)) || (rc = ws_alloc(h, &ps.excl, S)) ||
         (rc = ws_alloc(h, &ps.slot_sorted, S)) || (rc = ws_alloc(h, &ps.slot_of_row, S)) ||
         (rc = ws_alloc(h, &ps.cats_row, S)))

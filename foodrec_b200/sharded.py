@@ -164,9 +164,10 @@ class ShardedEngine:
             self._rsend = torch.empty((self.world, blk), dtype=torch.int32, device=self.device)
             self._rrecv = torch.empty_like(self._rsend)
             cap_out = e.max_rows // group
-            self._ru = torch.empty(cap_out, dtype=torch.int32, device=self.device)
-            self._ri = torch.empty(cap_out * group, dtype=torch.int32, device=self.device)
-            self._ry = torch.empty(cap_out, dtype=torch.float32, device=self.device)
+            # (two sets: the routed batch of step k+1 is written while step k may still read its own)
+            self._rus = [torch.empty(cap_out, dtype=torch.int32, device=self.device) for _ in range(2)]
+            self._ris = [torch.empty(cap_out * group, dtype=torch.int32, device=self.device) for _ in range(2)]
+            self._rys = [torch.empty(cap_out, dtype=torch.float32, device=self.device) for _ in range(2)]
             self._rn = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._rflag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._rflag.zero_()
@@ -180,6 +181,8 @@ class ShardedEngine:
         e = self.e
         mode = self._rmode
         group = 2 if mode == L.FR_BPR else 1
+        k = self._n_plan & 1
+        self._ru, self._ri, self._ry = self._rus[k], self._ris[k], self._rys[k]
         L.check(e.handle, e.lib.fr_shard_unroute(e.handle, mode, self.world, int(self._rcap), _ptr(self._rrecv), self._ru.numel(),
                                                  _ptr(self._ru), _ptr(self._ri), _ptr(self._ry), _ptr(self._rn), _ptr(self._rflag),
                                                  e._stream()))
@@ -343,9 +346,8 @@ class DistRunner:
         step's stream before every phase and after the last one -- bench.py's per-phase timing; None: no overhead.
 
         ``next_batch`` (a callable that gives the NEXT step's batch to ``set_batch*``): its fr_shard_plan and the id
-        all-to-all are issued on a side stream as soon as this step's all-reduce is queued, so they overlap this step's
-        update / apply (they depend only on the batch ids; the library keeps two plan slots).  The next call to step()
-        then starts at ``serve``."""
+        all-to-all are issued on a side stream, so they execute under this step's kernels (they depend only on the
+        batch ids; the library keeps two plan slots).  The next call to step() then starts at ``serve``."""
         d, g = self.dist, self.eng
         p2p = getattr(g, "p2p", False)
         cuda = torch.device(getattr(g, "device", "cpu")).type == "cuda"     # (the gloo wiring test drives CPU stubs)
@@ -373,20 +375,6 @@ class DistRunner:
             d.all_to_all_single(g.rbuf, g.rows)          # recipe rows -> requesters (NVLink)
         mark("forward"); g.forward()
         mark("all_reduce"); d.all_reduce(g.packed)       # loss, sum|g|^2, dCat, dG
-        if next_batch is not None and cuda:
-            if getattr(self, "_side", None) is None:
-                self._side = torch.cuda.Stream(device=g.device)
-            # the slot plan(k+1) writes (and its rreq) were last read by step k-1, which ended before this step began
-            if getattr(self, "_step_end", None) is not None:
-                self._side.wait_event(self._step_end)
-            with torch.cuda.stream(self._side):
-                next_batch()
-                req = g.plan()
-                d.all_to_all_single(g._rreq[(g._n_plan - 1) & 1], req)
-        elif next_batch is not None:
-            next_batch()
-            req = g.plan()
-            d.all_to_all_single(g._rreq[(g._n_plan - 1) & 1], req)
         mark("update"); g.update(write_personal)         # p2p: gradient rows land in the owners' rgrows
         mark("grads_exchange")
         if p2p:
@@ -395,8 +383,26 @@ class DistRunner:
             d.all_to_all_single(g.rgrows, g.grows)       # finished gradient rows -> owners
         mark("apply"); out = g.apply()
         mark("end")
+        prev_end = getattr(self, "_step_end", None)
         if cuda:
             self._step_end = torch.cuda.Event(); self._step_end.record(main)
+        # The next step's plan + id all-to-all, issued on the side stream once THIS step is fully queued (the host runs
+        # ahead of the device, so they still execute under this step's kernels; a next_batch that has to wait for the
+        # device -- an un-routed batch reads its routed size -- then blocks the host while the device is busy).
+        if next_batch is not None and cuda:
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(device=g.device)
+            # the slot plan(k+1) writes (and its rreq) were last read by step k-1, which ended before this step began
+            if prev_end is not None:
+                self._side.wait_event(prev_end)
+            with torch.cuda.stream(self._side):
+                next_batch()
+                req = g.plan()
+                d.all_to_all_single(g._rreq[(g._n_plan - 1) & 1], req)
+        elif next_batch is not None:
+            next_batch()
+            req = g.plan()
+            d.all_to_all_single(g._rreq[(g._n_plan - 1) & 1], req)
         return out
 
 

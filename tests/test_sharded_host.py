@@ -88,10 +88,10 @@ WIRING = textwrap.dedent("""
         return f
     batch(0)()
     assert run.step() == "done" and log == ["plan0", "serve0", "forward0", "update0", "apply0"]
-    # pipelined: the NEXT step's plan + request exchange are issued between this step's forward and update
+    # pipelined: the NEXT step's plan + request exchange are issued once this step is queued, before the next serve
     del log[:]; batch(1)()
     assert run.step(next_batch=batch(2)) == "done" and run.step(next_batch=batch(3)) == "done" and run.step() == "done"
-    assert log == ["plan1", "serve1", "forward1", "plan2", "update1", "apply1", "serve2", "forward2", "plan3", "update2", "apply2",
+    assert log == ["plan1", "serve1", "forward1", "update1", "apply1", "plan2", "serve2", "forward2", "update2", "apply2", "plan3",
                    "serve3", "forward3", "update3", "apply3"], log
     sys.stdout.write("WIRING_OK_%d\\n" % r); sys.stdout.flush()
 """)
