@@ -132,6 +132,7 @@ extern "C" int fr_destroy(fr_handle h) {
   if (h->stage) cudaFree(h->stage);
   for (auto& sl : h->feed) { if (sl.buf) cudaFree(sl.buf); if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->aux_fork); cudaEventDestroy(h->aux_join); }
   if (h->pieces_personal) cudaFree(h->pieces_personal);
   delete h;
   return FR_OK;
@@ -360,6 +361,34 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   launch_prep_rows(b->mode, B, b->users, b->items, b->labels, b->write_sign, h->cfg.num_users, h->cfg.num_items, h->ukeys,
                    h->ws_row, h->users_s, h->items_s, out + FR_OUT_OVERFLOW, l);
   const int32_t *users = h->users_s, *items = h->items_s;      // range-checked: every kernel below reads these
+  // 1b. FORK: the General_Memory pass's entry list -- non-zeros of the label feed -> (label, row, coef), sorted by label
+  //     -- depends only on the batch.  It is ~0.1 ms of small latency-bound kernels (count, scan, emit, one radix pass)
+  //     that used to sit on the step's critical path; they now run on a side stream beside the sorts / catch-up /
+  //     forward (which are small or bandwidth-bound) and are joined before the label segment-reduce needs them.
+  int rl = 0;
+  const uint32_t ecap = (uint32_t)h->sortL.cap;
+  {
+    if (!h->aux_stream) {
+      FR_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+      FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming));
+      FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming));
+    }
+    FR_CUDA(h, cudaEventRecord(h->aux_fork, st));
+    FR_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+    Launch la{h->sm_count, h->aux_stream, nullptr};
+    LabelEmitParams ep{};
+    ep.S = S; ep.group = group; ep.L = h->mc.L; ep.users = users;
+    ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
+    ep.ws_row = h->ws_row; ep.counts = h->counts; ep.offs = h->offs;
+    ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
+    ep.cap = ecap; ep.n_entries = h->n_entries; ep.out = out;
+    launch_label_count(ep, la);
+    exclusive_scan_u32(h->counts, h->offs, (uint32_t)S, h->scan_tmp, h->n_entries, h->aux_stream);
+    launch_label_emit(ep, la);
+    rl = radix_sort_pairs(h->sortL, h->ent_key, ecap, h->n_entries, bits_for(h->mc.L), h->aux_stream, h->sm_count);
+    FR_CHECK_LAUNCH(h);
+    FR_CUDA(h, cudaEventRecord(h->aux_join, h->aux_stream));
+  }
   SortJob sj[2] = {{&h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), 0},
                    {&h->sortI, (const uint32_t*)items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), 0}};
   radix_sort_jobs(sj, 2, st, h->sm_count);      // by user and by recipe, sharing their launches
@@ -460,23 +489,12 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   }
 
   FR_MARK(FR_T_LABEL);
-  // 5. General_Memory: label feed -> entries -> sort by label -> segment-reduce (reads pre-step R).
+  // 5. General_Memory: segment-reduce of the label entries (built in 1b) by label (reads pre-step R).
   //    (Round 2 tried a shared-memory scatter with one owner warp per label instead -- no sort, no entry list: measured
   //    354 us + 25 us against this pass's 254 us at 524k rows; see DESIGN.md "measured and rejected".)
   {
     l.mid = nullptr;
-    LabelEmitParams ep{};
-    ep.S = S; ep.group = group; ep.L = h->mc.L; ep.users = users;
-    ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
-    ep.ws_row = h->ws_row; ep.counts = h->counts; ep.offs = h->offs;
-    ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
-    ep.cap = (uint32_t)h->sortL.cap; ep.n_entries = h->n_entries; ep.out = out;
-    launch_label_count(ep, l);
-    exclusive_scan_u32(h->counts, h->offs, (uint32_t)S, h->scan_tmp, h->n_entries, st);
-    launch_label_emit(ep, l);
-    const uint32_t ecap = (uint32_t)h->sortL.cap;
-    const int rl = radix_sort_pairs(h->sortL, h->ent_key, ecap, h->n_entries, bits_for(h->mc.L), st, h->sm_count);
-    FR_CHECK_LAUNCH(h);
+    FR_CUDA(h, cudaStreamWaitEvent(st, h->aux_join, 0));      // JOIN: the entry list built on the side stream (1b)
     SegCommon c{};
     c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
     c.pieces = h->pieces_g; c.uniq_counter = nullptr;

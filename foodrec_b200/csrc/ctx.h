@@ -87,6 +87,9 @@ struct fr_ctx {
     cudaEvent_t copied = nullptr, consumed = nullptr;
   } feed[2];
   cudaStream_t copy_stream = nullptr;
+  // fork / join inside fr_train_step: the label feed's entry list (count, scan, emit, sort by label) depends only on the
+  // batch and is built on this stream while the sorts, catch-up and the forward run on the caller's
+  cudaStream_t aux_stream = nullptr; cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   int feed_next = 0;
   // per-phase timing (fr_timing_*)
   bool timing = false;
