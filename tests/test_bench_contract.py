@@ -33,6 +33,35 @@ def test_reference_arm_runs_and_prints_the_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_*gpu.json"))))
+def test_round2_gpu_lines_carry_the_contract(path):
+    d = last_json_line(open(path).read())
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "bpr_train_triples_per_sec" and d["scaling"] == "weak" and d["dtype"] == "f32"
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"] and d["single_pass"] is True
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    rf, rs = d["roofline"], d["roofline_step"]
+    assert rf["bound"] == "hbm" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0.4 < rf["frac"] < 1.0
+    assert rs["bound"] == "hbm" and 0.3 < rs["frac"] < 1.0
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["value"] != d["value"] and "dense feed" in e["feed"]
+    if d["n_gpus"] == 1:
+        assert d["ms_per_step"] < 1.5                                   # round 1: 1.659
+        assert abs(sorted(e["runs"])[1] - e["value"]) < 1e-6 * e["value"]   # the MEDIAN of the three runs
+        assert d["cpu_baseline"]["kind"] == "port" and d["cfg1"]["cpu_baseline"]["value"] > 0 and d["cfg1"]["gpu_e2e"]["value"] > 0
+        c2, c4 = d["catalog_topk"]
+        assert c2["fallback_rows"] == 0 and c2["train_steps_before"] >= 400     # the catalog leg runs AFTER the training legs
+        assert c4["users"] == 1_000_000 and c4["recipes"] == 10_000_000 and c4["fallback_rows"] == 0   # cfg4 in full
+    else:
+        sc = d["self_check"]
+        assert sc["ok"] is True and sc["loss_rel_err"] <= 1e-5 and max(sc["table_rel_err"].values()) <= 1e-4
+        assert d["shard_phases_ms"] and d["unrouted"]["value"] > 0 and d["e2e_compact"]["value"] > d["e2e"]["value"]
+        assert d["value"] > 0.7 * d["n_gpus"] * 184e6                    # weak scaling at constant per-GPU work >= 70 %
+        if d["n_gpus"] == 8:
+            assert d["cfg3"]["value"] > 0 and d["cfg3"]["local_rows"]["users"] == 12_500_000
+            assert "cfg4 IN FULL" in d["catalog_topk"][1]["workload"]
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r01c_bench_*gpu.json"))))
 def test_committed_gpu_lines_carry_the_contract(path):
     d = last_json_line(open(path).read())
