@@ -361,6 +361,125 @@ def cfg1_gpu_leg(dev, steps=200, B=128):
 
 
 # ----------------------------------------------------------------------------- GPU arm, N > 1
+def table_bytes(learner, bf16):
+    """bytes per table ELEMENT: (a row read for scoring, the optimizer's read + write of the variable and its fp32 slots)"""
+    slots = {"adam": 2, "adagrad": 1, "rmsprop": 2, "sgd": 0}[learner.lower()]
+    vb = 2 if bf16 else 4
+    return vb, 2 * vb + 8 * slots
+
+
+def cfg5_leg(args, cfg, B, dev, steps, n_neg=8):
+    """BASELINE configs[4] on ONE GPU: 1:8 sampled negatives (fr_sample_bpr_batch, Philox, drawn on the device inside the
+    timed region), Adagrad, Personal_Memory / Recipe_Embedding stored in bf16 (fp32 arithmetic, RNE on store, fp32
+    accumulators), the health term blended into sampled top-K at inference.  The same leg on fp32 tables runs beside it."""
+    import torch
+    from foodrec_b200 import Engine, Hyper, _lib as L
+    import synth_data as synth
+    U, I, Lb, D = cfg["U"], cfg["I"], cfg["L"], cfg["D"]
+    item_cats = synth.make_item_categories(I)
+    lab = synth.make_user_label_csr(U, Lb)
+    n_pos = B // n_neg
+    NB = 8
+    pins = []
+    for k in range(NB):
+        rng = np.random.default_rng(5000 + k)
+        pins.append((torch.as_tensor(rng.integers(0, U, n_pos).astype(np.int32)).pin_memory(),
+                     torch.as_tensor(synth.zipf_items(rng, I, n_pos).astype(np.int32)).pin_memory()))
+    devb = [(u.to(dev), p_.to(dev)) for u, p_ in pins]
+    peak, peak_src = peaks()
+    out = {}
+    for td in ("float32", "bf16"):
+        g = torch.Generator(device=dev); g.manual_seed(5)
+        cast = (lambda x: x.to(torch.bfloat16)) if td == "bf16" else (lambda x: x)
+        P = cast(torch.randn((U, 5, D), device=dev, generator=g) * 0.1); R = cast(torch.randn((I, D), device=dev, generator=g) * 0.1)
+        Cat = torch.randn((4, D), device=dev, generator=g) * 0.1; G = torch.randn((Lb, 5, D), device=dev, generator=g) * 0.1
+        eng = Engine(Hyper(learner="adagrad", lr=0.01), P, R, Cat, G, device=dev, max_rows=2 * B, item_cats=item_cats,
+                     user_label_csr=lab, adopt=True, table_dtype=td)
+        del P, R
+
+        def step(k):
+            u, p_ = devb[k % NB]
+            eng.train_step_sampled(u, p_, n_neg, seed=20260105, sample_offset=k * n_pos)
+        for k in range(10 + max(args.warmup, 3)):
+            step(k)
+        v = eng.read_scalars()
+        uu, ui = float(v[L.FR_OUT_UNIQ_USERS]), float(v[L.FR_OUT_UNIQ_ITEMS])
+        l0 = eng.lib.fr_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for k in range(steps):
+            step(k)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = eng.lib.fr_launch_count() - l0
+        eng.timing_enable(True)
+        for k in range(steps):
+            step(k)
+        torch.cuda.synchronize()
+        ph, _ = eng.timing_read()
+        eng.timing_enable(False)
+        rb, ub = table_bytes("adagrad", td == "bf16")
+        alg = {"fwd": B * (7 * D * rb + 16), "user_chunk": uu * 5 * D * ub, "item_chunk": ui * D * ub}
+        kern = {k: {"ms": ph[k], "alg_bytes": alg[k], "gbs": alg[k] / (ph[k] * 1e-3) / 1e9 if ph[k] > 0 else None} for k in alg}
+        # the 8 triples of a positive share their user row and positive recipe row: the bytes that MUST come from HBM are
+        # those of the distinct rows (the SURVEY 8(d) per-triple figure above counts every row of every triple)
+        kern["fwd"]["distinct_row_bytes"] = uu * 5 * D * rb + ui * D * rb + B * 16
+        step_bytes = alg["fwd"] + alg["user_chunk"] + alg["item_chunk"] + 4 * Lb * 5 * D
+        dom = max(alg, key=lambda k: ph[k])
+        # e2e: the (user, positive) pairs from pinned host memory, sampled + expanded on the device, loss read every step
+        ub_, pb_ = torch.empty(n_pos, dtype=torch.int32, device=dev), torch.empty(n_pos, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            hu, hp = pins[k % NB]
+            ub_.copy_(hu, non_blocking=True); pb_.copy_(hp, non_blocking=True)
+            eng.train_step_sampled(ub_, pb_, n_neg, seed=20260105, sample_offset=k * n_pos)
+            loss = float(eng.read_scalars()[L.FR_OUT_LOSS])
+        dt = time.perf_counter() - t0
+        # sampled top-K (51 candidates, K=10) with the health term blended in (fr_set_health_blend)
+        NU = min(U, 1 << 20)
+        rng = np.random.default_rng(5)
+        eu = torch.as_tensor(rng.permutation(U)[:NU].astype(np.int32)).to(dev)
+        cand = torch.as_tensor(rng.integers(0, I, (NU, 51)).astype(np.int32)).to(dev)
+        nc = torch.full((NU,), 51, dtype=torch.int32, device=dev)
+        eng.set_health_blend(True)
+        eng.eval_sampled_topk(eu, cand, nc, 10); torch.cuda.synchronize()
+        e0.record(); eng.eval_sampled_topk(eu, cand, nc, 10); e1.record(); torch.cuda.synchronize()
+        ems = e0.elapsed_time(e1)
+        ealg = NU * (5 * D * rb + 51 * D * rb + 51 * 12)
+        out[td] = {
+            "metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "gpu_launches": int(launches),
+            "phases_ms": {k: x for k, x in ph.items() if x > 0}, "kernels": kern,
+            "roofline": {"bound": "hbm", "kernel": {"fwd": "fwd_train_kernel", "user_chunk": "seg_chunk_kernel<UserPol>",
+                                                    "item_chunk": "seg_chunk_kernel<ItemPol>"}[dom],
+                         "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
+                         "peak_source": peak_src, "alg_bytes_per_launch": alg[dom], "ms_per_launch": ph[dom], "traffic": None},
+            "roofline_step": {"bound": "hbm", "alg_bytes_per_step": step_bytes, "achieved": step_bytes / (ms * 1e-3) / 1e9,
+                              "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms * 1e-3) / 1e9 / peak},
+            "e2e": {"value": B * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * n_pos, "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
+                    "feed": "(user, positive) pairs from pinned host memory; negatives drawn and the batch expanded on the device; "
+                            "loss read every step", "last_loss": loss},
+            "topk_health": {"metric": "sampled_topk_users_per_sec", "value": NU / (ems * 1e-3), "unit": "users/s", "ms": ems,
+                            "users": NU, "candidates": 51, "K": 10,
+                            "roofline": {"bound": "hbm", "achieved": ealg / (ems * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                         "frac": ealg / (ems * 1e-3) / 1e9 / peak}},
+            "uniq_users_per_step": uu, "uniq_items_per_step": ui,
+        }
+        eng.close(); del eng
+        torch.cuda.empty_cache()
+    res = out["bf16"]
+    res["workload"] = (f"cfg5 (BASELINE configs[4]) on one GPU: {U} users x {I} recipes x {Lb} labels, D={D}; {n_pos} positives x "
+                       f"{n_neg} sampled negatives = {B} BPR triples per step; Adagrad; bf16 Personal_Memory / Recipe_Embedding "
+                       "(fp32 arithmetic and accumulators, round-to-nearest-even on store); health term at inference")
+    res["dtype"] = "f32 arithmetic, bf16 table storage"
+    f = out["float32"]
+    res["same_leg_fp32_tables"] = {"value": f["value"], "ms_per_step": f["ms_per_step"], "phases_ms": f["phases_ms"],
+                                   "roofline_step_frac": f["roofline_step"]["frac"], "topk_health_ms": f["topk_health"]["ms"],
+                                   "e2e": f["e2e"]["value"]}
+    res["speedup_vs_fp32_tables"] = res["value"] / f["value"]
+    return res
+
+
 def shard_self_check(rank, world, dev, p2p):
     """Correctness of the N-rank step IN the bench run (the 2-GPU pytest cannot run on a 1-GPU lease): a small problem is
     trained for a few steps through the same DistRunner (same collectives, same peer-store path) while rank 0 trains
@@ -429,8 +548,11 @@ def shard_self_check(rank, world, dev, p2p):
     return res
 
 
-def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll, warmup, label, single_pass=None):
-    """One weak-scaling training measurement: every rank holds `cfg_local` rows (its shard), B triples per rank per step."""
+def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll, warmup, label, single_pass=None,
+                      learner=None, table_dtype="float32", n_neg=0, extras=True):
+    """One weak-scaling training measurement: every rank holds `cfg_local` rows (its shard), B triples per rank per step.
+    n_neg > 0: B/n_neg (user, positive) pairs per rank, negatives drawn on the device over the global catalog
+    (fr_sample_bpr_batch) inside the timed region.  extras=False: no e2e / un-routed legs."""
     import torch
     import torch.distributed as dist
     from foodrec_b200 import Hyper, _lib as L
@@ -438,15 +560,20 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
     import synth_data as synth
     Ul, Il, Lb, D = cfg_local["U"], cfg_local["I"], cfg_local["L"], cfg_local["D"]
     I = Il * world
+    learner = learner or args.learner
+    bf16 = table_dtype == "bf16"
     g = torch.Generator(device=dev); g.manual_seed(1 + rank)
     P = torch.empty((Ul, 5, D), device=dev).normal_(0, 0.1, generator=g); R = torch.empty((Il, D), device=dev).normal_(0, 0.1, generator=g)
+    if bf16:
+        P, R = P.to(torch.bfloat16), R.to(torch.bfloat16)
     g2 = torch.Generator(device=dev); g2.manual_seed(99)          # replicated tables: same on every rank
     Cat = torch.randn((4, D), device=dev, generator=g2) * 0.1; G = torch.randn((Lb, 5, D), device=dev, generator=g2) * 0.1
     item_cats = synth.make_item_categories(I)
     lab = synth.make_user_label_csr(Ul, Lb, seed=synth.BASE_SEED + 200 + rank)
-    eng = ShardedEngine(Hyper(learner=args.learner, lr=0.001), P, R, Cat, G, rank, world, device=dev, max_rows=2 * B + 16384,
+    eng = ShardedEngine(Hyper(learner=learner, lr=0.001), P, R, Cat, G, rank, world, device=dev, max_rows=2 * B + 16384,
                         adam_mode=args.adam_mode, item_cats_global=item_cats, user_label_csr_local=lab, adopt=True,
-                        single_pass=single_pass)       # (+16384 rows: an un-routed batch lands B +- a few hundred groups per rank)
+                        single_pass=single_pass, table_dtype=table_dtype)
+    # (+16384 rows: an un-routed batch lands B +- a few hundred groups per rank)
     del P, R
     run = DistRunner(eng)
     if p2p:
@@ -459,12 +586,17 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
         pos = synth.zipf_items(rng, I, B)
         neg = rng.integers(0, I, B).astype(np.int32); neg[neg == pos] = (neg[neg == pos] + 1) % I
         items = np.stack([pos, neg], 1).reshape(-1).copy()
+        if n_neg:
+            users, items = users[:B // n_neg].copy(), pos[:B // n_neg].astype(np.int32)
         pin.append((torch.as_tensor(users).pin_memory(), torch.as_tensor(items).pin_memory()))
         devb.append((pin[-1][0].to(dev), pin[-1][1].to(dev)))
 
     def setb(k):
         u, it = devb[k % NB]
-        eng.set_batch_dev(L.FR_BPR, B, u, it, global_batch=world * B)
+        if n_neg:
+            eng.set_batch_sampled(u, it, n_neg, seed=20260105, sample_offset=(k * world + rank) * (B // n_neg), global_batch=world * B)
+        else:
+            eng.set_batch_dev(L.FR_BPR, B, u, it, global_batch=world * B)
 
     def step(k, **kw):
         # the NEXT step's fr_shard_plan + id all-to-all ride on a side stream under this step's update / apply
@@ -504,7 +636,8 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
             shard_ms[name] = shard_ms.get(name, 0.0) + e0.elapsed_time(e1) / n_ph
     v = eng.e.read_scalars()
     peak, peak_src = peaks()
-    adam_k = {"adam": 6, "adagrad": 4, "rmsprop": 6, "sgd": 2}.get(args.learner.lower(), 2)
+    rb, upd = table_bytes(learner, bf16)
+    adam_k = upd / 4                     # (fp32: 6 for Adam = var + m + v read and written; kept as a factor of 4-byte words)
     uu, ui = float(v[L.FR_OUT_UNIQ_USERS]), float(v[L.FR_OUT_UNIQ_ITEMS])
     fused = bool(eng.e.single_pass)
     # dominant kernel on rank 0: the single-pass kernel lives in the `forward` phase, the two-pass user pass in `update`
@@ -516,12 +649,25 @@ def sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, steps, preroll,
         kms = sphases.get("user_chunk", 0.0)
         kalg = uu * adam_k * 20 * D
         kname, kscope = "seg_chunk_kernel<UserPol>", "per GPU (rank 0)"
+        if sphases.get("fwd", 0.0) > kms:           # (1:8 sampled negatives: few distinct users, the forward dominates)
+            kms, kalg, kname = sphases["fwd"], B * (7 * D * rb + 16), "fwd_train_kernel"
     sroof = None
     if kms > 0:
         sroof = {"bound": "hbm", "kernel": kname, "achieved": kalg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                  "frac": kalg / (kms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "alg_bytes_per_launch": kalg,
                  "ms_per_launch": kms, "scope": kscope, "traffic": None}
-    step_bytes = B * (28 * D + 16) + uu * adam_k * 20 * D + ui * adam_k * 4 * D + 4 * Lb * 5 * D
+    step_bytes = B * (7 * D * rb + 16) + uu * adam_k * 20 * D + ui * adam_k * 4 * D + 4 * Lb * 5 * D
+    if not extras:
+        res = {
+            "label": label, "value": world * B * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "launches": int(launches), "window": (t_begin, t_end), "p2p": p2p, "cap": eng.cap, "optimizer": learner,
+            "table_dtype": table_dtype, "sampled_negatives_per_positive": n_neg,
+            "local_rows": {"users": Ul, "recipes": Il}, "global_rows": {"users": Ul * world, "recipes": I},
+            "roofline": sroof, "shard_phases_ms": shard_ms, "update_phase_kernels_ms": {k: sphases[k] for k in sphases if sphases[k] > 0},
+            "roofline_step": {"bound": "hbm", "alg_bytes_per_step_per_gpu": step_bytes, "achieved": step_bytes / (ms / steps * 1e-3) / 1e9,
+                              "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms / steps * 1e-3) / 1e9 / peak, "scope": "per GPU"},
+            "uniq_users_per_step": uu, "uniq_items_per_step": ui, "overflow_flag": float(v[L.FR_OUT_OVERFLOW])}
+        return res, eng, run
     # e2e, both feeds: ids only (side tables resident) and the reference's dense feed (categories + user_one_hot_label)
     ubuf = torch.empty(B, dtype=torch.int32, device=dev); ibuf = torch.empty(2 * B, dtype=torch.int32, device=dev)
 
@@ -710,6 +856,21 @@ def run_sharded(args, cfg, B):
             "dense_equivalent_tflops_per_gpu": 2.0 * n_users4 * Il4 * 5 * D / (cms4 * 1e-3) / 1e12}]
         e4.e.close(); del e4, run4
         torch.cuda.empty_cache()
+    # ---- BASELINE configs[4]: 1:8 sampled negatives, Adagrad, bf16 tables, row-sharded like the main leg (and the same
+    # leg on fp32 tables beside it)
+    cfg5_line = None
+    if not args.small and not args.cfg3 and not args.no_cfg5:
+        c5 = {}
+        for td in ("float32", "bf16"):
+            c5[td], e5, r5 = sharded_train_leg(args, cfg_local, B, rank, world, dev, p2p, args.steps, 10, 3,
+                                               "cfg5 (BASELINE configs[4]): 1:8 sampled negatives, Adagrad, " + td + " tables; " + mode,
+                                               single_pass=False, learner="adagrad", table_dtype=td, n_neg=8, extras=False)
+            c5[td].pop("window")
+            e5.e.close(); del e5, r5
+            torch.cuda.empty_cache()
+        cfg5_line = c5["bf16"]
+        cfg5_line["same_leg_fp32_tables"] = {k: c5["float32"][k] for k in ("value", "ms_per_step", "shard_phases_ms", "update_phase_kernels_ms")}
+        cfg5_line["speedup_vs_fp32_tables"] = c5["bf16"]["value"] / c5["float32"]["value"]
     # ---- BASELINE configs[2] at N = 8: 100M users / 10M recipes row-sharded (12.5M users = 96 GB of P + Adam slots per
     # GPU: no room for the single-pass shadow copy -> two-pass step), fewer steps (the tables take a while to fill)
     cfg3_line = None
@@ -738,7 +899,7 @@ def run_sharded(args, cfg, B):
             "update_phase_kernels_ms": main["update_phase_kernels_ms"], "self_check": check,
             "e2e": main["e2e"], "e2e_compact": main["e2e_compact"], "unrouted": main["unrouted"],
             "uniq_users_per_step": main["uniq_users_per_step"], "uniq_items_per_step": main["uniq_items_per_step"],
-            "overflow_flag": main["overflow_flag"], "cfg3": cfg3_line}
+            "overflow_flag": main["overflow_flag"], "cfg3": cfg3_line, "cfg5": cfg5_line}
         print(json.dumps(line, default=float))
     dist.destroy_process_group()
 
@@ -981,6 +1142,9 @@ def run_ours(args, cfg, B):
             eng = e4
         catalog_launches = catalog_launches_cfg2 + eng.lib.fr_launch_count() - launches_c0
 
+    cfg5 = None
+    if world == 1 and not args.no_cfg5:
+        cfg5 = cfg5_leg(args, cfg, B, dev, args.steps)
     if rank == 0:
         for tid in os.listdir("/proc/self/task"):          # the CPU legs use every core the box gives us: every thread
             try:                                           # (pool threads created while bound inherited the mask)
@@ -1015,6 +1179,7 @@ def run_ours(args, cfg, B):
                                   "frac": eval_alg / (eval_ms * 1e-3) / 1e9 / peak}},
             "pointwise": pw, "host_numa": numa,
             "uniq_users_per_step": uniq_users, "uniq_items_per_step": uniq_items,
+            "cfg5": cfg5,
         }
         if catalog:
             if world == 1 and not args.no_cpu:
@@ -1048,6 +1213,7 @@ def main():
                     "instead of a cfg2-sized shard per GPU (constant per-GPU work)")
     ap.add_argument("--no-cfg3", action="store_true", help="N=8: skip the cfg3 leg (100M users / 10M recipes)")
     ap.add_argument("--no-plan-ahead", action="store_true", help="N>1: plan every step in sequence instead of one step ahead on a side stream")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg5 leg (1:8 sampled negatives, Adagrad, bf16 tables)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-catalog", action="store_true", help="skip the full-catalog top-K legs")
     ap.add_argument("--learner", default="adam", help="adam (reference default) | adagrad | rmsprop | sgd")

@@ -156,8 +156,20 @@ extern "C" int fr_set_tables(fr_handle h, const fr_tables* t) {
   return FR_OK;
 }
 
+extern "C" int fr_set_table_format(fr_handle h, int32_t format) {
+  if (!h) return FR_ERR_ARG;
+  if (format != FR_TABLE_F32 && format != FR_TABLE_BF16) return fail(h, FR_ERR_ARG, "unknown table format %d", format);
+  if (h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_table_format must precede fr_set_tables");
+  if (format == FR_TABLE_BF16 && h->cfg.learner == FR_ADAM)
+    return fail(h, FR_ERR_UNSUPPORTED, "bf16 tables are offered for SGD / Adagrad / RMSProp: TF-1.x Adam moves every row every "
+                "step, which re-rounds all of Personal_Memory to bf16 each time (see include/foodrec_b200.h)");
+  h->table_bf16 = format == FR_TABLE_BF16;
+  return FR_OK;
+}
+
 extern "C" int fr_set_shadow(fr_handle h, float* P_alt, float* s1_alt, float* s2_alt) {
   if (!h || !h->has_tables) return fail(h, FR_ERR_STATE, "fr_set_tables first");
+  if (h->table_bf16 && (P_alt || s1_alt || s2_alt)) return fail(h, FR_ERR_UNSUPPORTED, "the single-pass step is not available with bf16 tables");
   if (!P_alt && !s1_alt && !s2_alt) {             // switch the single-pass step off again
     int rc = shadow_sync(h, 0); if (rc) return rc;
     FR_CUDA(h, cudaDeviceSynchronize());
@@ -264,7 +276,7 @@ extern "C" int fr_fwd_score(fr_handle h, const int32_t* users, const int32_t* it
   Launch l{h->sm_count, (cudaStream_t)s};
   launch_fwd_score(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, items,
                    (const float4*)(cats ? cats : h->tab.item_cats), cats ? 0 : 1, n, scores, health_of(h), l,
-                   h->cfg.num_users, h->cfg.num_items);
+                   h->cfg.num_users, h->cfg.num_items, h->table_bf16 ? 1 : 0);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -282,7 +294,7 @@ extern "C" int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int
   if (l2_window(h, h->tab.R, (size_t)h->cfg.num_items * h->mc.D * sizeof(float), &win)) { l.win = &win; h->l2_lines_pinned = true; }
   launch_eval_sampled(h->mc, (const float4*)h->tab.P, (const float4*)h->tab.R, (const float4*)h->tab.Cat, users, cand,
                       n_cand, n_users, cand_stride, (const float4*)cand_cats, (const float4*)h->tab.item_cats, K,
-                      topk_ids, gt_rank, scores, health_of(h), l, h->cfg.num_users, h->cfg.num_items);
+                      topk_ids, gt_rank, scores, health_of(h), l, h->cfg.num_users, h->cfg.num_items, h->table_bf16 ? 1 : 0);
   // (lines the window marked persisting are demoted by cudaCtxResetPersistingL2Cache at the next fr_train_step)
   FR_CHECK_LAUNCH(h);
   return FR_OK;
@@ -332,6 +344,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   if (!b->cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cats is NULL and no item_cats table");
   if (!b->user_labels && !(h->tab.user_label_off && h->tab.user_label_idx))
     return fail(h, FR_ERR_ARG, "user_labels is NULL and no user-label CSR table");
+  if (h->table_bf16 && write_personal) return fail(h, FR_ERR_UNSUPPORTED, "personal-write steps are not available with bf16 tables");
   cudaStream_t st = (cudaStream_t)s;
   if (h->l2_lines_pinned) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); h->l2_lines_pinned = false; }
   Launch l{h->sm_count, st, nullptr};
@@ -435,6 +448,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   fp.g = h->g; fp.z = h->z; fp.scores = out_scores ? out_scores : h->scores;
   fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
   fp.lazy = lazy ? 1 : 0; fp.mP = (const float4*)T.s1_P; fp.vP = (const float4*)T.s2_P; fp.lastP = T.last_P; fp.oc = oc;
+  fp.tab = h->table_bf16 ? 1 : 0;
   fgrid = fwd_train_grid(B, h->sm_count);
   launch_fwd_train(NV, group, fp, fgrid, l);
   FR_CHECK_LAUNCH(h);
@@ -461,6 +475,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     up.items = items; up.g = h->g; up.cats = cats; up.cats_by_item = cats_by_item;
     up.ws_row = h->ws_row; up.out = out; up.group = group; up.mc = h->mc; up.oc = oc;
     up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = users;
+    up.tab = h->table_bf16 ? 1 : 0;
     if (fused) {
       // 4'. the norm is known.  scale == 1 exactly: the speculative rows become current (stamp bits flipped).  Otherwise
       //     nothing was committed: every row goes back to the caller's tables and the ordinary update pass runs with
@@ -502,7 +517,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     LabelPolParams lp{};
     lp.G = (float4*)T.G; lp.R = (const float4*)T.R; lp.cat = h->cat_pre;
     lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = items; lp.cats = cats;
-    lp.cats_by_item = cats_by_item; lp.mc = h->mc;
+    lp.cats_by_item = cats_by_item; lp.mc = h->mc; lp.tab = h->table_bf16 ? 1 : 0;
     launch_label_pass(NV, c, lp, l);
     FR_CHECK_LAUNCH(h);
   }
@@ -517,7 +532,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     c.long_list = h->long_list; c.long_count = h->counters + 3; c.long_cap = h->long_cap;
     ItemPolParams ip{};
     ip.R = (float4*)T.R; ip.s1 = (float4*)T.s1_R; ip.s2 = (float4*)T.s2_R; ip.last = T.last_R;
-    ip.z = h->z; ip.g = h->g; ip.out = out; ip.mc = h->mc; ip.oc = oc;
+    ip.z = h->z; ip.g = h->g; ip.out = out; ip.mc = h->mc; ip.oc = oc; ip.tab = h->table_bf16 ? 1 : 0;
     launch_item_pass(NV, c, ip, l);
     FR_CHECK_LAUNCH(h);
   }

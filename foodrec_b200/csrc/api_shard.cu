@@ -192,7 +192,8 @@ extern "C" int fr_gather_user_rows(fr_handle h, const int32_t* users, int32_t n,
   int rc = shadow_sync(h, st); if (rc) return rc;
   Launch l{h->sm_count, st, nullptr};
   PeerPtrs none{}; none.world = 0;
-  launch_gather_rows((const float4*)h->tab.P, users, (uint32_t)n, 5 * h->mc.DV, (float4*)out, none, l, (uint32_t)h->cfg.num_users);
+  launch_gather_rows((const float4*)h->tab.P, users, (uint32_t)n, 5 * h->mc.DV, (float4*)out, none, l, (uint32_t)h->cfg.num_users,
+                     h->table_bf16 ? 1 : 0);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -234,7 +235,7 @@ extern "C" int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rr
                         h->mc.DV, oc, l, w.n_valid);
   PeerPtrs none{}; none.world = 0;
   launch_gather_rows((const float4*)T.R, rreq, (uint32_t)n, h->mc.DV, (float4*)rows, rows ? none : w.peer_rbuf, l,
-                     (uint32_t)h->cfg.num_items);
+                     (uint32_t)h->cfg.num_items, h->table_bf16 ? 1 : 0);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }
@@ -291,6 +292,7 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   fp.g = h->g; fp.z = h->z; fp.scores = h->scores;
   fp.part_loss = h->part_loss; fp.part_nrm = h->part_nrm; fp.part_gcat = h->part_gcat;
   fp.lazy = lazy ? 1 : 0; fp.mP = (const float4*)T.s1_P; fp.vP = (const float4*)T.s2_P; fp.lastP = T.last_P; fp.oc = oc;
+  fp.tab = h->table_bf16 ? 2 : 0;        // bf16 Personal_Memory, fp32 received recipe rows
   fgrid = fwd_train_grid(B, h->sm_count);
   launch_fwd_train(NV, ps.group, fp, fgrid, l);
   }
@@ -322,7 +324,7 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   LabelPolParams lp{};
   lp.G = (float4*)dG; lp.R = (const float4*)rbuf; lp.cat = h->cat_pre;
   lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = ps.slot_of_row; lp.cats = ps.cats_row;
-  lp.cats_by_item = 0; lp.mc = h->mc;
+  lp.cats_by_item = 0; lp.mc = h->mc; lp.tab = 0;
   launch_label_pass(NV, c, lp, l);
   FR_CHECK_LAUNCH(h);
   return FR_OK;
@@ -337,6 +339,7 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   auto& w = h->sh;
   auto& ps = w.ps[w.n_apply & 1];
   if (!grows && w.peer_rgrows.world != sh->world) return fail(h, FR_ERR_ARG, "grows is NULL but fr_shard_set_peers has not been called for this world");
+  if (h->table_bf16 && write_personal) return fail(h, FR_ERR_UNSUPPORTED, "personal-write steps are not available with bf16 tables");
   if (!ps.planned || b->n_groups != ps.B) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_update");
   cudaStream_t st = (cudaStream_t)s;
   Launch l{h->sm_count, st, nullptr};
@@ -374,6 +377,7 @@ extern "C" int fr_shard_update(fr_handle h, const fr_batch* b, const fr_shard* s
   up.items = ps.slot_of_row; up.g = h->g; up.cats = ps.cats_row; up.cats_by_item = 0;
   up.ws_row = ps.ws_row; up.out = out; up.group = ps.group; up.mc = h->mc; up.oc = oc;
   up.user_labels = b->user_labels; up.lab_off = T.user_label_off; up.lab_idx = T.user_label_idx; up.users = ps.users_s;
+  up.tab = h->table_bf16 ? 2 : 0;
   FR_MARK(FR_T_USER_CHUNK);
   l.mid = ts ? ts->ev[FR_T_USER_COMBINE] : nullptr;
   if (S > 0 && ps.fused) {
@@ -446,7 +450,7 @@ extern "C" int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rr
   c.pieces = w.pieces_s; c.uniq_counter = nullptr;
   ItemPolParams ip{};
   ip.R = (float4*)T.R; ip.s1 = (float4*)T.s1_R; ip.s2 = (float4*)T.s2_R; ip.last = T.last_R;
-  ip.z = (const float4*)rgrows; ip.g = nullptr; ip.out = out; ip.mc = h->mc; ip.oc = oc;
+  ip.z = (const float4*)rgrows; ip.g = nullptr; ip.out = out; ip.mc = h->mc; ip.oc = oc; ip.tab = h->table_bf16 ? 1 : 0;
   launch_item_pass(NV, c, ip, l);
 
   if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode == FR_ADAM_LAZY_SERIES)

@@ -835,6 +835,7 @@ extern "C" int fr_catalog_topk(fr_handle h, const int32_t* users, const float* P
   if (K <= 0 || K > CAT_MAXK) return fail(h, FR_ERR_UNSUPPORTED, "K must be in [1,%d], got %d", CAT_MAXK, K);
   if (n_users == 0) return FR_OK;
   if (P_rows && h->health_blend) return fail(h, FR_ERR_ARG, "the health term needs user ids (labels): pass users, not dense P_rows");
+  if (h->table_bf16) return fail(h, FR_ERR_UNSUPPORTED, "fr_catalog_* reads fp32 tables (exact fp64 re-rank): not available with bf16 tables");
   if (!P_rows) { const int rcs = shadow_sync(h, static_cast<cudaStream_t>(s)); if (rcs) return rcs; }
   if (!P_rows && !users && n_users > h->cfg.num_users)
     return fail(h, FR_ERR_ARG, "n_users=%d exceeds the %d rows of Personal_Memory", n_users, h->cfg.num_users);

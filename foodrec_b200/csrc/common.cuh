@@ -1,5 +1,6 @@
 // Shared device helpers for the foodrec_b200 kernels (sm_100a).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -108,6 +109,64 @@ __device__ __forceinline__ void store_row(float4* row, const float4 (&src)[NV], 
   for (int k = 0; k < NV; ++k) {
     const int i = lane + 32 * k;
     if (i < DV) st_stream(row + i, src[k]);
+  }
+}
+
+// ---- table storage formats (fr_set_table_format).  A Personal_Memory / Recipe_Embedding row is either fp32 (one float4
+// per 4 elements) or bf16 (one uint2 per 4 elements: BASELINE configs[4]).  All arithmetic is fp32; a bf16 table is
+// converted on load and rounded to nearest-even on store.  Index arithmetic is in 4-element units either way: kernels keep
+// their `float4*` table pointers and go through tab_at<BF>() for the address.
+template <bool BF> struct TabVec { using type = float4; };
+template <> struct TabVec<true> { using type = uint2; };
+template <bool BF>
+__device__ __forceinline__ const typename TabVec<BF>::type* tab_at(const float4* base, size_t idx4) {
+  return reinterpret_cast<const typename TabVec<BF>::type*>(base) + idx4;
+}
+template <bool BF>
+__device__ __forceinline__ typename TabVec<BF>::type* tab_at(float4* base, size_t idx4) {
+  return reinterpret_cast<typename TabVec<BF>::type*>(base) + idx4;
+}
+__device__ __forceinline__ float4 bf4_to_f4(const uint2 v) {
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
+                     __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
+__device__ __forceinline__ uint2 f4_to_bf4(const float4 v) {           // round to nearest even
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<const uint32_t*>(&a); r.y = *reinterpret_cast<const uint32_t*>(&b);
+  return r;
+}
+__device__ __forceinline__ float4 tab_ld_ro(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float4 tab_ld_ro(const uint2* p) { return bf4_to_f4(__ldg(p)); }
+__device__ __forceinline__ float4 tab_ld_cs(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 tab_ld_cs(const uint2* p) { return bf4_to_f4(__ldcs(p)); }
+__device__ __forceinline__ float4 tab_ld_stream(const float4* p) { return ld_stream(p); }
+__device__ __forceinline__ float4 tab_ld_stream(const uint2* p) { return bf4_to_f4(__ldcs(p)); }
+__device__ __forceinline__ void tab_st_cs(float4* p, const float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void tab_st_cs(uint2* p, const float4 v) { __stcs(p, f4_to_bf4(v)); }
+// 16-byte-vector rows of either format: lane l owns 4-element group l, l+32, ...
+template <int NV, class V>
+__device__ __forceinline__ void load_row_t(float4 (&dst)[NV], const V* row, int DV, int lane) {       // read once
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    dst[k] = (i < DV) ? tab_ld_stream(row + i) : f4zero();
+  }
+}
+template <int NV, class V>
+__device__ __forceinline__ void load_row_cs_t(float4 (&dst)[NV], const V* row, int DV, int lane) {     // evict-first
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    dst[k] = (i < DV) ? tab_ld_cs(row + i) : f4zero();
+  }
+}
+template <int NV, class V>
+__device__ __forceinline__ void load_row_ro_t(float4 (&dst)[NV], const V* __restrict__ row, int DV, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    dst[k] = (i < DV) ? tab_ld_ro(row + i) : f4zero();
   }
 }
 

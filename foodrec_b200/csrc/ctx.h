@@ -74,6 +74,7 @@ struct fr_ctx {
   // single-pass training (fr_set_shadow): second copy of Personal_Memory + Adam slots; shadow_dirty = some row's current
   // copy may be the shadow (cleared by shadow_sync, which every reader of the caller's tables runs first)
   float *shP = nullptr, *shM = nullptr, *shV = nullptr; bool shadow_dirty = false;
+  bool table_bf16 = false;          // fr_set_table_format: Personal_Memory and Recipe_Embedding are stored in bf16
   bool health_blend = false;        // fr_set_health_blend: inference scores P[u] + alpha * mean G[labels(u)]
   fr::CatalogWs* cat = nullptr;     // full-catalog top-K (catalog.cu): index + pass workspace
   // staging for fr_train_step_host

@@ -7,12 +7,12 @@
 namespace fr {
 
 // score of one (user row in registers, item) pair; all lanes return the same value.
-template <int NV>
-__device__ __forceinline__ float score_pair(const float4 (&pr)[5][NV], const float4* __restrict__ Rrow,
+template <int NV, class V>
+__device__ __forceinline__ float score_pair(const float4 (&pr)[5][NV], const V* __restrict__ Rrow,
                                             const float4 m, const float4* sCat, int DV, int lane,
                                             float a, float oma) {
   float4 rr[NV], pcs[NV];
-  load_row_ro<NV>(rr, Rrow, DV, lane);
+  load_row_ro_t<NV>(rr, Rrow, DV, lane);
   pooled_cat<NV>(pcs, sCat, m, DV, lane);
   float hs = 0.f, ls = 0.f;
 #pragma unroll
@@ -30,7 +30,7 @@ __device__ __forceinline__ float score_pair(const float4 (&pr)[5][NV], const flo
   return a * (hs / n) + oma * (ls / n);
 }
 
-template <int NV>
+template <int NV, bool BF>         // BF: Personal_Memory and Recipe_Embedding are stored in bf16 (fr_set_table_format)
 __global__ void __launch_bounds__(FR_THREADS)
 fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, const float4* __restrict__ Cat,
                  int DV, const int32_t* __restrict__ users, const int32_t* __restrict__ items,
@@ -59,12 +59,12 @@ fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, con
       }
       if (u != cur_u) {
 #pragma unroll
-        for (int s = 0; s < 5; ++s) load_row_ro<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
+        for (int s = 0; s < 5; ++s) load_row_ro_t<NV>(pr[s], tab_at<BF>(P, ((size_t)u * 5 + s) * DV), DV, lane);
         health_blend_rows<NV>(pr, hb, u, DV, lane);
         cur_u = u;
       }
       const float4 m = __ldg(cats + (cats_by_item ? it : r));
-      const float s = score_pair<NV>(pr, R + (size_t)it * DV, m, sCat, DV, lane, a, oma);
+      const float s = score_pair<NV>(pr, tab_at<BF>(R, (size_t)it * DV), m, sCat, DV, lane, a, oma);
       if (lane == 0) scores[r] = s;
     }
   }
@@ -73,16 +73,17 @@ fwd_score_kernel(const float4* __restrict__ P, const float4* __restrict__ R, con
 void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                       const int32_t* users, const int32_t* items, const float4* cats,
                       int cats_by_item, int n, float* scores, const HealthBlend& hb, const Launch& l,
-                      int64_t n_users, int64_t n_items) {
+                      int64_t n_users, int64_t n_items, int bf16) {
   if (n <= 0) return;
   int grid = (n + 8 * FR_WARPS_PER_BLOCK - 1) / (8 * FR_WARPS_PER_BLOCK);
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   const size_t smem = (size_t)4 * mc.DV * sizeof(float4);
   ++g_launches;
-  if (mc.DV <= 32)
-    fwd_score_kernel<1><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb, (uint32_t)n_users, (uint32_t)n_items);
-  else
-    fwd_score_kernel<2><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, n, mc.a, mc.oma, scores, hb, (uint32_t)n_users, (uint32_t)n_items);
+#define FR_SCORE(NVV, BFF) fwd_score_kernel<NVV, BFF><<<grid, FR_THREADS, smem, l.st>>>(P, R, Cat, mc.DV, users, items, cats, cats_by_item, \
+    n, mc.a, mc.oma, scores, hb, (uint32_t)n_users, (uint32_t)n_items)
+  if (mc.DV <= 32) { if (bf16) FR_SCORE(1, true); else FR_SCORE(1, false); }
+  else             { if (bf16) FR_SCORE(2, true); else FR_SCORE(2, false); }
+#undef FR_SCORE
 }
 
 // One warp per test user.  Candidate j lives in lane j&31, slot j>>5 (<= 128 candidates; SLOTS = 2 covers the
@@ -91,7 +92,7 @@ void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, c
 // 5-step shuffle reductions and two IEEE divisions on every candidate: ~110 warp instructions each, 22 ms per 1M
 // users while the recipe table sits in L2).  The category term a/n * sum_c m_c <P[u,0], Cat[c]> needs the four dot
 // products <P[u,0], Cat[c]> once per user; the recipe term is sum_d (sum_c m_c P[u,1+c]_d) R[i]_d accumulated by the lane.
-template <int NV, int SLOTS>
+template <int NV, int SLOTS, bool BF>
 __global__ void __launch_bounds__(FR_THREADS)
 eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, const float4* __restrict__ Cat,
                     int DV, float a, float oma, const int32_t* __restrict__ users,
@@ -135,7 +136,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       float4 pr[5][NV];
 #pragma unroll
       // read-once rows: streamed (evict-first) so that the recipe table, which every user re-reads, stays in L2
-      for (int s = 0; s < 5; ++s) load_row_cs<NV>(pr[s], P + ((size_t)u * 5 + s) * DV, DV, lane);
+      for (int s = 0; s < 5; ++s) load_row_cs_t<NV>(pr[s], tab_at<BF>(P, ((size_t)u * 5 + s) * DV), DV, lane);
       health_blend_rows<NV>(pr, hb, u, DV, lane);
       float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
       __syncwarp();                                                  // the previous user's rows are no longer read
@@ -162,13 +163,13 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       if (q * 32 >= nc) break;
       const bool vA = id[q] >= 0, vB = id[q + 1] >= 0;
       const float4 mA = mq[q], mB = mq[q + 1];
-      const float4* rpA = R + (size_t)(vA ? id[q] : 0) * DV;
-      const float4* rpB = R + (size_t)(vB ? id[q + 1] : 0) * DV;
+      const typename TabVec<BF>::type* rpA = tab_at<BF>(R, (size_t)(vA ? id[q] : 0) * DV);
+      const typename TabVec<BF>::type* rpB = tab_at<BF>(R, (size_t)(vB ? id[q + 1] : 0) * DV);
       float accA = 0.f, accB = 0.f;
       if ((q + 1) * 32 < nc) {
 #pragma unroll 4
         for (int i = 0; i < DV; ++i) {
-          const float4 ra = __ldg(rpA + i), rb = __ldg(rpB + i);
+          const float4 ra = tab_ld_ro(rpA + i), rb = tab_ld_ro(rpB + i);
           const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
           float4 za, zb;
           za.x = mA.x * p1.x + mA.y * p2.x + mA.z * p3.x + mA.w * p4.x;
@@ -184,7 +185,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       } else {
         float acc1 = 0.f;
         auto step = [&](int i, float& acc) {
-          const float4 r = __ldg(rpA + i);
+          const float4 r = tab_ld_ro(rpA + i);
           const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
           float4 z;
           z.x = mA.x * p1.x + mA.y * p2.x + mA.z * p3.x + mA.w * p4.x;
@@ -282,7 +283,7 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
                          const int32_t* users, const int32_t* cand, const int32_t* n_cand, int n_users,
                          int stride, const float4* cand_cats, const float4* item_cats, int K,
                          int32_t* topk_ids, int32_t* gt_rank, float* scores, const HealthBlend& hb, const Launch& l,
-                         int64_t n_table_users, int64_t n_items) {
+                         int64_t n_table_users, int64_t n_items, int bf16) {
   if (n_users <= 0) return;
   int grid = (n_users + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
@@ -301,11 +302,13 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   }
   const int DVv = mc.DV; const float av = mc.a, omav = mc.oma;
   const uint32_t ntu = (uint32_t)n_table_users, nit = (uint32_t)n_items;
-#define FR_EVAL(NVV, SL) cudaLaunchKernelEx(&cfg, eval_sampled_kernel<NVV, SL>, P, R, Cat, DVv, av, omav, users, cand, \
+#define FR_EVAL_(NVV, SL, BFF) cudaLaunchKernelEx(&cfg, eval_sampled_kernel<NVV, SL, BFF>, P, R, Cat, DVv, av, omav, users, cand, \
     n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb, ntu, nit)
+#define FR_EVAL(NVV, SL) do { if (bf16) FR_EVAL_(NVV, SL, true); else FR_EVAL_(NVV, SL, false); } while (0)
   const bool two = stride <= 64;
   if (mc.DV <= 32) { if (two) FR_EVAL(1, 2); else FR_EVAL(1, 4); }
   else             { if (two) FR_EVAL(2, 2); else FR_EVAL(2, 4); }
+#undef FR_EVAL_
 #undef FR_EVAL
 }
 

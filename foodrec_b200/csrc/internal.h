@@ -98,12 +98,12 @@ struct HealthBlend { const float4* G; const int32_t* lab_off; const int32_t* lab
 void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                       const int32_t* users, const int32_t* items, const float4* cats,
                       int cats_by_item, int n, float* scores, const HealthBlend& hb, const Launch& l,
-                      int64_t n_users, int64_t n_items);
+                      int64_t n_users, int64_t n_items, int bf16);
 
 void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R, const float4* Cat,
                          const int32_t* users, const int32_t* cand, const int32_t* n_cand, int n_users,
                          int stride, const float4* cand_cats, const float4* item_cats, int K,
                          int32_t* topk_ids, int32_t* gt_rank, float* scores, const HealthBlend& hb, const Launch& l,
-                         int64_t n_table_users, int64_t n_items);
+                         int64_t n_table_users, int64_t n_items, int bf16);
 
 }  // namespace fr

@@ -153,7 +153,8 @@ struct RowState {
   int last;
 };
 
-template <int OPT, int NR, int NV>
+// BF: the variable table is stored in bf16 (fr_set_table_format); the optimizer slots are always fp32.
+template <int OPT, int NR, int NV, bool BF = false>
 __device__ __forceinline__ void load_state(RowState<NR, NV>& st, const float4* var_t, const float4* s1_t,
                                            const float4* s2_t, const int32_t* last_t, uint32_t rowid,
                                            const OptConsts& oc, int DV, int lane) {
@@ -167,14 +168,14 @@ __device__ __forceinline__ void load_state(RowState<NR, NV>& st, const float4* v
       const int i = lane + 32 * k;
       const bool ok = i < DV;
       const size_t off = base + (size_t)s * DV + i;
-      st.var[s][k] = ok ? __ldcs(var_t + off) : f4zero();
+      st.var[s][k] = ok ? tab_ld_cs(tab_at<BF>(var_t, off)) : f4zero();
       st.s1[s][k] = (ok && has1) ? __ldcs(s1_t + off) : f4zero();
       st.s2[s][k] = (ok && has2) ? __ldcs(s2_t + off) : f4zero();
     }
   st.last = (OPT == OPT_ADAM_EXACT || OPT == OPT_ADAM_SERIES) ? last_t[rowid] : 0;
 }
 
-template <int OPT, int NR, int NV>
+template <int OPT, int NR, int NV, bool BF = false>
 __device__ __forceinline__ void apply_and_store(RowState<NR, NV>& st, float4* var_t, float4* s1_t, float4* s2_t,
                                                 int32_t* last_t, uint32_t rowid, const float4 (&grad)[NR][NV],
                                                 const OptConsts& oc, int DV, int lane) {
@@ -204,7 +205,7 @@ __device__ __forceinline__ void apply_and_store(RowState<NR, NV>& st, float4* va
         sgd_touch(var.x, g.x, oc); sgd_touch(var.y, g.y, oc); sgd_touch(var.z, g.z, oc); sgd_touch(var.w, g.w, oc);
       }
       const size_t off = base + (size_t)s * DV + i;
-      __stcs(var_t + off, var);
+      tab_st_cs(tab_at<BF>(var_t, off), var);         // (bf16 table: round to nearest even on store)
       if (has1) __stcs(s1_t + off, a);
       if (has2) __stcs(s2_t + off, b);
     }

@@ -17,6 +17,7 @@ struct FwdParams {
   // lazy-exact Adam: P[u] in memory may be stale; the forward replays the skipped decay
   // steps last+1..step-1 in registers from (m, v) so that it scores the row TF would see
   int lazy; const float4 *mP, *vP; const int32_t* lastP; OptConsts oc;
+  int tab;                          // table storage: 0 fp32 P and R, 1 bf16 P and R, 2 bf16 P + fp32 R (fr_set_table_format)
 };
 
 struct FinalizeParams {
@@ -51,6 +52,7 @@ struct UserPolParams {
   const float* ws_row; const float* out;    // out[FR_OUT_SCALE]
   int group; ModelConsts mc; OptConsts oc;
   const float* user_labels; const int32_t *lab_off, *lab_idx; const int32_t* users;
+  int tab;                                  // as FwdParams::tab
 };
 // single-pass step (user_fused_kernel, train_seg.cu): forward + segment reduce + Adam in one walk over the user-sorted rows
 struct FusedParams {
@@ -74,12 +76,14 @@ struct ItemPolParams {
   float4 *R, *s1, *s2; int32_t* last;
   const float4* z; const float* g; const float* out;
   ModelConsts mc; OptConsts oc;
+  int tab;                                  // != 0: Recipe_Embedding is stored in bf16
 };
 struct LabelPolParams {
   float4* G; const float4 *R, *cat;
   const uint32_t* ent_row; const float* ent_coef;
   const int32_t* items; const float4* cats; int cats_by_item;
   ModelConsts mc;
+  int tab;                                  // 1: the recipe rows read here are bf16
 };
 
 struct LabelEmitParams {
@@ -140,7 +144,7 @@ void launch_shard_fill(const ShardPlanParams& p, const Launch& l);
 void launch_serve_keys(const int32_t* rreq, uint32_t n, uint32_t items_per_rank, uint32_t* keys, uint32_t* n_valid,
                        const Launch& l);
 void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const PeerPtrs& peers, const Launch& l,
-                        uint32_t n_table);
+                        uint32_t n_table, int bf16);
 void launch_add_inplace(float4* dst, const float4* src, int64_t n4, const Launch& l);
 void launch_route_keys(const int32_t* users, int B, int W, uint32_t* keys, uint32_t* owner_counts, const Launch& l);
 void launch_route_fill(const int32_t* users, const int32_t* items, const float* labels, int B, int W, int group, int rcap,

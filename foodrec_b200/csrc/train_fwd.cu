@@ -60,9 +60,13 @@ void launch_prep_rows(int mode, int B, const int32_t* users, const int32_t* item
 // LAZY = 0 (rows in memory are current) | OPT_ADAM_EXACT | OPT_ADAM_SERIES: P[u] in memory may
 // be stale and is brought to step-1 in registers from (m, v) before it is scored.
 // (__launch_bounds__(FR_THREADS, 3) -> 80 registers, 24 warps/SM: measured SLOWER, 0.78 vs 0.65 ms, spills)
-template <int NV, int GROUP, int LAZY>
+// TAB = storage format of the tables (fr_set_table_format): 0 fp32 P and R; 1 bf16 P and R; 2 bf16 P, fp32 R (the
+// row-sharded step: R = the receive buffer, filled in fp32 by the owners' gather).  bf16 only without lazy Adam.
+template <int NV, int GROUP, int LAZY, int TAB>
 __global__ void __launch_bounds__(FR_THREADS)
 fwd_train_kernel(const FwdParams p) {
+  constexpr bool BFP = TAB != 0, BFR = TAB == 1;
+  static_assert(TAB == 0 || LAZY == 0, "bf16 tables: no lazy Adam");
   extern __shared__ float4 smem[];
   const int DV = p.DV;
   float4* sCat = smem;                 // [4*DV]
@@ -117,21 +121,21 @@ fwd_train_kernel(const FwdParams p) {
 #pragma unroll
       for (int j = 0; j < GROUP; ++j) mc1[j] = __ldg(p.cats + (p.cats_by_item ? it1[j] : gn * GROUP + j));
 #ifndef FR_NO_FWD_PREFETCH
-      const uint32_t ub = 5u * (uint32_t)DV * 16u, rb = (uint32_t)DV * 16u;
+      const uint32_t ub = 5u * (uint32_t)DV * (BFP ? 8u : 16u), rb = (uint32_t)DV * (BFR ? 8u : 16u);
       const size_t uo = (size_t)u1 * 5 * DV;
-      prefetch_l2_warp(p.P + uo, ub, lane);
+      prefetch_l2_warp(tab_at<BFP>(p.P, uo), ub, lane);
       if (LAZY != 0) { prefetch_l2_warp(p.mP + uo, ub, (lane + 31) & 31); prefetch_l2_warp(p.vP + uo, ub, (lane + 30) & 31); }
 #pragma unroll
       for (int j = 0; j < GROUP; ++j)
-        prefetch_l2_warp(p.R + (size_t)it1[j] * DV, rb, (lane + 29 - j) & 31);
+        prefetch_l2_warp(tab_at<BFR>(p.R, (size_t)it1[j] * DV), rb, (lane + 29 - j) & 31);
 #endif
     }
     float4 pr[5][NV];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) load_row<NV>(pr[s], p.P + ((size_t)u * 5 + s) * DV, DV, lane);
+    for (int s = 0; s < 5; ++s) load_row_t<NV>(pr[s], tab_at<BFP>(p.P, ((size_t)u * 5 + s) * DV), DV, lane);
     float4 rr[GROUP][NV], pcn[GROUP][NV];   // R rows, pooledCat (normalised)
 #pragma unroll
-    for (int j = 0; j < GROUP; ++j) load_row_ro<NV>(rr[j], p.R + (size_t)it[j] * DV, DV, lane);
+    for (int j = 0; j < GROUP; ++j) load_row_ro_t<NV>(rr[j], tab_at<BFR>(p.R, (size_t)it[j] * DV), DV, lane);
     if constexpr (LAZY != 0) {
       const int to = p.oc.step - 1;
       if (lastu < to) {
@@ -278,9 +282,10 @@ int fwd_train_grid(int B, int sm_count) {
 void launch_fwd_train(int NV, int group, const FwdParams& p, int grid, const Launch& l) {
   const size_t smem = (size_t)(4 * p.DV) * sizeof(float4) * (1 + FR_WARPS_PER_BLOCK);
   const int lz = !p.lazy ? 0 : (p.oc.adam_mode == FR_ADAM_LAZY_SERIES ? OPT_ADAM_SERIES : OPT_ADAM_EXACT);
-#define FR_FWD(NVV, GG, LZ) fwd_train_kernel<NVV, GG, LZ><<<grid, FR_THREADS, smem, l.st>>>(p)
-#define FR_FWD_L(NVV, GG) do { if (lz == 0) FR_FWD(NVV, GG, 0); else if (lz == OPT_ADAM_EXACT) FR_FWD(NVV, GG, OPT_ADAM_EXACT); \
-                               else FR_FWD(NVV, GG, OPT_ADAM_SERIES); } while (0)
+#define FR_FWD(NVV, GG, LZ, TB) fwd_train_kernel<NVV, GG, LZ, TB><<<grid, FR_THREADS, smem, l.st>>>(p)
+#define FR_FWD_L(NVV, GG) do { if (p.tab == 1) FR_FWD(NVV, GG, 0, 1); else if (p.tab == 2) FR_FWD(NVV, GG, 0, 2);             \
+                               else if (lz == 0) FR_FWD(NVV, GG, 0, 0); else if (lz == OPT_ADAM_EXACT) FR_FWD(NVV, GG, OPT_ADAM_EXACT, 0); \
+                               else FR_FWD(NVV, GG, OPT_ADAM_SERIES, 0); } while (0)
   if (NV == 1) { if (group == 1) FR_FWD_L(1, 1); else FR_FWD_L(1, 2); }
   else         { if (group == 1) FR_FWD_L(2, 1); else FR_FWD_L(2, 2); }
 #undef FR_FWD_L

@@ -195,10 +195,12 @@ __device__ __forceinline__ RowTerms<NV> row_terms(const float4 m, const float4* 
 
 // ---- policy: Personal_Memory rows.  grad slice of item row r (App. A.3):
 //   dP[u,0]   += g*a*pooledCat_r ;  dP[u,1+c] += g*(1-a)*w_rc*R[i_r]
-template <int NVV, int OPT>
+// TAB: table storage (FwdParams::tab): 0 fp32, 1 bf16 P and R, 2 bf16 P + fp32 R (row-sharded step)
+template <int NVV, int OPT, int TAB = 0>
 struct UserPol {
   static constexpr int NV = NVV;
   static constexpr int NR = 5;
+  static constexpr bool BFP = TAB != 0, BFR = TAB == 1;
   UserPolParams p;
   struct Entry { int item; float g; float4 m; };
   using State = RowState<5, NVV>;
@@ -220,8 +222,8 @@ struct UserPol {
     for (int j0 = e0; j0 < e1; j0 += 2) {
       const int jn = (j0 + 1 < e1) ? j0 + 1 : j0;
       float4 rr2[2][NV];
-      load_row_ro<NV>(rr2[0], p.R + (size_t)__shfl_sync(FR_FULL, e.item, j0) * DVv, DVv, lane);
-      load_row_ro<NV>(rr2[1], p.R + (size_t)__shfl_sync(FR_FULL, e.item, jn) * DVv, DVv, lane);
+      load_row_ro_t<NV>(rr2[0], tab_at<BFR>(p.R, (size_t)__shfl_sync(FR_FULL, e.item, j0) * DVv), DVv, lane);
+      load_row_ro_t<NV>(rr2[1], tab_at<BFR>(p.R, (size_t)__shfl_sync(FR_FULL, e.item, jn) * DVv), DVv, lane);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int j = j0 + u;
@@ -240,9 +242,9 @@ struct UserPol {
     }
   }
   __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
-    fr::load_state<OPT, 5, NV>(st, p.P, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
+    fr::load_state<OPT, 5, NV, BFP>(st, p.P, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
   }
-  __device__ __forceinline__ void prefetch_state(uint32_t key, int lane) const {
+  __device__ __forceinline__ void prefetch_state(uint32_t key, int lane) const {      // (FR_PREFETCH_SEG builds: fp32 tables)
     const uint32_t bytes = 5u * (uint32_t)p.mc.DV * 16u;      // a user's 5 slots are contiguous
     const size_t off = (size_t)key * 5 * p.mc.DV;
     prefetch_l2_warp(p.P + off, bytes, lane);
@@ -250,7 +252,7 @@ struct UserPol {
     if (OPT != OPT_GENERIC || p.oc.learner == FR_RMSPROP) prefetch_l2_warp(p.s2 + off, bytes, (lane + 30) & 31);
   }
   __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[5][NV], int lane) const {
-    apply_and_store<OPT, 5, NV>(st, p.P, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
+    apply_and_store<OPT, 5, NV, BFP>(st, p.P, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
   }
 };
 
@@ -363,7 +365,7 @@ struct PersonalPol {
 };
 
 // ---- policy: Recipe_Embedding rows.  dR[i] += g * z_r  (z stashed by the forward pass)
-template <int NVV, int OPT>
+template <int NVV, int OPT, bool BFR = false>       // BFR: Recipe_Embedding stored in bf16
 struct ItemPol {
   static constexpr int NV = NVV;
   static constexpr int NR = 1;
@@ -403,7 +405,7 @@ struct ItemPol {
     }
   }
   __device__ __forceinline__ void load_state(State& st, uint32_t key, int lane) const {
-    fr::load_state<OPT, 1, NV>(st, p.R, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
+    fr::load_state<OPT, 1, NV, BFR>(st, p.R, p.s1, p.s2, p.last, key, p.oc, p.mc.DV, lane);
   }
   __device__ __forceinline__ void prefetch_state(uint32_t key, int lane) const {
     const uint32_t bytes = (uint32_t)p.mc.DV * 16u;
@@ -413,7 +415,7 @@ struct ItemPol {
     if (OPT != OPT_GENERIC || p.oc.learner == FR_RMSPROP) prefetch_l2_warp(p.s2 + off, bytes, (lane + 30) & 31);
   }
   __device__ __forceinline__ void apply(State& st, uint32_t key, float4 (&acc)[1][NV], int lane) const {
-    apply_and_store<OPT, 1, NV>(st, p.R, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
+    apply_and_store<OPT, 1, NV, BFR>(st, p.R, p.s1, p.s2, p.last, key, acc, p.oc, p.mc.DV, lane);
   }
 };
 
@@ -444,7 +446,7 @@ struct ItemGradPol : ItemPol<NVV, OPT_GENERIC> {
 
 // ---- policy: General_Memory rows (Write_Memory :201-215), entries = non-zeros of the
 // label feed sorted by label:  G[l] += sum lam*ws*[beta_2*pooledCat ; beta_1*m_c*R[i]]
-template <int NVV>
+template <int NVV, bool BFR = false>                // BFR: the recipe rows read here are bf16
 struct LabelPol {
   static constexpr int NV = NVV;
   static constexpr int NR = 5;
@@ -496,7 +498,7 @@ struct LabelPol {
       float4 rr4[PF][NV];
 #pragma unroll
       for (int u = 0; u < PF; ++u)
-        load_row_ro<NV>(rr4[u], p.R + (size_t)__shfl_sync(FR_FULL, e.item, min(j0 + u, e1 - 1)) * DVv, DVv, lane);
+        load_row_ro_t<NV>(rr4[u], tab_at<BFR>(p.R, (size_t)__shfl_sync(FR_FULL, e.item, min(j0 + u, e1 - 1)) * DVv), DVv, lane);
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         const int j = j0 + u;
@@ -1242,6 +1244,13 @@ void launch_user_commit(const uint32_t* keys, uint32_t n, int32_t* last, const f
 
 void launch_user_pass(int NV, const SegCommon& c, const UserPolParams& p, const Launch& l) {
   const int opt = opt_of(p.oc.learner, p.oc.adam_mode);
+  if (p.tab != 0) {      // bf16 tables: SGD / Adagrad / RMSProp only (fr_set_table_format checks the learner)
+    if (NV == 1) { if (p.tab == 1) { UserPol<1, OPT_GENERIC, 1> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
+                   else { UserPol<1, OPT_GENERIC, 2> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); } }
+    else         { if (p.tab == 1) { UserPol<2, OPT_GENERIC, 1> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); }
+                   else { UserPol<2, OPT_GENERIC, 2> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); } }
+    return;
+  }
   FR_DISPATCH_NV_OPT(NV, opt, { UserPol<NV_, OPT_> pol{p}; launch_seg(c, pol, p.mc.DV, true, l); });
 }
 void launch_personal_pass(int NV, const SegCommon& c, const UserPolParams& p, const Launch& l) {
@@ -1250,6 +1259,11 @@ void launch_personal_pass(int NV, const SegCommon& c, const UserPolParams& p, co
 }
 void launch_item_pass(int NV, const SegCommon& c, const ItemPolParams& p, const Launch& l) {
   const int opt = opt_of(p.oc.learner, p.oc.adam_mode);
+  if (p.tab != 0) {
+    if (NV == 1) { ItemPol<1, OPT_GENERIC, true> pol{p}; launch_seg(c, pol, p.mc.DV, false, l); }
+    else { ItemPol<2, OPT_GENERIC, true> pol{p}; launch_seg(c, pol, p.mc.DV, false, l); }
+    return;
+  }
   FR_DISPATCH_NV_OPT(NV, opt, { ItemPol<NV_, OPT_> pol{p}; launch_seg(c, pol, p.mc.DV, false, l); });
 }
 void launch_item_grad_pass(int NV, const SegCommon& c, const ItemPolParams& p, float4* gbuf, const PeerPtrs& peers,
@@ -1262,6 +1276,11 @@ void launch_label_pass(int NV, const SegCommon& c, const LabelPolParams& p, cons
 #ifndef FR_LABEL_TC
 #define FR_LABEL_TC 8
 #endif
+  if (p.tab == 1) {
+    if (NV == 1) { LabelPol<1, true> pol{p}; launch_seg_tiled<LabelPol<1, true>, FR_LABEL_TC>(c, pol, p.mc.DV, true, l); }
+    else { LabelPol<2, true> pol{p}; launch_seg_tiled<LabelPol<2, true>, FR_LABEL_TC>(c, pol, p.mc.DV, true, l); }
+    return;
+  }
   if (NV == 1) { LabelPol<1> pol{p}; launch_seg_tiled<LabelPol<1>, FR_LABEL_TC>(c, pol, p.mc.DV, true, l); }
   else { LabelPol<2> pol{p}; launch_seg_tiled<LabelPol<2>, FR_LABEL_TC>(c, pol, p.mc.DV, true, l); }
 }

@@ -83,7 +83,7 @@ void launch_serve_keys(const int32_t* rreq, uint32_t n, uint32_t items_per_rank,
 // (source s, j) is stored straight into rank s's receive buffer over NVLink (fused gather + exchange).
 __global__ void __launch_bounds__(FR_THREADS)
 gather_rows_kernel(const float4* __restrict__ R, const int32_t* __restrict__ rreq, uint32_t n, int DV,
-                   float4* __restrict__ out, const PeerPtrs peers, uint32_t n_table) {
+                   float4* __restrict__ out, const PeerPtrs peers, uint32_t n_table, int bf16) {
   const int lane = threadIdx.x & 31;
   const uint32_t gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5), nw = gridDim.x * FR_WARPS_PER_BLOCK;
   for (uint32_t r = gw; r < n; r += nw) {
@@ -95,15 +95,16 @@ gather_rows_kernel(const float4* __restrict__ R, const int32_t* __restrict__ rre
     }
     if (id < 0 && peers.world > 0) continue;          // empty request slot: the consumer never reads it -- no store over NVLink
     for (int i = lane; i < DV; i += 32)
-      dst[i] = (uint32_t)id < n_table ? R[(size_t)id * DV + i] : f4zero();      // (never out of the table)
+      dst[i] = (uint32_t)id >= n_table ? f4zero()                                  // (never out of the table)
+               : (bf16 ? tab_ld_ro(tab_at<true>(R, (size_t)id * DV + i)) : R[(size_t)id * DV + i]);   // bf16 table -> fp32 row
   }
 }
 void launch_gather_rows(const float4* R, const int32_t* rreq, uint32_t n, int DV, float4* out, const PeerPtrs& peers,
-                        const Launch& l, uint32_t n_table) {
+                        const Launch& l, uint32_t n_table, int bf16) {
   if (n == 0) return;
   int grid = (int)((n + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK);
   if (grid > l.sm_count * 16) grid = l.sm_count * 16;
-  gather_rows_kernel<<<grid, FR_THREADS, 0, l.st>>>(R, rreq, n, DV, out, peers, n_table); ++g_launches;
+  gather_rows_kernel<<<grid, FR_THREADS, 0, l.st>>>(R, rreq, n, DV, out, peers, n_table, bf16); ++g_launches;
 }
 
 // ---- routing of an UN-routed batch: a rank received arbitrary users; every group (sample / BPR triple) must reach

@@ -45,7 +45,7 @@ def _ptr(t):
 class Engine:
     def __init__(self, hyper: Hyper, P, R, Cat, G, device="cuda:0", max_rows=1 << 16,
                  max_label_entries=None, adam_mode="lazy", item_cats=None, user_labels=None,
-                 user_label_csr=None, adopt=False, single_pass=None):
+                 user_label_csr=None, adopt=False, single_pass=None, table_dtype="float32"):
         self.lib = L.lib()                       # raises if the .so is missing
         if not torch.cuda.is_available():
             raise RuntimeError("foodrec_b200 needs a CUDA device (no CPU fallback)")
@@ -55,11 +55,23 @@ class Engine:
         # adopt=True: float32 tensors that already live on the device are used in place (no second copy of a
         # table that fills a third of the HBM: cfg3 shards)
         def dev(x):
-            if adopt and torch.is_tensor(x) and x.dtype == torch.float32 and x.device == self.device and x.is_contiguous():
+            if adopt and torch.is_tensor(x) and x.device == self.device and x.is_contiguous() and (
+                    x.dtype == torch.float32 or (x.dtype == torch.bfloat16 and table_dtype == "bf16")):
                 return x
             return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x,
                                    dtype=torch.float32).to(self.device).contiguous().clone()
         self.P, self.R, self.Cat, self.G = dev(P), dev(R), dev(Cat), dev(G)
+        # bf16 tables (BASELINE configs[4]): Personal_Memory / Recipe_Embedding are STORED in bfloat16 (fp32 arithmetic,
+        # round to nearest even on store: fr_set_table_format); Cat, G and the optimizer slots stay fp32
+        if table_dtype not in ("float32", "bf16"):
+            raise ValueError("table_dtype must be 'float32' or 'bf16'")
+        self.table_bf16 = table_dtype == "bf16"
+        if self.table_bf16:
+            if L.learner_code(hyper.learner) == L.FR_ADAM:
+                raise L.FoodRecError("bf16 tables are offered for SGD / Adagrad / RMSProp (TF-1.x Adam moves every row every "
+                                     "step: see include/foodrec_b200.h:fr_set_table_format)")
+            self.P, self.R = self.P.to(torch.bfloat16), self.R.to(torch.bfloat16)     # torch rounds to nearest even
+            self.Cat, self.G = self.Cat.float(), self.G.float()
         self.U, five, self.D = self.P.shape
         assert five == 5 and self.Cat.shape == (4, self.D) and self.R.shape[1] == self.D
         self.I, self.Lb = self.R.shape[0], self.G.shape[0]
@@ -69,15 +81,15 @@ class Engine:
         if adam_mode not in modes:
             raise ValueError(f"adam_mode must be one of {sorted(modes)}")
         self.adam_mode = modes[adam_mode]
-        z = torch.zeros_like
+        z = lambda t: torch.zeros(t.shape, dtype=torch.float32, device=t.device)
         self.s1 = {}; self.s2 = {}
         tabs = {"P": self.P, "R": self.R, "Cat": self.Cat}
         if self.learner == L.FR_ADAM:
             self.s1 = {k: z(v) for k, v in tabs.items()}; self.s2 = {k: z(v) for k, v in tabs.items()}
         elif self.learner == L.FR_ADAGRAD:
-            self.s1 = {k: torch.full_like(v, hyper.adagrad_init) for k, v in tabs.items()}
+            self.s1 = {k: torch.full(v.shape, hyper.adagrad_init, dtype=torch.float32, device=v.device) for k, v in tabs.items()}
         elif self.learner == L.FR_RMSPROP:
-            self.s1 = {k: torch.ones_like(v) for k, v in tabs.items()}; self.s2 = {k: z(v) for k, v in tabs.items()}
+            self.s1 = {k: z(v) + 1.0 for k, v in tabs.items()}; self.s2 = {k: z(v) for k, v in tabs.items()}
         self.last_P = torch.zeros(self.U, dtype=torch.int32, device=self.device)
         self.last_R = torch.zeros(self.I, dtype=torch.int32, device=self.device)
         self.item_cats = None
@@ -127,6 +139,9 @@ class Engine:
             msg = self.lib.fr_last_error(self.handle).decode() if self.handle else "fr_create failed"
             self.lib.fr_destroy(self.handle); self.handle = None
             raise L.FoodRecError(msg)
+        if self.table_bf16:
+            L.check(self.handle, self.lib.fr_set_table_format(self.handle, L.FR_TABLE_BF16))
+            single_pass = False
         self._set_tables()
         # Single-pass step (fr_set_shadow): a second copy of Personal_Memory + its Adam slots lets the library score and
         # update a user's rows in ONE kernel (the two-pass step reads them twice: 6.1 -> 4.0 GB of DRAM traffic per
@@ -443,13 +458,23 @@ class Engine:
         self._keep = [pos]
         return out
 
+    def sample_bpr_batch(self, users, pos_items, n_neg, seed, sample_offset=0, num_items=0):
+        """(users [n*n_neg], items [2*n*n_neg]) int32 device: the 1:n_neg BPR batch of n positives -- every (user,
+        positive) repeated against n_neg sampled negatives (the draws of ``sample_negatives``), laid out as the step
+        consumes it.  ``num_items``: catalog size to draw from (0 = this engine's; a row-sharded rank passes the global one)."""
+        u, pos = self._i32(users), self._i32(pos_items)
+        n = pos.numel()
+        ou = torch.empty(n * int(n_neg), dtype=torch.int32, device=self.device)
+        oi = torch.empty(2 * n * int(n_neg), dtype=torch.int32, device=self.device)
+        L.check(self.handle, self.lib.fr_sample_bpr_batch(self.handle, _ptr(u), _ptr(pos), n, int(n_neg), int(seed) & (2**64 - 1),
+                                                          int(sample_offset), int(num_items), _ptr(ou), _ptr(oi), self._stream()))
+        self._keep = [u, pos]
+        return ou, oi
+
     def train_step_sampled(self, users, pos_items, n_neg, seed, sample_offset=0, **kw):
         """One BPR step with n_neg sampled negatives per positive: the batch of B positives becomes
         B*n_neg triples (u, i+, i-_j) drawn on the device (resident side tables required)."""
-        u, pos = self._i32(users), self._i32(pos_items)
-        neg = self.sample_negatives(pos, n_neg, seed, sample_offset)
-        items = torch.stack([pos.unsqueeze(1).expand(-1, n_neg), neg], 2).reshape(-1).contiguous()
-        uu = u.unsqueeze(1).expand(-1, n_neg).reshape(-1).contiguous()
+        uu, items = self.sample_bpr_batch(users, pos_items, n_neg, seed, sample_offset)
         return self._step_dev(L.FR_BPR, uu.numel(), uu, items, None, None, None, None, **kw)
 
     def philox(self, ctr_key):
@@ -469,11 +494,11 @@ class Engine:
     def tables(self):
         """Host copies of the four tables at the current step (flushes lazy Adam)."""
         self.flush()
-        return {k: getattr(self, k).detach().cpu().numpy() for k in ("P", "R", "Cat", "G")}
+        return {k: getattr(self, k).detach().float().cpu().numpy() for k in ("P", "R", "Cat", "G")}
 
     def state_dict(self):
         self.flush()
-        sd = {k: getattr(self, k).detach().cpu().numpy() for k in ("P", "R", "Cat", "G")}
+        sd = {k: getattr(self, k).detach().float().cpu().numpy() for k in ("P", "R", "Cat", "G")}
         for name, d in (("s1", self.s1), ("s2", self.s2)):
             for k, v in d.items():
                 sd[f"{name}_{k}"] = v.detach().cpu().numpy()

@@ -71,15 +71,16 @@ class ShardedEngine:
 
     def __init__(self, hyper: Hyper, P_loc, R_loc, Cat, G, rank, world, device="cuda:0", max_rows=1 << 16,
                  cap=None, adam_mode="lazy", item_cats_global=None, user_label_csr_local=None,
-                 max_label_entries=None, adopt=False, single_pass=None):
+                 max_label_entries=None, adopt=False, single_pass=None, table_dtype="float32"):
         if not (1 <= world <= 8):
             raise ValueError("1 <= world <= 8")
         self.rank, self.world = rank, world
         self.e = Engine(hyper, P_loc, R_loc, Cat, G, device=device, max_rows=max_rows, adam_mode=adam_mode,
                         item_cats=item_cats_global, user_label_csr=user_label_csr_local,
-                        max_label_entries=max_label_entries, adopt=adopt, single_pass=single_pass)
+                        max_label_entries=max_label_entries, adopt=adopt, single_pass=single_pass, table_dtype=table_dtype)
         e = self.e
         self.device = e.device
+        self.I_global = None if item_cats_global is None else int(len(item_cats_global))
         if cap is None:
             # unique recipes per (source, owner).  A batch has at most max_rows distinct recipes,
             # spread over the owners by id % W: max_rows/W on average even when every row is
@@ -139,6 +140,17 @@ class ShardedEngine:
         BPR rows interleaved pos/neg): nothing is copied or reshaped."""
         self._pending = (L.fr_batch(mode, B, _ptr(users_local), _ptr(items), _ptr(None), _ptr(labels), _ptr(None), _ptr(None)),
                          self._shard(global_batch if global_batch is not None else B), [users_local, items, labels])
+
+    def set_batch_sampled(self, users_local, pos_items_global, n_neg, seed, sample_offset=0, global_batch=None, num_items=None):
+        """1:n_neg BPR batch drawn on the device (fr_sample_bpr_batch): n (user, positive) pairs of THIS rank's users ->
+        n*n_neg triples, negatives uniform over the GLOBAL catalog.  ``sample_offset`` = the global index of this
+        rank's first pair, so the draws do not depend on how the pairs are spread over the ranks."""
+        ni = num_items if num_items is not None else self.I_global
+        if ni is None:
+            raise ValueError("set_batch_sampled needs the global recipe count (num_items= or item_cats_global)")
+        uu, items = self.e.sample_bpr_batch(users_local, pos_items_global, n_neg, seed, sample_offset, num_items=ni)
+        B = uu.numel()
+        self.set_batch_dev(L.FR_BPR, B, uu, items, global_batch=global_batch if global_batch is not None else B)
 
     def set_batch_raw(self, batch, keep, global_batch):
         """An fr_batch built by the caller (device pointers) -- e.g. the reference's dense feed."""

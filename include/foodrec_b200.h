@@ -114,6 +114,17 @@ int fr_destroy(fr_handle h);
 const char* fr_last_error(fr_handle h);
 int fr_set_tables(fr_handle h, const fr_tables* t);
 
+/* Storage format of Personal_Memory and Recipe_Embedding (BASELINE configs[4]: bf16 tables).  FR_TABLE_BF16: tables.P and
+ * tables.R point to bf16 rows (same shapes, 2 bytes per element, 8-byte aligned); Category_Embedding, General_Memory and
+ * the optimizer slots stay fp32.  All arithmetic is fp32: a row is converted on load and ROUNDED TO NEAREST EVEN ON STORE
+ * (the rule oracle/recommender_oracle.py states and the CUDA path is tested against).  Offered for the natively sparse
+ * optimizers (SGD, Adagrad, RMSProp): TF-1.x Adam moves EVERY row EVERY step, which has no sensible meaning on rows that
+ * are re-rounded to 8 bits of mantissa each time (updates below half an ulp vanish) -- FR_ADAM returns FR_ERR_UNSUPPORTED.
+ * Not available with bf16 tables: personal-write steps, fr_catalog_* (its exact re-rank reads fp32 rows), fr_set_shadow.
+ * The row-sharded phases exchange recipe rows in fp32 (the owner's gather converts).  Call before fr_set_tables. */
+enum { FR_TABLE_F32 = 0, FR_TABLE_BF16 = 1 };
+int fr_set_table_format(fr_handle h, int32_t format);
+
 /* Single-pass training step (lazy Adam only).  The two-pass step reads Personal_Memory and its Adam slots twice per
  * step -- once to score, once to update -- because tf.clip_by_global_norm (Model_Recommender.py:237) separates the
  * gradient from apply_gradients.  With a second, caller-owned copy of P / m / v ([U,5,D] each, contents irrelevant)
@@ -293,6 +304,13 @@ int fr_catalog_fallback_rows(fr_handle h, int32_t* out, fr_stream s);
  * pos_items [n] device; out [n, n_neg] device; sample index = sample_offset + row. */
 int fr_sample_negatives(fr_handle h, const int32_t* pos_items, int64_t n, int32_t n_neg, uint64_t seed,
                         uint64_t sample_offset, int32_t* out, fr_stream s);
+/* The same draws written as the expanded BPR batch fr_train_step / fr_shard_plan consume: for sample s and negative j,
+ * triple t = s*n_neg + j gets out_users[t] = users[s], out_items[2t] = pos_items[s], out_items[2t+1] = the negative.
+ * num_items = the size of the catalog the negatives are drawn from (0: this handle's Recipe_Embedding; a row-sharded
+ * rank passes the GLOBAL recipe count).  out_users [n*n_neg], out_items [2*n*n_neg] (8-byte aligned), device. */
+int fr_sample_bpr_batch(fr_handle h, const int32_t* users, const int32_t* pos_items, int64_t n, int32_t n_neg,
+                        uint64_t seed, uint64_t sample_offset, int64_t num_items, int32_t* out_users,
+                        int32_t* out_items, fr_stream s);
 /* The raw generator (known-answer tests): ctr_key [n,6] = counter[4], key[2] -> out [n,4]. */
 int fr_philox4x32_10(fr_handle h, const uint32_t* ctr_key, int32_t n, uint32_t* out, fr_stream s);
 

@@ -72,6 +72,18 @@ def sigmoid(s):
     return np.where(s >= 0, 1 / (1 + e), e / (1 + e)).astype(s.dtype)
 
 
+def round_bf16(x):
+    """Round-to-nearest-even to bfloat16, returned in x's dtype (the storage rule of bf16 tables: BASELINE configs[4];
+    an extension -- the reference has no reduced-precision path, so this function IS the definition the CUDA path is
+    held to).  Values are first taken to float32 (exact for the float32 oracle; for the float64 oracle this is the
+    float32 value the kernels' fp32 arithmetic would hold, up to its own rounding)."""
+    a = np.ascontiguousarray(np.asarray(x, np.float32))
+    u = a.view(np.uint32)
+    r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    out = ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+    return out.astype(np.asarray(x).dtype)
+
+
 def _segment_sum(idx, values):
     """unique + unsorted_segment_sum, sequential in batch order
     (``optimizer.py:_deduplicate_indexed_slices``)."""
@@ -102,17 +114,27 @@ def health_rows(P, G, user_labels, alpha, users=None):
 
 
 class OracleModel:
-    def __init__(self, P, R, Cat, G, hyper: Hyper | None = None, dtype=np.float32):
+    def __init__(self, P, R, Cat, G, hyper: Hyper | None = None, dtype=np.float32, table_dtype=None):
+        """``table_dtype="bf16"`` (extension, BASELINE configs[4]): Personal_Memory and Recipe_Embedding only ever hold
+        bfloat16-representable values -- rounded to nearest even when the model is built and whenever the optimizer
+        stores a row; all arithmetic, Category_Embedding, General_Memory and the optimizer slots stay in ``dtype``.
+        Offered for SGD / Adagrad / RMSProp (rows outside the batch never change); Adam and personal-write steps raise."""
         self.h = hyper or Hyper()
         self.dt = np.dtype(dtype)
+        self.bf16 = table_dtype == "bf16"
+        assert table_dtype in (None, "bf16")
         c = lambda x: np.array(x, dtype=self.dt, copy=True)
         self.P, self.R, self.Cat, self.G = c(P), c(R), c(Cat), c(G)
+        if self.bf16:
+            self.P, self.R = round_bf16(self.P), round_bf16(self.R)
         self.U, _, self.D = self.P.shape
         self.I = self.R.shape[0]
         self.L = self.G.shape[0]
         self.learner = self.h.learner.lower()
         if self.learner not in ("adam", "adagrad", "rmsprop"):
             self.learner = "sgd"                       # :234-235 (anything else)
+        if self.bf16 and self.learner == "adam":
+            raise ValueError("bf16 tables: SGD / Adagrad / RMSProp only (TF-1.x Adam moves every row every step)")
         f = self.dt.type
         self.a = f(self.h.high_level_score_coefficient)   # tf.constant(...)  :17
         self.one_minus_a = f(1) - self.a                  # (1 - coef)        :96
@@ -231,6 +253,11 @@ class OracleModel:
                 self._adagrad(uu, gP, ui, gR, dCat)
             else:
                 self._rmsprop(uu, gP, ui, gR, dCat)
+        if self.bf16:      # the rows the optimizer stored: round to nearest even (one store per touched row per step)
+            if write_personal:
+                raise ValueError("bf16 tables: personal-write steps are not defined")
+            tu, ti = np.unique(slice_users), np.unique(items)
+            self.P[tu] = round_bf16(self.P[tu]); self.R[ti] = round_bf16(self.R[ti])
         # ---- commit the memory write ----
         out = dict(loss=f(loss), lr=f(self.h.lr), norm=norm, scale=scale, scores=scores)
         if write_personal:
