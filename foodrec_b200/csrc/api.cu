@@ -132,7 +132,7 @@ extern "C" int fr_destroy(fr_handle h) {
   if (h->stage) cudaFree(h->stage);
   for (auto& sl : h->feed) { if (sl.buf) cudaFree(sl.buf); if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->aux_fork); cudaEventDestroy(h->aux_join); }
+  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->aux_fork); cudaEventDestroy(h->aux_fork2); cudaEventDestroy(h->aux_join); }
   if (h->pieces_personal) cudaFree(h->pieces_personal);
   delete h;
   return FR_OK;
@@ -381,11 +381,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   int rl = 0;
   const uint32_t ecap = (uint32_t)h->sortL.cap;
   {
-    if (!h->aux_stream) {
-      FR_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
-      FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming));
-      FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming));
-    }
+    if ((rc = aux_ensure(h))) return rc;
     FR_CUDA(h, cudaEventRecord(h->aux_fork, st));
     FR_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
     Launch la{h->sm_count, h->aux_stream, nullptr};
@@ -400,7 +396,6 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     launch_label_emit(ep, la);
     rl = radix_sort_pairs(h->sortL, h->ent_key, ecap, h->n_entries, bits_for(h->mc.L), h->aux_stream, h->sm_count);
     FR_CHECK_LAUNCH(h);
-    FR_CUDA(h, cudaEventRecord(h->aux_join, h->aux_stream));
   }
   SortJob sj[2] = {{&h->sortU, h->ukeys, (uint32_t)S, nullptr, bits_for(h->cfg.num_users), 0},
                    {&h->sortI, (const uint32_t*)items, (uint32_t)S, nullptr, bits_for(h->cfg.num_items), 0}};
@@ -417,6 +412,33 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
                         T.last_R, DV, oc, l);
     FR_CHECK_LAUNCH(h);
   }
+  // 1c. General_Memory pass (5): it reads only pre-step state (R rows of this batch -- current after the catch-up above --
+  //     the Category_Embedding snapshot, the entry list of 1b) and writes G, which nothing else in the step reads except
+  //     a personal-write pass (pre-step G, Model_Recommender.py:170-198) and the final mean.  So on ordinary steps it runs
+  //     on the side stream too, beside the forward / user pass (bandwidth-bound; this pass is issue-bound), and is joined
+  //     before the recipe pass overwrites R.
+  //     (With fr_timing_enable the pass runs in sequence, so that every phase time is that of its kernels alone.)
+  const bool label_aside = !write_personal && !h->timing && !getenv("FOODREC_LABEL_SERIAL");
+  auto label_pass = [&](Launch& ll) -> int {
+    SegCommon c{};
+    c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
+    c.pieces = h->pieces_g; c.uniq_counter = nullptr;
+    c.long_list = h->long_list; c.long_count = h->counters + 2; c.long_cap = h->long_cap;
+    LabelPolParams lp{};
+    lp.G = (float4*)T.G; lp.R = (const float4*)T.R; lp.cat = h->cat_pre;
+    lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = items; lp.cats = cats;
+    lp.cats_by_item = cats_by_item; lp.mc = h->mc; lp.tab = h->table_bf16 ? 1 : 0;
+    launch_label_pass(NV, c, lp, ll);
+    FR_CHECK_LAUNCH(h);
+    return FR_OK;
+  };
+  if (label_aside) {
+    FR_CUDA(h, cudaEventRecord(h->aux_fork2, st));
+    FR_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_fork2, 0));
+    Launch la{h->sm_count, h->aux_stream, nullptr};
+    rc = label_pass(la); if (rc) return rc;
+  }
+  FR_CUDA(h, cudaEventRecord(h->aux_join, h->aux_stream));
 
   FR_MARK(FR_T_FWD);
   int fgrid;
@@ -509,17 +531,8 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   //    354 us + 25 us against this pass's 254 us at 524k rows; see DESIGN.md "measured and rejected".)
   {
     l.mid = nullptr;
-    FR_CUDA(h, cudaStreamWaitEvent(st, h->aux_join, 0));      // JOIN: the entry list built on the side stream (1b)
-    SegCommon c{};
-    c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
-    c.pieces = h->pieces_g; c.uniq_counter = nullptr;
-    c.long_list = h->long_list; c.long_count = h->counters + 2; c.long_cap = h->long_cap;
-    LabelPolParams lp{};
-    lp.G = (float4*)T.G; lp.R = (const float4*)T.R; lp.cat = h->cat_pre;
-    lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = items; lp.cats = cats;
-    lp.cats_by_item = cats_by_item; lp.mc = h->mc; lp.tab = h->table_bf16 ? 1 : 0;
-    launch_label_pass(NV, c, lp, l);
-    FR_CHECK_LAUNCH(h);
+    FR_CUDA(h, cudaStreamWaitEvent(st, h->aux_join, 0));      // JOIN: the side stream (entry list 1b, and the pass itself 1c)
+    if (!label_aside) { rc = label_pass(l); if (rc) return rc; }
   }
 
   FR_MARK(FR_T_ITEM_CHUNK);

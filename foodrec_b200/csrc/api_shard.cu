@@ -263,6 +263,46 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   const OptConsts oc = make_oc(h, h->step + 1);
   const bool lazy = h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE;
 
+  const bool aside = !getenv("FOODREC_LABEL_SERIAL");
+  auto label_chain = [&](Launch& la) -> int {
+    // General_Memory delta of this rank's rows -> packed (G itself is updated after the all-reduce).  Entry list (count,
+    // scan, emit, sort by label) and the segment reduce read only the batch, the received rows and the Cat snapshot: they
+    // run on the library's side stream BESIDE the forward / single-pass kernel (bandwidth-bound; this chain is issue- and
+    // latency-bound) and are joined at the end of the phase (FOODREC_LABEL_SERIAL: in sequence, as before).
+    float* dG = packed + 4 + 4 * (size_t)h->mc.D;
+    FR_CUDA(h, cudaMemsetAsync(dG, 0, 5 * (size_t)h->mc.L * h->mc.D * sizeof(float), la.st));
+    LabelEmitParams ep{};
+    ep.S = S; ep.group = ps.group; ep.L = h->mc.L; ep.users = ps.users_s;
+    ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
+    ep.ws_row = ps.ws_row; ep.counts = h->counts; ep.offs = h->offs;
+    ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
+    ep.cap = (uint32_t)h->sortL.cap; ep.n_entries = h->n_entries; ep.out = ps.flag_out;
+    launch_label_count(ep, la);
+    exclusive_scan_u32(h->counts, h->offs, (uint32_t)S, h->scan_tmp, h->n_entries, la.st);
+    launch_label_emit(ep, la);
+    const uint32_t ecap = (uint32_t)h->sortL.cap;
+    const int rl = radix_sort_pairs(h->sortL, h->ent_key, ecap, h->n_entries, bits_for(h->mc.L), la.st, h->sm_count);
+    SegCommon c{};
+    c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
+    c.pieces = h->pieces_g; c.uniq_counter = nullptr;
+    c.long_list = h->long_list; c.long_count = h->counters + 2; c.long_cap = h->long_cap;
+    LabelPolParams lp{};
+    lp.G = (float4*)dG; lp.R = (const float4*)rbuf; lp.cat = h->cat_pre;
+    lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = ps.slot_of_row; lp.cats = ps.cats_row;
+    lp.cats_by_item = 0; lp.mc = h->mc; lp.tab = 0;
+    launch_label_pass(NV, c, lp, la);
+    FR_CHECK_LAUNCH(h);
+    return FR_OK;
+  };
+  if (aside) {
+    if ((rc = aux_ensure(h))) return rc;
+    FR_CUDA(h, cudaEventRecord(h->aux_fork, st));
+    FR_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+    Launch la{h->sm_count, h->aux_stream, nullptr};
+    rc = label_chain(la); if (rc) return rc;
+    FR_CUDA(h, cudaEventRecord(h->aux_join, h->aux_stream));
+  }
+
   int fgrid;
   ps.fused = lazy && h->shP && !getenv("FOODREC_TWO_PASS");
   if (ps.fused) {
@@ -303,29 +343,8 @@ extern "C" int fr_shard_forward(fr_handle h, const fr_batch* b, const fr_shard* 
   fin.oc = oc; fin.clip = h->cfg.clip_norm; fin.out = ps.flag_out; fin.lr_hist = nullptr;
   launch_finalize(fin, l);
 
-  // General_Memory delta of this rank's rows -> packed (G itself is updated after the all-reduce)
-  float* dG = packed + 4 + 4 * (size_t)h->mc.D;
-  FR_CUDA(h, cudaMemsetAsync(dG, 0, 5 * (size_t)h->mc.L * h->mc.D * sizeof(float), st));
-  LabelEmitParams ep{};
-  ep.S = S; ep.group = ps.group; ep.L = h->mc.L; ep.users = ps.users_s;
-  ep.user_labels = b->user_labels; ep.lab_off = T.user_label_off; ep.lab_idx = T.user_label_idx;
-  ep.ws_row = ps.ws_row; ep.counts = h->counts; ep.offs = h->offs;
-  ep.ent_key = h->ent_key; ep.ent_row = h->ent_row; ep.ent_coef = h->ent_coef;
-  ep.cap = (uint32_t)h->sortL.cap; ep.n_entries = h->n_entries; ep.out = ps.flag_out;
-  launch_label_count(ep, l);
-  exclusive_scan_u32(h->counts, h->offs, (uint32_t)S, h->scan_tmp, h->n_entries, st);
-  launch_label_emit(ep, l);
-  const uint32_t ecap = (uint32_t)h->sortL.cap;
-  const int rl = radix_sort_pairs(h->sortL, h->ent_key, ecap, h->n_entries, bits_for(h->mc.L), st, h->sm_count);
-  SegCommon c{};
-  c.keys = h->sortL.k[rl]; c.perm = h->sortL.v[rl]; c.n_dev = h->n_entries; c.n_host = ecap;
-  c.pieces = h->pieces_g; c.uniq_counter = nullptr;
-  c.long_list = h->long_list; c.long_count = h->counters + 2; c.long_cap = h->long_cap;
-  LabelPolParams lp{};
-  lp.G = (float4*)dG; lp.R = (const float4*)rbuf; lp.cat = h->cat_pre;
-  lp.ent_row = h->ent_row; lp.ent_coef = h->ent_coef; lp.items = ps.slot_of_row; lp.cats = ps.cats_row;
-  lp.cats_by_item = 0; lp.mc = h->mc; lp.tab = 0;
-  launch_label_pass(NV, c, lp, l);
+  if (aside) FR_CUDA(h, cudaStreamWaitEvent(st, h->aux_join, 0));
+  else { rc = label_chain(l); if (rc) return rc; }
   FR_CHECK_LAUNCH(h);
   return FR_OK;
 }

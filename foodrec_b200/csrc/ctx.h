@@ -90,7 +90,7 @@ struct fr_ctx {
   cudaStream_t copy_stream = nullptr;
   // fork / join inside fr_train_step: the label feed's entry list (count, scan, emit, sort by label) depends only on the
   // batch and is built on this stream while the sorts, catch-up and the forward run on the caller's
-  cudaStream_t aux_stream = nullptr; cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  cudaStream_t aux_stream = nullptr; cudaEvent_t aux_fork = nullptr, aux_fork2 = nullptr, aux_join = nullptr;
   int feed_next = 0;
   // per-phase timing (fr_timing_*)
   bool timing = false;
@@ -133,6 +133,18 @@ static inline int dalloc(fr_ctx* h, T** p, size_t count) {
   if (e != cudaSuccess) return fail(h, FR_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
   h->allocs.push_back(q);
   *p = static_cast<T*>(q);
+  return FR_OK;
+}
+
+// the step's side stream (highest priority: its CTAs are placed first when both streams have work) + fork/join events
+static inline int aux_ensure(fr_ctx* h) {
+  if (h->aux_stream) return FR_OK;
+  int lo = 0, hi = 0;
+  FR_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  FR_CUDA(h, cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi));
+  FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming));
+  FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_fork2, cudaEventDisableTiming));
+  FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming));
   return FR_OK;
 }
 
