@@ -86,12 +86,10 @@ void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, c
 #undef FR_SCORE
 }
 
-// One warp per test user.  Candidate j lives in lane j&31, slot j>>5 (<= 128 candidates; SLOTS = 2 covers the
-// reference's 51).  Scoring is LANE-PER-CANDIDATE: the user's five rows are staged in shared memory, and lane j walks
-// the recipe row of ITS candidate, so a score costs no warp reduction at all (the row-per-warp form spent two
-// 5-step shuffle reductions and two IEEE divisions on every candidate: ~110 warp instructions each, 22 ms per 1M
-// users while the recipe table sits in L2).  The category term a/n * sum_c m_c <P[u,0], Cat[c]> needs the four dot
-// products <P[u,0], Cat[c]> once per user; the recipe term is sum_d (sum_c m_c P[u,1+c]_d) R[i]_d accumulated by the lane.
+// One warp per test user.  Candidate j's id, category weights and final score live in lane j&31, slot j>>5 (<= 128
+// candidates; SLOTS = 2 covers the reference's 51); the user's five rows live in registers (lane l: 16-byte group l).
+// The category term a/n * sum_c m_c <P[u,0], Cat[c]> needs the four dot products <P[u,0], Cat[c]> once per user; the
+// recipe term sum_d (sum_c m_c P[u,1+c]_d) R[i]_d is computed row-per-warp with a transposed reduction (see below).
 template <int NV, int SLOTS, bool BF>
 __global__ void __launch_bounds__(FR_THREADS)
 eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, const float4* __restrict__ Cat,
@@ -105,7 +103,6 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
   for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) sCat[i] = Cat[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  float4* sP = smem + 4 * DV + (threadIdx.x >> 5) * 5 * DV;         // this warp's user rows [5*DV]
   const int gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5), nw = gridDim.x * FR_WARPS_PER_BLOCK;
   for (int w = gw; w < n_users; w += nw) {
     const int u = users[w];
@@ -132,86 +129,87 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       if (id[q] >= 0) mq[q] = cand_cats ? __ldg(cand_cats + (size_t)w * stride + j) : __ldg(item_cats + id[q]);
     }
     float b0, b1, b2, b3;
-    {
-      float4 pr[5][NV];
+    float4 pr[5][NV];
 #pragma unroll
-      // read-once rows: streamed (evict-first) so that the recipe table, which every user re-reads, stays in L2
-      for (int s = 0; s < 5; ++s) load_row_cs_t<NV>(pr[s], tab_at<BF>(P, ((size_t)u * 5 + s) * DV), DV, lane);
-      health_blend_rows<NV>(pr, hb, u, DV, lane);
+    // read-once rows: streamed (evict-first) so that the recipe table, which every user re-reads, stays in L2
+    for (int s = 0; s < 5; ++s) load_row_cs_t<NV>(pr[s], tab_at<BF>(P, ((size_t)u * 5 + s) * DV), DV, lane);
+    health_blend_rows<NV>(pr, hb, u, DV, lane);
+    {
       float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-      __syncwarp();                                                  // the previous user's rows are no longer read
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int i = lane + 32 * k;
         if (i < DV) {
-#pragma unroll
-          for (int s = 1; s < 5; ++s) sP[s * DV + i] = pr[s][k];
           t0 += dot4(pr[0][k], sCat[i]); t1 += dot4(pr[0][k], sCat[DV + i]);
           t2 += dot4(pr[0][k], sCat[2 * DV + i]); t3 += dot4(pr[0][k], sCat[3 * DV + i]);
         }
       }
       b0 = warp_sum(t0); b1 = warp_sum(t1); b2 = warp_sum(t2); b3 = warp_sum(t3);
-      __syncwarp();
     }
-    // two slots per walk: the shared-memory reads of the user rows serve both candidates and twice as many recipe
-    // row loads are in flight per lane.
-    // (Round 2 measured an alternative -- eight lanes per candidate row, i.e. four full 128-byte lines per load
-    //  instruction instead of 32 partial ones, one 3-step shuffle reduction per four candidates: 9.4 ms per 1M users
-    //  against this form's 7.5 ms; the extra shuffles and shared-memory reads cost more than the coalescing saves.)
+    // Scoring: ROW-PER-WARP loads, one reduction per 32 candidates.  Candidate j's recipe row is read by the whole warp
+    // (lane l takes 16-byte group l: a 512-byte row is 4 full lines, 4 L1 wavefronts), each lane forms its part of
+    // sum_d (sum_c m_c P[u,1+c]_d) R[i]_d against the user rows it holds in registers, and the 32 partials a lane has
+    // collected for 32 candidates are summed across the warp by ONE transposing butterfly (31 shuffles per 32
+    // candidates; lane j ends with candidate j's sum) instead of a 5-step reduction per candidate.
+    // (History: the first form, row-per-warp with two shuffle reductions and two divisions per candidate, took 22 ms
+    //  per 1M users; the second, lane-per-candidate -- lane j walks the row of ITS candidate, no reduction at all --
+    //  7.5 ms: every load instruction touched 32 different lines for 16 bytes each, 2048 L1 wavefronts per user, and
+    //  the SM's one-wavefront-per-cycle L1 port was the limit (2048 x 1M / 148 SMs / 1.9 GHz = 7.3 ms).  An eight-lanes-
+    //  per-candidate variant with a reduction per four candidates measured 9.4 ms.)
+    constexpr int CB = 8;                         // candidate rows in flight per warp
 #pragma unroll
-    for (int q = 0; q < SLOTS; q += 2) {
-      if (q * 32 >= nc) break;
-      const bool vA = id[q] >= 0, vB = id[q + 1] >= 0;
-      const float4 mA = mq[q], mB = mq[q + 1];
-      const typename TabVec<BF>::type* rpA = tab_at<BF>(R, (size_t)(vA ? id[q] : 0) * DV);
-      const typename TabVec<BF>::type* rpB = tab_at<BF>(R, (size_t)(vB ? id[q + 1] : 0) * DV);
-      float accA = 0.f, accB = 0.f;
-      if ((q + 1) * 32 < nc) {
-#pragma unroll 4
-        for (int i = 0; i < DV; ++i) {
-          const float4 ra = tab_ld_ro(rpA + i), rb = tab_ld_ro(rpB + i);
-          const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
-          float4 za, zb;
-          za.x = mA.x * p1.x + mA.y * p2.x + mA.z * p3.x + mA.w * p4.x;
-          za.y = mA.x * p1.y + mA.y * p2.y + mA.z * p3.y + mA.w * p4.y;
-          za.z = mA.x * p1.z + mA.y * p2.z + mA.z * p3.z + mA.w * p4.z;
-          za.w = mA.x * p1.w + mA.y * p2.w + mA.z * p3.w + mA.w * p4.w;
-          zb.x = mB.x * p1.x + mB.y * p2.x + mB.z * p3.x + mB.w * p4.x;
-          zb.y = mB.x * p1.y + mB.y * p2.y + mB.z * p3.y + mB.w * p4.y;
-          zb.z = mB.x * p1.z + mB.y * p2.z + mB.z * p3.z + mB.w * p4.z;
-          zb.w = mB.x * p1.w + mB.y * p2.w + mB.z * p3.w + mB.w * p4.w;
-          accA += dot4(za, ra); accB += dot4(zb, rb);
+    for (int q = 0; q < SLOTS; ++q) {
+      const int ncg = nc - q * 32;                // candidates of this slot (warp-uniform)
+      if (ncg <= 0) break;
+      float v[32];
+#pragma unroll
+      for (int b = 0; b < 32; b += CB) {
+        if (b >= ncg) {
+#pragma unroll
+          for (int t = 0; t < CB; ++t) v[b + t] = 0.f;
+          continue;
         }
-      } else {
-        float acc1 = 0.f;
-        auto step = [&](int i, float& acc) {
-          const float4 r = tab_ld_ro(rpA + i);
-          const float4 p1 = sP[DV + i], p2 = sP[2 * DV + i], p3 = sP[3 * DV + i], p4 = sP[4 * DV + i];
-          float4 z;
-          z.x = mA.x * p1.x + mA.y * p2.x + mA.z * p3.x + mA.w * p4.x;
-          z.y = mA.x * p1.y + mA.y * p2.y + mA.z * p3.y + mA.w * p4.y;
-          z.z = mA.x * p1.z + mA.y * p2.z + mA.z * p3.z + mA.w * p4.z;
-          z.w = mA.x * p1.w + mA.y * p2.w + mA.z * p3.w + mA.w * p4.w;
-          acc += dot4(z, r);
-        };
-        const int DVe = DV & ~1;
-#pragma unroll 4
-        for (int i = 0; i < DVe; i += 2) { step(i, accA); step(i + 1, acc1); }
-        if (DV & 1) step(DV - 1, accA);
-        accA += acc1;
+        int idj[CB]; float4 rr[CB][NV];
+#pragma unroll
+        for (int t = 0; t < CB; ++t) idj[t] = __shfl_sync(FR_FULL, id[q], b + t);
+#pragma unroll
+        // (a lane without a candidate -- past n_cand, or an id outside the table -- reads row 0: its score is never kept)
+        for (int t = 0; t < CB; ++t) load_row_ro_t<NV>(rr[t], tab_at<BF>(R, (size_t)(idj[t] >= 0 ? idj[t] : 0) * DV), DV, lane);
+#pragma unroll
+        for (int t = 0; t < CB; ++t) {
+          float4 m;                               // the candidate's category weights, from the lane that holds them
+          m.x = __shfl_sync(FR_FULL, mq[q].x, b + t); m.y = __shfl_sync(FR_FULL, mq[q].y, b + t);
+          m.z = __shfl_sync(FR_FULL, mq[q].z, b + t); m.w = __shfl_sync(FR_FULL, mq[q].w, b + t);
+          float part = 0.f;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            float4 z;
+            z.x = m.x * pr[1][k].x + m.y * pr[2][k].x + m.z * pr[3][k].x + m.w * pr[4][k].x;
+            z.y = m.x * pr[1][k].y + m.y * pr[2][k].y + m.z * pr[3][k].y + m.w * pr[4][k].y;
+            z.z = m.x * pr[1][k].z + m.y * pr[2][k].z + m.z * pr[3][k].z + m.w * pr[4][k].z;
+            z.w = m.x * pr[1][k].w + m.y * pr[2][k].w + m.z * pr[3][k].w + m.w * pr[4][k].w;
+            part += dot4(z, rr[t][k]);
+          }
+          v[b + t] = part;
+        }
       }
-      {
-        const float rn = __frcp_rn(((mA.x + mA.y) + mA.z) + mA.w);     // x * (1/n): exact for n = 1, 2, 4
-        const float high = (((mA.x * b0 + mA.y * b1) + mA.z * b2) + mA.w * b3) * rn;   // :67-79
-        const float s = a * high + oma * (accA * rn);                                  // :82-96
-        if (vA) { sc[q] = s; if (scores_out) scores_out[(size_t)w * stride + q * 32 + lane] = s; }
+      // transposing butterfly: after the step with offset o, v[i] (i < o) holds the sum over 32/o lanes for the
+      // candidate whose index has this lane's bits >= o and low bits i; after offset 1, v[0] is candidate `lane`
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+          const float send = hi ? v[i] : v[i + off];
+          const float keep = hi ? v[i + off] : v[i];
+          v[i] = keep + __shfl_xor_sync(FR_FULL, send, off);
+        }
       }
-      {
-        const float rn = __frcp_rn(((mB.x + mB.y) + mB.z) + mB.w);
-        const float high = (((mB.x * b0 + mB.y * b1) + mB.z * b2) + mB.w * b3) * rn;
-        const float s = a * high + oma * (accB * rn);
-        if (vB) { sc[q + 1] = s; if (scores_out) scores_out[(size_t)w * stride + (q + 1) * 32 + lane] = s; }
-      }
+      const float4 m = mq[q];
+      const float rn = __frcp_rn(((m.x + m.y) + m.z) + m.w);       // x * (1/n): exact for n = 1, 2, 4
+      const float high = (((m.x * b0 + m.y * b1) + m.z * b2) + m.w * b3) * rn;   // :67-79
+      const float sq = a * high + oma * (v[0] * rn);                              // :82-96
+      if (id[q] >= 0) { sc[q] = sq; if (scores_out) scores_out[(size_t)w * stride + q * 32 + lane] = sq; }
     }
     // dict semantics (evaluate.py:60-61): the first position of an id survives and takes the score of its last
     // occurrence.  Repeated ids are rare (0.65 % of users at 51 of 200k), so they are DETECTED first -- match.any
@@ -287,7 +285,7 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   if (n_users <= 0) return;
   int grid = (n_users + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
-  const size_t smem = (size_t)(4 + 5 * FR_WARPS_PER_BLOCK) * mc.DV * sizeof(float4);
+  const size_t smem = (size_t)4 * mc.DV * sizeof(float4);
   ++g_launches;
   // launched with cudaLaunchKernelEx so that a persisting-L2 access-policy window (Recipe_Embedding: every user re-reads
   // 51 random rows of it while 2.5 KB of read-once user rows per user stream past) can ride on the LAUNCH: a stream
