@@ -288,6 +288,8 @@ extern "C" int fr_eval_sampled_topk(fr_handle h, const int32_t* users, const int
   if (n_users < 0 || cand_stride <= 0 || cand_stride > 128 || K <= 0) return fail(h, FR_ERR_ARG, "need 0<cand_stride<=128, K>0");
   if (n_users > 0 && (!users || !cand || !n_cand || !topk_ids || !gt_rank)) return fail(h, FR_ERR_ARG, "null pointer");
   if (!cand_cats && !h->tab.item_cats) return fail(h, FR_ERR_ARG, "cand_cats is NULL and no item_cats table");
+  if ((int64_t)h->cfg.num_items * h->mc.DV >= (1ll << 32))     // (row offsets travel between lanes as 32-bit words)
+    return fail(h, FR_ERR_UNSUPPORTED, "fr_eval_sampled_topk: Recipe_Embedding of %d x %d exceeds 2^32 16-byte groups", h->cfg.num_items, h->mc.D);
   { int rc = shadow_sync(h, (cudaStream_t)s); if (rc) return rc; }
   Launch l{h->sm_count, (cudaStream_t)s};
   cudaAccessPolicyWindow win{};

@@ -90,7 +90,8 @@ void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, c
 // candidates; SLOTS = 2 covers the reference's 51); the user's five rows live in registers (lane l: 16-byte group l).
 // The category term a/n * sum_c m_c <P[u,0], Cat[c]> needs the four dot products <P[u,0], Cat[c]> once per user; the
 // recipe term sum_d (sum_c m_c P[u,1+c]_d) R[i]_d is computed row-per-warp with a transposed reduction (see below).
-template <int NV, int SLOTS, bool BF>
+// EXACT: DV == 32 * NV (D = 128, 256): every lane owns a 16-byte group of every row, no bounds predicates.
+template <int NV, int SLOTS, bool BF, bool EXACT>
 __global__ void __launch_bounds__(FR_THREADS)
 eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, const float4* __restrict__ Cat,
                     int DV, float a, float oma, const int32_t* __restrict__ users,
@@ -103,31 +104,59 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
   for (int i = threadIdx.x; i < 4 * DV; i += blockDim.x) sCat[i] = Cat[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  // per warp: the candidates' category weights and row offsets, written by the lane that owns the candidate and read
+  // back by the whole warp (one broadcast LDS.128 per candidate / per four offsets instead of five shuffles)
+  float4* sM = smem + 4 * DV + (threadIdx.x >> 5) * (40 * SLOTS);           // [32*SLOTS] float4
+  uint32_t* sO = reinterpret_cast<uint32_t*>(sM + 32 * SLOTS);              // [32*SLOTS] uint32
   const int gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5), nw = gridDim.x * FR_WARPS_PER_BLOCK;
+  const typename TabVec<BF>::type* Rl = tab_at<BF>(R, 0) + lane;            // this lane's column of Recipe_Embedding
+  asm volatile("" : "+l"(Rl));          // (kept as one pointer: a row address is then ONE wide multiply-add, offset * 16 + Rl)
+  // The user loop is software-pipelined by one user: ids of user w+1 are loaded while user w is scored, and just before
+  // user w's ranking phase (no loads in flight there) user w+1's rows are requested into L2, so that its row loads
+  // find them there (half of the recipe-row reads miss L2 otherwise: the 102 MB table does not stay resident).
+  constexpr int VB = (int)sizeof(typename TabVec<BF>::type);
+  int un = 0, ncn = 0, idn[SLOTS];
+  auto fetch_ids = [&](int w2) {
+    if (w2 < n_users) {
+      un = users[w2]; ncn = n_cand[w2];
+#pragma unroll
+      for (int q = 0; q < SLOTS; ++q) {
+        const int j = q * 32 + lane;
+        idn[q] = j < stride ? cand[(size_t)w2 * stride + j] : -1;
+      }
+    }
+  };
+  fetch_ids(gw);
   for (int w = gw; w < n_users; w += nw) {
-    const int u = users[w];
-    int nc = n_cand[w];
+    const int u = un;
+    int nc = ncn;
     if (nc > stride) nc = stride;
     if (nc > 32 * SLOTS) nc = 32 * SLOTS;
+    int id[SLOTS]; float sc[SLOTS]; bool alive[SLOTS]; float4 mq[SLOTS];
+    uint32_t roff[SLOTS];      // the candidate's row offset in 16-byte groups (a lane without a candidate -- past
+                               // n_cand, or an id outside the table -- points at row 0: its score is never kept)
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      const int j = q * 32 + lane;
+      id[q] = j < nc ? idn[q] : -1;
+      if ((uint32_t)id[q] >= n_items) id[q] = -1;      // a candidate outside Recipe_Embedding is dropped (never ranked)
+      sc[q] = 0.f; alive[q] = id[q] >= 0;
+      roff[q] = id[q] >= 0 ? (uint32_t)id[q] * (uint32_t)DV : 0u;
+    }
+    fetch_ids(w + nw);
     if ((uint32_t)u >= n_table_users) {          // a user id outside Personal_Memory: empty rank list, no row is read
       for (int k = lane; k < K; k += 32) topk_ids[(size_t)w * K + k] = -1;
       if (lane == 0) gt_rank[w] = -1;
       continue;
-    }
-    int id[SLOTS]; float sc[SLOTS]; bool alive[SLOTS]; float4 mq[SLOTS];
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-      const int j = q * 32 + lane;
-      id[q] = j < nc ? cand[(size_t)w * stride + j] : -1;
-      if ((uint32_t)id[q] >= n_items) id[q] = -1;      // a candidate outside Recipe_Embedding is dropped (never ranked)
-      sc[q] = 0.f; alive[q] = id[q] >= 0;
     }
 #pragma unroll
     for (int q = 0; q < SLOTS; ++q) {
       const int j = q * 32 + lane;
       mq[q] = make_float4(1.f, 0.f, 0.f, 0.f);
       if (id[q] >= 0) mq[q] = cand_cats ? __ldg(cand_cats + (size_t)w * stride + j) : __ldg(item_cats + id[q]);
+      sM[j] = mq[q]; sO[j] = roff[q];
     }
+    __syncwarp();
     float b0, b1, b2, b3;
     float4 pr[5][NV];
 #pragma unroll
@@ -169,17 +198,22 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
           for (int t = 0; t < CB; ++t) v[b + t] = 0.f;
           continue;
         }
-        int idj[CB]; float4 rr[CB][NV];
+        float4 rr[CB][NV];
+        uint32_t offs[CB];
 #pragma unroll
-        for (int t = 0; t < CB; ++t) idj[t] = __shfl_sync(FR_FULL, id[q], b + t);
-#pragma unroll
-        // (a lane without a candidate -- past n_cand, or an id outside the table -- reads row 0: its score is never kept)
-        for (int t = 0; t < CB; ++t) load_row_ro_t<NV>(rr[t], tab_at<BF>(R, (size_t)(idj[t] >= 0 ? idj[t] : 0) * DV), DV, lane);
+        for (int t = 0; t < CB; t += 4) {
+          const uint4 o4 = *reinterpret_cast<const uint4*>(sO + q * 32 + b + t);
+          offs[t] = o4.x; offs[t + 1] = o4.y; offs[t + 2] = o4.z; offs[t + 3] = o4.w;
+        }
 #pragma unroll
         for (int t = 0; t < CB; ++t) {
-          float4 m;                               // the candidate's category weights, from the lane that holds them
-          m.x = __shfl_sync(FR_FULL, mq[q].x, b + t); m.y = __shfl_sync(FR_FULL, mq[q].y, b + t);
-          m.z = __shfl_sync(FR_FULL, mq[q].z, b + t); m.w = __shfl_sync(FR_FULL, mq[q].w, b + t);
+          const typename TabVec<BF>::type* rp = Rl + offs[t];
+#pragma unroll
+          for (int k = 0; k < NV; ++k) rr[t][k] = (EXACT || lane + 32 * k < DV) ? tab_ld_ro(rp + 32 * k) : f4zero();
+        }
+#pragma unroll
+        for (int t = 0; t < CB; ++t) {
+          const float4 m = sM[q * 32 + b + t];    // the candidate's category weights (broadcast read)
           float part = 0.f;
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
@@ -211,19 +245,31 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       const float sq = a * high + oma * (v[0] * rn);                              // :82-96
       if (id[q] >= 0) { sc[q] = sq; if (scores_out) scores_out[(size_t)w * stride + q * 32 + lane] = sq; }
     }
+    if (w + nw < n_users) {      // next user's rows -> L2 (hints only; ids outside a table are skipped)
+      if ((uint32_t)un < n_table_users) {
+        const char* pb = reinterpret_cast<const char*>(tab_at<BF>(P, (size_t)un * 5 * DV));
+        for (int o = lane * 128; o < 5 * DV * VB; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(pb + o));
+      }
+      int ncl = ncn < stride ? ncn : stride;
+#pragma unroll
+      for (int q = 0; q < SLOTS; ++q)
+        if (q * 32 + lane < ncl && (uint32_t)idn[q] < n_items) {
+          const char* rb = reinterpret_cast<const char*>(tab_at<BF>(R, (size_t)idn[q] * DV));
+          for (int o = 0; o < DV * VB; o += 128) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(rb + o));
+        }
+    }
     // dict semantics (evaluate.py:60-61): the first position of an id survives and takes the score of its last
     // occurrence.  Repeated ids are rare (0.65 % of users at 51 of 200k), so they are DETECTED first -- match.any
-    // inside a slot, one rotation of slot 0 against slot 1 -- and the O(n) fix-up below only runs for those users.
+    // inside a slot, slot 1's candidates broadcast against slot 0 -- and the O(n) fix-up below only runs for those users.
     bool dup = true;
     if constexpr (SLOTS == 2) {
       const uint32_t m0 = __match_any_sync(FR_FULL, id[0]), m1 = __match_any_sync(FR_FULL, id[1]);
       dup = (id[0] >= 0 && m0 != (1u << lane)) || (id[1] >= 0 && m1 != (1u << lane));
-      if (nc > 32) {
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const int o = __shfl_sync(FR_FULL, id[0], (lane + r) & 31);
-          dup |= (id[1] >= 0) & (o == id[1]);
-        }
+      // every candidate of slot 1 (nc - 32 of them: 19 for the reference's 51) against this lane's slot-0 candidate
+#pragma unroll 4
+      for (int t = 0; t < nc - 32; ++t) {
+        const int o = __shfl_sync(FR_FULL, id[1], t);
+        dup |= (o >= 0) & (o == id[0]);
       }
       dup = __any_sync(FR_FULL, dup);
     }
@@ -247,7 +293,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
     }
     // heapq.nlargest (evaluate.py:63): score desc, ties -> insertion order.  Scores become order-preserving
     // unsigned keys (-0 folded onto +0 so that float equality is key equality); per pick: the lane's own best, one
-    // REDUX max over the keys, one REDUX min over the positions of the lanes that hold it.
+    // REDUX max over the keys, one vote per slot for the lanes that hold it; the winning lane writes the id itself.
     uint32_t key[SLOTS];
 #pragma unroll
     for (int q = 0; q < SLOTS; ++q) {
@@ -257,23 +303,31 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
     const int gt = __shfl_sync(FR_FULL, id[0], 0);
     int rank_gt = -1;
     for (int k = 0; k < K; ++k) {
-      uint32_t bk = 0u; int bpos = 0x7fffffff;
+      uint32_t bk = 0u; bool any = false;
 #pragma unroll
       for (int q = 0; q < SLOTS; ++q)
-        if (alive[q] && (bpos == 0x7fffffff || key[q] > bk)) { bk = key[q]; bpos = q * 32 + lane; }
-      if (!__any_sync(FR_FULL, bpos != 0x7fffffff)) { if (lane == 0) topk_ids[(size_t)w * K + k] = -1; continue; }
-      const uint32_t top = __reduce_max_sync(FR_FULL, bpos != 0x7fffffff ? bk : 0u);
-      // (an alive key is >= 0x00800000 unless the score is NaN; lanes without a candidate offer position "none")
-      const int wpos = (int)__reduce_min_sync(FR_FULL, (bpos != 0x7fffffff && bk == top) ? (uint32_t)bpos : 0x7fffffffu);
-      int bid = 0;
+        if (alive[q] && (!any || key[q] > bk)) { bk = key[q]; any = true; }
+      const uint32_t top = __reduce_max_sync(FR_FULL, any ? bk : 0u);
+      // the winner is the LOWEST position that holds `top`: slots in order, lanes in order (two votes, no second reduce)
+      int wq = -1; uint32_t wb = 0u;
 #pragma unroll
-      for (int q = 0; q < SLOTS; ++q) if ((wpos >> 5) == q) bid = __shfl_sync(FR_FULL, id[q], wpos & 31);
+      for (int q = 0; q < SLOTS; ++q) {
+        const uint32_t bal = __ballot_sync(FR_FULL, alive[q] && key[q] == top);
+        if (wq < 0 && bal) { wq = q; wb = bal; }
+      }
+      if (wq < 0) { if (lane == 0) topk_ids[(size_t)w * K + k] = -1; continue; }      // no candidate left
+      const int wl = __ffs(wb) - 1;
 #pragma unroll
-      for (int q = 0; q < SLOTS; ++q) if (q * 32 + lane == wpos) alive[q] = false;
-      if (bid == gt && rank_gt < 0) rank_gt = k;
-      if (lane == 0) topk_ids[(size_t)w * K + k] = bid;
+      for (int q = 0; q < SLOTS; ++q)
+        if (q == wq && lane == wl) {
+          alive[q] = false;
+          topk_ids[(size_t)w * K + k] = id[q];
+          if (id[q] == gt && rank_gt < 0) rank_gt = k;
+        }
     }
+    rank_gt = (int)__reduce_max_sync(FR_FULL, (uint32_t)(rank_gt + 1)) - 1;      // (held by the lane that won that pick)
     if (lane == 0) gt_rank[w] = rank_gt;
+    __syncwarp();                                 // sM / sO are rewritten for the next user
   }
 }
 
@@ -285,7 +339,8 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   if (n_users <= 0) return;
   int grid = (n_users + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
   if (grid > l.sm_count * 8) grid = l.sm_count * 8;
-  const size_t smem = (size_t)4 * mc.DV * sizeof(float4);
+  const bool two = stride <= 64;
+  const size_t smem = ((size_t)4 * mc.DV + (size_t)FR_WARPS_PER_BLOCK * 40 * (two ? 2 : 4)) * sizeof(float4);
   ++g_launches;
   // launched with cudaLaunchKernelEx so that a persisting-L2 access-policy window (Recipe_Embedding: every user re-reads
   // 51 random rows of it while 2.5 KB of read-once user rows per user stream past) can ride on the LAUNCH: a stream
@@ -300,12 +355,13 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   }
   const int DVv = mc.DV; const float av = mc.a, omav = mc.oma;
   const uint32_t ntu = (uint32_t)n_table_users, nit = (uint32_t)n_items;
-#define FR_EVAL_(NVV, SL, BFF) cudaLaunchKernelEx(&cfg, eval_sampled_kernel<NVV, SL, BFF>, P, R, Cat, DVv, av, omav, users, cand, \
-    n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb, ntu, nit)
+#define FR_EVAL__(NVV, SL, BFF, EX) cudaLaunchKernelEx(&cfg, eval_sampled_kernel<NVV, SL, BFF, EX>, P, R, Cat, DVv, av, omav, users, \
+    cand, n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb, ntu, nit)
+#define FR_EVAL_(NVV, SL, BFF) do { if (mc.DV == 32 * NVV) FR_EVAL__(NVV, SL, BFF, true); else FR_EVAL__(NVV, SL, BFF, false); } while (0)
 #define FR_EVAL(NVV, SL) do { if (bf16) FR_EVAL_(NVV, SL, true); else FR_EVAL_(NVV, SL, false); } while (0)
-  const bool two = stride <= 64;
   if (mc.DV <= 32) { if (two) FR_EVAL(1, 2); else FR_EVAL(1, 4); }
   else             { if (two) FR_EVAL(2, 2); else FR_EVAL(2, 4); }
+#undef FR_EVAL__
 #undef FR_EVAL_
 #undef FR_EVAL
 }
