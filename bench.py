@@ -442,6 +442,9 @@ def cfg5_leg(args, cfg, B, dev, steps, n_neg=8):
         eu = torch.as_tensor(rng.permutation(U)[:NU].astype(np.int32)).to(dev)
         cand = torch.as_tensor(rng.integers(0, I, (NU, 51)).astype(np.int32)).to(dev)
         nc = torch.full((NU,), 51, dtype=torch.int32, device=dev)
+        eng.eval_sampled_topk(eu, cand, nc, 10); torch.cuda.synchronize()
+        e0.record(); eng.eval_sampled_topk(eu, cand, nc, 10); e1.record(); torch.cuda.synchronize()
+        ems_plain = e0.elapsed_time(e1)
         eng.set_health_blend(True)
         eng.eval_sampled_topk(eu, cand, nc, 10); torch.cuda.synchronize()
         e0.record(); eng.eval_sampled_topk(eu, cand, nc, 10); e1.record(); torch.cuda.synchronize()
@@ -462,7 +465,13 @@ def cfg5_leg(args, cfg, B, dev, steps, n_neg=8):
             "topk_health": {"metric": "sampled_topk_users_per_sec", "value": NU / (ems * 1e-3), "unit": "users/s", "ms": ems,
                             "users": NU, "candidates": 51, "K": 10,
                             "roofline": {"bound": "hbm", "achieved": ealg / (ems * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                         "frac": ealg / (ems * 1e-3) / 1e9 / peak}},
+                                         "frac": ealg / (ems * 1e-3) / 1e9 / peak},
+                            "note": "the health term adds the user's General_Memory rows (<= 3 labels x 5 x D floats, L2-resident) "
+                                    "to every user's reads; they are not in the algorithmic byte count"},
+            "topk": {"metric": "sampled_topk_users_per_sec", "value": NU / (ems_plain * 1e-3), "unit": "users/s", "ms": ems_plain,
+                     "users": NU, "candidates": 51, "K": 10, "health_term": False,
+                     "roofline": {"bound": "hbm", "achieved": ealg / (ems_plain * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": ealg / (ems_plain * 1e-3) / 1e9 / peak}},
             "uniq_users_per_step": uu, "uniq_items_per_step": ui,
         }
         eng.close(); del eng
@@ -475,6 +484,7 @@ def cfg5_leg(args, cfg, B, dev, steps, n_neg=8):
     f = out["float32"]
     res["same_leg_fp32_tables"] = {"value": f["value"], "ms_per_step": f["ms_per_step"], "phases_ms": f["phases_ms"],
                                    "roofline_step_frac": f["roofline_step"]["frac"], "topk_health_ms": f["topk_health"]["ms"],
+                                   "topk_ms": f["topk"]["ms"],
                                    "e2e": f["e2e"]["value"]}
     res["speedup_vs_fp32_tables"] = res["value"] / f["value"]
     return res
@@ -1064,6 +1074,7 @@ def run_ours(args, cfg, B):
             t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         return world * B * args.steps / dt, loss_sum / args.steps
     # the overlapped leg is run three times; the MEDIAN is reported, all three and their spread are in the line
+    e2e_run(True)                                  # (untimed: first touch of the staging buffers / copy stream)
     e2e_runs = [e2e_run(True) for _ in range(3)]
     e2e_val, e2e_loss = sorted(e2e_runs)[1]
     e2e_serial, _ = e2e_run(True, prefetch=False)
@@ -1167,7 +1178,7 @@ def run_ours(args, cfg, B):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * L.FR_OUT_COUNT,
                     "feed": "reference dense feed (user_input,item_input,categories,user_one_hot_label), pinned, "
                             "host read of the loss every step; the copy of feed k+1 (fr_feed_prefetch, library copy "
-                            "stream) overlaps the kernels of step k; median of 3 runs of K steps", "mean_loss": e2e_loss,
+                            "stream) overlaps the kernels of step k; median of 3 runs of K steps after one untimed run", "mean_loss": e2e_loss,
                     "runs": [v for v, _ in e2e_runs],
                     "spread": (max(v for v, _ in e2e_runs) - min(v for v, _ in e2e_runs)) / e2e_val,
                     "without_prefetch": e2e_serial},

@@ -90,9 +90,36 @@ void launch_fwd_score(const ModelConsts& mc, const float4* P, const float4* R, c
 // candidates; SLOTS = 2 covers the reference's 51); the user's five rows live in registers (lane l: 16-byte group l).
 // The category term a/n * sum_c m_c <P[u,0], Cat[c]> needs the four dot products <P[u,0], Cat[c]> once per user; the
 // recipe term sum_d (sum_c m_c P[u,1+c]_d) R[i]_d is computed row-per-warp with a transposed reduction (see below).
+// cp.async (LDGSTS) helpers of the sampled-evaluation kernel: each lane copies ITS 16 (8: bf16) bytes of a recipe row into
+// its own column of a per-warp ring in shared memory and later reads the same bytes back, so no cross-lane ordering is
+// needed -- the ring is simply storage for loads in flight that does not cost registers.
+__device__ __forceinline__ void cp_async_vec(float4* dst, const float4* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_vec(uint2* dst, const uint2* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ float4 ring_ld(const float4* p) { return *p; }
+__device__ __forceinline__ float4 ring_ld(const uint2* p) { return bf4_to_f4(*p); }
+
+constexpr int EV_WARPS = 4;                 // warps per CTA of eval_sampled_kernel
+constexpr int EV_THREADS = EV_WARPS * 32;
+constexpr int EV_CB = 8;                    // candidate rows per copy group
+#ifndef FR_EV_GROUPS
+#define FR_EV_GROUPS 2
+#endif
+#ifndef FR_EV_MINB
+#define FR_EV_MINB 4
+#endif
+template <int NV> struct EvRing { static constexpr int GROUPS = FR_EV_GROUPS; };    // copy groups in flight per warp
+
 // EXACT: DV == 32 * NV (D = 128, 256): every lane owns a 16-byte group of every row, no bounds predicates.
 template <int NV, int SLOTS, bool BF, bool EXACT>
-__global__ void __launch_bounds__(FR_THREADS)
+__global__ void __launch_bounds__(EV_THREADS, NV == 1 ? FR_EV_MINB : (FR_EV_MINB > 3 ? 3 : FR_EV_MINB))
 eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, const float4* __restrict__ Cat,
                     int DV, float a, float oma, const int32_t* __restrict__ users,
                     const int32_t* __restrict__ cand, const int32_t* __restrict__ n_cand, int n_users,
@@ -108,7 +135,11 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
   // back by the whole warp (one broadcast LDS.128 per candidate / per four offsets instead of five shuffles)
   float4* sM = smem + 4 * DV + (threadIdx.x >> 5) * (40 * SLOTS);           // [32*SLOTS] float4
   uint32_t* sO = reinterpret_cast<uint32_t*>(sM + 32 * SLOTS);              // [32*SLOTS] uint32
-  const int gw = blockIdx.x * FR_WARPS_PER_BLOCK + (threadIdx.x >> 5), nw = gridDim.x * FR_WARPS_PER_BLOCK;
+  // per warp: ring of GROUPS x EV_CB row slots, [slot][k][lane] vectors -- this lane's column only is ever touched by it
+  using V = typename TabVec<BF>::type;
+  constexpr int GROUPS = EvRing<NV>::GROUPS;
+  V* const ring = reinterpret_cast<V*>(smem + 4 * DV + EV_WARPS * (40 * SLOTS)) + ((threadIdx.x >> 5) * (GROUPS * EV_CB * NV) * 32 + lane);
+  const int gw = blockIdx.x * EV_WARPS + (threadIdx.x >> 5), nw = gridDim.x * EV_WARPS;
   const typename TabVec<BF>::type* Rl = tab_at<BF>(R, 0) + lane;            // this lane's column of Recipe_Embedding
   asm volatile("" : "+l"(Rl));          // (kept as one pointer: a row address is then ONE wide multiply-add, offset * 16 + Rl)
   // The user loop is software-pipelined by one user: ids of user w+1 are loaded while user w is scored, and just before
@@ -116,6 +147,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
   // find them there (half of the recipe-row reads miss L2 otherwise: the 102 MB table does not stay resident).
   constexpr int VB = (int)sizeof(typename TabVec<BF>::type);
   int un = 0, ncn = 0, idn[SLOTS];
+  float4 pr[5][NV], mqn[SLOTS];                 // the NEXT user's rows / category weights while they are in flight
   auto fetch_ids = [&](int w2) {
     if (w2 < n_users) {
       un = users[w2]; ncn = n_cand[w2];
@@ -126,7 +158,28 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       }
     }
   };
+  // user w2's own rows (read once: streamed, evict-first, so that the recipe table, which every user re-reads, keeps
+  // its place in L2) and category weights into registers, its recipe rows into L2 (hints; ids outside a table skipped)
+  auto fetch_rows = [&](int w2) {
+    if (w2 >= n_users) return;
+    if ((uint32_t)un < n_table_users) {
+#pragma unroll
+      for (int s = 0; s < 5; ++s) load_row_cs_t<NV>(pr[s], tab_at<BF>(P, ((size_t)un * 5 + s) * DV), DV, lane);
+    }
+    const int ncl = ncn < stride ? ncn : stride;
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      const int j = q * 32 + lane;
+      mqn[q] = make_float4(1.f, 0.f, 0.f, 0.f);
+      if (j < ncl && (uint32_t)idn[q] < n_items) {
+        mqn[q] = cand_cats ? __ldg(cand_cats + (size_t)w2 * stride + j) : __ldg(item_cats + idn[q]);
+        const char* rb = reinterpret_cast<const char*>(tab_at<BF>(R, (size_t)idn[q] * DV));
+        for (int o = 0; o < DV * VB; o += 128) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(rb + o));
+      }
+    }
+  };
   fetch_ids(gw);
+  fetch_rows(gw);
   for (int w = gw; w < n_users; w += nw) {
     const int u = un;
     int nc = ncn;
@@ -142,26 +195,19 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       if ((uint32_t)id[q] >= n_items) id[q] = -1;      // a candidate outside Recipe_Embedding is dropped (never ranked)
       sc[q] = 0.f; alive[q] = id[q] >= 0;
       roff[q] = id[q] >= 0 ? (uint32_t)id[q] * (uint32_t)DV : 0u;
+      mq[q] = id[q] >= 0 ? mqn[q] : make_float4(1.f, 0.f, 0.f, 0.f);
+      sM[j] = mq[q]; sO[j] = roff[q];
     }
-    fetch_ids(w + nw);
+    fetch_ids(w + nw);                           // (un, ncn, idn now describe the next user)
     if ((uint32_t)u >= n_table_users) {          // a user id outside Personal_Memory: empty rank list, no row is read
       for (int k = lane; k < K; k += 32) topk_ids[(size_t)w * K + k] = -1;
       if (lane == 0) gt_rank[w] = -1;
+      __syncwarp();
+      fetch_rows(w + nw);
       continue;
-    }
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-      const int j = q * 32 + lane;
-      mq[q] = make_float4(1.f, 0.f, 0.f, 0.f);
-      if (id[q] >= 0) mq[q] = cand_cats ? __ldg(cand_cats + (size_t)w * stride + j) : __ldg(item_cats + id[q]);
-      sM[j] = mq[q]; sO[j] = roff[q];
     }
     __syncwarp();
     float b0, b1, b2, b3;
-    float4 pr[5][NV];
-#pragma unroll
-    // read-once rows: streamed (evict-first) so that the recipe table, which every user re-reads, stays in L2
-    for (int s = 0; s < 5; ++s) load_row_cs_t<NV>(pr[s], tab_at<BF>(P, ((size_t)u * 5 + s) * DV), DV, lane);
     health_blend_rows<NV>(pr, hb, u, DV, lane);
     {
       float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
@@ -185,47 +231,68 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
     //  7.5 ms: every load instruction touched 32 different lines for 16 bytes each, 2048 L1 wavefronts per user, and
     //  the SM's one-wavefront-per-cycle L1 port was the limit (2048 x 1M / 148 SMs / 1.9 GHz = 7.3 ms).  An eight-lanes-
     //  per-candidate variant with a reduction per four candidates measured 9.4 ms.)
-    constexpr int CB = 8;                         // candidate rows in flight per warp
+    // Rows travel global -> shared memory by cp.async in groups of EV_CB, GROUPS groups in flight per warp (loads in
+    // flight cost no registers); group g+GROUPS is issued as soon as group g has been consumed.  Live groups are the
+    // first ceil(nc / EV_CB) in (slot, batch) order.
+    // Measured (1M users x 51 candidates, D = 128, fp32): 4.8 ms with 12, 16 or 20 warps per SM and with 1, 2, 3 or 4
+    // groups in flight -- occupancy and latency no longer matter: 31 GB of rows cross L2 -> SM in that time, 6.5 TB/s,
+    // which is the L2 slice throughput limit (B300_MICROARCH.md: ~6300 B per L2 clock chip-wide).  The row bytes are
+    // the floor at this storage width; bf16 tables halve them.
+    constexpr int CB = EV_CB, NG = SLOTS * (32 / CB);
+    auto issue = [&](int g) {                     // g: compile-time after unrolling
+      const int q = g / (32 / CB), b = (g % (32 / CB)) * CB;
+      if (g < NG && b < nc - q * 32) {
+        V* dst = ring + (size_t)((g % GROUPS) * CB * NV) * 32;
+#pragma unroll
+        for (int t = 0; t < CB; t += 4) {
+          const uint4 o4 = *reinterpret_cast<const uint4*>(sO + q * 32 + b + t);
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            const V* rp = Rl + (tt == 0 ? o4.x : tt == 1 ? o4.y : tt == 2 ? o4.z : o4.w);
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+              if (EXACT || lane + 32 * k < DV) cp_async_vec(dst + ((t + tt) * NV + k) * 32, rp + 32 * k);
+          }
+        }
+      }
+      cp_async_commit();                          // (an empty group when there is nothing left: the count stays in step)
+    };
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) issue(g);
 #pragma unroll
     for (int q = 0; q < SLOTS; ++q) {
       const int ncg = nc - q * 32;                // candidates of this slot (warp-uniform)
-      if (ncg <= 0) break;
+      if (ncg <= 0) {                             // (keep the copy-group count in step: nothing is in flight any more)
+        continue;
+      }
       float v[32];
 #pragma unroll
       for (int b = 0; b < 32; b += CB) {
+        const int g = q * (32 / CB) + b / CB;
         if (b >= ncg) {
 #pragma unroll
           for (int t = 0; t < CB; ++t) v[b + t] = 0.f;
           continue;
         }
-        float4 rr[CB][NV];
-        uint32_t offs[CB];
-#pragma unroll
-        for (int t = 0; t < CB; t += 4) {
-          const uint4 o4 = *reinterpret_cast<const uint4*>(sO + q * 32 + b + t);
-          offs[t] = o4.x; offs[t + 1] = o4.y; offs[t + 2] = o4.z; offs[t + 3] = o4.w;
-        }
-#pragma unroll
-        for (int t = 0; t < CB; ++t) {
-          const typename TabVec<BF>::type* rp = Rl + offs[t];
-#pragma unroll
-          for (int k = 0; k < NV; ++k) rr[t][k] = (EXACT || lane + 32 * k < DV) ? tab_ld_ro(rp + 32 * k) : f4zero();
-        }
+        cp_async_wait<GROUPS - 1>();              // group g has landed (at most the GROUPS-1 younger ones are pending)
+        const V* src = ring + (size_t)((g % GROUPS) * CB * NV) * 32;
 #pragma unroll
         for (int t = 0; t < CB; ++t) {
           const float4 m = sM[q * 32 + b + t];    // the candidate's category weights (broadcast read)
           float part = 0.f;
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
+            const float4 r = (EXACT || lane + 32 * k < DV) ? ring_ld(src + (t * NV + k) * 32) : f4zero();
             float4 z;
             z.x = m.x * pr[1][k].x + m.y * pr[2][k].x + m.z * pr[3][k].x + m.w * pr[4][k].x;
             z.y = m.x * pr[1][k].y + m.y * pr[2][k].y + m.z * pr[3][k].y + m.w * pr[4][k].y;
             z.z = m.x * pr[1][k].z + m.y * pr[2][k].z + m.z * pr[3][k].z + m.w * pr[4][k].z;
             z.w = m.x * pr[1][k].w + m.y * pr[2][k].w + m.z * pr[3][k].w + m.w * pr[4][k].w;
-            part += dot4(z, rr[t][k]);
+            part += dot4(z, r);
           }
           v[b + t] = part;
         }
+        issue(g + GROUPS);                        // reuse the slots just read
       }
       // transposing butterfly: after the step with offset o, v[i] (i < o) holds the sum over 32/o lanes for the
       // candidate whose index has this lane's bits >= o and low bits i; after offset 1, v[0] is candidate `lane`
@@ -245,19 +312,7 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
       const float sq = a * high + oma * (v[0] * rn);                              // :82-96
       if (id[q] >= 0) { sc[q] = sq; if (scores_out) scores_out[(size_t)w * stride + q * 32 + lane] = sq; }
     }
-    if (w + nw < n_users) {      // next user's rows -> L2 (hints only; ids outside a table are skipped)
-      if ((uint32_t)un < n_table_users) {
-        const char* pb = reinterpret_cast<const char*>(tab_at<BF>(P, (size_t)un * 5 * DV));
-        for (int o = lane * 128; o < 5 * DV * VB; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(pb + o));
-      }
-      int ncl = ncn < stride ? ncn : stride;
-#pragma unroll
-      for (int q = 0; q < SLOTS; ++q)
-        if (q * 32 + lane < ncl && (uint32_t)idn[q] < n_items) {
-          const char* rb = reinterpret_cast<const char*>(tab_at<BF>(R, (size_t)idn[q] * DV));
-          for (int o = 0; o < DV * VB; o += 128) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(rb + o));
-        }
-    }
+    fetch_rows(w + nw);                           // the rows are dead: the next user's take their place while this one is ranked
     // dict semantics (evaluate.py:60-61): the first position of an id survives and takes the score of its last
     // occurrence.  Repeated ids are rare (0.65 % of users at 51 of 200k), so they are DETECTED first -- match.any
     // inside a slot, slot 1's candidates broadcast against slot 0 -- and the O(n) fix-up below only runs for those users.
@@ -337,16 +392,17 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
                          int32_t* topk_ids, int32_t* gt_rank, float* scores, const HealthBlend& hb, const Launch& l,
                          int64_t n_table_users, int64_t n_items, int bf16) {
   if (n_users <= 0) return;
-  int grid = (n_users + FR_WARPS_PER_BLOCK - 1) / FR_WARPS_PER_BLOCK;
-  if (grid > l.sm_count * 8) grid = l.sm_count * 8;
   const bool two = stride <= 64;
-  const size_t smem = ((size_t)4 * mc.DV + (size_t)FR_WARPS_PER_BLOCK * 40 * (two ? 2 : 4)) * sizeof(float4);
+  const int NVr = mc.DV <= 32 ? 1 : 2, SL = two ? 2 : 4, VBy = bf16 ? 8 : 16;
+  const int groups = NVr == 1 ? EvRing<1>::GROUPS : EvRing<2>::GROUPS;
+  const size_t smem = ((size_t)4 * mc.DV + (size_t)EV_WARPS * 40 * SL) * sizeof(float4) +
+                      (size_t)EV_WARPS * groups * EV_CB * NVr * 32 * VBy;
   ++g_launches;
   // launched with cudaLaunchKernelEx so that a persisting-L2 access-policy window (Recipe_Embedding: every user re-reads
   // 51 random rows of it while 2.5 KB of read-once user rows per user stream past) can ride on the LAUNCH: a stream
   // attribute does not take on the legacy default stream the Python layer hands over
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FR_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = l.st;
+  cfg.blockDim = dim3(EV_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = l.st;
   cudaLaunchAttribute attr[1];
   if (l.win) {
     attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -355,10 +411,19 @@ void launch_eval_sampled(const ModelConsts& mc, const float4* P, const float4* R
   }
   const int DVv = mc.DV; const float av = mc.a, omav = mc.oma;
   const uint32_t ntu = (uint32_t)n_table_users, nit = (uint32_t)n_items;
-#define FR_EVAL__(NVV, SL, BFF, EX) cudaLaunchKernelEx(&cfg, eval_sampled_kernel<NVV, SL, BFF, EX>, P, R, Cat, DVv, av, omav, users, \
-    cand, n_cand, n_users, stride, cand_cats, item_cats, K, topk_ids, gt_rank, scores, hb, ntu, nit)
-#define FR_EVAL_(NVV, SL, BFF) do { if (mc.DV == 32 * NVV) FR_EVAL__(NVV, SL, BFF, true); else FR_EVAL__(NVV, SL, BFF, false); } while (0)
-#define FR_EVAL(NVV, SL) do { if (bf16) FR_EVAL_(NVV, SL, true); else FR_EVAL_(NVV, SL, false); } while (0)
+  // persistent grid: exactly the CTAs that are resident (the user loop is software-pipelined, see the kernel)
+#define FR_EVAL__(NVV, SLL, BFF, EX) do {                                                                              \
+    auto kern = eval_sampled_kernel<NVV, SLL, BFF, EX>;                                                                \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                \
+    int per_sm = 1;                                                                                                    \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EV_THREADS, smem);                                    \
+    int grid = (n_users + EV_WARPS - 1) / EV_WARPS;                                                                    \
+    if (grid > l.sm_count * (per_sm > 0 ? per_sm : 1)) grid = l.sm_count * (per_sm > 0 ? per_sm : 1);                  \
+    cfg.gridDim = dim3(grid);                                                                                          \
+    cudaLaunchKernelEx(&cfg, kern, P, R, Cat, DVv, av, omav, users, cand, n_cand, n_users, stride, cand_cats,          \
+                       item_cats, K, topk_ids, gt_rank, scores, hb, ntu, nit); } while (0)
+#define FR_EVAL_(NVV, SLL, BFF) do { if (mc.DV == 32 * NVV) FR_EVAL__(NVV, SLL, BFF, true); else FR_EVAL__(NVV, SLL, BFF, false); } while (0)
+#define FR_EVAL(NVV, SLL) do { if (bf16) FR_EVAL_(NVV, SLL, true); else FR_EVAL_(NVV, SLL, false); } while (0)
   if (mc.DV <= 32) { if (two) FR_EVAL(1, 2); else FR_EVAL(1, 4); }
   else             { if (two) FR_EVAL(2, 2); else FR_EVAL(2, 4); }
 #undef FR_EVAL__
