@@ -53,11 +53,15 @@ static int plan_slot_ensure(fr_ctx* h, int idx, size_t S) {
 static int owner_ensure(fr_ctx* h, size_t n) {            // owner-side buffers for W*cap request slots
   auto& w = h->sh;
   int rc;
-  if (!w.n_valid && (rc = dalloc(h, &w.n_valid, 1))) return rc;
+  for (auto& sv : w.ss)
+    if (!sv.n_valid && (rc = dalloc(h, &sv.n_valid, 1))) return rc;
   if (!w.route_counts && (rc = dalloc(h, &w.route_counts, 8))) return rc;
   if (n > w.n_cap) {
-    if ((rc = ws_alloc(h, &w.serve_keys, n))) return rc;
-    if ((rc = alloc_sort(h, w.sortS, n))) return rc;       // (old buffers stay in allocs until fr_destroy)
+    for (auto& sv : w.ss) {
+      if ((rc = ws_alloc(h, &sv.serve_keys, n))) return rc;
+      if ((rc = alloc_sort(h, sv.sortS, n))) return rc;    // (old buffers stay in allocs until fr_destroy)
+      sv.prepared = false;
+    }
     if ((rc = ws_alloc(h, &w.pieces_s, (n / 32 + 2) * 2 * (size_t)h->mc.DV))) return rc;
     w.n_cap = n;
   }
@@ -215,6 +219,27 @@ extern "C" int fr_shard_set_peers(fr_handle h, const fr_shard* sh, float* const*
 }
 
 // ---------------------------------------------------------------- 2. serve
+// received requests -> (recipe, slot) keys, stable sort by recipe: the order the catch-up and fr_shard_apply walk.
+// Depends on the request list only, not on the tables.
+static void serve_sort(fr_ctx* h, const fr_shard* sh, const int32_t* rreq, fr_ctx::ShardWs::ServeSlot& sv, size_t n, const Launch& l) {
+  launch_serve_keys(rreq, (uint32_t)n, (uint32_t)sh->items_per_rank, sv.serve_keys, sv.n_valid, l);
+  sv.rs = radix_sort_pairs(sv.sortS, sv.serve_keys, (uint32_t)n, nullptr, bits_for((int64_t)sh->items_per_rank + 1), l.st, h->sm_count);
+  sv.prepared = true;
+}
+
+extern "C" int fr_shard_serve_prepare(fr_handle h, const fr_shard* sh, const int32_t* rreq, fr_stream s) {
+  int rc = shard_check(h, sh); if (rc) return rc;
+  if (!rreq) return fail(h, FR_ERR_ARG, "null rreq");
+  auto& w = h->sh;
+  if (w.n_plan <= w.n_apply) return fail(h, FR_ERR_STATE, "fr_shard_plan must precede fr_shard_serve_prepare");
+  const size_t n = (size_t)sh->world * sh->cap;
+  if ((rc = owner_ensure(h, n))) return rc;
+  Launch l{h->sm_count, (cudaStream_t)s, nullptr};
+  serve_sort(h, sh, rreq, w.ss[(w.n_plan - 1) & 1], n, l);     // the step planned last
+  FR_CHECK_LAUNCH(h);
+  return FR_OK;
+}
+
 extern "C" int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rreq, float* rows, fr_stream s) {
   int rc = shard_check(h, sh); if (rc) return rc;
   if (!rreq) return fail(h, FR_ERR_ARG, "null rreq");
@@ -228,11 +253,11 @@ extern "C" int fr_shard_serve(fr_handle h, const fr_shard* sh, const int32_t* rr
   const int64_t step = h->step + 1;
   if ((rc = ensure_lr_hist(h, step + 1, st))) return rc;
   const OptConsts oc = make_oc(h, step);
-  launch_serve_keys(rreq, (uint32_t)n, (uint32_t)sh->items_per_rank, w.serve_keys, w.n_valid, l);
-  w.rs = radix_sort_pairs(w.sortS, w.serve_keys, (uint32_t)n, nullptr, bits_for((int64_t)sh->items_per_rank + 1), st, h->sm_count);
+  auto& sv = w.ss[w.n_apply & 1];
+  if (!sv.prepared) serve_sort(h, sh, rreq, sv, n, l);      // (else fr_shard_serve_prepare did it, one step ahead)
   if (h->cfg.learner == FR_ADAM && h->cfg.adam_mode != FR_ADAM_DENSE)    // requested rows must be current
-    launch_item_catchup(h->NV, w.sortS.k[w.rs], (uint32_t)n, (float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R, T.last_R,
-                        h->mc.DV, oc, l, w.n_valid);
+    launch_item_catchup(h->NV, sv.sortS.k[sv.rs], (uint32_t)n, (float4*)T.R, (float4*)T.s1_R, (float4*)T.s2_R, T.last_R,
+                        h->mc.DV, oc, l, sv.n_valid);
   PeerPtrs none{}; none.world = 0;
   launch_gather_rows((const float4*)T.R, rreq, (uint32_t)n, h->mc.DV, (float4*)rows, rows ? none : w.peer_rbuf, l,
                      (uint32_t)h->cfg.num_items, h->table_bf16 ? 1 : 0);
@@ -465,7 +490,9 @@ extern "C" int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rr
 
   // received (recipe, gradient row) pairs, sorted by recipe at serve time (stable: rank order)
   SegCommon c{};
-  c.keys = w.sortS.k[w.rs]; c.perm = w.sortS.v[w.rs]; c.n_dev = w.n_valid; c.n_host = n;
+  auto& sv = w.ss[w.n_apply & 1];
+  if (!sv.prepared) return fail(h, FR_ERR_STATE, "fr_shard_serve must precede fr_shard_apply");
+  c.keys = sv.sortS.k[sv.rs]; c.perm = sv.sortS.v[sv.rs]; c.n_dev = sv.n_valid; c.n_host = n;
   c.pieces = w.pieces_s; c.uniq_counter = nullptr;
   ItemPolParams ip{};
   ip.R = (float4*)T.R; ip.s1 = (float4*)T.s1_R; ip.s2 = (float4*)T.s2_R; ip.last = T.last_R;
@@ -483,6 +510,7 @@ extern "C" int fr_shard_apply(fr_handle h, const fr_shard* sh, const int32_t* rr
   launch_write_counters(h->counters, out, l);
   FR_CHECK_LAUNCH(h);
   ps.S = 0; ps.planned = false;
+  sv.prepared = false;
   ++w.n_apply;
   h->step = step;
   h->b1p *= h->cfg.adam_beta1;

@@ -65,10 +65,17 @@ struct fr_ctx {
     PlanSlot ps[2];
     uint64_t n_plan = 0, n_apply = 0;      // plan k writes slot k & 1; forward / update / apply of step k read slot k & 1
     size_t n_cap = 0;                      // W*cap the owner-side buffers are sized for
-    uint32_t *serve_keys = nullptr, *n_valid = nullptr, *route_counts = nullptr;
-    SortBufs sortS;                        // owner side: received requests
+    uint32_t* route_counts = nullptr;
+    // owner side: the received requests of a step sorted by recipe (keys, stable sort, count of valid slots).  Two
+    // sets, like the plan slots: fr_shard_serve_prepare of step k+1 may run (side stream) while fr_shard_apply of
+    // step k still reads step k's order.
+    struct ServeSlot {
+      uint32_t *serve_keys = nullptr, *n_valid = nullptr;
+      SortBufs sortS;
+      int rs = 0;
+      bool prepared = false;
+    } ss[2];
     float4* pieces_s = nullptr;
-    int rs = 0;
     fr::PeerPtrs peer_rbuf{}, peer_rgrows{};   // fr_shard_set_peers: NVLink P2P exchange instead of all-to-alls
   } sh;
   // single-pass training (fr_set_shadow): second copy of Personal_Memory + Adam slots; shadow_dirty = some row's current

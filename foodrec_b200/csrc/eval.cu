@@ -224,28 +224,29 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
     // Scoring: ROW-PER-WARP loads, one reduction per 32 candidates.  Candidate j's recipe row is read by the whole warp
     // (lane l takes 16-byte group l: a 512-byte row is 4 full lines, 4 L1 wavefronts), each lane forms its part of
     // sum_d (sum_c m_c P[u,1+c]_d) R[i]_d against the user rows it holds in registers, and the 32 partials a lane has
-    // collected for 32 candidates are summed across the warp by ONE transposing butterfly (31 shuffles per 32
-    // candidates; lane j ends with candidate j's sum) instead of a 5-step reduction per candidate.
+    // collected for a group of candidates are summed across the warp by ONE transposing butterfly (lane j ends with
+    // candidate j's sum) instead of a 5-step reduction per candidate.
     // (History: the first form, row-per-warp with two shuffle reductions and two divisions per candidate, took 22 ms
     //  per 1M users; the second, lane-per-candidate -- lane j walks the row of ITS candidate, no reduction at all --
     //  7.5 ms: every load instruction touched 32 different lines for 16 bytes each, 2048 L1 wavefronts per user, and
     //  the SM's one-wavefront-per-cycle L1 port was the limit (2048 x 1M / 148 SMs / 1.9 GHz = 7.3 ms).  An eight-lanes-
     //  per-candidate variant with a reduction per four candidates measured 9.4 ms.)
-    // Rows travel global -> shared memory by cp.async in groups of EV_CB, GROUPS groups in flight per warp (loads in
-    // flight cost no registers); group g+GROUPS is issued as soon as group g has been consumed.  Live groups are the
-    // first ceil(nc / EV_CB) in (slot, batch) order.
-    // Measured (1M users x 51 candidates, D = 128, fp32): 4.8 ms with 12, 16 or 20 warps per SM and with 1, 2, 3 or 4
-    // groups in flight -- occupancy and latency no longer matter: 31 GB of rows cross L2 -> SM in that time, 6.5 TB/s,
-    // which is the L2 slice throughput limit (B300_MICROARCH.md: ~6300 B per L2 clock chip-wide).  The row bytes are
-    // the floor at this storage width; bf16 tables halve them.
-    constexpr int CB = EV_CB, NG = SLOTS * (32 / CB);
-    auto issue = [&](int g) {                     // g: compile-time after unrolling
-      const int q = g / (32 / CB), b = (g % (32 / CB)) * CB;
-      if (g < NG && b < nc - q * 32) {
+    // Rows travel global -> shared memory by cp.async in groups of EV_CB = 8, GROUPS groups in flight per warp (loads in
+    // flight cost no registers); group g+GROUPS is issued as soon as group g has been consumed.  Group g holds candidates
+    // 8g .. 8g+7; the live groups are the first ceil(nc / 8).
+    // The loop over groups is a RUNTIME loop with an 8-wide butterfly per group (7 exchanges + 2 to add the four 8-lane
+    // groups), not an unrolled pass with one 32-wide butterfly per slot: fully unrolled, the kernel's hot path was ~46 KB
+    // of straight-line code, more than the SM's instruction cache, and ncu showed where the time went --
+    // gcc__cache_requests_type_instruction at 94 % of peak, sm__icc hit rate 86 %, the same 4.8 ms at 12, 16 or 20 warps
+    // per SM, with 1-4 groups in flight, with fp32 or bf16 rows: the SMs were waiting for INSTRUCTIONS.
+    constexpr int CB = EV_CB;
+    const int ng = (nc + CB - 1) / CB;
+    auto issue = [&](int g) {
+      if (g < ng) {
         V* dst = ring + (size_t)((g % GROUPS) * CB * NV) * 32;
 #pragma unroll
         for (int t = 0; t < CB; t += 4) {
-          const uint4 o4 = *reinterpret_cast<const uint4*>(sO + q * 32 + b + t);
+          const uint4 o4 = *reinterpret_cast<const uint4*>(sO + g * CB + t);
 #pragma unroll
           for (int tt = 0; tt < 4; ++tt) {
             const V* rp = Rl + (tt == 0 ? o4.x : tt == 1 ? o4.y : tt == 2 ? o4.z : o4.w);
@@ -259,45 +260,36 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
     };
 #pragma unroll
     for (int g = 0; g < GROUPS; ++g) issue(g);
+    float accq[SLOTS];
 #pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-      const int ncg = nc - q * 32;                // candidates of this slot (warp-uniform)
-      if (ncg <= 0) {                             // (keep the copy-group count in step: nothing is in flight any more)
-        continue;
-      }
-      float v[32];
+    for (int q = 0; q < SLOTS; ++q) accq[q] = 0.f;
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+      cp_async_wait<GROUPS - 1>();                // group g has landed (at most the GROUPS-1 younger ones are pending)
+      const V* src = ring + (size_t)((g % GROUPS) * CB * NV) * 32;
+      float v[CB];
 #pragma unroll
-      for (int b = 0; b < 32; b += CB) {
-        const int g = q * (32 / CB) + b / CB;
-        if (b >= ncg) {
+      for (int t = 0; t < CB; ++t) {
+        const float4 m = sM[g * CB + t];          // the candidate's category weights (broadcast read)
+        float part = 0.f;
 #pragma unroll
-          for (int t = 0; t < CB; ++t) v[b + t] = 0.f;
-          continue;
+        for (int k = 0; k < NV; ++k) {
+          const float4 r = (EXACT || lane + 32 * k < DV) ? ring_ld(src + (t * NV + k) * 32) : f4zero();
+          float4 z;
+          z.x = m.x * pr[1][k].x + m.y * pr[2][k].x + m.z * pr[3][k].x + m.w * pr[4][k].x;
+          z.y = m.x * pr[1][k].y + m.y * pr[2][k].y + m.z * pr[3][k].y + m.w * pr[4][k].y;
+          z.z = m.x * pr[1][k].z + m.y * pr[2][k].z + m.z * pr[3][k].z + m.w * pr[4][k].z;
+          z.w = m.x * pr[1][k].w + m.y * pr[2][k].w + m.z * pr[3][k].w + m.w * pr[4][k].w;
+          part += dot4(z, r);
         }
-        cp_async_wait<GROUPS - 1>();              // group g has landed (at most the GROUPS-1 younger ones are pending)
-        const V* src = ring + (size_t)((g % GROUPS) * CB * NV) * 32;
-#pragma unroll
-        for (int t = 0; t < CB; ++t) {
-          const float4 m = sM[q * 32 + b + t];    // the candidate's category weights (broadcast read)
-          float part = 0.f;
-#pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            const float4 r = (EXACT || lane + 32 * k < DV) ? ring_ld(src + (t * NV + k) * 32) : f4zero();
-            float4 z;
-            z.x = m.x * pr[1][k].x + m.y * pr[2][k].x + m.z * pr[3][k].x + m.w * pr[4][k].x;
-            z.y = m.x * pr[1][k].y + m.y * pr[2][k].y + m.z * pr[3][k].y + m.w * pr[4][k].y;
-            z.z = m.x * pr[1][k].z + m.y * pr[2][k].z + m.z * pr[3][k].z + m.w * pr[4][k].z;
-            z.w = m.x * pr[1][k].w + m.y * pr[2][k].w + m.z * pr[3][k].w + m.w * pr[4][k].w;
-            part += dot4(z, r);
-          }
-          v[b + t] = part;
-        }
-        issue(g + GROUPS);                        // reuse the slots just read
+        v[t] = part;
       }
-      // transposing butterfly: after the step with offset o, v[i] (i < o) holds the sum over 32/o lanes for the
-      // candidate whose index has this lane's bits >= o and low bits i; after offset 1, v[0] is candidate `lane`
+      issue(g + GROUPS);                          // reuse the slots just read
+      // transposing butterfly over the low three lane bits: after the step with offset o, v[i] (i < o) is the sum over
+      // 8/o lanes for the candidate whose index has this lane's bits (4, 2, 1 >= o) and low bits i; then the four
+      // 8-lane groups are added: every lane ends with the complete sum of candidate 8g + (lane & 7)
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
+      for (int off = CB / 2; off >= 1; off >>= 1) {
         const bool hi = (lane & off) != 0;
 #pragma unroll
         for (int i = 0; i < off; ++i) {
@@ -306,10 +298,20 @@ eval_sampled_kernel(const float4* __restrict__ P, const float4* __restrict__ R, 
           v[i] = keep + __shfl_xor_sync(FR_FULL, send, off);
         }
       }
+      float tot = v[0];
+      tot += __shfl_xor_sync(FR_FULL, tot, 8);
+      tot += __shfl_xor_sync(FR_FULL, tot, 16);
+      // candidate c lives in lane c & 31 of slot c >> 5: group g is lanes 8(g & 3) .. +7 of slot g >> 2
+#pragma unroll
+      for (int q = 0; q < SLOTS; ++q)
+        if ((g >> 2) == q && (lane >> 3) == (g & 3)) accq[q] = tot;
+    }
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
       const float4 m = mq[q];
       const float rn = __frcp_rn(((m.x + m.y) + m.z) + m.w);       // x * (1/n): exact for n = 1, 2, 4
       const float high = (((m.x * b0 + m.y * b1) + m.z * b2) + m.w * b3) * rn;   // :67-79
-      const float sq = a * high + oma * (v[0] * rn);                              // :82-96
+      const float sq = a * high + oma * (accq[q] * rn);                           // :82-96
       if (id[q] >= 0) { sc[q] = sq; if (scores_out) scores_out[(size_t)w * stride + q * 32 + lane] = sq; }
     }
     fetch_rows(w + nw);                           // the rows are dead: the next user's take their place while this one is ranked

@@ -235,6 +235,14 @@ class ShardedEngine:
         L.check(self.e.handle, self.e.lib.fr_shard_set_peers(self.e.handle, C.byref(sh), a, b))
         self.p2p = True
 
+    def serve_prepare(self):
+        """fr_shard_serve_prepare for the step planned last (its received requests must be in place): the owner-side
+        sort of the request list, which serve / apply of that step then find done.  Like plan(), it may be queued on
+        another stream while the previous step's update / apply are still running."""
+        e = self.e
+        slot = (self._n_plan - 1) & 1
+        L.check(e.handle, e.lib.fr_shard_serve_prepare(e.handle, C.byref(self._slots[slot][1]), _ptr(self._rreq[slot]), e._stream()))
+
     def serve(self):
         e = self.e
         rows = None if getattr(self, "p2p", False) else self.rows
@@ -411,6 +419,8 @@ class DistRunner:
                 next_batch()
                 req = g.plan()
                 d.all_to_all_single(g._rreq[(g._n_plan - 1) & 1], req)
+                if hasattr(g, "serve_prepare"):
+                    g.serve_prepare()                     # owner-side request sort: depends on the requests only
         elif next_batch is not None:
             next_batch()
             req = g.plan()
@@ -493,6 +503,7 @@ class LocalRunner:
             plan_ahead()
             for g in self.engs: g.plan()
             self._exchange_requests()
+            for g in self.engs: g.serve_prepare()
         for g in self.engs: g.update(write_personal)
         if not p2p: self._all_to_all("grows", "rgrows")
         self._outs = [g.apply() for g in self.engs]

@@ -234,6 +234,12 @@ int64_t fr_shard_route_block(const fr_batch* b, int32_t rcap);
 int fr_shard_route(fr_handle h, const fr_batch* b, int32_t world, int32_t rcap, int32_t* send, float* out_flag, fr_stream s);
 int fr_shard_unroute(fr_handle h, int32_t mode, int32_t world, int32_t rcap, const int32_t* recv, int32_t cap_out,
                      int32_t* users, int32_t* items, float* labels, int32_t* n_out, float* out_flag, fr_stream s);
+/* Optional, one step ahead: the owner-side ordering of the request list fr_shard_serve / fr_shard_apply walk (keys +
+ * stable sort by recipe) depends on the requests only, not on the tables, so it may be issued -- on another stream --
+ * right after the id all-to-all of the step fr_shard_plan planned last, while the previous step is still running
+ * (two sets of buffers, like the plan slots).  fr_shard_serve does it itself when this was not called. */
+int fr_shard_serve_prepare(fr_handle h, const fr_shard* sh, const int32_t* rreq, fr_stream s);
+
 /* Peer-memory exchange over NVLink instead of the two row all-to-alls: peer_rbuf[w] / peer_rgrows[w] are rank w's
  * receive buffers ([W*cap, D] each) mapped into this process (CUDA IPC; the caller's own buffers at index rank).
  * Afterwards fr_shard_serve(rows = NULL) stores every gathered recipe row straight into the requester's rbuf and
