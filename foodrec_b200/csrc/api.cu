@@ -132,7 +132,8 @@ extern "C" int fr_destroy(fr_handle h) {
   if (h->stage) cudaFree(h->stage);
   for (auto& sl : h->feed) { if (sl.buf) cudaFree(sl.buf); if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->aux_fork); cudaEventDestroy(h->aux_fork2); cudaEventDestroy(h->aux_join); }
+  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->aux_fork); cudaEventDestroy(h->aux_fork2); cudaEventDestroy(h->aux_join);
+                       cudaStreamDestroy(h->aux2_stream); cudaEventDestroy(h->aux2_fork); cudaEventDestroy(h->aux2_join); }
   if (h->pieces_personal) cudaFree(h->pieces_personal);
   delete h;
   return FR_OK;
@@ -439,6 +440,9 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     FR_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_fork2, 0));
     Launch la{h->sm_count, h->aux_stream, nullptr};
     rc = label_pass(la); if (rc) return rc;
+    // the `general` fetch = mean(G) (:219) only needs the pass above: off the main stream too
+    launch_mean((const float4*)T.G, (int64_t)h->mc.L * 5 * DV, h->mean_partials, out + FR_OUT_GENERAL,
+                (double)h->mc.L * 5.0 * h->mc.D, la);
   }
   FR_CUDA(h, cudaEventRecord(h->aux_join, h->aux_stream));
 
@@ -447,6 +451,7 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   SegCommon cu{};
   cu.keys = h->sortU.k[ru]; cu.perm = h->sortU.v[ru]; cu.n_dev = nullptr; cu.n_host = (uint32_t)S;
   cu.uniq_counter = h->counters + 0; cu.pieces = h->pieces_u;
+  const bool fin_aside = fused && !h->timing && !getenv("FOODREC_FINALIZE_SERIAL");
   if (fused) {
     // 2'. forward + loss + norms + dCat partials + z stash + segment reduce + Adam (clip scale speculated = 1), new rows
     //     into the other copy of the double-buffered Personal_Memory
@@ -460,7 +465,11 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
     fz.part_loss = h->part_loss; fz.part_nrm = h->part_nrm; fz.part_gcat = h->part_gcat;
     fz.mc = h->mc; fz.oc = oc;
     fgrid = user_fused_grid((uint32_t)S, h->sm_count);
+    // (the norm / loss / dCat partials are complete when the kernel ends; its crossing-run combine does not touch them:
+    //  finalize runs beside the combine on a second side stream -- the event is recorded between the two launches)
+    if (fin_aside) l.mid = h->aux2_fork;
     launch_user_fused(NV, group, cu, fz, fgrid, l);
+    l.mid = nullptr;
     FR_CHECK_LAUNCH(h);
     h->shadow_dirty = true;
   } else {
@@ -485,7 +494,15 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
   fin.DV = DV; fin.B = (float)B; fin.packed = h->packed; fin.do_reduce = 1; fin.do_apply = 1;
   fin.Cat = (float4*)T.Cat; fin.s1Cat = (float4*)T.s1_Cat; fin.s2Cat = (float4*)T.s2_Cat;
   fin.oc = oc; fin.clip = h->cfg.clip_norm; fin.out = out; fin.lr_hist = h->lr_hist;
-  launch_finalize(fin, l);
+  if (fin_aside) {
+    FR_CUDA(h, cudaStreamWaitEvent(h->aux2_stream, h->aux2_fork, 0));
+    Launch l2{h->sm_count, h->aux2_stream, nullptr};
+    launch_finalize(fin, l2);
+    FR_CUDA(h, cudaEventRecord(h->aux2_join, h->aux2_stream));
+    FR_CUDA(h, cudaStreamWaitEvent(st, h->aux2_join, 0));
+  } else {
+    launch_finalize(fin, l);
+  }
   FR_CHECK_LAUNCH(h);
 
   FR_MARK(FR_T_USER_CHUNK);
@@ -567,8 +584,9 @@ extern "C" int fr_train_step(fr_handle h, const fr_batch* b, int32_t write_perso
 
   FR_MARK(FR_T_MISC);
   // 8. fetches: general = mean(G) (:219), personal = mean(P) (:218, personal steps only)
-  launch_mean((const float4*)T.G, (int64_t)h->mc.L * 5 * DV, h->mean_partials, out + FR_OUT_GENERAL,
-              (double)h->mc.L * 5.0 * h->mc.D, l);
+  if (!label_aside)
+    launch_mean((const float4*)T.G, (int64_t)h->mc.L * 5 * DV, h->mean_partials, out + FR_OUT_GENERAL,
+                (double)h->mc.L * 5.0 * h->mc.D, l);
   if (write_personal) {
     if (lazy) {
       // mean(P) must see every row at step t

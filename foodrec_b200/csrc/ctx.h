@@ -98,6 +98,7 @@ struct fr_ctx {
   // fork / join inside fr_train_step: the label feed's entry list (count, scan, emit, sort by label) depends only on the
   // batch and is built on this stream while the sorts, catch-up and the forward run on the caller's
   cudaStream_t aux_stream = nullptr; cudaEvent_t aux_fork = nullptr, aux_fork2 = nullptr, aux_join = nullptr;
+  cudaStream_t aux2_stream = nullptr; cudaEvent_t aux2_fork = nullptr, aux2_join = nullptr;      // finalize beside the fused kernel's combine
   int feed_next = 0;
   // per-phase timing (fr_timing_*)
   bool timing = false;
@@ -152,6 +153,9 @@ static inline int aux_ensure(fr_ctx* h) {
   FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming));
   FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_fork2, cudaEventDisableTiming));
   FR_CUDA(h, cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming));
+  FR_CUDA(h, cudaStreamCreateWithPriority(&h->aux2_stream, cudaStreamNonBlocking, hi));
+  FR_CUDA(h, cudaEventCreateWithFlags(&h->aux2_fork, cudaEventDisableTiming));
+  FR_CUDA(h, cudaEventCreateWithFlags(&h->aux2_join, cudaEventDisableTiming));
   return FR_OK;
 }
 
@@ -169,6 +173,8 @@ static inline int alloc_sort(fr_ctx* h, SortBufs& s, size_t cap) {
   }
   const size_t ntiles = (cap + SORT_TILE - 1) / SORT_TILE;
   int rc = dalloc(h, &s.tile_hist, RADIX_BINS * ntiles + 1); if (rc) return rc;
+  if ((rc = dalloc(h, &s.ticket, 1))) return rc;
+  FR_CUDA(h, cudaMemset(s.ticket, 0, sizeof(uint32_t)));
   return dalloc(h, &s.scan_tmp, (RADIX_BINS * ntiles) / 4096 + 2);
 }
 

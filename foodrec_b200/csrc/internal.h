@@ -15,6 +15,7 @@ struct SortBufs {
   uint32_t* v[2] = {nullptr, nullptr};
   uint32_t* tile_hist = nullptr;   // [RADIX_BINS * ntiles]
   uint32_t* scan_tmp = nullptr;    // block sums for the multi-block scan
+  uint32_t* ticket = nullptr;      // [1], zero between launches: "last block done" counter of the one-launch offset scan
   int cap = 0;
 };
 

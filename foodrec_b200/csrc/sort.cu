@@ -27,6 +27,7 @@ __device__ __forceinline__ uint32_t resolve_n(const uint32_t* n_dev, uint32_t n_
 
 constexpr int MAX_DIGIT_BITS = 10;
 constexpr int MAX_BINS = 1 << MAX_DIGIT_BITS;
+constexpr int SCAN_TILE_C = 4096;          // = SCAN_TILE below (entries of the offset table one scan block covers)
 constexpr int FUSED_SCAN_MAX_TILES = 16;   // every block re-reads bins x tiles counters: measured 0.30 ms per step at 128 tiles vs 0.145 ms with the separate scan at 256
 
 struct PassJob {
@@ -35,6 +36,7 @@ struct PassJob {
   uint32_t n_host; const uint32_t* n_dev;
   int shift, bits;                                     // bits == 0: job idle in this pass
   uint32_t ntiles; uint32_t* tile_hist; int fused;
+  const uint32_t* blk_pref;                            // separate scan: exclusive prefix of the scan blocks (see scan_offsets_kernel)
 };
 struct PassJobs { PassJob j[2]; };
 
@@ -131,7 +133,10 @@ radix_scatter_kernel(const PassJobs jobs) {
         for (int q = 0; q < BPT; ++q) { run[q] = acc + pre[q]; acc += tot[q]; }
       } else {
 #pragma unroll
-        for (int q = 0; q < BPT; ++q) run[q] = (b0 + q < bins) ? J.tile_hist[(size_t)(b0 + q) * J.ntiles + tile] : 0u;
+        for (int q = 0; q < BPT; ++q) {
+          const size_t e = (size_t)(b0 + q) * J.ntiles + tile;      // block-local scan + the prefix of its scan block
+          run[q] = (b0 + q < bins) ? J.tile_hist[e] + J.blk_pref[e / SCAN_TILE_C] : 0u;
+        }
       }
 #pragma unroll
       for (int q = 0; q < BPT; ++q) {
@@ -268,46 +273,52 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t*
   g_launches += 3;
 }
 
-// Two independent scans sharing their three launches (the two sort jobs of a step: blockIdx.y picks the job).
-struct Scan2 { const uint32_t* in[2]; uint32_t* out[2]; uint32_t n[2]; uint32_t* tmp[2]; };
+// The offset scan of a radix pass in ONE launch, for up to two jobs (blockIdx.y).  Every block scans its SCAN_TILE
+// entries of the bin-major [bins x ntiles] histogram in place and leaves its total; the block that finishes LAST (a
+// ticket counter) turns the totals into exclusive prefixes.  The table is NOT rewritten with the prefixes added: the
+// scatter kernel adds blk_pref[entry / SCAN_TILE] when it reads an entry.  (Three launches before -- tile sums, a
+// one-block scan of them, apply -- on the critical path of every pass.)
+static_assert(SCAN_TILE == SCAN_TILE_C, "scatter kernel's block size of the offset scan");
+struct Scan2 { uint32_t* data[2]; uint32_t n[2]; uint32_t* tmp[2]; uint32_t* ticket[2]; };
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan2_tile_sums_kernel(const Scan2 s) {
+scan_offsets_kernel(const Scan2 s) {
+  __shared__ bool last;
   const int j = blockIdx.y;
-  if (blockIdx.x * SCAN_TILE >= s.n[j]) return;
-  uint32_t v[SCAN_ITEMS];
-  scan_load(s.in[j], blockIdx.x * SCAN_TILE, s.n[j], v);
-  const uint32_t tot = block_scan_tile(v, 0);
-  if (threadIdx.x == 0) s.tmp[j][blockIdx.x] = tot;
-}
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan2_single_kernel(const Scan2 s) {
-  const int j = blockIdx.y;
-  const uint32_t n = (s.n[j] + SCAN_TILE - 1) / SCAN_TILE;
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < n; base += SCAN_TILE) {
+  const uint32_t n = s.n[j], nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (blockIdx.x >= nb) return;
+  {
     uint32_t v[SCAN_ITEMS];
-    scan_load(s.tmp[j], base, n, v);
+    scan_load(s.data[j], blockIdx.x * SCAN_TILE, n, v);
+    const uint32_t tot = block_scan_tile(v, 0);
+    scan_store(s.data[j], blockIdx.x * SCAN_TILE, n, v);
+    if (threadIdx.x == 0) {
+      s.tmp[j][blockIdx.x] = tot;
+      __threadfence();
+      last = atomicAdd(s.ticket[j], 1u) == nb - 1;
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nb; base += SCAN_TILE) {
+    uint32_t v[SCAN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      const uint32_t idx = base + threadIdx.x * SCAN_ITEMS + i;
+      v[i] = idx < nb ? __ldcg(s.tmp[j] + idx) : 0u;
+    }
     const uint32_t tot = block_scan_tile(v, carry);
-    scan_store(s.tmp[j], base, n, v);
+    scan_store(s.tmp[j], base, nb, v);
     carry += tot;
   }
+  if (threadIdx.x == 0) *s.ticket[j] = 0u;         // ready for the next launch
 }
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan2_apply_kernel(const Scan2 s) {
-  const int j = blockIdx.y;
-  if (blockIdx.x * SCAN_TILE >= s.n[j]) return;
-  uint32_t v[SCAN_ITEMS];
-  scan_load(s.in[j], blockIdx.x * SCAN_TILE, s.n[j], v);
-  block_scan_tile(v, s.tmp[j][blockIdx.x]);
-  scan_store(s.out[j], blockIdx.x * SCAN_TILE, s.n[j], v);
-}
-static void exclusive_scan2_u32(const Scan2& s, cudaStream_t st) {
+static void scan_offsets(const Scan2& s, int njobs, cudaStream_t st) {
   const uint32_t nmax = s.n[0] > s.n[1] ? s.n[0] : s.n[1];
   const uint32_t nb = (nmax + SCAN_TILE - 1) / SCAN_TILE;
-  scan2_tile_sums_kernel<<<dim3(nb, 2), SCAN_THREADS, 0, st>>>(s);
-  scan2_single_kernel<<<dim3(1, 2), SCAN_THREADS, 0, st>>>(s);
-  scan2_apply_kernel<<<dim3(nb, 2), SCAN_THREADS, 0, st>>>(s);
-  g_launches += 3;
+  scan_offsets_kernel<<<dim3(nb, njobs), SCAN_THREADS, 0, st>>>(s);
+  g_launches += 1;
 }
 
 // ---------------------------------------------------------------- host side
@@ -352,20 +363,16 @@ void radix_sort_jobs(SortJob* jobs, int njobs, cudaStream_t st, int sm_count) {
     }
     radix_hist_kernel<<<dim3(gx, njobs), FR_THREADS, 0, st>>>(pj);
     ++g_launches;
-    const bool need0 = pj.j[0].bits && !pj.j[0].fused, need1 = njobs > 1 && pj.j[1].bits && !pj.j[1].fused;
-    if (need0 && need1) {      // both jobs: one set of launches
-      Scan2 sc{};
-      for (int i = 0; i < 2; ++i) {
-        sc.in[i] = pj.j[i].tile_hist; sc.out[i] = pj.j[i].tile_hist;
-        sc.n[i] = (uint32_t)(1u << pj.j[i].bits) * pj.j[i].ntiles; sc.tmp[i] = jobs[i].bufs->scan_tmp;
-      }
-      exclusive_scan2_u32(sc, st);
-    } else {
-      for (int i = 0; i < njobs; ++i)
-        if (pj.j[i].bits && !pj.j[i].fused)
-          exclusive_scan_u32(pj.j[i].tile_hist, pj.j[i].tile_hist, (uint32_t)(1u << pj.j[i].bits) * pj.j[i].ntiles,
-                             jobs[i].bufs->scan_tmp, nullptr, st);
+    Scan2 sc{};
+    bool any_scan = false;
+    for (int i = 0; i < njobs; ++i) {
+      if (!pj.j[i].bits || pj.j[i].fused) continue;        // (n = 0: the job's blocks exit at once)
+      sc.data[i] = pj.j[i].tile_hist; sc.n[i] = (uint32_t)(1u << pj.j[i].bits) * pj.j[i].ntiles;
+      sc.tmp[i] = jobs[i].bufs->scan_tmp; sc.ticket[i] = jobs[i].bufs->ticket;
+      pj.j[i].blk_pref = jobs[i].bufs->scan_tmp;
+      any_scan = true;
     }
+    if (any_scan) scan_offsets(sc, njobs, st);
     radix_scatter_kernel<<<dim3(gx, njobs), FR_THREADS, 0, st>>>(pj);
     ++g_launches;
     for (int i = 0; i < njobs; ++i) {
