@@ -425,6 +425,8 @@ class DistRunner:
             next_batch()
             req = g.plan()
             d.all_to_all_single(g._rreq[(g._n_plan - 1) & 1], req)
+            if hasattr(g, "serve_prepare"):
+                g.serve_prepare()
         return out
 
 

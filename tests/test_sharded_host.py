@@ -66,6 +66,12 @@ WIRING = textwrap.dedent("""
             slot = s._n_plan & 1; s.batches[slot] = s.batch
             s._req[slot].copy_(torch.tensor([1000 * s.batch + 100 * r + 10 * o + j for o in range(W) for j in range(cap)], dtype=torch.int32))
             s._n_plan += 1; log.append("plan%d" % s.batch); return s._req[slot]
+        def serve_prepare(s):                     # one step ahead: the requests of the step planned LAST are already here
+            k = s.batches[(s._n_plan - 1) & 1]
+            v = s._rreq[(s._n_plan - 1) & 1].view(W, cap)
+            for src in range(W):
+                assert v[src].tolist() == [1000 * k + 100 * src + 10 * r + j for j in range(cap)], v
+            log.append("prep%d" % k)
         def serve(s):                             # I am the owner: every request must be addressed to me, for THIS step's batch
             k = s.batches[s._n_apply & 1]
             v = s.rreq.view(W, cap)
@@ -91,8 +97,8 @@ WIRING = textwrap.dedent("""
     # pipelined: the NEXT step's plan + request exchange are issued once this step is queued, before the next serve
     del log[:]; batch(1)()
     assert run.step(next_batch=batch(2)) == "done" and run.step(next_batch=batch(3)) == "done" and run.step() == "done"
-    assert log == ["plan1", "serve1", "forward1", "update1", "apply1", "plan2", "serve2", "forward2", "update2", "apply2", "plan3",
-                   "serve3", "forward3", "update3", "apply3"], log
+    assert log == ["plan1", "serve1", "forward1", "update1", "apply1", "plan2", "prep2", "serve2", "forward2", "update2", "apply2",
+                   "plan3", "prep3", "serve3", "forward3", "update3", "apply3"], log
     sys.stdout.write("WIRING_OK_%d\\n" % r); sys.stdout.flush()
 """)
 
