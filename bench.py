@@ -891,6 +891,24 @@ def run_sharded(args, cfg, B):
         cfg3_line.pop("window")
         e3.e.close(); del e3, r3
         torch.cuda.empty_cache()
+    # ---- BASELINE configs[4] at SURVEY 8(d)'s sizes (cfg3's: 100M users / 10M recipes), N = 8: 1:8 sampled negatives,
+    # Adagrad, bf16 tables -- 16 GB of Personal_Memory + 32 GB of fp32 accumulators per GPU
+    # (FOODREC_CFG5_BIG_USERS / _RECIPES: totals for a dry run of this leg at another N)
+    cfg5_big = None
+    big_u = int(os.environ.get("FOODREC_CFG5_BIG_USERS", CFG3["U"] if world == 8 else 0))
+    big_i = int(os.environ.get("FOODREC_CFG5_BIG_RECIPES", CFG3["I"]))
+    if big_u and not args.small and not args.cfg3 and not args.no_cfg3 and not args.no_cfg5:
+        try:
+            c5b = dict(U=local_rows(big_u, world), I=local_rows(big_i, world), L=Lb, D=D)
+            cfg5_big, e5, r5 = sharded_train_leg(args, c5b, B, rank, world, dev, p2p, min(args.steps, 20), 8, 3,
+                                                 f"cfg5 at cfg3's sizes: {big_u} users / {big_i} recipes over {world} GPUs, 1:8 sampled "
+                                                 "negatives, Adagrad, bf16 tables", single_pass=False, learner="adagrad",
+                                                 table_dtype="bf16", n_neg=8, extras=False)
+            cfg5_big.pop("window")
+            e5.e.close(); del e5, r5
+            torch.cuda.empty_cache()
+        except Exception as ex:          # (every rank runs the same leg on the same shapes: a failure is one on all ranks)
+            cfg5_big = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     if rank == 0:
         line = {
             "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -909,7 +927,7 @@ def run_sharded(args, cfg, B):
             "update_phase_kernels_ms": main["update_phase_kernels_ms"], "self_check": check,
             "e2e": main["e2e"], "e2e_compact": main["e2e_compact"], "unrouted": main["unrouted"],
             "uniq_users_per_step": main["uniq_users_per_step"], "uniq_items_per_step": main["uniq_items_per_step"],
-            "overflow_flag": main["overflow_flag"], "cfg3": cfg3_line, "cfg5": cfg5_line}
+            "overflow_flag": main["overflow_flag"], "cfg3": cfg3_line, "cfg5": cfg5_line, "cfg5_cfg3_sizes": cfg5_big}
         print(json.dumps(line, default=float))
     dist.destroy_process_group()
 
