@@ -1,6 +1,8 @@
 """CPU: the bf16-table rule the oracle defines (BASELINE configs[4]) -- round_bf16 is IEEE round-to-nearest-even to
 bfloat16 (checked against torch's conversion), OracleModel(table_dtype="bf16") keeps Personal_Memory / Recipe_Embedding
 representable after every step, rounds only the touched rows, and refuses what the rule does not define."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -51,3 +53,30 @@ def test_oracle_bf16_refuses_adam_and_personal_writes():
     om = OracleModel(p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, Hyper(learner="sgd"), table_dtype="bf16")
     with pytest.raises(ValueError):
         om.train_step(p.pointwise(20, seed=2), write_personal=True)
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def replay_golden(g, step_fn):
+    """feeds of tests/golden/bf16_tables_*.npz (2 BPR steps, 2 pointwise) -> step_fn(s, feed, bpr)"""
+    for s in range(4):
+        f = {k[len(f"s{s}_"):]: g[k] for k in g.files if k.startswith(f"s{s}_") and k not in (f"s{s}_loss", f"s{s}_norm")}
+        step_fn(s, f, s < 2)
+
+
+@pytest.mark.parametrize("learner", ["adagrad", "rmsprop", "sgd"])
+def test_oracle_reproduces_the_committed_bf16_vectors(learner):
+    """tests/golden/make_bf16_golden.py: the rule is OURS (no reference path), the fixture freezes it."""
+    g = np.load(os.path.join(GOLD, f"bf16_tables_{learner}.npz"))
+    om = OracleModel(g["P0"], g["R0"], g["Cat0"], g["G0"], Hyper(learner=learner, lr=float(g["lr"])), dtype=np.float32,
+                     table_dtype="bf16")
+
+    def step(s, f, bpr):
+        o = om.train_step_bpr(f) if bpr else om.train_step(f)
+        assert o["loss"] == pytest.approx(float(g[f"s{s}_loss"]), rel=1e-6) and o["norm"] == pytest.approx(float(g[f"s{s}_norm"]), rel=1e-6)
+    replay_golden(g, step)
+    for k in ("P", "R"):
+        got = (np.ascontiguousarray(getattr(om, k), np.float32).view(np.uint32) >> 16).astype(np.uint16)
+        assert np.array_equal(got, g[k + "_bits"]), k
+    np.testing.assert_allclose(om.Cat, g["Cat"], rtol=1e-6); np.testing.assert_allclose(om.G, g["G"], rtol=1e-6, atol=1e-9)

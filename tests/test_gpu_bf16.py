@@ -4,6 +4,8 @@ arithmetic, round-to-nearest-even on store, fp32 optimizer slots -- the rule ora
 against that definition).  A stored value is an 8-bit-mantissa rounding of an fp32 result: the CUDA path and the float32
 oracle must agree BIT FOR BIT except where their fp32 results (different summation order) straddle a rounding boundary --
 then by exactly one bf16 ulp."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -170,4 +172,30 @@ def test_bf16_tables_refuse_what_is_not_defined():
         e.train_step(f["user_input"], f["item_input"], labels=f["labels"], write_personal=True)
     with pytest.raises(L.FoodRecError, match="bf16"):
         e.catalog_topk(K=5)
+    e.close()
+
+
+@pytest.mark.parametrize("learner", ["adagrad", "rmsprop", "sgd"])
+def test_cuda_path_against_the_committed_bf16_vectors(learner):
+    """tests/golden/bf16_tables_*.npz (made by the float32 oracle, tests/golden/make_bf16_golden.py): the stored bit
+    patterns of P / R after 4 steps -- identical for >= 99.9 % of the entries, one bf16 ulp otherwise."""
+    from foodrec_b200 import Engine, Hyper
+    from tests.test_bf16_oracle import GOLD, replay_golden
+    g = np.load(os.path.join(GOLD, f"bf16_tables_{learner}.npz"))
+    e = Engine(Hyper(learner=learner, lr=float(g["lr"])), g["P0"], g["R0"], g["Cat0"], g["G0"], max_rows=256,
+               max_label_entries=256 * int(g["dims"][2]), table_dtype="bf16")
+
+    def step(s, f, bpr):
+        kw = dict(neg_items=f["neg_item_input"], neg_categories=f["neg_categories"]) if bpr else {}
+        e.train_step(f["user_input"], f["item_input"], labels=None if bpr else f["labels"], categories=f["categories"],
+                     write_sign=None if bpr else f["write_sign"], user_one_hot_label=f["user_one_hot_label"], **kw)
+        v = e.read_scalars()
+        assert v[0] == pytest.approx(float(g[f"s{s}_loss"]), rel=1e-5) and v[1] == pytest.approx(float(g[f"s{s}_norm"]), rel=1e-5)
+    replay_golden(g, step)
+    t = e.tables()
+    for k in ("P", "R"):
+        got = (np.ascontiguousarray(t[k], np.float32).view(np.uint32) >> 16).astype(np.int64)
+        d = np.abs(got - g[k + "_bits"].astype(np.int64))
+        assert d.max() <= 1 and (d == 0).mean() >= 0.999, (k, int(d.max()), float((d == 0).mean()))
+    assert_close(t["Cat"], g["Cat"], rtol=2e-5, what="Cat"); assert_close(t["G"], g["G"], rtol=2e-5, what="G")
     e.close()
