@@ -199,3 +199,25 @@ def test_cuda_path_against_the_committed_bf16_vectors(learner):
         assert d.max() <= 1 and (d == 0).mean() >= 0.999, (k, int(d.max()), float((d == 0).mean()))
     assert_close(t["Cat"], g["Cat"], rtol=2e-5, what="Cat"); assert_close(t["G"], g["G"], rtol=2e-5, what="G")
     e.close()
+
+
+def test_bf16_checkpoint_round_trip_continues_bit_for_bit():
+    """state_dict() widens P / R to float32 (exactly), load_state_dict() stores them back as the same bf16 values with
+    the fp32 accumulators: a restored engine continues exactly like the uninterrupted one."""
+    from foodrec_b200 import Engine, Hyper
+    p = Problem(300, 200, 7, 64, seed=29)
+    mk = lambda: Engine(Hyper(learner="adagrad", lr=0.05), p.tb.P, p.tb.R, p.tb.Cat, p.tb.G, max_rows=1024, item_cats=p.item_cats,
+                        user_labels=p.user_labels, table_dtype="bf16")
+    a, b = mk(), mk()
+    fs = [p.bpr(200, seed=60 + s) for s in range(3)]
+    run = lambda e, f: e.train_step(f["user_input"], f["item_input"], neg_items=f["neg_item_input"])
+    for f in fs[:2]:
+        run(a, f)
+    sd = a.state_dict()
+    assert sd["P"].dtype == np.float32 and np.array_equal(round_bf16(sd["P"]), sd["P"])
+    b.load_state_dict(sd)
+    run(a, fs[2]); run(b, fs[2])
+    ta, tb = a.tables(), b.tables()
+    for k in ta:
+        np.testing.assert_array_equal(ta[k], tb[k], err_msg=k)
+    a.close(); b.close()
