@@ -1,6 +1,7 @@
 #!/bin/bash
 # round-2 ncu captures of bench.py's own command (run on the GPU box AFTER the plain bench exited 0):
 #   launch list (gpu__time_duration.sum) + one --set full capture of each train kernel at steady state + the eval kernel
+#   (+ the catalog GEMM unless SKIP_CATALOG=1); summaries: profiles/summarize.py full | traffic
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 TAG=${1:-r02}
 python bench.py --no-cpu --no-catalog --no-cfg5 --steps 10 --warmup 5 > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || exit 1
